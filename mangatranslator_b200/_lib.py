@@ -1,0 +1,75 @@
+"""ctypes binding of libmtb200.so (the C ABI declared in include/mtb200.h).
+
+The product path has no fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("MTB200_LIB", _HERE / "lib" / "libmtb200.so"))
+
+
+class MtbError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad",
+        "planes_in", "planes_out", "act", "res_planes", "tile_w", "tile_h")]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise MtbError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        _lib = C.CDLL(str(LIB_PATH))
+        _declare(_lib)
+    return _lib
+
+
+def _declare(l: C.CDLL) -> None:
+    vp, i32, f32p = C.c_void_p, C.c_int, C.c_void_p
+    l.mtb_last_error.restype = C.c_char_p
+    l.mtb_version.restype = C.c_int
+    l.mtb_launch_count.restype = C.c_longlong
+    l.mtb_conv_plan_create.argtypes = [C.POINTER(ConvDesc), vp, vp, f32p, vp, vp, f32p, C.POINTER(vp)]
+    l.mtb_conv_plan_create.restype = i32
+    l.mtb_conv_plan_run.argtypes = [vp, vp]
+    l.mtb_conv_plan_run.restype = i32
+    l.mtb_conv_plan_num_mtiles.argtypes = [vp]
+    l.mtb_conv_plan_num_mtiles.restype = i32
+    l.mtb_conv_plan_destroy.argtypes = [vp]
+    l.mtb_conv_plan_destroy.restype = None
+    if hasattr(l, "mtb_exp_shifted_desc"):
+        l.mtb_exp_shifted_desc.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+        l.mtb_exp_shifted_desc.restype = i32
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().mtb_last_error().decode("utf-8", "replace")
+        raise MtbError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().mtb_launch_count())

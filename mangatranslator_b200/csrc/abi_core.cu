@@ -1,0 +1,210 @@
+// C-ABI: library plumbing + conv plan entry points (include/mtb200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <new>
+
+#include "../../include/mtb200.h"
+#include "common.cuh"
+#include "conv_gemm.cuh"
+
+namespace mtb {
+
+static thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  MTB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = elem_strides ? elem_strides[i] : 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MTB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu]",
+              static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0));
+  return 0;
+}
+
+}  // namespace mtb
+
+using namespace mtb;
+
+struct mtb_conv_plan {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  ConvParams p;
+  int nsplit;
+};
+
+extern "C" {
+
+const char* mtb_last_error(void) { return mtb::last_error(); }
+int mtb_version(void) { return 100; }
+long long mtb_launch_count(void) { return mtb::g_launches.load(); }
+
+int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, const float* bias, void* out,
+                         const void* residual, float* tile_sums, mtb_conv_plan** plan_out) {
+  MTB_REQUIRE(d && x && w && out && plan_out, "mtb_conv_plan_create: null argument");
+  MTB_REQUIRE(d->Cin % 64 == 0 && d->Cin > 0, "conv: Cin (%d) must be padded to a multiple of 64", d->Cin);
+  MTB_REQUIRE(d->Cout % 16 == 0 && d->Cout > 0, "conv: Cout (%d) must be padded to a multiple of 16", d->Cout);
+  MTB_REQUIRE(d->planes_in == 1 || d->planes_in == 2, "conv: planes_in must be 1 or 2");
+  MTB_REQUIRE(d->planes_out == 1 || d->planes_out == 2 || d->planes_out == 4, "conv: planes_out must be 1, 2 or 4");
+  MTB_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
+  MTB_REQUIRE(d->res_planes >= 0 && d->res_planes <= 2, "conv: res_planes must be 0..2");
+  MTB_REQUIRE((d->res_planes == 0) == (residual == nullptr), "conv: residual pointer / res_planes mismatch");
+  MTB_REQUIRE(!(d->planes_out == 4 && residual), "conv: fp32 output with residual is not supported");
+
+  mtb_conv_plan* pl = new (std::nothrow) mtb_conv_plan();
+  MTB_REQUIRE(pl != nullptr, "conv: out of host memory");
+  ConvParams& p = pl->p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N;
+  p.H = d->H;
+  p.W = d->W;
+  p.KH = d->KH;
+  p.KW = d->KW;
+  p.pad = d->pad;
+  p.stride = d->stride;
+  p.Ho = (d->H + 2 * d->pad - d->KH) / d->stride + 1;
+  p.Wo = (d->W + 2 * d->pad - d->KW) / d->stride + 1;
+  p.cin_chunks = d->Cin / 64;
+  p.Cout = d->Cout;
+  // channel tile: largest multiple-of-16 divisor of Cout that is <= 256
+  int bn = 0;
+  for (int c = 256; c >= 16; c -= 16)
+    if (d->Cout % c == 0) {
+      bn = c;
+      break;
+    }
+  p.BN = bn;
+  p.n_tiles_n = d->Cout / bn;
+  if (d->tile_w > 0 && d->tile_h > 0) {
+    p.TW = d->tile_w;
+    p.TH = d->tile_h;
+  } else if (p.Ho == 1) {
+    p.TW = 128;
+    p.TH = 1;
+  } else if (p.Wo <= 8) {
+    p.TW = 8;
+    p.TH = 16;
+  } else {
+    p.TW = 16;
+    p.TH = 8;
+  }
+  if (p.TW * p.TH != 128) {
+    const int tw = p.TW, th = p.TH;
+    delete pl;
+    MTB_REQUIRE(false, "conv: tile %dx%d must hold 128 pixels", tw, th);
+  }
+  p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
+  p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
+  p.planes_out = d->planes_out == 4 ? 1 : d->planes_out;
+  p.act = d->act;
+  p.out_plane_stride = static_cast<long long>(p.N) * p.Ho * p.Wo * p.Cout;
+  p.res_plane_stride = p.out_plane_stride;
+  p.res_planes = d->res_planes;
+  p.bias = bias;
+  if (d->planes_out == 4) {
+    p.out = nullptr;
+    p.out_f32 = static_cast<float*>(out);
+  } else {
+    p.out = static_cast<uint16_t*>(out);
+    p.out_f32 = nullptr;
+  }
+  p.residual = static_cast<const uint16_t*>(residual);
+  p.tile_sums = tile_sums;
+  pl->nsplit = d->planes_in == 2 ? 3 : 1;
+  int cols = 32;
+  while (cols < 2 * p.BN) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t stage = static_cast<size_t>(d->planes_in) * (128 * 128 + p.BN * 128);
+  int stages = static_cast<int>((200 * 1024) / stage);
+  if (stages > 8) stages = 8;
+  p.num_stages = stages;
+  if (stages < 2) {
+    delete pl;
+    MTB_REQUIRE(false, "conv: stage of %zu bytes leaves < 2 pipeline stages", stage);
+  }
+
+  // activations: [planes*N][H][W][Cin] bf16
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+                              static_cast<uint64_t>(d->N) * d->planes_in};
+    const uint64_t strides[3] = {static_cast<uint64_t>(d->Cin) * 2, static_cast<uint64_t>(d->W) * d->Cin * 2,
+                                 static_cast<uint64_t>(d->H) * d->W * d->Cin * 2};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(p.TW * d->stride), static_cast<uint32_t>(p.TH * d->stride), 1};
+    const uint32_t es[4] = {1, static_cast<uint32_t>(d->stride), static_cast<uint32_t>(d->stride), 1};
+    if (encode_tmap(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, es,
+                    CU_TENSOR_MAP_SWIZZLE_128B) != 0) {
+      delete pl;
+      return -3;
+    }
+  }
+  // weights: [planes*taps*Cout][Cin] bf16
+  {
+    const uint64_t rows = static_cast<uint64_t>(d->planes_in) * d->KH * d->KW * d->Cout;
+    const uint64_t dims[2] = {static_cast<uint64_t>(d->Cin), rows};
+    const uint64_t strides[1] = {static_cast<uint64_t>(d->Cin) * 2};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(p.BN)};
+    if (encode_tmap(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, strides, box, nullptr,
+                    CU_TENSOR_MAP_SWIZZLE_128B) != 0) {
+      delete pl;
+      return -3;
+    }
+  }
+  *plan_out = pl;
+  return 0;
+}
+
+int mtb_conv_plan_run(mtb_conv_plan* plan, void* stream) {
+  MTB_REQUIRE(plan != nullptr, "mtb_conv_plan_run: null plan");
+  int rc = launch_conv_gemm(plan->tmA, plan->tmB, plan->p, plan->nsplit, static_cast<cudaStream_t>(stream));
+  if (rc == 0) mtb::g_launches.fetch_add(1);
+  return rc;
+}
+
+int mtb_conv_plan_num_mtiles(const mtb_conv_plan* plan) {
+  return plan ? plan->p.N * plan->p.tiles_y * plan->p.tiles_x : 0;
+}
+
+void mtb_conv_plan_destroy(mtb_conv_plan* plan) { delete plan; }
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+// Implicit-GEMM convolution / linear layer on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// One kernel serves every GEMM-shaped contraction of the hot path:
+//   * YOLO Conv+SiLU blocks (3x3 / 1x1)                      (reference: core/image/detection.py:1338-1345 -> ultralytics)
+//   * RCAN residual-channel-attention conv stack (3x3)       (reference: core/image/image_utils.py:369-374 -> spandrel RCAN)
+//   * SAM 2.1 linears / 1x1 convs (as 1x1 "convs" over tokens) (reference: core/image/detection.py:475-511 -> transformers Sam2Model)
+//
+// Layout: activations are NHWC bf16 "planes".  A value that must keep fp32-grade accuracy is carried as two
+// planes (hi = bf16_rn(v), lo = bf16_rn(v - hi)); the contraction then issues three bf16 MMAs
+// (Ahi*Bhi + Ahi*Blo + Alo*Bhi) into one fp32 TMEM accumulator ("bf16x3", ~2^-16 relative error).
+// With one plane it is a plain bf16 GEMM.
+//
+// CTA = 192 threads, persistent over output tiles:
+//   warp 0     : TMA producer   (one lane)  global -> 128B-swizzled shared tiles, per (tap, 64-channel chunk)
+//   warp 1     : MMA issuer     (one lane)  tcgen05.mma kind::f16, M=128 pixels x N=BN channels, K=16 per instr
+//   warps 2..5 : epilogue       tcgen05.ld TMEM -> regs -> bias/activation/residual -> bf16 planes (or fp32) -> HBM
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#pragma once
+#include "common.cuh"
+
+namespace mtb {
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_GELU = 3, ACT_SIGMOID = 4 };
+
+struct ConvParams {
+  int N, H, W, Ho, Wo;
+  int KH, KW, pad, stride;
+  int cin_chunks;   // padded Cin / 64
+  int Cout;         // padded Cout (multiple of 16)
+  int BN;           // channel tile (N of the MMA), multiple of 16, <= 256
+  int n_tiles_n;    // Cout / BN
+  int TW, TH;       // pixel tile: TW * TH == 128
+  int tiles_x, tiles_y;
+  int planes_out;   // 1 (bf16), 2 (bf16 hi/lo); ignored when out_f32 != nullptr
+  int act;
+  int num_stages;
+  int tmem_cols;    // power of two >= 2*BN
+  long long out_plane_stride;  // elements between the hi and lo planes of `out`
+  long long res_plane_stride;  // elements between the hi and lo planes of `residual`
+  int res_planes;              // 0, 1 or 2
+  const float* bias;           // [Cout] or nullptr
+  uint16_t* out;               // bf16 planes [planes_out][N][Ho][Wo][Cout]
+  float* out_f32;              // optional fp32 output [N][Ho][Wo][Cout]
+  const uint16_t* residual;    // optional, same geometry as out, added after the activation
+  float* tile_sums;            // optional [N*tiles_y*tiles_x][4][Cout] per-warp channel sums of the output
+};
+
+int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int nsplit,
+                     cudaStream_t stream);
+size_t conv_gemm_smem_bytes(const ConvParams& p, int nsplit);
+
+}  // namespace mtb

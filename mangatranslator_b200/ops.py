@@ -1,0 +1,55 @@
+"""Thin Python wrappers over the C-ABI plan objects (device pointers + stream in, nothing computed here)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check, lib, ptr, stream_ptr
+
+ACT = {None: 0, "none": 0, "relu": 1, "silu": 2, "gelu": 3, "sigmoid": 4}
+
+
+class ConvPlan:
+    """One tcgen05 implicit-GEMM conv / linear layer bound to fixed device buffers.
+
+    x: bf16 [planes_in][N][H][W][Cin]; w: bf16 [planes_in][KH*KW][Cout][Cin]; out: bf16 [planes_out][N][Ho][Wo][Cout]
+    (or fp32 [N][Ho][Wo][Cout] when ``out`` is float32).
+    """
+
+    def __init__(self, x, w, bias, out, *, k=1, stride=1, pad=0, act=None, residual=None, tile_sums=None,
+                 tile=None):
+        planes_in, n, h, wd, cin = x.shape
+        assert w.shape[0] == planes_in and w.shape[1] == k * k and w.shape[3] == cin, (w.shape, x.shape)
+        cout = w.shape[2]
+        d = ConvDesc()
+        d.N, d.H, d.W, d.Cin, d.Cout = n, h, wd, cin, cout
+        d.KH = d.KW = k
+        d.stride, d.pad = stride, pad
+        d.planes_in = planes_in
+        d.planes_out = 4 if out.dtype == torch.float32 else out.shape[0]
+        d.act = ACT[act]
+        d.res_planes = 0 if residual is None else residual.shape[0]
+        d.tile_w, d.tile_h = tile if tile else (0, 0)
+        self._keep = (x, w, bias, out, residual, tile_sums)
+        h = C.c_void_p()
+        check(lib().mtb_conv_plan_create(C.byref(d), ptr(x), ptr(w), ptr(bias), ptr(out), ptr(residual),
+                                         ptr(tile_sums), C.byref(h)), "mtb_conv_plan_create")
+        self._h = h
+        self.out = out
+
+    @property
+    def num_mtiles(self) -> int:
+        return lib().mtb_conv_plan_num_mtiles(self._h)
+
+    def run(self) -> None:
+        check(lib().mtb_conv_plan_run(self._h, stream_ptr()), "mtb_conv_plan_run")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().mtb_conv_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
