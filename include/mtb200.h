@@ -58,6 +58,77 @@ int mtb_conv_plan_run(mtb_conv_plan* plan, void* stream);
 int mtb_conv_plan_num_mtiles(const mtb_conv_plan* plan);
 void mtb_conv_plan_destroy(mtb_conv_plan* plan);
 
+/* ---- bubble cleaning (bit-exact integer path) ------------------------------------------------------------
+ * Replaces the per-bubble OpenCV pipeline of core/image/cleaning.py:210-521 (process_single_bubble) and the
+ * colour-grouped fill of core/image/cleaning.py:1021-1039, for all bubbles of all pages of a batch in one launch.
+ */
+#define MTB_CLEAN_MAX_SE 63
+#define MTB_CLEAN_MAX_BALL 65
+#define MTB_CLEAN_MAX_NEIGHBORS 8
+
+typedef struct mtb_clean_params {
+  int thr_value;   /* CleaningConfig.thresholding_value (core/config.py:28) */
+  int use_otsu;    /* CleaningConfig.use_otsu_threshold */
+  int retry_otsu;  /* retry failed bubbles once with Otsu (core/image/cleaning.py:690-734) */
+  int kd, ke;      /* scale_kernel(DILATION/EROSION_KERNEL_SIZE, processing_scale) (cleaning.py:637-642) */
+  int sed_hw[MTB_CLEAN_MAX_SE]; /* half-width of each row of cv2.getStructuringElement(MORPH_ELLIPSE,(kd,kd)); -1 = empty */
+  int see_hw[MTB_CLEAN_MAX_SE];
+  int ball_r;                               /* rows -ball_r..ball_r of the chamfer ball {N(dx,dy) < roi_shrink} */
+  int ball_hw[2 * MTB_CLEAN_MAX_BALL + 1];
+  int jball_r;                              /* same for JUNCTION_MIN_SHRINK (cleaning.py:38-39,167-168) */
+  int jball_hw[2 * MTB_CLEAN_MAX_BALL + 1];
+  int junction_margin;
+  double min_area; /* scale_area(MIN_CONTOUR_AREA, ...) (cleaning.py:643-648) */
+  int margin;      /* window margin applied by the host around each detection bbox */
+} mtb_clean_params;
+
+typedef struct mtb_clean_job {
+  const uint8_t* img; /* device: page, interleaved BGR or BGRA */
+  long long img_pitch;
+  int img_h, img_w, img_c;
+  const uint8_t* mask; /* device: mask bytes (>0 = set) of a rectangle placed at (mask_x0, mask_y0) */
+  long long mask_pitch;
+  int mask_x0, mask_y0, mask_w, mask_h;
+  int wx0, wy0, cw, ch; /* crop window, inside the page */
+  int bbox[4];          /* detection bbox (x0,y0,x1,y1) */
+  int n_neighbors;      /* conjoined_neighbor_bboxes (core/image/detection.py:1197-1205) */
+  int neighbors[MTB_CLEAN_MAX_NEIGHBORS][4];
+  uint32_t* work;       /* device workspace of mtb_clean_workspace_words(cw, ch, max_runs) 32-bit words */
+  int max_runs;
+  int page_index;
+} mtb_clean_job;
+
+typedef struct mtb_clean_result {
+  int status; /* 0 ok, 1 empty mask, 2 no valid contour, 3 window too small, 4 workspace overflow */
+  int used_otsu, otsu_thr;
+  int is_black;
+  int fill_bgr[3];
+  int text_bbox[4];
+  int has_text_color;
+  int text_color[4];
+  int n_components, n_valid;
+  int final_start;
+  long long final_pixels;
+  double final_area;
+  unsigned long long gray_sum;
+  unsigned int gray_cnt;
+} mtb_clean_result;
+
+unsigned long long mtb_clean_workspace_words(int cw, int ch, int max_runs);
+/* jobs/results: device arrays of n_jobs entries; params: host pointer (copied). One CTA per job. */
+int mtb_clean_bubbles(const mtb_clean_params* params, const mtb_clean_job* jobs_dev, mtb_clean_result* results_dev,
+                      int n_jobs, void* stream);
+/* paint every ok job's final mask with its fill colour into pages_out[page_index] (same geometry as the job's
+ * page). Colour groups are applied in first-seen order per page, later groups overwrite earlier ones
+ * (core/image/cleaning.py:1021-1039); max_ranks bounds the number of distinct colours per page (2 unless
+ * coloured-bubble classification is on). The alpha channel of BGRA pages is preserved. */
+int mtb_clean_paint(const mtb_clean_job* jobs_dev, const mtb_clean_result* results_dev, int n_jobs,
+                    uint8_t* const* pages_out_dev, int* rank_scratch_dev /* n_jobs ints */, int max_ranks,
+                    void* stream);
+/* expand one job's final mask (bit-plane, crop window) into a full-frame uint8 {0,255} mask */
+int mtb_clean_export_mask(const mtb_clean_job* jobs_dev, int job_index, uint8_t* out /* img_h x img_w */,
+                          long long out_pitch, int plane /* 9 = final mask */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,47 @@
+"""CPU: the C-ABI shared library loads and exports every function include/mtb200.h declares (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build_if_needed():
+    so = os.path.join(ROOT, "mangatranslator_b200", "lib", "libmtb200.so")
+    if not os.path.exists(so):
+        import __graft_entry__ as g
+        g.build()
+    return so
+
+
+def test_library_exports_every_declared_symbol():
+    so = _build_if_needed()
+    lib = C.CDLL(so)
+    hdr = open(os.path.join(ROOT, "include", "mtb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(mtb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 8
+    for n in sorted(names):
+        assert hasattr(lib, n), f"libmtb200.so does not export {n}"
+
+
+def test_struct_layouts_match_header_sizes():
+    from mangatranslator_b200 import clean_host as H
+    # sizes as the C compiler lays the header structs out (natural alignment)
+    assert C.sizeof(H.CleanParams) % 8 == 0
+    assert C.sizeof(H.CleanJob) % 8 == 0
+    assert C.sizeof(H.CleanResult) % 8 == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    import importlib
+    import mangatranslator_b200._lib as L
+    monkeypatch.setattr(L, "LIB_PATH", tmp_path / "nope.so")
+    monkeypatch.setattr(L, "_lib", None)
+    try:
+        L.lib()
+        raised = False
+    except L.MtbError:
+        raised = True
+    assert raised
+    importlib.reload(L)

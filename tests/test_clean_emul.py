@@ -1,0 +1,141 @@
+"""CPU: the cleaning KERNEL LOGIC (clean_core.cuh compiled as a sequential host emulation, tests/host_emul) is
+bit-exact against the cv2 oracle: golden pages, random bubbles, Otsu, conjoined neighbours, page borders, RGBA,
+and the host-side structuring-element / chamfer-ball tables against cv2 itself."""
+import cv2
+import numpy as np
+import pytest
+
+import clean_oracle
+from helpers import build_clean_case, emul_clean_bubble, load_clean_golden
+from mangatranslator_b200 import clean_host as H
+
+GOLD = load_clean_golden()
+
+
+@pytest.mark.parametrize("k", list(range(1, 64, 2)))
+def test_ellipse_rows_match_cv2(k):
+    se = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (k, k))
+    rows = H.ellipse_rows(k)
+    c = k // 2
+    for i, w in enumerate(rows):
+        exp = np.zeros(k, np.uint8)
+        if w >= 0:
+            exp[c - w:c + w + 1] = 1
+        assert np.array_equal(se[i], exp), (k, i)
+
+
+@pytest.mark.parametrize("t", [0.5, 1.0, 1.3, 2.2, 4.43, 5.0, 6.2706, 10.0, 17.3])
+def test_chamfer_ball_equals_distance_transform_threshold(t):
+    rng = np.random.default_rng(int(t * 100))
+    r, rows = H.chamfer_ball_rows(t)
+    for _ in range(6):
+        h, w = int(rng.integers(40, 120)), int(rng.integers(40, 120))
+        m = (rng.random((h, w)) < 0.985).astype(np.uint8) * 255
+        cv2.circle(m, (w // 2, h // 2), int(min(h, w) * 0.3), 255, -1)
+        dist = cv2.distanceTransform(m, cv2.DIST_L2, 5)
+        exp = dist >= np.float32(t)
+        # erosion by the open ball, out-of-image pixels ignored
+        pad = r + max(rows) + 1
+        big = np.ones((h + 2 * pad, w + 2 * pad), bool)
+        big[pad:pad + h, pad:pad + w] = m > 0
+        got = np.ones((h, w), bool)
+        for dy, hw in zip(range(-r, r + 1), rows):
+            for dx in range(-hw, hw + 1):
+                got &= big[pad + dy:pad + dy + h, pad + dx:pad + dx + w]
+        assert np.array_equal(got, exp)
+
+
+def test_otsu_and_hsv_match_cv2():
+    import ctypes as C
+    from helpers import clean_emul_lib
+    E = clean_emul_lib()
+    rng = np.random.default_rng(3)
+    for _ in range(40):
+        n = int(rng.integers(10, 5000))
+        a = np.clip(rng.normal(rng.integers(40, 200), rng.integers(5, 80), n), 0, 255).astype(np.uint8)
+        thr, _ = cv2.threshold(a, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
+        hist = np.bincount(a, minlength=256).astype(np.uint32)
+        assert E.emul_otsu(hist.ctypes.data_as(C.POINTER(C.c_uint)), C.c_uint(n)) == int(thr)
+    px = rng.integers(0, 256, size=(4000, 3), dtype=np.uint8)
+    hsv = cv2.cvtColor(px.reshape(1, -1, 3), cv2.COLOR_BGR2HSV)[0]
+    for (b, g, r), s in zip(px.tolist(), hsv[:, 1].tolist()):
+        assert E.emul_hsv_sat(b, g, r) == s
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_emulated_kernel_matches_oracle_on_golden_pages(name):
+    g = GOLD[name]
+    bgr, dets = build_clean_case(g)
+    _, bubbles = clean_oracle.clean_page(bgr, dets, thresholding_value=g["thresholding_value"],
+                                         use_otsu_threshold=g["use_otsu"], roi_shrink_px=g["roi_shrink_px"],
+                                         processing_scale=g["processing_scale"])
+    params = H.build_params(g["thresholding_value"], g["use_otsu"], g["roi_shrink_px"], g["processing_scale"])
+    by_bbox = {tuple(b["bbox"]): b for b in bubbles}
+    for d in dets:
+        R, mask = emul_clean_bubble(bgr, d["sam_mask"], d["bbox"], params, d.get("conjoined_neighbor_bboxes"))
+        o = by_bbox.get(tuple(d["bbox"]))
+        if o is None:
+            assert R.status != 0
+            continue
+        assert R.status == 0
+        assert np.array_equal(mask, o["mask"])
+        assert tuple(R.fill_bgr) == tuple(o["color"]) and tuple(R.text_bbox) == tuple(o["text_bbox"])
+        tc = None
+        if R.has_text_color:
+            tc = tuple(R.text_color)[:3] if R.text_color[3] == -1 else tuple(R.text_color)[:bgr.shape[2]]
+        assert tc == (None if o["text_color_bgr"] is None else tuple(o["text_color_bgr"]))
+        assert bool(R.used_otsu) == bool(o["used_otsu"])
+
+
+def test_emulated_kernel_fuzz_against_oracle():
+    rng = np.random.default_rng(11)
+    n_ok = 0
+    for it in range(60):
+        h, w = int(rng.integers(100, 360)), int(rng.integers(100, 360))
+        c = 4 if rng.random() < 0.3 else 3
+        scale = float(rng.choice([0.5, 0.8868, 1.0, 1.2541, 2.0]))
+        img = rng.integers(0, 256, size=(h, w, c), dtype=np.uint8)
+        mask = np.zeros((h, w), np.uint8)
+        cv2.ellipse(mask, (int(rng.integers(0, w)), int(rng.integers(0, h))),
+                    (int(rng.integers(20, w // 2 + 21)), int(rng.integers(20, h // 2 + 21))),
+                    int(rng.integers(0, 180)), 0, 360, 255, -1)
+        if rng.random() < 0.3:
+            cv2.circle(mask, (int(rng.integers(0, w)), int(rng.integers(0, h))), int(rng.integers(5, 40)),
+                       0 if rng.random() < 0.5 else 255, -1)
+        if not mask.any():
+            continue
+        bright = 255 if rng.random() < 0.7 else 5
+        sel = mask > 0
+        if rng.random() < 0.6:
+            img[sel] = np.clip(bright + rng.integers(-25, 26, size=(int(sel.sum()), c)), 0, 255).astype(np.uint8)
+        for _ in range(int(rng.integers(0, 40))):
+            p0 = (int(rng.integers(0, w)), int(rng.integers(0, h)))
+            col = tuple(int(v) for v in (rng.integers(0, 60, size=c) if bright == 255 else rng.integers(200, 256, size=c)))
+            cv2.line(img, p0, (p0[0] + int(rng.integers(-30, 31)), p0[1] + int(rng.integers(-30, 31))), col,
+                     int(rng.integers(1, 5)))
+        img = np.ascontiguousarray(img)
+        gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY if c == 3 else cv2.COLOR_BGRA2GRAY)
+        thr = int(rng.choice([200, 180, 128, 220]))
+        otsu = bool(rng.random() < 0.25)
+        shrink = float(rng.choice([5, 0, 2, 8, 12]))
+        ys, xs = np.nonzero(mask)
+        bbox = (int(xs.min()), int(ys.min()), int(xs.max()) + 1, int(ys.max()) + 1)
+        nbs = None
+        if rng.random() < 0.3:
+            nbs = [(bbox[2] - int(rng.integers(0, 30)), bbox[1] + int(rng.integers(-20, 20)),
+                    bbox[2] + int(rng.integers(20, 100)), bbox[3] + int(rng.integers(-20, 20)))]
+        kd, ke, eff, min_area = clean_oracle.scaled_params(shrink, scale)
+        o = clean_oracle.clean_bubble(mask, gray, img, threshold=thr, otsu=otsu, shrink_px=eff, kd=kd, ke=ke,
+                                      min_area=min_area, bbox=bbox, neighbors=nbs, scale=scale)
+        params = H.build_params(thr, otsu, shrink, scale, retry_otsu=False)
+        R, m = emul_clean_bubble(img, mask, bbox, params, nbs)
+        assert (R.status == 0) == o.ok, (it, R.status, o.reason)
+        if o.ok:
+            n_ok += 1
+            assert np.array_equal(m, o.mask), it
+            assert tuple(R.fill_bgr) == tuple(o.fill_bgr) and tuple(R.text_bbox) == tuple(o.text_bbox), it
+            tc = None
+            if R.has_text_color:
+                tc = tuple(R.text_color)[:3] if R.text_color[3] == -1 else tuple(R.text_color)[:c]
+            assert tc == o.text_color, it
+    assert n_ok > 20
