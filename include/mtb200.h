@@ -45,6 +45,8 @@ typedef struct mtb_conv_desc {
   int act;        /* 0 none, 1 relu, 2 silu, 3 gelu(erf), 4 sigmoid */
   int res_planes; /* planes of the residual tensor (0 = none) */
   int tile_w, tile_h; /* pixel tile (product 128); 0 = choose */
+  int pixel_shuffle;  /* 1: fuse PixelShuffle(2) into the store (Cout = 4 blocks [dy*2+dx] of Cout/4 channels) */
+  int mode;           /* 0 auto, 1 force the per-tap kernel, 2 require the halo-tile kernel (3x3 s1 p1, 64->64) */
 } mtb_conv_desc;
 
 typedef struct mtb_conv_plan mtb_conv_plan;
@@ -128,6 +130,21 @@ int mtb_clean_paint(const mtb_clean_job* jobs_dev, const mtb_clean_result* resul
 /* expand one job's final mask (bit-plane, crop window) into a full-frame uint8 {0,255} mask */
 int mtb_clean_export_mask(const mtb_clean_job* jobs_dev, int job_index, uint8_t* out /* img_h x img_w */,
                           long long out_pitch, int plane /* 9 = final mask */, void* stream);
+
+/* ---- HBM-bound glue around the convolutions ---------------------------------------------------------------
+ * image_to_planes : core/image/image_utils.py:351-358 image_to_tensor (u8 -> float/255 NCHW), here u8 HWC -> NHWC planes
+ * ca_scale        : RCAN CALayer (adaptive avg-pool finish + 1x1 -> ReLU -> 1x1 -> sigmoid), spandrel RCAN
+ * scale_residual  : RCAB tail  y = x + t * gate[c]
+ * f32_to_u8       : core/image/image_utils.py:361-366 tensor_to_image (clamp, *255, truncate)
+ */
+int mtb_image_to_planes(const uint8_t* img, int H, int W, int cimg, int swap_rb, float mul, const float* sub3 /* host */,
+                        void* planes_out /* bf16 [planes][H][W][cpad] */, int cpad, int planes, void* stream);
+int mtb_ca_scale(const float* sums, int n_images, int parts_per_image, int C, float inv_hw, const float* w1,
+                 const float* b1, const float* w2, const float* b2, int R, float* scale_out, void* stream);
+int mtb_scale_residual(const void* t, const void* x, const float* scale, void* y, long long pix_per_image, int N, int C,
+                       void* stream);
+int mtb_f32_to_u8(const float* in, long long npix, int cpad, const float* add3 /* host */, float mul, uint8_t* out,
+                  float* out_f /* optional float copy [npix][3] */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,11 +67,18 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* 
 
 using namespace mtb;
 
+namespace mtb {
+bool conv_halo_eligible(const ConvParams& p, int cin);
+int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int nsplit,
+                     cudaStream_t stream);
+}  // namespace mtb
+
 struct mtb_conv_plan {
   CUtensorMap tmA;
   CUtensorMap tmB;
   ConvParams p;
   int nsplit;
+  int halo;
 };
 
 extern "C" {
@@ -134,8 +141,6 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
     delete pl;
     MTB_REQUIRE(false, "conv: tile %dx%d must hold 128 pixels", tw, th);
   }
-  p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
-  p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
   p.planes_out = d->planes_out == 4 ? 1 : d->planes_out;
   p.act = d->act;
   p.out_plane_stride = static_cast<long long>(p.N) * p.Ho * p.Wo * p.Cout;
@@ -151,6 +156,23 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
   }
   p.residual = static_cast<const uint16_t*>(residual);
   p.tile_sums = tile_sums;
+  p.pixel_shuffle = d->pixel_shuffle ? 1 : 0;
+  if (p.pixel_shuffle && (d->Cout % 64 != 0 || d->planes_out == 4 || residual)) {
+    delete pl;
+    MTB_REQUIRE(false, "conv: pixel_shuffle needs Cout %% 64 == 0, bf16 plane output and no residual");
+  }
+  // halo-tile kernel for the RCAN body layer (3x3, stride 1, 64 -> 64 channels); mode 1 forces the per-tap kernel
+  pl->halo = (d->mode != 1 && conv_halo_eligible(p, d->Cin)) ? 1 : 0;
+  if (d->mode == 2 && !pl->halo) {
+    delete pl;
+    MTB_REQUIRE(false, "conv: halo mode requested but layer is not eligible (needs 3x3 s1 p1, 64->64 channels)");
+  }
+  if (pl->halo) {
+    p.TW = 8;
+    p.TH = 16;
+  }
+  p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
+  p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
   pl->nsplit = d->planes_in == 2 ? 3 : 1;
   int cols = 32;
   while (cols < 2 * p.BN) cols <<= 1;
@@ -170,7 +192,11 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
                               static_cast<uint64_t>(d->N) * d->planes_in};
     const uint64_t strides[3] = {static_cast<uint64_t>(d->Cin) * 2, static_cast<uint64_t>(d->W) * d->Cin * 2,
                                  static_cast<uint64_t>(d->H) * d->W * d->Cin * 2};
-    const uint32_t box[4] = {64, static_cast<uint32_t>(p.TW * d->stride), static_cast<uint32_t>(p.TH * d->stride), 1};
+    uint32_t box[4] = {64, static_cast<uint32_t>(p.TW * d->stride), static_cast<uint32_t>(p.TH * d->stride), 1};
+    if (pl->halo) {
+      box[1] = static_cast<uint32_t>(p.TW + 2);
+      box[2] = static_cast<uint32_t>(p.TH + 2);
+    }
     const uint32_t es[4] = {1, static_cast<uint32_t>(d->stride), static_cast<uint32_t>(d->stride), 1};
     if (encode_tmap(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, es,
                     CU_TENSOR_MAP_SWIZZLE_128B) != 0) {
@@ -196,7 +222,9 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
 
 int mtb_conv_plan_run(mtb_conv_plan* plan, void* stream) {
   MTB_REQUIRE(plan != nullptr, "mtb_conv_plan_run: null plan");
-  int rc = launch_conv_gemm(plan->tmA, plan->tmB, plan->p, plan->nsplit, static_cast<cudaStream_t>(stream));
+  int rc = plan->halo
+               ? launch_conv_halo(plan->tmA, plan->tmB, plan->p, plan->nsplit, static_cast<cudaStream_t>(stream))
+               : launch_conv_gemm(plan->tmA, plan->tmB, plan->p, plan->nsplit, static_cast<cudaStream_t>(stream));
   if (rc == 0) mtb::g_launches.fetch_add(1);
   return rc;
 }

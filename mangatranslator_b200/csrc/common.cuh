@@ -92,9 +92,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug becomes a trapped kernel (CUDA error) instead of a hung GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
       printf("mtb: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }

@@ -252,11 +252,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               hi[j] = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
               lo[j] = static_cast<uint32_t>(l0) | (static_cast<uint32_t>(l1) << 16);
             }
-            uint4* o4 = reinterpret_cast<uint4*>(p.out + pix * p.Cout + cbase);
+            long long off = pix * p.Cout + cbase;
+            if (p.pixel_shuffle) {
+              // PixelShuffle(2) fused into the store: channel block b = dy*2+dx lands on the 2x finer grid
+              const int cq = p.Cout >> 2;
+              const int blk = cbase / cq, cc = cbase - blk * cq;
+              const long long hp = (static_cast<long long>(t.n) * (2 * p.Ho) + 2 * oy + (blk >> 1)) * (2 * p.Wo) +
+                                   2 * ox + (blk & 1);
+              off = hp * cq + cc;
+            }
+            uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
             o4[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             o4[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
             if (p.planes_out == 2) {
-              uint4* l4 = reinterpret_cast<uint4*>(p.out + p.out_plane_stride + pix * p.Cout + cbase);
+              uint4* l4 = reinterpret_cast<uint4*>(p.out + p.out_plane_stride + off);
               l4[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
               l4[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
             }

@@ -43,6 +43,7 @@ struct ConvParams {
   float* out_f32;              // optional fp32 output [N][Ho][Wo][Cout]
   const uint16_t* residual;    // optional, same geometry as out, added after the activation
   float* tile_sums;            // optional [N*tiles_y*tiles_x][4][Cout] per-warp channel sums of the output
+  int pixel_shuffle;           // 1: Cout = 4 blocks of Cout/4 channels, block (dy*2+dx) is stored at pixel (2y+dy, 2x+dx)
 };
 
 int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int nsplit,

@@ -1,0 +1,296 @@
+// 3x3 / stride 1 / pad 1 convolution with 64 input and 64 output channels — the RCAN residual-channel-attention body
+// layer that runs ~400 times per page (reference: spandrel RCAN behind core/image/image_utils.py:369-374) — as a
+// HALO-TILE implicit GEMM on tcgen05:
+//
+//   * the 9 filter taps are 9 SHIFTED VIEWS of one shared-memory tile: TMA loads the (16+2) x (8+2) pixel halo of a
+//     16x8 output tile once (128B-swizzled, one 128-byte row per pixel) and the UMMA shared-memory descriptor of tap
+//     (ky,kx) just starts (ky*10+kx) rows later with a 10-row stride between 8-pixel groups (SBO = 1280 B).
+//     (Verified on B200 by mtb_exp_shifted_desc: the 128B swizzle is a function of absolute smem address bits, so
+//     row-shifted descriptors with base_offset = 0 read the rows TMA wrote.)  L2->SM traffic per tile drops from
+//     9 x 32 KB (one TMA box per tap) to 46 KB.
+//   * all weights (9 taps x [hi|lo] x 64x64 bf16 = 144 KB) are loaded once per persistent CTA and stay resident.
+//   * bf16x3 with ONE N=128 MMA per (tap, k16): A_hi x [W_hi ; W_lo] -> columns 0..63 = Ahi*Whi, 64..127 = Ahi*Wlo,
+//     then A_lo x W_hi accumulates into columns 0..63; the epilogue adds the two halves.  Shared-memory operand
+//     traffic per MMA is then 128 B/clk for the N=128 instruction, i.e. matched to the SMEM bandwidth.
+//   * ring of 3 shared-memory slots, one (tile, plane) halo per slot, so the next tile's hi plane streams in while the
+//     current tile's lo plane is being multiplied; 2 TMEM accumulator stages overlap the epilogue with the next tile.
+#include "conv_gemm.cuh"
+
+namespace mtb {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kTW = 8, kTH = 16;                    // output tile (pixels)
+constexpr int kHW = kTW + 2, kHH = kTH + 2;         // halo tile
+constexpr int kHaloBytes = kHW * kHH * 128;         // 23040
+constexpr int kSlotBytes = 23552;                   // 1024-aligned slot
+constexpr int kSlots = 3;
+constexpr int kTapBytes = 128 * 128;                // [W_hi(64 rows) ; W_lo(64 rows)] x 128 B
+constexpr int kWBytes = 9 * kTapBytes;              // 147456
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.0f);
+    case ACT_SILU: return v / (1.0f + expf(-v));
+    case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    case ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    default: return v;
+  }
+}
+
+// PLANES == 2: bf16x3 (fp32-grade);  PLANES == 1: plain bf16
+template <int PLANES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;                         // resident weights
+  uint8_t* sA = smem + kWBytes;               // ring of halo slots
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + kSlots * kSlotBytes);
+  uint64_t* empty_bar = full_bar + kSlots;
+  uint64_t* tfull_bar = empty_bar + kSlots;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint64_t* w_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int ACC_COLS = (PLANES == 2) ? 128 : 64;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * ACC_COLS);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+  const int total_tiles = p.N * tiles_per_img;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: per tap, W_hi rows then W_lo rows
+      mbar_expect_tx(w_bar, static_cast<uint32_t>(9 * PLANES * 64 * 128));
+      for (int tap = 0; tap < 9; ++tap)
+        for (int pl = 0; pl < PLANES; ++pl)
+          tma_load_2d(sW + tap * kTapBytes + pl * 64 * 128, &tmB, w_bar, 0, (pl * 9 + tap) * 64);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
+        for (int pl = 0; pl < PLANES; ++pl) {
+          mbar_wait(&empty_bar[slot], phase ^ 1);
+          mbar_expect_tx(&full_bar[slot], kHaloBytes);
+          tma_load_4d(sA + slot * kSlotBytes, &tmA, &full_bar[slot], 0, txi * kTW - 1, tyi * kTH - 1, pl * p.N + n);
+          if (++slot == kSlots) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_wide = make_idesc_bf16(128, ACC_COLS);  // A_hi x [W_hi;W_lo]  (or A x W for bf16)
+    const uint32_t idesc_64 = make_idesc_bf16(128, 64);          // A_lo x W_hi
+    mbar_wait(w_bar, 0);
+    tc_fence_after();
+    const uint32_t sw = smem_u32(sW);
+    int slot = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * ACC_COLS);
+      for (int pl = 0; pl < PLANES; ++pl) {
+        mbar_wait(&full_bar[slot], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(sA + slot * kSlotBytes);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const uint32_t a0 = sa + (ky * kHW + kx) * 128;
+            const uint32_t b0 = sw + tap * kTapBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = make_sdesc_sw128(a0 + k * 32, kHW * 128, 0);
+              const uint64_t db = make_sdesc_sw128(b0 + k * 32, 1024, 0);
+              if (pl == 0) umma_bf16(d_tmem, da, db, idesc_wide, (tap > 0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, da, db, idesc_64, 1u);
+            }
+          }
+          umma_commit(&empty_bar[slot]);
+        }
+        __syncwarp();
+        if (++slot == kSlots) {
+          slot = 0;
+          phase ^= 1;
+        }
+      }
+      if (lane == 0) umma_commit(&tfull_bar[as]);
+      __syncwarp();
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int ty = r >> 3, tx = r & 7;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
+      const int oy = tyi * kTH + ty, ox = txi * kTW + tx;
+      const bool valid = (oy < p.Ho) && (ox < p.Wo);
+      const long long pix = (static_cast<long long>(n) * p.Ho + oy) * p.Wo + ox;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * ACC_COLS);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t acc[16];
+        float v[16];
+        tmem_ld16(taddr + c0, acc);
+        if (PLANES == 2) {
+          uint32_t acc2[16];
+          tmem_ld16(taddr + 64 + c0, acc2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) + __uint_as_float(acc2[j]);
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x = v[j];
+          if (p.bias) x += __ldg(p.bias + c0 + j);
+          v[j] = act_fn(x, p.act);
+        }
+        if (p.residual && valid) {
+          const uint16_t* rp = p.residual + pix * 64 + c0;
+          for (int pl = 0; pl < p.res_planes; ++pl) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(rp + pl * p.res_plane_stride);
+            const uint4 a = __ldg(r4), b = __ldg(r4 + 1);
+            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[2 * j] += bf16_to_f(static_cast<uint16_t>(w[j] & 0xFFFF));
+              v[2 * j + 1] += bf16_to_f(static_cast<uint16_t>(w[j] >> 16));
+            }
+          }
+        }
+        if (!valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+        }
+        if (p.tile_sums) {
+          float s[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s[j] = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 16);
+#pragma unroll
+          for (int w = 8; w >= 1; w >>= 1) {
+            const bool upper = (lane & w) != 0;
+#pragma unroll
+            for (int j = 0; j < w; ++j) {
+              const float send = upper ? s[j] : s[j + w];
+              const float keep = upper ? s[j + w] : s[j];
+              s[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+            }
+          }
+          if (lane < 16) p.tile_sums[(static_cast<long long>(tile) * 4 + q) * 64 + c0 + lane] = s[0];
+        }
+        if (valid) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint16_t h0, l0, h1, l1;
+            split_bf16(v[2 * j], h0, l0);
+            split_bf16(v[2 * j + 1], h1, l1);
+            hi[j] = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
+            lo[j] = static_cast<uint32_t>(l0) | (static_cast<uint32_t>(l1) << 16);
+          }
+          uint4* o4 = reinterpret_cast<uint4*>(p.out + pix * 64 + c0);
+          o4[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          o4[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          if (p.planes_out == 2) {
+            uint4* l4 = reinterpret_cast<uint4*>(p.out + p.out_plane_stride + pix * 64 + c0);
+            l4[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            l4[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * ACC_COLS);
+}
+
+}  // namespace
+
+bool conv_halo_eligible(const ConvParams& p, int cin) {
+  return p.KH == 3 && p.KW == 3 && p.stride == 1 && p.pad == 1 && cin == 64 && p.Cout == 64 && p.out != nullptr &&
+         p.Ho > 1;
+}
+
+int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int nsplit,
+                     cudaStream_t stream) {
+  const size_t smem = 1024 + kWBytes + kSlots * kSlotBytes + 16 * 8 + 16;
+  int dev = 0, sms = 0;
+  MTB_CUDA_OK(cudaGetDevice(&dev));
+  MTB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long total = static_cast<long long>(p.N) * p.tiles_y * p.tiles_x;
+  const int grid = static_cast<int>(total < sms ? total : sms);
+  if (grid <= 0) return 0;
+  if (nsplit == 3) {
+    MTB_CUDA_OK(cudaFuncSetAttribute(conv3x3_c64_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+    conv3x3_c64_halo_kernel<2><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  } else {
+    MTB_CUDA_OK(cudaFuncSetAttribute(conv3x3_c64_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+    conv3x3_c64_halo_kernel<1><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  }
+  MTB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mtb

@@ -1,0 +1,217 @@
+// HBM-bound glue kernels around the tensor-core convolutions: image <-> plane conversion, RCAN channel attention
+// (global average pool finish + squeeze/excite MLP + gate + residual), nearest upsample, concat, max-pool.
+// All are pure streaming kernels: 16-byte vector loads/stores, grid = multiple of the SM count, one pass over HBM.
+#include <atomic>
+
+#include "../../include/mtb200.h"
+#include "common.cuh"
+
+namespace mtb {
+extern std::atomic<long long> g_launches;
+}
+using namespace mtb;
+
+namespace {
+
+inline int grid_for(long long work_items, int block, int sms) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = static_cast<long long>(sms) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+// u8 interleaved image (Cimg = 3 or 4) -> hi/lo planes NHWC, C = cpad (channels >= 3 zero)
+__global__ void image_to_planes_kernel(const uint8_t* __restrict__ img, int H, int W, int cimg, int swap_rb, float mul,
+                                       float s0, float s1, float s2, uint16_t* __restrict__ out, long long plane_stride,
+                                       int cpad, int planes) {
+  const long long npix = static_cast<long long>(H) * W;
+  const int vec_per_pix = cpad / 8;  // 16-byte vectors per pixel per plane
+  const long long total = npix * vec_per_pix;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i / vec_per_pix;
+    const int v = static_cast<int>(i - pix * vec_per_pix);
+    uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+    if (v == 0) {
+      const uint8_t* p = img + pix * cimg;
+      float c0 = p[swap_rb ? 2 : 0], c1 = p[1], c2 = p[swap_rb ? 0 : 2];
+      c0 = c0 * mul - s0;
+      c1 = c1 * mul - s1;
+      c2 = c2 * mul - s2;
+      uint16_t h0, l0, h1, l1, h2, l2;
+      split_bf16(c0, h0, l0);
+      split_bf16(c1, h1, l1);
+      split_bf16(c2, h2, l2);
+      hi.x = h0 | (static_cast<uint32_t>(h1) << 16);
+      hi.y = h2;
+      lo.x = l0 | (static_cast<uint32_t>(l1) << 16);
+      lo.y = l2;
+    }
+    reinterpret_cast<uint4*>(out + pix * cpad)[v] = hi;
+    if (planes == 2) reinterpret_cast<uint4*>(out + plane_stride + pix * cpad)[v] = lo;
+  }
+}
+
+// finish the global average pool from the conv epilogue's per-warp partial sums and run the squeeze/excite MLP
+// one block per image; C <= 256, R <= 64
+__global__ void ca_scale_kernel(const float* __restrict__ sums, int parts, int C, float inv_hw,
+                                const float* __restrict__ w1, const float* __restrict__ b1,
+                                const float* __restrict__ w2, const float* __restrict__ b2, int R,
+                                float* __restrict__ scale) {
+  __shared__ float mean[256];
+  __shared__ float hid[64];
+  __shared__ float part[8][256];
+  const int n = blockIdx.x;
+  const float* s = sums + static_cast<long long>(n) * parts * C;
+  // deterministic two-level reduction: 8 row-groups of threads, fixed order inside each
+  const int c = threadIdx.x % C;
+  const int g = threadIdx.x / C;       // blockDim = 8*C (<= 1024 when C <= 128) or C
+  const int groups = blockDim.x / C;
+  float acc = 0.f;
+  for (int p = g; p < parts; p += groups) acc += s[static_cast<long long>(p) * C + c];
+  part[g][c] = acc;
+  __syncthreads();
+  if (g == 0) {
+    float t = 0.f;
+    for (int k = 0; k < groups; ++k) t += part[k][c];
+    mean[c] = t * inv_hw;
+  }
+  __syncthreads();
+  if (threadIdx.x < R) {
+    float h = b1 ? b1[threadIdx.x] : 0.f;
+    for (int k = 0; k < C; ++k) h += w1[threadIdx.x * C + k] * mean[k];
+    hid[threadIdx.x] = fmaxf(h, 0.f);
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float o = b2 ? b2[threadIdx.x] : 0.f;
+    for (int k = 0; k < R; ++k) o += w2[threadIdx.x * R + k] * hid[k];
+    scale[n * C + threadIdx.x] = 1.0f / (1.0f + expf(-o));
+  }
+}
+
+// y = x + t * scale[n][c]   (all hi/lo planes, NHWC, C multiple of 8)
+__global__ void scale_residual_kernel(const uint16_t* __restrict__ t, const uint16_t* __restrict__ x,
+                                      const float* __restrict__ scale, uint16_t* __restrict__ y,
+                                      long long plane_stride, long long pix_per_image, int N, int C) {
+  const int vec_per_pix = C / 8;
+  const long long total = pix_per_image * N * vec_per_pix;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i / vec_per_pix;
+    const int v = static_cast<int>(i - pix * vec_per_pix);
+    const int n = static_cast<int>(pix / pix_per_image);
+    const long long off = pix * C + v * 8;
+    const uint4 th = *reinterpret_cast<const uint4*>(t + off);
+    const uint4 tl = *reinterpret_cast<const uint4*>(t + plane_stride + off);
+    const uint4 xh = *reinterpret_cast<const uint4*>(x + off);
+    const uint4 xl = *reinterpret_cast<const uint4*>(x + plane_stride + off);
+    const uint32_t thw[4] = {th.x, th.y, th.z, th.w}, tlw[4] = {tl.x, tl.y, tl.z, tl.w};
+    const uint32_t xhw[4] = {xh.x, xh.y, xh.z, xh.w}, xlw[4] = {xl.x, xl.y, xl.z, xl.w};
+    const float* sc = scale + n * C + v * 8;
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t0 = bf16_to_f(thw[j] & 0xFFFF) + bf16_to_f(tlw[j] & 0xFFFF);
+      const float t1 = bf16_to_f(thw[j] >> 16) + bf16_to_f(tlw[j] >> 16);
+      const float x0 = bf16_to_f(xhw[j] & 0xFFFF) + bf16_to_f(xlw[j] & 0xFFFF);
+      const float x1 = bf16_to_f(xhw[j] >> 16) + bf16_to_f(xlw[j] >> 16);
+      const float y0 = x0 + t0 * sc[2 * j];
+      const float y1 = x1 + t1 * sc[2 * j + 1];
+      uint16_t h0, l0, h1, l1;
+      split_bf16(y0, h0, l0);
+      split_bf16(y1, h1, l1);
+      oh[j] = h0 | (static_cast<uint32_t>(h1) << 16);
+      ol[j] = l0 | (static_cast<uint32_t>(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(y + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4*>(y + plane_stride + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+  }
+}
+
+// fp32 NHWC (C = cpad, first 3 channels used) -> (v + add[c]) * mul, clamp [0,1], *255, truncate -> u8 HxWx3;
+// optionally also the float value before quantisation
+__global__ void f32_to_u8_kernel(const float* __restrict__ in, long long npix, int cpad, float a0, float a1, float a2,
+                                 float mul, uint8_t* __restrict__ out, float* __restrict__ out_f) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < npix;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float* p = in + i * cpad;
+    const float add[3] = {a0, a1, a2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = (p[c] + add[c]) * mul;
+      if (out_f) out_f[i * 3 + c] = v;
+      const float q = fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f;
+      out[i * 3 + c] = static_cast<uint8_t>(q);  // truncation like .astype(np.uint8) (image_utils.py:363-365)
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mtb_image_to_planes(const uint8_t* img, int H, int W, int cimg, int swap_rb, float mul, const float* sub3,
+                        void* planes_out, int cpad, int planes, void* stream) {
+  MTB_REQUIRE(img && planes_out && (cimg == 3 || cimg == 4) && cpad % 8 == 0 && cpad >= 8 && (planes == 1 || planes == 2),
+              "mtb_image_to_planes: bad arguments");
+  const long long total = static_cast<long long>(H) * W * (cpad / 8);
+  const float s0 = sub3 ? sub3[0] : 0.f, s1 = sub3 ? sub3[1] : 0.f, s2 = sub3 ? sub3[2] : 0.f;
+  image_to_planes_kernel<<<grid_for(total, 256, sm_count()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, H, W, cimg, swap_rb, mul, s0, s1, s2, static_cast<uint16_t*>(planes_out),
+      static_cast<long long>(H) * W * cpad, cpad, planes);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_ca_scale(const float* sums, int n_images, int parts_per_image, int C, float inv_hw, const float* w1,
+                 const float* b1, const float* w2, const float* b2, int R, float* scale_out, void* stream) {
+  MTB_REQUIRE(sums && w1 && w2 && scale_out, "mtb_ca_scale: null argument");
+  MTB_REQUIRE(C <= 256 && R <= 64 && C >= R, "mtb_ca_scale: C<=256, R<=64 required (C=%d R=%d)", C, R);
+  int groups = 1024 / C;
+  if (groups > 8) groups = 8;
+  if (groups < 1) groups = 1;
+  ca_scale_kernel<<<n_images, groups * C, 0, static_cast<cudaStream_t>(stream)>>>(sums, parts_per_image, C, inv_hw, w1,
+                                                                                b1, w2, b2, R, scale_out);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_scale_residual(const void* t, const void* x, const float* scale, void* y, long long pix_per_image, int N, int C,
+                       void* stream) {
+  MTB_REQUIRE(t && x && scale && y && C % 8 == 0, "mtb_scale_residual: bad arguments");
+  const long long total = pix_per_image * N * (C / 8);
+  scale_residual_kernel<<<grid_for(total, 256, sm_count()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(t), static_cast<const uint16_t*>(x), scale, static_cast<uint16_t*>(y),
+      pix_per_image * N * C, pix_per_image, N, C);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_f32_to_u8(const float* in, long long npix, int cpad, const float* add3, float mul, uint8_t* out, float* out_f,
+                  void* stream) {
+  MTB_REQUIRE(in && out && cpad >= 3, "mtb_f32_to_u8: bad arguments");
+  const float a0 = add3 ? add3[0] : 0.f, a1 = add3 ? add3[1] : 0.f, a2 = add3 ? add3[2] : 0.f;
+  f32_to_u8_kernel<<<grid_for(npix, 256, sm_count()), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, npix, cpad, a0,
+                                                                                                 a1, a2, mul, out,
+                                                                                                 out_f);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+}  // extern "C"

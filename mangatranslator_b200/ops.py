@@ -19,7 +19,7 @@ class ConvPlan:
     """
 
     def __init__(self, x, w, bias, out, *, k=1, stride=1, pad=0, act=None, residual=None, tile_sums=None,
-                 tile=None):
+                 tile=None, mode=0, pixel_shuffle=False):
         planes_in, n, h, wd, cin = x.shape
         assert w.shape[0] == planes_in and w.shape[1] == k * k and w.shape[3] == cin, (w.shape, x.shape)
         cout = w.shape[2]
@@ -32,6 +32,8 @@ class ConvPlan:
         d.act = ACT[act]
         d.res_planes = 0 if residual is None else residual.shape[0]
         d.tile_w, d.tile_h = tile if tile else (0, 0)
+        d.mode = mode
+        d.pixel_shuffle = int(bool(pixel_shuffle))
         self._keep = (x, w, bias, out, residual, tile_sums)
         h = C.c_void_p()
         check(lib().mtb_conv_plan_create(C.byref(d), ptr(x), ptr(w), ptr(bias), ptr(out), ptr(residual),

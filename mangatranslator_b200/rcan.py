@@ -1,0 +1,187 @@
+"""B200 RCAN upscaler (2x-AnimeSharpV4 architecture) — the object `ModelManager.load_upscale()` returns.
+
+Mirrors what the reference gets from spandrel (core/ml/model_manager.py:617-657): a callable
+`model(x: float32 (1,3,h,w) in [0,1]) -> (1,3,2h,2w)`; additionally `upscale_u8` keeps the page on the device as
+uint8 (what the batch pipeline uses).  Every convolution is a tcgen05 plan (bf16x3 by default = fp32-grade); the
+~200 RCAB body layers use the halo-tile kernel (conv_halo.cu).  Buffers are allocated once per input size.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import planes as P
+from ._lib import check, lib, ptr, stream_ptr
+from .ops import ConvPlan
+
+
+def _declare(l) -> None:
+    if getattr(l, "_ew_declared", False):
+        return
+    vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
+    l.mtb_image_to_planes.argtypes = [vp, i32, i32, i32, i32, f32, C.POINTER(f32), vp, i32, i32, vp]
+    l.mtb_ca_scale.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp, vp, i32, vp, vp]
+    l.mtb_scale_residual.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, i32, vp]
+    l.mtb_f32_to_u8.argtypes = [vp, C.c_longlong, i32, C.POINTER(f32), f32, vp, vp, vp]
+    for n in ("mtb_image_to_planes", "mtb_ca_scale", "mtb_scale_residual", "mtb_f32_to_u8"):
+        getattr(l, n).restype = i32
+    l._ew_declared = True
+
+
+def infer_config(sd: Dict[str, torch.Tensor]) -> dict:
+    """n_resgroups / n_resblocks / n_feats / reduction from state-dict keys and shapes (what spandrel's loader does)."""
+    groups = {int(k.split(".")[1]) for k in sd if k.startswith("body.") and k.count(".") >= 4}
+    blocks = {int(k.split(".")[3]) for k in sd if k.startswith("body.0.body.") and ".body." in k[12:]}
+    f = sd["head.0.weight"].shape[0]
+    red = f // sd["body.0.body.0.body.3.conv_du.0.weight"].shape[0]
+    return dict(n_resgroups=max(groups) + 1, n_resblocks=max(blocks) + 1, n_feats=f, reduction=red)
+
+
+class RcanB200:
+    DIV2K_MEAN = (0.4488, 0.4371, 0.4040)
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device, *, precision: str = "bf16x3",
+                 rgb_range: float = 1.0, norm: bool = False, conv_mode: int = 0):
+        assert precision in ("bf16x3", "bf16")
+        self.l = lib()
+        _declare(self.l)
+        self.device = device
+        self.planes = 2 if precision == "bf16x3" else 1
+        self.precision = precision
+        self.cfg = infer_config(state_dict)
+        self.rgb_range, self.norm, self.conv_mode = float(rgb_range), bool(norm), conv_mode
+        f = self.cfg["n_feats"]
+        if f != 64:
+            raise ValueError(f"RcanB200: n_feats={f} not supported (kernels are built for 64 feature channels)")
+        sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in state_dict.items()}
+        self.F = f
+        pl = self.planes
+
+        def conv_w(name):
+            return P.conv_weight_to_planes(sd[name + ".weight"], pl), P.pad_bias(sd.get(name + ".bias"), sd[name + ".weight"].shape[0])
+
+        self.w_head = conv_w("head.0")
+        G, R = self.cfg["n_resgroups"], self.cfg["n_resblocks"]
+        self.blocks = []
+        for g in range(G):
+            grp = []
+            for b in range(R):
+                base = f"body.{g}.body.{b}.body"
+                w1, w2 = conv_w(base + ".0"), conv_w(base + ".2")
+                cd1 = sd[base + ".3.conv_du.0.weight"].reshape(-1, f).contiguous()
+                cb1 = sd[base + ".3.conv_du.0.bias"].contiguous()
+                cd2 = sd[base + ".3.conv_du.2.weight"].reshape(f, -1).contiguous()
+                cb2 = sd[base + ".3.conv_du.2.bias"].contiguous()
+                grp.append((w1, w2, cd1, cb1, cd2, cb2))
+            self.blocks.append((grp, conv_w(f"body.{g}.body.{R}")))
+        self.w_body_tail = conv_w(f"body.{G}")
+        # upsampler conv: reorder output channels so the four PixelShuffle phases are contiguous 64-channel blocks
+        wu, bu = sd["tail.0.0.weight"], sd["tail.0.0.bias"]
+        idx = torch.arange(4 * f, device=device).view(f, 4).t().reshape(-1)   # new[(dy*2+dx)*f + c] = old[c*4 + dy*2+dx]
+        self.w_up = (P.conv_weight_to_planes(wu[idx], pl), P.pad_bias(bu[idx], 4 * f))
+        self.w_tail = conv_w("tail.1")
+        self._plans: Dict[Tuple[int, int], dict] = {}
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _build(self, h: int, w: int) -> dict:
+        dev, pl, f = self.device, self.planes, self.F
+        bf = torch.bfloat16
+        n = 1
+
+        def act(hh, ww, c=f):
+            return torch.zeros((pl, n, hh, ww, c), dtype=bf, device=dev)
+
+        b = dict(x_in=act(h, w), head=act(h, w), u=act(h, w), t=act(h, w), pa=act(h, w), pb=act(h, w),
+                 g0=act(h, w), g1=act(h, w), up=act(2 * h, 2 * w),
+                 out32=torch.zeros((n, 2 * h, 2 * w, 16), dtype=torch.float32, device=dev),
+                 scale=torch.zeros((n, f), dtype=torch.float32, device=dev))
+        steps = []
+        mode = self.conv_mode
+
+        def conv(x, wgt, out, **kw):
+            return ConvPlan(x, wgt[0], wgt[1], out, k=3, pad=1, mode=kw.pop("mode", mode), **kw)
+
+        # head conv: only 3 of the 64 padded input channels are non-zero (per-tap kernel)
+        steps.append(("conv", conv(b["x_in"], self.w_head, b["head"], mode=1)))
+        probe = conv(b["head"], self.blocks[0][0][0][0], b["u"], act="relu")
+        parts = probe.num_mtiles * 4
+        sums = torch.zeros((parts, f), dtype=torch.float32, device=dev)
+        b["sums"] = sums
+        src = b["head"]
+        for gi, (grp, tailw) in enumerate(self.blocks):
+            grp_in = src
+            x = grp_in
+            for (w1, w2, cd1, cb1, cd2, cb2) in grp:
+                steps.append(("conv", conv(x, w1, b["u"], act="relu")))
+                steps.append(("conv", conv(b["u"], w2, b["t"], tile_sums=sums)))
+                steps.append(("ca", (parts, cd1, cb1, cd2, cb2)))
+                dst = b["pa"] if x is not b["pa"] else b["pb"]
+                steps.append(("apply", (b["t"], x, dst)))     # RCAB: x + t * gate
+                x = dst
+            gout = b["g0"] if grp_in is not b["g0"] else b["g1"]
+            steps.append(("conv", conv(x, tailw, gout, residual=grp_in)))   # group tail conv + group skip
+            src = gout
+        steps.append(("conv", conv(src, self.w_body_tail, b["u"], residual=b["head"])))
+        steps.append(("conv", ConvPlan(b["u"], self.w_up[0], self.w_up[1], b["up"], k=3, pad=1, pixel_shuffle=True,
+                                       mode=1)))
+        steps.append(("conv", ConvPlan(b["up"], self.w_tail[0], self.w_tail[1], b["out32"], k=3, pad=1, mode=1)))
+        b["steps"] = steps
+        return b
+
+    def _get(self, h: int, w: int) -> dict:
+        key = (h, w)
+        if key not in self._plans:
+            self._plans[key] = self._build(h, w)
+        return self._plans[key]
+
+    def _run_body(self, b: dict, h: int, w: int) -> None:
+        l, st = self.l, stream_ptr()
+        f = self.F
+        inv_hw = 1.0 / float(h * w)
+        for kind, arg in b["steps"]:
+            if kind == "conv":
+                arg.run()
+            elif kind == "ca":
+                parts, cd1, cb1, cd2, cb2 = arg
+                check(l.mtb_ca_scale(ptr(b["sums"]), 1, parts, f, inv_hw, ptr(cd1), ptr(cb1), ptr(cd2), ptr(cb2),
+                                     cd1.shape[0], ptr(b["scale"]), st), "mtb_ca_scale")
+            else:
+                t, x, dst = arg
+                check(l.mtb_scale_residual(ptr(t), ptr(x), ptr(b["scale"]), ptr(dst), h * w, 1, f, st),
+                      "mtb_scale_residual")
+
+    def upscale_u8(self, img: torch.Tensor, *, swap_rb: bool = False, want_float: bool = False):
+        """img: device uint8 HxWx(3|4).  Returns uint8 2Hx2Wx3 (same channel order as the model's RGB output unless
+        swap_rb), and optionally the float output before quantisation (2Hx2Wx3)."""
+        assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_contiguous()
+        h, w, c = img.shape
+        b = self._get(h, w)
+        l, st = self.l, stream_ptr()
+        mean = [m * self.rgb_range for m in self.DIV2K_MEAN] if self.norm else [0.0, 0.0, 0.0]
+        sub = (C.c_float * 3)(*mean)
+        check(l.mtb_image_to_planes(ptr(img), h, w, c, int(swap_rb), self.rgb_range / 255.0, sub, ptr(b["x_in"]), 64,
+                                    self.planes, st), "mtb_image_to_planes")
+        self._run_body(b, h, w)
+        out = torch.empty((2 * h, 2 * w, 3), dtype=torch.uint8, device=self.device)
+        outf = torch.empty((2 * h, 2 * w, 3), dtype=torch.float32, device=self.device) if want_float else None
+        add = (C.c_float * 3)(*mean)
+        check(l.mtb_f32_to_u8(ptr(b["out32"]), 4 * h * w, 16, add, 1.0 / self.rgb_range, ptr(out), ptr(outf), st),
+              "mtb_f32_to_u8")
+        return (out, outf) if want_float else out
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """Reference call shape (core/image/image_utils.py:369-374): float32 (1,3,h,w) in [0,1] -> (1,3,2h,2w)."""
+        assert x.dim() == 4 and x.shape[0] == 1 and x.shape[1] == 3
+        h, w = x.shape[2], x.shape[3]
+        b = self._get(h, w)
+        xin = x.to(self.device, torch.float32) * self.rgb_range
+        if self.norm:
+            xin = xin - torch.tensor(self.DIV2K_MEAN, device=self.device).view(1, 3, 1, 1) * self.rgb_range
+        b["x_in"].copy_(P.nchw_to_planes(xin, self.planes))
+        self._run_body(b, h, w)
+        y = b["out32"][..., :3].permute(0, 3, 1, 2)
+        if self.norm:
+            y = y + torch.tensor(self.DIV2K_MEAN, device=self.device).view(1, 3, 1, 1) * self.rgb_range
+        return (y / self.rgb_range).contiguous()
