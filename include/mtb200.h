@@ -45,13 +45,16 @@ typedef struct mtb_conv_desc {
   int act;        /* 0 none, 1 relu, 2 silu, 3 gelu(erf), 4 sigmoid */
   int res_planes; /* planes of the residual tensor (0 = none) */
   int tile_w, tile_h; /* pixel tile (product 128); 0 = choose */
+  int x_ctotal, x_coff;     /* input tensor channel count (0 = Cin) and first channel read (concat slices) */
+  int out_ctotal, out_coff; /* output tensor channel count (0 = Cout) and first channel written */
+  int res_ctotal, res_coff; /* same for the residual tensor */
   int pixel_shuffle;  /* 1: fuse PixelShuffle(2) into the store (Cout = 4 blocks [dy*2+dx] of Cout/4 channels) */
   int mode;           /* 0 auto, 1 force the per-tap kernel, 2 require the halo-tile kernel (3x3 s1 p1, 64->64) */
 } mtb_conv_desc;
 
 typedef struct mtb_conv_plan mtb_conv_plan;
 
-/* x: bf16 [planes_in][N][H][W][Cin]; w: bf16 [planes_in][KH*KW][Cout][Cin]; bias: fp32 [Cout] or NULL;
+/* x: bf16 [planes_in][N][H][W][x_ctotal]; w: bf16 [planes_in][KH*KW][Cout][Cin]; bias: fp32 [Cout] or NULL;
  * out: bf16 [planes_out][N][Ho][Wo][Cout] (or fp32 [N][Ho][Wo][Cout]); residual: like out (res_planes) or NULL;
  * tile_sums: fp32 [mtb_conv_plan_num_mtiles()*4][Cout] or NULL (per-warp channel sums of the output). */
 int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, const float* bias, void* out,
@@ -142,9 +145,60 @@ int mtb_image_to_planes(const uint8_t* img, int H, int W, int cimg, int swap_rb,
 int mtb_ca_scale(const float* sums, int n_images, int parts_per_image, int C, float inv_hw, const float* w1,
                  const float* b1, const float* w2, const float* b2, int R, float* scale_out, void* stream);
 int mtb_scale_residual(const void* t, const void* x, const float* scale, void* y, long long pix_per_image, int N, int C,
-                       void* stream);
+                       int planes, void* stream);
 int mtb_f32_to_u8(const float* in, long long npix, int cpad, const float* add3 /* host */, float mul, uint8_t* out,
                   float* out_f /* optional float copy [npix][3] */, void* stream);
+
+/* ---- detection glue ---------------------------------------------------------------------------------------
+ * maxpool / upsample2x : SPPF and FPN ops of the YOLO graph on channel slices of NHWC plane tensors
+ * yolo_decode          : ultralytics Segment head decode (DFL + sigmoid) + confidence filter
+ *                        (reference call: core/image/detection.py:1338-1345)
+ * nms                  : ultralytics non_max_suppression + scale_boxes, then the reference's own
+ *                        _deduplicate_primary_boxes / _remove_contained_boxes (core/image/detection.py:219-295)
+ */
+int mtb_maxpool(const void* x, void* y, int N, int H, int W, int ct_in, int ci, int ct_out, int co, int c, int k,
+                int planes, void* stream);
+int mtb_upsample2x(const void* x, void* y, int N, int H, int W, int ct_in, int ci, int ct_out, int co, int c, int planes,
+                   void* stream);
+
+typedef struct mtb_yolo_level {
+  const float* box; /* device fp32 [N][H][W][64] DFL logits */
+  const float* cls; /* device fp32 [N][H][W][ncp] class logits */
+  int H, W, stride, reserved;
+} mtb_yolo_level;
+
+/* cand: [N][max_cand][6] (x1,y1,x2,y2 in letterboxed px, score, class); count: [N] */
+int mtb_yolo_decode(const mtb_yolo_level* levels /* host */, int n_levels, int N, int nc, int ncp, float conf,
+                    int max_cand, float* cand, int* cand_anchor, int* count, void* stream);
+
+typedef struct mtb_nms_params {
+  int N, max_cand, max_det;
+  float iou_thr, max_wh;
+  float gain; /* letterbox gain (scale_boxes) */
+  int pad_x, pad_y, img_w, img_h;
+  double dedup_iou, contain_ioa;
+  int apply_dedup;
+} mtb_nms_params;
+
+/* out_det: [N][max_det][8] (x1,y1,x2,y2 original px, score, class, anchor, kept-by-reference-logic);
+ * out_count: [N][2] (after NMS, after dedup+containment); final_idx: [N][max_det] rows of out_det kept, in the
+ * reference's order */
+int mtb_nms(const mtb_nms_params* p /* host */, const float* cand, const int* cand_anchor, const int* count,
+            int* order_ws /* [N][max_cand] */, unsigned char* dead_ws /* [N][max_cand] */, float* out_det,
+            int* out_count, int* final_idx, void* stream);
+
+/* ---- input pre-processing, bit-exact with the CPU libraries the reference calls ----------------------------
+ * letterbox_u8 : ultralytics LetterBox (cv2.resize INTER_LINEAR on uint8 + 114 border + BGR->RGB), detection.py:1338-1345
+ * resize_aa_u8 : Sam2ImageProcessorFast resize (torchvision bilinear, antialias=True, uint8), detection.py:494-495
+ */
+int mtb_letterbox_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* dst /* dh x dw x 3 */, int dh, int dw, int top,
+                     int left, int nh, int nw, int pad_value, int swap_rb, int* tables_dev /* >= 3*(nw+nh) ints */,
+                     void* stream);
+/* host-only: int16 antialias weight table of one axis (what resize_aa_u8 uploads); used by the CPU tests */
+int mtb_aa_weights_host(int in_size, int out_size, int* start, int* len, short* weights, int kmax_cap, int* kmax,
+                        int* prec);
+int mtb_resize_aa_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp /* sh x ow x 3 */,
+                     uint8_t* dst /* oh x ow x 3 */, int oh, int ow, int* tables_dev, long long tables_ints, void* stream);
 
 #ifdef __cplusplus
 }

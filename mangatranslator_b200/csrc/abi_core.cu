@@ -98,6 +98,10 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
   MTB_REQUIRE(d->res_planes >= 0 && d->res_planes <= 2, "conv: res_planes must be 0..2");
   MTB_REQUIRE((d->res_planes == 0) == (residual == nullptr), "conv: residual pointer / res_planes mismatch");
   MTB_REQUIRE(!(d->planes_out == 4 && residual), "conv: fp32 output with residual is not supported");
+  MTB_REQUIRE((d->x_ctotal == 0 || d->x_ctotal % 8 == 0) && d->x_coff % 8 == 0 && d->out_coff % 8 == 0 &&
+                  d->res_coff % 8 == 0 && (d->out_ctotal == 0 || d->out_ctotal % 8 == 0) &&
+                  (d->res_ctotal == 0 || d->res_ctotal % 8 == 0),
+              "conv: channel totals / offsets must be multiples of 8 (16-byte rows)");
 
   mtb_conv_plan* pl = new (std::nothrow) mtb_conv_plan();
   MTB_REQUIRE(pl != nullptr, "conv: out of host memory");
@@ -143,8 +147,13 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
   }
   p.planes_out = d->planes_out == 4 ? 1 : d->planes_out;
   p.act = d->act;
-  p.out_plane_stride = static_cast<long long>(p.N) * p.Ho * p.Wo * p.Cout;
-  p.res_plane_stride = p.out_plane_stride;
+  p.in_coff = d->x_coff;
+  p.out_cstride = d->out_ctotal > 0 ? d->out_ctotal : d->Cout;
+  p.out_coff = d->out_coff;
+  p.res_cstride = d->res_ctotal > 0 ? d->res_ctotal : d->Cout;
+  p.res_coff = d->res_coff;
+  p.out_plane_stride = static_cast<long long>(p.N) * p.Ho * p.Wo * p.out_cstride;
+  p.res_plane_stride = static_cast<long long>(p.N) * p.Ho * p.Wo * p.res_cstride;
   p.res_planes = d->res_planes;
   p.bias = bias;
   if (d->planes_out == 4) {
@@ -188,10 +197,10 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
 
   // activations: [planes*N][H][W][Cin] bf16
   {
-    const uint64_t dims[4] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+    const uint64_t xc = static_cast<uint64_t>(d->x_ctotal > 0 ? d->x_ctotal : d->Cin);
+    const uint64_t dims[4] = {xc, static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
                               static_cast<uint64_t>(d->N) * d->planes_in};
-    const uint64_t strides[3] = {static_cast<uint64_t>(d->Cin) * 2, static_cast<uint64_t>(d->W) * d->Cin * 2,
-                                 static_cast<uint64_t>(d->H) * d->W * d->Cin * 2};
+    const uint64_t strides[3] = {xc * 2, static_cast<uint64_t>(d->W) * xc * 2, static_cast<uint64_t>(d->H) * d->W * xc * 2};
     uint32_t box[4] = {64, static_cast<uint32_t>(p.TW * d->stride), static_cast<uint32_t>(p.TH * d->stride), 1};
     if (pl->halo) {
       box[1] = static_cast<uint32_t>(p.TW + 2);

@@ -1,24 +1,15 @@
 // tcgen05 implicit-GEMM convolution kernel (see conv_gemm.cuh for the design).
 #include "conv_gemm.cuh"
+#include "epilogue.cuh"
 
 namespace mtb {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = kConvThreads;
 constexpr int kTileM = 128;         // pixels per tile == TMEM lanes
 constexpr int kChunkBytes = 128;    // 64 bf16 channels == one 128B swizzle row
 constexpr int kATileBytes = kTileM * kChunkBytes;
-
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case ACT_RELU: return fmaxf(v, 0.0f);
-    case ACT_SILU: return v / (1.0f + expf(-v));
-    case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-    case ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
-    default: return v;
-  }
-}
 
 struct TileCoord {
   int n, y0, x0, tyi, txi, nt;
@@ -37,7 +28,7 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const ConvParams& p) 
   return t;
 }
 
-template <int NSPLIT>
+template <int NSPLIT, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvParams p) {
@@ -65,7 +56,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -107,7 +98,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int yi = t.y0 * p.stride + ky - p.pad;
 #pragma unroll
           for (int pl = 0; pl < PLANES; ++pl) {
-            tma_load_4d(sa + pl * kATileBytes, &tmA, &full_bar[stage], cc * 64, xi, yi, pl * p.N + t.n);
+            tma_load_4d(sa + pl * kATileBytes, &tmA, &full_bar[stage], p.in_coff + cc * 64, xi, yi, pl * p.N + t.n);
           }
 #pragma unroll
           for (int pl = 0; pl < PLANES; ++pl) {
@@ -165,8 +156,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------- epilogue (warps 2..5) -------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------- epilogue (warps 2..17) -------------------------------
+    // warp w may touch TMEM lanes [32*(w%4), +32); the four warps of a lane quarter split the channel chunks
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int ty = r / p.TW;
     const int tx = r - ty * p.TW;
@@ -179,101 +172,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int ox = t.x0 + tx;
       const bool valid = (oy < p.Ho) && (ox < p.Wo);
       const long long pix = (static_cast<long long>(t.n) * p.Ho + oy) * p.Wo + ox;
+      const long long mtile = (static_cast<long long>(t.n) * p.tiles_y + t.tyi) * p.tiles_x + t.txi;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.BN);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      for (int c0 = cg * 16; c0 < p.BN; c0 += 64) {
         uint32_t acc[16];
         tmem_ld16(taddr + c0, acc);
         tmem_ld_wait();
         float v[16];
-        const int cbase = n0 + c0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = __uint_as_float(acc[j]);
-          if (p.bias) x += __ldg(p.bias + cbase + j);
-          v[j] = apply_act(x, p.act);
-        }
-        if (p.residual && valid) {
-          const uint16_t* rp = p.residual + pix * p.Cout + cbase;
-          for (int pl = 0; pl < p.res_planes; ++pl) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(rp + pl * p.res_plane_stride);
-            uint4 a = __ldg(r4), b = __ldg(r4 + 1);
-            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[2 * j] += bf16_to_f(static_cast<uint16_t>(w[j] & 0xFFFF));
-              v[2 * j + 1] += bf16_to_f(static_cast<uint16_t>(w[j] >> 16));
-            }
-          }
-        }
-        if (!valid) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.0f;
-        }
-        if (p.tile_sums) {
-          // channel sums over the warp's 32 pixels: 16 values x 32 lanes -> lanes 0..15 hold channel sums
-          float s[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) s[j] = v[j];
-          // fold lanes 16..31 onto 0..15
-#pragma unroll
-          for (int j = 0; j < 16; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
-          // transpose-reduce across the remaining 16 lanes: 8+4+2+1 exchanges
-#pragma unroll
-          for (int w = 8; w >= 1; w >>= 1) {
-            const bool upper = (lane & w) != 0;
-#pragma unroll
-            for (int j = 0; j < w; ++j) {
-              const float send = upper ? s[j] : s[j + w];
-              const float keep = upper ? s[j + w] : s[j];
-              s[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-            }
-          }
-          // lane l (< 16) now holds the sum for channel index bitrev-free mapping: channel = l's bits select halves
-          // channel owned by lane l: at step w the lane kept the upper half iff (l & w) -> channel = l & 15
-          if (lane < 16) {
-            const long long mt = (static_cast<long long>(t.n) * p.tiles_y + t.tyi) * p.tiles_x + t.txi;
-            p.tile_sums[(mt * 4 + q) * p.Cout + cbase + lane] = s[0];
-          }
-        }
-        if (valid) {
-          if (p.out_f32) {
-            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + pix * p.Cout + cbase);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint16_t h0, l0, h1, l1;
-              split_bf16(v[2 * j], h0, l0);
-              split_bf16(v[2 * j + 1], h1, l1);
-              hi[j] = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
-              lo[j] = static_cast<uint32_t>(l0) | (static_cast<uint32_t>(l1) << 16);
-            }
-            long long off = pix * p.Cout + cbase;
-            if (p.pixel_shuffle) {
-              // PixelShuffle(2) fused into the store: channel block b = dy*2+dx lands on the 2x finer grid
-              const int cq = p.Cout >> 2;
-              const int blk = cbase / cq, cc = cbase - blk * cq;
-              const long long hp = (static_cast<long long>(t.n) * (2 * p.Ho) + 2 * oy + (blk >> 1)) * (2 * p.Wo) +
-                                   2 * ox + (blk & 1);
-              off = hp * cq + cc;
-            }
-            uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
-            o4[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            o4[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            if (p.planes_out == 2) {
-              uint4* l4 = reinterpret_cast<uint4*>(p.out + p.out_plane_stride + off);
-              l4[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              l4[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            }
-          }
-        }
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+        epilogue_chunk16<ACT>(p, v, valid, pix, n0 + c0, t.n, oy, ox, lane, q, mtile);
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -309,15 +223,28 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvP
   const long long total = static_cast<long long>(p.N) * p.tiles_y * p.tiles_x * p.n_tiles_n;
   const int grid = static_cast<int>(total < sms ? total : sms);
   if (grid <= 0) return 0;
+#define MTB_LAUNCH_GEMM(NS, ACT)                                                                              \
+  do {                                                                                                        \
+    MTB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<NS, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     static_cast<int>(smem)));                                                \
+    conv_gemm_kernel<NS, ACT><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);                                 \
+  } while (0)
   if (nsplit == 3) {
-    MTB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-    conv_gemm_kernel<3><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+    switch (p.act) {
+      case ACT_NONE: MTB_LAUNCH_GEMM(3, ACT_NONE); break;
+      case ACT_RELU: MTB_LAUNCH_GEMM(3, ACT_RELU); break;
+      case ACT_SILU: MTB_LAUNCH_GEMM(3, ACT_SILU); break;
+      default: MTB_LAUNCH_GEMM(3, -1); break;
+    }
   } else {
-    MTB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-    conv_gemm_kernel<1><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+    switch (p.act) {
+      case ACT_NONE: MTB_LAUNCH_GEMM(1, ACT_NONE); break;
+      case ACT_RELU: MTB_LAUNCH_GEMM(1, ACT_RELU); break;
+      case ACT_SILU: MTB_LAUNCH_GEMM(1, ACT_SILU); break;
+      default: MTB_LAUNCH_GEMM(1, -1); break;
+    }
   }
+#undef MTB_LAUNCH_GEMM
   MTB_CUDA_OK(cudaGetLastError());
   return 0;
 }

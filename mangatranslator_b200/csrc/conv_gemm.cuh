@@ -43,6 +43,9 @@ struct ConvParams {
   float* out_f32;              // optional fp32 output [N][Ho][Wo][Cout]
   const uint16_t* residual;    // optional, same geometry as out, added after the activation
   float* tile_sums;            // optional [N*tiles_y*tiles_x][4][Cout] per-warp channel sums of the output
+  int in_coff;                 // first input channel inside the (wider) input tensor
+  int out_cstride, out_coff;   // channel count of the output tensor and first channel written (concat slices)
+  int res_cstride, res_coff;   // same for the residual tensor
   int pixel_shuffle;           // 1: Cout = 4 blocks of Cout/4 channels, block (dy*2+dx) is stored at pixel (2y+dy, 2x+dx)
 };
 

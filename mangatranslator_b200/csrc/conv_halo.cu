@@ -15,12 +15,13 @@
 //   * ring of 3 shared-memory slots, one (tile, plane) halo per slot, so the next tile's hi plane streams in while the
 //     current tile's lo plane is being multiplied; 2 TMEM accumulator stages overlap the epilogue with the next tile.
 #include "conv_gemm.cuh"
+#include "epilogue.cuh"
 
 namespace mtb {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = kConvThreads;
 constexpr int kTW = 8, kTH = 16;                    // output tile (pixels)
 constexpr int kHW = kTW + 2, kHH = kTH + 2;         // halo tile
 constexpr int kHaloBytes = kHW * kHH * 128;         // 23040
@@ -29,18 +30,8 @@ constexpr int kSlots = 3;
 constexpr int kTapBytes = 128 * 128;                // [W_hi(64 rows) ; W_lo(64 rows)] x 128 B
 constexpr int kWBytes = 9 * kTapBytes;              // 147456
 
-__device__ __forceinline__ float act_fn(float v, int act) {
-  switch (act) {
-    case ACT_RELU: return fmaxf(v, 0.0f);
-    case ACT_SILU: return v / (1.0f + expf(-v));
-    case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-    case ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
-    default: return v;
-  }
-}
-
 // PLANES == 2: bf16x3 (fp32-grade);  PLANES == 1: plain bf16
-template <int PLANES>
+template <int PLANES, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const ConvParams p) {
@@ -66,7 +57,7 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     mbar_init(w_bar, 1);
     fence_barrier_init();
@@ -159,9 +150,12 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
     }
   } else {
+    // 16 epilogue warps: lane quarter q = warp % 4, channel chunk cg = (warp - 2) / 4 (16 channels each)
     const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int ty = r >> 3, tx = r & 7;
+    const int c0 = cg * 16;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -174,83 +168,25 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * ACC_COLS);
-#pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        uint32_t acc[16];
-        float v[16];
-        tmem_ld16(taddr + c0, acc);
-        if (PLANES == 2) {
-          uint32_t acc2[16];
-          tmem_ld16(taddr + 64 + c0, acc2);
-          tmem_ld_wait();
+      uint32_t acc[16];
+      float v[16];
+      tmem_ld16(taddr + c0, acc);
+      if (PLANES == 2) {
+        uint32_t acc2[16];
+        tmem_ld16(taddr + 64 + c0, acc2);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) + __uint_as_float(acc2[j]);
-        } else {
-          tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) + __uint_as_float(acc2[j]);
+      } else {
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = v[j];
-          if (p.bias) x += __ldg(p.bias + c0 + j);
-          v[j] = act_fn(x, p.act);
-        }
-        if (p.residual && valid) {
-          const uint16_t* rp = p.residual + pix * 64 + c0;
-          for (int pl = 0; pl < p.res_planes; ++pl) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(rp + pl * p.res_plane_stride);
-            const uint4 a = __ldg(r4), b = __ldg(r4 + 1);
-            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[2 * j] += bf16_to_f(static_cast<uint16_t>(w[j] & 0xFFFF));
-              v[2 * j + 1] += bf16_to_f(static_cast<uint16_t>(w[j] >> 16));
-            }
-          }
-        }
-        if (!valid) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.0f;
-        }
-        if (p.tile_sums) {
-          float s[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) s[j] = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 16);
-#pragma unroll
-          for (int w = 8; w >= 1; w >>= 1) {
-            const bool upper = (lane & w) != 0;
-#pragma unroll
-            for (int j = 0; j < w; ++j) {
-              const float send = upper ? s[j] : s[j + w];
-              const float keep = upper ? s[j + w] : s[j];
-              s[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-            }
-          }
-          if (lane < 16) p.tile_sums[(static_cast<long long>(tile) * 4 + q) * 64 + c0 + lane] = s[0];
-        }
-        if (valid) {
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint16_t h0, l0, h1, l1;
-            split_bf16(v[2 * j], h0, l0);
-            split_bf16(v[2 * j + 1], h1, l1);
-            hi[j] = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
-            lo[j] = static_cast<uint32_t>(l0) | (static_cast<uint32_t>(l1) << 16);
-          }
-          uint4* o4 = reinterpret_cast<uint4*>(p.out + pix * 64 + c0);
-          o4[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          o4[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          if (p.planes_out == 2) {
-            uint4* l4 = reinterpret_cast<uint4*>(p.out + p.out_plane_stride + pix * 64 + c0);
-            l4[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            l4[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          }
-        }
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
       }
+      // the accumulator values are in registers: release the TMEM stage before the (long) store path
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      epilogue_chunk16<ACT>(p, v, valid, pix, c0, n, oy, ox, lane, q, tile);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -268,7 +204,8 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
 bool conv_halo_eligible(const ConvParams& p, int cin) {
   return p.KH == 3 && p.KW == 3 && p.stride == 1 && p.pad == 1 && cin == 64 && p.Cout == 64 && p.out != nullptr &&
-         p.Ho > 1;
+         p.Ho > 1 && p.in_coff == 0 && p.out_coff == 0 && p.out_cstride == 64 &&
+         (p.residual == nullptr || (p.res_coff == 0 && p.res_cstride == 64)) && !p.pixel_shuffle;
 }
 
 int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int nsplit,
@@ -280,15 +217,26 @@ int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvP
   const long long total = static_cast<long long>(p.N) * p.tiles_y * p.tiles_x;
   const int grid = static_cast<int>(total < sms ? total : sms);
   if (grid <= 0) return 0;
+#define MTB_LAUNCH_HALO(PL, ACT)                                                                                    \
+  do {                                                                                                              \
+    MTB_CUDA_OK(cudaFuncSetAttribute(conv3x3_c64_halo_kernel<PL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     static_cast<int>(smem)));                                                      \
+    conv3x3_c64_halo_kernel<PL, ACT><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);                                \
+  } while (0)
   if (nsplit == 3) {
-    MTB_CUDA_OK(cudaFuncSetAttribute(conv3x3_c64_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-    conv3x3_c64_halo_kernel<2><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+    switch (p.act) {
+      case ACT_NONE: MTB_LAUNCH_HALO(2, ACT_NONE); break;
+      case ACT_RELU: MTB_LAUNCH_HALO(2, ACT_RELU); break;
+      default: MTB_LAUNCH_HALO(2, -1); break;
+    }
   } else {
-    MTB_CUDA_OK(cudaFuncSetAttribute(conv3x3_c64_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-    conv3x3_c64_halo_kernel<1><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+    switch (p.act) {
+      case ACT_NONE: MTB_LAUNCH_HALO(1, ACT_NONE); break;
+      case ACT_RELU: MTB_LAUNCH_HALO(1, ACT_RELU); break;
+      default: MTB_LAUNCH_HALO(1, -1); break;
+    }
   }
+#undef MTB_LAUNCH_HALO
   MTB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -104,7 +104,7 @@ __global__ void ca_scale_kernel(const float* __restrict__ sums, int parts, int C
 // y = x + t * scale[n][c]   (all hi/lo planes, NHWC, C multiple of 8)
 __global__ void scale_residual_kernel(const uint16_t* __restrict__ t, const uint16_t* __restrict__ x,
                                       const float* __restrict__ scale, uint16_t* __restrict__ y,
-                                      long long plane_stride, long long pix_per_image, int N, int C) {
+                                      long long plane_stride, long long pix_per_image, int N, int C, int planes) {
   const int vec_per_pix = C / 8;
   const long long total = pix_per_image * N * vec_per_pix;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -114,9 +114,10 @@ __global__ void scale_residual_kernel(const uint16_t* __restrict__ t, const uint
     const int n = static_cast<int>(pix / pix_per_image);
     const long long off = pix * C + v * 8;
     const uint4 th = *reinterpret_cast<const uint4*>(t + off);
-    const uint4 tl = *reinterpret_cast<const uint4*>(t + plane_stride + off);
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    const uint4 tl = planes == 2 ? *reinterpret_cast<const uint4*>(t + plane_stride + off) : zero4;
     const uint4 xh = *reinterpret_cast<const uint4*>(x + off);
-    const uint4 xl = *reinterpret_cast<const uint4*>(x + plane_stride + off);
+    const uint4 xl = planes == 2 ? *reinterpret_cast<const uint4*>(x + plane_stride + off) : zero4;
     const uint32_t thw[4] = {th.x, th.y, th.z, th.w}, tlw[4] = {tl.x, tl.y, tl.z, tl.w};
     const uint32_t xhw[4] = {xh.x, xh.y, xh.z, xh.w}, xlw[4] = {xl.x, xl.y, xl.z, xl.w};
     const float* sc = scale + n * C + v * 8;
@@ -136,7 +137,7 @@ __global__ void scale_residual_kernel(const uint16_t* __restrict__ t, const uint
       ol[j] = l0 | (static_cast<uint32_t>(l1) << 16);
     }
     *reinterpret_cast<uint4*>(y + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-    *reinterpret_cast<uint4*>(y + plane_stride + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    if (planes == 2) *reinterpret_cast<uint4*>(y + plane_stride + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
   }
 }
 
@@ -191,12 +192,12 @@ int mtb_ca_scale(const float* sums, int n_images, int parts_per_image, int C, fl
 }
 
 int mtb_scale_residual(const void* t, const void* x, const float* scale, void* y, long long pix_per_image, int N, int C,
-                       void* stream) {
-  MTB_REQUIRE(t && x && scale && y && C % 8 == 0, "mtb_scale_residual: bad arguments");
+                       int planes, void* stream) {
+  MTB_REQUIRE(t && x && scale && y && C % 8 == 0 && (planes == 1 || planes == 2), "mtb_scale_residual: bad arguments");
   const long long total = pix_per_image * N * (C / 8);
   scale_residual_kernel<<<grid_for(total, 256, sm_count()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint16_t*>(t), static_cast<const uint16_t*>(x), scale, static_cast<uint16_t*>(y),
-      pix_per_image * N * C, pix_per_image, N, C);
+      pix_per_image * N * C, pix_per_image, N, C, planes);
   MTB_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -1,0 +1,293 @@
+// Input pre-processing on the device, bit-exact with the CPU libraries the reference goes through:
+//   * mtb_letterbox_u8 : ultralytics LetterBox = cv2.resize(INTER_LINEAR) on uint8 (OpenCV's 11-bit fixed-point
+//     bilinear: horizontal pass with short coefficients, vertical pass `(((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2`)
+//     + constant 114 border + BGR->RGB                       (reference call: core/image/detection.py:1338-1345)
+//   * mtb_resize_aa_u8 : torchvision/ATen bilinear antialias resize of a uint8 image (Sam2ImageProcessorFast), i.e.
+//     Pillow-style separable resampling with int16 weights and a uint8 intermediate
+//                                                             (reference call: core/image/detection.py:494-495)
+#include <math.h>
+
+#include <atomic>
+#include <vector>
+
+#include "../../include/mtb200.h"
+#include "common.cuh"
+
+namespace mtb {
+extern std::atomic<long long> g_launches;
+}
+using namespace mtb;
+
+namespace {
+
+// dst[(top+dy), (left+dx)] = cv2-bilinear(src); everything else = pad value
+__global__ void letterbox_kernel(const uint8_t* __restrict__ src, int sh, int sw, int sc, uint8_t* __restrict__ dst,
+                                 int dh, int dw, int top, int left, int nh, int nw, int pad_value, int swap_rb,
+                                 const int* __restrict__ xofs, const short* __restrict__ xa,
+                                 const int* __restrict__ yofs, const short* __restrict__ ya) {
+  const long long total = static_cast<long long>(dh) * dw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int oy = static_cast<int>(i / dw), ox = static_cast<int>(i - static_cast<long long>(oy) * dw);
+    uint8_t* o = dst + i * 3;
+    const int ry = oy - top, rx = ox - left;
+    if (ry < 0 || ry >= nh || rx < 0 || rx >= nw) {
+      o[0] = o[1] = o[2] = static_cast<uint8_t>(pad_value);
+      continue;
+    }
+    const int sx = xofs[rx], a0 = xa[2 * rx], a1 = xa[2 * rx + 1];
+    const int sx1 = sx + 1 < sw ? sx + 1 : sw - 1;
+    const int sy0 = yofs[2 * ry], sy1 = yofs[2 * ry + 1], b0 = ya[2 * ry], b1 = ya[2 * ry + 1];
+    const uint8_t* r0 = src + static_cast<long long>(sy0) * sw * sc;
+    const uint8_t* r1 = src + static_cast<long long>(sy1) * sw * sc;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int h0 = r0[sx * sc + c] * a0 + r0[sx1 * sc + c] * a1;
+      const int h1 = r1[sx * sc + c] * a0 + r1[sx1 * sc + c] * a1;
+      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      o[swap_rb ? 2 - c : c] = static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+  }
+}
+
+__global__ void copy_pad_kernel(const uint8_t* __restrict__ src, int sh, int sw, int sc, uint8_t* __restrict__ dst, int dh,
+                                int dw, int top, int left, int pad_value, int swap_rb) {
+  const long long total = static_cast<long long>(dh) * dw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int oy = static_cast<int>(i / dw), ox = static_cast<int>(i - static_cast<long long>(oy) * dw);
+    uint8_t* o = dst + i * 3;
+    const int ry = oy - top, rx = ox - left;
+    if (ry < 0 || ry >= sh || rx < 0 || rx >= sw) {
+      o[0] = o[1] = o[2] = static_cast<uint8_t>(pad_value);
+      continue;
+    }
+    const uint8_t* s = src + (static_cast<long long>(ry) * sw + rx) * sc;
+    o[0] = s[swap_rb ? 2 : 0];
+    o[1] = s[1];
+    o[2] = s[swap_rb ? 0 : 2];
+  }
+}
+
+int cv_round_f(float v) { return static_cast<int>(lrintf(v)); }  // round half to even (default FP mode)
+
+short sat_short(int v) { return static_cast<short>(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
+
+// separable antialiased resample of one axis: out[o] = clip8((half + sum_k w[o][k] * in[start[o] + k]) >> prec)
+__global__ void resample_axis_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int out_h, int out_w,
+                                     int in_w_stride /* pixels per src row */, int c_in, int c_out, int horizontal,
+                                     const int* __restrict__ start, const int* __restrict__ len,
+                                     const short* __restrict__ wts, int kmax, int prec) {
+  const long long total = static_cast<long long>(out_h) * out_w;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int oy = static_cast<int>(i / out_w), ox = static_cast<int>(i - static_cast<long long>(oy) * out_w);
+    const int o = horizontal ? ox : oy;
+    const int s0 = start[o], n = len[o];
+    const short* w = wts + static_cast<long long>(o) * kmax;
+    int acc[3] = {1 << (prec - 1), 1 << (prec - 1), 1 << (prec - 1)};
+    for (int k = 0; k < n; ++k) {
+      const uint8_t* px = horizontal ? src + (static_cast<long long>(oy) * in_w_stride + s0 + k) * c_in
+                                     : src + (static_cast<long long>(s0 + k) * in_w_stride + ox) * c_in;
+      const int wk = w[k];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] += wk * px[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int v = acc[c] >> prec;
+      dst[i * c_out + c] = static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+  }
+}
+
+// ATen `_compute_indices_int16_weights_aa` for the bilinear (triangle) filter with antialias
+void aa_weights(int in_size, int out_size, std::vector<int>& start, std::vector<int>& len, std::vector<short>& w16,
+                int& kmax, int& prec) {
+  const double scale = static_cast<double>(in_size) / out_size;
+  const double support = scale >= 1.0 ? 1.0 * scale : 1.0;
+  const int ksize = static_cast<int>(ceil(support)) * 2 + 1;
+  kmax = ksize;
+  std::vector<double> wd(static_cast<size_t>(out_size) * ksize, 0.0);
+  start.assign(out_size, 0);
+  len.assign(out_size, 0);
+  double wmax = 0.0;
+  const double invscale = scale >= 1.0 ? 1.0 / scale : 1.0;
+  for (int i = 0; i < out_size; ++i) {
+    const double center = scale * (i + 0.5);
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    const int n = xmax - xmin;
+    double total = 0.0;
+    for (int j = 0; j < n; ++j) {
+      double x = (j + xmin - center + 0.5) * invscale;
+      if (x < 0) x = -x;
+      const double v = x < 1.0 ? 1.0 - x : 0.0;
+      wd[static_cast<size_t>(i) * ksize + j] = v;
+      total += v;
+    }
+    for (int j = 0; j < n; ++j) {
+      if (total != 0.0) wd[static_cast<size_t>(i) * ksize + j] /= total;
+      if (wd[static_cast<size_t>(i) * ksize + j] > wmax) wmax = wd[static_cast<size_t>(i) * ksize + j];
+    }
+    start[i] = xmin;
+    len[i] = n;
+  }
+  prec = 0;
+  for (prec = 0; prec < 22; ++prec) {
+    const int next = static_cast<int>(0.5 + wmax * (1 << (prec + 1)));
+    if (next >= (1 << 15)) break;
+  }
+  w16.assign(static_cast<size_t>(out_size) * ksize, 0);
+  for (int i = 0; i < out_size; ++i)
+    for (int j = 0; j < len[i]; ++j) {
+      const double v = wd[static_cast<size_t>(i) * ksize + j];
+      w16[static_cast<size_t>(i) * ksize + j] =
+          static_cast<short>(v < 0 ? static_cast<int>(-0.5 + v * (1 << prec)) : static_cast<int>(0.5 + v * (1 << prec)));
+    }
+}
+
+int sm_count3() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+}  // namespace
+
+extern "C" {
+
+// host-only helper exported for the CPU tests: the int16 antialias weight tables of one axis
+int mtb_aa_weights_host(int in_size, int out_size, int* start /* [out] */, int* len /* [out] */,
+                        short* weights /* [out][kmax_cap] */, int kmax_cap, int* kmax, int* prec) {
+  std::vector<int> s, l;
+  std::vector<short> w;
+  int k = 0, p = 0;
+  aa_weights(in_size, out_size, s, l, w, k, p);
+  MTB_REQUIRE(k <= kmax_cap, "mtb_aa_weights_host: kmax %d > capacity %d", k, kmax_cap);
+  for (int i = 0; i < out_size; ++i) {
+    start[i] = s[i];
+    len[i] = l[i];
+    for (int j = 0; j < k; ++j) weights[static_cast<size_t>(i) * kmax_cap + j] = w[static_cast<size_t>(i) * k + j];
+  }
+  *kmax = k;
+  *prec = p;
+  return 0;
+}
+
+// tables: device scratch of at least 3*(nw + nh) ints (used as int / short tables), filled by this call
+int mtb_letterbox_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* dst, int dh, int dw, int top, int left, int nh,
+                     int nw, int pad_value, int swap_rb, int* tables_dev, void* stream) {
+  MTB_REQUIRE(src && dst && tables_dev && (sc == 3 || sc == 4), "mtb_letterbox_u8: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = sm_count3() * 8;
+  if (nh == sh && nw == sw) {
+    copy_pad_kernel<<<grid, 256, 0, st>>>(src, sh, sw, sc, dst, dh, dw, top, left, pad_value, swap_rb);
+    MTB_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+  }
+  // coefficient tables exactly as cv::resize builds them (resize.cpp, INTER_LINEAR, 8-bit)
+  std::vector<int> xofs(nw), yofs(2 * nh);
+  std::vector<short> xa(2 * nw), ya(2 * nh);
+  const double scale_x = 1.0 / (static_cast<double>(nw) / sw), scale_y = 1.0 / (static_cast<double>(nh) / sh);
+  for (int dx = 0; dx < nw; ++dx) {
+    float fx = static_cast<float>((dx + 0.5) * scale_x - 0.5);
+    int sx = static_cast<int>(floorf(fx));
+    fx -= sx;
+    if (sx < 0) {
+      fx = 0;
+      sx = 0;
+    }
+    if (sx >= sw - 1) {
+      fx = 0;
+      sx = sw - 1;
+    }
+    xofs[dx] = sx;
+    xa[2 * dx] = sat_short(cv_round_f((1.f - fx) * 2048.f));
+    xa[2 * dx + 1] = sat_short(cv_round_f(fx * 2048.f));
+  }
+  for (int dy = 0; dy < nh; ++dy) {
+    float fy = static_cast<float>((dy + 0.5) * scale_y - 0.5);
+    int sy = static_cast<int>(floorf(fy));
+    fy -= sy;
+    const int s0 = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);
+    const int s1 = sy + 1 < 0 ? 0 : (sy + 1 > sh - 1 ? sh - 1 : sy + 1);
+    yofs[2 * dy] = s0;
+    yofs[2 * dy + 1] = s1;
+    ya[2 * dy] = sat_short(cv_round_f((1.f - fy) * 2048.f));
+    ya[2 * dy + 1] = sat_short(cv_round_f(fy * 2048.f));
+  }
+  int* d_xofs = tables_dev;
+  int* d_yofs = d_xofs + nw;
+  short* d_xa = reinterpret_cast<short*>(d_yofs + 2 * nh);
+  short* d_ya = d_xa + 2 * nw;
+  MTB_CUDA_OK(cudaMemcpyAsync(d_xofs, xofs.data(), sizeof(int) * nw, cudaMemcpyHostToDevice, st));
+  MTB_CUDA_OK(cudaMemcpyAsync(d_yofs, yofs.data(), sizeof(int) * 2 * nh, cudaMemcpyHostToDevice, st));
+  MTB_CUDA_OK(cudaMemcpyAsync(d_xa, xa.data(), sizeof(short) * 2 * nw, cudaMemcpyHostToDevice, st));
+  MTB_CUDA_OK(cudaMemcpyAsync(d_ya, ya.data(), sizeof(short) * 2 * nh, cudaMemcpyHostToDevice, st));
+  MTB_CUDA_OK(cudaStreamSynchronize(st));  // the host tables go out of scope
+  letterbox_kernel<<<grid, 256, 0, st>>>(src, sh, sw, sc, dst, dh, dw, top, left, nh, nw, pad_value, swap_rb, d_xofs,
+                                         d_xa, d_yofs, d_ya);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+// antialiased bilinear resize HxW -> oh x ow of a uint8 image (first 3 channels), ATen CPU uint8 semantics:
+// horizontal pass first (into `tmp`, sh x ow x 3), then vertical.
+int mtb_resize_aa_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp, uint8_t* dst, int oh, int ow,
+                     int* tables_dev, long long tables_ints, void* stream) {
+  MTB_REQUIRE(src && tmp && dst && tables_dev, "mtb_resize_aa_u8: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<int> hs, hl, vs, vl;
+  std::vector<short> hw, vw;
+  int hk = 0, hp = 0, vk = 0, vp = 0;
+  aa_weights(sw, ow, hs, hl, hw, hk, hp);
+  aa_weights(sh, oh, vs, vl, vw, vk, vp);
+  const long long need =
+      2LL * ow + 2LL * oh + (static_cast<long long>(ow) * hk + static_cast<long long>(oh) * vk + 3) / 2 + 4;
+  MTB_REQUIRE(tables_ints >= need, "mtb_resize_aa_u8: tables scratch too small (%lld < %lld ints)", tables_ints, need);
+  int* d_hs = tables_dev;
+  int* d_hl = d_hs + ow;
+  int* d_vs = d_hl + ow;
+  int* d_vl = d_vs + oh;
+  short* d_hw = reinterpret_cast<short*>(d_vl + oh);
+  short* d_vw = d_hw + static_cast<long long>(ow) * hk + ((static_cast<long long>(ow) * hk) & 1);
+  MTB_CUDA_OK(cudaMemcpyAsync(d_hs, hs.data(), sizeof(int) * ow, cudaMemcpyHostToDevice, st));
+  MTB_CUDA_OK(cudaMemcpyAsync(d_hl, hl.data(), sizeof(int) * ow, cudaMemcpyHostToDevice, st));
+  MTB_CUDA_OK(cudaMemcpyAsync(d_vs, vs.data(), sizeof(int) * oh, cudaMemcpyHostToDevice, st));
+  MTB_CUDA_OK(cudaMemcpyAsync(d_vl, vl.data(), sizeof(int) * oh, cudaMemcpyHostToDevice, st));
+  MTB_CUDA_OK(cudaMemcpyAsync(d_hw, hw.data(), sizeof(short) * hw.size(), cudaMemcpyHostToDevice, st));
+  MTB_CUDA_OK(cudaMemcpyAsync(d_vw, vw.data(), sizeof(short) * vw.size(), cudaMemcpyHostToDevice, st));
+  MTB_CUDA_OK(cudaStreamSynchronize(st));
+  const int grid = sm_count3() * 8;
+  const uint8_t* cur = src;
+  int cur_w = sw, cur_c = sc;
+  if (ow != sw) {
+    resample_axis_kernel<<<grid, 256, 0, st>>>(cur, tmp, sh, ow, sw, sc, 3, 1, d_hs, d_hl, d_hw, hk, hp);
+    MTB_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    cur = tmp;
+    cur_w = ow;
+    cur_c = 3;
+  }
+  if (oh != sh) {
+    resample_axis_kernel<<<grid, 256, 0, st>>>(cur, dst, oh, ow, cur_w, cur_c, 3, 0, d_vs, d_vl, d_vw, vk, vp);
+    MTB_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+  } else {
+    copy_pad_kernel<<<grid, 256, 0, st>>>(cur, sh, cur_w, cur_c, dst, oh, ow, 0, 0, 0, 0);
+    MTB_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -19,10 +19,13 @@ class ConvPlan:
     """
 
     def __init__(self, x, w, bias, out, *, k=1, stride=1, pad=0, act=None, residual=None, tile_sums=None,
-                 tile=None, mode=0, pixel_shuffle=False):
-        planes_in, n, h, wd, cin = x.shape
-        assert w.shape[0] == planes_in and w.shape[1] == k * k and w.shape[3] == cin, (w.shape, x.shape)
-        cout = w.shape[2]
+                 tile=None, mode=0, pixel_shuffle=False, x_coff=0, out_coff=0, res_coff=0):
+        """Channel slices: `x` / `out` / `residual` may be wider (concat) tensors; the layer reads channels
+        [x_coff, x_coff + Cin) and writes [out_coff, out_coff + Cout).  The weights' Cin is padded to a multiple of
+        64 with zeros, so whatever lies beyond the slice (or beyond the tensor: TMA zero-fills) contributes 0."""
+        planes_in, n, h, wd, x_ctotal = x.shape
+        assert w.shape[0] == planes_in and w.shape[1] == k * k, (w.shape, x.shape)
+        cout, cin = w.shape[2], w.shape[3]
         d = ConvDesc()
         d.N, d.H, d.W, d.Cin, d.Cout = n, h, wd, cin, cout
         d.KH = d.KW = k
@@ -32,6 +35,13 @@ class ConvPlan:
         d.act = ACT[act]
         d.res_planes = 0 if residual is None else residual.shape[0]
         d.tile_w, d.tile_h = tile if tile else (0, 0)
+        d.x_ctotal, d.x_coff = x_ctotal, x_coff
+        if pixel_shuffle:
+            d.out_ctotal, d.out_coff = 0, 0
+        else:
+            d.out_ctotal, d.out_coff = out.shape[-1], out_coff
+        if residual is not None:
+            d.res_ctotal, d.res_coff = residual.shape[-1], res_coff
         d.mode = mode
         d.pixel_shuffle = int(bool(pixel_shuffle))
         self._keep = (x, w, bias, out, residual, tile_sums)

@@ -1,0 +1,58 @@
+"""Device pre-processing wrappers (C ABI: mtb_letterbox_u8, mtb_resize_aa_u8)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+
+
+def _declare(l) -> None:
+    if getattr(l, "_pre_declared", False):
+        return
+    vp, i32 = C.c_void_p, C.c_int
+    l.mtb_letterbox_u8.argtypes = [vp, i32, i32, i32, vp] + [i32] * 8 + [vp, vp]
+    l.mtb_letterbox_u8.restype = i32
+    l.mtb_resize_aa_u8.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, C.c_longlong, vp]
+    l.mtb_resize_aa_u8.restype = i32
+    l._pre_declared = True
+
+
+def letterbox_geometry(h0: int, w0: int, imgsz: int, stride: int = 32):
+    """ultralytics LetterBox(auto=True, scaleup=True): ((nw, nh), (top, bottom, left, right), (H, W), gain)."""
+    r = min(imgsz / h0, imgsz / w0)
+    nw, nh = int(round(w0 * r)), int(round(h0 * r))
+    dw, dh = ((imgsz - nw) % stride) / 2, ((imgsz - nh) % stride) / 2
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    return (nw, nh), (top, bottom, left, right), (nh + top + bottom, nw + left + right), r
+
+
+def letterbox_device(img: torch.Tensor, imgsz: int, *, swap_rb: bool = True) -> torch.Tensor:
+    """img: device uint8 HxWx(3|4) (BGR[A]) -> letterboxed uint8 H'xW'x3 (RGB when swap_rb)."""
+    l = lib()
+    _declare(l)
+    h0, w0, c = img.shape
+    (nw, nh), (top, _, left, _), (oh, ow), _ = letterbox_geometry(h0, w0, imgsz)
+    out = torch.empty((oh, ow, 3), dtype=torch.uint8, device=img.device)
+    tables = torch.empty(3 * (nw + nh) + 16, dtype=torch.int32, device=img.device)
+    check(l.mtb_letterbox_u8(ptr(img), h0, w0, c, ptr(out), oh, ow, top, left, nh, nw, 114, int(swap_rb), ptr(tables),
+                             stream_ptr()), "mtb_letterbox_u8")
+    return out
+
+
+def resize_aa_device(img: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+    """torchvision bilinear antialias resize of a device uint8 HxWx(3|4) image -> uint8 oh x ow x 3 (same channel order)."""
+    l = lib()
+    _declare(l)
+    h0, w0, c = img.shape
+    tmp = torch.empty((h0, ow, 3), dtype=torch.uint8, device=img.device)
+    out = torch.empty((oh, ow, 3), dtype=torch.uint8, device=img.device)
+    kx = (int(-(-max(w0 / ow, 1.0) // 1)) * 2 + 1)
+    ky = (int(-(-max(h0 / oh, 1.0) // 1)) * 2 + 1)
+    n_ints = 2 * ow + 2 * oh + (ow * kx + oh * ky + 3) // 2 + 64
+    tables = torch.empty(n_ints, dtype=torch.int32, device=img.device)
+    check(l.mtb_resize_aa_u8(ptr(img), h0, w0, c, ptr(tmp), ptr(out), oh, ow, ptr(tables), n_ints, stream_ptr()),
+          "mtb_resize_aa_u8")
+    return out

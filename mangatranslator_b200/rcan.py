@@ -23,7 +23,7 @@ def _declare(l) -> None:
     vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
     l.mtb_image_to_planes.argtypes = [vp, i32, i32, i32, i32, f32, C.POINTER(f32), vp, i32, i32, vp]
     l.mtb_ca_scale.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp, vp, i32, vp, vp]
-    l.mtb_scale_residual.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, i32, vp]
+    l.mtb_scale_residual.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, i32, i32, vp]
     l.mtb_f32_to_u8.argtypes = [vp, C.c_longlong, i32, C.POINTER(f32), f32, vp, vp, vp]
     for n in ("mtb_image_to_planes", "mtb_ca_scale", "mtb_scale_residual", "mtb_f32_to_u8"):
         getattr(l, n).restype = i32
@@ -149,7 +149,7 @@ class RcanB200:
                                      cd1.shape[0], ptr(b["scale"]), st), "mtb_ca_scale")
             else:
                 t, x, dst = arg
-                check(l.mtb_scale_residual(ptr(t), ptr(x), ptr(b["scale"]), ptr(dst), h * w, 1, f, st),
+                check(l.mtb_scale_residual(ptr(t), ptr(x), ptr(b["scale"]), ptr(dst), h * w, 1, f, self.planes, st),
                       "mtb_scale_residual")
 
     def upscale_u8(self, img: torch.Tensor, *, swap_rb: bool = False, want_float: bool = False):

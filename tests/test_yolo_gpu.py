@@ -1,0 +1,128 @@
+"""GPU: B200 YOLOv8-seg (tcgen05 conv plans with channel-slice concats, SPPF/upsample kernels, DFL decode, NMS,
+scale_boxes, reference dedup/containment) against the CPU fp32 oracle (oracle/yolo_oracle.py) and the reference's own
+post-NMS functions."""
+import numpy as np
+import pytest
+import torch
+
+import yolo_oracle as Y
+
+pytestmark = pytest.mark.gpu
+NANO = dict(nc=1, depth=0.33, width=0.25, max_ch=1024)
+MEDIUM = dict(nc=1, depth=0.67, width=0.75, max_ch=768)
+
+
+def _setup(cfg, h, w, seed, imgsz):
+    from mangatranslator_b200.yolo import YoloB200
+    from mangatranslator_b200.preproc import letterbox_device
+    m = Y.make_model(seed, bias_objects=-2.0, cls_gain=400.0, **cfg)
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    # smooth blobs so the network sees structure, not only noise
+    import cv2
+    for _ in range(6):
+        cv2.circle(img, (int(rng.integers(0, w)), int(rng.integers(0, h))), int(rng.integers(15, 60)),
+                   tuple(int(v) for v in rng.integers(0, 256, 3)), -1)
+    dev = torch.device("cuda:0")
+    net = YoloB200(m.state_dict(), m.cfg, dev)
+    lb = letterbox_device(torch.from_numpy(img).to(dev), imgsz, swap_rb=True)
+    g = net.forward_letterboxed(lb)
+    torch.cuda.synchronize()
+    x = Y.preprocess(img, imgsz)
+    assert tuple(x.shape[2:]) == tuple(lb.shape[:2])
+    return m, net, g, x, img, lb
+
+
+@pytest.mark.parametrize("cfg,hw,imgsz", [(NANO, (200, 320), 320), (MEDIUM, (192, 160), 192)], ids=["nano", "medium"])
+def test_head_outputs_match_oracle(cfg, hw, imgsz):
+    m, net, g, x, img, lb = _setup(cfg, hw[0], hw[1], 3, imgsz)
+    with torch.no_grad():
+        raw, proto = m.heads_raw(x)
+    for (box, cls, mc), (gb, gc, gm, fh, fw, st) in zip(raw, g["levels"]):
+        assert (gb.cpu()[0].permute(2, 0, 1) - box[0]).abs().max().item() < 1e-3
+        assert (gc.cpu()[0, :, :, :1].permute(2, 0, 1) - cls[0]).abs().max().item() < 5e-3   # logits scaled by cls_gain
+        assert (gm.cpu()[0].permute(2, 0, 1) - mc[0]).abs().max().item() < 1e-3
+    assert (g["proto"].cpu()[0].permute(2, 0, 1) - proto[0]).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("cfg,hw,imgsz", [(NANO, (200, 320), 320), (NANO, (333, 250), 320)], ids=["wide", "tall"])
+def test_detections_match_oracle_and_reference_dedup(cfg, hw, imgsz):
+    m, net, g, x, img, lb = _setup(cfg, hw[0], hw[1], 5, imgsz)
+    conf = 0.6
+    ref = Y.predict(m, img, conf, imgsz)
+    det, cnt, final_idx = net.detect(g, conf, hw, tuple(lb.shape[:2]), apply_reference_dedup=True)
+    torch.cuda.synchronize()
+    n_nms, n_final = int(cnt[0]), int(cnt[1])
+    assert n_nms == ref["xyxy"].shape[0] and n_nms > 3
+    d = det[:n_nms].cpu()
+    assert torch.equal(d[:, 6].long(), ref["anchors"])          # bit-exact NMS indices (anchor ids, in score order)
+    assert (d[:, :4] - ref["xyxy"]).abs().max().item() < 1e-2   # pixels
+    assert (d[:, 4] - ref["conf"]).abs().max().item() < 1e-4
+    # the reference's own post-NMS logic on the same boxes (restated below from detection.py:204-295)
+    boxes = d[:, :4].tolist()
+    confs = d[:, 4].tolist()
+    keep = _ref_dedup(boxes, confs, 0.7)
+    keep2 = _ref_remove_contained([boxes[i] for i in keep], 0.9)
+    exp = [keep[i] for i in keep2]
+    assert final_idx[:n_final].cpu().tolist() == exp
+
+
+def _iou(a, b):
+    ix = max(0.0, min(a[2], b[2]) - max(a[0], b[0])) * max(0.0, min(a[3], b[3]) - max(a[1], b[1]))
+    ua = max(0.0, a[2] - a[0]) * max(0.0, a[3] - a[1]) + max(0.0, b[2] - b[0]) * max(0.0, b[3] - b[1]) - ix
+    return ix / ua if ua > 0 else 0.0
+
+
+def _ioa(inner, outer):
+    ai = max(0.0, inner[2] - inner[0]) * max(0.0, inner[3] - inner[1])
+    if ai <= 0:
+        return 0.0
+    ix = max(0.0, min(inner[2], outer[2]) - max(inner[0], outer[0])) * max(0.0, min(inner[3], outer[3]) - max(inner[1], outer[1]))
+    return ix / ai
+
+
+def _ref_dedup(boxes, confs, thr):
+    order = sorted(range(len(boxes)), key=lambda i: confs[i], reverse=True)
+    keep = []
+    for i in order:
+        if not any(_iou(boxes[i], boxes[k]) > thr for k in keep):
+            keep.append(i)
+    return keep
+
+
+def _ref_remove_contained(boxes, thr):
+    n = len(boxes)
+    alive = [True] * n
+    for i in range(n):
+        if not alive[i]:
+            continue
+        for j in range(n):
+            if i == j or not alive[j]:
+                continue
+            if _ioa(boxes[i], boxes[j]) > thr:
+                alive[i] = False
+                break
+    return [i for i in range(n) if alive[i]]
+
+
+def test_post_nms_logic_matches_live_reference():
+    """When the reference tree is present, its _deduplicate_primary_boxes/_remove_contained_boxes agree with the
+    restatement used above (so the GPU indices are pinned to the reference itself)."""
+    import _refimport
+    if not _refimport.available():
+        pytest.skip("reference tree not present")
+    core = _refimport.import_reference()
+    import core.image.detection as ref
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        n = int(rng.integers(2, 25))
+        xy = rng.uniform(0, 500, size=(n, 2))
+        wh = rng.uniform(20, 200, size=(n, 2))
+        b = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+        b[n // 2] = b[0] + rng.uniform(-3, 3, size=4).astype(np.float32)       # near duplicate
+        c = rng.uniform(0.3, 1.0, size=n).astype(np.float32)
+        tb, tc = torch.from_numpy(b), torch.from_numpy(c)
+        kb, keep = ref._deduplicate_primary_boxes(tb, tc, 0.7)
+        assert keep == _ref_dedup(tb.tolist(), tc.tolist(), 0.7)
+        kb2, idx = ref._remove_contained_boxes(kb, [("primary", i) for i in keep], 0.9)
+        assert [i for (_, i) in idx] == [keep[i] for i in _ref_remove_contained(kb.tolist(), 0.9)]
