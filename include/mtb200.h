@@ -48,6 +48,8 @@ typedef struct mtb_conv_desc {
   int x_ctotal, x_coff;     /* input tensor channel count (0 = Cin) and first channel read (concat slices) */
   int out_ctotal, out_coff; /* output tensor channel count (0 = Cout) and first channel written */
   int res_ctotal, res_coff; /* same for the residual tensor */
+  int res_bcast;      /* 1: residual has batch 1, shared by all N images */
+  int act_after_res;  /* 1: activation after the residual add (default: before) */
   int pixel_shuffle;  /* 1: fuse PixelShuffle(2) into the store (Cout = 4 blocks [dy*2+dx] of Cout/4 channels) */
   int mode;           /* 0 auto, 1 force the per-tap kernel, 2 require the halo-tile kernel (3x3 s1 p1, 64->64) */
 } mtb_conv_desc;
@@ -199,6 +201,44 @@ int mtb_aa_weights_host(int in_size, int out_size, int* start, int* len, short* 
                         int* prec);
 int mtb_resize_aa_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp /* sh x ow x 3 */,
                      uint8_t* dst /* oh x ow x 3 */, int oh, int ow, int* tables_dev, long long tables_ints, void* stream);
+
+/* ---- SAM 2.1 glue (transformers Sam2Model behind core/image/detection.py:475-511) -------------------------------- */
+int mtb_layernorm(const void* x, long long rows, int C, int ct_in, int ci, int planes_in, const float* gamma,
+                  const float* beta, float eps, void* y, int ct_out, int co, int planes_out, int gelu, void* stream);
+int mtb_maxpool2x2(const void* x, void* y, int N, int H, int W, int C, int planes, void* stream);
+int mtb_add_planes(const void* a, const void* b, void* out, long long rows, int C, long long b_rows, int planes,
+                   void* stream);
+
+typedef struct mtb_attn_desc {
+  int B, heads, hd, nq, nk;
+  float scale;
+  const void *q, *k, *v; /* bf16 plane tensors, one row per token */
+  void* out;
+  int q_ct, q_off, k_ct, k_off, v_ct, v_off, o_ct, o_off; /* row width and first channel of q/k/v/out */
+  long long q_ps, k_ps, v_ps, o_ps;                       /* plane strides (elements) */
+  int planes;
+  int mode; /* 0: token t of batch b is row b*n + t; 1: Hiera windows (ws x ws) on a grid_h x grid_w token grid,
+               out-of-grid positions are padding whose q/k/v are pad_q/pad_k/pad_v (the qkv bias) */
+  int grid_h, grid_w, ws, pool; /* pool: queries are 2x2 max-pooled inside each window (Hiera stage transition) */
+  const float *pad_q, *pad_k, *pad_v;
+} mtb_attn_desc;
+int mtb_attention(const mtb_attn_desc* d /* host */, void* stream);
+
+/* Sam2PatchEmbeddings on the normalised image + positional embedding: u8 RGB HxWx3 -> planes [Ho][Wo][C] */
+int mtb_sam_patch_embed(const uint8_t* img, int H, int W, const float* mean3, const float* std3, const float* w,
+                        const float* b, const float* pos, int C, int k, int stride, int pad, void* out, int planes,
+                        void* stream);
+/* boxes in original pixels; sx = 1024/W, sy = 1024/H as the processor scales them */
+int mtb_sam_prompt_boxes(const float* boxes, float sx, float sy, int P, const float* gauss, int half, const float* pe2, const float* pe3,
+                         const float* not_a_point, float input_size, float* out, void* stream);
+int mtb_sam_hyper_masks(const void* up, int planes, const float* hyper, int P, int K, int C, long long npix, float* out,
+                        void* stream);
+int mtb_sam_select_mask(const float* logits, const float* iou, int P, int K, long long npix, float delta, float thresh,
+                        int* sel, void* stream);
+/* masks[p] = (bilinear(logits[p][sel[p]], HxW) > 0) & rect(floor/ceil of boxes[p]) as uint8 {0,255}
+ * (post_process_masks + core/image/detection.py:1732-1750); logit_out (optional) gets the interpolated logits */
+int mtb_sam_mask_write(const float* logits, const int* sel, int K, int S, const float* boxes, int P, int H, int W,
+                       uint8_t* masks, float* logit_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad",
         "planes_in", "planes_out", "act", "res_planes", "tile_w", "tile_h", "x_ctotal", "x_coff", "out_ctotal", "out_coff", "res_ctotal", "res_coff",
-        "pixel_shuffle", "mode")]
+        "res_bcast", "act_after_res", "pixel_shuffle", "mode")]
 
 
 _lib = None

@@ -153,7 +153,8 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
   p.res_cstride = d->res_ctotal > 0 ? d->res_ctotal : d->Cout;
   p.res_coff = d->res_coff;
   p.out_plane_stride = static_cast<long long>(p.N) * p.Ho * p.Wo * p.out_cstride;
-  p.res_plane_stride = static_cast<long long>(p.N) * p.Ho * p.Wo * p.res_cstride;
+  p.res_plane_stride = static_cast<long long>(d->res_bcast ? 1 : p.N) * p.Ho * p.Wo * p.res_cstride *
+                       (d->pixel_shuffle ? 4 : 1);
   p.res_planes = d->res_planes;
   p.bias = bias;
   if (d->planes_out == 4) {
@@ -166,9 +167,11 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
   p.residual = static_cast<const uint16_t*>(residual);
   p.tile_sums = tile_sums;
   p.pixel_shuffle = d->pixel_shuffle ? 1 : 0;
-  if (p.pixel_shuffle && (d->Cout % 64 != 0 || d->planes_out == 4 || residual)) {
+  p.res_bcast = d->res_bcast ? 1 : 0;
+  p.act_after_res = d->act_after_res ? 1 : 0;
+  if (p.pixel_shuffle && (d->Cout % 64 != 0 || d->planes_out == 4)) {
     delete pl;
-    MTB_REQUIRE(false, "conv: pixel_shuffle needs Cout %% 64 == 0, bf16 plane output and no residual");
+    MTB_REQUIRE(false, "conv: pixel_shuffle needs Cout %% 64 == 0 and bf16 plane output");
   }
   // halo-tile kernel for the RCAN body layer (3x3, stride 1, 64 -> 64 channels); mode 1 forces the per-tap kernel
   pl->halo = (d->mode != 1 && conv_halo_eligible(p, d->Cin)) ? 1 : 0;

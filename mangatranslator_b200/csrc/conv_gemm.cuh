@@ -46,6 +46,8 @@ struct ConvParams {
   int in_coff;                 // first input channel inside the (wider) input tensor
   int out_cstride, out_coff;   // channel count of the output tensor and first channel written (concat slices)
   int res_cstride, res_coff;   // same for the residual tensor
+  int res_bcast;               // 1: the residual has batch 1 and is shared by all N images
+  int act_after_res;           // 1: activation is applied after the residual add
   int pixel_shuffle;           // 1: Cout = 4 blocks of Cout/4 channels, block (dy*2+dx) is stored at pixel (2y+dy, 2x+dx)
 };
 

@@ -205,7 +205,7 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 bool conv_halo_eligible(const ConvParams& p, int cin) {
   return p.KH == 3 && p.KW == 3 && p.stride == 1 && p.pad == 1 && cin == 64 && p.Cout == 64 && p.out != nullptr &&
          p.Ho > 1 && p.in_coff == 0 && p.out_coff == 0 && p.out_cstride == 64 &&
-         (p.residual == nullptr || (p.res_coff == 0 && p.res_cstride == 64)) && !p.pixel_shuffle;
+         (p.residual == nullptr || (p.res_coff == 0 && p.res_cstride == 64 && !p.res_bcast)) && !p.pixel_shuffle;
 }
 
 int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int nsplit,

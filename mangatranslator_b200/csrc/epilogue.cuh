@@ -40,10 +40,23 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvParams& p, float (&v)
       v[4 * j + 3] += b.w;
     }
   }
+  // output location (element offset inside a plane) and the matching residual location
+  long long off = pix * p.out_cstride + p.out_coff + cbase;
+  long long roff = ((p.res_bcast ? (static_cast<long long>(oy) * p.Wo + ox) : pix)) * p.res_cstride + p.res_coff + cbase;
+  if (p.pixel_shuffle) {
+    // PixelShuffle(2) / ConvTranspose2d(2,2) fused into the store: channel block b = dy*2+dx lands on the 2x grid
+    const int cq = p.Cout >> 2;
+    const int blk = cbase / cq, cc = cbase - blk * cq;
+    const long long hy = 2 * oy + (blk >> 1), hx = 2 * ox + (blk & 1);
+    off = ((static_cast<long long>(n) * (2 * p.Ho) + hy) * (2 * p.Wo) + hx) * cq + cc;
+    roff = ((static_cast<long long>(p.res_bcast ? 0 : n) * (2 * p.Ho) + hy) * (2 * p.Wo) + hx) * p.res_cstride + p.res_coff + cc;
+  }
+  if (!p.act_after_res) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = epi_act<ACT>(v[j], p.act);
+    for (int j = 0; j < 16; ++j) v[j] = epi_act<ACT>(v[j], p.act);
+  }
   if (p.residual && valid) {
-    const uint16_t* rp = p.residual + pix * p.res_cstride + p.res_coff + cbase;
+    const uint16_t* rp = p.residual + roff;
     for (int pl = 0; pl < p.res_planes; ++pl) {
       const uint4* r4 = reinterpret_cast<const uint4*>(rp + pl * p.res_plane_stride);
       const uint4 a = __ldg(r4), b = __ldg(r4 + 1);
@@ -55,6 +68,10 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvParams& p, float (&v)
         v[2 * j + 1] += f.y;
       }
     }
+  }
+  if (p.act_after_res) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = epi_act<ACT>(v[j], p.act);
   }
   if (!valid) {
 #pragma unroll
@@ -80,18 +97,10 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvParams& p, float (&v)
   }
   if (!valid) return;
   if (p.out_f32) {
-    float4* o4 = reinterpret_cast<float4*>(p.out_f32 + pix * p.out_cstride + p.out_coff + cbase);
+    float4* o4 = reinterpret_cast<float4*>(p.out_f32 + off);
 #pragma unroll
     for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     return;
-  }
-  long long off = pix * p.out_cstride + p.out_coff + cbase;
-  if (p.pixel_shuffle) {
-    // PixelShuffle(2) / ConvTranspose2d(2,2) fused into the store: channel block b = dy*2+dx lands on the 2x grid
-    const int cq = p.Cout >> 2;
-    const int blk = cbase / cq, cc = cbase - blk * cq;
-    const long long hp = (static_cast<long long>(n) * (2 * p.Ho) + 2 * oy + (blk >> 1)) * (2 * p.Wo) + 2 * ox + (blk & 1);
-    off = hp * cq + cc;
   }
   uint32_t hi[8];
 #pragma unroll

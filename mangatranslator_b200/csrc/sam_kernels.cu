@@ -1,0 +1,571 @@
+// SAM 2.1 glue kernels (reference: transformers Sam2Model behind core/image/detection.py:475-511):
+//   layer norm (+GELU), 2x2 max-pool, plane add with broadcast, multi-head attention with the Hiera window
+//   partition / zero-padding / query-pooling folded into its addressing, box-prompt encoding, the hyper-network
+//   mask product, the stability-based mask selection and the fused "bilinear 256^2 -> HxW, > 0, clip to the box,
+//   write uint8 0/255" mask writer (core/image/detection.py:504-511,1732-1750).
+// All softmax / normalisation math is fp32; activations travel as bf16 hi/lo planes like everywhere else.
+#include <math.h>
+
+#include <atomic>
+
+#include "../../include/mtb200.h"
+#include "common.cuh"
+
+namespace mtb {
+extern std::atomic<long long> g_launches;
+}
+using namespace mtb;
+
+namespace {
+
+int sm_count4() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+inline int grid_for4(long long items, int block) {
+  long long g = (items + block - 1) / block;
+  const long long cap = static_cast<long long>(sm_count4()) * 16;
+  if (g > cap) g = cap;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
+__device__ __forceinline__ float ld_planes(const uint16_t* p, long long idx, long long ps, int planes) {
+  float v = bf16_to_f(p[idx]);
+  if (planes == 2) v += bf16_to_f(p[ps + idx]);
+  return v;
+}
+__device__ __forceinline__ void st_planes(uint16_t* p, long long idx, long long ps, int planes, float v) {
+  uint16_t h, l;
+  split_bf16(v, h, l);
+  p[idx] = h;
+  if (planes == 2) p[ps + idx] = l;
+}
+
+// ---- layer norm over the channel dimension of each row (pixel / token), optional GELU --------------------
+// one warp per row; two-pass mean / variance in fp32 like torch.nn.LayerNorm
+__global__ void layernorm_kernel(const uint16_t* __restrict__ x, long long rows, int C, int ct_in, int ci, long long ps_in,
+                                 int planes_in, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 uint16_t* __restrict__ y, int ct_out, int co, long long ps_out, int planes_out, int gelu) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long r = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); r < rows;
+       r += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const long long base = r * ct_in + ci;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += ld_planes(x, base + c, ps_in, planes_in);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / static_cast<float>(C);
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float d = ld_planes(x, base + c, ps_in, planes_in) - mean;
+      v += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = 1.0f / sqrtf(v / static_cast<float>(C) + eps);
+    const long long ob = r * ct_out + co;
+    for (int c = lane; c < C; c += 32) {
+      float o = (ld_planes(x, base + c, ps_in, planes_in) - mean) * rstd * gamma[c] + beta[c];
+      if (gelu) o = 0.5f * o * (1.0f + erff(o * 0.70710678118654752440f));
+      st_planes(y, ob + c, ps_out, planes_out, o);
+    }
+  }
+}
+
+// ---- 2x2 / stride 2 max-pool of an NHWC plane tensor --------------------------------------------------------
+__global__ void maxpool2x2_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W, int C,
+                                  long long ps_in, long long ps_out, int planes) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(N) * Ho * Wo * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    long long p = i / C;
+    const int ox = static_cast<int>(p % Wo);
+    p /= Wo;
+    const int oy = static_cast<int>(p % Ho);
+    const int n = static_cast<int>(p / Ho);
+    float best = -INFINITY;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const long long idx = ((static_cast<long long>(n) * H + 2 * oy + a) * W + 2 * ox + b) * C + c;
+        const float v = ld_planes(x, idx, ps_in, planes);
+        best = fmaxf(best, v);
+      }
+    st_planes(y, i, ps_out, planes, best);
+  }
+}
+
+// ---- out = a + b (b broadcast over the batch when b_rows < rows) -------------------------------------------------
+__global__ void add_planes_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, uint16_t* __restrict__ o,
+                                  long long rows, int C, long long b_rows, long long ps_a, long long ps_b, long long ps_o,
+                                  int planes) {
+  const long long total = rows * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C;
+    const int c = static_cast<int>(i - r * C);
+    const long long bi = (r % b_rows) * C + c;
+    st_planes(o, i, ps_o, planes, ld_planes(a, i, ps_a, planes) + ld_planes(b, bi, ps_b, planes));
+  }
+}
+
+// ---- attention ----------------------------------------------------------------------------------------------------
+struct AttnParams {
+  int B, heads, hd, nq, nk;
+  float scale;
+  const uint16_t *q, *k, *v;
+  uint16_t* out;
+  int q_ct, q_off, k_ct, k_off, v_ct, v_off, o_ct, o_off;
+  long long q_ps, k_ps, v_ps, o_ps;
+  int planes;
+  int mode;  // 0: rows b*n + t ; 1: Hiera windows on a grid
+  int grid_h, grid_w, ws, pool, nwx;
+  const float *pad_q, *pad_k, *pad_v;  // value of a padded token (= the qkv bias) [heads*hd] each
+};
+
+// memory row of token t of batch b, or -1 for a padded (out-of-grid) window position
+__device__ __forceinline__ long long tok_row(const AttnParams& P, int b, int t, int n) {
+  if (P.mode == 0) return static_cast<long long>(b) * n + t;
+  const int by = b / P.nwx, bx = b - by * P.nwx;
+  const int ty = t / P.ws, tx = t - ty * P.ws;
+  const int y = by * P.ws + ty, x = bx * P.ws + tx;
+  if (y >= P.grid_h || x >= P.grid_w) return -1;
+  return static_cast<long long>(y) * P.grid_w + x;
+}
+
+__device__ __forceinline__ float load_tok(const AttnParams& P, const uint16_t* base, int ct, int off, long long ps,
+                                          const float* pad, long long row, int ch) {
+  if (row < 0) return pad ? pad[ch] : 0.f;
+  return ld_planes(base, row * ct + off + ch, ps, P.planes);
+}
+
+constexpr int kAttnThreads = 256;
+constexpr int kQT = 64;   // queries per block (8 per warp)
+constexpr int kKT = 64;   // keys per shared-memory tile
+constexpr int kMaxHD = 128;
+
+__global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnParams P) {
+  extern __shared__ float sm[];
+  const int hd = P.hd, hdp = hd + 1;
+  float* sK = sm;                     // [kKT][hd+1]
+  float* sV = sK + kKT * hdp;         // [kKT][hd]
+  float* sQ = sV + kKT * hd;          // [kQT][hd]
+  const int bh = blockIdx.x;
+  const int b = bh / P.heads, h = bh - b * P.heads;
+  const int q0 = blockIdx.y * kQT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq_tile = min(kQT, P.nq - q0);
+  const int wso = P.pool ? P.ws / 2 : P.ws;
+
+  // stage the block's queries (scaled), applying the 2x2 max-pool inside the window when requested
+  for (int i = threadIdx.x; i < nq_tile * hd; i += kAttnThreads) {
+    const int qi = i / hd, d = i - qi * hd;
+    const int t = q0 + qi;
+    float v;
+    if (P.mode == 1 && P.pool) {
+      const int qy = t / wso, qx = t - qy * wso;
+      v = -INFINITY;
+      for (int a = 0; a < 2; ++a)
+        for (int c = 0; c < 2; ++c) {
+          const int tt = (2 * qy + a) * P.ws + 2 * qx + c;
+          v = fmaxf(v, load_tok(P, P.q, P.q_ct, P.q_off, P.q_ps, P.pad_q, tok_row(P, b, tt, P.nk), h * hd + d));
+        }
+    } else {
+      v = load_tok(P, P.q, P.q_ct, P.q_off, P.q_ps, P.pad_q, tok_row(P, b, t, P.nq), h * hd + d);
+    }
+    sQ[qi * hd + d] = v;
+  }
+  // per-warp state for its 8 queries
+  float m[8], l[8], acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    m[j] = -INFINITY;
+    l[j] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  }
+  for (int k0 = 0; k0 < P.nk; k0 += kKT) {
+    const int nk_tile = min(kKT, P.nk - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nk_tile * hd; i += kAttnThreads) {
+      const int ki = i / hd, d = i - ki * hd;
+      const long long row = tok_row(P, b, k0 + ki, P.nk);
+      sK[ki * hdp + d] = load_tok(P, P.k, P.k_ct, P.k_off, P.k_ps, P.pad_k, row, h * hd + d);
+      sV[ki * hd + d] = load_tok(P, P.v, P.v_ct, P.v_off, P.v_ps, P.pad_v, row, h * hd + d);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int qi = warp * 8 + j;
+      if (qi >= nq_tile) break;
+      const float* qv = sQ + qi * hd;
+      float s0 = -INFINITY, s1 = -INFINITY;
+      if (lane < nk_tile) {
+        float a = 0.f;
+        const float* kr = sK + lane * hdp;
+        for (int d = 0; d < hd; ++d) a += qv[d] * kr[d];
+        s0 = a * P.scale;
+      }
+      if (lane + 32 < nk_tile) {
+        float a = 0.f;
+        const float* kr = sK + (lane + 32) * hdp;
+        for (int d = 0; d < hd; ++d) a += qv[d] * kr[d];
+        s1 = a * P.scale;
+      }
+      float tm = fmaxf(s0, s1);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
+      const float nm = fmaxf(m[j], tm);
+      const float corr = expf(m[j] - nm);
+      const float p0 = (lane < nk_tile) ? expf(s0 - nm) : 0.f;
+      const float p1 = (lane + 32 < nk_tile) ? expf(s1 - nm) : 0.f;
+      float ps = p0 + p1;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      l[j] = l[j] * corr + ps;
+      m[j] = nm;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] *= corr;
+      for (int kk = 0; kk < nk_tile; ++kk) {
+        const float p = __shfl_sync(0xffffffffu, kk < 32 ? p0 : p1, kk & 31);
+        const float* vr = sV + kk * hd;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int d = lane + 32 * e;
+          if (d < hd) acc[j][e] += p * vr[d];
+        }
+      }
+    }
+  }
+  // write: out[b, t, h*hd + d]; window mode writes at the un-partitioned grid position and drops the padding
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int qi = warp * 8 + j;
+    if (qi >= nq_tile) break;
+    const int t = q0 + qi;
+    long long row;
+    if (P.mode == 0) {
+      row = static_cast<long long>(b) * P.nq + t;
+    } else {
+      const int by = b / P.nwx, bx = b - by * P.nwx;
+      const int ty = t / wso, tx = t - ty * wso;
+      const int y = by * wso + ty, x = bx * wso + tx;
+      const int gh = P.pool ? P.grid_h / 2 : P.grid_h, gw = P.pool ? P.grid_w / 2 : P.grid_w;
+      if (y >= gh || x >= gw) continue;
+      row = static_cast<long long>(y) * gw + x;
+    }
+    const float inv = 1.0f / l[j];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = lane + 32 * e;
+      if (d < hd) st_planes(P.out, row * P.o_ct + P.o_off + h * hd + d, P.o_ps, P.planes, acc[j][e] * inv);
+    }
+  }
+}
+
+
+// ---- patch embedding: (u8 - mean')/std' -> conv k x k / stride / pad (3 -> C) + bias + positional embedding -------
+// one thread per (output pixel, 8 output channels); weights in shared memory
+__global__ void patch_embed_kernel(const uint8_t* __restrict__ img, int H, int W, const float* __restrict__ mean,
+                                   const float* __restrict__ stdv, const float* __restrict__ w, const float* __restrict__ b,
+                                   const float* __restrict__ pos, int C, int k, int stride, int pad, int Ho, int Wo,
+                                   uint16_t* __restrict__ out, long long ps, int planes) {
+  extern __shared__ float sw[];  // [C][3*k*k]
+  const int kk = 3 * k * k;
+  for (int i = threadIdx.x; i < C * kk; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int groups = C / 8;
+  const long long total = static_cast<long long>(Ho) * Wo * groups;
+  const float m0 = mean[0], m1 = mean[1], m2 = mean[2], s0 = stdv[0], s1 = stdv[1], s2 = stdv[2];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    const long long pix = i / groups;
+    const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>(pix / Wo);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int c = 0; c < 3; ++c) {
+      const float mm = c == 0 ? m0 : (c == 1 ? m1 : m2), ss = c == 0 ? s0 : (c == 1 ? s1 : s2);
+      for (int ky = 0; ky < k; ++ky) {
+        const int iy = oy * stride + ky - pad;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < k; ++kx) {
+          const int ix = ox * stride + kx - pad;
+          if (ix < 0 || ix >= W) continue;
+          const float v = (static_cast<float>(img[(static_cast<long long>(iy) * W + ix) * 3 + c]) - mm) / ss;
+          const int wi = (c * k + ky) * k + kx;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += v * sw[(g * 8 + j) * kk + wi];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = g * 8 + j;
+      st_planes(out, pix * C + ch, ps, planes, acc[j] + b[ch] + pos[pix * C + ch]);
+    }
+  }
+}
+
+// ---- box prompts -> 3 sparse tokens per box (Sam2PromptEncoder._embed_boxes) -------------------------------------
+// boxes: [P][4] already scaled to the 1024 input frame; gauss: [2][half]; out fp32 [P][3][2*half]
+__global__ void prompt_boxes_kernel(const float* __restrict__ boxes, float sx, float sy, int Pn,
+                                    const float* __restrict__ gauss, int half,
+                                    const float* __restrict__ pe2, const float* __restrict__ pe3,
+                                    const float* __restrict__ not_a_point, float input_size, float* __restrict__ out) {
+  const int total = Pn * 3 * 2 * half;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % (2 * half);
+    const int t = (i / (2 * half)) % 3;
+    const int p = i / (6 * half);
+    float v;
+    if (t == 2) {
+      v = not_a_point[c];
+    } else {
+      // processor: coords * (1024 / W) in fp32 (processing_sam2.py:196-197); prompt encoder: + 0.5, / 1024
+      float x = (boxes[p * 4 + 2 * t] * sx + 0.5f) / input_size;
+      float y = (boxes[p * 4 + 2 * t + 1] * sy + 0.5f) / input_size;
+      x = 2.0f * x - 1.0f;
+      y = 2.0f * y - 1.0f;
+      const int cc = c < half ? c : c - half;
+      float proj = x * gauss[cc] + y * gauss[half + cc];
+      proj = 6.283185307179586f * proj;
+      v = (c < half ? sinf(proj) : cosf(proj)) + (t == 0 ? pe2[c] : pe3[c]);
+    }
+    out[i] = v;
+  }
+}
+
+// ---- masks[p][k][pix] = sum_c hyper[p][k][c] * up[p][pix][c] -------------------------------------------------------
+__global__ void hyper_masks_kernel(const uint16_t* __restrict__ up, long long ps, int planes, const float* __restrict__ hyper,
+                                   int Pn, int K, int C, long long npix, float* __restrict__ out) {
+  const long long total = static_cast<long long>(Pn) * npix;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(i / npix);
+    const long long pix = i - static_cast<long long>(p) * npix;
+    float u[32];
+    for (int c = 0; c < C; ++c) u[c] = ld_planes(up, i * C + c, ps, planes);
+    for (int k = 0; k < K; ++k) {
+      const float* hk = hyper + (static_cast<long long>(p) * K + k) * C;
+      float a = 0.f;
+      for (int c = 0; c < C; ++c) a += hk[c] * u[c];
+      out[(static_cast<long long>(p) * K + k) * npix + pix] = a;
+    }
+  }
+}
+
+// ---- _dynamic_multimask_via_stability: one block per box ----------------------------------------------------------
+__global__ void select_mask_kernel(const float* __restrict__ logits, const float* __restrict__ iou, int K, long long npix,
+                                   float delta, float thresh, int* __restrict__ sel) {
+  const int p = blockIdx.x;
+  const float* m0 = logits + static_cast<long long>(p) * K * npix;
+  __shared__ unsigned int s_i, s_u;
+  if (threadIdx.x == 0) {
+    s_i = 0;
+    s_u = 0;
+  }
+  __syncthreads();
+  unsigned int ai = 0, au = 0;
+  for (long long i = threadIdx.x; i < npix; i += blockDim.x) {
+    const float v = m0[i];
+    ai += v > delta;
+    au += v > -delta;
+  }
+  atomicAdd(&s_i, ai);
+  atomicAdd(&s_u, au);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float area_i = static_cast<float>(s_i), area_u = static_cast<float>(s_u);
+    const float stab = area_u > 0.f ? area_i / area_u : 1.0f;
+    int best = 0;
+    if (!(stab >= thresh)) {
+      best = 1;
+      for (int k = 2; k < K; ++k)
+        if (iou[p * K + k] > iou[p * K + best]) best = k;  // torch.argmax: first maximum
+    }
+    sel[p] = best;
+  }
+}
+
+// ---- bilinear 256^2 -> HxW (align_corners=False), > 0, AND the floor/ceil box, write uint8 {0,255} --------------
+// One thread per output pixel of the box window; pixels outside every box stay 0 (the mask buffer is zeroed here too).
+__global__ void mask_write_kernel(const float* __restrict__ logits, const int* __restrict__ sel, int K, int S,
+                                  const float* __restrict__ boxes /* [P][4] original px */, int Pn, int H, int W,
+                                  uint8_t* __restrict__ masks /* [P][H][W] */, float* __restrict__ logit_out) {
+  const long long per = static_cast<long long>(H) * W;
+  const long long total = per * Pn;
+  const float sy = static_cast<float>(S) / static_cast<float>(H), sx = static_cast<float>(S) / static_cast<float>(W);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(i / per);
+    const long long r = i - static_cast<long long>(p) * per;
+    const int y = static_cast<int>(r / W), x = static_cast<int>(r - static_cast<long long>(y) * W);
+    const float* b = boxes + p * 4;
+    // clip rectangle: floor(x0), floor(y0), ceil(x1), ceil(y1) clamped to the page (detection.py:1733-1737)
+    const int bx0 = static_cast<int>(floorf(fminf(fmaxf(b[0], 0.f), static_cast<float>(W))));
+    const int by0 = static_cast<int>(floorf(fminf(fmaxf(b[1], 0.f), static_cast<float>(H))));
+    const int bx1 = static_cast<int>(ceilf(fminf(fmaxf(b[2], 0.f), static_cast<float>(W))));
+    const int by1 = static_cast<int>(ceilf(fminf(fmaxf(b[3], 0.f), static_cast<float>(H))));
+    uint8_t o = 0;
+    const bool inside = x >= bx0 && x < bx1 && y >= by0 && y < by1;
+    if (inside || logit_out) {
+      float fy = sy * (static_cast<float>(y) + 0.5f) - 0.5f;
+      float fx = sx * (static_cast<float>(x) + 0.5f) - 0.5f;
+      if (fy < 0.f) fy = 0.f;
+      if (fx < 0.f) fx = 0.f;
+      const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+      const int y1 = y0 + (y0 < S - 1 ? 1 : 0), x1 = x0 + (x0 < S - 1 ? 1 : 0);
+      const float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
+      const float* m = logits + (static_cast<long long>(p) * K + sel[p]) * S * S;
+      const float top = (1.f - lx) * m[y0 * S + x0] + lx * m[y0 * S + x1];
+      const float bot = (1.f - lx) * m[y1 * S + x0] + lx * m[y1 * S + x1];
+      const float v = (1.f - ly) * top + ly * bot;
+      if (logit_out) logit_out[i] = v;
+      if (inside && v > 0.0f) o = 255;
+    }
+    masks[i] = o;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mtb_layernorm(const void* x, long long rows, int C, int ct_in, int ci, int planes_in, const float* gamma,
+                  const float* beta, float eps, void* y, int ct_out, int co, int planes_out, int gelu, void* stream) {
+  MTB_REQUIRE(x && y && gamma && beta && rows >= 0, "mtb_layernorm: bad arguments");
+  if (rows == 0) return 0;
+  const int block = 256;
+  layernorm_kernel<<<grid_for4(rows, block / 32), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(x), rows, C, ct_in, ci, rows * ct_in, planes_in, gamma, beta, eps,
+      static_cast<uint16_t*>(y), ct_out, co, rows * ct_out, planes_out, gelu);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_maxpool2x2(const void* x, void* y, int N, int H, int W, int C, int planes, void* stream) {
+  MTB_REQUIRE(x && y && (H % 2 == 0) && (W % 2 == 0), "mtb_maxpool2x2: bad arguments");
+  const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * C;
+  maxpool2x2_kernel<<<grid_for4(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), N, H, W, C, static_cast<long long>(N) * H * W * C, total,
+      planes);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_add_planes(const void* a, const void* b, void* out, long long rows, int C, long long b_rows, int planes,
+                   void* stream) {
+  MTB_REQUIRE(a && b && out && b_rows > 0, "mtb_add_planes: bad arguments");
+  add_planes_kernel<<<grid_for4(rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(a), static_cast<const uint16_t*>(b), static_cast<uint16_t*>(out), rows, C, b_rows,
+      rows * C, b_rows * C, rows * C, planes);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_attention(const mtb_attn_desc* d, void* stream) {
+  MTB_REQUIRE(d && d->q && d->k && d->v && d->out, "mtb_attention: null argument");
+  MTB_REQUIRE(d->hd >= 1 && d->hd <= kMaxHD, "mtb_attention: head dim %d not supported (<= %d)", d->hd, kMaxHD);
+  MTB_REQUIRE(!(d->mode == 1 && d->pool && (d->ws & 1)), "mtb_attention: pooled windows need an even window size");
+  AttnParams P;
+  P.B = d->B;
+  P.heads = d->heads;
+  P.hd = d->hd;
+  P.nq = d->nq;
+  P.nk = d->nk;
+  P.scale = d->scale;
+  P.q = static_cast<const uint16_t*>(d->q);
+  P.k = static_cast<const uint16_t*>(d->k);
+  P.v = static_cast<const uint16_t*>(d->v);
+  P.out = static_cast<uint16_t*>(d->out);
+  P.q_ct = d->q_ct; P.q_off = d->q_off; P.k_ct = d->k_ct; P.k_off = d->k_off;
+  P.v_ct = d->v_ct; P.v_off = d->v_off; P.o_ct = d->o_ct; P.o_off = d->o_off;
+  P.q_ps = d->q_ps; P.k_ps = d->k_ps; P.v_ps = d->v_ps; P.o_ps = d->o_ps;
+  P.planes = d->planes;
+  P.mode = d->mode;
+  P.grid_h = d->grid_h; P.grid_w = d->grid_w; P.ws = d->ws; P.pool = d->pool;
+  P.nwx = d->ws > 0 ? (d->grid_w + d->ws - 1) / d->ws : 1;
+  P.pad_q = d->pad_q; P.pad_k = d->pad_k; P.pad_v = d->pad_v;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(kKT) * (d->hd + 1) + static_cast<size_t>(kKT) * d->hd +
+                                       static_cast<size_t>(kQT) * d->hd);
+  MTB_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid(static_cast<unsigned>(d->B * d->heads), static_cast<unsigned>((d->nq + kQT - 1) / kQT));
+  attention_kernel<<<grid, kAttnThreads, smem, static_cast<cudaStream_t>(stream)>>>(P);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+
+int mtb_sam_patch_embed(const uint8_t* img, int H, int W, const float* mean3, const float* std3, const float* w,
+                        const float* b, const float* pos, int C, int k, int stride, int pad, void* out, int planes,
+                        void* stream) {
+  MTB_REQUIRE(img && mean3 && std3 && w && b && pos && out && C % 8 == 0, "mtb_sam_patch_embed: bad arguments");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const size_t smem = sizeof(float) * static_cast<size_t>(C) * 3 * k * k;
+  MTB_CUDA_OK(cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const long long total = static_cast<long long>(Ho) * Wo * (C / 8);
+  patch_embed_kernel<<<grid_for4(total, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      img, H, W, mean3, std3, w, b, pos, C, k, stride, pad, Ho, Wo, static_cast<uint16_t*>(out),
+      static_cast<long long>(Ho) * Wo * C, planes);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_sam_prompt_boxes(const float* boxes, float sx, float sy, int P, const float* gauss, int half, const float* pe2, const float* pe3,
+                         const float* not_a_point, float input_size, float* out, void* stream) {
+  MTB_REQUIRE(boxes && gauss && pe2 && pe3 && not_a_point && out, "mtb_sam_prompt_boxes: null argument");
+  if (P <= 0) return 0;
+  prompt_boxes_kernel<<<grid_for4(static_cast<long long>(P) * 6 * half, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      boxes, sx, sy, P, gauss, half, pe2, pe3, not_a_point, input_size, out);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_sam_hyper_masks(const void* up, int planes, const float* hyper, int P, int K, int C, long long npix, float* out,
+                        void* stream) {
+  MTB_REQUIRE(up && hyper && out && C <= 32, "mtb_sam_hyper_masks: bad arguments");
+  if (P <= 0) return 0;
+  hyper_masks_kernel<<<grid_for4(static_cast<long long>(P) * npix, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(up), static_cast<long long>(P) * npix * C, planes, hyper, P, K, C, npix, out);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_sam_select_mask(const float* logits, const float* iou, int P, int K, long long npix, float delta, float thresh,
+                        int* sel, void* stream) {
+  MTB_REQUIRE(logits && iou && sel, "mtb_sam_select_mask: null argument");
+  if (P <= 0) return 0;
+  select_mask_kernel<<<P, 512, 0, static_cast<cudaStream_t>(stream)>>>(logits, iou, K, npix, delta, thresh, sel);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_sam_mask_write(const float* logits, const int* sel, int K, int S, const float* boxes, int P, int H, int W,
+                       uint8_t* masks, float* logit_out, void* stream) {
+  MTB_REQUIRE(logits && sel && boxes && masks, "mtb_sam_mask_write: null argument");
+  if (P <= 0) return 0;
+  mask_write_kernel<<<grid_for4(static_cast<long long>(P) * H * W, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, sel, K, S, boxes, P, H, W, masks, logit_out);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+}  // extern "C"

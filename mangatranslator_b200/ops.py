@@ -19,7 +19,7 @@ class ConvPlan:
     """
 
     def __init__(self, x, w, bias, out, *, k=1, stride=1, pad=0, act=None, residual=None, tile_sums=None,
-                 tile=None, mode=0, pixel_shuffle=False, x_coff=0, out_coff=0, res_coff=0):
+                 tile=None, mode=0, pixel_shuffle=False, x_coff=0, out_coff=0, res_coff=0, res_bcast=False, act_after_res=False):
         """Channel slices: `x` / `out` / `residual` may be wider (concat) tensors; the layer reads channels
         [x_coff, x_coff + Cin) and writes [out_coff, out_coff + Cout).  The weights' Cin is padded to a multiple of
         64 with zeros, so whatever lies beyond the slice (or beyond the tensor: TMA zero-fills) contributes 0."""
@@ -42,6 +42,7 @@ class ConvPlan:
             d.out_ctotal, d.out_coff = out.shape[-1], out_coff
         if residual is not None:
             d.res_ctotal, d.res_coff = residual.shape[-1], res_coff
+        d.res_bcast, d.act_after_res = int(bool(res_bcast)), int(bool(act_after_res))
         d.mode = mode
         d.pixel_shuffle = int(bool(pixel_shuffle))
         self._keep = (x, w, bias, out, residual, tile_sums)

@@ -291,13 +291,36 @@ def predict(model: YoloV8Seg, img_bgr: np.ndarray, conf: float, imgsz: int, reti
     return dict(xyxy=boxes, conf=det[:, 4], cls=det[:, 5], masks=masks, anchors=anchors, raw=pred, proto=proto)
 
 
-def make_model(seed: int = 0, bias_objects: float = 0.0, cls_gain: float = 1.0, **cfg) -> YoloV8Seg:
-    """Seeded random weights (no checkpoint offline).  `bias_objects` shifts the class-logit bias of the head and
-    `cls_gain` scales its last layer so that scores spread out and a controllable fraction of anchors clears the
-    confidence threshold with margins far above the numerical noise (index parity is only well-posed then)."""
+def make_model(seed: int = 0, bias_objects: float = 0.0, cls_gain: float = 1.0, signal_init: bool = True,
+               **cfg) -> YoloV8Seg:
+    """Seeded random weights (no checkpoint offline).
+
+    PyTorch's default conv init shrinks the signal at every layer, so a 60-layer random network's outputs are almost
+    input-independent (every anchor gets the same score and NMS degenerates into tie-breaking).  `signal_init` draws
+    variance-preserving weights instead (N(0, 2.6/fan_in), small random biases) so activations stay O(1) and scores
+    differ from anchor to anchor.  `bias_objects` / `cls_gain` shift and scale the class logits so a controllable
+    fraction of anchors clears the confidence threshold with margins far above the numerical noise."""
     torch.manual_seed(seed)
     m = YoloV8Seg(**cfg).eval()
     with torch.no_grad():
+        if signal_init:
+            for mod in m.modules():
+                if isinstance(mod, (nn.Conv2d, nn.ConvTranspose2d)):
+                    fan_in = mod.weight[0].numel() if isinstance(mod, nn.Conv2d) else mod.weight.shape[0]
+                    mod.weight.normal_(0.0, (2.6 / fan_in) ** 0.5)
+                    if mod.bias is not None:
+                        mod.bias.normal_(0.0, 0.1)
+        if signal_init:
+            # calibrate the last 1x1 conv of every head branch on a probe image so the head outputs are O(1)
+            g = torch.Generator().manual_seed(seed + 1)
+            probe = torch.rand((1, 3, 160, 160), generator=g)
+            raw, _ = m.heads_raw(probe)
+            for i, (box, cls, mc) in enumerate(raw):
+                for seq, out, target in ((m.head.cv2[i], box, 2.0), (m.head.cv3[i], cls, 1.5), (m.head.cv4[i], mc, 1.0)):
+                    sd = float(out.std())
+                    if sd > 0:
+                        seq[-1].weight.mul_(target / sd)
+                        seq[-1].bias.mul_(target / sd)
         for seq in m.head.cv3:
             seq[-1].weight.mul_(cls_gain)
             seq[-1].bias.fill_(bias_objects)

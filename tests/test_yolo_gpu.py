@@ -12,17 +12,20 @@ NANO = dict(nc=1, depth=0.33, width=0.25, max_ch=1024)
 MEDIUM = dict(nc=1, depth=0.67, width=0.75, max_ch=768)
 
 
+def _image(seed, h, w):
+    """Low-frequency colour field + noise: no constant regions, so no two anchors see the same receptive field."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    low = rng.uniform(0, 255, size=(h // 16 + 2, w // 16 + 2, 3)).astype(np.float32)
+    low = cv2.resize(low, (w, h), interpolation=cv2.INTER_CUBIC)
+    return np.clip(low + rng.normal(0, 12, size=(h, w, 3)), 0, 255).astype(np.uint8)
+
+
 def _setup(cfg, h, w, seed, imgsz):
     from mangatranslator_b200.yolo import YoloB200
     from mangatranslator_b200.preproc import letterbox_device
-    m = Y.make_model(seed, bias_objects=-2.0, cls_gain=400.0, **cfg)
-    rng = np.random.default_rng(seed)
-    img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
-    # smooth blobs so the network sees structure, not only noise
-    import cv2
-    for _ in range(6):
-        cv2.circle(img, (int(rng.integers(0, w)), int(rng.integers(0, h))), int(rng.integers(15, 60)),
-                   tuple(int(v) for v in rng.integers(0, 256, 3)), -1)
+    m = Y.make_model(seed, bias_objects=-7.0, **cfg)
+    img = _image(seed, h, w)
     dev = torch.device("cuda:0")
     net = YoloB200(m.state_dict(), m.cfg, dev)
     lb = letterbox_device(torch.from_numpy(img).to(dev), imgsz, swap_rb=True)
@@ -31,6 +34,27 @@ def _setup(cfg, h, w, seed, imgsz):
     x = Y.preprocess(img, imgsz)
     assert tuple(x.shape[2:]) == tuple(lb.shape[:2])
     return m, net, g, x, img, lb
+
+
+def _well_posed_conf(m, x, lo=20, hi=60):
+    """A confidence threshold that ~lo..hi anchors clear, placed in the widest score gap, and the decision margins of
+    the oracle at that threshold (score gap at the cut, min gap between kept scores, min |IoU - 0.7|)."""
+    with torch.no_grad():
+        pred, _ = m(x)
+    sc = torch.sort(pred[0, 4], descending=True).values
+    gaps = sc[lo - 1:hi - 1] - sc[lo:hi]
+    k = lo + int(torch.argmax(gaps))
+    conf = float((sc[k - 1] + sc[k]) / 2)
+    top = sc[:k]
+    p = pred[0].t()
+    b = p[p[:, 4] > conf]
+    xyxy = torch.cat((b[:, :2] - b[:, 2:4] / 2, b[:, :2] + b[:, 2:4] / 2), 1)
+    iou = Y.box_iou_matrix(xyxy)
+    d = (iou - 0.7).abs()
+    d.fill_diagonal_(1.0)
+    if d.numel() == 0 or b.shape[0] < 2:
+        return conf, 0.0, 0.0, 0.0
+    return conf, float(gaps.max()), float((top[:-1] - top[1:]).min()), float(d.min())
 
 
 @pytest.mark.parametrize("cfg,hw,imgsz", [(NANO, (200, 320), 320), (MEDIUM, (192, 160), 192)], ids=["nano", "medium"])
@@ -47,13 +71,22 @@ def test_head_outputs_match_oracle(cfg, hw, imgsz):
 
 @pytest.mark.parametrize("cfg,hw,imgsz", [(NANO, (200, 320), 320), (NANO, (333, 250), 320)], ids=["wide", "tall"])
 def test_detections_match_oracle_and_reference_dedup(cfg, hw, imgsz):
-    m, net, g, x, img, lb = _setup(cfg, hw[0], hw[1], 5, imgsz)
-    conf = 0.6
+    # index parity is only well-posed when the oracle's own decisions are not knife-edge: walk seeds until the
+    # oracle's margins (score gap at the cut, gaps between kept scores, |IoU - 0.7|) are far above numerical noise
+    for seed in range(5, 40):
+        mm = Y.make_model(seed, bias_objects=-7.0, **cfg)
+        xx = Y.preprocess(_image(seed, hw[0], hw[1]), imgsz)
+        conf, cut_gap, min_gap, iou_margin = _well_posed_conf(mm, xx)
+        if cut_gap > 1e-4 and min_gap > 5e-5 and iou_margin > 1e-3:
+            break
+    else:
+        pytest.fail("no well-posed synthetic case found")
+    m, net, g, x, img, lb = _setup(cfg, hw[0], hw[1], seed, imgsz)
     ref = Y.predict(m, img, conf, imgsz)
     det, cnt, final_idx = net.detect(g, conf, hw, tuple(lb.shape[:2]), apply_reference_dedup=True)
     torch.cuda.synchronize()
     n_nms, n_final = int(cnt[0]), int(cnt[1])
-    assert n_nms == ref["xyxy"].shape[0] and n_nms > 3
+    assert n_nms == ref["xyxy"].shape[0] and n_nms > 3, (n_nms, ref["xyxy"].shape[0])
     d = det[:n_nms].cpu()
     assert torch.equal(d[:, 6].long(), ref["anchors"])          # bit-exact NMS indices (anchor ids, in score order)
     assert (d[:, :4] - ref["xyxy"]).abs().max().item() < 1e-2   # pixels
