@@ -1,0 +1,75 @@
+"""Per-image result cache with the reference's entry points (core/caching.py:12-658: UnifiedCache, get_cache).
+The reference hashes the whole page with SHA-256 two to four times per page to key size-1 LRU slots; on the batch
+path that is pure overhead, so this build keeps the API (set_current_image / get_* / set_*) but keys by object identity
+of the page and holds at most one page worth of entries."""
+from __future__ import annotations
+
+import threading
+from typing import Any, Dict, Optional
+
+
+class UnifiedCache:
+    def __init__(self):
+        self._lock = threading.Lock()
+        self._store: Dict[Any, Any] = {}
+        self._current = None
+
+    def set_current_image(self, image, verbose: bool = False) -> None:
+        with self._lock:
+            key = id(image)
+            if key != self._current:
+                self._store.clear()
+                self._current = key
+
+    def _get(self, key):
+        with self._lock:
+            return self._store.get(key)
+
+    def _set(self, key, value) -> None:
+        with self._lock:
+            self._store[key] = value
+
+    # YOLO
+    def get_yolo_cache_key(self, image, model_path, confidence, *extra):
+        return ("yolo", id(image), str(model_path), float(confidence)) + tuple(extra)
+
+    def get_yolo_detection(self, key):
+        return self._get(key)
+
+    def set_yolo_detection(self, key, value) -> None:
+        self._set(key, value)
+
+    # SAM
+    def get_sam_cache_key(self, image, *extra):
+        return ("sam", id(image)) + tuple(str(e) for e in extra)
+
+    def get_sam_masks(self, key):
+        return self._get(key)
+
+    def set_sam_masks(self, key, value) -> None:
+        self._set(key, value)
+
+    # upscale
+    def get_upscale_cache_key(self, image, factor, model_type, *extra):
+        return ("upscale", id(image), float(factor), str(model_type)) + tuple(extra)
+
+    def get_upscaled_image(self, key):
+        return self._get(key)
+
+    def set_upscaled_image(self, key, value) -> None:
+        self._set(key, value)
+
+    def clear(self) -> None:
+        with self._lock:
+            self._store.clear()
+            self._current = None
+
+
+_cache: Optional[UnifiedCache] = None
+
+
+def get_cache() -> UnifiedCache:
+    global _cache
+    if _cache is None:
+        _cache = UnifiedCache()
+    return _cache

@@ -1,0 +1,217 @@
+"""Model loader — drop-in for the reference's core/ml/model_manager.py (ModelManager singleton :57-69, load_* :617-1046,
+unload_* :1369-1493, get_model_manager :1520) for the hot-path models.
+
+`load_yolo_speech_bubble`, `load_sam2`, `load_upscale`, `load_upscale_lite` return B200-native objects that satisfy
+exactly what the stage functions touch on the third-party objects the reference returns:
+  YOLO     -> mangatranslator_b200.yolo.YoloB200     (callable -> [Results], .names)
+  SAM 2.1  -> (Sam2ProcessorB200, Sam2ModelB200)     (processor(...), model(...).pred_masks, post_process_masks)
+  upscaler -> mangatranslator_b200.rcan.RcanB200     (callable float32 (1,3,h,w) -> (1,3,2h,2w))
+Objects injected into ``ModelManager.models[ModelType.X]`` by a caller are returned as they are (the reference's tests /
+integrations do that).  Models outside the hot path (RT-DETR, OSB text, panels, Flux, SAM3) raise ModelError.
+"""
+from __future__ import annotations
+
+import gc
+import os
+import threading
+from enum import Enum
+from pathlib import Path
+from typing import Any, Dict, Optional
+
+import torch
+
+from mangatranslator_b200 import weights as W
+from mangatranslator_b200.core.device import get_best_device, get_best_dtype
+from mangatranslator_b200.utils.exceptions import ModelError
+from mangatranslator_b200.utils.logging import log_message
+
+
+class ModelType(Enum):
+    """Same member names as the reference (core/ml/model_manager.py:31-54)."""
+    UPSCALE = "upscale"
+    UPSCALE_LITE = "upscale_lite"
+    YOLO_SPEECH_BUBBLE = "yolo_speech_bubble"
+    YOLO_SPEECH_BUBBLE_V2 = "yolo_speech_bubble_v2"
+    YOLO_CONJOINED_BUBBLE = "yolo_conjoined_bubble"
+    YOLO_OSBTEXT = "yolo_osbtext"
+    YOLO_PANEL = "yolo_panel"
+    SAM2 = "sam2"
+    SAM3 = "sam3"
+    MANGA_OCR = "manga_ocr"
+    FLUX_KONTEXT = "flux_kontext"
+    FLUX_KLEIN = "flux_klein"
+
+
+class ModelManager:
+    _instance = None
+    _lock = threading.RLock()
+
+    def __new__(cls, *args, **kwargs):
+        with cls._lock:
+            if cls._instance is None:
+                cls._instance = super().__new__(cls)
+                cls._instance._initialized = False
+            return cls._instance
+
+    def __init__(self, models_dir: str = "./models"):
+        with self._lock:
+            if self._initialized:
+                return
+            self.device = get_best_device()
+            self.dtype = get_best_dtype(self.device)
+            self.models: Dict[ModelType, Any] = {}
+            self.models_dir = Path(models_dir)
+            self.model_paths: Dict[ModelType, Path] = {
+                ModelType.UPSCALE: self.models_dir / "upscale" / "2x-AnimeSharpV4_RCAN.safetensors",
+                ModelType.UPSCALE_LITE: self.models_dir / "upscale" / "2x-AnimeSharpV4_Fast_RCAN_PU.safetensors",
+                ModelType.YOLO_SPEECH_BUBBLE: self.models_dir / "yolo" / "yolov8m_seg-speech-bubble.pt",
+                ModelType.YOLO_SPEECH_BUBBLE_V2: self.models_dir / "yolo" / "manga109-segmentation-bubble.pt",
+            }
+            self.model_hf_repos: Dict[ModelType, str] = {
+                ModelType.SAM2: "facebook/sam2.1-hiera-large",
+                ModelType.YOLO_SPEECH_BUBBLE: "kitsumed/yolov8m_seg-speech-bubble",
+                ModelType.YOLO_SPEECH_BUBBLE_V2: "huyvux3005/manga109-segmentation-bubble",
+            }
+            self.hf_token: str = ""
+            self.flux_inference_lock = threading.Lock()
+            self.precision = os.environ.get("MTB200_PRECISION", "bf16x3")
+            self.synthetic_seed = int(os.environ.get("MTB200_WEIGHT_SEED", "0"))
+            self._initialized = True
+
+    # ---- helpers ---------------------------------------------------------------------------------------------
+    def _require_cuda(self) -> torch.device:
+        if not torch.cuda.is_available():
+            raise ModelError("CUDA device required: the B200 build has no CPU fallback")
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def set_hf_token(self, token: str) -> None:
+        self.hf_token = token or ""
+
+    def is_loaded(self, model_type: ModelType) -> bool:
+        return model_type in self.models
+
+    def _load_file_state_dict(self, path: Path) -> Optional[dict]:
+        if not path.exists():
+            return None
+        if path.suffix == ".safetensors":
+            from safetensors.torch import load_file
+            return load_file(str(path))
+        obj = torch.load(str(path), map_location="cpu")
+        return obj if isinstance(obj, dict) else None
+
+    # ---- loaders -----------------------------------------------------------------------------------------------
+    def _resolve_yolo_type(self, model_path) -> ModelType:
+        """core/ml/model_manager.py:702-709: only the resolved default v2 path maps to the V2 slot."""
+        try:
+            if model_path and Path(model_path).resolve() == self.model_paths[ModelType.YOLO_SPEECH_BUBBLE_V2].resolve():
+                return ModelType.YOLO_SPEECH_BUBBLE_V2
+        except Exception:
+            pass
+        return ModelType.YOLO_SPEECH_BUBBLE
+
+    def load_yolo_speech_bubble(self, model_path=None, verbose: bool = False):
+        mt = self._resolve_yolo_type(model_path)
+        with self._lock:
+            if mt in self.models:
+                return self.models[mt]
+            from mangatranslator_b200.yolo import YoloB200
+            dev = self._require_cuda()
+            cfg = W.yolo_cfg("m")
+            sd = self._load_file_state_dict(Path(model_path)) if model_path else None
+            if sd is None:
+                log_message("YOLO: no checkpoint on disk, using seeded synthetic weights (MTB200_WEIGHT_SEED)",
+                            verbose=verbose)
+                sd = W.yolo_state_dict(self.synthetic_seed, cfg)
+            self.models[mt] = YoloB200(sd, cfg, dev, precision=self.precision)
+            return self.models[mt]
+
+    def load_sam2(self, verbose: bool = False):
+        with self._lock:
+            if ModelType.SAM2 in self.models:
+                return self.models[ModelType.SAM2]
+            from mangatranslator_b200.sam2 import Sam2B200
+            from mangatranslator_b200.sam2_api import Sam2ModelB200, Sam2ProcessorB200
+            dev = self._require_cuda()
+            cfg, sd = W.sam2_model_and_state(self.synthetic_seed, os.environ.get("MTB200_SAM_VARIANT", "tiny"))
+            net = Sam2B200(sd, cfg, dev, precision=self.precision)
+            self.models[ModelType.SAM2] = (Sam2ProcessorB200(net), Sam2ModelB200(net))
+            return self.models[ModelType.SAM2]
+
+    def _load_rcan(self, mt: ModelType, verbose: bool):
+        with self._lock:
+            if mt in self.models:
+                return self.models[mt]
+            from mangatranslator_b200.rcan import RcanB200
+            dev = self._require_cuda()
+            sd = self._load_file_state_dict(self.model_paths[mt])
+            if sd is None:
+                log_message("Upscaler: no checkpoint on disk, using seeded synthetic RCAN weights", verbose=verbose)
+                sd = W.rcan_state_dict(self.synthetic_seed, n_resblocks=20 if mt == ModelType.UPSCALE else 6,
+                                       n_resgroups=10 if mt == ModelType.UPSCALE else 4)
+            self.models[mt] = RcanB200(sd, dev, precision=self.precision)
+            return self.models[mt]
+
+    def load_upscale(self, verbose: bool = False):
+        return self._load_rcan(ModelType.UPSCALE, verbose)
+
+    def load_upscale_lite(self, verbose: bool = False):
+        return self._load_rcan(ModelType.UPSCALE_LITE, verbose)
+
+    def _out_of_scope(self, what: str):
+        raise ModelError(f"{what} is outside the B200 hot path of this build (SURVEY.md §8f)")
+
+    def load_rtdetr_conjoined_bubble(self, verbose: bool = False):
+        if ModelType.YOLO_CONJOINED_BUBBLE in self.models:
+            return self.models[ModelType.YOLO_CONJOINED_BUBBLE]
+        self._out_of_scope("RT-DETRv2 conjoined-bubble detector")
+
+    def load_yolo_osbtext(self, token: str = "", verbose: bool = False):
+        if ModelType.YOLO_OSBTEXT in self.models:
+            return self.models[ModelType.YOLO_OSBTEXT]
+        self._out_of_scope("OSB text detector")
+
+    def load_yolo_panel(self, verbose: bool = False):
+        if ModelType.YOLO_PANEL in self.models:
+            return self.models[ModelType.YOLO_PANEL]
+        self._out_of_scope("panel detector")
+
+    def load_sam3(self, token: str = "", verbose: bool = False):
+        self._out_of_scope("SAM3")
+
+    # ---- lifecycle ---------------------------------------------------------------------------------------------
+    def unload_model(self, model_type: ModelType, force_gc: bool = True, verbose: bool = False) -> None:
+        with self._lock:
+            self.models.pop(model_type, None)
+        if force_gc:
+            self.clear_cache()
+
+    def unload_ocr_models(self, verbose: bool = False) -> None:
+        self.unload_model(ModelType.MANGA_OCR, verbose=verbose)
+
+    def unload_upscale_models(self, verbose: bool = False) -> None:
+        self.unload_model(ModelType.UPSCALE, verbose=verbose)
+        self.unload_model(ModelType.UPSCALE_LITE, verbose=verbose)
+
+    def unload_all(self, verbose: bool = False) -> None:
+        with self._lock:
+            self.models.clear()
+        self.clear_cache()
+
+    def clear_cache(self) -> None:
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+
+    def get_memory_stats(self) -> dict:
+        stats = {"loaded_models": [m.value for m in self.models]}
+        if torch.cuda.is_available():
+            stats["cuda_allocated_mb"] = torch.cuda.memory_allocated() / 2 ** 20
+            stats["cuda_reserved_mb"] = torch.cuda.memory_reserved() / 2 ** 20
+        return stats
+
+    def print_memory_stats(self) -> None:
+        log_message(f"Model memory: {self.get_memory_stats()}", always_print=True)
+
+
+def get_model_manager() -> ModelManager:
+    return ModelManager()

@@ -1,0 +1,212 @@
+"""Pipeline orchestration for the vision hot path — drop-in for the stage-calling skeleton of the reference's
+core/pipeline.py (`translate_and_render` :638-2024, `_clean_speech_bubbles_for_page` :76-130,
+`batch_translate_images` :2481-2731) in the modes that need no LLM / text renderer:
+
+    cleaning_only = True   detect -> segment -> clean [-> upscale_final_image]     (pipeline.py:995-996,1993-2000)
+    upscaling_only = True  upscale only                                             (pipeline.py:723-762)
+
+Anything that needs OCR/translation/rendering is outside this build and raises.
+
+Two entry levels:
+  * `translate_and_render` / `batch_translate_images`: the reference's signatures, PIL in / PIL + files out.
+  * `HotPathPipeline`: the device-resident batch engine the bench and the batch path use — pages go H2D once (pinned),
+    every stage runs in CUDA kernels, one D2H of the finished page.
+"""
+from __future__ import annotations
+
+import math
+import os
+import re
+import time
+from pathlib import Path
+from typing import Any, Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+from PIL import Image
+
+from mangatranslator_b200.core.batch_coordinator import PageShardCoordinator
+from mangatranslator_b200.core.caching import get_cache
+from mangatranslator_b200.core.config import MangaTranslatorConfig
+from mangatranslator_b200.core.image.cleaning import clean_pages_device, clean_speech_bubbles
+from mangatranslator_b200.core.image.detection import detect_pages_device, detect_speech_bubbles
+from mangatranslator_b200.core.image.image_utils import convert_image_to_target_mode, cv2_to_pil, upscale_image
+from mangatranslator_b200.core.ml.model_manager import get_model_manager
+from mangatranslator_b200.utils.exceptions import CancellationError, ImageProcessingError, ValidationError
+from mangatranslator_b200.utils.logging import log_message
+
+IMAGE_EXTS = {".png", ".jpg", ".jpeg", ".webp", ".bmp"}
+
+
+def _processing_scale(width: int, height: int, auto: bool = True) -> float:
+    return math.sqrt((width * height) / 1_000_000) if auto else 1.0     # pipeline.py:765-772
+
+
+def _clean_speech_bubbles_for_page(pil_image, config: MangaTranslatorConfig, bubble_data, processing_scale, verbose):
+    """pipeline.py:76-130: clean with the pre-computed detections; on failure keep the original page."""
+    try:
+        cleaned, processed = clean_speech_bubbles(
+            pil_image, config.yolo_model_path, config.detection.confidence, pre_computed_detections=bubble_data,
+            device=config.device, thresholding_value=config.cleaning.thresholding_value,
+            use_otsu_threshold=config.cleaning.use_otsu_threshold, roi_shrink_px=config.cleaning.roi_shrink_px,
+            verbose=verbose, processing_scale=processing_scale,
+            conjoined_confidence=config.detection.conjoined_confidence,
+            inpaint_colored_bubbles=config.cleaning.inpaint_colored_bubbles,
+            bubble_detector_model=config.detection.bubble_detector_model)
+        return cv2_to_pil(cleaned), processed
+    except Exception as e:
+        log_message(f"Error during bubble cleaning: {e}. Proceeding with uncleaned image.", always_print=True)
+        return pil_image, []
+
+
+def translate_and_render(image_path, config: MangaTranslatorConfig, output_path=None, cancellation_manager=None,
+                         previous_context_images=None, previous_context_texts=None,
+                         previous_context_texts_provider=None, ocr_texts_out=None) -> Image.Image:
+    start = time.time()
+    verbose = config.verbose
+    if not (config.cleaning_only or config.upscaling_only):
+        raise ValidationError("this build implements the vision hot path only: set cleaning_only or upscaling_only "
+                              "(translation/rendering are outside scope, SURVEY.md §8)")
+    if cancellation_manager is not None and cancellation_manager.is_cancelled():
+        raise CancellationError("Process cancelled by user.")
+    try:
+        pil = Image.open(image_path)
+        pil.load()
+    except Exception as e:
+        raise ImageProcessingError(f"Error loading image {image_path}: {e}")
+    target_mode = "RGBA" if (config.output.output_format == "png" and pil.mode in ("RGBA", "LA")) else "RGB"
+    pil = convert_image_to_target_mode(pil, target_mode, verbose)
+    if config.preprocessing.enabled:
+        pil = upscale_image(pil, config.preprocessing.factor, model_type="model_lite", verbose=verbose)
+    if config.upscaling_only:
+        out = upscale_image(pil, config.output.image_upscale_factor, model_type=config.output.image_upscale_model,
+                            verbose=verbose)
+    else:
+        scale = _processing_scale(pil.width, pil.height, config.preprocessing.auto_scale)
+        get_cache().set_current_image(pil, verbose)
+        try:
+            bubbles, _ = detect_speech_bubbles(
+                Path(image_path), config.yolo_model_path, config.detection.confidence, verbose=verbose,
+                device=config.device, seg_model=config.detection.seg_model,
+                conjoined_detection=config.detection.conjoined_detection,
+                conjoined_confidence=config.detection.conjoined_confidence, image_override=pil,
+                osb_enabled=config.outside_text.enabled,
+                osb_text_verification=config.detection.use_osb_text_verification,
+                bubble_detector_model=config.detection.bubble_detector_model)
+        except Exception as e:      # pipeline.py:797-800
+            log_message(f"Error during detection: {e}", always_print=True)
+            bubbles = []
+        out, _ = _clean_speech_bubbles_for_page(pil, config, bubbles, scale, verbose)
+        if config.output.upscale_final_image:
+            out = upscale_image(out, config.output.image_upscale_factor, model_type=config.output.image_upscale_model,
+                                verbose=verbose)
+    if output_path:
+        if out.mode != target_mode:
+            out = out.convert(target_mode)
+        Path(output_path).parent.mkdir(parents=True, exist_ok=True)
+        out.save(output_path)
+    log_message(f"Processing completed in {time.time() - start:.2f}s", always_print=True)
+    return out
+
+
+def _natural_key(p: Path):
+    return [int(t) if t.isdigit() else t.lower() for t in re.split(r"(\d+)", p.name)]
+
+
+def batch_translate_images(input_dir, config: MangaTranslatorConfig, output_dir=None, progress_callback=None,
+                           preserve_structure: bool = False, cancellation_manager=None, source_path_map=None) -> dict:
+    """Reference contract (pipeline.py:2481-2511): processes every image of `input_dir` in natural order and returns
+    {success_count, error_count, errors, failed_image_paths[, failed_paths_file]}.  When launched under torchrun the
+    pages are sharded across the ranks by PageShardCoordinator and rank 0 returns the merged result."""
+    input_dir = Path(input_dir)
+    files = sorted([p for p in input_dir.rglob("*") if p.suffix.lower() in IMAGE_EXTS], key=_natural_key)
+    out_dir = Path(output_dir) if output_dir else input_dir / "output_translated"
+    coord = PageShardCoordinator()
+    mine = coord.shard(list(enumerate(files)))
+    res = {"success_count": 0, "error_count": 0, "errors": {}, "failed_image_paths": []}
+    for k, (idx, path) in enumerate(mine):
+        if cancellation_manager is not None and cancellation_manager.is_cancelled():
+            break
+        rel = path.relative_to(input_dir) if preserve_structure else Path(path.name)
+        try:
+            translate_and_render(path, config, out_dir / rel, cancellation_manager)
+            res["success_count"] += 1
+        except Exception as e:
+            res["error_count"] += 1
+            res["errors"][str(path)] = str(e)
+            res["failed_image_paths"].append(str(path))
+        if progress_callback:
+            progress_callback((k + 1) / max(len(mine), 1), f"Processed {k + 1}/{len(mine)}")
+    parts = coord.gather(res)
+    if coord.rank != 0:
+        return res
+    merged = {"success_count": 0, "error_count": 0, "errors": {}, "failed_image_paths": []}
+    for p in parts:
+        merged["success_count"] += p["success_count"]
+        merged["error_count"] += p["error_count"]
+        merged["errors"].update(p["errors"])
+        merged["failed_image_paths"].extend(p["failed_image_paths"])
+    if merged["failed_image_paths"]:
+        out_dir.mkdir(parents=True, exist_ok=True)
+        fp = out_dir / "failed_paths.txt"
+        fp.write_text("\n".join(merged["failed_image_paths"]))
+        merged["failed_paths_file"] = str(fp)
+    return merged
+
+
+# ---- device-resident batch engine --------------------------------------------------------------------------------------
+class HotPathPipeline:
+    """detect -> segment -> clean -> upscale for a stream of pages, everything on the device.
+
+    `run_page(page_bgr_u8_host_pinned)`: H2D copy, YOLO detect (+NMS/dedup on device), SAM 2.1 masks, bubble cleaning,
+    RCAN 2x upscale, D2H of the uint8 result.  Per page there is one small D2H (the detection table) besides the final
+    image."""
+
+    def __init__(self, *, confidence: float = 0.6, imgsz: int = 1600, seg_model: str = "sam2", upscale: bool = True,
+                 upscale_model: str = "model", thresholding_value: int = 200, roi_shrink_px: int = 5,
+                 device: Optional[torch.device] = None):
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.confidence, self.imgsz, self.seg_model = confidence, imgsz, seg_model
+        self.upscale, self.upscale_model = upscale, upscale_model
+        self.thr, self.shrink = thresholding_value, roi_shrink_px
+        mm = get_model_manager()
+        self.yolo = mm.load_yolo_speech_bubble(None)
+        self.sam = mm.load_sam2() if seg_model == "sam2" else None
+        self.rcan = (mm.load_upscale() if upscale_model == "model" else mm.load_upscale_lite()) if upscale else None
+        self.stage_ms: Dict[str, float] = {}
+
+    def run_page_device(self, page_bgr: torch.Tensor, injected_boxes: Optional[np.ndarray] = None,
+                        timings: Optional[dict] = None):
+        """page_bgr: device uint8 HxWx3.  Returns (cleaned [and upscaled] page uint8 on device in RGB order when
+        upscaled else BGR, detections, clean results)."""
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        t = [ev() for _ in range(4)] if timings is not None else None
+        if t: t[0].record()
+        h, w = int(page_bgr.shape[0]), int(page_bgr.shape[1])
+        dets = detect_pages_device([page_bgr], confidence=self.confidence, imgsz=self.imgsz, seg_model=self.seg_model,
+                                   injected_boxes=None if injected_boxes is None else [injected_boxes])[0]
+        if t: t[1].record()
+        scale = _processing_scale(w, h)
+        batch = clean_pages_device([page_bgr], [dets], thresholding_value=self.thr, roi_shrink_px=self.shrink,
+                                   processing_scale=scale)
+        cleaned = batch.pages_out[0]
+        if t: t[2].record()
+        out = cleaned
+        if self.rcan is not None:
+            out = self.rcan.upscale_u8(cleaned, swap_rb=True)        # BGR page -> RGB model input/output
+        if t:
+            t[3].record()
+            torch.cuda.synchronize()
+            for name, a, b in (("detect_segment", 0, 1), ("clean", 1, 2), ("upscale", 2, 3)):
+                timings[name] = timings.get(name, 0.0) + t[a].elapsed_time(t[b])
+        return out, dets, batch
+
+    def run_page(self, page_bgr_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, **kw):
+        """Host (pinned) uint8 HxWx3 in, host uint8 out (the call a user of the stage API makes)."""
+        page = page_bgr_host.to(self.device, non_blocking=True)
+        out, dets, batch = self.run_page_device(page, **kw)
+        if out_host is None:
+            out_host = torch.empty(out.shape, dtype=torch.uint8, pin_memory=True)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host, dets, batch

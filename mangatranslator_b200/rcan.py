@@ -114,8 +114,8 @@ class RcanB200:
             grp_in = src
             x = grp_in
             for (w1, w2, cd1, cb1, cd2, cb2) in grp:
-                steps.append(("conv", conv(x, w1, b["u"], act="relu")))
-                steps.append(("conv", conv(b["u"], w2, b["t"], tile_sums=sums)))
+                steps.append(("conv_body", conv(x, w1, b["u"], act="relu")))
+                steps.append(("conv_body", conv(b["u"], w2, b["t"], tile_sums=sums)))
                 steps.append(("ca", (parts, cd1, cb1, cd2, cb2)))
                 dst = b["pa"] if x is not b["pa"] else b["pb"]
                 steps.append(("apply", (b["t"], x, dst)))     # RCAB: x + t * gate
@@ -141,7 +141,7 @@ class RcanB200:
         f = self.F
         inv_hw = 1.0 / float(h * w)
         for kind, arg in b["steps"]:
-            if kind == "conv":
+            if kind in ("conv", "conv_body"):
                 arg.run()
             elif kind == "ca":
                 parts, cd1, cb1, cd2, cb2 = arg
@@ -151,6 +151,33 @@ class RcanB200:
                 t, x, dst = arg
                 check(l.mtb_scale_residual(ptr(t), ptr(x), ptr(b["scale"]), ptr(dst), h * w, 1, f, self.planes, st),
                       "mtb_scale_residual")
+
+    def time_body_convs(self, img: torch.Tensor):
+        """CUDA-event duration (ms) of every RCAB body conv launch during one pass over `img` (bench roofline)."""
+        h, w, _ = img.shape
+        b = self._get(h, w)
+        evs = []
+        l, st = self.l, stream_ptr()
+        inv_hw = 1.0 / float(h * w)
+        for kind, arg in b["steps"]:
+            if kind == "conv_body":
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                arg.run()
+                e1.record()
+                evs.append((e0, e1))
+            elif kind == "conv":
+                arg.run()
+            elif kind == "ca":
+                parts, cd1, cb1, cd2, cb2 = arg
+                check(l.mtb_ca_scale(ptr(b["sums"]), 1, parts, self.F, inv_hw, ptr(cd1), ptr(cb1), ptr(cd2), ptr(cb2),
+                                     cd1.shape[0], ptr(b["scale"]), st), "mtb_ca_scale")
+            else:
+                t, x, dst = arg
+                check(l.mtb_scale_residual(ptr(t), ptr(x), ptr(b["scale"]), ptr(dst), h * w, 1, self.F, self.planes, st),
+                      "mtb_scale_residual")
+        torch.cuda.synchronize()
+        return [a.elapsed_time(c) for a, c in evs]
 
     def upscale_u8(self, img: torch.Tensor, *, swap_rb: bool = False, want_float: bool = False):
         """img: device uint8 HxWx(3|4).  Returns uint8 2Hx2Wx3 (same channel order as the model's RGB output unless

@@ -477,6 +477,26 @@ class Sam2B200:
             return masks, d["logits"], d["sel"], lo, iou
         return masks
 
+    def decode_lowres(self, enc: dict, boxes_xyxy: torch.Tensor, orig_hw: Tuple[int, int]) -> torch.Tensor:
+        """Low-res logits [P][256][256] of the selected mask (what Sam2Model returns as pred_masks)."""
+        self._last = (enc, boxes_xyxy.clone(), orig_hw)
+        self.decode(enc, boxes_xyxy, orig_hw)
+        d = self._dec[int(boxes_xyxy.shape[0])]
+        S = 4 * d["S"]
+        idx = d["sel"].long().view(-1, 1, 1).expand(-1, 1, S * S)
+        return torch.gather(d["logits"], 1, idx).view(-1, S, S)
+
+    def _last_full_masks(self, h: int, w: int) -> torch.Tensor:
+        """uint8 (P,H,W): bilinear upsample of the last decode's selected logits, > 0, WITHOUT the box clip."""
+        enc, boxes, _ = self._last
+        Pn = int(boxes.shape[0])
+        d = self._dec[Pn]
+        big = torch.tensor([[0.0, 0.0, float(w), float(h)]] * Pn, dtype=torch.float32, device=self.device)
+        masks = torch.empty((Pn, h, w), dtype=torch.uint8, device=self.device)
+        check(self.l.mtb_sam_mask_write(ptr(d["logits"]), ptr(d["sel"]), 4, 4 * d["S"], ptr(big), Pn, h, w, ptr(masks), None,
+                                        stream_ptr()), "mtb_sam_mask_write")
+        return masks
+
     def segment(self, img_rgb_u8: torch.Tensor, boxes_xyxy: torch.Tensor):
         enc = self.encode(img_rgb_u8)
         return self.decode(enc, boxes_xyxy, (img_rgb_u8.shape[0], img_rgb_u8.shape[1]))

@@ -1,0 +1,148 @@
+"""Weight sources for the hot-path models.
+
+Real checkpoints are read from ``$MT_MODELS_DIR`` when present (same file names the reference's ModelManager uses,
+core/ml/model_manager.py:108-119,183-204).  There is no network in the build / GPU containers and no checkpoint on
+disk, so otherwise the state dicts below are generated: correct key names and shapes for the architectures, seeded
+variance-preserving random values (so activations stay O(1) through the ~60-400 layer stacks and parity tests exercise
+every layer), with the YOLO / SAM heads calibrated to produce a realistic number of detections / non-trivial masks.
+The SAME tensors feed the CPU oracle (tests, bench cpu_baseline) and the CUDA path.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, Optional
+
+import torch
+
+
+def models_dir() -> Optional[str]:
+    d = os.environ.get("MT_MODELS_DIR")
+    return d if d and os.path.isdir(d) else None
+
+
+def _gen(seed: int) -> torch.Generator:
+    return torch.Generator().manual_seed(seed)
+
+
+def _conv(g, cout, cin, k, gain=1.0, bias_std=0.02):
+    fan_in = cin * k * k
+    w = torch.randn((cout, cin, k, k), generator=g) * (gain / math.sqrt(fan_in))
+    b = torch.randn((cout,), generator=g) * bias_std
+    return w, b
+
+
+# ---- RCAN (2x-AnimeSharpV4 architecture family) -----------------------------------------------------------------
+def rcan_state_dict(seed: int = 0, n_resgroups: int = 10, n_resblocks: int = 20, n_feats: int = 64,
+                    reduction: int = 16) -> Dict[str, torch.Tensor]:
+    g = _gen(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def put(name, w, b):
+        sd[name + ".weight"], sd[name + ".bias"] = w, b
+
+    f = n_feats
+    put("head.0", *_conv(g, f, 3, 3, gain=1.4))
+    for gi in range(n_resgroups):
+        for bi in range(n_resblocks):
+            base = f"body.{gi}.body.{bi}.body"
+            put(base + ".0", *_conv(g, f, f, 3, gain=1.4))          # conv + ReLU
+            put(base + ".2", *_conv(g, f, f, 3, gain=0.5))          # residual branch kept small, like trained nets
+            put(base + ".3.conv_du.0", *_conv(g, f // reduction, f, 1, gain=1.0))
+            put(base + ".3.conv_du.2", *_conv(g, f, f // reduction, 1, gain=1.0))
+        put(f"body.{gi}.body.{n_resblocks}", *_conv(g, f, f, 3, gain=0.5))
+    put(f"body.{n_resgroups}", *_conv(g, f, f, 3, gain=0.5))
+    put("tail.0.0", *_conv(g, 4 * f, f, 3, gain=1.0))
+    put("tail.1", *_conv(g, 3, f, 3, gain=0.3))
+    sd["tail.1.bias"] = torch.full((3,), 0.5)                        # mid-grey output so pixels are not clipped
+    return sd
+
+
+# ---- YOLOv8-seg ---------------------------------------------------------------------------------------------------
+def yolo_cfg(variant: str = "m", nc: int = 1) -> dict:
+    depth, width, max_ch = {"n": (0.33, 0.25, 1024), "s": (0.33, 0.50, 1024), "m": (0.67, 0.75, 768),
+                            "l": (1.0, 1.0, 512), "x": (1.0, 1.25, 512)}[variant]
+    return dict(nc=nc, depth=depth, width=width, max_ch=max_ch, nm=32, npr=256)
+
+
+def yolo_state_dict(seed: int = 0, cfg: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+    """Keys follow the layer naming of mangatranslator_b200.yolo / oracle.yolo_oracle (l0..l21, head.*)."""
+    cfg = cfg or yolo_cfg("m")
+    g = _gen(seed)
+    depth, width, max_ch = cfg["depth"], cfg["width"], cfg["max_ch"]
+    d = lambda n: max(round(n * depth), 1)
+    c = lambda x: int(math.ceil(min(x, max_ch) * width / 8) * 8)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, cin, cout, k, gain=1.6):
+        w, b = _conv(g, cout, cin, k, gain=gain, bias_std=0.1)
+        sd[name + ".weight"], sd[name + ".bias"] = w, b
+
+    def c2f(name, c1, c2, n):
+        hc = c2 // 2
+        conv(f"{name}.cv1.conv", c1, 2 * hc, 1)
+        conv(f"{name}.cv2.conv", (2 + n) * hc, c2, 1)
+        for i in range(n):
+            conv(f"{name}.m.{i}.cv1.conv", hc, hc, 3)
+            conv(f"{name}.m.{i}.cv2.conv", hc, hc, 3)
+
+    c64, c128, c256, c512, c1024 = c(64), c(128), c(256), c(512), c(1024)
+    conv("l0.conv", 3, c64, 3)
+    conv("l1.conv", c64, c128, 3)
+    c2f("l2", c128, c128, d(3))
+    conv("l3.conv", c128, c256, 3)
+    c2f("l4", c256, c256, d(6))
+    conv("l5.conv", c256, c512, 3)
+    c2f("l6", c512, c512, d(6))
+    conv("l7.conv", c512, c1024, 3)
+    c2f("l8", c1024, c1024, d(3))
+    conv("l9.cv1.conv", c1024, c1024 // 2, 1)
+    conv("l9.cv2.conv", c1024 // 2 * 4, c1024, 1)
+    c2f("l12", c1024 + c512, c512, d(3))
+    c2f("l15", c512 + c256, c256, d(3))
+    conv("l16.conv", c256, c256, 3)
+    c2f("l18", c256 + c512, c512, d(3))
+    conv("l19.conv", c512, c512, 3)
+    c2f("l21", c512 + c1024, c1024, d(3))
+    nc, nm = cfg["nc"], cfg["nm"]
+    ch = (c256, c512, c1024)
+    c2h, c3h, c4h = max(16, ch[0] // 4, 64), max(ch[0], min(nc, 100)), max(ch[0] // 4, nm)
+    for i, x in enumerate(ch):
+        for br, hcx, oc in (("cv2", c2h, 64), ("cv3", c3h, nc), ("cv4", c4h, nm)):
+            conv(f"head.{br}.{i}.0.conv", x, hcx, 3)
+            conv(f"head.{br}.{i}.1.conv", hcx, hcx, 3)
+            conv(f"head.{br}.{i}.2", hcx, oc, 1, gain=0.05)
+    npr = c(cfg["npr"])
+    conv("head.proto.cv1.conv", c256, npr, 3)
+    w = torch.randn((npr, npr, 2, 2), generator=g) * (1.6 / math.sqrt(npr))
+    sd["head.proto.upsample.weight"], sd["head.proto.upsample.bias"] = w, torch.randn((npr,), generator=g) * 0.1
+    conv("head.proto.cv2.conv", npr, npr, 3)
+    conv("head.proto.cv3.conv", npr, nm, 1)
+    return sd
+
+
+# ---- SAM 2.1 ----------------------------------------------------------------------------------------------------------
+def sam2_model_and_state(seed: int = 0, variant: str = "tiny"):
+    """(config, state_dict).  Initialisation and (when a checkpoint directory exists) loading go through the same
+    library the reference uses (`transformers`, core/ml/model_manager.py:996-1005); no forward pass happens here."""
+    from transformers import Sam2Config, Sam2Model
+    d = models_dir()
+    if d and os.path.isdir(os.path.join(d, "sam")):
+        m = Sam2Model.from_pretrained(os.path.join(d, "sam"))
+        return m.config, m.state_dict()
+    torch.manual_seed(seed)
+    if variant == "tiny":
+        cfg = Sam2Config()
+    else:  # hiera-large: the checkpoint the reference actually loads (core/ml/model_manager.py:202-204)
+        cfg = Sam2Config()
+        bc = cfg.vision_config.backbone_config
+        bc.hidden_size, bc.embed_dim_per_stage = 144, [144, 288, 576, 1152]
+        bc.blocks_per_stage, bc.num_attention_heads_per_stage = [2, 6, 36, 4], [2, 4, 8, 16]
+        bc.global_attention_blocks, bc.window_size_per_stage = [23, 33, 43], [8, 4, 16, 8]
+        bc.window_positional_embedding_background_size = [7, 7]
+        cfg.vision_config.backbone_channel_list = [1152, 576, 288, 144]
+    m = Sam2Model(cfg).eval()
+    with torch.no_grad():
+        for mlp in m.mask_decoder.output_hypernetworks_mlps:   # default init gives |logit| ~ 1e-2: widen for real masks
+            mlp.proj_out.weight.mul_(100.0)
+    return cfg, m.state_dict()

