@@ -1,0 +1,130 @@
+"""CPU: host-side logic of the boundary — parameter scaling vs the reference, box post-processing vs the reference,
+page sharding over torch.distributed (gloo, world size 2), drop-in aliasing."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_scaling_matches_reference_when_present():
+    import _refimport
+    from mangatranslator_b200.core import scaling as ours
+    if not _refimport.available():
+        pytest.skip("reference tree not present")
+    _refimport.import_reference()
+    import core.scaling as ref
+    for s in [None, 0.0, 0.3, 0.8868, 1.0, 1.2541, 2.0, 3.7, 9.5, 40.0]:
+        for k in [(7, 7), (5, 5), (3, 9)]:
+            assert ours.scale_kernel(k, s) == ref.scale_kernel(k, s)
+        assert ours.scale_area(50, s, minimum=50, maximum=5000) == ref.scale_area(50, s, minimum=50, maximum=5000)
+        assert ours.scale_scalar(5, s, minimum=0.0, maximum=64.0) == ref.scale_scalar(5, s, minimum=0.0, maximum=64.0)
+        assert ours.scale_length(12, s) == ref.scale_length(12, s)
+
+
+def test_scaling_known_values():
+    from mangatranslator_b200 import clean_host as H
+    p = H.build_params(200, False, 5, (1536 * 1024 / 1e6) ** 0.5)
+    assert (p.kd, p.ke, p.min_area) == (9, 7, 79.0)
+    p = H.build_params(200, False, 5, (1024 * 768 / 1e6) ** 0.5)
+    assert (p.kd, p.ke, p.min_area) == (7, 5, 50.0)
+
+
+def test_box_postprocessing_matches_reference():
+    import _refimport
+    from mangatranslator_b200.core.image import detection as ours
+    if not _refimport.available():
+        pytest.skip("reference tree not present")
+    core = _refimport.import_reference()
+    import core.image.detection as ref
+    rng = np.random.default_rng(1)
+    for _ in range(30):
+        n = int(rng.integers(1, 30))
+        xy = rng.uniform(0, 800, size=(n, 2))
+        wh = rng.uniform(10, 300, size=(n, 2))
+        b = torch.from_numpy(np.concatenate([xy, xy + wh], 1).astype(np.float32))
+        if n > 3:
+            b[1] = b[0] + 2.0
+            b[2, :2] = b[0, :2] + 5
+            b[2, 2:] = b[0, 2:] - 5
+        c = torch.from_numpy(rng.uniform(0.3, 1.0, size=n).astype(np.float32))
+        rb, rk = ref._deduplicate_primary_boxes(b, c, 0.7)
+        ob, ok = ours._deduplicate_primary_boxes(b, c, 0.7)
+        assert rk == ok and torch.equal(rb, ob)
+        rb2, ri = ref._remove_contained_boxes(rb, [("primary", i) for i in rk])
+        ob2, oi = ours._remove_contained_boxes(ob, [("primary", i) for i in ok])
+        assert ri == oi and torch.equal(rb2, ob2)
+        m1 = ref._build_rect_mask_from_box(b[0], 600, 700)
+        m2 = ours._build_rect_mask_from_box(b[0], 600, 700)
+        assert np.array_equal(m1, m2)
+
+
+def test_batch_coordinator_helpers():
+    from mangatranslator_b200.core import batch_coordinator as bc
+    c = bc.BatchRequestCoordinator(2)
+    assert c.map_ordered([lambda i=i: i * i for i in range(6)]) == [0, 1, 4, 9, 16, 25]
+    with c.slot():
+        assert c.in_slot()
+        with c.slot():
+            pass
+    assert bc.bboxes_overlap((0, 0, 10, 10), (5, 5, 20, 20)) and not bc.bboxes_overlap((0, 0, 10, 10), (10, 0, 20, 10))
+    m = np.zeros((100, 200), np.uint8)
+    m[40:60, 50:90] = 1
+    assert bc.expanded_mask_bbox(m, (200, 100)) == (0, 0, 170, 100)
+    waves = bc.partition_non_overlapping_waves([(0, 0, 10, 10), (20, 0, 30, 10), (5, 5, 25, 25), None], lambda b: b)
+    assert [len(w) for w in waves] == [2, 1, 1]
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+from mangatranslator_b200.core.batch_coordinator import PageShardCoordinator
+c = PageShardCoordinator(backend="gloo")
+pages = list(range(11))
+mine = c.shard(pages)
+assert all(c.owner_of(i) == c.rank for i in mine)
+c.barrier()
+got = c.gather(dict(rank=c.rank, pages=mine))
+mx = c.all_reduce_max(float(c.rank + 1))
+assert mx == float(c.world)
+if c.rank == 0:
+    allp = sorted(p for g in got for p in g["pages"])
+    assert allp == pages, allp
+    print("SHARD_OK", [g["pages"] for g in got])
+c.close()
+"""
+
+
+def test_page_sharding_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(script)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "SHARD_OK [[0, 2, 4, 6, 8, 10], [1, 3, 5, 7, 9]]" in out.stdout
+
+
+def test_drop_in_aliases_share_singletons():
+    import mangatranslator_b200.drop_in as d
+    saved = {k: sys.modules.get(k) for k, _ in d._MODULES}
+    try:
+        for k, _ in d._MODULES:
+            sys.modules.pop(k, None)
+        d.install()
+        import core.ml.model_manager as a
+        import mangatranslator_b200.core.ml.model_manager as b
+        assert a is b and a.get_model_manager() is b.get_model_manager()
+        from core.image.cleaning import clean_speech_bubbles  # noqa: F401
+        from utils.exceptions import CleaningError  # noqa: F401
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

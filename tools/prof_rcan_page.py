@@ -1,0 +1,12 @@
+"""One RCAN page (bf16x3) for an ncu launch list."""
+import sys
+sys.path.insert(0, ".")
+import torch
+from mangatranslator_b200 import weights as W
+from mangatranslator_b200.rcan import RcanB200
+dev = torch.device("cuda:0")
+net = RcanB200(W.rcan_state_dict(0), dev)
+img = torch.randint(0, 256, (1536, 1024, 3), dtype=torch.uint8, device=dev)
+net.upscale_u8(img)
+torch.cuda.synchronize()
+print("done")
