@@ -58,11 +58,14 @@ typedef struct mtb_conv_plan mtb_conv_plan;
 
 /* x: bf16 [planes_in][N][H][W][x_ctotal]; w: bf16 [planes_in][KH*KW][Cout][Cin]; bias: fp32 [Cout] or NULL;
  * out: bf16 [planes_out][N][Ho][Wo][Cout] (or fp32 [N][Ho][Wo][Cout]); residual: like out (res_planes) or NULL;
- * tile_sums: fp32 [mtb_conv_plan_num_mtiles()*4][Cout] or NULL (per-warp channel sums of the output). */
+ * tile_sums: fp32 [mtb_conv_plan_num_sum_rows()][Cout] or NULL (partial channel sums of the output). */
 int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, const float* bias, void* out,
                          const void* residual, float* tile_sums, mtb_conv_plan** plan);
 int mtb_conv_plan_run(mtb_conv_plan* plan, void* stream);
 int mtb_conv_plan_num_mtiles(const mtb_conv_plan* plan);
+/* rows of the tile_sums buffer this plan writes ([rows][Cout] fp32): per (CTA, lane quarter) when the launch covers a
+ * single image, else per (pixel tile, lane quarter) */
+int mtb_conv_plan_num_sum_rows(const mtb_conv_plan* plan);
 void mtb_conv_plan_destroy(mtb_conv_plan* plan);
 
 /* ---- bubble cleaning (bit-exact integer path) ------------------------------------------------------------

@@ -166,6 +166,7 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
   }
   p.residual = static_cast<const uint16_t*>(residual);
   p.tile_sums = tile_sums;
+  p.sums_per_cta = 0;
   p.pixel_shuffle = d->pixel_shuffle ? 1 : 0;
   p.res_bcast = d->res_bcast ? 1 : 0;
   p.act_after_res = d->act_after_res ? 1 : 0;
@@ -185,6 +186,8 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
   }
   p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
   p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
+  // global-average-pool partials: one row per (CTA, lane quarter) when a launch covers a single image
+  p.sums_per_cta = (p.N == 1 && p.n_tiles_n == 1) ? 1 : 0;
   pl->nsplit = d->planes_in == 2 ? 3 : 1;
   int cols = 32;
   while (cols < 2 * p.BN) cols <<= 1;
@@ -243,6 +246,16 @@ int mtb_conv_plan_run(mtb_conv_plan* plan, void* stream) {
 
 int mtb_conv_plan_num_mtiles(const mtb_conv_plan* plan) {
   return plan ? plan->p.N * plan->p.tiles_y * plan->p.tiles_x : 0;
+}
+
+int mtb_conv_plan_num_sum_rows(const mtb_conv_plan* plan) {
+  if (!plan) return 0;
+  const long long total = static_cast<long long>(plan->p.N) * plan->p.tiles_y * plan->p.tiles_x * plan->p.n_tiles_n;
+  if (!plan->p.sums_per_cta) return static_cast<int>(static_cast<long long>(plan->p.N) * plan->p.tiles_y * plan->p.tiles_x * 4);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return static_cast<int>((total < sms ? total : sms) * 4);
 }
 
 void mtb_conv_plan_destroy(mtb_conv_plan* plan) { delete plan; }

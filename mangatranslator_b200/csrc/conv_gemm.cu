@@ -165,6 +165,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int tx = r - ty * p.TW;
     int as = 0;
     uint32_t aphase = 0;
+    float cta_sums[4] = {0.f, 0.f, 0.f, 0.f};   // per-CTA channel sums of this warp's chunks (sums_per_cta mode)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(tile, p);
       const int n0 = t.nt * p.BN;
@@ -183,7 +184,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-        epilogue_chunk16<ACT>(p, v, valid, pix, n0 + c0, t.n, oy, ox, lane, q, mtile);
+        epilogue_chunk16<ACT>(p, v, valid, pix, n0 + c0, t.n, oy, ox, lane, q, mtile, cta_sums[(c0 >> 6) & 3]);
       }
       tc_fence_before();
       __syncwarp();
@@ -192,6 +193,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         as = 0;
         aphase ^= 1;
       }
+    }
+    if (p.tile_sums && p.sums_per_cta && lane < 16) {
+      for (int c0 = cg * 16, k = 0; c0 < p.BN; c0 += 64, ++k)
+        p.tile_sums[(static_cast<long long>(blockIdx.x) * 4 + q) * p.Cout + c0 + lane] = cta_sums[k];
     }
   }
 

@@ -42,7 +42,10 @@ struct ConvParams {
   uint16_t* out;               // bf16 planes [planes_out][N][Ho][Wo][Cout]
   float* out_f32;              // optional fp32 output [N][Ho][Wo][Cout]
   const uint16_t* residual;    // optional, same geometry as out, added after the activation
-  float* tile_sums;            // optional [N*tiles_y*tiles_x][4][Cout] per-warp channel sums of the output
+  float* tile_sums;            // optional per-warp channel sums of the output (global-average-pool partials):
+                               //   sums_per_cta == 0: [N*tiles_y*tiles_x][4][Cout], one row per (tile, lane quarter)
+                               //   sums_per_cta == 1: [gridDim.x][4][Cout], accumulated over the CTA's tiles (N == 1)
+  int sums_per_cta;
   int in_coff;                 // first input channel inside the (wider) input tensor
   int out_cstride, out_coff;   // channel count of the output tensor and first channel written (concat slices)
   int res_cstride, res_coff;   // same for the residual tensor

@@ -91,6 +91,18 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int n = tile / tiles_per_img;
         const int rem = tile - n * tiles_per_img;
         const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
+        // pull the halos of the tile three iterations ahead into L2 while this one streams into shared memory: the
+        // 3-slot ring only hides ~1.5 tiles of latency, so the eventual TMA load should be an L2 hit
+        {
+          const int pt = tile + 3 * gridDim.x;
+          if (pt < total_tiles) {
+            const int pn = pt / tiles_per_img;
+            const int prem = pt - pn * tiles_per_img;
+            const int pty = prem / p.tiles_x, ptx = prem - pty * p.tiles_x;
+            for (int pl = 0; pl < PLANES; ++pl)
+              tma_prefetch_l2_4d(&tmA, 0, ptx * kTW - 1, pty * kTH - 1, pl * p.N + pn);
+          }
+        }
         for (int pl = 0; pl < PLANES; ++pl) {
           mbar_wait(&empty_bar[slot], phase ^ 1);
           mbar_expect_tx(&full_bar[slot], kHaloBytes);
@@ -158,6 +170,7 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int c0 = cg * 16;
     int as = 0;
     uint32_t aphase = 0;
+    float cta_sum = 0.f;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n = tile / tiles_per_img;
       const int rem = tile - n * tiles_per_img;
@@ -186,12 +199,14 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      epilogue_chunk16<ACT>(p, v, valid, pix, c0, n, oy, ox, lane, q, tile);
+      epilogue_chunk16<ACT>(p, v, valid, pix, c0, n, oy, ox, lane, q, tile, cta_sum);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
       }
     }
+    if (p.tile_sums && p.sums_per_cta && lane < 16)
+      p.tile_sums[(static_cast<long long>(blockIdx.x) * 4 + q) * 64 + c0 + lane] = cta_sum;
   }
 
   tc_fence_before();

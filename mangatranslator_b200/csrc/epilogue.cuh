@@ -28,7 +28,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 
 template <int ACT>
 __device__ __forceinline__ void epilogue_chunk16(const ConvParams& p, float (&v)[16], bool valid, long long pix, int cbase,
-                                                 int n, int oy, int ox, int lane, int q, long long mtile) {
+                                                 int n, int oy, int ox, int lane, int q, long long mtile,
+                                                 float& cta_sum) {
   if (p.bias) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + cbase);
 #pragma unroll
@@ -93,7 +94,8 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvParams& p, float (&v)
         s[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
       }
     }
-    if (lane < 16) p.tile_sums[(mtile * 4 + q) * p.Cout + cbase + lane] = s[0];
+    if (p.sums_per_cta) cta_sum += s[0];   // fixed tile order per CTA -> deterministic
+    else if (lane < 16) p.tile_sums[(mtile * 4 + q) * p.Cout + cbase + lane] = s[0];
   }
   if (!valid) return;
   if (p.out_f32) {

@@ -56,6 +56,11 @@ class ConvPlan:
     def num_mtiles(self) -> int:
         return lib().mtb_conv_plan_num_mtiles(self._h)
 
+    @property
+    def num_sum_rows(self) -> int:
+        """Rows of the tile_sums buffer ([rows][Cout] fp32) this plan writes."""
+        return lib().mtb_conv_plan_num_sum_rows(self._h)
+
     def run(self) -> None:
         check(lib().mtb_conv_plan_run(self._h, stream_ptr()), "mtb_conv_plan_run")
 

@@ -106,7 +106,7 @@ class RcanB200:
         # head conv: only 3 of the 64 padded input channels are non-zero (per-tap kernel)
         steps.append(("conv", conv(b["x_in"], self.w_head, b["head"], mode=1)))
         probe = conv(b["head"], self.blocks[0][0][0][0], b["u"], act="relu")
-        parts = probe.num_mtiles * 4
+        parts = probe.num_sum_rows
         sums = torch.zeros((parts, f), dtype=torch.float32, device=dev)
         b["sums"] = sums
         src = b["head"]

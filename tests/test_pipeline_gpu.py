@@ -77,14 +77,19 @@ def test_reference_shaped_stage_functions(small_models, tmp_path):
     boxes = torch.from_numpy(pg.boxes_xyxy)
     dup = torch.cat([boxes, boxes[:1] + 1.0])                        # one near-duplicate the dedup must remove
 
+    class FakeBoxes:
+        def __init__(self):
+            self.xyxy, self.conf, self.cls = dup.clone(), torch.tensor([0.9, 0.8, 0.7, 0.65]), torch.zeros(4)
+
+        def __len__(self):
+            return 4
+
     class FakeYolo:
         names = {0: "speech_bubble"}
 
         def __call__(self, im, conf, device, verbose, imgsz, retina_masks):
             assert imgsz == 1600 and retina_masks
-            b = SimpleNamespace(xyxy=dup.clone(), conf=torch.tensor([0.9, 0.8, 0.7, 0.65]), cls=torch.zeros(4))
-            b.__class__.__len__ = lambda self: 4
-            return [SimpleNamespace(boxes=b, masks=None, orig_shape=im.shape[:2], names=self.names)]
+            return [SimpleNamespace(boxes=FakeBoxes(), masks=None, orig_shape=im.shape[:2], names=self.names)]
 
     real = mm.models[ModelType.YOLO_SPEECH_BUBBLE]
     mm.models[ModelType.YOLO_SPEECH_BUBBLE] = FakeYolo()
