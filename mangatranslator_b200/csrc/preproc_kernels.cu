@@ -6,8 +6,12 @@
 //     Pillow-style separable resampling with int16 weights and a uint8 intermediate
 //                                                             (reference call: core/image/detection.py:494-495)
 #include <math.h>
+#include <string.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "../../include/mtb200.h"
@@ -149,6 +153,30 @@ void aa_weights(int in_size, int out_size, std::vector<int>& start, std::vector<
     }
 }
 
+// Coefficient tables depend only on the geometry: build + upload once, keep on the device (no per-call H2D / sync,
+// which also makes the calls CUDA-graph capturable).
+std::mutex g_tab_mu;
+std::map<std::tuple<int, int, int, int, int>, void*> g_tab_cache;
+
+void* cached_table(int kind, int a, int b, int c, int d, const std::vector<char>& bytes) {
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  auto key = std::make_tuple(kind, a, b, c, d);
+  auto it = g_tab_cache.find(key);
+  if (it != g_tab_cache.end()) return it->second;
+  void* dev = nullptr;
+  if (cudaMalloc(&dev, bytes.size()) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(dev, bytes.data(), bytes.size(), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  g_tab_cache[key] = dev;
+  return dev;
+}
+bool table_cached(int kind, int a, int b, int c, int d, void** out) {
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  auto it = g_tab_cache.find(std::make_tuple(kind, a, b, c, d));
+  if (it == g_tab_cache.end()) return false;
+  *out = it->second;
+  return true;
+}
+
 int sm_count3() {
   static int sms = 0;
   if (!sms) {
@@ -193,46 +221,53 @@ int mtb_letterbox_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* dst, i
     g_launches.fetch_add(1);
     return 0;
   }
-  // coefficient tables exactly as cv::resize builds them (resize.cpp, INTER_LINEAR, 8-bit)
-  std::vector<int> xofs(nw), yofs(2 * nh);
-  std::vector<short> xa(2 * nw), ya(2 * nh);
-  const double scale_x = 1.0 / (static_cast<double>(nw) / sw), scale_y = 1.0 / (static_cast<double>(nh) / sh);
-  for (int dx = 0; dx < nw; ++dx) {
-    float fx = static_cast<float>((dx + 0.5) * scale_x - 0.5);
-    int sx = static_cast<int>(floorf(fx));
-    fx -= sx;
-    if (sx < 0) {
-      fx = 0;
-      sx = 0;
+  // coefficient tables exactly as cv::resize builds them (resize.cpp, INTER_LINEAR, 8-bit), cached per geometry
+  void* tab = nullptr;
+  if (!table_cached(0, sh, sw, nh, nw, &tab)) {
+    std::vector<int> xofs(nw), yofs(2 * nh);
+    std::vector<short> xa(2 * nw), ya(2 * nh);
+    const double scale_x = 1.0 / (static_cast<double>(nw) / sw), scale_y = 1.0 / (static_cast<double>(nh) / sh);
+    for (int dx = 0; dx < nw; ++dx) {
+      float fx = static_cast<float>((dx + 0.5) * scale_x - 0.5);
+      int sx = static_cast<int>(floorf(fx));
+      fx -= sx;
+      if (sx < 0) {
+        fx = 0;
+        sx = 0;
+      }
+      if (sx >= sw - 1) {
+        fx = 0;
+        sx = sw - 1;
+      }
+      xofs[dx] = sx;
+      xa[2 * dx] = sat_short(cv_round_f((1.f - fx) * 2048.f));
+      xa[2 * dx + 1] = sat_short(cv_round_f(fx * 2048.f));
     }
-    if (sx >= sw - 1) {
-      fx = 0;
-      sx = sw - 1;
+    for (int dy = 0; dy < nh; ++dy) {
+      float fy = static_cast<float>((dy + 0.5) * scale_y - 0.5);
+      int sy = static_cast<int>(floorf(fy));
+      fy -= sy;
+      yofs[2 * dy] = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);
+      yofs[2 * dy + 1] = sy + 1 < 0 ? 0 : (sy + 1 > sh - 1 ? sh - 1 : sy + 1);
+      ya[2 * dy] = sat_short(cv_round_f((1.f - fy) * 2048.f));
+      ya[2 * dy + 1] = sat_short(cv_round_f(fy * 2048.f));
     }
-    xofs[dx] = sx;
-    xa[2 * dx] = sat_short(cv_round_f((1.f - fx) * 2048.f));
-    xa[2 * dx + 1] = sat_short(cv_round_f(fx * 2048.f));
+    std::vector<char> bytes(sizeof(int) * (nw + 2 * nh) + sizeof(short) * (2 * nw + 2 * nh));
+    char* w = bytes.data();
+    memcpy(w, xofs.data(), sizeof(int) * nw);
+    w += sizeof(int) * nw;
+    memcpy(w, yofs.data(), sizeof(int) * 2 * nh);
+    w += sizeof(int) * 2 * nh;
+    memcpy(w, xa.data(), sizeof(short) * 2 * nw);
+    w += sizeof(short) * 2 * nw;
+    memcpy(w, ya.data(), sizeof(short) * 2 * nh);
+    tab = cached_table(0, sh, sw, nh, nw, bytes);
+    MTB_REQUIRE(tab != nullptr, "mtb_letterbox_u8: table upload failed");
   }
-  for (int dy = 0; dy < nh; ++dy) {
-    float fy = static_cast<float>((dy + 0.5) * scale_y - 0.5);
-    int sy = static_cast<int>(floorf(fy));
-    fy -= sy;
-    const int s0 = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);
-    const int s1 = sy + 1 < 0 ? 0 : (sy + 1 > sh - 1 ? sh - 1 : sy + 1);
-    yofs[2 * dy] = s0;
-    yofs[2 * dy + 1] = s1;
-    ya[2 * dy] = sat_short(cv_round_f((1.f - fy) * 2048.f));
-    ya[2 * dy + 1] = sat_short(cv_round_f(fy * 2048.f));
-  }
-  int* d_xofs = tables_dev;
+  int* d_xofs = static_cast<int*>(tab);
   int* d_yofs = d_xofs + nw;
   short* d_xa = reinterpret_cast<short*>(d_yofs + 2 * nh);
   short* d_ya = d_xa + 2 * nw;
-  MTB_CUDA_OK(cudaMemcpyAsync(d_xofs, xofs.data(), sizeof(int) * nw, cudaMemcpyHostToDevice, st));
-  MTB_CUDA_OK(cudaMemcpyAsync(d_yofs, yofs.data(), sizeof(int) * 2 * nh, cudaMemcpyHostToDevice, st));
-  MTB_CUDA_OK(cudaMemcpyAsync(d_xa, xa.data(), sizeof(short) * 2 * nw, cudaMemcpyHostToDevice, st));
-  MTB_CUDA_OK(cudaMemcpyAsync(d_ya, ya.data(), sizeof(short) * 2 * nh, cudaMemcpyHostToDevice, st));
-  MTB_CUDA_OK(cudaStreamSynchronize(st));  // the host tables go out of scope
   letterbox_kernel<<<grid, 256, 0, st>>>(src, sh, sw, sc, dst, dh, dw, top, left, nh, nw, pad_value, swap_rb, d_xofs,
                                          d_xa, d_yofs, d_ya);
   MTB_CUDA_OK(cudaGetLastError());
@@ -246,27 +281,50 @@ int mtb_resize_aa_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp, u
                      int* tables_dev, long long tables_ints, void* stream) {
   MTB_REQUIRE(src && tmp && dst && tables_dev, "mtb_resize_aa_u8: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::vector<int> hs, hl, vs, vl;
-  std::vector<short> hw, vw;
-  int hk = 0, hp = 0, vk = 0, vp = 0;
-  aa_weights(sw, ow, hs, hl, hw, hk, hp);
-  aa_weights(sh, oh, vs, vl, vw, vk, vp);
-  const long long need =
-      2LL * ow + 2LL * oh + (static_cast<long long>(ow) * hk + static_cast<long long>(oh) * vk + 3) / 2 + 4;
-  MTB_REQUIRE(tables_ints >= need, "mtb_resize_aa_u8: tables scratch too small (%lld < %lld ints)", tables_ints, need);
-  int* d_hs = tables_dev;
+  int hk = static_cast<int>(ceil(sw >= ow ? static_cast<double>(sw) / ow : 1.0)) * 2 + 1;
+  int vk = static_cast<int>(ceil(sh >= oh ? static_cast<double>(sh) / oh : 1.0)) * 2 + 1;
+  int hp = 0, vp = 0;
+  void* tab = nullptr;
+  if (!table_cached(1, sh, sw, oh, ow, &tab)) {
+    std::vector<int> hs, hl, vs, vl;
+    std::vector<short> hw, vw;
+    aa_weights(sw, ow, hs, hl, hw, hk, hp);
+    aa_weights(sh, oh, vs, vl, vw, vk, vp);
+    std::vector<char> bytes(sizeof(int) * (2 + 2 * ow + 2 * oh) + sizeof(short) * (hw.size() + vw.size() + 2));
+    char* w = bytes.data();
+    const int precs[2] = {hp, vp};
+    memcpy(w, precs, sizeof(precs));
+    w += sizeof(precs);
+    memcpy(w, hs.data(), sizeof(int) * ow);
+    w += sizeof(int) * ow;
+    memcpy(w, hl.data(), sizeof(int) * ow);
+    w += sizeof(int) * ow;
+    memcpy(w, vs.data(), sizeof(int) * oh);
+    w += sizeof(int) * oh;
+    memcpy(w, vl.data(), sizeof(int) * oh);
+    w += sizeof(int) * oh;
+    memcpy(w, hw.data(), sizeof(short) * hw.size());
+    w += sizeof(short) * (hw.size() + (hw.size() & 1));
+    memcpy(w, vw.data(), sizeof(short) * vw.size());
+    tab = cached_table(1, sh, sw, oh, ow, bytes);
+    MTB_REQUIRE(tab != nullptr, "mtb_resize_aa_u8: table upload failed");
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    g_tab_cache[std::make_tuple(2, sh, sw, oh, ow)] = reinterpret_cast<void*>(static_cast<intptr_t>(hp * 64 + vp));
+  }
+  {
+    void* pv = nullptr;
+    table_cached(2, sh, sw, oh, ow, &pv);
+    const intptr_t code = reinterpret_cast<intptr_t>(pv);
+    hp = static_cast<int>(code / 64);
+    vp = static_cast<int>(code % 64);
+  }
+  int* d_hs = static_cast<int*>(tab) + 2;
   int* d_hl = d_hs + ow;
   int* d_vs = d_hl + ow;
   int* d_vl = d_vs + oh;
   short* d_hw = reinterpret_cast<short*>(d_vl + oh);
-  short* d_vw = d_hw + static_cast<long long>(ow) * hk + ((static_cast<long long>(ow) * hk) & 1);
-  MTB_CUDA_OK(cudaMemcpyAsync(d_hs, hs.data(), sizeof(int) * ow, cudaMemcpyHostToDevice, st));
-  MTB_CUDA_OK(cudaMemcpyAsync(d_hl, hl.data(), sizeof(int) * ow, cudaMemcpyHostToDevice, st));
-  MTB_CUDA_OK(cudaMemcpyAsync(d_vs, vs.data(), sizeof(int) * oh, cudaMemcpyHostToDevice, st));
-  MTB_CUDA_OK(cudaMemcpyAsync(d_vl, vl.data(), sizeof(int) * oh, cudaMemcpyHostToDevice, st));
-  MTB_CUDA_OK(cudaMemcpyAsync(d_hw, hw.data(), sizeof(short) * hw.size(), cudaMemcpyHostToDevice, st));
-  MTB_CUDA_OK(cudaMemcpyAsync(d_vw, vw.data(), sizeof(short) * vw.size(), cudaMemcpyHostToDevice, st));
-  MTB_CUDA_OK(cudaStreamSynchronize(st));
+  const size_t hw_n = static_cast<size_t>(ow) * hk;
+  short* d_vw = d_hw + hw_n + (hw_n & 1);
   const int grid = sm_count3() * 8;
   const uint8_t* cur = src;
   int cur_w = sw, cur_c = sc;

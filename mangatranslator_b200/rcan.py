@@ -179,24 +179,41 @@ class RcanB200:
         torch.cuda.synchronize()
         return [a.elapsed_time(c) for a, c in evs]
 
-    def upscale_u8(self, img: torch.Tensor, *, swap_rb: bool = False, want_float: bool = False):
-        """img: device uint8 HxWx(3|4).  Returns uint8 2Hx2Wx3 (same channel order as the model's RGB output unless
-        swap_rb), and optionally the float output before quantisation (2Hx2Wx3)."""
-        assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_contiguous()
-        h, w, c = img.shape
-        b = self._get(h, w)
+    def _upscale_static(self, b: dict, h: int, w: int, c: int, swap_rb: bool, want_float: bool) -> None:
+        """page in b['in_u8'] -> b['out_u8'] (and b['out_f']); only static buffers, so the sequence can be graph-captured."""
         l, st = self.l, stream_ptr()
         mean = [m * self.rgb_range for m in self.DIV2K_MEAN] if self.norm else [0.0, 0.0, 0.0]
         sub = (C.c_float * 3)(*mean)
-        check(l.mtb_image_to_planes(ptr(img), h, w, c, int(swap_rb), self.rgb_range / 255.0, sub, ptr(b["x_in"]), 64,
+        check(l.mtb_image_to_planes(ptr(b["in_u8"]), h, w, c, int(swap_rb), self.rgb_range / 255.0, sub, ptr(b["x_in"]), 64,
                                     self.planes, st), "mtb_image_to_planes")
         self._run_body(b, h, w)
-        out = torch.empty((2 * h, 2 * w, 3), dtype=torch.uint8, device=self.device)
-        outf = torch.empty((2 * h, 2 * w, 3), dtype=torch.float32, device=self.device) if want_float else None
         add = (C.c_float * 3)(*mean)
-        check(l.mtb_f32_to_u8(ptr(b["out32"]), 4 * h * w, 16, add, 1.0 / self.rgb_range, ptr(out), ptr(outf), st),
-              "mtb_f32_to_u8")
-        return (out, outf) if want_float else out
+        check(l.mtb_f32_to_u8(ptr(b["out32"]), 4 * h * w, 16, add, 1.0 / self.rgb_range, ptr(b["out_u8"]),
+                              ptr(b["out_f"]) if want_float else None, st), "mtb_f32_to_u8")
+
+    def upscale_u8(self, img: torch.Tensor, *, swap_rb: bool = False, want_float: bool = False):
+        """img: device uint8 HxWx(3|4).  Returns uint8 2Hx2Wx3 (RGB model output; `swap_rb` feeds a BGR page), and
+        optionally the float output before quantisation (2Hx2Wx3).  The returned tensors are the model's static output
+        buffers: consume (copy) them before the next call."""
+        from . import graphs
+        assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_contiguous()
+        h, w, c = img.shape
+        b = self._get(h, w)
+        key = ("io", c)
+        if key not in b:
+            b[key] = True
+            b["in_u8"] = torch.empty((h, w, c), dtype=torch.uint8, device=self.device)
+            b["out_u8"] = torch.empty((2 * h, 2 * w, 3), dtype=torch.uint8, device=self.device)
+            b["out_f"] = torch.empty((2 * h, 2 * w, 3), dtype=torch.float32, device=self.device)
+        b["in_u8"].copy_(img)
+        gkey = ("graph", c, bool(swap_rb), bool(want_float))
+        if graphs.ENABLED:
+            if gkey not in b:
+                b[gkey] = graphs.CapturedGraph(lambda: self._upscale_static(b, h, w, c, swap_rb, want_float))
+            b[gkey].replay()
+        else:
+            self._upscale_static(b, h, w, c, swap_rb, want_float)
+        return (b["out_u8"], b["out_f"]) if want_float else b["out_u8"]
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         """Reference call shape (core/image/image_utils.py:369-374): float32 (1,3,h,w) in [0,1] -> (1,3,2h,2w)."""

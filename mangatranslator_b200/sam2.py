@@ -424,19 +424,30 @@ class Sam2B200:
     # ---- public ----------------------------------------------------------------------------------------------------
     def encode(self, img_rgb_u8: torch.Tensor) -> dict:
         """img_rgb_u8: device uint8 HxWx3 (RGB).  Runs resize -> normalise -> patch embed -> Hiera -> neck."""
+        from . import graphs
         if self._enc is None:
             self._enc = self._build_encoder()
+            self._enc["in1024"] = torch.empty((self.img, self.img, 3), dtype=torch.uint8, device=self.device)
         enc = self._enc
         x = img_rgb_u8
         if x.shape[0] != self.img or x.shape[1] != self.img:
             x = resize_aa_device(x, self.img, self.img)
+        enc["in1024"].copy_(x[:, :, :3])
         w = self.sd["vision_encoder.backbone.patch_embed.projection.weight"]
         b = self.sd["vision_encoder.backbone.patch_embed.projection.bias"]
-        g = self.img // 4
-        check(self.l.mtb_sam_patch_embed(ptr(x), self.img, self.img, ptr(self.norm_mean), ptr(self.norm_std), ptr(w), ptr(b),
-                                         ptr(self.pos_embed), w.shape[0], 7, 4, 3, ptr(enc["x0"]), self.planes,
-                                         stream_ptr()), "mtb_sam_patch_embed")
-        self._run(enc["steps"])
+
+        def body():
+            check(self.l.mtb_sam_patch_embed(ptr(enc["in1024"]), self.img, self.img, ptr(self.norm_mean), ptr(self.norm_std),
+                                             ptr(w), ptr(b), ptr(self.pos_embed), w.shape[0], 7, 4, 3, ptr(enc["x0"]),
+                                             self.planes, stream_ptr()), "mtb_sam_patch_embed")
+            self._run(enc["steps"])
+
+        if graphs.ENABLED:
+            if "cuda_graph" not in enc:
+                enc["cuda_graph"] = graphs.CapturedGraph(body)
+            enc["cuda_graph"].replay()
+        else:
+            body()
         return enc
 
     def decode(self, enc: dict, boxes_xyxy: torch.Tensor, orig_hw: Tuple[int, int], *, want_logits: bool = False):
@@ -447,32 +458,58 @@ class Sam2B200:
         dev = self.device
         if Pn == 0:
             return torch.zeros((0, H, W), dtype=torch.uint8, device=dev)
-        boxes = boxes_xyxy.to(device=dev, dtype=torch.float32).contiguous()
+        from . import graphs
         if Pn not in self._dec:
             self._dec[Pn] = self._build_decoder(Pn, enc)
+            self._dec[Pn]["boxes_in"] = torch.zeros((Pn, 4), dtype=torch.float32, device=dev)
         d = self._dec[Pn]
-        l, st = self.l, stream_ptr()
-        check(l.mtb_sam_prompt_boxes(ptr(boxes), float(self.img / W), float(self.img / H), Pn, ptr(self.gauss_prompt),
-                                     self.hidden // 2, ptr(self.pe2), ptr(self.pe3), ptr(self.not_a_point), float(self.img),
-                                     ptr(d["sparse"]), st), "mtb_sam_prompt_boxes")
+        d["boxes_in"].copy_(boxes_xyxy.to(dtype=torch.float32))
+        boxes = d["boxes_in"]
+        l = self.l
         T, S = d["T"], d["S"]
-        tokens = torch.cat([self.out_tokens.unsqueeze(0).expand(Pn, -1, -1), d["sparse"]], 1)      # [P][9][256]
-        tp = P.split_planes(tokens.reshape(1, 1, Pn * T, self.hidden), self.planes)
-        d["pe_q"].copy_(tp)
-        d["queries0"].copy_(tp)
-        d["keys0"].copy_(enc["emb"].expand(-1, Pn, -1, -1, -1))
-        self._run(d["steps"])
-        hyper = torch.stack([d["hyp_out"][k][0, 0, 2 + k::T, :] for k in range(4)], 1).contiguous()   # [P][4][32]
-        iou = d["iou_o"][0, 0, 1::T, :4].contiguous()                                                   # [P][4]
         npix = 16 * S * S
-        check(l.mtb_sam_hyper_masks(ptr(d["up2"]), self.planes, ptr(hyper), Pn, 4, 32, npix, ptr(d["logits"]), st),
-              "mtb_sam_hyper_masks")
-        check(l.mtb_sam_select_mask(ptr(d["logits"]), ptr(iou), Pn, 4, npix, self.stab_delta, self.stab_thresh, ptr(d["sel"]),
-                                    st), "mtb_sam_select_mask")
-        masks = torch.empty((Pn, H, W), dtype=torch.uint8, device=dev)
-        lo = torch.empty((Pn, H, W), dtype=torch.float32, device=dev) if want_logits else None
-        check(l.mtb_sam_mask_write(ptr(d["logits"]), ptr(d["sel"]), 4, 4 * S, ptr(boxes), Pn, H, W, ptr(masks), ptr(lo), st),
-              "mtb_sam_mask_write")
+        gkey = ("graph", H, W)
+        if "hyper" not in d:
+            d["hyper"] = torch.zeros((Pn, 4, 32), dtype=torch.float32, device=dev)
+            d["iou"] = torch.zeros((Pn, 4), dtype=torch.float32, device=dev)
+        mkey = ("masks", H, W)
+        if mkey not in d:
+            d[mkey] = torch.empty((Pn, H, W), dtype=torch.uint8, device=dev)
+
+        def body():
+            st = stream_ptr()
+            check(l.mtb_sam_prompt_boxes(ptr(boxes), float(self.img / W), float(self.img / H), Pn, ptr(self.gauss_prompt),
+                                         self.hidden // 2, ptr(self.pe2), ptr(self.pe3), ptr(self.not_a_point),
+                                         float(self.img), ptr(d["sparse"]), st), "mtb_sam_prompt_boxes")
+            tokens = torch.cat([self.out_tokens.unsqueeze(0).expand(Pn, -1, -1), d["sparse"]], 1)      # [P][9][256]
+            tp = P.split_planes(tokens.reshape(1, 1, Pn * T, self.hidden), self.planes)
+            d["pe_q"].copy_(tp)
+            d["queries0"].copy_(tp)
+            d["keys0"].copy_(enc["emb"].expand(-1, Pn, -1, -1, -1))
+            self._run(d["steps"])
+            d["hyper"].copy_(torch.stack([d["hyp_out"][k][0, 0, 2 + k::T, :] for k in range(4)], 1))    # [P][4][32]
+            d["iou"].copy_(d["iou_o"][0, 0, 1::T, :4])                                                   # [P][4]
+            check(l.mtb_sam_hyper_masks(ptr(d["up2"]), self.planes, ptr(d["hyper"]), Pn, 4, 32, npix, ptr(d["logits"]), st),
+                  "mtb_sam_hyper_masks")
+            check(l.mtb_sam_select_mask(ptr(d["logits"]), ptr(d["iou"]), Pn, 4, npix, self.stab_delta, self.stab_thresh,
+                                        ptr(d["sel"]), st), "mtb_sam_select_mask")
+            if not want_logits:
+                check(l.mtb_sam_mask_write(ptr(d["logits"]), ptr(d["sel"]), 4, 4 * S, ptr(boxes), Pn, H, W, ptr(d[mkey]), None,
+                                           st), "mtb_sam_mask_write")
+
+        if graphs.ENABLED and not want_logits:
+            if gkey not in d:
+                d[gkey] = graphs.CapturedGraph(body)
+            d[gkey].replay()
+        else:
+            body()
+        masks = d[mkey]
+        iou = d["iou"]
+        lo = None
+        if want_logits:
+            lo = torch.empty((Pn, H, W), dtype=torch.float32, device=dev)
+            check(l.mtb_sam_mask_write(ptr(d["logits"]), ptr(d["sel"]), 4, 4 * S, ptr(boxes), Pn, H, W, ptr(masks), ptr(lo),
+                                       stream_ptr()), "mtb_sam_mask_write")
         if want_logits:
             return masks, d["logits"], d["sel"], lo, iou
         return masks

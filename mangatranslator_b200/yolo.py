@@ -253,12 +253,25 @@ class YoloB200:
     # ---- public ----------------------------------------------------------------------------------------------
     def forward_letterboxed(self, lb_rgb_u8: torch.Tensor):
         """lb_rgb_u8: device uint8 [H][W][3] RGB letterboxed input.  Runs the graph; returns the graph dict."""
+        from . import graphs
         h, w, c = lb_rgb_u8.shape
         g = self._get(1, h, w)
-        zero = (C.c_float * 3)(0.0, 0.0, 0.0)
-        check(self.l.mtb_image_to_planes(ptr(lb_rgb_u8), h, w, c, 0, 1.0 / 255.0, zero, ptr(g["x_in"]), 8, self.planes,
-                                         stream_ptr()), "mtb_image_to_planes")
-        self._run_graph(g)
+        if "lb_in" not in g:
+            g["lb_in"] = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+
+        def body():
+            zero = (C.c_float * 3)(0.0, 0.0, 0.0)
+            check(self.l.mtb_image_to_planes(ptr(g["lb_in"]), h, w, 3, 0, 1.0 / 255.0, zero, ptr(g["x_in"]), 8, self.planes,
+                                             stream_ptr()), "mtb_image_to_planes")
+            self._run_graph(g)
+
+        g["lb_in"].copy_(lb_rgb_u8[:, :, :3])
+        if graphs.ENABLED:
+            if "cuda_graph" not in g:
+                g["cuda_graph"] = graphs.CapturedGraph(body)
+            g["cuda_graph"].replay()
+        else:
+            body()
         return g
 
     def detect(self, g: dict, conf: float, orig_hw: Tuple[int, int], lb_hw: Tuple[int, int], *, iou: float = 0.7,
