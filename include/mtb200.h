@@ -176,6 +176,12 @@ typedef struct mtb_yolo_level {
 int mtb_yolo_decode(const mtb_yolo_level* levels /* host */, int n_levels, int N, int nc, int ncp, float conf,
                     int max_cand, float* cand, int* cand_anchor, int* count, void* stream);
 
+/* retina masks (ultralytics process_mask_native, detection.py:1338-1345 retina_masks=True): out u8 [n][H][W] in {0,1};
+ * rows (optional) selects rows of det; (top,left,ch,cw) = prototype crop that strips the letterbox padding */
+int mtb_yolo_masks(const float* proto, int mh, int mw, int nm, const float* const* mc_levels /* host array of 3 device ptrs */,
+                   const int* level_hw /* host 3x2 */, const float* det, const int* rows, int n, int top, int left, int ch,
+                   int cw, int H, int W, uint8_t* out, void* stream);
+
 typedef struct mtb_nms_params {
   int N, max_cand, max_det;
   float iou_thr, max_wh;

@@ -51,6 +51,7 @@ struct ConvParams {
   int res_cstride, res_coff;   // same for the residual tensor
   int res_bcast;               // 1: the residual has batch 1 and is shared by all N images
   int act_after_res;           // 1: activation is applied after the residual add
+  int debug;                   // perf experiments only (halo kernel): 1 skip stores, 2 skip MMA issue, 4 skip TMA loads
   int pixel_shuffle;           // 1: Cout = 4 blocks of Cout/4 channels, block (dy*2+dx) is stored at pixel (2y+dy, 2x+dx)
 };
 

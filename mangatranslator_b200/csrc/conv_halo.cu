@@ -14,6 +14,8 @@
 //     traffic per MMA is then 128 B/clk for the N=128 instruction, i.e. matched to the SMEM bandwidth.
 //   * ring of 3 shared-memory slots, one (tile, plane) halo per slot, so the next tile's hi plane streams in while the
 //     current tile's lo plane is being multiplied; 2 TMEM accumulator stages overlap the epilogue with the next tile.
+#include <stdlib.h>
+
 #include "conv_gemm.cuh"
 #include "epilogue.cuh"
 
@@ -105,8 +107,12 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
         for (int pl = 0; pl < PLANES; ++pl) {
           mbar_wait(&empty_bar[slot], phase ^ 1);
-          mbar_expect_tx(&full_bar[slot], kHaloBytes);
-          tma_load_4d(sA + slot * kSlotBytes, &tmA, &full_bar[slot], 0, txi * kTW - 1, tyi * kTH - 1, pl * p.N + n);
+          if (p.debug & 4) {
+            mbar_arrive(&full_bar[slot]);
+          } else {
+            mbar_expect_tx(&full_bar[slot], kHaloBytes);
+            tma_load_4d(sA + slot * kSlotBytes, &tmA, &full_bar[slot], 0, txi * kTW - 1, tyi * kTH - 1, pl * p.N + n);
+          }
           if (++slot == kSlots) {
             slot = 0;
             phase ^= 1;
@@ -134,7 +140,7 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         if (lane == 0) {
           const uint32_t sa = smem_u32(sA + slot * kSlotBytes);
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < ((p.debug & 2) ? 1 : 9); ++tap) {
             const int ky = tap / 3, kx = tap - ky * 3;
             const uint32_t a0 = sa + (ky * kHW + kx) * 128;
             const uint32_t b0 = sw + tap * kTapBytes;
@@ -199,7 +205,7 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      epilogue_chunk16<ACT>(p, v, valid, pix, c0, n, oy, ox, lane, q, tile, cta_sum);
+      epilogue_chunk16<ACT>(p, v, valid && !(p.debug & 1), pix, c0, n, oy, ox, lane, q, tile, cta_sum);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -223,8 +229,10 @@ bool conv_halo_eligible(const ConvParams& p, int cin) {
          (p.residual == nullptr || (p.res_coff == 0 && p.res_cstride == 64 && !p.res_bcast)) && !p.pixel_shuffle;
 }
 
-int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int nsplit,
+int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p_in, int nsplit,
                      cudaStream_t stream) {
+  ConvParams p = p_in;
+  if (const char* e = getenv("MTB200_HALO_DEBUG")) p.debug = atoi(e);
   const size_t smem = 1024 + kWBytes + kSlots * kSlotBytes + 16 * 8 + 16;
   int dev = 0, sms = 0;
   MTB_CUDA_OK(cudaGetDevice(&dev));

@@ -363,6 +363,57 @@ __global__ void nms_kernel(NmsParams P, const float* __restrict__ cand, const in
   }
 }
 
+
+// ---- retina masks (ultralytics process_mask_native): coeff . proto -> strip letterbox pad -> bilinear to the page ->
+//      zero outside the box -> > 0.  One thread per page pixel per detection; the 32-term dot product is evaluated at the
+//      four neighbouring prototype pixels.
+struct MaskLevel {
+  const float* mc;  // [H][W][32]
+  int H, W, anchor0;
+};
+__global__ void yolo_masks_kernel(const float* __restrict__ proto, int mh, int mw, int nm, MaskLevel l0, MaskLevel l1,
+                                  MaskLevel l2, const float* __restrict__ det /* [n][8] */, const int* __restrict__ rows,
+                                  int n, int top, int left, int ch, int cw, int H, int W, uint8_t* __restrict__ out) {
+  const long long per = static_cast<long long>(H) * W;
+  const long long total = per * n;
+  const float sy = static_cast<float>(ch) / static_cast<float>(H), sx = static_cast<float>(cw) / static_cast<float>(W);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i / per);
+    const long long r = i - static_cast<long long>(k) * per;
+    const int y = static_cast<int>(r / W), x = static_cast<int>(r - static_cast<long long>(y) * W);
+    const float* d = det + static_cast<long long>(rows ? rows[k] : k) * 8;
+    uint8_t o = 0;
+    const float fxp = static_cast<float>(x), fyp = static_cast<float>(y);
+    if (fxp >= d[0] && fxp < d[2] && fyp >= d[1] && fyp < d[3]) {
+      const int a = static_cast<int>(d[6]);
+      const MaskLevel& L = a >= l2.anchor0 ? l2 : (a >= l1.anchor0 ? l1 : l0);
+      const float* c = L.mc + static_cast<long long>(a - L.anchor0) * nm;
+      float fy = sy * (fyp + 0.5f) - 0.5f, fx = sx * (fxp + 0.5f) - 0.5f;
+      if (fy < 0.f) fy = 0.f;
+      if (fx < 0.f) fx = 0.f;
+      const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+      const int y1 = y0 + (y0 < ch - 1 ? 1 : 0), x1 = x0 + (x0 < cw - 1 ? 1 : 0);
+      const float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
+      const float* p00 = proto + (static_cast<long long>(y0 + top) * mw + x0 + left) * nm;
+      const float* p01 = proto + (static_cast<long long>(y0 + top) * mw + x1 + left) * nm;
+      const float* p10 = proto + (static_cast<long long>(y1 + top) * mw + x0 + left) * nm;
+      const float* p11 = proto + (static_cast<long long>(y1 + top) * mw + x1 + left) * nm;
+      float m00 = 0.f, m01 = 0.f, m10 = 0.f, m11 = 0.f;
+      for (int q = 0; q < nm; ++q) {
+        const float cq = c[q];
+        m00 += cq * p00[q];
+        m01 += cq * p01[q];
+        m10 += cq * p10[q];
+        m11 += cq * p11[q];
+      }
+      const float v = (1.f - ly) * ((1.f - lx) * m00 + lx * m01) + ly * ((1.f - lx) * m10 + lx * m11);
+      o = v > 0.0f ? 1 : 0;
+    }
+    out[i] = o;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -441,6 +492,28 @@ int mtb_nms(const mtb_nms_params* p, const float* cand, const int* cand_anchor, 
   P.apply_dedup = p->apply_dedup;
   nms_kernel<<<P.N, 256, 0, static_cast<cudaStream_t>(stream)>>>(P, cand, cand_anchor, count, order_ws, dead_ws, out_det,
                                                                 out_count, final_idx);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+
+int mtb_yolo_masks(const float* proto, int mh, int mw, int nm, const float* const* mc_levels, const int* level_hw /* 3x2 */,
+                   const float* det, const int* rows, int n, int top, int left, int ch, int cw, int H, int W, uint8_t* out,
+                   void* stream) {
+  MTB_REQUIRE(proto && mc_levels && level_hw && det && out, "mtb_yolo_masks: null argument");
+  if (n <= 0) return 0;
+  MaskLevel L[3];
+  int a0 = 0;
+  for (int i = 0; i < 3; ++i) {
+    L[i].mc = mc_levels[i];
+    L[i].H = level_hw[2 * i];
+    L[i].W = level_hw[2 * i + 1];
+    L[i].anchor0 = a0;
+    a0 += L[i].H * L[i].W;
+  }
+  yolo_masks_kernel<<<grid_for2(static_cast<long long>(n) * H * W, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      proto, mh, mw, nm, L[0], L[1], L[2], det, rows, n, top, left, ch, cw, H, W, out);
   MTB_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -9,6 +9,7 @@ from typing import Callable
 import torch
 
 ENABLED = os.environ.get("MTB200_CUDA_GRAPHS", "1") != "0"
+replayed_launches = 0     # kernels of this library launched through graph replays (bench.py's gpu_launches)
 
 
 class CapturedGraph:
@@ -21,9 +22,14 @@ class CapturedGraph:
                 fn()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        from ._lib import launch_count
         self.graph = torch.cuda.CUDAGraph()
+        n0 = launch_count()
         with torch.cuda.graph(self.graph):
             fn()
+        self.n_kernels = launch_count() - n0          # C-ABI launches recorded into the graph
 
     def replay(self) -> None:
+        global replayed_launches
         self.graph.replay()
+        replayed_launches += self.n_kernels

@@ -44,6 +44,8 @@ def _declare(l) -> None:
     l.mtb_yolo_decode.argtypes = [C.POINTER(YoloLevel), i32, i32, i32, i32, f32, i32, vp, vp, vp, vp]
     l.mtb_nms.argtypes = [C.POINTER(NmsParams), vp, vp, vp, vp, vp, vp, vp, vp, vp]
     l.mtb_image_to_planes.argtypes = [vp, i32, i32, i32, i32, f32, C.POINTER(f32), vp, i32, i32, vp]
+    l.mtb_yolo_masks.argtypes = [vp, i32, i32, i32, C.POINTER(vp), C.POINTER(i32), vp, vp] + [i32] * 7 + [vp, vp]
+    l.mtb_yolo_masks.restype = i32
     for n in ("mtb_maxpool", "mtb_upsample2x", "mtb_yolo_decode", "mtb_nms", "mtb_image_to_planes"):
         getattr(l, n).restype = i32
     l._det_declared = True
@@ -73,6 +75,16 @@ class Boxes:
 
     def __len__(self):
         return int(self.xyxy.shape[0])
+
+
+class Masks:
+    """`Results.masks` as far as the reference touches it: `.data` (n,H,W float {0,1}) and `len()`."""
+
+    def __init__(self, data):
+        self.data = data
+
+    def __len__(self):
+        return int(self.data.shape[0])
 
 
 class Results:
@@ -310,4 +322,23 @@ class YoloB200:
         n = int(cnt[0].item())
         d = det[:n]
         boxes = Boxes(d[:, :4].contiguous(), d[:, 4].contiguous(), d[:, 5].contiguous()) if n else None
-        return [Results(boxes, None, (h0, w0), self.names)]
+        masks = None
+        if n and retina_masks:
+            masks = Masks(self.retina_masks(g, det, None, n, (h0, w0), tuple(lb.shape[:2])).float())
+        return [Results(boxes, masks, (h0, w0), self.names)]
+
+    def retina_masks(self, g: dict, det: torch.Tensor, rows: Optional[torch.Tensor], n: int, orig_hw, lb_hw) -> torch.Tensor:
+        """uint8 {0,1} masks [n][H][W] for rows of the detection table (process_mask_native)."""
+        h0, w0 = orig_hw
+        proto = g["proto"]
+        mh, mw, nm = int(proto.shape[1]), int(proto.shape[2]), int(proto.shape[3])
+        gain = min(mh / h0, mw / w0)
+        pad_w, pad_h = (mw - w0 * gain) / 2, (mh - h0 * gain) / 2
+        top, left = int(round(pad_h - 0.1)), int(round(pad_w - 0.1))
+        bottom, right = mh - int(round(pad_h + 0.1)), mw - int(round(pad_w + 0.1))
+        out = torch.empty((n, h0, w0), dtype=torch.uint8, device=self.device)
+        mcs = (C.c_void_p * 3)(*[lv[2].data_ptr() for lv in g["levels"]])
+        hw = (C.c_int * 6)(*[v for lv in g["levels"] for v in (lv[3], lv[4])])
+        check(self.l.mtb_yolo_masks(ptr(proto), mh, mw, nm, mcs, hw, ptr(det), ptr(rows), n, top, left, bottom - top,
+                                    right - left, h0, w0, ptr(out), stream_ptr()), "mtb_yolo_masks")
+        return out

@@ -163,3 +163,26 @@ def test_post_nms_logic_matches_live_reference():
         assert keep == _ref_dedup(tb.tolist(), tc.tolist(), 0.7)
         kb2, idx = ref._remove_contained_boxes(kb, [("primary", i) for i in keep], 0.9)
         assert [i for (_, i) in idx] == [keep[i] for i in _ref_remove_contained(kb.tolist(), 0.9)]
+
+
+def test_call_shape_and_retina_masks_match_oracle():
+    """`model(image_bgr, conf=..., imgsz=..., retina_masks=True)[0]` like the reference calls it (detection.py:1338-1345):
+    boxes, scores and the native-resolution masks (process_mask_native) against the oracle."""
+    from mangatranslator_b200.yolo import YoloB200
+    cfg, hw, imgsz = NANO, (333, 250), 320
+    for seed in range(5, 40):
+        mm = Y.make_model(seed, bias_objects=-7.0, **cfg)
+        img = _image(seed, hw[0], hw[1])
+        conf, cut_gap, min_gap, iou_margin = _well_posed_conf(mm, Y.preprocess(img, imgsz))
+        if cut_gap > 1e-4 and min_gap > 5e-5 and iou_margin > 1e-3:
+            break
+    ref = Y.predict(mm, img, conf, imgsz)
+    net = YoloB200(mm.state_dict(), mm.cfg, torch.device("cuda:0"))
+    res = net(np.ascontiguousarray(img), conf=conf, device=None, verbose=False, imgsz=imgsz, retina_masks=True)[0]
+    assert res.orig_shape == hw and len(res.boxes) == ref["xyxy"].shape[0] == len(res.masks)
+    assert (res.boxes.xyxy.cpu() - ref["xyxy"]).abs().max().item() < 1e-2
+    got = res.masks.data.cpu().numpy() > 0.5
+    exp = ref["masks"].numpy()
+    assert got.shape == exp.shape
+    assert (got != exp).mean() < 1e-3          # knife-edge pixels of the `> 0` decision only
+    assert exp.any()
