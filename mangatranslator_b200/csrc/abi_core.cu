@@ -209,7 +209,7 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
     const uint64_t strides[3] = {xc * 2, static_cast<uint64_t>(d->W) * xc * 2, static_cast<uint64_t>(d->H) * d->W * xc * 2};
     uint32_t box[4] = {64, static_cast<uint32_t>(p.TW * d->stride), static_cast<uint32_t>(p.TH * d->stride), 1};
     if (pl->halo) {
-      box[1] = static_cast<uint32_t>(p.TW + 2);
+      box[1] = static_cast<uint32_t>(p.TW);       // kx-preshifted 18 x 8 pixel columns (conv_halo.cu)
       box[2] = static_cast<uint32_t>(p.TH + 2);
     }
     const uint32_t es[4] = {1, static_cast<uint32_t>(d->stride), static_cast<uint32_t>(d->stride), 1};

@@ -218,6 +218,35 @@ __device__ double box_area_d(const double* a) {
   return __dmul_rn(w > 0.0 ? w : 0.0, h > 0.0 ? h : 0.0);
 }
 
+
+// rank of every candidate in (score desc, anchor asc) order: order[n][rank] = candidate slot.  Grid = (chunks, N).
+__global__ void rank_kernel(const float* __restrict__ cand, const int* __restrict__ cand_anchor,
+                            const int* __restrict__ count, int max_cand, int* __restrict__ order_ws) {
+  const int n = blockIdx.y;
+  const int m = count[n] < max_cand ? count[n] : max_cand;
+  const float* c = cand + static_cast<long long>(n) * max_cand * 6;
+  const int* ca = cand_anchor + static_cast<long long>(n) * max_cand;
+  int* order = order_ws + static_cast<long long>(n) * max_cand;
+  __shared__ float s_sc[256];
+  __shared__ int s_an[256];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float si = i < m ? c[i * 6 + 4] : 0.f;
+  const int ai = i < m ? ca[i] : 0;
+  int r = 0;
+  for (int j0 = 0; j0 < m; j0 += 256) {
+    const int j = j0 + threadIdx.x;
+    __syncthreads();
+    s_sc[threadIdx.x] = j < m ? c[j * 6 + 4] : -1.f;
+    s_an[threadIdx.x] = j < m ? ca[j] : 0x7fffffff;
+    __syncthreads();
+    const int lim = min(256, m - j0);
+    if (i < m)
+      for (int t = 0; t < lim; ++t)
+        if (cand_before(s_sc[t], s_an[t], si, ai)) ++r;
+  }
+  if (i < m) order[r] = i;
+}
+
 // out_det: [N][max_det][8] = x1,y1,x2,y2 (original px), score, cls, anchor, kept_by_reference_logic(0/1)
 // out_count: [N][2] = (n after NMS, n after dedup+containment)
 __global__ void nms_kernel(NmsParams P, const float* __restrict__ cand, const int* __restrict__ cand_anchor,
@@ -231,16 +260,8 @@ __global__ void nms_kernel(NmsParams P, const float* __restrict__ cand, const in
   unsigned char* dead = dead_ws + static_cast<long long>(n) * P.max_cand;
   __shared__ int s_keep[512];
   __shared__ int s_nkeep;
-  // rank sort (m is small: anchors above the confidence threshold); O(m^2 / threads)
-  for (int i = threadIdx.x; i < m; i += blockDim.x) {
-    int r = 0;
-    const float si = c[i * 6 + 4];
-    const int ai = ca[i];
-    for (int j = 0; j < m; ++j)
-      if (j != i && cand_before(c[j * 6 + 4], ca[j], si, ai)) ++r;
-    order[r] = i;
-    dead[i] = 0;
-  }
+  // `order` was filled by rank_kernel (one thread per candidate, many blocks)
+  for (int i = threadIdx.x; i < m; i += blockDim.x) dead[i] = 0;
   if (threadIdx.x == 0) s_nkeep = 0;
   __syncthreads();
   // greedy NMS in sorted order, class offset trick (boxes + cls * max_wh), fp32 like torchvision
@@ -490,6 +511,12 @@ int mtb_nms(const mtb_nms_params* p, const float* cand, const int* cand_anchor, 
   P.dedup_iou = p->dedup_iou;
   P.contain_ioa = p->contain_ioa;
   P.apply_dedup = p->apply_dedup;
+  {
+    dim3 rgrid(static_cast<unsigned>((P.max_cand + 255) / 256), static_cast<unsigned>(P.N));
+    rank_kernel<<<rgrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(cand, cand_anchor, count, P.max_cand, order_ws);
+    MTB_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+  }
   nms_kernel<<<P.N, 256, 0, static_cast<cudaStream_t>(stream)>>>(P, cand, cand_anchor, count, order_ws, dead_ws, out_det,
                                                                 out_count, final_idx);
   MTB_CUDA_OK(cudaGetLastError());

@@ -140,17 +140,40 @@ __device__ __forceinline__ long long tok_row(const AttnParams& P, int b, int t, 
   return static_cast<long long>(y) * P.grid_w + x;
 }
 
-__device__ __forceinline__ float load_tok(const AttnParams& P, const uint16_t* base, int ct, int off, long long ps,
-                                          const float* pad, long long row, int ch) {
-  if (row < 0) return pad ? pad[ch] : 0.f;
-  return ld_planes(base, row * ct + off + ch, ps, P.planes);
-}
-
 constexpr int kAttnThreads = 256;
 constexpr int kQT = 64;   // queries per block (8 per warp)
 constexpr int kKT = 64;   // keys per shared-memory tile
 constexpr int kMaxHD = 128;
 
+// 8 consecutive channels of one token as fp32 (16-byte loads of the hi and lo planes); padded tokens read `pad`
+__device__ __forceinline__ void load_tok8(const AttnParams& P, const uint16_t* base, int ct, int off, long long ps,
+                                          const float* pad, long long row, int ch, float (&v)[8]) {
+  if (row < 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = pad ? pad[ch + j] : 0.f;
+    return;
+  }
+  const long long idx = row * ct + off + ch;
+  const uint4 h = *reinterpret_cast<const uint4*>(base + idx);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = __uint_as_float(hw[j] << 16);
+    v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u);
+  }
+  if (P.planes == 2) {
+    const uint4 l = *reinterpret_cast<const uint4*>(base + ps + idx);
+    const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] += __uint_as_float(lw[j] << 16);
+      v[2 * j + 1] += __uint_as_float(lw[j] & 0xFFFF0000u);
+    }
+  }
+}
+
+// Flash-style attention on CUDA cores in fp32 (exact softmax, online rescaling).  Block = 64 queries x one (batch, head);
+// each warp owns 8 queries processed as two register-blocked groups of 4 so every K/V shared-memory read feeds 4 FMAs.
 __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnParams P) {
   extern __shared__ float sm[];
   const int hd = P.hd, hdp = hd + 1;
@@ -163,26 +186,36 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq_tile = min(kQT, P.nq - q0);
   const int wso = P.pool ? P.ws / 2 : P.ws;
+  const int hv = hd >> 3;             // 8-channel vectors per token
 
-  // stage the block's queries (scaled), applying the 2x2 max-pool inside the window when requested
-  for (int i = threadIdx.x; i < nq_tile * hd; i += kAttnThreads) {
-    const int qi = i / hd, d = i - qi * hd;
-    const int t = q0 + qi;
-    float v;
-    if (P.mode == 1 && P.pool) {
-      const int qy = t / wso, qx = t - qy * wso;
-      v = -INFINITY;
-      for (int a = 0; a < 2; ++a)
-        for (int c = 0; c < 2; ++c) {
-          const int tt = (2 * qy + a) * P.ws + 2 * qx + c;
-          v = fmaxf(v, load_tok(P, P.q, P.q_ct, P.q_off, P.q_ps, P.pad_q, tok_row(P, b, tt, P.nk), h * hd + d));
-        }
+  // stage the block's queries, applying the 2x2 max-pool inside the window when requested
+  for (int i = threadIdx.x; i < kQT * hv; i += kAttnThreads) {
+    const int qi = i / hv, dv = i - qi * hv;
+    float v[8];
+    if (qi >= nq_tile) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
     } else {
-      v = load_tok(P, P.q, P.q_ct, P.q_off, P.q_ps, P.pad_q, tok_row(P, b, t, P.nq), h * hd + d);
+      const int t = q0 + qi;
+      if (P.mode == 1 && P.pool) {
+        const int qy = t / wso, qx = t - qy * wso;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = -INFINITY;
+        for (int a = 0; a < 2; ++a)
+          for (int c = 0; c < 2; ++c) {
+            float u[8];
+            const int tt = (2 * qy + a) * P.ws + 2 * qx + c;
+            load_tok8(P, P.q, P.q_ct, P.q_off, P.q_ps, P.pad_q, tok_row(P, b, tt, P.nk), h * hd + dv * 8, u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], u[j]);
+          }
+      } else {
+        load_tok8(P, P.q, P.q_ct, P.q_off, P.q_ps, P.pad_q, tok_row(P, b, t, P.nq), h * hd + dv * 8, v);
+      }
     }
-    sQ[qi * hd + d] = v;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sQ[qi * hd + dv * 8 + j] = v[j] * P.scale;
   }
-  // per-warp state for its 8 queries
   float m[8], l[8], acc[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -194,52 +227,71 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnParams P) {
   for (int k0 = 0; k0 < P.nk; k0 += kKT) {
     const int nk_tile = min(kKT, P.nk - k0);
     __syncthreads();
-    for (int i = threadIdx.x; i < nk_tile * hd; i += kAttnThreads) {
-      const int ki = i / hd, d = i - ki * hd;
-      const long long row = tok_row(P, b, k0 + ki, P.nk);
-      sK[ki * hdp + d] = load_tok(P, P.k, P.k_ct, P.k_off, P.k_ps, P.pad_k, row, h * hd + d);
-      sV[ki * hd + d] = load_tok(P, P.v, P.v_ct, P.v_off, P.v_ps, P.pad_v, row, h * hd + d);
+    for (int i = threadIdx.x; i < kKT * hv; i += kAttnThreads) {
+      const int ki = i / hv, dv = i - ki * hv;
+      float kv[8], vv[8];
+      if (ki < nk_tile) {
+        const long long row = tok_row(P, b, k0 + ki, P.nk);
+        load_tok8(P, P.k, P.k_ct, P.k_off, P.k_ps, P.pad_k, row, h * hd + dv * 8, kv);
+        load_tok8(P, P.v, P.v_ct, P.v_off, P.v_ps, P.pad_v, row, h * hd + dv * 8, vv);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) kv[j] = vv[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sK[ki * hdp + dv * 8 + j] = kv[j];
+        sV[ki * hd + dv * 8 + j] = vv[j];
+      }
     }
     __syncthreads();
+    const float* k0r = sK + lane * hdp;
+    const float* k1r = sK + (lane + 32) * hdp;
+    const bool v0 = lane < nk_tile, v1 = lane + 32 < nk_tile;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int qi = warp * 8 + j;
-      if (qi >= nq_tile) break;
-      const float* qv = sQ + qi * hd;
-      float s0 = -INFINITY, s1 = -INFINITY;
-      if (lane < nk_tile) {
-        float a = 0.f;
-        const float* kr = sK + lane * hdp;
-        for (int d = 0; d < hd; ++d) a += qv[d] * kr[d];
-        s0 = a * P.scale;
+    for (int g = 0; g < 2; ++g) {
+      if (warp * 8 + g * 4 >= nq_tile) break;
+      const float* q0p = sQ + (warp * 8 + g * 4) * hd;
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int d = 0; d < hd; ++d) {
+        const float ka = k0r[d], kb = k1r[d];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float qv = q0p[j * hd + d];
+          s0[j] += qv * ka;
+          s1[j] += qv * kb;
+        }
       }
-      if (lane + 32 < nk_tile) {
-        float a = 0.f;
-        const float* kr = sK + (lane + 32) * hdp;
-        for (int d = 0; d < hd; ++d) a += qv[d] * kr[d];
-        s1 = a * P.scale;
+      float p0[4], p1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int jj = g * 4 + j;
+        const float a0 = v0 ? s0[j] : -INFINITY, a1 = v1 ? s1[j] : -INFINITY;
+        float tm = fmaxf(a0, a1);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
+        const float nm = fmaxf(m[jj], tm);
+        const float corr = expf(m[jj] - nm);
+        p0[j] = v0 ? expf(a0 - nm) : 0.f;
+        p1[j] = v1 ? expf(a1 - nm) : 0.f;
+        float ps = p0[j] + p1[j];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+        l[jj] = l[jj] * corr + ps;
+        m[jj] = nm;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[jj][e] *= corr;
       }
-      float tm = fmaxf(s0, s1);
-#pragma unroll
-      for (int o = 16; o; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
-      const float nm = fmaxf(m[j], tm);
-      const float corr = expf(m[j] - nm);
-      const float p0 = (lane < nk_tile) ? expf(s0 - nm) : 0.f;
-      const float p1 = (lane + 32 < nk_tile) ? expf(s1 - nm) : 0.f;
-      float ps = p0 + p1;
-#pragma unroll
-      for (int o = 16; o; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
-      l[j] = l[j] * corr + ps;
-      m[j] = nm;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[j][e] *= corr;
       for (int kk = 0; kk < nk_tile; ++kk) {
-        const float p = __shfl_sync(0xffffffffu, kk < 32 ? p0 : p1, kk & 31);
         const float* vr = sV + kk * hd;
+        float ve[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int d = lane + 32 * e;
-          if (d < hd) acc[j][e] += p * vr[d];
+        for (int e = 0; e < 4; ++e) ve[e] = (lane + 32 * e < hd) ? vr[lane + 32 * e] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float p = __shfl_sync(0xffffffffu, kk < 32 ? p0[j] : p1[j], kk & 31);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[g * 4 + j][e] += p * ve[e];
         }
       }
     }
@@ -269,7 +321,6 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnParams P) {
     }
   }
 }
-
 
 // ---- patch embedding: (u8 - mean')/std' -> conv k x k / stride / pad (3 -> C) + bias + positional embedding -------
 // one thread per (output pixel, 8 output channels); weights in shared memory

@@ -112,6 +112,10 @@ def yolo_state_dict(seed: int = 0, cfg: Optional[dict] = None) -> Dict[str, torc
             conv(f"head.{br}.{i}.0.conv", x, hcx, 3)
             conv(f"head.{br}.{i}.1.conv", hcx, hcx, 3)
             conv(f"head.{br}.{i}.2", hcx, oc, 1, gain=0.05)
+        # class head: tiny gain and a negative bias so that (like a trained detector on a clean page) only a handful of
+        # anchors, not thousands, clear conf=0.6; stage-level runs inject the page's ground-truth boxes anyway
+        sd[f"head.cv3.{i}.2.weight"] *= 0.02
+        sd[f"head.cv3.{i}.2.bias"] = torch.full((nc,), -4.0)
     npr = c(cfg["npr"])
     conv("head.proto.cv1.conv", c256, npr, 3)
     w = torch.randn((npr, npr, 2, 2), generator=g) * (1.6 / math.sqrt(npr))
