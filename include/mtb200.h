@@ -62,6 +62,9 @@ typedef struct mtb_conv_plan mtb_conv_plan;
 int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, const float* bias, void* out,
                          const void* residual, float* tile_sums, mtb_conv_plan** plan);
 int mtb_conv_plan_run(mtb_conv_plan* plan, void* stream);
+/* optional per-output-channel factor applied to (acc + bias) before activation / residual: out = act((acc+b)*s) + res.
+ * `scale` ([Cout] floats, device) is read at run time, so a kernel earlier in the stream may produce it. */
+int mtb_conv_plan_set_channel_scale(mtb_conv_plan* plan, const float* scale);
 int mtb_conv_plan_num_mtiles(const mtb_conv_plan* plan);
 /* rows of the tile_sums buffer this plan writes ([rows][Cout] fp32): per (CTA, lane quarter) when the launch covers a
  * single image, else per (pixel tile, lane quarter) */
@@ -151,6 +154,14 @@ int mtb_ca_scale(const float* sums, int n_images, int parts_per_image, int C, fl
                  const float* b1, const float* w2, const float* b2, int R, float* scale_out, void* stream);
 int mtb_scale_residual(const void* t, const void* x, const float* scale, void* y, long long pix_per_image, int N, int C,
                        int planes, void* stream);
+/* rcan_gate: the CALayer gate of an RCAB computed from the INPUT of the block's second 3x3 conv (64 channels, one
+ * image): sums = per-channel partial sums of u (conv1's tile_sums rows), u = conv1's output planes; conv_w/conv_b =
+ * the second conv's fp32 weights [64][64][3][3] / bias; w1,b1,w2,b2 = conv_du.  By linearity of the zero-padded conv
+ * mean(conv2(u)) follows from the total and the four border lines of u, so conv2 can apply the gate in its own
+ * epilogue (mtb_conv_plan_set_channel_scale) and RCAB's `x + gate * t` needs no pass of its own. */
+int mtb_rcan_gate(const float* sums, int parts, const void* u, int planes, int H, int W, const float* conv_w,
+                  const float* conv_b, const float* w1, const float* b1, const float* w2, const float* b2, int R,
+                  float* scale_out, void* stream);
 int mtb_f32_to_u8(const float* in, long long npix, int cpad, const float* add3 /* host */, float mul, uint8_t* out,
                   float* out_f /* optional float copy [npix][3] */, void* stream);
 

@@ -69,6 +69,9 @@ using namespace mtb;
 
 namespace mtb {
 bool conv_halo_eligible(const ConvParams& p, int cin);
+void conv_halo_cm_tile(int* tw, int* th);
+bool conv_halo_cm_eligible(const ConvParams& p);
+int launch_conv_halo_cm(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvParams& p, cudaStream_t stream);
 int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int nsplit,
                      cudaStream_t stream);
 }  // namespace mtb
@@ -183,6 +186,11 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
   if (pl->halo) {
     p.TW = 8;
     p.TH = 16;
+    // bf16x3 layers take the channel-major kernel (conv_halo_cm.cu) unless mode 3 pins the pixel-major one
+    if (d->planes_in == 2 && d->mode != 3 && conv_halo_cm_eligible(p)) {
+      pl->halo = 2;
+      conv_halo_cm_tile(&p.TW, &p.TH);
+    }
   }
   p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
   p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
@@ -209,7 +217,7 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
     const uint64_t strides[3] = {xc * 2, static_cast<uint64_t>(d->W) * xc * 2, static_cast<uint64_t>(d->H) * d->W * xc * 2};
     uint32_t box[4] = {64, static_cast<uint32_t>(p.TW * d->stride), static_cast<uint32_t>(p.TH * d->stride), 1};
     if (pl->halo) {
-      box[1] = static_cast<uint32_t>(p.TW);       // kx-preshifted 18 x 8 pixel columns (conv_halo.cu)
+      box[1] = static_cast<uint32_t>(p.TW + 2);
       box[2] = static_cast<uint32_t>(p.TH + 2);
     }
     const uint32_t es[4] = {1, static_cast<uint32_t>(d->stride), static_cast<uint32_t>(d->stride), 1};
@@ -224,7 +232,7 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
     const uint64_t rows = static_cast<uint64_t>(d->planes_in) * d->KH * d->KW * d->Cout;
     const uint64_t dims[2] = {static_cast<uint64_t>(d->Cin), rows};
     const uint64_t strides[1] = {static_cast<uint64_t>(d->Cin) * 2};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(p.BN)};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(pl->halo == 2 ? 16 : p.BN)};
     if (encode_tmap(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, strides, box, nullptr,
                     CU_TENSOR_MAP_SWIZZLE_128B) != 0) {
       delete pl;
@@ -237,11 +245,19 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
 
 int mtb_conv_plan_run(mtb_conv_plan* plan, void* stream) {
   MTB_REQUIRE(plan != nullptr, "mtb_conv_plan_run: null plan");
-  int rc = plan->halo
-               ? launch_conv_halo(plan->tmA, plan->tmB, plan->p, plan->nsplit, static_cast<cudaStream_t>(stream))
-               : launch_conv_gemm(plan->tmA, plan->tmB, plan->p, plan->nsplit, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = plan->halo == 2   ? launch_conv_halo_cm(plan->tmA, plan->tmB, plan->p, st)
+           : plan->halo == 1 ? launch_conv_halo(plan->tmA, plan->tmB, plan->p, plan->nsplit, st)
+                             : launch_conv_gemm(plan->tmA, plan->tmB, plan->p, plan->nsplit, st);
   if (rc == 0) mtb::g_launches.fetch_add(1);
   return rc;
+}
+
+int mtb_conv_plan_set_channel_scale(mtb_conv_plan* plan, const float* scale) {
+  MTB_REQUIRE(plan != nullptr, "mtb_conv_plan_set_channel_scale: null plan");
+  MTB_REQUIRE(!plan->p.pixel_shuffle, "conv: channel scale with pixel_shuffle is not supported");
+  plan->p.chan_scale = scale;
+  return 0;
 }
 
 int mtb_conv_plan_num_mtiles(const mtb_conv_plan* plan) {

@@ -48,6 +48,9 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// one lane of the (converged) warp.  Branching on this instead of `lane == 0` lets the compiler issue uniform-datapath
+// instructions (UTCHMMA, UTMALDG, ...) back to back; under `lane == 0` each one is wrapped in an ELECT / R2UR /
+// BRA.U.ANY loop (~100 clk per MMA), which made the issuing thread the bottleneck of the conv kernels.
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -79,18 +79,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(tile, p);
-        const int n0 = t.nt * p.BN;
-        for (int ks = 0; ks < KS; ++ks) {
-          const int tap = ks / p.cin_chunks;
-          const int cc = ks - tap * p.cin_chunks;
-          const int ky = tap / p.KW;
-          const int kx = tap - ky * p.KW;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // the whole warp walks the loop; one elected lane issues (see elect_one() in common.cuh)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(tile, p);
+      const int n0 = t.nt * p.BN;
+      for (int ks = 0; ks < KS; ++ks) {
+        const int tap = ks / p.cin_chunks;
+        const int cc = ks - tap * p.cin_chunks;
+        const int ky = tap / p.KW;
+        const int kx = tap - ky * p.KW;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
           uint8_t* sb = sa + PLANES * kATileBytes;
@@ -104,10 +105,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int pl = 0; pl < PLANES; ++pl) {
             tma_load_2d(sb + pl * b_tile_bytes, &tmB, &full_bar[stage], cc * 64, (pl * taps + tap) * p.Cout + n0);
           }
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -125,7 +127,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int ks = 0; ks < KS; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
           const uint32_t sb = sa + PLANES * kATileBytes;
 #pragma unroll
@@ -148,7 +150,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           phase ^= 1;
         }
       }
-      if (lane == 0) umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+      if (elect_one()) umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
       __syncwarp();
       if (++as == 2) {
         as = 0;

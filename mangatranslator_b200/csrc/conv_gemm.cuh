@@ -39,6 +39,7 @@ struct ConvParams {
   long long res_plane_stride;  // elements between the hi and lo planes of `residual`
   int res_planes;              // 0, 1 or 2
   const float* bias;           // [Cout] or nullptr
+  const float* chan_scale;     // [Cout] or nullptr: out = act((acc + bias) * chan_scale) (+ residual)
   uint16_t* out;               // bf16 planes [planes_out][N][Ho][Wo][Cout]
   float* out_f32;              // optional fp32 output [N][Ho][Wo][Cout]
   const uint16_t* residual;    // optional, same geometry as out, added after the activation
@@ -52,6 +53,7 @@ struct ConvParams {
   int res_bcast;               // 1: the residual has batch 1 and is shared by all N images
   int act_after_res;           // 1: activation is applied after the residual add
   int debug;                   // perf experiments only (halo kernel): 1 skip stores, 2 skip MMA issue, 4 skip TMA loads
+  long long* dbg_out;          // perf experiments only: per-CTA counters (halo kernels, debug bit 16)
   int pixel_shuffle;           // 1: Cout = 4 blocks of Cout/4 channels, block (dy*2+dx) is stored at pixel (2y+dy, 2x+dx)
 };
 

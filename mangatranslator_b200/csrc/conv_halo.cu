@@ -2,15 +2,12 @@
 // layer that runs ~400 times per page (reference: spandrel RCAN behind core/image/image_utils.py:369-374) — as a
 // HALO-TILE implicit GEMM on tcgen05:
 //
-//   * the three vertical taps (ky) of one filter column are three SHIFTED VIEWS of one shared-memory tile: for each kx
-//     TMA loads the 18-row x 8-pixel column-shifted halo of a 16x8 output tile (128B-swizzled, one 128-byte row per
-//     pixel) and the UMMA shared-memory descriptor of tap (ky,kx) starts ky*1024 B later.  (mtb_exp_shifted_desc showed
-//     the 128B swizzle is a function of absolute smem address bits, so row-shifted descriptors with base_offset = 0
-//     read what TMA wrote.)  An earlier version loaded ONE 18x10 halo and shifted by (ky*10+kx) rows; its ablation
-//     (profiles/r01_halo_ablation.json) showed the MMAs themselves running 1.7x slower than the shared-memory-operand
-//     model: operand atoms that are not 1024-byte aligned cost ~2.3x the A-operand reads.  With kx-preshifted tiles
-//     every tap's A operand is a dense, 1024B-aligned canonical tile (SBO = 1024) at 3x(18/16) instead of 9x the
-//     L2->SM traffic of per-tap loads.
+//   * the 9 filter taps are 9 SHIFTED VIEWS of one shared-memory tile: TMA loads the (16+2) x (8+2) pixel halo of a
+//     16x8 output tile once (128B-swizzled, one 128-byte row per pixel) and the UMMA shared-memory descriptor of tap
+//     (ky,kx) just starts (ky*10+kx) rows later with a 10-row stride between 8-pixel groups (SBO = 1280 B).
+//     (Verified on B200 by mtb_exp_shifted_desc: the 128B swizzle is a function of absolute smem address bits, so
+//     row-shifted descriptors with base_offset = 0 read the rows TMA wrote.)  L2->SM traffic per tile drops from
+//     9 x 32 KB (one TMA box per tap) to 46 KB.
 //   * all weights (9 taps x [hi|lo] x 64x64 bf16 = 144 KB) are loaded once per persistent CTA and stay resident.
 //   * bf16x3 with ONE N=128 MMA per (tap, k16): A_hi x [W_hi ; W_lo] -> columns 0..63 = Ahi*Whi, 64..127 = Ahi*Wlo,
 //     then A_lo x W_hi accumulates into columns 0..63; the epilogue adds the two halves.  Shared-memory operand
@@ -28,10 +25,10 @@ namespace {
 
 constexpr int kThreads = kConvThreads;
 constexpr int kTW = 8, kTH = 16;                    // output tile (pixels)
-constexpr int kHH = kTH + 2;                        // halo rows
-constexpr int kItemBytes = kTW * kHH * 128;         // 18432: one kx-shifted 18x8 pixel column of one plane
-constexpr int kSlotBytes = kItemBytes;              // multiple of 1024
-constexpr int kSlots = 4;
+constexpr int kHW = kTW + 2, kHH = kTH + 2;         // halo tile
+constexpr int kHaloBytes = kHW * kHH * 128;         // 23040
+constexpr int kSlotBytes = 23552;                   // 1024-aligned slot
+constexpr int kSlots = 3;
 constexpr int kTapBytes = 128 * 128;                // [W_hi(64 rows) ; W_lo(64 rows)] x 128 B
 constexpr int kWBytes = 9 * kTapBytes;              // 147456
 
@@ -96,32 +93,29 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int n = tile / tiles_per_img;
         const int rem = tile - n * tiles_per_img;
         const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
-        // pull the tile three iterations ahead into L2 while this one streams into shared memory
+        // pull the halos of the tile three iterations ahead into L2 while this one streams into shared memory: the
+        // 3-slot ring only hides ~1.5 tiles of latency, so the eventual TMA load should be an L2 hit
         {
           const int pt = tile + 3 * gridDim.x;
           if (pt < total_tiles) {
             const int pn = pt / tiles_per_img;
             const int prem = pt - pn * tiles_per_img;
             const int pty = prem / p.tiles_x, ptx = prem - pty * p.tiles_x;
-            for (int pl = 0; pl < PLANES; ++pl) {
+            for (int pl = 0; pl < PLANES; ++pl)
               tma_prefetch_l2_4d(&tmA, 0, ptx * kTW - 1, pty * kTH - 1, pl * p.N + pn);
-              tma_prefetch_l2_4d(&tmA, 0, ptx * kTW + 1, pty * kTH - 1, pl * p.N + pn);
-            }
           }
         }
         for (int pl = 0; pl < PLANES; ++pl) {
-          for (int kx = 0; kx < 3; ++kx) {
-            mbar_wait(&empty_bar[slot], phase ^ 1);
-            if (p.debug & 4) {
-              mbar_arrive(&full_bar[slot]);
-            } else {
-              mbar_expect_tx(&full_bar[slot], kItemBytes);
-              tma_load_4d(sA + slot * kSlotBytes, &tmA, &full_bar[slot], 0, txi * kTW + kx - 1, tyi * kTH - 1, pl * p.N + n);
-            }
-            if (++slot == kSlots) {
-              slot = 0;
-              phase ^= 1;
-            }
+          mbar_wait(&empty_bar[slot], phase ^ 1);
+          if (p.debug & 4) {
+            mbar_arrive(&full_bar[slot]);
+          } else {
+            mbar_expect_tx(&full_bar[slot], kHaloBytes);
+            tma_load_4d(sA + slot * kSlotBytes, &tmA, &full_bar[slot], 0, txi * kTW - 1, tyi * kTH - 1, pl * p.N + n);
+          }
+          if (++slot == kSlots) {
+            slot = 0;
+            phase ^= 1;
           }
         }
       }
@@ -136,44 +130,58 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
+    long long dbg_wfull = 0, dbg_wtempty = 0, dbg_tiles = 0;
+    const long long dbg_t0 = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const long long ta = (p.debug & 32) ? clock64() : 0;
       mbar_wait(&tempty_bar[as], aphase ^ 1);
+      if (p.debug & 32) {
+        dbg_wtempty += clock64() - ta;
+        ++dbg_tiles;
+      }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * ACC_COLS);
       for (int pl = 0; pl < PLANES; ++pl) {
-        for (int kx = 0; kx < 3; ++kx) {
-          mbar_wait(&full_bar[slot], phase);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(sA + slot * kSlotBytes);
+        const long long tf = (p.debug & 32) ? clock64() : 0;
+        mbar_wait(&full_bar[slot], phase);
+        if (p.debug & 32) dbg_wfull += clock64() - tf;
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(sA + slot * kSlotBytes);
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              if ((p.debug & 2) && (ky | kx)) continue;
-              const uint32_t a0 = sa + ky * (kTW * 128);          // 1024-byte aligned row shift
-              const uint32_t b0 = sw + (ky * 3 + kx) * kTapBytes;
+          for (int tap = 0; tap < 9; ++tap) {
+            if ((p.debug & 2) && tap > 0) continue;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const uint32_t a0 = sa + (ky * kHW + kx) * 128;
+            const uint32_t b0 = sw + tap * kTapBytes;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t da = make_sdesc_sw128(a0 + k * 32, 1024, 0);
-                const uint64_t db = make_sdesc_sw128(b0 + k * 32, 1024, 0);
-                if (pl == 0) umma_bf16(d_tmem, da, db, idesc_wide, (kx > 0 || ky > 0 || k > 0) ? 1u : 0u);
-                else umma_bf16(d_tmem, da, db, idesc_64, 1u);
-              }
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = make_sdesc_sw128(a0 + k * 32, kHW * 128, 0);
+              const uint64_t db = make_sdesc_sw128(b0 + k * 32, 1024, 0);
+              if (pl == 0) umma_bf16(d_tmem, da, db, idesc_wide, (tap > 0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, da, db, idesc_64, 1u);
             }
-            umma_commit(&empty_bar[slot]);
           }
-          __syncwarp();
-          if (++slot == kSlots) {
-            slot = 0;
-            phase ^= 1;
-          }
+          umma_commit(&empty_bar[slot]);
+        }
+        __syncwarp();
+        if (++slot == kSlots) {
+          slot = 0;
+          phase ^= 1;
         }
       }
-      if (lane == 0) umma_commit(&tfull_bar[as]);
+      if (elect_one()) umma_commit(&tfull_bar[as]);
       __syncwarp();
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
       }
+    }
+    if ((p.debug & 32) && p.dbg_out && lane == 0) {
+      p.dbg_out[blockIdx.x * 16 + 4] = dbg_wfull;
+      p.dbg_out[blockIdx.x * 16 + 5] = dbg_wtempty;
+      p.dbg_out[blockIdx.x * 16 + 6] = dbg_tiles;
+      p.dbg_out[blockIdx.x * 16 + 7] = clock64() - dbg_t0;
     }
   } else {
     // 16 epilogue warps: lane quarter q = warp % 4, channel chunk cg = (warp - 2) / 4 (16 channels each)
@@ -241,6 +249,7 @@ int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvP
                      cudaStream_t stream) {
   ConvParams p = p_in;
   if (const char* e = getenv("MTB200_HALO_DEBUG")) p.debug = atoi(e);
+  if (const char* e = getenv("MTB200_HALO_DEBUG_PTR")) p.dbg_out = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   const size_t smem = 1024 + kWBytes + kSlots * kSlotBytes + 16 * 8 + 16;
   int dev = 0, sms = 0;
   MTB_CUDA_OK(cudaGetDevice(&dev));

@@ -101,6 +101,109 @@ __global__ void ca_scale_kernel(const float* __restrict__ sums, int parts, int C
   }
 }
 
+
+// RCAB channel-attention gate computed BEFORE the block's second convolution runs.
+// The gate needs mean_pixels(conv2(u) + b2).  A zero-padded 3x3 convolution is linear, so that mean follows from sums of
+// its INPUT: for tap (dy,dx) the sum over all output pixels of u[oy+dy][ox+dx] is the total minus the border row /
+// column the shifted window never reaches (plus the doubly removed corner).  conv1's epilogue already delivers the total
+// per channel; this kernel adds the four border lines, forms mean_y2 = b2 + W2 . S / HW in fp32 and runs the
+// squeeze/excite MLP.  conv2's epilogue can then write x + gate*(conv2(u)+b2) directly and the separate
+// read-scale-add pass over the page (1.2 GB per block) disappears.   One block of 1024 threads, C = 64.
+__global__ void __launch_bounds__(1024, 1)
+rcan_gate_kernel(const float* __restrict__ sums, int parts, const uint16_t* __restrict__ u, long long plane_stride,
+                 int planes, int H, int W, const float* __restrict__ wconv /* [64][64][3][3] */,
+                 const float* __restrict__ bconv, const float* __restrict__ w1, const float* __restrict__ b1,
+                 const float* __restrict__ w2, const float* __restrict__ b2, int R, float* __restrict__ scale) {
+  constexpr int C = 64;
+  __shared__ float red[128][C + 1];
+  __shared__ float tot[C], line[4][C], corner[4][C], shifted[9][C], mean[C], hid[64];
+  const int tid = threadIdx.x;
+  {  // total per channel from the conv epilogue's partial rows (fixed order -> deterministic)
+    const int c = tid & 63, g = tid >> 6;
+    float acc = 0.f;
+    for (int p = g; p < parts; p += 16) acc += sums[static_cast<long long>(p) * C + c];
+    red[g][c] = acc;
+    __syncthreads();
+    if (tid < C) {
+      float t = 0.f;
+      for (int k = 0; k < 16; ++k) t += red[k][tid];
+      tot[tid] = t;
+    }
+    __syncthreads();
+  }
+  // border lines: 0 = row 0, 1 = row H-1, 2 = column 0, 3 = column W-1; 8 threads cover the 64 channels of a pixel
+  const int v = tid & 7, slot = tid >> 3;
+  for (int b = 0; b < 4; ++b) {
+    const int len = b < 2 ? W : H;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = slot; i < len; i += 128) {
+      const long long pix = b == 0 ? i : b == 1 ? static_cast<long long>(H - 1) * W + i
+                            : b == 2 ? static_cast<long long>(i) * W : static_cast<long long>(i) * W + (W - 1);
+      for (int pl = 0; pl < planes; ++pl) {
+        const uint4 q = *reinterpret_cast<const uint4*>(u + pl * plane_stride + pix * C + v * 8);
+        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += bf16_to_f(w4[j] & 0xFFFF);
+          acc[2 * j + 1] += bf16_to_f(w4[j] >> 16);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[slot][v * 8 + j] = acc[j];
+    __syncthreads();
+    if (tid < C) {
+      float t = 0.f;
+      for (int k = 0; k < 128; ++k) t += red[k][tid];
+      line[b][tid] = t;
+    }
+    __syncthreads();
+  }
+  if (tid < 4 * C) {
+    const int k = tid >> 6, c = tid & 63;
+    const long long pix = (k & 2 ? static_cast<long long>(H - 1) * W : 0) + (k & 1 ? W - 1 : 0);
+    float t = 0.f;
+    for (int pl = 0; pl < planes; ++pl) t += bf16_to_f(u[pl * plane_stride + pix * C + c]);
+    corner[k][c] = t;   // 0 = (0,0), 1 = (0,W-1), 2 = (H-1,0), 3 = (H-1,W-1)
+  }
+  __syncthreads();
+  if (tid < 9 * C) {
+    const int tap = tid >> 6, c = tid & 63;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    float sft = tot[c];
+    if (dy == 1) sft -= line[0][c];
+    if (dy == -1) sft -= line[1][c];
+    if (dx == 1) sft -= line[2][c];
+    if (dx == -1) sft -= line[3][c];
+    if (dy != 0 && dx != 0) sft += corner[(dy == -1 ? 2 : 0) + (dx == -1 ? 1 : 0)][c];
+    shifted[tap][c] = sft;
+  }
+  __syncthreads();
+  {  // mean of conv2's output: 16 threads per output channel, 36 of the 576 terms each
+    const int co = tid >> 4, part = tid & 15;
+    float acc = 0.f;
+    for (int t = part; t < 576; t += 16) {
+      const int ci = t / 9, tap = t - ci * 9;
+      acc += wconv[co * 576 + t] * shifted[tap][ci];
+    }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (part == 0) mean[co] = acc / (static_cast<float>(H) * static_cast<float>(W)) + (bconv ? bconv[co] : 0.f);
+  }
+  __syncthreads();
+  if (tid < R) {
+    float h = b1 ? b1[tid] : 0.f;
+    for (int k = 0; k < C; ++k) h += w1[tid * C + k] * mean[k];
+    hid[tid] = fmaxf(h, 0.f);
+  }
+  __syncthreads();
+  if (tid < C) {
+    float o = b2 ? b2[tid] : 0.f;
+    for (int k = 0; k < R; ++k) o += w2[tid * R + k] * hid[k];
+    scale[tid] = 1.0f / (1.0f + expf(-o));
+  }
+}
+
 // y = x + t * scale[n][c]   (all hi/lo planes, NHWC, C multiple of 8)
 __global__ void scale_residual_kernel(const uint16_t* __restrict__ t, const uint16_t* __restrict__ x,
                                       const float* __restrict__ scale, uint16_t* __restrict__ y,
@@ -186,6 +289,20 @@ int mtb_ca_scale(const float* sums, int n_images, int parts_per_image, int C, fl
   if (groups < 1) groups = 1;
   ca_scale_kernel<<<n_images, groups * C, 0, static_cast<cudaStream_t>(stream)>>>(sums, parts_per_image, C, inv_hw, w1,
                                                                                 b1, w2, b2, R, scale_out);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_rcan_gate(const float* sums, int parts, const void* u, int planes, int H, int W, const float* conv_w,
+                  const float* conv_b, const float* w1, const float* b1, const float* w2, const float* b2, int R,
+                  float* scale_out, void* stream) {
+  MTB_REQUIRE(sums && u && conv_w && w1 && w2 && scale_out, "mtb_rcan_gate: null argument");
+  MTB_REQUIRE((planes == 1 || planes == 2) && H > 0 && W > 0 && R > 0 && R <= 64 && parts > 0,
+              "mtb_rcan_gate: bad arguments");
+  rcan_gate_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, parts, static_cast<const uint16_t*>(u), static_cast<long long>(H) * W * 64, planes, H, W, conv_w, conv_b, w1,
+      b1, w2, b2, R, scale_out);
   MTB_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -41,6 +41,17 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvParams& p, float (&v)
       v[4 * j + 3] += b.w;
     }
   }
+  if (p.chan_scale) {
+    const float4* s4 = reinterpret_cast<const float4*>(p.chan_scale + cbase);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b = __ldg(s4 + j);
+      v[4 * j] *= b.x;
+      v[4 * j + 1] *= b.y;
+      v[4 * j + 2] *= b.z;
+      v[4 * j + 3] *= b.w;
+    }
+  }
   // output location (element offset inside a plane) and the matching residual location
   long long off = pix * p.out_cstride + p.out_coff + cbase;
   long long roff = ((p.res_bcast ? (static_cast<long long>(oy) * p.Wo + ox) : pix)) * p.res_cstride + p.res_coff + cbase;

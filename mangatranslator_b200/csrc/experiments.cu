@@ -68,7 +68,93 @@ shifted_desc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, 64);
 }
 
+// MMA rate probe: one elected lane per CTA issues `iters` rounds of 36 tcgen05.mma (nine row-shifted A views x four
+// k16 slices, like one output tile of the halo kernels) on arbitrary shared-memory contents and the CTA reports the
+// clock64 span from first issue to commit arrival.  The shape is a template parameter and the issue loop is branch-free
+// so that the tensor pipe, not the issuing thread, is what is measured.  M2 > 0 appends a second MMA of shape M2 x N2
+// after each one (the mixed shapes of the bf16x3 schemes).
+template <int M1, int N1, int M2, int N2>
+__global__ void __launch_bounds__(64, 1) mma_rate_kernel(long long* cycles, int iters, int a_sbo, int a_shift) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (48 + 144) * 1024);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (48 + 144) * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + i;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    long long t0 = clock64();
+    if (elect_one()) {
+      constexpr uint32_t id1 = make_idesc_bf16(M1, N1);
+      constexpr uint32_t id2 = make_idesc_bf16(M2 > 0 ? M2 : 128, N2 > 0 ? N2 : 64);
+      const uint32_t a_base = sbase, b_base = sbase + 48 * 1024;
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t a0 = a_base + tap * a_shift, b0 = b_base + (tap & 7) * 16384;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_sdesc_sw128(a0 + k * 32, a_sbo, 0);
+            const uint64_t db = make_sdesc_sw128(b0 + k * 32, 1024, 0);
+            umma_bf16(0, da, db, id1, (it | tap | k) ? 1u : 0u);
+            if (M2 > 0) umma_bf16(256, da, db, id2, (it | tap | k) ? 1u : 0u);
+          }
+        }
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(0, 512);
+}
+
 }  // namespace
+
+// pattern: 0 M128N64, 1 M128N128, 2 M128N256, 3 M128N128+M128N64, 4 M128N240, 5 M64N240, 6 M64N256, 7 M64N128,
+//          8 M128N240+M64N240, 9 M64N64
+extern "C" int mtb_exp_mma_rate(long long* cycles, int ctas, int pattern, int iters, int a_sbo, int a_shift, int a_off,
+                                void* stream) {
+  (void)a_off;
+  const size_t smem = 1024 + (48 + 144) * 1024 + 64;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define MTB_RATE(M1, N1, M2, N2)                                                                              \
+  do {                                                                                                        \
+    MTB_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel<M1, N1, M2, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     static_cast<int>(smem)));                                                \
+    mma_rate_kernel<M1, N1, M2, N2><<<ctas, 64, smem, st>>>(cycles, iters, a_sbo, a_shift);                   \
+  } while (0)
+  switch (pattern) {
+    case 0: MTB_RATE(128, 64, 0, 0); break;
+    case 1: MTB_RATE(128, 128, 0, 0); break;
+    case 2: MTB_RATE(128, 256, 0, 0); break;
+    case 3: MTB_RATE(128, 128, 128, 64); break;
+    case 4: MTB_RATE(128, 240, 0, 0); break;
+    case 5: MTB_RATE(64, 240, 0, 0); break;
+    case 6: MTB_RATE(64, 256, 0, 0); break;
+    case 7: MTB_RATE(64, 128, 0, 0); break;
+    case 8: MTB_RATE(128, 240, 64, 240); break;
+    default: MTB_RATE(64, 64, 0, 0); break;
+  }
+#undef MTB_RATE
+  MTB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int mtb_exp_shifted_desc(const void* A /* bf16 [512][64] */, const void* B /* bf16 [64][64] */,
                                     float* D /* [128][64] */, int shift_rows, int sbo_bytes, int base_offset,

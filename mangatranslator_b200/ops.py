@@ -19,10 +19,12 @@ class ConvPlan:
     """
 
     def __init__(self, x, w, bias, out, *, k=1, stride=1, pad=0, act=None, residual=None, tile_sums=None,
-                 tile=None, mode=0, pixel_shuffle=False, x_coff=0, out_coff=0, res_coff=0, res_bcast=False, act_after_res=False):
+                 tile=None, mode=0, pixel_shuffle=False, x_coff=0, out_coff=0, res_coff=0, res_bcast=False, act_after_res=False,
+                 channel_scale=None):
         """Channel slices: `x` / `out` / `residual` may be wider (concat) tensors; the layer reads channels
         [x_coff, x_coff + Cin) and writes [out_coff, out_coff + Cout).  The weights' Cin is padded to a multiple of
-        64 with zeros, so whatever lies beyond the slice (or beyond the tensor: TMA zero-fills) contributes 0."""
+        64 with zeros, so whatever lies beyond the slice (or beyond the tensor: TMA zero-fills) contributes 0.
+        `channel_scale` (fp32 [Cout], device): out = act((conv + bias) * scale) + residual, read when the plan runs."""
         planes_in, n, h, wd, x_ctotal = x.shape
         assert w.shape[0] == planes_in and w.shape[1] == k * k, (w.shape, x.shape)
         cout, cin = w.shape[2], w.shape[3]
@@ -51,6 +53,10 @@ class ConvPlan:
                                          ptr(tile_sums), C.byref(h)), "mtb_conv_plan_create")
         self._h = h
         self.out = out
+        if channel_scale is not None:
+            assert channel_scale.dtype == torch.float32 and channel_scale.numel() >= cout
+            self._keep = self._keep + (channel_scale,)
+            check(lib().mtb_conv_plan_set_channel_scale(self._h, ptr(channel_scale)), "mtb_conv_plan_set_channel_scale")
 
     @property
     def num_mtiles(self) -> int:

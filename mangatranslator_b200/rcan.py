@@ -3,7 +3,14 @@
 Mirrors what the reference gets from spandrel (core/ml/model_manager.py:617-657): a callable
 `model(x: float32 (1,3,h,w) in [0,1]) -> (1,3,2h,2w)`; additionally `upscale_u8` keeps the page on the device as
 uint8 (what the batch pipeline uses).  Every convolution is a tcgen05 plan (bf16x3 by default = fp32-grade); the
-~200 RCAB body layers use the halo-tile kernel (conv_halo.cu).  Buffers are allocated once per input size.
+~400 RCAB body convs use the halo-tile kernels (conv_halo_cm.cu / conv_halo.cu).  Buffers are allocated once per
+input size.
+
+RCAB (spandrel RCAN: conv -> ReLU -> conv -> CALayer -> + x) runs as three launches:
+    u   = relu(conv1(x))                       halo conv, epilogue also emits per-channel sums of u
+    g   = gate(mean(conv2(u)))                 mtb_rcan_gate: the mean follows from sums of u (linearity), see the header
+    x'  = x + g * conv2(u)                     halo conv with channel scale + residual in the epilogue
+so the block's output is written once and the attention-weighted tensor is never materialised.
 """
 from __future__ import annotations
 
@@ -24,8 +31,9 @@ def _declare(l) -> None:
     l.mtb_image_to_planes.argtypes = [vp, i32, i32, i32, i32, f32, C.POINTER(f32), vp, i32, i32, vp]
     l.mtb_ca_scale.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp, vp, i32, vp, vp]
     l.mtb_scale_residual.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, i32, i32, vp]
+    l.mtb_rcan_gate.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     l.mtb_f32_to_u8.argtypes = [vp, C.c_longlong, i32, C.POINTER(f32), f32, vp, vp, vp]
-    for n in ("mtb_image_to_planes", "mtb_ca_scale", "mtb_scale_residual", "mtb_f32_to_u8"):
+    for n in ("mtb_image_to_planes", "mtb_ca_scale", "mtb_scale_residual", "mtb_f32_to_u8", "mtb_rcan_gate"):
         getattr(l, n).restype = i32
     l._ew_declared = True
 
@@ -74,7 +82,9 @@ class RcanB200:
                 cb1 = sd[base + ".3.conv_du.0.bias"].contiguous()
                 cd2 = sd[base + ".3.conv_du.2.weight"].reshape(f, -1).contiguous()
                 cb2 = sd[base + ".3.conv_du.2.bias"].contiguous()
-                grp.append((w1, w2, cd1, cb1, cd2, cb2))
+                w2f = sd[base + ".2.weight"].contiguous()                 # fp32 [64][64][3][3] for the gate's mean
+                b2f = sd[base + ".2.bias"].contiguous() if (base + ".2.bias") in sd else None
+                grp.append((w1, w2, cd1, cb1, cd2, cb2, w2f, b2f))
             self.blocks.append((grp, conv_w(f"body.{g}.body.{R}")))
         self.w_body_tail = conv_w(f"body.{G}")
         # upsampler conv: reorder output channels so the four PixelShuffle phases are contiguous 64-channel blocks
@@ -93,7 +103,7 @@ class RcanB200:
         def act(hh, ww, c=f):
             return torch.zeros((pl, n, hh, ww, c), dtype=bf, device=dev)
 
-        b = dict(x_in=act(h, w), head=act(h, w), u=act(h, w), t=act(h, w), pa=act(h, w), pb=act(h, w),
+        b = dict(x_in=act(h, w), head=act(h, w), u=act(h, w), pa=act(h, w), pb=act(h, w),
                  g0=act(h, w), g1=act(h, w), up=act(2 * h, 2 * w),
                  out32=torch.zeros((n, 2 * h, 2 * w, 16), dtype=torch.float32, device=dev),
                  scale=torch.zeros((n, f), dtype=torch.float32, device=dev))
@@ -113,12 +123,11 @@ class RcanB200:
         for gi, (grp, tailw) in enumerate(self.blocks):
             grp_in = src
             x = grp_in
-            for (w1, w2, cd1, cb1, cd2, cb2) in grp:
-                steps.append(("conv_body", conv(x, w1, b["u"], act="relu")))
-                steps.append(("conv_body", conv(b["u"], w2, b["t"], tile_sums=sums)))
-                steps.append(("ca", (parts, cd1, cb1, cd2, cb2)))
+            for (w1, w2, cd1, cb1, cd2, cb2, w2f, b2f) in grp:
                 dst = b["pa"] if x is not b["pa"] else b["pb"]
-                steps.append(("apply", (b["t"], x, dst)))     # RCAB: x + t * gate
+                steps.append(("conv_body", conv(x, w1, b["u"], act="relu", tile_sums=sums)))
+                steps.append(("gate", (parts, w2f, b2f, cd1, cb1, cd2, cb2)))
+                steps.append(("conv_body", conv(b["u"], w2, dst, residual=x, channel_scale=b["scale"])))
                 x = dst
             gout = b["g0"] if grp_in is not b["g0"] else b["g1"]
             steps.append(("conv", conv(x, tailw, gout, residual=grp_in)))   # group tail conv + group skip
@@ -143,14 +152,13 @@ class RcanB200:
         for kind, arg in b["steps"]:
             if kind in ("conv", "conv_body"):
                 arg.run()
-            elif kind == "ca":
-                parts, cd1, cb1, cd2, cb2 = arg
-                check(l.mtb_ca_scale(ptr(b["sums"]), 1, parts, f, inv_hw, ptr(cd1), ptr(cb1), ptr(cd2), ptr(cb2),
-                                     cd1.shape[0], ptr(b["scale"]), st), "mtb_ca_scale")
             else:
-                t, x, dst = arg
-                check(l.mtb_scale_residual(ptr(t), ptr(x), ptr(b["scale"]), ptr(dst), h * w, 1, f, self.planes, st),
-                      "mtb_scale_residual")
+                self._gate(b, arg, h, w, st)
+
+    def _gate(self, b: dict, arg, h: int, w: int, st) -> None:
+        parts, w2f, b2f, cd1, cb1, cd2, cb2 = arg
+        check(self.l.mtb_rcan_gate(ptr(b["sums"]), parts, ptr(b["u"]), self.planes, h, w, ptr(w2f), ptr(b2f), ptr(cd1),
+                                   ptr(cb1), ptr(cd2), ptr(cb2), cd1.shape[0], ptr(b["scale"]), st), "mtb_rcan_gate")
 
     def time_body_convs(self, img: torch.Tensor):
         """CUDA-event duration (ms) of every RCAB body conv launch during one pass over `img` (bench roofline)."""
@@ -168,14 +176,8 @@ class RcanB200:
                 evs.append((e0, e1))
             elif kind == "conv":
                 arg.run()
-            elif kind == "ca":
-                parts, cd1, cb1, cd2, cb2 = arg
-                check(l.mtb_ca_scale(ptr(b["sums"]), 1, parts, self.F, inv_hw, ptr(cd1), ptr(cb1), ptr(cd2), ptr(cb2),
-                                     cd1.shape[0], ptr(b["scale"]), st), "mtb_ca_scale")
             else:
-                t, x, dst = arg
-                check(l.mtb_scale_residual(ptr(t), ptr(x), ptr(b["scale"]), ptr(dst), h * w, 1, self.F, self.planes, st),
-                      "mtb_scale_residual")
+                self._gate(b, arg, h, w, st)
         torch.cuda.synchronize()
         return [a.elapsed_time(c) for a, c in evs]
 

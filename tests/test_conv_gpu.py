@@ -51,3 +51,25 @@ def test_conv_matches_fp64_reference(case):
         s = sums.sum(0)[:cout].double()
         rs = ref.sum((0, 2, 3))
         assert (s - rs).abs().max().item() < 1e-3 * max(1.0, rs.abs().max().item())
+
+
+def test_pixel_major_halo_kernel_still_matches():
+    """mode 3 pins the pixel-major bf16x3 halo kernel (conv_halo.cu), kept as the A/B partner of the channel-major one."""
+    from mangatranslator_b200 import planes as P
+    from mangatranslator_b200.ops import ConvPlan
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    x = torch.randn(1, 64, 70, 45, device=dev)
+    wt = torch.randn(64, 64, 3, 3, device=dev) / 24
+    xp, wp = P.nchw_to_planes(x, 2), P.conv_weight_to_planes(wt, 2)
+    outs = []
+    for mode in (3, 2):
+        o = torch.zeros(2, 1, 70, 45, 64, dtype=torch.bfloat16, device=dev)
+        ConvPlan(xp, wp, None, o, k=3, pad=1, act="relu", mode=mode).run()
+        torch.cuda.synchronize()
+        outs.append(P.planes_to_nchw(o, 64).double())
+    ref = F.relu(F.conv2d(P.planes_to_nchw(xp, 64).double(),
+                          P.merge_planes(wp)[:, :64, :64].reshape(3, 3, 64, 64).permute(2, 3, 0, 1).contiguous().double(),
+                          padding=1))
+    for got in outs:
+        assert (got - ref).abs().max().item() < 2e-4

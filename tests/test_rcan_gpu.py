@@ -52,3 +52,40 @@ def test_reference_call_shape_and_determinism():
     with torch.no_grad():
         ref = m(x)
     assert (y1.cpu() - ref).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("hw", [(37, 53), (1, 9), (16, 1)], ids=["odd", "one_row", "one_col"])
+def test_gate_from_input_sums_equals_gate_of_conv_output(hw):
+    """mtb_rcan_gate derives mean(conv2(u)) from sums of u (linearity of the zero-padded conv); it must equal the gate
+    the reference's CALayer computes from the materialised conv output."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from mangatranslator_b200 import planes as P
+    from mangatranslator_b200._lib import check, lib, ptr, stream_ptr
+    from mangatranslator_b200.rcan import _declare
+    h, w = hw
+    dev = torch.device("cuda:0")
+    l = lib()
+    _declare(l)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    u = torch.relu(torch.randn(1, 64, h, w, generator=g)).to(dev)
+    up = P.nchw_to_planes(u, 2)
+    uq = P.planes_to_nchw(up, 64).double()                      # what the kernels actually see
+    wc = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(dev)
+    bc = torch.randn(64, generator=g).to(dev)
+    w1 = (torch.randn(4, 64, generator=g) / 8).to(dev)
+    b1 = torch.randn(4, generator=g).to(dev)
+    w2 = torch.randn(64, 4, generator=g).to(dev)
+    b2 = torch.randn(64, generator=g).to(dev)
+    # partial-sum rows as a conv epilogue would deliver them: any partition of the per-channel total
+    tot = uq.sum((0, 2, 3)).float()
+    parts = 7
+    rows = torch.rand(parts, 64, device=dev)
+    rows = rows / rows.sum(0, keepdim=True) * tot
+    scale = torch.zeros(64, device=dev)
+    check(l.mtb_rcan_gate(ptr(rows.contiguous()), parts, ptr(up), 2, h, w, ptr(wc), ptr(bc), ptr(w1), ptr(b1), ptr(w2),
+                          ptr(b2), 4, ptr(scale), stream_ptr()), "mtb_rcan_gate")
+    torch.cuda.synchronize()
+    mean = (F.conv2d(uq, wc.double(), bc.double(), padding=1)).mean((0, 2, 3))
+    ref = torch.sigmoid(w2.double() @ torch.relu(w1.double() @ mean + b1.double()) + b2.double())
+    assert (scale.double() - ref).abs().max().item() < 2e-5

@@ -21,7 +21,7 @@ wt = torch.randn(64, 64, 3, 3, device=dev) / 24
 for planes in (2, 1):
     xp, wp = P.nchw_to_planes(x, planes), P.conv_weight_to_planes(wt, planes)
     o = torch.zeros(planes, 1, H, W, 64, dtype=torch.bfloat16, device=dev)
-    for mode, name in ((2, "halo"), (1, "per_tap")):
+    for mode, name in ((2, "halo"), (3, "halo_pixel_major"), (1, "per_tap")):
         plan = ConvPlan(xp, wp, None, o, k=3, pad=1, act="relu", mode=mode)
         ms = timeit(plan.run)
         out[f"layer_{name}_planes{planes}"] = dict(ms=ms, tflops_alg=2.0 * H * W * 64 * 64 * 9 / ms / 1e9)
