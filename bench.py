@@ -156,9 +156,10 @@ def measure_dominant_kernel(pipe, page_dev, peaks):
     flops = 2.0 * H * W * 64 * 64 * 9
     ach = flops / (avg_ms * 1e-3) / 1e12
     return dict(bound="tensor", achieved=ach, peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=ach / peaks["bf16_sustained"],
-                traffic=None, kernel="conv3x3_c64_halo_kernel<bf16x3>", launches_timed=len(durs), avg_ms=avg_ms,
+                traffic=None, kernel="conv3x3_c64_cm_kernel<bf16x3>", launches_timed=len(durs), avg_ms=avg_ms,
                 peak_source=peaks["source"] + " bf16_tflops_sustained",
-                note="algorithmic FLOPs (2*MAC of the fp32-grade conv); the bf16x3 scheme issues 3x that in bf16 MMAs")
+                note="algorithmic FLOPs (2*MAC of the fp32-grade conv); the channel-major bf16x3 kernel issues 4x that in "
+                     "bf16 MMAs ([W_hi;W_lo] rows against the hi and the lo activation plane)")
 
 
 def run_ours(args, coord):
@@ -221,7 +222,9 @@ def run_ours(args, coord):
     if coord.rank != 0:
         return
     roof = measure_dominant_kernel(pipe, devp[0], peaks)
-    prof = os.path.join(ROOT, "profiles", "r01_halo_conv_ncu.json")
+    prof = os.path.join(ROOT, "profiles", "r01_halo_cm_ncu.json")
+    if not os.path.exists(prof):
+        prof = os.path.join(ROOT, "profiles", "r01_halo_conv_ncu.json")
     if os.path.exists(prof):
         try:
             roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")

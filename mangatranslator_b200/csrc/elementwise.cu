@@ -115,56 +115,73 @@ rcan_gate_kernel(const float* __restrict__ sums, int parts, const uint16_t* __re
                  const float* __restrict__ bconv, const float* __restrict__ w1, const float* __restrict__ b1,
                  const float* __restrict__ w2, const float* __restrict__ b2, int R, float* __restrict__ scale) {
   constexpr int C = 64;
-  __shared__ float red[128][C + 1];
+  __shared__ float red[32][C];                      // per-warp partials (border lines) / per-group partials (total)
   __shared__ float tot[C], line[4][C], corner[4][C], shifted[9][C], mean[C], hid[64];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // second conv's weights for this thread's slice of the mean (16 threads per output channel, 36 terms each): issued
+  // first so the L2 round trip overlaps everything below
+  const int co = tid >> 4, part = tid & 15;
+  float wreg[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) wreg[i] = __ldg(wconv + co * 576 + part + 16 * i);
+
+  // border lines of u, one per group of 8 warps: 0 = row 0, 1 = row H-1, 2 = column 0, 3 = column W-1.
+  // 8 lanes cover the 64 channels of a pixel (16-byte loads), a warp takes 4 pixels per step.
+  {
+    const int b = warp >> 3, v = lane & 7, slot = ((warp & 7) << 2) | (lane >> 3);   // 32 pixel slots per line
+    const int len = b < 2 ? W : H;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long base = b == 1 ? static_cast<long long>(H - 1) * W : b == 3 ? W - 1 : 0;
+    const long long step = b < 2 ? 1 : W;           // pixels between consecutive elements of the line
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+#pragma unroll 4
+    for (int i = slot; i < len; i += 32) {
+      const uint16_t* px = u + (base + i * step) * C + v * 8;
+      const uint4 qh = *reinterpret_cast<const uint4*>(px);
+      const uint4 ql = planes == 2 ? *reinterpret_cast<const uint4*>(px + plane_stride) : zero4;
+      const uint32_t wh[4] = {qh.x, qh.y, qh.z, qh.w}, wl[4] = {ql.x, ql.y, ql.z, ql.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += bf16_to_f(wh[j] & 0xFFFF) + bf16_to_f(wl[j] & 0xFFFF);
+        acc[2 * j + 1] += bf16_to_f(wh[j] >> 16) + bf16_to_f(wl[j] >> 16);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][v * 8 + j] = acc[j];
+    }
+  }
+  __syncthreads();
+  if (tid < 4 * C) {
+    const int b = tid >> 6, c = tid & 63;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[b * 8 + k][c];
+    line[b][c] = t;
+    // corners: 0 = (0,0), 1 = (0,W-1), 2 = (H-1,0), 3 = (H-1,W-1)
+    const long long pix = (b & 2 ? static_cast<long long>(H - 1) * W : 0) + (b & 1 ? W - 1 : 0);
+    float cv = 0.f;
+    for (int pl = 0; pl < planes; ++pl) cv += bf16_to_f(u[pl * plane_stride + pix * C + c]);
+    corner[b][c] = cv;
+  }
+  __syncthreads();
   {  // total per channel from the conv epilogue's partial rows (fixed order -> deterministic)
     const int c = tid & 63, g = tid >> 6;
     float acc = 0.f;
     for (int p = g; p < parts; p += 16) acc += sums[static_cast<long long>(p) * C + c];
     red[g][c] = acc;
-    __syncthreads();
-    if (tid < C) {
-      float t = 0.f;
-      for (int k = 0; k < 16; ++k) t += red[k][tid];
-      tot[tid] = t;
-    }
-    __syncthreads();
   }
-  // border lines: 0 = row 0, 1 = row H-1, 2 = column 0, 3 = column W-1; 8 threads cover the 64 channels of a pixel
-  const int v = tid & 7, slot = tid >> 3;
-  for (int b = 0; b < 4; ++b) {
-    const int len = b < 2 ? W : H;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int i = slot; i < len; i += 128) {
-      const long long pix = b == 0 ? i : b == 1 ? static_cast<long long>(H - 1) * W + i
-                            : b == 2 ? static_cast<long long>(i) * W : static_cast<long long>(i) * W + (W - 1);
-      for (int pl = 0; pl < planes; ++pl) {
-        const uint4 q = *reinterpret_cast<const uint4*>(u + pl * plane_stride + pix * C + v * 8);
-        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[2 * j] += bf16_to_f(w4[j] & 0xFFFF);
-          acc[2 * j + 1] += bf16_to_f(w4[j] >> 16);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[slot][v * 8 + j] = acc[j];
-    __syncthreads();
-    if (tid < C) {
-      float t = 0.f;
-      for (int k = 0; k < 128; ++k) t += red[k][tid];
-      line[b][tid] = t;
-    }
-    __syncthreads();
-  }
-  if (tid < 4 * C) {
-    const int k = tid >> 6, c = tid & 63;
-    const long long pix = (k & 2 ? static_cast<long long>(H - 1) * W : 0) + (k & 1 ? W - 1 : 0);
+  __syncthreads();
+  if (tid < C) {
     float t = 0.f;
-    for (int pl = 0; pl < planes; ++pl) t += bf16_to_f(u[pl * plane_stride + pix * C + c]);
-    corner[k][c] = t;   // 0 = (0,0), 1 = (0,W-1), 2 = (H-1,0), 3 = (H-1,W-1)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t += red[k][tid];
+    tot[tid] = t;
   }
   __syncthreads();
   if (tid < 9 * C) {
@@ -179,12 +196,13 @@ rcan_gate_kernel(const float* __restrict__ sums, int parts, const uint16_t* __re
     shifted[tap][c] = sft;
   }
   __syncthreads();
-  {  // mean of conv2's output: 16 threads per output channel, 36 of the 576 terms each
-    const int co = tid >> 4, part = tid & 15;
+  {  // mean of conv2's output
     float acc = 0.f;
-    for (int t = part; t < 576; t += 16) {
+#pragma unroll
+    for (int i = 0; i < 36; ++i) {
+      const int t = part + 16 * i;
       const int ci = t / 9, tap = t - ci * 9;
-      acc += wconv[co * 576 + t] * shifted[tap][ci];
+      acc += wreg[i] * shifted[tap][ci];
     }
 #pragma unroll
     for (int o = 8; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

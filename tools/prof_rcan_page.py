@@ -1,5 +1,6 @@
 """One RCAN page (bf16x3) for an ncu launch list."""
-import sys
+import os, sys
+os.environ["MTB200_CUDA_GRAPHS"] = "0"
 sys.path.insert(0, ".")
 import torch
 from mangatranslator_b200 import weights as W
@@ -10,3 +11,4 @@ img = torch.randint(0, 256, (1536, 1024, 3), dtype=torch.uint8, device=dev)
 net.upscale_u8(img)
 torch.cuda.synchronize()
 print("done")
+
