@@ -231,12 +231,15 @@ def detect_speech_bubbles(image_path: Path, model_path, confidence=0.6, verbose=
 
 # ---- device-resident fast path used by the batch pipeline / bench -------------------------------------------------------
 def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.6, imgsz: int = 1600,
-                        seg_model: str = "sam2", injected_boxes: Optional[List[np.ndarray]] = None):
+                        seg_model: str = "sam2", injected_boxes: Optional[List[np.ndarray]] = None,
+                        own_masks: bool = False):
     """pages_bgr: device uint8 HxWx3 (BGR, like the cleaning stage wants).  Per page: letterbox -> YOLO graph -> decode
     + NMS + scale_boxes + reference dedup/containment (all on device, one small D2H of the box table) -> SAM 2.1
     masks on device.  Returns per page a list of detection dicts whose `sam_mask` is a DEVICE uint8 tensor and which
     carry `mask_bbox` so the cleaning stage needs no further host work.  `injected_boxes` (per page [P,4] float32
-    original-pixel boxes) bypasses the detector output (ground-truth boxes for stage-level parity runs)."""
+    original-pixel boxes) bypasses the detector output (ground-truth boxes for stage-level parity runs).  The SAM masks
+    live in the segmenter's static output buffer, which the next page overwrites: pass `own_masks=True` to get a copy
+    when detections of several pages must stay alive together."""
     from mangatranslator_b200.preproc import letterbox_device
     mm = get_model_manager()
     yolo = mm.load_yolo_speech_bubble(None)
@@ -262,6 +265,8 @@ def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.
             rgb = page[:, :, [2, 1, 0]].contiguous() if page.shape[2] == 3 else page[:, :, [2, 1, 0]].contiguous()
             enc = sam.encode(rgb)
             masks = sam.decode(enc, torch.from_numpy(boxes), (h, w))
+            if own_masks:
+                masks = masks.clone()
         for k in range(boxes.shape[0]):
             x0, y0, x1, y1 = [float(v) for v in boxes[k]]
             bx0, by0 = int(np.floor(max(0, min(x0, w)))), int(np.floor(max(0, min(y0, h))))

@@ -201,6 +201,56 @@ class HotPathPipeline:
                 timings[name] = timings.get(name, 0.0) + t[a].elapsed_time(t[b])
         return out, dets, batch
 
+    def run_pages_device(self, pages_bgr: Sequence[torch.Tensor],
+                         injected_boxes: Optional[Sequence[Optional[np.ndarray]]] = None,
+                         consume: Optional[Callable[[int, torch.Tensor], None]] = None):
+        """A group of device pages: detect+segment page by page, ONE cleaning launch for every bubble of the group (the
+        cleaning kernel runs one CTA per bubble, so a single page's ~12 bubbles leave most SMs idle), then the upscale
+        page by page.  `consume(i, out)` is called as each page's result becomes available (the upscaler's output is a
+        static buffer that the next page overwrites).  Returns (outputs or None when consumed, detections, clean batch)."""
+        n = len(pages_bgr)
+        dets = []
+        for i, page in enumerate(pages_bgr):
+            inj = None if injected_boxes is None or injected_boxes[i] is None else [injected_boxes[i]]
+            dets.append(detect_pages_device([page], confidence=self.confidence, imgsz=self.imgsz, seg_model=self.seg_model,
+                                            injected_boxes=inj, own_masks=n > 1)[0])
+        scales = {_processing_scale(int(p.shape[1]), int(p.shape[0])) for p in pages_bgr}
+        if len(scales) == 1:
+            batch = clean_pages_device(list(pages_bgr), dets, thresholding_value=self.thr, roi_shrink_px=self.shrink,
+                                       processing_scale=scales.pop())
+            cleaned = batch.pages_out
+        else:                                   # mixed page sizes: the scale-derived parameters differ per page
+            batch, cleaned = None, []
+            for page, d in zip(pages_bgr, dets):
+                b1 = clean_pages_device([page], [d], thresholding_value=self.thr, roi_shrink_px=self.shrink,
+                                        processing_scale=_processing_scale(int(page.shape[1]), int(page.shape[0])))
+                cleaned.append(b1.pages_out[0])
+        outs = []
+        for i in range(n):
+            out = cleaned[i]
+            if self.rcan is not None:
+                out = self.rcan.upscale_u8(cleaned[i], swap_rb=True)
+            if consume is not None:
+                consume(i, out)
+            else:
+                outs.append(out.clone() if self.rcan is not None else out)
+        return (None if consume is not None else outs), dets, batch
+
+    def run_pages(self, pages_bgr_host: Sequence[torch.Tensor], outs_host: Optional[Sequence[torch.Tensor]] = None,
+                  injected_boxes: Optional[Sequence[Optional[np.ndarray]]] = None):
+        """Host (pinned) uint8 pages in, host uint8 pages out, as a group (see run_pages_device)."""
+        pages = [p.to(self.device, non_blocking=True) for p in pages_bgr_host]
+        results: List[Optional[torch.Tensor]] = [None] * len(pages)
+
+        def consume(i: int, out: torch.Tensor) -> None:
+            dst = outs_host[i] if outs_host is not None else torch.empty(out.shape, dtype=torch.uint8, pin_memory=True)
+            dst.copy_(out, non_blocking=True)      # stream-ordered: done before the next page overwrites `out`
+            results[i] = dst
+
+        _, dets, batch = self.run_pages_device(pages, injected_boxes, consume)
+        torch.cuda.current_stream().synchronize()
+        return results, dets, batch
+
     def run_page(self, page_bgr_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, **kw):
         """Host (pinned) uint8 HxWx3 in, host uint8 out (the call a user of the stage API makes)."""
         page = page_bgr_host.to(self.device, non_blocking=True)

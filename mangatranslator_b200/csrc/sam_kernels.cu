@@ -322,6 +322,102 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnParams P) {
   }
 }
 
+// Few queries against many keys (the mask decoder's token -> image cross attention: 9 queries x 4096 keys per box and
+// head).  The general kernel above parallelises over queries and would leave one warp walking all keys; here one block
+// owns a (batch, head), keeps the whole score matrix [nq][nk] in shared memory and parallelises over KEYS.
+// Exact softmax in fp32 (max-subtracted), same arithmetic as the general kernel up to summation order.
+constexpr int kFewQThreads = 512;
+template <int HD>
+__global__ void __launch_bounds__(kFewQThreads) attention_fewq_kernel(AttnParams P) {
+  extern __shared__ float sm[];
+  const int nq = P.nq, nk = P.nk;
+  constexpr int hd = HD;
+  float* sc = sm;                                   // [nq][nk] scores, then unnormalised probabilities
+  float* qs = sc + static_cast<size_t>(nq) * nk;    // [nq][hd] scaled queries
+  float* lsum = qs + nq * hd;                       // [nq]
+  float* red = lsum + 16;                           // [kFewQThreads]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / P.heads, h = blockIdx.x - b * P.heads;
+  for (int i = tid; i < nq * hd; i += kFewQThreads) {
+    const int qi = i / hd, d = i - qi * hd;
+    const long long idx = (static_cast<long long>(b) * nq + qi) * P.q_ct + P.q_off + h * hd + d;
+    float v = bf16_to_f(P.q[idx]);
+    if (P.planes == 2) v += bf16_to_f(P.q[P.q_ps + idx]);
+    qs[i] = v * P.scale;
+  }
+  __syncthreads();
+  // scores: a thread takes whole keys (hd <= 32 values in registers) against all queries
+  for (int key = tid; key < nk; key += kFewQThreads) {
+    float kv[HD];
+    const long long row = static_cast<long long>(b) * nk + key;
+#pragma unroll
+    for (int c = 0; c < hd; c += 8) {
+      float t8[8];
+      load_tok8(P, P.k, P.k_ct, P.k_off + h * hd, P.k_ps, nullptr, row, c, t8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kv[c + j] = t8[j];
+    }
+    for (int qi = 0; qi < nq; ++qi) {
+      float sdot = 0.f;
+#pragma unroll
+      for (int d = 0; d < hd; ++d) sdot += qs[qi * hd + d] * kv[d];
+      sc[static_cast<size_t>(qi) * nk + key] = sdot;
+    }
+  }
+  __syncthreads();
+  // softmax statistics: warp w owns query w
+  if (warp < nq) {
+    float* row = sc + static_cast<size_t>(warp) * nk;
+    float m = -INFINITY;
+    for (int k2 = lane; k2 < nk; k2 += 32) m = fmaxf(m, row[k2]);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float l = 0.f;
+    for (int k2 = lane; k2 < nk; k2 += 32) {
+      const float pv = __expf(row[k2] - m);
+      row[k2] = pv;
+      l += pv;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (lane == 0) lsum[warp] = l;
+  }
+  __syncthreads();
+  // output: thread = (key split, query, channel)
+  const int per = nq * hd;
+  const int nsplit = kFewQThreads / per;            // >= 1 (checked by the launcher)
+  const int ks = tid / per, r = tid - ks * per;
+  float acc = 0.f;
+  if (ks < nsplit) {
+    const int qi = r / hd, d = r - qi * hd;
+    const int k0 = static_cast<int>(static_cast<long long>(nk) * ks / nsplit);
+    const int k1 = static_cast<int>(static_cast<long long>(nk) * (ks + 1) / nsplit);
+    const float* row = sc + static_cast<size_t>(qi) * nk;
+    const uint16_t* vp = P.v + (static_cast<long long>(b) * nk) * P.v_ct + P.v_off + h * hd + d;
+#pragma unroll 4
+    for (int key = k0; key < k1; ++key) {
+      const long long idx = static_cast<long long>(key) * P.v_ct;
+      float v = bf16_to_f(vp[idx]);
+      if (P.planes == 2) v += bf16_to_f(vp[P.v_ps + idx]);
+      acc += row[key] * v;
+    }
+  }
+  red[tid] = acc;
+  __syncthreads();
+  if (tid < per) {
+    float o = 0.f;
+    for (int s2 = 0; s2 < nsplit; ++s2) o += red[s2 * per + tid];
+    const int qi = tid / hd, d = tid - qi * hd;
+    o /= lsum[qi];
+    const long long idx = (static_cast<long long>(b) * nq + qi) * P.o_ct + P.o_off + h * hd + d;
+    uint16_t hi, lo;
+    split_bf16(o, hi, lo);
+    P.out[idx] = hi;
+    if (P.planes == 2) P.out[P.o_ps + idx] = lo;
+  }
+}
+
+
 // ---- patch embedding: (u8 - mean')/std' -> conv k x k / stride / pad (3 -> C) + bias + positional embedding -------
 // one thread per (output pixel, 8 output channels); weights in shared memory
 __global__ void patch_embed_kernel(const uint8_t* __restrict__ img, int H, int W, const float* __restrict__ mean,
@@ -549,6 +645,23 @@ int mtb_attention(const mtb_attn_desc* d, void* stream) {
   P.grid_h = d->grid_h; P.grid_w = d->grid_w; P.ws = d->ws; P.pool = d->pool;
   P.nwx = d->ws > 0 ? (d->grid_w + d->ws - 1) / d->ws : 1;
   P.pad_q = d->pad_q; P.pad_k = d->pad_k; P.pad_v = d->pad_v;
+  if (d->mode == 0 && d->nq <= 16 && d->nk >= 512 && (d->hd == 16 || d->hd == 32) && d->nq * d->hd <= kFewQThreads) {
+    const size_t fsmem = sizeof(float) * (static_cast<size_t>(d->nq) * d->nk + d->nq * d->hd + 16 + kFewQThreads);
+    if (fsmem <= 200 * 1024) {
+      if (d->hd == 16) {
+        MTB_CUDA_OK(cudaFuncSetAttribute(attention_fewq_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(fsmem)));
+        attention_fewq_kernel<16><<<d->B * d->heads, kFewQThreads, fsmem, static_cast<cudaStream_t>(stream)>>>(P);
+      } else {
+        MTB_CUDA_OK(cudaFuncSetAttribute(attention_fewq_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(fsmem)));
+        attention_fewq_kernel<32><<<d->B * d->heads, kFewQThreads, fsmem, static_cast<cudaStream_t>(stream)>>>(P);
+      }
+      MTB_CUDA_OK(cudaGetLastError());
+      g_launches.fetch_add(1);
+      return 0;
+    }
+  }
   const size_t smem = sizeof(float) * (static_cast<size_t>(kKT) * (d->hd + 1) + static_cast<size_t>(kKT) * d->hd +
                                        static_cast<size_t>(kQT) * d->hd);
   MTB_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -61,6 +61,22 @@ def test_hot_path_pipeline_matches_cpu_pipeline(small_models):
     assert (d > 1).mean() < 5e-3
 
 
+def test_grouped_pages_equal_page_by_page(small_models):
+    """run_pages (one cleaning launch for a group, masks copied out of the segmenter's static buffer) must return
+    byte-identical pages to run_page called page by page."""
+    from mangatranslator_b200 import synth
+    from mangatranslator_b200.core.pipeline import HotPathPipeline
+    h, w = 448, 384
+    pages = [synth.make_page(30 + i, h, w, n_bubbles=3 + i) for i in range(3)]
+    pipe = HotPathPipeline(seg_model="sam2", upscale=True, imgsz=640)
+    hosts = [torch.from_numpy(np.ascontiguousarray(p.image_rgb[:, :, ::-1])).pin_memory() for p in pages]
+    single = [pipe.run_page(hh, injected_boxes=p.boxes_xyxy)[0].clone() for hh, p in zip(hosts, pages)]
+    outs, dets, batch = pipe.run_pages(hosts, None, [p.boxes_xyxy for p in pages])
+    assert len(outs) == 3 and len(dets) == 3
+    for a, b in zip(single, outs):
+        assert torch.equal(a, b)
+
+
 def test_reference_shaped_stage_functions(small_models, tmp_path):
     """detect_speech_bubbles / clean_speech_bubbles / upscale_image / translate_and_render with the reference's
     signatures (cleaning_only + upscale_final_image), fake detector injected through ModelManager.models exactly like

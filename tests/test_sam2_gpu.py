@@ -64,3 +64,46 @@ def test_sam2_single_box_and_many_boxes_shapes():
     boxes = torch.tensor([[10., 20., 200., 300.]] * 12)
     out = net.decode(enc, boxes, (384, 512))
     assert out.shape == (12, 384, 512) and torch.equal(out[0], out[11])
+
+
+@pytest.mark.parametrize("shape", [(3, 8, 16, 9, 1024), (2, 2, 32, 100, 77), (1, 4, 96, 512, 512), (12, 8, 16, 9, 4096)],
+                         ids=["few_queries", "general", "global_hd96", "decoder_t2i"])
+def test_attention_kernels_match_torch(shape):
+    """mtb_attention (mode 0) against torch softmax attention on the plane-rounded inputs: every dispatch target
+    (general register-blocked kernel, few-queries/many-keys kernel) must agree to fp32 accuracy."""
+    import ctypes as C
+    from mangatranslator_b200 import planes as P
+    from mangatranslator_b200._lib import check, lib, stream_ptr
+    from mangatranslator_b200.sam2 import AttnDesc, _declare
+    B, heads, hd, nq, nk = shape
+    dev = torch.device("cuda:0")
+    l = lib()
+    _declare(l)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    ct = heads * hd
+
+    def mk(n):
+        x = torch.randn(B * n, ct, generator=g).to(dev)
+        xp = torch.stack([x.to(torch.bfloat16), (x - x.to(torch.bfloat16).float()).to(torch.bfloat16)])   # hi, lo planes
+        return xp.contiguous(), (xp[0].float() + xp[1].float()).double()
+
+    qp, q = mk(nq)
+    kp, k = mk(nk)
+    vp, v = mk(nk)
+    out = torch.zeros(2, B * nq, ct, dtype=torch.bfloat16, device=dev)
+    d = AttnDesc()
+    d.B, d.heads, d.hd, d.nq, d.nk = B, heads, hd, nq, nk
+    d.scale = float(hd) ** -0.5
+    d.q, d.k, d.v, d.out = qp.data_ptr(), kp.data_ptr(), vp.data_ptr(), out.data_ptr()
+    d.q_ct = d.k_ct = d.v_ct = d.o_ct = ct
+    d.q_ps, d.k_ps, d.v_ps, d.o_ps = qp[0].numel(), kp[0].numel(), vp[0].numel(), out[0].numel()
+    d.planes, d.mode = 2, 0
+    check(l.mtb_attention(C.byref(d), stream_ptr()), "mtb_attention")
+    torch.cuda.synchronize()
+    qh = q.view(B, nq, heads, hd).permute(0, 2, 1, 3)
+    kh = k.view(B, nk, heads, hd).permute(0, 2, 1, 3)
+    vh = v.view(B, nk, heads, hd).permute(0, 2, 1, 3)
+    ref = torch.softmax(qh @ kh.transpose(-1, -2) * d.scale, -1) @ vh
+    ref = ref.permute(0, 2, 1, 3).reshape(B * nq, ct)
+    got = out[0].double() + out[1].double()
+    assert (got - ref).abs().max().item() < 2e-5
