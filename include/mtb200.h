@@ -241,8 +241,11 @@ typedef struct mtb_attn_desc {
                out-of-grid positions are padding whose q/k/v are pad_q/pad_k/pad_v (the qkv bias) */
   int grid_h, grid_w, ws, pool; /* pool: queries are 2x2 max-pooled inside each window (Hiera stage transition) */
   const float *pad_q, *pad_k, *pad_v;
+  void* workspace;           /* optional device scratch: with >= mtb_attention_workspace_bytes() a mode-0 call with */
+  long long workspace_bytes; /* two planes, head dim 64/96/128, nq >= 128, nk >= 256 runs on tcgen05 (attn_tc.cu)    */
 } mtb_attn_desc;
 int mtb_attention(const mtb_attn_desc* d /* host */, void* stream);
+long long mtb_attention_workspace_bytes(int B, int heads, int hd, int nk);
 
 /* Sam2PatchEmbeddings on the normalised image + positional embedding: u8 RGB HxWx3 -> planes [Ho][Wo][C] */
 int mtb_sam_patch_embed(const uint8_t* img, int H, int W, const float* mean3, const float* std3, const float* w,

@@ -16,6 +16,11 @@ extern std::atomic<long long> g_launches;
 }
 using namespace mtb;
 
+namespace mtb {
+long long attention_tc_workspace_bytes(int B, int heads, int hd, int nk);
+int launch_attention_tc(const mtb_attn_desc* d, cudaStream_t st);
+}  // namespace mtb
+
 namespace {
 
 int sm_count4() {
@@ -622,8 +627,20 @@ int mtb_add_planes(const void* a, const void* b, void* out, long long rows, int 
   return 0;
 }
 
+long long mtb_attention_workspace_bytes(int B, int heads, int hd, int nk) {
+  return mtb::attention_tc_workspace_bytes(B, heads, hd, nk);
+}
+
 int mtb_attention(const mtb_attn_desc* d, void* stream) {
   MTB_REQUIRE(d && d->q && d->k && d->v && d->out, "mtb_attention: null argument");
+  {
+    const int rc = mtb::launch_attention_tc(d, static_cast<cudaStream_t>(stream));
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      g_launches.fetch_add(2);   // V transpose + attention
+      return 0;
+    }
+  }
   MTB_REQUIRE(d->hd >= 1 && d->hd <= kMaxHD, "mtb_attention: head dim %d not supported (<= %d)", d->hd, kMaxHD);
   MTB_REQUIRE(!(d->mode == 1 && d->pool && (d->ws & 1)), "mtb_attention: pooled windows need an even window size");
   AttnParams P;

@@ -37,7 +37,8 @@ class AttnDesc(C.Structure):
                 ("q_ps", C.c_longlong), ("k_ps", C.c_longlong), ("v_ps", C.c_longlong), ("o_ps", C.c_longlong),
                 ("planes", C.c_int), ("mode", C.c_int),
                 ("grid_h", C.c_int), ("grid_w", C.c_int), ("ws", C.c_int), ("pool", C.c_int),
-                ("pad_q", C.c_void_p), ("pad_k", C.c_void_p), ("pad_v", C.c_void_p)]
+                ("pad_q", C.c_void_p), ("pad_k", C.c_void_p), ("pad_v", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong)]
 
 
 def _declare(l) -> None:
@@ -48,6 +49,8 @@ def _declare(l) -> None:
     l.mtb_maxpool2x2.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     l.mtb_add_planes.argtypes = [vp, vp, vp, i64, i32, i64, i32, vp]
     l.mtb_attention.argtypes = [C.POINTER(AttnDesc), vp]
+    l.mtb_attention_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    l.mtb_attention_workspace_bytes.restype = i64
     l.mtb_sam_prompt_boxes.argtypes = [vp, f32, f32, i32, vp, i32, vp, vp, vp, f32, vp, vp]
     l.mtb_sam_hyper_masks.argtypes = [vp, i32, vp, i32, i32, i32, i64, vp, vp]
     l.mtb_sam_select_mask.argtypes = [vp, vp, i32, i32, i64, f32, f32, vp, vp]
@@ -409,6 +412,10 @@ class Sam2B200:
         elif ws == 0:                      # global attention over the whole token grid
             g = a["grid"]
             d.mode, d.B, d.nq, d.nk = 0, 1, g * g, g * g
+            if "ws_buf" not in a:          # scratch for the tensor-core path (transposed V), allocated once per step
+                need = self.l.mtb_attention_workspace_bytes(1, a["heads"], a["hd"], g * g)
+                a["ws_buf"] = torch.empty(max(int(need), 16), dtype=torch.uint8, device=self.device)
+            d.workspace, d.workspace_bytes = a["ws_buf"].data_ptr(), a["ws_buf"].numel()
         else:                              # Hiera windows (+ optional query pooling)
             g = a["grid"]
             nw = (g + ws - 1) // ws

@@ -66,8 +66,10 @@ def test_sam2_single_box_and_many_boxes_shapes():
     assert out.shape == (12, 384, 512) and torch.equal(out[0], out[11])
 
 
-@pytest.mark.parametrize("shape", [(3, 8, 16, 9, 1024), (2, 2, 32, 100, 77), (1, 4, 96, 512, 512), (12, 8, 16, 9, 4096)],
-                         ids=["few_queries", "general", "global_hd96", "decoder_t2i"])
+@pytest.mark.parametrize("shape", [(3, 8, 16, 9, 1024), (2, 2, 32, 100, 77), (1, 4, 96, 512, 512), (12, 8, 16, 9, 4096),
+                                   (1, 4, 96, 4096, 4096), (2, 2, 64, 200, 300), (1, 2, 128, 256, 320)],
+                         ids=["few_queries", "general", "tc_hd96", "decoder_t2i", "tc_sam_global", "tc_ragged_hd64",
+                              "tc_hd128"])
 def test_attention_kernels_match_torch(shape):
     """mtb_attention (mode 0) against torch softmax attention on the plane-rounded inputs: every dispatch target
     (general register-blocked kernel, few-queries/many-keys kernel) must agree to fp32 accuracy."""
@@ -98,8 +100,13 @@ def test_attention_kernels_match_torch(shape):
     d.q_ct = d.k_ct = d.v_ct = d.o_ct = ct
     d.q_ps, d.k_ps, d.v_ps, d.o_ps = qp[0].numel(), kp[0].numel(), vp[0].numel(), out[0].numel()
     d.planes, d.mode = 2, 0
+    expect_tc = hd in (64, 96, 128) and nq >= 128 and nk >= 256
+    ws = torch.empty(max(int(l.mtb_attention_workspace_bytes(B, heads, hd, nk)), 16), dtype=torch.uint8, device=dev)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+    n0 = l.mtb_launch_count()
     check(l.mtb_attention(C.byref(d), stream_ptr()), "mtb_attention")
     torch.cuda.synchronize()
+    assert (l.mtb_launch_count() - n0 == 2) == expect_tc        # tensor-core path = V transpose + attention
     qh = q.view(B, nq, heads, hd).permute(0, 2, 1, 3)
     kh = k.view(B, nk, heads, hd).permute(0, 2, 1, 3)
     vh = v.view(B, nk, heads, hd).permute(0, 2, 1, 3)
