@@ -121,15 +121,6 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
   p.Wo = (d->W + 2 * d->pad - d->KW) / d->stride + 1;
   p.cin_chunks = d->Cin / 64;
   p.Cout = d->Cout;
-  // channel tile: largest multiple-of-16 divisor of Cout that is <= 256
-  int bn = 0;
-  for (int c = 256; c >= 16; c -= 16)
-    if (d->Cout % c == 0) {
-      bn = c;
-      break;
-    }
-  p.BN = bn;
-  p.n_tiles_n = d->Cout / bn;
   if (d->tile_w > 0 && d->tile_h > 0) {
     p.TW = d->tile_w;
     p.TH = d->tile_h;
@@ -194,6 +185,37 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
   }
   p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
   p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
+  {
+    // channel tile (N of the MMA): a multiple-of-16 divisor of Cout.  Start from the largest one that still leaves
+    // three pipeline stages (two-plane layers: 128), then shrink towards 64 while the layer has fewer tiles than SMs —
+    // deep, spatially small layers are latency bound and gain more from extra CTAs and ring depth than from a wide N.
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long m_tiles = static_cast<long long>(p.N) * p.tiles_y * p.tiles_x;
+    const int cap = d->planes_in == 2 ? 128 : 256;
+    int bn = 0;
+    for (int c = cap; c >= 16; c -= 16)
+      if (d->Cout % c == 0) {
+        bn = c;
+        break;
+      }
+    if (bn == 0)
+      for (int c = 256; c > cap; c -= 16)     // no divisor below the cap (e.g. Cout = 176): take what divides
+        if (d->Cout % c == 0) bn = c;
+    while (bn > 64 && m_tiles * (d->Cout / bn) < sms) {
+      int nb = 0;
+      for (int c = bn - 16; c >= 64; c -= 16)
+        if (d->Cout % c == 0) {
+          nb = c;
+          break;
+        }
+      if (nb == 0) break;
+      bn = nb;
+    }
+    p.BN = bn;
+    p.n_tiles_n = d->Cout / bn;
+  }
   // global-average-pool partials: one row per (CTA, lane quarter) when a launch covers a single image
   p.sums_per_cta = (p.N == 1 && p.n_tiles_n == 1) ? 1 : 0;
   pl->nsplit = d->planes_in == 2 ? 3 : 1;

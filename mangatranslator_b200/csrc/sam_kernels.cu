@@ -340,7 +340,6 @@ __global__ void __launch_bounds__(kFewQThreads) attention_fewq_kernel(AttnParams
   float* sc = sm;                                   // [nq][nk] scores, then unnormalised probabilities
   float* qs = sc + static_cast<size_t>(nq) * nk;    // [nq][hd] scaled queries
   float* lsum = qs + nq * hd;                       // [nq]
-  float* red = lsum + 16;                           // [kFewQThreads]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / P.heads, h = blockIdx.x - b * P.heads;
   for (int i = tid; i < nq * hd; i += kFewQThreads) {
@@ -388,33 +387,39 @@ __global__ void __launch_bounds__(kFewQThreads) attention_fewq_kernel(AttnParams
     if (lane == 0) lsum[warp] = l;
   }
   __syncthreads();
-  // output: thread = (key split, query, channel)
-  const int per = nq * hd;
-  const int nsplit = kFewQThreads / per;            // >= 1 (checked by the launcher)
+  // output: thread = (key split, query, 8-channel group); 16-byte loads of V, partial sums folded through shared memory
+  constexpr int DG = HD / 8;
+  const int per = nq * DG;                          // threads per key split
+  const int nsplit = min(kFewQThreads / per, nk / hd);   // >= 1; the partials must fit in the score storage
   const int ks = tid / per, r = tid - ks * per;
-  float acc = 0.f;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int qi = r / DG, dg = r - qi * DG;
   if (ks < nsplit) {
-    const int qi = r / hd, d = r - qi * hd;
     const int k0 = static_cast<int>(static_cast<long long>(nk) * ks / nsplit);
     const int k1 = static_cast<int>(static_cast<long long>(nk) * (ks + 1) / nsplit);
     const float* row = sc + static_cast<size_t>(qi) * nk;
-    const uint16_t* vp = P.v + (static_cast<long long>(b) * nk) * P.v_ct + P.v_off + h * hd + d;
-#pragma unroll 4
+#pragma unroll 2
     for (int key = k0; key < k1; ++key) {
-      const long long idx = static_cast<long long>(key) * P.v_ct;
-      float v = bf16_to_f(vp[idx]);
-      if (P.planes == 2) v += bf16_to_f(vp[P.v_ps + idx]);
-      acc += row[key] * v;
+      float v8[8];
+      load_tok8(P, P.v, P.v_ct, P.v_off + h * hd, P.v_ps, nullptr, static_cast<long long>(b) * nk + key, dg * 8, v8);
+      const float pw = row[key];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += pw * v8[j];
     }
   }
-  red[tid] = acc;
+  __syncthreads();                                  // scores are dead from here: reuse their storage for the partials
+  float* part = sc;                                 // [nsplit][nq][hd]
+  if (ks < nsplit) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[(ks * nq + qi) * hd + dg * 8 + j] = acc[j];
+  }
   __syncthreads();
-  if (tid < per) {
+  if (tid < nq * hd) {
     float o = 0.f;
-    for (int s2 = 0; s2 < nsplit; ++s2) o += red[s2 * per + tid];
-    const int qi = tid / hd, d = tid - qi * hd;
-    o /= lsum[qi];
-    const long long idx = (static_cast<long long>(b) * nq + qi) * P.o_ct + P.o_off + h * hd + d;
+    for (int s2 = 0; s2 < nsplit; ++s2) o += part[s2 * nq * hd + tid];
+    const int q2 = tid / hd, d = tid - q2 * hd;
+    o /= lsum[q2];
+    const long long idx = (static_cast<long long>(b) * nq + q2) * P.o_ct + P.o_off + h * hd + d;
     uint16_t hi, lo;
     split_bf16(o, hi, lo);
     P.out[idx] = hi;
@@ -663,7 +668,7 @@ int mtb_attention(const mtb_attn_desc* d, void* stream) {
   P.nwx = d->ws > 0 ? (d->grid_w + d->ws - 1) / d->ws : 1;
   P.pad_q = d->pad_q; P.pad_k = d->pad_k; P.pad_v = d->pad_v;
   if (d->mode == 0 && d->nq <= 16 && d->nk >= 512 && (d->hd == 16 || d->hd == 32) && d->nq * d->hd <= kFewQThreads) {
-    const size_t fsmem = sizeof(float) * (static_cast<size_t>(d->nq) * d->nk + d->nq * d->hd + 16 + kFewQThreads);
+    const size_t fsmem = sizeof(float) * (static_cast<size_t>(d->nq) * d->nk + d->nq * d->hd + 16);
     if (fsmem <= 200 * 1024) {
       if (d->hd == 16) {
         MTB_CUDA_OK(cudaFuncSetAttribute(attention_fewq_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
