@@ -17,12 +17,26 @@ TOL = 1e-3
 MARGIN = 2e-3
 
 
-def _case(seed, h, w, n_boxes, spread):
+def _large_like_config():
+    """Hiera-large geometry (the checkpoint the reference loads, core/ml/model_manager.py:202-204: 144..1152 channels,
+    2/4/8/16 heads = head dim 72, windows 8/4/16/8) with fewer blocks per stage so the CPU oracle stays in seconds."""
+    from transformers import Sam2Config
+    cfg = Sam2Config()
+    bc = cfg.vision_config.backbone_config
+    bc.hidden_size, bc.embed_dim_per_stage = 144, [144, 288, 576, 1152]
+    bc.blocks_per_stage, bc.num_attention_heads_per_stage = [1, 2, 4, 2], [2, 4, 8, 16]
+    bc.global_attention_blocks, bc.window_size_per_stage = [4, 6], [8, 4, 16, 8]
+    bc.window_positional_embedding_background_size = [7, 7]
+    cfg.vision_config.backbone_channel_list = [1152, 576, 288, 144]
+    return cfg
+
+
+def _case(seed, h, w, n_boxes, spread, config=None):
     from mangatranslator_b200 import synth
     from mangatranslator_b200.sam2 import Sam2B200
     pg = synth.make_page(seed, h, w, n_bubbles=max(n_boxes, 3))
     boxes = pg.boxes_xyxy[:n_boxes].astype(np.float32)
-    m = S.make_model(seed, spread=spread)
+    m = S.make_model(seed, config=config, spread=spread)
     ref = S.segment(m, S.make_processor(), Image.fromarray(pg.image_rgb), boxes)
     dev = torch.device("cuda:0")
     net = Sam2B200(m.state_dict(), m.config, dev)
@@ -33,10 +47,11 @@ def _case(seed, h, w, n_boxes, spread):
     return m, net, enc, ref, masks, logits, sel, full, iou
 
 
-@pytest.mark.parametrize("hw,spread", [((480, 400), 1.0), ((600, 448), 100.0)], ids=["default_init", "spread100"])
-def test_sam2_matches_transformers_oracle(hw, spread):
+@pytest.mark.parametrize("hw,spread,large", [((480, 400), 1.0, False), ((600, 448), 100.0, False), ((480, 400), 100.0, True)],
+                         ids=["default_init", "spread100", "hiera_large_geometry"])
+def test_sam2_matches_transformers_oracle(hw, spread, large):
     from mangatranslator_b200 import planes as P
-    m, net, enc, ref, masks, logits, sel, full, iou = _case(3, hw[0], hw[1], 3, spread)
+    m, net, enc, ref, masks, logits, sel, full, iou = _case(3, hw[0], hw[1], 3, spread, _large_like_config() if large else None)
     # encoder / neck features
     extra = (m.prompt_encoder.no_mask_embed.weight.reshape(-1)).view(1, -1, 1, 1)
     emb = P.planes_to_nchw(enc["emb"], 256).cpu() - extra
