@@ -151,13 +151,19 @@ def measure_dominant_kernel(pipe, page_dev, peaks):
     rcan = pipe.rcan
     rcan.upscale_u8(page_dev, swap_rb=True)
     torch.cuda.synchronize()
-    durs = rcan.time_body_convs(page_dev)
+    steps = rcan.time_steps(page_dev)
+    durs = [ms for k, ms in steps if k == "conv_body"]
     avg_ms = float(np.mean(durs))
+    by_kind = {}
+    for k, ms in steps:
+        by_kind[k] = by_kind.get(k, 0.0) + ms
     flops = 2.0 * H * W * 64 * 64 * 9
     ach = flops / (avg_ms * 1e-3) / 1e12
     return dict(bound="tensor", achieved=ach, peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=ach / peaks["bf16_sustained"],
                 traffic=None, kernel="conv3x3_c64_cm_kernel<bf16x3>", launches_timed=len(durs), avg_ms=avg_ms,
                 peak_source=peaks["source"] + " bf16_tflops_sustained",
+                upscale_launch_ms_by_kind={k: round(v, 3) for k, v in by_kind.items()},
+                conv1_avg_ms=float(np.mean(durs[0::2])), conv2_avg_ms=float(np.mean(durs[1::2])),
                 note="algorithmic FLOPs (2*MAC of the fp32-grade conv); the channel-major bf16x3 kernel issues 4x that in "
                      "bf16 MMAs ([W_hi;W_lo] rows against the hi and the lo activation plane)")
 

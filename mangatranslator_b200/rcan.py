@@ -160,26 +160,28 @@ class RcanB200:
         check(self.l.mtb_rcan_gate(ptr(b["sums"]), parts, ptr(b["u"]), self.planes, h, w, ptr(w2f), ptr(b2f), ptr(cd1),
                                    ptr(cb1), ptr(cd2), ptr(cb2), cd1.shape[0], ptr(b["scale"]), st), "mtb_rcan_gate")
 
-    def time_body_convs(self, img: torch.Tensor):
-        """CUDA-event duration (ms) of every RCAB body conv launch during one pass over `img` (bench roofline)."""
+    def time_steps(self, img: torch.Tensor):
+        """CUDA-event duration (ms) of every launch of one pass over `img`, as (kind, ms) in launch order; kinds:
+        "conv_body" (RCAB 3x3 convs), "gate", "conv" (head / group tails / upsampler / tail)."""
         h, w, _ = img.shape
         b = self._get(h, w)
         evs = []
-        l, st = self.l, stream_ptr()
-        inv_hw = 1.0 / float(h * w)
+        st = stream_ptr()
         for kind, arg in b["steps"]:
-            if kind == "conv_body":
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                arg.run()
-                e1.record()
-                evs.append((e0, e1))
-            elif kind == "conv":
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if kind in ("conv", "conv_body"):
                 arg.run()
             else:
                 self._gate(b, arg, h, w, st)
+            e1.record()
+            evs.append((kind, e0, e1))
         torch.cuda.synchronize()
-        return [a.elapsed_time(c) for a, c in evs]
+        return [(k, a.elapsed_time(c)) for k, a, c in evs]
+
+    def time_body_convs(self, img: torch.Tensor):
+        """CUDA-event duration (ms) of every RCAB body conv launch during one pass over `img` (bench roofline)."""
+        return [ms for k, ms in self.time_steps(img) if k == "conv_body"]
 
     def _upscale_static(self, b: dict, h: int, w: int, c: int, swap_rb: bool, want_float: bool) -> None:
         """page in b['in_u8'] -> b['out_u8'] (and b['out_f']); only static buffers, so the sequence can be graph-captured."""

@@ -1,0 +1,86 @@
+"""GPU: the BASELINE-size workload (1536x1024 page, YOLOv8m-seg@1600, SAM 2.1-tiny, RCAN 10x20) through the whole hot
+path, checked with size-independent properties the domain offers — the CPU oracles take minutes at this size, so the
+oracle comparisons live in the small-size tests and this file pins what must hold for ANY correct implementation:
+NMS invariants, masks inside their clip boxes, cleaning touches only masked regions, bit-identical reruns, grouped ==
+page-by-page."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+H, W = 1536, 1024
+
+
+def _iou(a, b):
+    ix = max(0.0, min(a[2], b[2]) - max(a[0], b[0]))
+    iy = max(0.0, min(a[3], b[3]) - max(a[1], b[1]))
+    inter = ix * iy
+    ua = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
+    return inter / ua if ua > 0 else 0.0
+
+
+@pytest.fixture(scope="module")
+def pipe():
+    from mangatranslator_b200.core.ml.model_manager import get_model_manager
+    from mangatranslator_b200.core.pipeline import HotPathPipeline
+    mm = get_model_manager()
+    mm.unload_all()
+    p = HotPathPipeline(seg_model="sam2", upscale=True, upscale_model="model")
+    yield p
+    mm.unload_all()
+
+
+def test_detector_output_satisfies_nms_invariants(pipe):
+    """Raw detector output (before the reference's dedup): sorted by confidence, all above the threshold, no pair of
+    kept same-class boxes above the IoU threshold, boxes inside the image."""
+    from mangatranslator_b200 import synth
+    from mangatranslator_b200.preproc import letterbox_device
+    pg = synth.make_page(77, H, W)
+    page = torch.from_numpy(np.ascontiguousarray(pg.image_rgb[:, :, ::-1])).cuda()
+    lb = letterbox_device(page, 1600, swap_rb=True)
+    assert tuple(lb.shape) == (1600, 1088, 3)
+    g = pipe.yolo.forward_letterboxed(lb)
+    conf = 0.05                                              # low threshold: plenty of candidates from synthetic weights
+    det, cnt, _ = pipe.yolo.detect(g, conf, (H, W), tuple(lb.shape[:2]), apply_reference_dedup=False)
+    n = int(cnt[0].item())
+    rows = det[:n].cpu().numpy()
+    assert 0 <= n <= 300
+    if n:
+        assert np.all(rows[:, 4] > conf)
+        assert np.all(np.diff(rows[:, 4]) <= 0)             # confidence-descending
+        assert rows[:, 0].min() >= 0 and rows[:, 1].min() >= 0 and rows[:, 2].max() <= W and rows[:, 3].max() <= H
+        for i in range(n):
+            for j in range(i):
+                if int(rows[i, 5]) == int(rows[j, 5]):
+                    assert _iou(rows[i, :4], rows[j, :4]) <= 0.7 + 1e-4
+
+
+def test_page_properties_and_determinism(pipe):
+    from mangatranslator_b200 import synth
+    pg = synth.make_page(78, H, W)
+    host = torch.from_numpy(np.ascontiguousarray(pg.image_rgb[:, :, ::-1])).pin_memory()
+    out1, dets, batch = pipe.run_page(host, injected_boxes=pg.boxes_xyxy)
+    out1 = out1.clone()
+    assert tuple(out1.shape) == (2 * H, 2 * W, 3) and out1.dtype == torch.uint8
+    assert len(dets) == len(pg.boxes_xyxy)
+    cleaned = batch.pages_out[0].cpu().numpy()
+    changed = np.any(cleaned != host.numpy(), axis=2)
+    union = np.zeros((H, W), bool)
+    for d, box in zip(dets, pg.boxes_xyxy):
+        m = d["sam_mask"].cpu().numpy()
+        assert set(np.unique(m)) <= {0, 255}
+        x0, y0 = int(np.floor(box[0])), int(np.floor(box[1]))
+        x1, y1 = int(np.ceil(box[2])), int(np.ceil(box[3]))
+        outside = m.copy()
+        outside[max(y0, 0):y1, max(x0, 0):x1] = 0
+        assert not outside.any()                             # SAM mask is clipped to floor/ceil of its box
+        union[max(y0 - 8, 0):y1 + 8, max(x0 - 8, 0):x1 + 8] = True
+    # cleaning paints only inside the bubbles' regions of interest (mask dilated by the 9x9 ellipse, so within 8 px of
+    # the clip box)
+    assert not (changed & ~union).any()
+    # bit-identical rerun (CUDA graphs, static buffers, per-CTA partial sums are all order-deterministic)
+    out2, _, _ = pipe.run_page(host, injected_boxes=pg.boxes_xyxy)
+    assert torch.equal(out1, out2)
+    # group API returns the same bytes
+    outs, _, _ = pipe.run_pages([host, host], None, [pg.boxes_xyxy, pg.boxes_xyxy])
+    assert torch.equal(outs[0], out1) and torch.equal(outs[1], out1)
