@@ -65,6 +65,10 @@ int mtb_conv_plan_run(mtb_conv_plan* plan, void* stream);
 /* optional per-output-channel factor applied to (acc + bias) before activation / residual: out = act((acc+b)*s) + res.
  * `scale` ([Cout] floats, device) is read at run time, so a kernel earlier in the stream may produce it. */
 int mtb_conv_plan_set_channel_scale(mtb_conv_plan* plan, const float* scale);
+/* optional second reduction of the same launch: per-channel sums of the output over image row 0, row Ho-1, column 0
+ * and column Wo-1, as [num_sum_rows][4][Cout] floats (row split as tile_sums).  Only the channel-major halo kernel
+ * with per-CTA sums provides it (returns an error otherwise); consumed by mtb_rcan_gate. */
+int mtb_conv_plan_set_border_sums(mtb_conv_plan* plan, float* border);
 int mtb_conv_plan_num_mtiles(const mtb_conv_plan* plan);
 /* rows of the tile_sums buffer this plan writes ([rows][Cout] fp32): per (CTA, lane quarter) when the launch covers a
  * single image, else per (pixel tile, lane quarter) */
@@ -159,9 +163,9 @@ int mtb_scale_residual(const void* t, const void* x, const float* scale, void* y
  * the second conv's fp32 weights [64][64][3][3] / bias; w1,b1,w2,b2 = conv_du.  By linearity of the zero-padded conv
  * mean(conv2(u)) follows from the total and the four border lines of u, so conv2 can apply the gate in its own
  * epilogue (mtb_conv_plan_set_channel_scale) and RCAB's `x + gate * t` needs no pass of its own. */
-int mtb_rcan_gate(const float* sums, int parts, const void* u, int planes, int H, int W, const float* conv_w,
-                  const float* conv_b, const float* w1, const float* b1, const float* w2, const float* b2, int R,
-                  float* scale_out, void* stream);
+int mtb_rcan_gate(const float* sums, int parts, const float* border_sums /* [parts][4][64] or NULL: read u's lines */,
+                  const void* u, int planes, int H, int W, const float* conv_w, const float* conv_b, const float* w1,
+                  const float* b1, const float* w2, const float* b2, int R, float* scale_out, void* stream);
 int mtb_f32_to_u8(const float* in, long long npix, int cpad, const float* add3 /* host */, float mul, uint8_t* out,
                   float* out_f /* optional float copy [npix][3] */, void* stream);
 

@@ -53,6 +53,8 @@ def _declare(l: C.CDLL) -> None:
     l.mtb_conv_plan_num_sum_rows.restype = i32
     l.mtb_conv_plan_set_channel_scale.argtypes = [vp, vp]
     l.mtb_conv_plan_set_channel_scale.restype = i32
+    l.mtb_conv_plan_set_border_sums.argtypes = [vp, vp]
+    l.mtb_conv_plan_set_border_sums.restype = i32
     l.mtb_conv_plan_destroy.argtypes = [vp]
     l.mtb_conv_plan_destroy.restype = None
     if hasattr(l, "mtb_exp_shifted_desc"):

@@ -282,6 +282,14 @@ int mtb_conv_plan_set_channel_scale(mtb_conv_plan* plan, const float* scale) {
   return 0;
 }
 
+int mtb_conv_plan_set_border_sums(mtb_conv_plan* plan, float* border) {
+  MTB_REQUIRE(plan != nullptr, "mtb_conv_plan_set_border_sums: null plan");
+  MTB_REQUIRE(plan->halo == 2 && plan->p.sums_per_cta && plan->p.tile_sums != nullptr,
+              "conv: border sums need the channel-major halo kernel with per-CTA tile sums (one image, bf16x3)");
+  plan->p.border_sums = border;
+  return 0;
+}
+
 int mtb_conv_plan_num_mtiles(const mtb_conv_plan* plan) {
   return plan ? plan->p.N * plan->p.tiles_y * plan->p.tiles_x : 0;
 }

@@ -47,6 +47,8 @@ struct ConvParams {
                                //   sums_per_cta == 0: [N*tiles_y*tiles_x][4][Cout], one row per (tile, lane quarter)
                                //   sums_per_cta == 1: [gridDim.x][4][Cout], accumulated over the CTA's tiles (N == 1)
   int sums_per_cta;
+  float* border_sums;          // optional (channel-major halo kernel, sums_per_cta): [gridDim.x][4][4][Cout] sums of the
+                               //   output over image row 0, row Ho-1, column 0, column Wo-1 (same row split as tile_sums)
   int in_coff;                 // first input channel inside the (wider) input tensor
   int out_cstride, out_coff;   // channel count of the output tensor and first channel written (concat slices)
   int res_cstride, res_coff;   // same for the residual tensor

@@ -229,6 +229,8 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const bool want_sums = p.tile_sums != nullptr;
     const long long row2 = 2ll * p.Wo * 64;          // elements between the tile rows of consecutive chunks
     float sum0 = 0.0f, sum1 = 0.0f;
+    const bool want_border = want_sums && p.sums_per_cta && p.border_sums != nullptr;
+    float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // (top, bottom, left, right) x 2 channels
     int as = 0;
     uint32_t aphase = 0;
     long long dbg_wtfull = 0, dbg_work = 0;
@@ -305,8 +307,10 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           x0[j] = odd ? recv : mine;
           x1[j] = odd ? mine : recv;
         }
-        const int nv = (oy0 + 2 * ci < p.Ho) ? nvalid : 0;
+        const int oy = oy0 + 2 * ci;
+        const int nv = (oy < p.Ho) ? nvalid : 0;
         uint16_t* op = p.out + off0 + ci * row2;
+        float c0 = 0.f, c1 = 0.f;                    // this chunk's contribution to the channel sums
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float a = epi_act<ACT>((x0[j] + b0) * s0, p.act);
@@ -317,14 +321,35 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             b += r0.y + r1.y;
           }
           if (j < nv) {
-            if (want_sums) {
-              t0 += a;
-              t1 += b;
+            c0 += a;
+            c1 += b;
+            if (want_border) {
+              const int ox = ox0 + j;
+              if (ox == 0) {
+                bsum[4] += a;
+                bsum[5] += b;
+              }
+              if (ox == p.Wo - 1) {
+                bsum[6] += a;
+                bsum[7] += b;
+              }
             }
             const uint32_t hi = pack_bf16x2(a, b);
             const float2 h = unpack_bf16x2(hi);
             *reinterpret_cast<uint32_t*>(op + j * 64) = hi;
             *reinterpret_cast<uint32_t*>(op + p.out_plane_stride + j * 64) = pack_bf16x2(a - h.x, b - h.y);
+          }
+        }
+        t0 += c0;
+        t1 += c1;
+        if (want_border) {
+          if (oy == 0) {
+            bsum[0] += c0;
+            bsum[1] += c1;
+          }
+          if (oy == p.Ho - 1) {
+            bsum[2] += c0;
+            bsum[3] += c1;
           }
         }
         if (HAS_RES) {
@@ -361,6 +386,21 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     if ((p.debug & 32) && p.dbg_out && lane == 0 && (warp == 2 || warp == 17)) {
       p.dbg_out[blockIdx.x * 16 + (warp == 2 ? 8 : 10)] = dbg_wtfull;
       p.dbg_out[blockIdx.x * 16 + (warp == 2 ? 9 : 11)] = dbg_work;
+    }
+    if (want_border) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], 1);
+        bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], 16);
+      }
+      if (!upper && !odd) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float* row = p.border_sums + ((static_cast<long long>(blockIdx.x) * 4 + wj) * 4 + k) * 64 + cpair;
+          row[0] = bsum[2 * k];
+          row[1] = bsum[2 * k + 1];
+        }
+      }
     }
     if (want_sums && p.sums_per_cta) {
       sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);

@@ -110,7 +110,8 @@ __global__ void ca_scale_kernel(const float* __restrict__ sums, int parts, int C
 // squeeze/excite MLP.  conv2's epilogue can then write x + gate*(conv2(u)+b2) directly and the separate
 // read-scale-add pass over the page (1.2 GB per block) disappears.   One block of 1024 threads, C = 64.
 __global__ void __launch_bounds__(1024, 1)
-rcan_gate_kernel(const float* __restrict__ sums, int parts, const uint16_t* __restrict__ u, long long plane_stride,
+rcan_gate_kernel(const float* __restrict__ sums, int parts, const float* __restrict__ border,
+                 const uint16_t* __restrict__ u, long long plane_stride,
                  int planes, int H, int W, const float* __restrict__ wconv /* [64][64][3][3] */,
                  const float* __restrict__ bconv, const float* __restrict__ w1, const float* __restrict__ b1,
                  const float* __restrict__ w2, const float* __restrict__ b2, int R, float* __restrict__ scale) {
@@ -125,44 +126,48 @@ rcan_gate_kernel(const float* __restrict__ sums, int parts, const uint16_t* __re
 #pragma unroll
   for (int i = 0; i < 36; ++i) wreg[i] = __ldg(wconv + co * 576 + part + 16 * i);
 
-  // border lines of u, one per group of 8 warps: 0 = row 0, 1 = row H-1, 2 = column 0, 3 = column W-1.
-  // 8 lanes cover the 64 channels of a pixel (16-byte loads), a warp takes 4 pixels per step.
-  {
-    const int b = warp >> 3, v = lane & 7, slot = ((warp & 7) << 2) | (lane >> 3);   // 32 pixel slots per line
-    const int len = b < 2 ? W : H;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const long long base = b == 1 ? static_cast<long long>(H - 1) * W : b == 3 ? W - 1 : 0;
-    const long long step = b < 2 ? 1 : W;           // pixels between consecutive elements of the line
-    const uint4 zero4 = make_uint4(0, 0, 0, 0);
-#pragma unroll 4
-    for (int i = slot; i < len; i += 32) {
-      const uint16_t* px = u + (base + i * step) * C + v * 8;
-      const uint4 qh = *reinterpret_cast<const uint4*>(px);
-      const uint4 ql = planes == 2 ? *reinterpret_cast<const uint4*>(px + plane_stride) : zero4;
-      const uint32_t wh[4] = {qh.x, qh.y, qh.z, qh.w}, wl[4] = {ql.x, ql.y, ql.z, ql.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[2 * j] += bf16_to_f(wh[j] & 0xFFFF) + bf16_to_f(wl[j] & 0xFFFF);
-        acc[2 * j + 1] += bf16_to_f(wh[j] >> 16) + bf16_to_f(wl[j] >> 16);
+  if (border == nullptr) {
+    // border lines of u, one per group of 8 warps: 0 = row 0, 1 = row H-1, 2 = column 0, 3 = column W-1.
+    // 8 lanes cover the 64 channels of a pixel (16-byte loads), a warp takes 4 pixels per step.
+    {
+      const int b = warp >> 3, v = lane & 7, slot = ((warp & 7) << 2) | (lane >> 3);   // 32 pixel slots per line
+      const int len = b < 2 ? W : H;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const long long base = b == 1 ? static_cast<long long>(H - 1) * W : b == 3 ? W - 1 : 0;
+      const long long step = b < 2 ? 1 : W;           // pixels between consecutive elements of the line
+      const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  #pragma unroll 4
+      for (int i = slot; i < len; i += 32) {
+        const uint16_t* px = u + (base + i * step) * C + v * 8;
+        const uint4 qh = *reinterpret_cast<const uint4*>(px);
+        const uint4 ql = planes == 2 ? *reinterpret_cast<const uint4*>(px + plane_stride) : zero4;
+        const uint32_t wh[4] = {qh.x, qh.y, qh.z, qh.w}, wl[4] = {ql.x, ql.y, ql.z, ql.w};
+  #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += bf16_to_f(wh[j] & 0xFFFF) + bf16_to_f(wl[j] & 0xFFFF);
+          acc[2 * j + 1] += bf16_to_f(wh[j] >> 16) + bf16_to_f(wl[j] >> 16);
+        }
       }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
-      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
-    }
-    if (lane < 8) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) red[warp][v * 8 + j] = acc[j];
+  #pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+      }
+      if (lane < 8) {
+  #pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp][v * 8 + j] = acc[j];
+      }
     }
   }
   __syncthreads();
   if (tid < 4 * C) {
     const int b = tid >> 6, c = tid & 63;
     float t = 0.f;
+    if (border == nullptr) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[b * 8 + k][c];
-    line[b][c] = t;
+      for (int k = 0; k < 8; ++k) t += red[b * 8 + k][c];
+      line[b][c] = t;
+    }
     // corners: 0 = (0,0), 1 = (0,W-1), 2 = (H-1,0), 3 = (H-1,W-1)
     const long long pix = (b & 2 ? static_cast<long long>(H - 1) * W : 0) + (b & 1 ? W - 1 : 0);
     float cv = 0.f;
@@ -184,6 +189,19 @@ rcan_gate_kernel(const float* __restrict__ sums, int parts, const uint16_t* __re
     tot[tid] = t;
   }
   __syncthreads();
+  if (border != nullptr) {
+    // the four border lines arrive as partial rows from the same conv epilogue: 4 lines x 64 channels x 4 row groups
+    const int c = tid & 63, b = (tid >> 6) & 3, g = tid >> 8;
+    float acc = 0.f;
+    for (int p = g; p < parts; p += 4) acc += border[(static_cast<long long>(p) * 4 + b) * C + c];
+    red[g * 4 + b][c] = acc;
+    __syncthreads();
+    if (tid < 4 * C) {
+      const int b2 = tid >> 6, c2 = tid & 63;
+      line[b2][c2] = red[b2][c2] + red[4 + b2][c2] + red[8 + b2][c2] + red[12 + b2][c2];
+    }
+    __syncthreads();
+  }
   if (tid < 9 * C) {
     const int tap = tid >> 6, c = tid & 63;
     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -312,14 +330,14 @@ int mtb_ca_scale(const float* sums, int n_images, int parts_per_image, int C, fl
   return 0;
 }
 
-int mtb_rcan_gate(const float* sums, int parts, const void* u, int planes, int H, int W, const float* conv_w,
-                  const float* conv_b, const float* w1, const float* b1, const float* w2, const float* b2, int R,
-                  float* scale_out, void* stream) {
+int mtb_rcan_gate(const float* sums, int parts, const float* border_sums, const void* u, int planes, int H, int W,
+                  const float* conv_w, const float* conv_b, const float* w1, const float* b1, const float* w2,
+                  const float* b2, int R, float* scale_out, void* stream) {
   MTB_REQUIRE(sums && u && conv_w && w1 && w2 && scale_out, "mtb_rcan_gate: null argument");
   MTB_REQUIRE((planes == 1 || planes == 2) && H > 0 && W > 0 && R > 0 && R <= 64 && parts > 0,
               "mtb_rcan_gate: bad arguments");
   rcan_gate_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
-      sums, parts, static_cast<const uint16_t*>(u), static_cast<long long>(H) * W * 64, planes, H, W, conv_w, conv_b, w1,
+      sums, parts, border_sums, static_cast<const uint16_t*>(u), static_cast<long long>(H) * W * 64, planes, H, W, conv_w, conv_b, w1,
       b1, w2, b2, R, scale_out);
   MTB_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1);

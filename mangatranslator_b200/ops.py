@@ -67,6 +67,14 @@ class ConvPlan:
         """Rows of the tile_sums buffer ([rows][Cout] fp32) this plan writes."""
         return lib().mtb_conv_plan_num_sum_rows(self._h)
 
+    def set_border_sums(self, border) -> bool:
+        """Ask the layer to also emit per-channel sums of its output over the four image border lines
+        ([num_sum_rows][4][Cout] fp32).  Returns False when the kernel that runs this layer cannot provide them."""
+        rc = lib().mtb_conv_plan_set_border_sums(self._h, ptr(border))
+        if rc == 0:
+            self._keep = self._keep + (border,)
+        return rc == 0
+
     def run(self) -> None:
         check(lib().mtb_conv_plan_run(self._h, stream_ptr()), "mtb_conv_plan_run")
 

@@ -31,7 +31,7 @@ def _declare(l) -> None:
     l.mtb_image_to_planes.argtypes = [vp, i32, i32, i32, i32, f32, C.POINTER(f32), vp, i32, i32, vp]
     l.mtb_ca_scale.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp, vp, i32, vp, vp]
     l.mtb_scale_residual.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, i32, i32, vp]
-    l.mtb_rcan_gate.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    l.mtb_rcan_gate.argtypes = [vp, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     l.mtb_f32_to_u8.argtypes = [vp, C.c_longlong, i32, C.POINTER(f32), f32, vp, vp, vp]
     for n in ("mtb_image_to_planes", "mtb_ca_scale", "mtb_scale_residual", "mtb_f32_to_u8", "mtb_rcan_gate"):
         getattr(l, n).restype = i32
@@ -119,13 +119,20 @@ class RcanB200:
         parts = probe.num_sum_rows
         sums = torch.zeros((parts, f), dtype=torch.float32, device=dev)
         b["sums"] = sums
+        # border-line sums of conv1's output come out of the same epilogue when the channel-major kernel runs the
+        # layer (bf16x3); otherwise the gate kernel reads the four lines of u itself
+        border = torch.zeros((parts, 4, f), dtype=torch.float32, device=dev)
+        b["border"] = None
         src = b["head"]
         for gi, (grp, tailw) in enumerate(self.blocks):
             grp_in = src
             x = grp_in
             for (w1, w2, cd1, cb1, cd2, cb2, w2f, b2f) in grp:
                 dst = b["pa"] if x is not b["pa"] else b["pb"]
-                steps.append(("conv_body", conv(x, w1, b["u"], act="relu", tile_sums=sums)))
+                c1 = conv(x, w1, b["u"], act="relu", tile_sums=sums)
+                if c1.set_border_sums(border):
+                    b["border"] = border
+                steps.append(("conv_body", c1))
                 steps.append(("gate", (parts, w2f, b2f, cd1, cb1, cd2, cb2)))
                 steps.append(("conv_body", conv(b["u"], w2, dst, residual=x, channel_scale=b["scale"])))
                 x = dst
@@ -157,7 +164,7 @@ class RcanB200:
 
     def _gate(self, b: dict, arg, h: int, w: int, st) -> None:
         parts, w2f, b2f, cd1, cb1, cd2, cb2 = arg
-        check(self.l.mtb_rcan_gate(ptr(b["sums"]), parts, ptr(b["u"]), self.planes, h, w, ptr(w2f), ptr(b2f), ptr(cd1),
+        check(self.l.mtb_rcan_gate(ptr(b["sums"]), parts, ptr(b["border"]), ptr(b["u"]), self.planes, h, w, ptr(w2f), ptr(b2f), ptr(cd1),
                                    ptr(cb1), ptr(cd2), ptr(cb2), cd1.shape[0], ptr(b["scale"]), st), "mtb_rcan_gate")
 
     def time_steps(self, img: torch.Tensor):

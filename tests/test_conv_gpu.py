@@ -73,3 +73,32 @@ def test_pixel_major_halo_kernel_still_matches():
                           padding=1))
     for got in outs:
         assert (got - ref).abs().max().item() < 2e-4
+
+
+def test_border_line_sums_from_the_conv_epilogue():
+    """The channel-major halo kernel can emit per-channel sums of its output over row 0, row H-1, column 0, column W-1
+    next to the totals (the RCAB gate needs them); other kernels must refuse."""
+    from mangatranslator_b200 import planes as P
+    from mangatranslator_b200.ops import ConvPlan
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    h, w = 67, 41
+    x = torch.randn(1, 64, h, w, device=dev)
+    wt = torch.randn(64, 64, 3, 3, device=dev) / 24
+    xp, wp = P.nchw_to_planes(x, 2), P.conv_weight_to_planes(wt, 2)
+    o = torch.zeros(2, 1, h, w, 64, dtype=torch.bfloat16, device=dev)
+    probe = ConvPlan(xp, wp, None, o, k=3, pad=1, act="relu")
+    rows = probe.num_sum_rows
+    sums = torch.zeros(rows, 64, device=dev)
+    border = torch.zeros(rows, 4, 64, device=dev)
+    plan = ConvPlan(xp, wp, None, o, k=3, pad=1, act="relu", tile_sums=sums)
+    assert plan.set_border_sums(border)
+    plan.run()
+    torch.cuda.synchronize()
+    y = P.planes_to_nchw(o, 64).double()[0]
+    ref = torch.stack([y[:, 0, :].sum(1), y[:, h - 1, :].sum(1), y[:, :, 0].sum(1), y[:, :, w - 1].sum(1)])
+    got = border.sum(0).double()
+    assert (got - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+    assert (sums.sum(0).double() - y.sum((1, 2))).abs().max().item() < 1e-3 * max(1.0, y.sum((1, 2)).abs().max().item())
+    per_tap = ConvPlan(xp, wp, None, o, k=3, pad=1, act="relu", tile_sums=torch.zeros(probe.num_mtiles * 4, 64, device=dev), mode=1)
+    assert not per_tap.set_border_sums(border)

@@ -46,13 +46,17 @@ def test_detector_output_satisfies_nms_invariants(pipe):
     rows = det[:n].cpu().numpy()
     assert 0 <= n <= 300
     if n:
-        assert np.all(rows[:, 4] > conf)
-        assert np.all(np.diff(rows[:, 4]) <= 0)             # confidence-descending
-        assert rows[:, 0].min() >= 0 and rows[:, 1].min() >= 0 and rows[:, 2].max() <= W and rows[:, 3].max() <= H
+        assert np.all(rows[:, 4] > conf), rows[:, 4].min()
+        assert np.all(np.diff(rows[:, 4]) <= 0), "not confidence-descending"
+        assert rows[:, 0].min() >= 0 and rows[:, 1].min() >= 0 and rows[:, 2].max() <= W and rows[:, 3].max() <= H, \
+            (rows[:, :4].min(0), rows[:, :4].max(0))
+        # suppression ran on the unclipped letterbox-space boxes; clipping to the image can change an IoU, so the pairwise
+        # check is made on boxes that lie strictly inside the page
+        inside = (rows[:, 0] > 0) & (rows[:, 1] > 0) & (rows[:, 2] < W) & (rows[:, 3] < H)
         for i in range(n):
             for j in range(i):
-                if int(rows[i, 5]) == int(rows[j, 5]):
-                    assert _iou(rows[i, :4], rows[j, :4]) <= 0.7 + 1e-4
+                if inside[i] and inside[j] and int(rows[i, 5]) == int(rows[j, 5]):
+                    assert _iou(rows[i, :4], rows[j, :4]) <= 0.7 + 1e-3, (i, j, rows[i], rows[j])
 
 
 def test_page_properties_and_determinism(pipe):

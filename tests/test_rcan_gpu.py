@@ -83,9 +83,18 @@ def test_gate_from_input_sums_equals_gate_of_conv_output(hw):
     rows = torch.rand(parts, 64, device=dev)
     rows = rows / rows.sum(0, keepdim=True) * tot
     scale = torch.zeros(64, device=dev)
-    check(l.mtb_rcan_gate(ptr(rows.contiguous()), parts, ptr(up), 2, h, w, ptr(wc), ptr(bc), ptr(w1), ptr(b1), ptr(w2),
-                          ptr(b2), 4, ptr(scale), stream_ptr()), "mtb_rcan_gate")
+    check(l.mtb_rcan_gate(ptr(rows.contiguous()), parts, None, ptr(up), 2, h, w, ptr(wc), ptr(bc), ptr(w1), ptr(b1),
+                          ptr(w2), ptr(b2), 4, ptr(scale), stream_ptr()), "mtb_rcan_gate")
     torch.cuda.synchronize()
+    # same gate when the four border lines arrive as partial rows (what the conv epilogue emits) instead of being read
+    lines = torch.stack([uq[0, :, 0, :].sum(1), uq[0, :, h - 1, :].sum(1), uq[0, :, :, 0].sum(1), uq[0, :, :, w - 1].sum(1)]).float()
+    split = torch.rand(parts, 4, 64, device=dev)
+    split = (split / split.sum(0, keepdim=True) * lines).contiguous()
+    scale2 = torch.zeros(64, device=dev)
+    check(l.mtb_rcan_gate(ptr(rows.contiguous()), parts, ptr(split), ptr(up), 2, h, w, ptr(wc), ptr(bc), ptr(w1), ptr(b1),
+                          ptr(w2), ptr(b2), 4, ptr(scale2), stream_ptr()), "mtb_rcan_gate")
+    torch.cuda.synchronize()
+    assert (scale2 - scale).abs().max().item() < 2e-5
     mean = (F.conv2d(uq, wc.double(), bc.double(), padding=1)).mean((0, 2, 3))
     ref = torch.sigmoid(w2.double() @ torch.relu(w1.double() @ mean + b1.double()) + b2.double())
     assert (scale.double() - ref).abs().max().item() < 2e-5
