@@ -71,7 +71,8 @@ namespace mtb {
 bool conv_halo_eligible(const ConvParams& p, int cin);
 void conv_halo_cm_tile(int* tw, int* th);
 bool conv_halo_cm_eligible(const ConvParams& p);
-int launch_conv_halo_cm(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvParams& p, cudaStream_t stream);
+int launch_conv_halo_cm(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmO, const ConvParams& p,
+                        cudaStream_t stream);
 int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int nsplit,
                      cudaStream_t stream);
 }  // namespace mtb
@@ -79,6 +80,7 @@ int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvP
 struct mtb_conv_plan {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmO;   // channel-major halo kernel with staged stores: the output planes, box = 64 ch x 8 px x 2 rows
   ConvParams p;
   int nsplit;
   int halo;
@@ -249,6 +251,18 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
       return -3;
     }
   }
+  memset(&pl->tmO, 0, sizeof(pl->tmO));
+  if (pl->halo == 2) {
+    // output planes [2*N][Ho][Wo][64] for the staged TMA store
+    const uint64_t dims[4] = {64, static_cast<uint64_t>(p.Wo), static_cast<uint64_t>(p.Ho), static_cast<uint64_t>(p.N) * 2};
+    const uint64_t strides[3] = {128, static_cast<uint64_t>(p.Wo) * 128, static_cast<uint64_t>(p.Ho) * p.Wo * 128};
+    const uint32_t box[4] = {64, 8, 2, 1};
+    if (encode_tmap(&pl->tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, nullptr,
+                    CU_TENSOR_MAP_SWIZZLE_128B) != 0) {
+      delete pl;
+      return -3;
+    }
+  }
   // weights: [planes*taps*Cout][Cin] bf16
   {
     const uint64_t rows = static_cast<uint64_t>(d->planes_in) * d->KH * d->KW * d->Cout;
@@ -268,7 +282,7 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
 int mtb_conv_plan_run(mtb_conv_plan* plan, void* stream) {
   MTB_REQUIRE(plan != nullptr, "mtb_conv_plan_run: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = plan->halo == 2   ? launch_conv_halo_cm(plan->tmA, plan->tmB, plan->p, st)
+  int rc = plan->halo == 2   ? launch_conv_halo_cm(plan->tmA, plan->tmB, plan->tmO, plan->p, st)
            : plan->halo == 1 ? launch_conv_halo(plan->tmA, plan->tmB, plan->p, plan->nsplit, st)
                              : launch_conv_gemm(plan->tmA, plan->tmB, plan->p, plan->nsplit, st);
   if (rc == 0) mtb::g_launches.fetch_add(1);

@@ -35,26 +35,35 @@ namespace mtb {
 namespace {
 
 constexpr int kThreads = kConvThreads;
-constexpr int kTW = 8, kTH = 30;                    // output tile (pixels)
-constexpr int kNPix = kTW * kTH;                    // 240 = N of the MMA
-constexpr int kHW = kTW + 2, kHH = kTH + 2;         // halo tile 10 x 32
-constexpr int kSlotBytes = kHW * kHH * 128;         // 40960 (a multiple of 1024)
+constexpr int kTW = 8;                              // output tile width (pixels); the height is a template parameter:
+                                                    //   30 rows (N = 240) with direct 4-byte global stores (default), or
+                                                    //   22 rows (N = 176), which frees 16 KB of shared memory to stage the
+                                                    //   output and write it with TMA (experiment, see conv_halo_cm_tile)
+constexpr int kHW = kTW + 2;                        // halo tile width
 constexpr int kSlots = 2;
+constexpr int kStageBytes = 4096;                   // per epilogue group: [hi|lo][16 pixels][128 B], 128B-swizzled
 constexpr int kTapBytes = 128 * 128;                // 128 interleaved weight rows x 128 B
 constexpr int kWBytes = 9 * kTapBytes;              // 147456
 constexpr int kAccCols = 256;                       // TMEM columns per accumulator stage
-constexpr int kChunks = kNPix / 16;                 // 15 column chunks of 16 pixels (= 2 tile rows)
 
-// ACT: activation (-1 = from ConvParams); HAS_RES: a two-plane residual is added after the activation
-template <int ACT, bool HAS_RES>
+// ACT: activation (-1 = from ConvParams); HAS_RES: a two-plane residual is added after the activation;
+// TH: tile height (30: direct stores, 22: staged TMA stores)
+template <int ACT, bool HAS_RES, int TH>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                      const ConvParams p) {
+                      const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
+  constexpr int kTH = TH;
+  constexpr bool kStaged = (TH == 22);
+  constexpr int kNPix = kTW * kTH;                  // N of the MMA
+  constexpr int kHH = kTH + 2;
+  constexpr int kSlotBytes = kHW * kHH * 128;       // a multiple of 1024 for both tile heights
+  constexpr int kChunks = kNPix / 16;               // column chunks of 16 pixels (= 2 tile rows)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;                         // resident weights (A operand)
   uint8_t* sX = smem + kWBytes;               // ring of halo plane slots (B operand)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sX + kSlots * kSlotBytes);
+  uint8_t* sStage = sX + kSlots * kSlotBytes; // staged output (kStaged only): 4 groups x kStageBytes
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + (kStaged ? 4 * kStageBytes : 0));
   uint64_t* empty_bar = full_bar + kSlots;
   uint64_t* tfull_bar = empty_bar + kSlots;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
@@ -83,6 +92,7 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
+    if (kStaged) tma_prefetch_desc(&tmO);
   }
   tc_fence_before();
   __syncthreads();
@@ -311,6 +321,7 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const int nv = (oy < p.Ho) ? nvalid : 0;
         uint16_t* op = p.out + off0 + ci * row2;
         float c0 = 0.f, c1 = 0.f;                    // this chunk's contribution to the channel sums
+        uint32_t hiw[4], low[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float a = epi_act<ACT>((x0[j] + b0) * s0, p.act);
@@ -334,10 +345,43 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 bsum[7] += b;
               }
             }
+          }
+          {
             const uint32_t hi = pack_bf16x2(a, b);
             const float2 h = unpack_bf16x2(hi);
-            *reinterpret_cast<uint32_t*>(op + j * 64) = hi;
-            *reinterpret_cast<uint32_t*>(op + p.out_plane_stride + j * 64) = pack_bf16x2(a - h.x, b - h.y);
+            hiw[j] = hi;
+            low[j] = pack_bf16x2(a - h.x, b - h.y);
+          }
+          if (!kStaged && j < nv) {
+            *reinterpret_cast<uint32_t*>(op + j * 64) = hiw[j];
+            *reinterpret_cast<uint32_t*>(op + p.out_plane_stride + j * 64) = low[j];
+          }
+        }
+        if (kStaged) {
+          // stage the chunk (16 pixels x 64 channels x hi/lo) in shared memory, 128B-swizzled, and let TMA write full
+          // lines; the four warps of this group (one per TMEM lane quarter) each contribute 32 B of every pixel row
+          uint8_t* stg = sStage + wj * kStageBytes;
+          if (q == 0 && lane == 0) bulk_wait_read0();          // the previous chunk's store has read the buffer
+          named_bar_sync(1 + wj, 128);
+          const int cp = (lane & 15) >> 1;                     // channel pair inside the quarter
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // upper lanes walk their pixels rotated by two so the four pixel rows of one instruction differ in more
+            // than address bit 7: with the XOR swizzle that makes the 32 lanes hit 32 distinct banks
+            const int jj = upper ? (k ^ 2) : k;
+            const uint32_t wh = upper ? hiw[k ^ 2] : hiw[k];
+            const uint32_t wl = upper ? low[k ^ 2] : low[k];
+            const int px = (upper ? 8 : 0) + (odd ? 4 : 0) + jj;
+            const int boff = px * 128 + ((((q << 1) | (cp >> 2)) ^ (px & 7)) << 4) + ((cp & 3) << 2);
+            *reinterpret_cast<uint32_t*>(stg + boff) = wh;
+            *reinterpret_cast<uint32_t*>(stg + 2048 + boff) = wl;
+          }
+          fence_proxy_async();
+          named_bar_sync(1 + wj, 128);
+          if (q == 0 && lane == 0 && !(p.debug & 1)) {
+            tma_store_4d(&tmO, stg, 0, txi * kTW, tyi * kTH + 2 * ci, n);
+            tma_store_4d(&tmO, stg + 2048, 0, txi * kTW, tyi * kTH + 2 * ci, p.N + n);
+            bulk_commit_group();
           }
         }
         t0 += c0;
@@ -383,6 +427,7 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         aphase ^= 1;
       }
     }
+    if (kStaged && q == 0 && lane == 0) bulk_wait_all0();      // all staged stores have landed
     if ((p.debug & 32) && p.dbg_out && lane == 0 && (warp == 2 || warp == 17)) {
       p.dbg_out[blockIdx.x * 16 + (warp == 2 ? 8 : 10)] = dbg_wtfull;
       p.dbg_out[blockIdx.x * 16 + (warp == 2 ? 9 : 11)] = dbg_work;
@@ -429,27 +474,32 @@ bool conv_halo_cm_eligible(const ConvParams& p) {
   return p.planes_out == 2 && p.out_f32 == nullptr && (p.residual == nullptr || p.res_planes == 2) && !p.act_after_res;
 }
 
+// tile geometry of the two variants: direct stores (8 x 30, the default) or staged TMA stores (8 x 22,
+// MTB200_CM_STAGED_STORES=1).  Measured on B200 (profiles/r01_cm_staged_stores.json): staging removes the store
+// wavefronts but the smaller tile pays more per-tile pipeline bubbles and two named barriers per chunk — 436K vs 413K
+// cycles per CTA, 162 vs 156 ms per RCAN page — so it stays an experiment.
 void conv_halo_cm_tile(int* tw, int* th) {
+  const char* e = getenv("MTB200_CM_STAGED_STORES");
   *tw = kTW;
-  *th = kTH;
+  *th = (e && atoi(e) != 0) ? 22 : 30;
 }
 
-int launch_conv_halo_cm(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvParams& p_in, cudaStream_t stream) {
-  ConvParams p = p_in;
-  if (const char* e = getenv("MTB200_HALO_DEBUG")) p.debug = atoi(e);
-  if (const char* e = getenv("MTB200_HALO_DEBUG_PTR")) p.dbg_out = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
-  const size_t smem = 1024 + kWBytes + kSlots * kSlotBytes + 16 * 8 + 16;
+template <int TH>
+static int launch_cm_th(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmO, const ConvParams& p,
+                        cudaStream_t stream) {
+  constexpr int slot = kHW * (TH + 2) * 128;
+  const size_t smem = 1024 + kWBytes + kSlots * slot + (TH == 22 ? 4 * kStageBytes : 0) + 16 * 8 + 16;
   int dev = 0, sms = 0;
   MTB_CUDA_OK(cudaGetDevice(&dev));
   MTB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long total = static_cast<long long>(p.N) * p.tiles_y * p.tiles_x;
   const int grid = static_cast<int>(total < sms ? total : sms);
   if (grid <= 0) return 0;
-#define MTB_LAUNCH_CM(ACT, RES)                                                                                    \
-  do {                                                                                                             \
-    MTB_CUDA_OK(cudaFuncSetAttribute(conv3x3_c64_cm_kernel<ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     static_cast<int>(smem)));                                                     \
-    conv3x3_c64_cm_kernel<ACT, RES><<<grid, kThreads, smem, stream>>>(tmX, tmW, p);                                \
+#define MTB_LAUNCH_CM(ACT, RES)                                                                                       \
+  do {                                                                                                                \
+    MTB_CUDA_OK(cudaFuncSetAttribute(conv3x3_c64_cm_kernel<ACT, RES, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     static_cast<int>(smem)));                                                        \
+    conv3x3_c64_cm_kernel<ACT, RES, TH><<<grid, kThreads, smem, stream>>>(tmX, tmW, tmO, p);                          \
   } while (0)
   const bool res = p.residual != nullptr;
   switch (p.act) {
@@ -460,6 +510,14 @@ int launch_conv_halo_cm(const CUtensorMap& tmX, const CUtensorMap& tmW, const Co
 #undef MTB_LAUNCH_CM
   MTB_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int launch_conv_halo_cm(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmO, const ConvParams& p_in,
+                        cudaStream_t stream) {
+  ConvParams p = p_in;
+  if (const char* e = getenv("MTB200_HALO_DEBUG")) p.debug = atoi(e);
+  if (const char* e = getenv("MTB200_HALO_DEBUG_PTR")) p.dbg_out = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+  return p.TH == 22 ? launch_cm_th<22>(tmX, tmW, tmO, p, stream) : launch_cm_th<30>(tmX, tmW, tmO, p, stream);
 }
 
 }  // namespace mtb
