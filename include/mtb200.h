@@ -168,6 +168,14 @@ int mtb_rcan_gate(const float* sums, int parts, const float* border_sums /* [par
                   const float* b1, const float* w2, const float* b2, int R, float* scale_out, void* stream);
 int mtb_f32_to_u8(const float* in, long long npix, int cpad, const float* add3 /* host */, float mul, uint8_t* out,
                   float* out_f /* optional float copy [npix][3] */, void* stream);
+/* "_PU" RCAN variants (ModelManager.load_upscale_lite, core/ml/model_manager.py:660-700 -> spandrel RCAN with
+ * unshuffle_mod): PixelUnshuffle(d) of the reflect-padded page folded into the u8 -> planes conversion
+ * (planes_out: bf16 [planes][ceil(H/d)][ceil(W/d)][cpad], channel c*d*d + dy*d + dx), and the crop back to the
+ * un-padded frame folded into the float -> u8 conversion. */
+int mtb_image_to_planes_unshuffle(const uint8_t* img, int H, int W, int cimg, int swap_rb, float mul,
+                                  const float* sub3 /* host */, int d, void* planes_out, int cpad, int planes, void* stream);
+int mtb_f32_to_u8_crop(const float* in, int Hin, int Win, int cpad, int Hout, int Wout, const float* add3 /* host */,
+                       float mul, uint8_t* out, float* out_f, void* stream);
 
 /* ---- detection glue ---------------------------------------------------------------------------------------
  * maxpool / upsample2x : SPPF and FPN ops of the YOLO graph on channel slices of NHWC plane tensors
@@ -225,6 +233,16 @@ int mtb_aa_weights_host(int in_size, int out_size, int* start, int* len, short* 
                         int* prec);
 int mtb_resize_aa_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp /* sh x ow x 3 */,
                      uint8_t* dst /* oh x ow x 3 */, int oh, int ow, int* tables_dev, long long tables_ints, void* stream);
+/* resize_lanczos_u8 : PIL `Image.resize((ow, oh), Image.LANCZOS)` on uint8 RGB — the exact-size resample after the RCAN
+ * passes (core/image/image_utils.py:545) and resize_to_min_side / resize_to_max_side (:551-595) behind
+ * process_bubble_image_cached (:678-746).  Pillow's separable resampler: double-precision windowed-sinc coefficients
+ * rounded to 22 bits, uint8 intermediate after the horizontal pass.  `tables_dev`: caller-owned scratch of
+ * mtb_resize_lanczos_table_ints(...) ints; `tmp`: sh x ow x 3 (may be NULL when only one axis changes). */
+long long mtb_resize_lanczos_table_ints(int sh, int sw, int oh, int ow);
+int mtb_resize_lanczos_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp, uint8_t* dst /* oh x ow x 3 */,
+                          int oh, int ow, int* tables_dev, long long tables_ints, void* stream);
+/* host-only: Pillow's 22-bit LANCZOS coefficient table of one axis (what resize_lanczos_u8 uploads); CPU tests */
+int mtb_lanczos_weights_host(int in_size, int out_size, int* start, int* len, int* weights, int ksize_cap, int* ksize);
 
 /* ---- SAM 2.1 glue (transformers Sam2Model behind core/image/detection.py:475-511) -------------------------------- */
 int mtb_layernorm(const void* x, long long rows, int C, int ct_in, int ci, int planes_in, const float* gamma,

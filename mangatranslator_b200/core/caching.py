@@ -53,10 +53,16 @@ class UnifiedCache:
     def get_upscale_cache_key(self, image, factor, model_type, *extra):
         return ("upscale", id(image), float(factor), str(model_type)) + tuple(extra)
 
+    def get_upscale_dimension_cache_key(self, image, target, mode, model_type="model"):
+        return ("upscale_dim", id(image), int(target), str(mode), str(model_type))
+
+    def get_bubble_processing_cache_key(self, image, target, mode, model_type="model"):
+        return ("bubble_proc", id(image), int(target), str(mode), str(model_type))
+
     def get_upscaled_image(self, key):
         return self._get(key)
 
-    def set_upscaled_image(self, key, value) -> None:
+    def set_upscaled_image(self, key, value, verbose: bool = False) -> None:
         self._set(key, value)
 
     def clear(self) -> None:

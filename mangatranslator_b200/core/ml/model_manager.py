@@ -146,8 +146,9 @@ class ModelManager:
             sd = self._load_file_state_dict(self.model_paths[mt])
             if sd is None:
                 log_message("Upscaler: no checkpoint on disk, using seeded synthetic RCAN weights", verbose=verbose)
-                sd = W.rcan_state_dict(self.synthetic_seed, n_resblocks=20 if mt == ModelType.UPSCALE else 6,
-                                       n_resgroups=10 if mt == ModelType.UPSCALE else 4)
+                lite = mt == ModelType.UPSCALE_LITE        # "_PU": pixel-unshuffle x2 in front of a shallower body
+                sd = W.rcan_state_dict(self.synthetic_seed, n_resblocks=6 if lite else 20, n_resgroups=4 if lite else 10,
+                                       unshuffle=2 if lite else 1)
             self.models[mt] = RcanB200(sd, dev, precision=self.precision)
             return self.models[mt]
 

@@ -63,6 +63,50 @@ __global__ void image_to_planes_kernel(const uint8_t* __restrict__ img, int H, i
   }
 }
 
+// PixelUnshuffle(d) folded into the same conversion (RCAN "_PU" variants): out[yb][xb][c*d*d + dy*d + dx] =
+// img[yb*d+dy][xb*d+dx][c]; rows/columns past the image edge (H or W not a multiple of d) are reflect-padded
+__global__ void image_to_planes_unshuffle_kernel(const uint8_t* __restrict__ img, int H, int W, int cimg, int swap_rb,
+                                                 float mul, float s0, float s1, float s2, int d,
+                                                 uint16_t* __restrict__ out, long long plane_stride, int cpad, int planes) {
+  const int Hb = (H + d - 1) / d, Wb = (W + d - 1) / d, dd = d * d;
+  const int vec_per_pix = cpad / 8;
+  const long long total = static_cast<long long>(Hb) * Wb * vec_per_pix;
+  const float sub[3] = {s0, s1, s2};
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i / vec_per_pix;
+    const int v = static_cast<int>(i - pix * vec_per_pix);
+    const int yb = static_cast<int>(pix / Wb), xb = static_cast<int>(pix - static_cast<long long>(yb) * Wb);
+    uint16_t h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = v * 8 + e;
+      h[e] = l[e] = 0;
+      if (ch < 3 * dd) {
+        const int c = ch / dd, r = ch - c * dd;
+        int y = yb * d + r / d, x = xb * d + r % d;
+        if (y >= H) y = 2 * (H - 1) - y;
+        if (x >= W) x = 2 * (W - 1) - x;
+        y = y < 0 ? 0 : y;
+        x = x < 0 ? 0 : x;
+        const float val = img[(static_cast<long long>(y) * W + x) * cimg + (swap_rb ? 2 - c : c)] * mul - sub[c];
+        split_bf16(val, h[e], l[e]);
+      }
+    }
+    uint4 hi, lo;
+    hi.x = h[0] | (static_cast<uint32_t>(h[1]) << 16);
+    hi.y = h[2] | (static_cast<uint32_t>(h[3]) << 16);
+    hi.z = h[4] | (static_cast<uint32_t>(h[5]) << 16);
+    hi.w = h[6] | (static_cast<uint32_t>(h[7]) << 16);
+    lo.x = l[0] | (static_cast<uint32_t>(l[1]) << 16);
+    lo.y = l[2] | (static_cast<uint32_t>(l[3]) << 16);
+    lo.z = l[4] | (static_cast<uint32_t>(l[5]) << 16);
+    lo.w = l[6] | (static_cast<uint32_t>(l[7]) << 16);
+    reinterpret_cast<uint4*>(out + pix * cpad)[v] = hi;
+    if (planes == 2) reinterpret_cast<uint4*>(out + plane_stride + pix * cpad)[v] = lo;
+  }
+}
+
 // finish the global average pool from the conv epilogue's per-warp partial sums and run the squeeze/excite MLP
 // one block per image; C <= 256, R <= 64
 __global__ void ca_scale_kernel(const float* __restrict__ sums, int parts, int C, float inv_hw,
@@ -298,6 +342,26 @@ __global__ void f32_to_u8_kernel(const float* __restrict__ in, long long npix, i
   }
 }
 
+// same as f32_to_u8_kernel for the top-left Hout x Wout window of a Hin x Win tensor (the "_PU" models compute on
+// a frame padded to a multiple of the unshuffle factor)
+__global__ void f32_to_u8_crop_kernel(const float* __restrict__ in, int Win, int cpad, int Hout, int Wout, float a0,
+                                      float a1, float a2, float mul, uint8_t* __restrict__ out, float* __restrict__ out_f) {
+  const long long npix = static_cast<long long>(Hout) * Wout;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < npix;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int y = static_cast<int>(i / Wout), x = static_cast<int>(i - static_cast<long long>(y) * Wout);
+    const float* p = in + (static_cast<long long>(y) * Win + x) * cpad;
+    const float add[3] = {a0, a1, a2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = (p[c] + add[c]) * mul;
+      if (out_f) out_f[i * 3 + c] = v;
+      const float q = fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f;
+      out[i * 3 + c] = static_cast<uint8_t>(q);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -311,6 +375,34 @@ int mtb_image_to_planes(const uint8_t* img, int H, int W, int cimg, int swap_rb,
   image_to_planes_kernel<<<grid_for(total, 256, sm_count()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       img, H, W, cimg, swap_rb, mul, s0, s1, s2, static_cast<uint16_t*>(planes_out),
       static_cast<long long>(H) * W * cpad, cpad, planes);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_image_to_planes_unshuffle(const uint8_t* img, int H, int W, int cimg, int swap_rb, float mul, const float* sub3,
+                                  int d, void* planes_out, int cpad, int planes, void* stream) {
+  MTB_REQUIRE(img && planes_out && (cimg == 3 || cimg == 4) && cpad % 8 == 0 && (planes == 1 || planes == 2) && d >= 1 &&
+                  3 * d * d <= cpad && H >= 1 && W >= 1,
+              "mtb_image_to_planes_unshuffle: bad arguments");
+  MTB_REQUIRE((H % d == 0 || H > d) && (W % d == 0 || W > d), "mtb_image_to_planes_unshuffle: image smaller than the reflect pad");
+  const int Hb = (H + d - 1) / d, Wb = (W + d - 1) / d;
+  const long long total = static_cast<long long>(Hb) * Wb * (cpad / 8);
+  const float s0 = sub3 ? sub3[0] : 0.f, s1 = sub3 ? sub3[1] : 0.f, s2 = sub3 ? sub3[2] : 0.f;
+  image_to_planes_unshuffle_kernel<<<grid_for(total, 256, sm_count()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, H, W, cimg, swap_rb, mul, s0, s1, s2, d, static_cast<uint16_t*>(planes_out),
+      static_cast<long long>(Hb) * Wb * cpad, cpad, planes);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_f32_to_u8_crop(const float* in, int Hin, int Win, int cpad, int Hout, int Wout, const float* add3, float mul,
+                       uint8_t* out, float* out_f, void* stream) {
+  MTB_REQUIRE(in && out && cpad >= 3 && Hout >= 1 && Wout >= 1 && Hout <= Hin && Wout <= Win, "mtb_f32_to_u8_crop: bad arguments");
+  const float a0 = add3 ? add3[0] : 0.f, a1 = add3 ? add3[1] : 0.f, a2 = add3 ? add3[2] : 0.f;
+  f32_to_u8_crop_kernel<<<grid_for(static_cast<long long>(Hout) * Wout, 256, sm_count()), 256, 0,
+                          static_cast<cudaStream_t>(stream)>>>(in, Win, cpad, Hout, Wout, a0, a1, a2, mul, out, out_f);
   MTB_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -78,17 +78,19 @@ int cv_round_f(float v) { return static_cast<int>(lrintf(v)); }  // round half t
 short sat_short(int v) { return static_cast<short>(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
 
 // separable antialiased resample of one axis: out[o] = clip8((half + sum_k w[o][k] * in[start[o] + k]) >> prec)
+// WT = short (ATen int16 tables) or int (Pillow's 22-bit tables; 255 * sum|w| stays below 2^31 by construction)
+template <typename WT>
 __global__ void resample_axis_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int out_h, int out_w,
                                      int in_w_stride /* pixels per src row */, int c_in, int c_out, int horizontal,
                                      const int* __restrict__ start, const int* __restrict__ len,
-                                     const short* __restrict__ wts, int kmax, int prec) {
+                                     const WT* __restrict__ wts, int kmax, int prec) {
   const long long total = static_cast<long long>(out_h) * out_w;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int oy = static_cast<int>(i / out_w), ox = static_cast<int>(i - static_cast<long long>(oy) * out_w);
     const int o = horizontal ? ox : oy;
     const int s0 = start[o], n = len[o];
-    const short* w = wts + static_cast<long long>(o) * kmax;
+    const WT* w = wts + static_cast<long long>(o) * kmax;
     int acc[3] = {1 << (prec - 1), 1 << (prec - 1), 1 << (prec - 1)};
     for (int k = 0; k < n; ++k) {
       const uint8_t* px = horizontal ? src + (static_cast<long long>(oy) * in_w_stride + s0 + k) * c_in
@@ -151,6 +153,53 @@ void aa_weights(int in_size, int out_size, std::vector<int>& start, std::vector<
       w16[static_cast<size_t>(i) * ksize + j] =
           static_cast<short>(v < 0 ? static_cast<int>(-0.5 + v * (1 << prec)) : static_cast<int>(0.5 + v * (1 << prec)));
     }
+}
+
+// Pillow `precompute_coeffs` + `normalize_coeffs_8bpc` (libImaging/Resample.c) for the LANCZOS filter (support 3) over
+// the full-image box: double-precision windowed sinc, normalised per output sample, rounded to 22-bit integers.
+double pil_sinc(double x) {
+  if (x == 0.0) return 1.0;
+  x = x * M_PI;
+  return sin(x) / x;
+}
+double pil_lanczos(double x) { return (-3.0 <= x && x < 3.0) ? pil_sinc(x) * pil_sinc(x / 3) : 0.0; }
+
+constexpr int kPilPrecisionBits = 32 - 8 - 2;
+
+void lanczos_weights(int in_size, int out_size, std::vector<int>& start, std::vector<int>& len, std::vector<int>& w32,
+                     int& ksize) {
+  double filterscale, scale;
+  filterscale = scale = static_cast<double>(static_cast<float>(in_size) - 0.0f) / out_size;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = 3.0 * filterscale;
+  ksize = static_cast<int>(ceil(support)) * 2 + 1;
+  start.assign(out_size, 0);
+  len.assign(out_size, 0);
+  w32.assign(static_cast<size_t>(out_size) * ksize, 0);
+  std::vector<double> k(ksize);
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = 0.0 + (xx + 0.5) * scale;
+    double ww = 0.0;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    for (int x = 0; x < xmax; ++x) {
+      const double w = pil_lanczos((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x) {
+      if (ww != 0.0) k[x] /= ww;
+      const double v = k[x];
+      w32[static_cast<size_t>(xx) * ksize + x] =
+          v < 0 ? static_cast<int>(-0.5 + v * (1 << kPilPrecisionBits)) : static_cast<int>(0.5 + v * (1 << kPilPrecisionBits));
+    }
+    start[xx] = xmin;
+    len[xx] = xmax;
+  }
 }
 
 // Coefficient tables depend only on the geometry: build + upload once, keep on the device (no per-call H2D / sync,
@@ -329,7 +378,7 @@ int mtb_resize_aa_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp, u
   const uint8_t* cur = src;
   int cur_w = sw, cur_c = sc;
   if (ow != sw) {
-    resample_axis_kernel<<<grid, 256, 0, st>>>(cur, tmp, sh, ow, sw, sc, 3, 1, d_hs, d_hl, d_hw, hk, hp);
+    resample_axis_kernel<short><<<grid, 256, 0, st>>>(cur, tmp, sh, ow, sw, sc, 3, 1, d_hs, d_hl, d_hw, hk, hp);
     MTB_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     cur = tmp;
@@ -337,10 +386,89 @@ int mtb_resize_aa_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp, u
     cur_c = 3;
   }
   if (oh != sh) {
-    resample_axis_kernel<<<grid, 256, 0, st>>>(cur, dst, oh, ow, cur_w, cur_c, 3, 0, d_vs, d_vl, d_vw, vk, vp);
+    resample_axis_kernel<short><<<grid, 256, 0, st>>>(cur, dst, oh, ow, cur_w, cur_c, 3, 0, d_vs, d_vl, d_vw, vk, vp);
     MTB_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
   } else {
+    copy_pad_kernel<<<grid, 256, 0, st>>>(cur, sh, cur_w, cur_c, dst, oh, ow, 0, 0, 0, 0);
+    MTB_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+  }
+  return 0;
+}
+
+// host-only helper for the CPU tests: Pillow's 22-bit LANCZOS coefficient table of one axis
+int mtb_lanczos_weights_host(int in_size, int out_size, int* start /* [out] */, int* len /* [out] */,
+                             int* weights /* [out][ksize_cap] */, int ksize_cap, int* ksize) {
+  MTB_REQUIRE(in_size > 0 && out_size > 0 && start && len && weights && ksize, "mtb_lanczos_weights_host: bad arguments");
+  std::vector<int> s, l, w;
+  int k = 0;
+  lanczos_weights(in_size, out_size, s, l, w, k);
+  MTB_REQUIRE(k <= ksize_cap, "mtb_lanczos_weights_host: ksize %d > capacity %d", k, ksize_cap);
+  for (int i = 0; i < out_size; ++i) {
+    start[i] = s[i];
+    len[i] = l[i];
+    for (int j = 0; j < k; ++j) weights[static_cast<size_t>(i) * ksize_cap + j] = w[static_cast<size_t>(i) * k + j];
+  }
+  *ksize = k;
+  return 0;
+}
+
+long long mtb_resize_lanczos_table_ints(int sh, int sw, int oh, int ow) {
+  const double fx = sw > ow ? static_cast<double>(sw) / ow : 1.0, fy = sh > oh ? static_cast<double>(sh) / oh : 1.0;
+  const long long kx = static_cast<long long>(ceil(3.0 * fx)) * 2 + 1, ky = static_cast<long long>(ceil(3.0 * fy)) * 2 + 1;
+  return 2LL * ow + 2LL * oh + ow * kx + oh * ky;
+}
+
+// PIL `Image.resize((ow, oh), Image.LANCZOS)` of a uint8 image (first 3 channels): horizontal pass into `tmp`
+// (sh x ow x 3, uint8 like Pillow's intermediate image), then vertical; a pass whose size does not change is skipped
+// as in ImagingResample.  `tables_dev` is caller-owned scratch of mtb_resize_lanczos_table_ints() ints.
+int mtb_resize_lanczos_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp, uint8_t* dst, int oh, int ow,
+                          int* tables_dev, long long tables_ints, void* stream) {
+  MTB_REQUIRE(src && dst && tables_dev && (sc == 3 || sc == 4) && sh > 0 && sw > 0 && oh > 0 && ow > 0,
+              "mtb_resize_lanczos_u8: bad arguments");
+  MTB_REQUIRE(tables_ints >= mtb_resize_lanczos_table_ints(sh, sw, oh, ow), "mtb_resize_lanczos_u8: table scratch too small");
+  MTB_REQUIRE(tmp || ow == sw || oh == sh, "mtb_resize_lanczos_u8: two passes need the intermediate buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<int> hs, hl, hw, vs, vl, vw;
+  int hk = 0, vk = 0;
+  lanczos_weights(sw, ow, hs, hl, hw, hk);
+  lanczos_weights(sh, oh, vs, vl, vw, vk);
+  std::vector<int> all;
+  all.reserve(2 * ow + 2 * oh + hw.size() + vw.size());
+  all.insert(all.end(), hs.begin(), hs.end());
+  all.insert(all.end(), hl.begin(), hl.end());
+  all.insert(all.end(), vs.begin(), vs.end());
+  all.insert(all.end(), vl.begin(), vl.end());
+  all.insert(all.end(), hw.begin(), hw.end());
+  all.insert(all.end(), vw.begin(), vw.end());
+  MTB_REQUIRE(static_cast<long long>(all.size()) <= tables_ints, "mtb_resize_lanczos_u8: table scratch too small");
+  // pageable source: the copy is staged before the call returns, so `all` may go out of scope
+  MTB_CUDA_OK(cudaMemcpyAsync(tables_dev, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  const int* d_hs = tables_dev;
+  const int* d_hl = d_hs + ow;
+  const int* d_vs = d_hl + ow;
+  const int* d_vl = d_vs + oh;
+  const int* d_hw = d_vl + oh;
+  const int* d_vw = d_hw + hw.size();
+  const int grid = sm_count3() * 8;
+  const uint8_t* cur = src;
+  int cur_w = sw, cur_c = sc;
+  const bool need_h = ow != sw, need_v = oh != sh;
+  if (need_h) {
+    uint8_t* out = need_v ? tmp : dst;
+    resample_axis_kernel<int><<<grid, 256, 0, st>>>(cur, out, sh, ow, sw, sc, 3, 1, d_hs, d_hl, d_hw, hk, kPilPrecisionBits);
+    MTB_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    cur = out;
+    cur_w = ow;
+    cur_c = 3;
+  }
+  if (need_v) {
+    resample_axis_kernel<int><<<grid, 256, 0, st>>>(cur, dst, oh, ow, cur_w, cur_c, 3, 0, d_vs, d_vl, d_vw, vk, kPilPrecisionBits);
+    MTB_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+  } else if (!need_h) {
     copy_pad_kernel<<<grid, 256, 0, st>>>(cur, sh, cur_w, cur_c, dst, oh, ow, 0, 0, 0, 0);
     MTB_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);

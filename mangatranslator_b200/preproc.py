@@ -1,4 +1,4 @@
-"""Device pre-processing wrappers (C ABI: mtb_letterbox_u8, mtb_resize_aa_u8)."""
+"""Device pre-/post-processing wrappers (C ABI: mtb_letterbox_u8, mtb_resize_aa_u8, mtb_resize_lanczos_u8)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -16,6 +16,10 @@ def _declare(l) -> None:
     l.mtb_letterbox_u8.restype = i32
     l.mtb_resize_aa_u8.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, C.c_longlong, vp]
     l.mtb_resize_aa_u8.restype = i32
+    l.mtb_resize_lanczos_table_ints.argtypes = [i32] * 4
+    l.mtb_resize_lanczos_table_ints.restype = C.c_longlong
+    l.mtb_resize_lanczos_u8.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, C.c_longlong, vp]
+    l.mtb_resize_lanczos_u8.restype = i32
     l._pre_declared = True
 
 
@@ -55,4 +59,22 @@ def resize_aa_device(img: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
     tables = torch.empty(n_ints, dtype=torch.int32, device=img.device)
     check(l.mtb_resize_aa_u8(ptr(img), h0, w0, c, ptr(tmp), ptr(out), oh, ow, ptr(tables), n_ints, stream_ptr()),
           "mtb_resize_aa_u8")
+    return out
+
+
+def resize_lanczos_device(img: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+    """PIL `Image.resize((ow, oh), Image.LANCZOS)` of a device uint8 HxWx(3|4) image -> uint8 oh x ow x 3, bit-exact with
+    Pillow (reference: core/image/image_utils.py:545,551-595)."""
+    l = lib()
+    _declare(l)
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_contiguous()
+    h0, w0, c = img.shape
+    if (oh, ow) == (h0, w0) and c == 3:
+        return img                                   # PIL returns a copy of the same pixels
+    tmp = torch.empty((h0, ow, 3), dtype=torch.uint8, device=img.device) if (ow != w0 and oh != h0) else None
+    out = torch.empty((oh, ow, 3), dtype=torch.uint8, device=img.device)
+    n_ints = int(l.mtb_resize_lanczos_table_ints(h0, w0, oh, ow))
+    tables = torch.empty(n_ints, dtype=torch.int32, device=img.device)
+    check(l.mtb_resize_lanczos_u8(ptr(img), h0, w0, c, ptr(tmp), ptr(out), oh, ow, ptr(tables), n_ints, stream_ptr()),
+          "mtb_resize_lanczos_u8")
     return out

@@ -11,10 +11,17 @@ RCAB (spandrel RCAN: conv -> ReLU -> conv -> CALayer -> + x) runs as three launc
     g   = gate(mean(conv2(u)))                 mtb_rcan_gate: the mean follows from sums of u (linearity), see the header
     x'  = x + g * conv2(u)                     halo conv with channel scale + residual in the epilogue
 so the block's output is written once and the attention-weighted tensor is never materialised.
+
+The lite model (`load_upscale_lite`, 2x-AnimeSharpV4_Fast_RCAN_PU) is the same network behind a PixelUnshuffle: the
+head sees 3*d*d channels of the page reflect-padded to a multiple of d, the body runs on 1/d^2 of the pixels, the
+upsampler has log2(2d) conv+PixelShuffle(2) stages and the output is cropped to 2H x 2W.  d, the stage count and the
+depth are read from the state dict (keys/shapes), as spandrel's loader does.
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -33,7 +40,10 @@ def _declare(l) -> None:
     l.mtb_scale_residual.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, i32, i32, vp]
     l.mtb_rcan_gate.argtypes = [vp, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     l.mtb_f32_to_u8.argtypes = [vp, C.c_longlong, i32, C.POINTER(f32), f32, vp, vp, vp]
-    for n in ("mtb_image_to_planes", "mtb_ca_scale", "mtb_scale_residual", "mtb_f32_to_u8", "mtb_rcan_gate"):
+    l.mtb_image_to_planes_unshuffle.argtypes = [vp, i32, i32, i32, i32, f32, C.POINTER(f32), i32, vp, i32, i32, vp]
+    l.mtb_f32_to_u8_crop.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(f32), f32, vp, vp, vp]
+    for n in ("mtb_image_to_planes", "mtb_ca_scale", "mtb_scale_residual", "mtb_f32_to_u8", "mtb_rcan_gate",
+              "mtb_image_to_planes_unshuffle", "mtb_f32_to_u8_crop"):
         getattr(l, n).restype = i32
     l._ew_declared = True
 
@@ -44,7 +54,21 @@ def infer_config(sd: Dict[str, torch.Tensor]) -> dict:
     blocks = {int(k.split(".")[3]) for k in sd if k.startswith("body.0.body.") and ".body." in k[12:]}
     f = sd["head.0.weight"].shape[0]
     red = f // sd["body.0.body.0.body.3.conv_du.0.weight"].shape[0]
-    return dict(n_resgroups=max(groups) + 1, n_resblocks=max(blocks) + 1, n_feats=f, reduction=red)
+    # "_PU" variants (spandrel RCAN unshuffle_mod): the head sees PixelUnshuffle(d) of the page = 3*d*d channels, and the
+    # upsampler has one conv+PixelShuffle(2) stage more per factor of two (tail.0.0, tail.0.2, ...)
+    in_ch = sd["head.0.weight"].shape[1]
+    d = int(round((in_ch / 3) ** 0.5))
+    if 3 * d * d != in_ch:
+        raise ValueError(f"RCAN: head input channels {in_ch} are not 3*d*d")
+    stages = sorted(int(k.split(".")[2]) for k in sd if k.startswith("tail.0.") and k.endswith(".weight"))
+    for i in stages:
+        if sd[f"tail.0.{i}.weight"].shape[0] != 4 * f:
+            raise ValueError("RCAN: only PixelShuffle(2) upsampler stages are supported")
+    scale = (2 ** len(stages)) // d
+    if scale * d != 2 ** len(stages) or scale < 1:
+        raise ValueError(f"RCAN: upsampler x{2 ** len(stages)} does not undo unshuffle x{d}")
+    return dict(n_resgroups=max(groups) + 1, n_resblocks=max(blocks) + 1, n_feats=f, reduction=red, unshuffle=d,
+                up_stages=stages, scale=scale)
 
 
 class RcanB200:
@@ -88,32 +112,39 @@ class RcanB200:
             self.blocks.append((grp, conv_w(f"body.{g}.body.{R}")))
         self.w_body_tail = conv_w(f"body.{G}")
         # upsampler conv: reorder output channels so the four PixelShuffle phases are contiguous 64-channel blocks
-        wu, bu = sd["tail.0.0.weight"], sd["tail.0.0.bias"]
         idx = torch.arange(4 * f, device=device).view(f, 4).t().reshape(-1)   # new[(dy*2+dx)*f + c] = old[c*4 + dy*2+dx]
-        self.w_up = (P.conv_weight_to_planes(wu[idx], pl), P.pad_bias(bu[idx], 4 * f))
+        self.w_up = []
+        for i in self.cfg["up_stages"]:
+            wu, bu = sd[f"tail.0.{i}.weight"], sd[f"tail.0.{i}.bias"]
+            self.w_up.append((P.conv_weight_to_planes(wu[idx], pl), P.pad_bias(bu[idx], 4 * f)))
         self.w_tail = conv_w("tail.1")
-        self._plans: Dict[Tuple[int, int], dict] = {}
+        self.unshuffle, self.scale = self.cfg["unshuffle"], self.cfg["scale"]
+        # plans (buffers + launch descriptors) per input size, least recently used first; crops make the sizes ragged
+        self._plans: "collections.OrderedDict[Tuple[int, int], dict]" = collections.OrderedDict()
+        self.max_plans = int(os.environ.get("MTB200_RCAN_MAX_PLANS", "12"))
+        self.max_plan_bytes = int(float(os.environ.get("MTB200_RCAN_MAX_PLAN_GB", "48")) * 2 ** 30)
 
     # ---------------------------------------------------------------------------------------------------------
     def _build(self, h: int, w: int) -> dict:
+        """h, w: size of the frame the conv body sees (the page, or the page / unshuffle factor rounded up)."""
         dev, pl, f = self.device, self.planes, self.F
         bf = torch.bfloat16
         n = 1
+        nbytes = [0]
 
         def act(hh, ww, c=f):
+            nbytes[0] += pl * n * hh * ww * c * 2
             return torch.zeros((pl, n, hh, ww, c), dtype=bf, device=dev)
 
         b = dict(x_in=act(h, w), head=act(h, w), u=act(h, w), pa=act(h, w), pb=act(h, w),
-                 g0=act(h, w), g1=act(h, w), up=act(2 * h, 2 * w),
-                 out32=torch.zeros((n, 2 * h, 2 * w, 16), dtype=torch.float32, device=dev),
-                 scale=torch.zeros((n, f), dtype=torch.float32, device=dev))
+                 g0=act(h, w), g1=act(h, w), scale=torch.zeros((n, f), dtype=torch.float32, device=dev))
         steps = []
         mode = self.conv_mode
 
         def conv(x, wgt, out, **kw):
             return ConvPlan(x, wgt[0], wgt[1], out, k=3, pad=1, mode=kw.pop("mode", mode), **kw)
 
-        # head conv: only 3 of the 64 padded input channels are non-zero (per-tap kernel)
+        # head conv: only 3*d*d of the 64 padded input channels are non-zero (per-tap kernel)
         steps.append(("conv", conv(b["x_in"], self.w_head, b["head"], mode=1)))
         probe = conv(b["head"], self.blocks[0][0][0][0], b["u"], act="relu")
         parts = probe.num_sum_rows
@@ -140,17 +171,38 @@ class RcanB200:
             steps.append(("conv", conv(x, tailw, gout, residual=grp_in)))   # group tail conv + group skip
             src = gout
         steps.append(("conv", conv(src, self.w_body_tail, b["u"], residual=b["head"])))
-        steps.append(("conv", ConvPlan(b["u"], self.w_up[0], self.w_up[1], b["up"], k=3, pad=1, pixel_shuffle=True,
-                                       mode=1)))
-        steps.append(("conv", ConvPlan(b["up"], self.w_tail[0], self.w_tail[1], b["out32"], k=3, pad=1, mode=1)))
+        # upsampler: conv F -> 4F with the PixelShuffle(2) folded into the store, once per stage
+        cur, hh, ww = b["u"], h, w
+        for si, wu in enumerate(self.w_up):
+            nxt = act(2 * hh, 2 * ww)
+            b[f"up{si}"] = nxt
+            steps.append(("conv", ConvPlan(cur, wu[0], wu[1], nxt, k=3, pad=1, pixel_shuffle=True, mode=1)))
+            cur, hh, ww = nxt, 2 * hh, 2 * ww
+        b["out32"] = torch.zeros((n, hh, ww, 16), dtype=torch.float32, device=dev)
+        nbytes[0] += n * hh * ww * 16 * 4
+        b["out_hw"] = (hh, ww)
+        steps.append(("conv", ConvPlan(cur, self.w_tail[0], self.w_tail[1], b["out32"], k=3, pad=1, mode=1)))
         b["steps"] = steps
+        b["nbytes"] = nbytes[0]
+        b["uses"] = 0
         return b
 
+    def body_hw(self, h: int, w: int) -> Tuple[int, int]:
+        d = self.unshuffle
+        return -(-h // d), -(-w // d)
+
     def _get(self, h: int, w: int) -> dict:
+        """Plan for an input page of h x w (least-recently-used plans are dropped beyond max_plans / max_plan_bytes)."""
         key = (h, w)
-        if key not in self._plans:
-            self._plans[key] = self._build(h, w)
-        return self._plans[key]
+        if key in self._plans:
+            self._plans.move_to_end(key)
+            return self._plans[key]
+        plan = self._build(*self.body_hw(h, w))
+        self._plans[key] = plan
+        while len(self._plans) > 1 and (len(self._plans) > self.max_plans or
+                                         sum(p["nbytes"] for p in self._plans.values()) > self.max_plan_bytes):
+            self._plans.popitem(last=False)
+        return plan
 
     def _run_body(self, b: dict, h: int, w: int) -> None:
         l, st = self.l, stream_ptr()
@@ -172,6 +224,7 @@ class RcanB200:
         "conv_body" (RCAB 3x3 convs), "gate", "conv" (head / group tails / upsampler / tail)."""
         h, w, _ = img.shape
         b = self._get(h, w)
+        hb, wb = self.body_hw(h, w)
         evs = []
         st = stream_ptr()
         for kind, arg in b["steps"]:
@@ -180,7 +233,7 @@ class RcanB200:
             if kind in ("conv", "conv_body"):
                 arg.run()
             else:
-                self._gate(b, arg, h, w, st)
+                self._gate(b, arg, hb, wb, st)
             e1.record()
             evs.append((kind, e0, e1))
         torch.cuda.synchronize()
@@ -195,30 +248,44 @@ class RcanB200:
         l, st = self.l, stream_ptr()
         mean = [m * self.rgb_range for m in self.DIV2K_MEAN] if self.norm else [0.0, 0.0, 0.0]
         sub = (C.c_float * 3)(*mean)
-        check(l.mtb_image_to_planes(ptr(b["in_u8"]), h, w, c, int(swap_rb), self.rgb_range / 255.0, sub, ptr(b["x_in"]), 64,
-                                    self.planes, st), "mtb_image_to_planes")
-        self._run_body(b, h, w)
+        d, sc = self.unshuffle, self.scale
+        hb, wb = self.body_hw(h, w)
+        if d == 1:
+            check(l.mtb_image_to_planes(ptr(b["in_u8"]), h, w, c, int(swap_rb), self.rgb_range / 255.0, sub, ptr(b["x_in"]),
+                                        64, self.planes, st), "mtb_image_to_planes")
+        else:
+            check(l.mtb_image_to_planes_unshuffle(ptr(b["in_u8"]), h, w, c, int(swap_rb), self.rgb_range / 255.0, sub, d,
+                                                  ptr(b["x_in"]), 64, self.planes, st), "mtb_image_to_planes_unshuffle")
+        self._run_body(b, hb, wb)
         add = (C.c_float * 3)(*mean)
-        check(l.mtb_f32_to_u8(ptr(b["out32"]), 4 * h * w, 16, add, 1.0 / self.rgb_range, ptr(b["out_u8"]),
-                              ptr(b["out_f"]) if want_float else None, st), "mtb_f32_to_u8")
+        oh, ow = b["out_hw"]
+        if (oh, ow) == (sc * h, sc * w):
+            check(l.mtb_f32_to_u8(ptr(b["out32"]), oh * ow, 16, add, 1.0 / self.rgb_range, ptr(b["out_u8"]),
+                                  ptr(b["out_f"]) if want_float else None, st), "mtb_f32_to_u8")
+        else:
+            check(l.mtb_f32_to_u8_crop(ptr(b["out32"]), oh, ow, 16, sc * h, sc * w, add, 1.0 / self.rgb_range,
+                                       ptr(b["out_u8"]), ptr(b["out_f"]) if want_float else None, st), "mtb_f32_to_u8_crop")
 
     def upscale_u8(self, img: torch.Tensor, *, swap_rb: bool = False, want_float: bool = False):
-        """img: device uint8 HxWx(3|4).  Returns uint8 2Hx2Wx3 (RGB model output; `swap_rb` feeds a BGR page), and
-        optionally the float output before quantisation (2Hx2Wx3).  The returned tensors are the model's static output
-        buffers: consume (copy) them before the next call."""
+        """img: device uint8 HxWx(3|4).  Returns uint8 sH x sW x 3 (s = model scale, 2 for both AnimeSharp models; RGB
+        model output, `swap_rb` feeds a BGR page), and optionally the float output before quantisation.  The returned
+        tensors are the plan's static output buffers: consume (copy) them before the next call of the same size."""
         from . import graphs
         assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_contiguous()
         h, w, c = img.shape
+        sc = self.scale
         b = self._get(h, w)
         key = ("io", c)
         if key not in b:
             b[key] = True
             b["in_u8"] = torch.empty((h, w, c), dtype=torch.uint8, device=self.device)
-            b["out_u8"] = torch.empty((2 * h, 2 * w, 3), dtype=torch.uint8, device=self.device)
-            b["out_f"] = torch.empty((2 * h, 2 * w, 3), dtype=torch.float32, device=self.device)
+            b["out_u8"] = torch.empty((sc * h, sc * w, 3), dtype=torch.uint8, device=self.device)
+            b["out_f"] = torch.empty((sc * h, sc * w, 3), dtype=torch.float32, device=self.device)
         b["in_u8"].copy_(img)
+        b["uses"] += 1
         gkey = ("graph", c, bool(swap_rb), bool(want_float))
-        if graphs.ENABLED:
+        # a size seen once (ragged bubble crops) runs eagerly; from its second use on the ~600 launches replay as a graph
+        if graphs.ENABLED and (gkey in b or b["uses"] >= 2):
             if gkey not in b:
                 b[gkey] = graphs.CapturedGraph(lambda: self._upscale_static(b, h, w, c, swap_rb, want_float))
             b[gkey].replay()
@@ -227,16 +294,21 @@ class RcanB200:
         return (b["out_u8"], b["out_f"]) if want_float else b["out_u8"]
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
-        """Reference call shape (core/image/image_utils.py:369-374): float32 (1,3,h,w) in [0,1] -> (1,3,2h,2w)."""
+        """Reference call shape (core/image/image_utils.py:369-374): float32 (1,3,h,w) in [0,1] -> (1,3,sh,sw)."""
         assert x.dim() == 4 and x.shape[0] == 1 and x.shape[1] == 3
         h, w = x.shape[2], x.shape[3]
+        d, sc = self.unshuffle, self.scale
+        hb, wb = self.body_hw(h, w)
         b = self._get(h, w)
         xin = x.to(self.device, torch.float32) * self.rgb_range
         if self.norm:
             xin = xin - torch.tensor(self.DIV2K_MEAN, device=self.device).view(1, 3, 1, 1) * self.rgb_range
+        if d > 1:
+            xin = torch.nn.functional.pad(xin, (0, wb * d - w, 0, hb * d - h), mode="reflect")
+            xin = torch.nn.functional.pixel_unshuffle(xin, d)
         b["x_in"].copy_(P.nchw_to_planes(xin, self.planes))
-        self._run_body(b, h, w)
-        y = b["out32"][..., :3].permute(0, 3, 1, 2)
+        self._run_body(b, hb, wb)
+        y = b["out32"][:, :sc * h, :sc * w, :3].permute(0, 3, 1, 2)
         if self.norm:
             y = y + torch.tensor(self.DIV2K_MEAN, device=self.device).view(1, 3, 1, 1) * self.rgb_range
         return (y / self.rgb_range).contiguous()

@@ -34,7 +34,8 @@ def _conv(g, cout, cin, k, gain=1.0, bias_std=0.02):
 
 # ---- RCAN (2x-AnimeSharpV4 architecture family) -----------------------------------------------------------------
 def rcan_state_dict(seed: int = 0, n_resgroups: int = 10, n_resblocks: int = 20, n_feats: int = 64,
-                    reduction: int = 16) -> Dict[str, torch.Tensor]:
+                    reduction: int = 16, unshuffle: int = 1) -> Dict[str, torch.Tensor]:
+    """`unshuffle` = 2 gives the "_PU" layout (12 input channels, two upsampler stages: tail.0.0 and tail.0.2)."""
     g = _gen(seed)
     sd: Dict[str, torch.Tensor] = {}
 
@@ -42,7 +43,7 @@ def rcan_state_dict(seed: int = 0, n_resgroups: int = 10, n_resblocks: int = 20,
         sd[name + ".weight"], sd[name + ".bias"] = w, b
 
     f = n_feats
-    put("head.0", *_conv(g, f, 3, 3, gain=1.4))
+    put("head.0", *_conv(g, f, 3 * unshuffle * unshuffle, 3, gain=1.4))
     for gi in range(n_resgroups):
         for bi in range(n_resblocks):
             base = f"body.{gi}.body.{bi}.body"
@@ -53,6 +54,10 @@ def rcan_state_dict(seed: int = 0, n_resgroups: int = 10, n_resblocks: int = 20,
         put(f"body.{gi}.body.{n_resblocks}", *_conv(g, f, f, 3, gain=0.5))
     put(f"body.{n_resgroups}", *_conv(g, f, f, 3, gain=0.5))
     put("tail.0.0", *_conv(g, 4 * f, f, 3, gain=1.0))
+    up, i = 2 * unshuffle, 2
+    while up > 2:
+        put(f"tail.0.{i}", *_conv(g, 4 * f, f, 3, gain=1.0))
+        up, i = up // 2, i + 2
     put("tail.1", *_conv(g, 3, f, 3, gain=0.3))
     sd["tail.1.bias"] = torch.full((3,), 0.5)                        # mid-grey output so pixels are not clipped
     return sd

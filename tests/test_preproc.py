@@ -1,6 +1,7 @@
 """Pre-processing parity: cv2.resize(INTER_LINEAR) letterbox (ultralytics LetterBox) and torchvision/ATen uint8
 antialias-bilinear resize (Sam2 image processor) — the restated algorithms (CPU) and the CUDA kernels (GPU) are
-bit-exact against the libraries themselves."""
+bit-exact against the libraries themselves; likewise Pillow's LANCZOS resample (the exact-size step after the RCAN passes
+and resize_to_min_side, core/image/image_utils.py:545,551-595)."""
 import ctypes as C
 
 import cv2
@@ -106,3 +107,75 @@ def test_aa_resize_kernel_matches_torch(hw):
     ref = F.interpolate(t, size=(1024, 1024), mode="bilinear", antialias=True, align_corners=False)[0].permute(1, 2, 0).numpy()
     got = resize_aa_device(torch.from_numpy(img).cuda(), 1024, 1024).cpu().numpy()
     assert np.array_equal(got, ref)
+
+
+# ---- Pillow LANCZOS (Resample.c: 22-bit coefficients, uint8 intermediate) ---------------------------------------------
+def _lanczos_tables(n_in, n_out):
+    from mangatranslator_b200 import _lib
+    l = _lib.lib()
+    l.mtb_lanczos_weights_host.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    cap = int(np.ceil(3.0 * max(n_in / n_out, 1.0))) * 2 + 1
+    st, ln = np.zeros(n_out, np.int32), np.zeros(n_out, np.int32)
+    w = np.zeros((n_out, cap), np.int32)
+    k = C.c_int()
+    assert l.mtb_lanczos_weights_host(n_in, n_out, st.ctypes.data, ln.ctypes.data, w.ctypes.data, cap, C.byref(k)) == 0
+    assert k.value == cap
+    return st, ln, w
+
+
+def _lanczos_axis(img, axis, n_out):
+    st, ln, w = _lanczos_tables(img.shape[axis], n_out)
+    x = np.moveaxis(img, axis, 0).astype(np.int64)
+    out = np.zeros((n_out,) + x.shape[1:], np.int64)
+    for o in range(n_out):
+        acc = np.full(x.shape[1:], 1 << 21, np.int64)
+        for j in range(ln[o]):
+            acc += int(w[o, j]) * x[st[o] + j]
+        assert np.abs(acc).max() < 2 ** 31            # the kernel accumulates in int32 like Pillow
+        out[o] = np.clip(acc >> 22, 0, 255)
+    return np.moveaxis(out, 0, axis).astype(np.uint8)
+
+
+def _lanczos_numpy(img, oh, ow):
+    a = _lanczos_axis(img, 1, ow) if ow != img.shape[1] else img
+    return _lanczos_axis(a, 0, oh) if oh != img.shape[0] else a
+
+
+LANCZOS_CASES = [((300, 200), (450, 300)), ((257, 391), (200, 304)), ((640, 480), (213, 160)), ((97, 131), (97, 400)),
+                 ((120, 90), (311, 90)), ((64, 64), (1, 1)), ((5, 7), (50, 70)), ((1536 // 2, 1024 // 2), (1152, 768))]
+
+
+@pytest.mark.parametrize("case", LANCZOS_CASES)
+def test_lanczos_algorithm_matches_pillow(case):
+    from PIL import Image
+    (h, w), (oh, ow) = case
+    img = np.random.default_rng(h * 7 + w).integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((ow, oh), Image.LANCZOS))
+    assert np.array_equal(_lanczos_numpy(img, oh, ow), ref)
+
+
+def test_lanczos_saturating_edges_match_pillow():
+    """Black/white step edges drive the negative lobes below 0 and above 255: clip8 on both passes."""
+    from PIL import Image
+    img = np.zeros((90, 120, 3), np.uint8)
+    img[:, 60:] = 255
+    img[45:, :, 1] = 255 - img[45:, :, 1]
+    for oh, ow in ((135, 180), (61, 77), (180, 77)):
+        ref = np.asarray(Image.fromarray(img).resize((ow, oh), Image.LANCZOS))
+        assert np.array_equal(_lanczos_numpy(img, oh, ow), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", LANCZOS_CASES + [((3072, 2048), (2304, 1536)), ((1536, 1024), (2000, 1333))])
+def test_lanczos_kernel_matches_pillow(case):
+    from PIL import Image
+    from mangatranslator_b200.preproc import resize_lanczos_device
+    (h, w), (oh, ow) = case
+    img = np.random.default_rng(h * 7 + w).integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((ow, oh), Image.LANCZOS))
+    got = resize_lanczos_device(torch.from_numpy(img).cuda(), oh, ow).cpu().numpy()
+    assert np.array_equal(got, ref)
+    # a 4-channel source reads its first three channels
+    img4 = np.concatenate([img, np.full((h, w, 1), 7, np.uint8)], axis=2)
+    got4 = resize_lanczos_device(torch.from_numpy(img4).cuda(), oh, ow).cpu().numpy()
+    assert np.array_equal(got4, ref)

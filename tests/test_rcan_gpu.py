@@ -41,6 +41,38 @@ def test_full_depth_rcan_matches_oracle():
     assert du8.max() <= 1
 
 
+@pytest.mark.parametrize("hw", [(96, 80), (37, 53), (9, 131)], ids=["even", "odd_reflect_pad", "thin"])
+def test_pixel_unshuffle_variant_matches_oracle(hw):
+    """The lite "_PU" model (load_upscale_lite): PixelUnshuffle(2) of the reflect-padded page, body at quarter
+    resolution, two PixelShuffle(2) stages, crop to 2H x 2W — inferred from the state dict alone."""
+    err, du8, net, m, rgb = _run(dict(n_resgroups=2, n_resblocks=2, unshuffle=2), hw[0], hw[1], 6)
+    assert net.cfg["unshuffle"] == 2 and net.cfg["up_stages"] == [0, 2] and net.scale == 2
+    assert err < TOL, err
+    assert du8.max() <= 1 and (du8 > 0).mean() < 0.01
+    x = torch.from_numpy(rgb).permute(2, 0, 1).float().div(255).unsqueeze(0)
+    y = net(x.cuda())                                   # the reference's tensor call shape goes the same way
+    with torch.no_grad():
+        ref = m(x)
+    assert y.shape == ref.shape == (1, 3, 2 * hw[0], 2 * hw[1])
+    assert (y.cpu() - ref).abs().max().item() < TOL
+
+
+def test_plan_cache_is_bounded_for_ragged_crop_sizes():
+    from mangatranslator_b200.rcan import RcanB200
+    dev = torch.device("cuda:0")
+    net = RcanB200(rcan_oracle.make_model(7, n_resgroups=1, n_resblocks=1).state_dict(), dev)
+    net.max_plans = 3
+    first = None
+    for i in range(6):
+        img = torch.randint(0, 256, (24 + 3 * i, 40 - i, 3), dtype=torch.uint8, device=dev)
+        out = net.upscale_u8(img).clone()
+        if i == 0:
+            first, first_img = out, img
+    assert len(net._plans) == 3
+    assert torch.equal(net.upscale_u8(first_img), first)           # an evicted size is rebuilt with the same result
+    assert torch.equal(net.upscale_u8(first_img), first)           # second use of a size replays as a CUDA graph
+
+
 def test_reference_call_shape_and_determinism():
     """model(x) with the reference's tensor contract (image_utils.py:369-374) and bit-identical reruns."""
     err, _, net, m, rgb = _run(dict(n_resgroups=1, n_resblocks=2), 40, 48, 3)

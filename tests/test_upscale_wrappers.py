@@ -1,0 +1,110 @@
+"""Upscale wrappers around the RCAN: `upscale_image` (reference core/image/image_utils.py:503-548: 2x passes + exact-size
+LANCZOS), `process_bubble_image_cached` (:678-746: per-bubble crops, passes until the min side reaches the target, then
+resize_to_min_side) for the full and the lite ("_PU") model.
+
+tests/golden/upscale_golden.npz holds the outputs of the UNMODIFIED reference functions run on CPU with the restated
+RCAN in its ModelManager slots (oracle/gen_golden_upscale.py).  CPU: the oracle's restatement of the wrappers equals
+them bit for bit.  GPU: the B200 path (RCAN kernels + the Pillow-exact LANCZOS kernel) gives the same geometry and
+pixels within the RCAN's float tolerance (1e-3 abs before quantisation = at most 1 LSB per pass, which the resample can
+spread to 2)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+import rcan_oracle
+from gen_golden_upscale import CASES, MODELS, SEED
+from helpers import ROOT
+
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "upscale_golden.npz"))
+
+
+def _crop(case):
+    from mangatranslator_b200 import synth
+    _, _, (y0, x0, h, w), _, _ = case
+    page = synth.make_page(11, 768, 1024, n_bubbles=6).image_rgb
+    return np.ascontiguousarray(page[y0:y0 + h, x0:x0 + w])
+
+
+def _state_dict(kind):
+    from mangatranslator_b200 import weights as W
+    cfg = MODELS[kind]
+    return W.rcan_state_dict(SEED, n_resgroups=cfg["n_resgroups"], n_resblocks=cfg["n_resblocks"], unshuffle=cfg["unshuffle"])
+
+
+def _oracle_model(kind):
+    m = rcan_oracle.RCAN(**MODELS[kind]).eval()
+    m.load_state_dict(_state_dict(kind))
+    return m
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_oracle_wrappers_match_reference_golden(case):
+    name, kind, _, arg, model = case
+    m = _oracle_model(model)
+    crop = _crop(case)
+    got = rcan_oracle.upscale_image(m, crop, arg) if kind == "upscale_image" else rcan_oracle.process_bubble(m, crop, arg, "min")
+    assert got.shape == GOLD[name].shape
+    assert np.array_equal(got, GOLD[name])
+
+
+def test_resize_geometry_and_argument_errors():
+    from mangatranslator_b200.core.image import image_utils as iu
+    from mangatranslator_b200.utils.exceptions import ImageProcessingError
+    assert iu.resize_side_geometry(280, 200, 200) is None
+    assert iu.resize_side_geometry(212, 308, 200) == (200, 291)
+    assert iu.resize_side_geometry(3, 1000, 1) == (1, 333)
+    with pytest.raises(ImageProcessingError):
+        iu.upscale_image_to_dimension(None, Image.new("RGB", (8, 8)), 100, torch.device("cpu"), mode="diag")
+    with pytest.raises(ImageProcessingError):
+        iu.resize_to_min_side(Image.new("RGBA", (8, 8)), 16)          # only RGB is on the hot path
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_b200_wrappers_match_reference_golden(case):
+    from mangatranslator_b200.core.caching import get_cache
+    from mangatranslator_b200.core.image import image_utils as iu
+    from mangatranslator_b200.core.ml.model_manager import ModelType, get_model_manager
+    from mangatranslator_b200.rcan import RcanB200
+    name, kind, _, arg, model = case
+    dev = torch.device("cuda:0")
+    mm = get_model_manager()
+    mm.unload_all()
+    mm.models[ModelType.UPSCALE] = RcanB200(_state_dict("model"), dev)
+    mm.models[ModelType.UPSCALE_LITE] = RcanB200(_state_dict("model_lite"), dev)
+    get_cache().clear()
+    crop = Image.fromarray(_crop(case))
+    if kind == "upscale_image":
+        res = iu.upscale_image(crop, arg, model_type=model)
+    else:
+        mdl = mm.models[ModelType.UPSCALE_LITE if model == "model_lite" else ModelType.UPSCALE]
+        res = iu.process_bubble_image_cached(crop, mdl, dev, arg, "min", model)
+        again = iu.process_bubble_image_cached(crop, mdl, dev, arg, "min", model)
+        assert again is res                                                # cached like the reference
+    got = np.asarray(res)
+    mm.unload_all()
+    assert got.shape == GOLD[name].shape
+    d = np.abs(got.astype(int) - GOLD[name].astype(int))
+    assert d.max() <= 2 and (d > 0).mean() < 0.02, (d.max(), (d > 0).mean())
+
+
+@pytest.mark.gpu
+def test_page_bubble_crops_stay_on_device_and_match_single_calls():
+    """process_page_bubbles_device (all crops of a device-resident page) == process_bubble_image_cached per crop."""
+    from mangatranslator_b200 import synth
+    from mangatranslator_b200.core.image import image_utils as iu
+    from mangatranslator_b200.rcan import RcanB200
+    dev = torch.device("cuda:0")
+    net = RcanB200(_state_dict("model_lite"), dev)
+    pg = synth.make_page(5, 480, 640, n_bubbles=4)
+    page = torch.from_numpy(np.ascontiguousarray(pg.image_rgb)).to(dev)
+    boxes = [[int(v) for v in b] for b in pg.boxes_xyxy]
+    outs = iu.process_page_bubbles_device(page, boxes, net, 200, "min")
+    assert len(outs) == len(boxes)
+    for (x0, y0, x1, y1), o in zip(boxes, outs):
+        assert o.is_cuda and min(o.shape[0], o.shape[1]) == 200
+        single = iu.process_bubble_crop_device(page[y0:y1, x0:x1].contiguous(), net, 200, "min")
+        assert torch.equal(single, o)
