@@ -221,6 +221,26 @@ int mtb_nms(const mtb_nms_params* p /* host */, const float* cand, const int* ca
             int* order_ws /* [N][max_cand] */, unsigned char* dead_ws /* [N][max_cand] */, float* out_det,
             int* out_count, int* final_idx, void* stream);
 
+/* ---- conjoined-bubble mask splitting (core/image/detection.py:971-1035 `_split_conjoined_mask` with
+ * `_seed_mask_from_box` :646-672, `_split_overlap_zone_with_line` :675-800, `_expand_resolved_masks_within_parent`
+ * :932-968) --------------------------------------------------------------------------------------------------
+ * parent: uint8 HxW (non-zero = inside), device.  rects [K][4] (x0,y0,x1,y1: floor/ceil clip of the child boxes,
+ * `_build_rect_mask_from_box` :568-579), centers [K][2] (float box centres, for the empty-seed fallback), window
+ * (x0,y0,x1,y1: must contain every parent pixel and every child rectangle) and pairs (one per overlapping (i<j) in
+ * the reference's loop order) are HOST arrays prepared by the caller.  A pair's zone parent∧rect_i∧rect_j is cleared
+ * from both children and re-divided by v = (x-cx)*ax + (y-cy)*ay in float64: mode 1 gives i the pixels with v <= 0
+ * and j those with v > 0, mode 2 gives i v >= 0 and j v < 0, mode 0 leaves the zone to the nearest-child rule.
+ * out: uint8 [K][H][W] {0,255}.  Bit-exact with the reference under OpenCV's own (non-IPP) distanceTransform. */
+#define MTB_SPLIT_MAX_CHILDREN 12
+typedef struct mtb_split_pair {
+  int i, j, mode, reserved;
+  double cx, cy, ax, ay;
+} mtb_split_pair;
+long long mtb_split_conjoined_workspace_bytes(int win_h, int win_w, int K);
+int mtb_split_conjoined(const uint8_t* parent, int H, int W, int K, const int* rects, const double* centers,
+                        const int* window, int n_pairs, const mtb_split_pair* pairs, uint8_t* out, void* workspace,
+                        long long workspace_bytes, void* stream);
+
 /* ---- input pre-processing, bit-exact with the CPU libraries the reference calls ----------------------------
  * letterbox_u8 : ultralytics LetterBox (cv2.resize INTER_LINEAR on uint8 + 114 border + BGR->RGB), detection.py:1338-1345
  * resize_aa_u8 : Sam2ImageProcessorFast resize (torchvision bilinear, antialias=True, uint8), detection.py:494-495

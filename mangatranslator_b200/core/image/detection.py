@@ -7,8 +7,12 @@ are duck-typed exactly like the reference's, so injected ultralytics/transformer
 B200-native objects everything between the page upload and the final masks stays on the device
 (`detect_pages_device`).
 
-Out of scope here: the RT-DETRv2 conjoined-bubble branch (its load failure is swallowed exactly like
-the reference does at :1541-1548, so all bubbles are treated as simple), OSB-text verification, SAM3, panel detection.
+Conjoined bubbles (:345-472, :582-1035, :1075-1260): primaries that overlap each other are grouped into synthetic
+conjoined bubbles on every page (:1596-1619), SAM segments the group's union box, and the parent mask is divided between
+the members by `mtb_split_conjoined` (mangatranslator_b200/conjoined.py holds the box geometry).  The same code serves
+conjoined parents found by a secondary detector when one is present in the ModelManager; the RT-DETRv2 network itself
+is out of scope: `load_rtdetr_conjoined_bubble` raises and the failure is swallowed exactly like the
+reference does at :1541-1548.  Also out of scope: OSB-text verification, SAM3, panel detection.
 """
 from __future__ import annotations
 
@@ -27,6 +31,7 @@ from mangatranslator_b200.utils.logging import log_message
 
 IOA_THRESHOLD = 0.50
 SAM_MASK_THRESHOLD = 0.5
+IOA_OVERLAP_THRESHOLD = 0.5
 IOU_DUPLICATE_THRESHOLD = 0.7
 
 
@@ -136,11 +141,134 @@ def _class_name(model, results, idx) -> str:
         return "speech_bubble"
 
 
+def _secondary_detections(mm, image_cv, primary_boxes, sources, conjoined_confidence, device, osb_enabled, verbose):
+    """The RT-DETR branch of the reference (:1392-1548) for a secondary detector present in the ModelManager (this build
+    ships none: `load_rtdetr_conjoined_bubble` raises and the caller keeps the primaries, like the reference does when
+    the model cannot be loaded).  Returns (primary_boxes, sources, secondary_boxes, secondary_sources, secondary_results,
+    text_free_boxes)."""
+    text_free: List[List[float]] = []
+    model = mm.load_rtdetr_conjoined_bubble()
+    results = model(image_cv, conf=conjoined_confidence, device=device, verbose=False, imgsz=640)[0]
+    sec = results.boxes.xyxy if results.boxes is not None else torch.tensor([])
+    sec_src = [("secondary", i) for i in range(len(sec))]
+    if len(sec) > 1:
+        sec, sec_src = _remove_contained_boxes(sec, sec_src)
+    if len(sec) > 0 and hasattr(model, "names"):
+        bubble_id = next((c for c, n in model.names.items() if n == "bubble"), None)
+        text_free_id = next((c for c, n in model.names.items() if n == "text_free"), None)
+        keep_b, keep_s = [], []
+        for i, sb in enumerate(sec):
+            cid = int(results.boxes.cls[sec_src[i][1]])
+            if text_free_id is not None and cid == text_free_id:
+                text_free.append(sb.tolist())
+            elif bubble_id is None or cid == bubble_id:
+                keep_b.append(sb)
+                keep_s.append(sec_src[i])
+        sec = torch.stack(keep_b) if keep_b else sec[:0]
+        sec_src = keep_s
+        if len(sec) > 0:                                   # bubbles the primary detector missed (:1456-1497)
+            plist = primary_boxes.tolist() if len(primary_boxes) > 0 else []
+            missed = [(sb, sec_src[i]) for i, sb in enumerate(sec)
+                      if not any(_calculate_ioa(sb.tolist(), pb) > IOA_OVERLAP_THRESHOLD or
+                                 _calculate_ioa(pb, sb.tolist()) > IOA_OVERLAP_THRESHOLD for pb in plist)]
+            if missed:
+                log_message(f"Found {len(missed)} missed bubbles from secondary model", always_print=True)
+                extra = torch.stack([m[0] for m in missed])
+                primary_boxes = torch.cat((primary_boxes, extra.to(primary_boxes.device)), dim=0) if len(primary_boxes) else extra
+                sources = sources + [m[1] for m in missed]
+    if text_free and len(primary_boxes) > 0:               # primaries that are really free text (:1499-1538)
+        plist = primary_boxes.tolist()
+        keep = [i for i, pb in enumerate(plist)
+                if not any(_calculate_ioa(pb, tf) > IOA_OVERLAP_THRESHOLD or _calculate_ioa(tf, pb) > IOA_OVERLAP_THRESHOLD
+                           for tf in text_free)]
+        if len(keep) < len(plist):
+            action = "routing to OSB pipeline" if osb_enabled else "discarding (OSB disabled)"
+            log_message(f"Removing {len(plist) - len(keep)} bubbles marked text_free ({action})", always_print=True)
+            primary_boxes = primary_boxes[keep] if keep else torch.tensor([])
+            sources = [sources[i] for i in keep]
+    return primary_boxes, sources, sec, sec_src, results, text_free
+
+
+def _detection_metadata(source, orig, primary_results, primary_model, secondary_results, conjoined_confidence):
+    """(:1038-1072) confidence / class name of a box by where it came from."""
+    if source == "primary" and primary_results is not None and len(primary_results.boxes) > 0:
+        k = min(orig, len(primary_results.boxes.conf) - 1)
+        return float(primary_results.boxes.conf[k]), _class_name(primary_model, primary_results, k)
+    if source == "secondary" and secondary_results is not None and len(secondary_results.boxes) > 0:
+        k = min(orig, len(secondary_results.boxes.conf) - 1)
+        names = getattr(secondary_results, "names", None)
+        cid = int(secondary_results.boxes.cls[k])
+        return float(secondary_results.boxes.conf[k]), (names.get(cid, "speech_bubble") if names is not None else "speech_bubble")
+    return conjoined_confidence, "speech_bubble"
+
+
+def _round_bbox(box) -> Tuple[int, int, int, int]:
+    x0, y0, x1, y1 = box.tolist() if hasattr(box, "tolist") else box
+    return (int(round(x0)), int(round(y0)), int(round(x1)), int(round(y1)))
+
+
+def _split_group_on_device(parent_mask: np.ndarray, group_boxes, device) -> List[np.ndarray]:
+    """`_split_conjoined_mask` of the parent (with the child rectangles ORed in, :1161-1164) through the CUDA kernel."""
+    from mangatranslator_b200.conjoined import split_conjoined_device
+    dev = get_model_manager()._require_cuda()
+    out, _ = split_conjoined_device(torch.from_numpy(np.ascontiguousarray(parent_mask)).to(dev), group_boxes)
+    return [m for m in out.cpu().numpy()]
+
+
+def _build_segmentation_detections(primary_boxes, grouping_boxes, sources, primary_results, primary_model, secondary_boxes,
+                                   secondary_sources, secondary_results, simple_indices, conjoined_indices, img_h, img_w,
+                                   conjoined_confidence, sam_masks=None, synthetic_groups=None, device=None) -> List[dict]:
+    """(:1075-1260) simple boxes first, then the children of every conjoined parent, then the synthetic groups."""
+    from mangatranslator_b200.conjoined import union_box
+    dets: List[dict] = []
+
+    def meta(src):
+        return _detection_metadata(src[0], src[1], primary_results, primary_model, secondary_results, conjoined_confidence)
+
+    def own_or_yolo_mask(idx):
+        if sam_masks is not None and sam_masks[idx] is not None:
+            return sam_masks[idx]
+        if sources[idx][0] == "primary":
+            return _fallback_to_yolo_mask(primary_results, sources[idx][1], "binary")
+        return None
+
+    for idx in simple_indices:
+        conf, cls = meta(sources[idx])
+        mask = own_or_yolo_mask(idx)
+        if mask is None:
+            mask = _build_rect_mask_from_box(primary_boxes[idx], img_h, img_w)
+        dets.append({"bbox": _round_bbox(primary_boxes[idx]), "confidence": conf, "class": cls, "sam_mask": mask})
+
+    def emit_group(parent_mask, group_boxes, group_sources):
+        masks = _split_group_on_device(parent_mask, group_boxes, device)
+        bboxes = [_round_bbox(b) for b in group_boxes]
+        for k, src in enumerate(group_sources):
+            conf, cls = meta(src)
+            dets.append({"bbox": bboxes[k], "confidence": conf, "class": cls, "sam_mask": masks[k],
+                         "conjoined_neighbor_bboxes": [b for n, b in enumerate(bboxes) if n != k]})
+
+    for p_idx, s_indices in conjoined_indices:
+        parent_box = union_box(torch.cat([primary_boxes[p_idx].unsqueeze(0)] +
+                                         [secondary_boxes[s].unsqueeze(0) for s in s_indices], dim=0))
+        parent_mask = own_or_yolo_mask(p_idx)
+        if parent_mask is None:
+            parent_mask = _build_rect_mask_from_box(parent_box, img_h, img_w)
+        emit_group(parent_mask, [secondary_boxes[s] for s in s_indices], [secondary_sources[s] for s in s_indices])
+    for sg in synthetic_groups or []:
+        parent_mask = sg.get("parent_mask")
+        if parent_mask is None:
+            parent_mask = _build_rect_mask_from_box(sg["parent_box"], img_h, img_w)
+        members = sg["member_indices"]
+        emit_group(parent_mask, [grouping_boxes[m] for m in members], [sources[m] for m in members])
+    return dets
+
+
 def detect_speech_bubbles(image_path: Path, model_path, confidence=0.6, verbose=False, device=None,
                           seg_model: str = "yolo", conjoined_detection: bool = True, conjoined_confidence=0.35,
                           image_override: Optional[Image.Image] = None, osb_enabled: bool = False,
                           osb_text_verification: bool = False, osb_text_hf_token: str = "",
                           bubble_detector_model: str = "yolo_2") -> Tuple[List[dict], List[List[float]]]:
+    from mangatranslator_b200.conjoined import categorize_detections, detect_overlapping_primaries, union_box
     detections: List[dict] = []
     text_free_boxes: List[List[float]] = []
     _device = device if device is not None else get_best_device()
@@ -187,46 +315,87 @@ def detect_speech_bubbles(image_path: Path, model_path, confidence=0.6, verbose=
         return detections, text_free_boxes
     log_message(f"Detected {len(primary_boxes)} speech bubbles with YOLO", always_print=True)
 
+    secondary_boxes, secondary_sources, secondary_results = torch.tensor([]), [], None
     if conjoined_detection:
         try:
-            mm.load_rtdetr_conjoined_bubble()
-            log_message("Secondary conjoined-bubble detector injected but its merge logic is not part of this build",
-                        verbose=verbose)
+            (primary_boxes, sources, secondary_boxes, secondary_sources, secondary_results,
+             text_free_boxes) = _secondary_detections(mm, image_cv, primary_boxes, sources, conjoined_confidence, _device,
+                                                      osb_enabled, verbose)
         except Exception as e:   # the reference swallows a secondary-model failure and keeps the primaries (:1541-1548)
-            log_message(f"Secondary detection skipped: {e}", verbose=verbose)
+            log_message(f"Warning: Could not load/run secondary RT-DETR model: {e}. "
+                        "Proceeding without conjoined/fallback detection.", verbose=verbose)
+            secondary_boxes, secondary_sources, secondary_results = torch.tensor([]), [], None
+    if len(primary_boxes) == 0:
+        return detections, text_free_boxes
+    if osb_text_verification:
+        log_message("OSB text verification is outside this build; boxes are not expanded", verbose=verbose)
+    primary_boxes = primary_boxes.detach().float().cpu()
+    grouping_boxes = primary_boxes.clone()
 
+    conjoined_indices: list = []
     simple = list(range(len(primary_boxes)))
-    sam_masks: Optional[list] = None
-    if seg_model in ("sam2", "sam3"):
-        if seg_model == "sam3":
-            raise ModelError("SAM3 is outside the B200 hot path of this build")
-        try:
-            processor, sam_model = mm.load_sam2(verbose=verbose)
-            raw = _process_simple_bubbles(image_pil, primary_boxes, simple, processor, sam_model, _device)
-            sam_masks = []
-            for m, box in zip(raw, primary_boxes):
+    if len(secondary_boxes) > 0 and conjoined_detection:
+        secondary_boxes = secondary_boxes.detach().float().cpu()
+        conjoined_indices, simple = categorize_detections(grouping_boxes, secondary_boxes, IOA_THRESHOLD)
+        if conjoined_indices:
+            log_message(f"Detected {len(conjoined_indices)} conjoined speech bubbles with RT-DETR", always_print=True)
+    # primaries that overlap each other = one bubble cut into sections by the detector (:1596-1619); no secondary model needed
+    synthetic_groups: List[dict] = []
+    if len(simple) > 1:
+        groups, simple = detect_overlapping_primaries(grouping_boxes, simple)
+        if groups:
+            log_message(f"Detected {len(groups)} synthetic conjoined group(s) from "
+                        f"{sum(len(g) for g in groups)} overlapping primary detections", always_print=True)
+        for members in groups:
+            synthetic_groups.append({"member_indices": members, "parent_box": union_box(grouping_boxes[members]),
+                                     "parent_mask": None})
+
+    def assemble(sam_masks):
+        return _build_segmentation_detections(primary_boxes, grouping_boxes, sources, primary_results, primary_model,
+                                              secondary_boxes, secondary_sources, secondary_results, simple,
+                                              conjoined_indices, img_h, img_w, conjoined_confidence, sam_masks=sam_masks,
+                                              synthetic_groups=synthetic_groups, device=_device)
+
+    if seg_model not in ("sam2", "sam3"):
+        return assemble(None), text_free_boxes
+    if seg_model == "sam3":
+        raise ModelError("SAM3 is outside the B200 hot path of this build")
+    try:
+        sam_key = cache.get_sam_cache_key(image_pil, primary_boxes, seg_model, conjoined_detection, conjoined_confidence)
+        hit = cache.get_sam_masks(sam_key)
+        if hit is not None:
+            return hit, text_free_boxes
+        processor, sam_model = mm.load_sam2(verbose=verbose)
+        # one SAM batch: simple boxes, the combined parent box of every conjoined group, the synthetic parents (:1660-1693)
+        prompts, owner = [primary_boxes[i] for i in simple], list(simple)
+        for p_idx, s_indices in conjoined_indices:
+            prompts.append(union_box(torch.cat([primary_boxes[p_idx].unsqueeze(0)] +
+                                               [secondary_boxes[s].unsqueeze(0) for s in s_indices], dim=0)))
+            owner.append(p_idx)
+        synth_start = len(prompts)
+        prompts += [sg["parent_box"] for sg in synthetic_groups]
+        sam_masks: List[Optional[np.ndarray]] = [None] * len(primary_boxes)
+        if prompts:
+            raw = _process_simple_bubbles(image_pil, torch.stack(prompts), list(range(len(prompts))), processor, sam_model,
+                                          _device)
+            for i, (m, box) in enumerate(zip(raw, prompts)):
                 clip = _build_rect_mask_from_box(box, img_h, img_w) > 0        # floor/ceil box clip (:1732-1750)
-                sam_masks.append(np.where(np.logical_and(m, clip), 255, 0).astype(np.uint8))
-        except ModelError:
-            raise
-        except Exception as e:    # SAM failure -> YOLO masks -> rectangles (:1783-1813)
-            log_message(f"SAM2 segmentation failed: {e}. Falling back to YOLO segmentation masks.", always_print=True)
-            sam_masks = None
-    for k in simple:
-        source, orig = sources[k]
-        box = primary_boxes[k]
-        mask = None
-        if sam_masks is not None and sam_masks[k] is not None:
-            mask = sam_masks[k]
-        else:
-            mask = _fallback_to_yolo_mask(primary_results, orig, "binary")
-        if mask is None:
-            mask = _build_rect_mask_from_box(box, img_h, img_w)
-        x0, y0, x1, y1 = box.tolist()
-        detections.append({"bbox": (int(round(x0)), int(round(y0)), int(round(x1)), int(round(y1))),
-                           "confidence": float(primary_results.boxes.conf[orig]),
-                           "class": _class_name(primary_model, primary_results, orig), "sam_mask": mask})
-    return detections, text_free_boxes
+                clipped = np.logical_and(m, clip).astype(np.uint8) * 255 if clip.any() else np.asarray(m).astype(np.uint8) * 255
+                if i < synth_start:
+                    sam_masks[owner[i]] = clipped
+                else:
+                    synthetic_groups[i - synth_start]["parent_mask"] = clipped
+            log_message(f"Generated {len(raw)} primary masks with SAM 2.1", always_print=True)
+        detections = assemble(sam_masks)
+        cache.set_sam_masks(sam_key, detections)
+        return detections, text_free_boxes
+    except ModelError:
+        raise
+    except Exception as e:    # SAM failure -> YOLO masks -> rectangles (:1783-1813)
+        log_message(f"SAM 2.1 segmentation failed: {e}. Falling back to YOLO segmentation masks.", always_print=True)
+        for sg in synthetic_groups:
+            sg["parent_mask"] = None
+        return assemble(None), text_free_boxes
 
 
 # ---- device-resident fast path used by the batch pipeline / bench -------------------------------------------------------
@@ -240,6 +409,7 @@ def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.
     original-pixel boxes) bypasses the detector output (ground-truth boxes for stage-level parity runs).  The SAM masks
     live in the segmenter's static output buffer, which the next page overwrites: pass `own_masks=True` to get a copy
     when detections of several pages must stay alive together."""
+    from mangatranslator_b200.conjoined import detect_overlapping_primaries, split_conjoined_device, union_box
     from mangatranslator_b200.preproc import letterbox_device
     mm = get_model_manager()
     yolo = mm.load_yolo_speech_bubble(None)
@@ -260,24 +430,47 @@ def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.
             boxes = np.asarray(injected_boxes[pi], np.float32).reshape(-1, 4)
             confs = np.full((boxes.shape[0],), 0.9, np.float32)
         dets: List[Dict[str, Any]] = []
+        # overlapping primaries form synthetic conjoined groups (:1596-1619): SAM is prompted with the group's union box
+        # and the parent mask is divided between the members on the device
+        tb = torch.from_numpy(boxes)
+        simple, groups = list(range(boxes.shape[0])), []
+        if boxes.shape[0] > 1:
+            groups, simple = detect_overlapping_primaries(tb, simple)
+        prompts = [tb[i] for i in simple] + [union_box(tb[g]) for g in groups]
         masks = None
-        if sam is not None and boxes.shape[0]:
-            rgb = page[:, :, [2, 1, 0]].contiguous() if page.shape[2] == 3 else page[:, :, [2, 1, 0]].contiguous()
+        if sam is not None and prompts:
+            rgb = page[:, :, [2, 1, 0]].contiguous()
             enc = sam.encode(rgb)
-            masks = sam.decode(enc, torch.from_numpy(boxes), (h, w))
+            masks = sam.decode(enc, torch.stack(prompts), (h, w))
             if own_masks:
                 masks = masks.clone()
-        for k in range(boxes.shape[0]):
-            x0, y0, x1, y1 = [float(v) for v in boxes[k]]
+
+        def clip_rect(b):
+            x0, y0, x1, y1 = [float(v) for v in b]
             bx0, by0 = int(np.floor(max(0, min(x0, w)))), int(np.floor(max(0, min(y0, h))))
             bx1, by1 = int(np.ceil(max(0, min(x1, w)))), int(np.ceil(max(0, min(y1, h))))
+            return bx0, by0, bx1, by1
+
+        def prompt_mask(n):
             if masks is not None:
-                m = masks[k]
-            else:
-                m = torch.zeros((h, w), dtype=torch.uint8, device=page.device)
-                m[by0:by1, bx0:bx1] = 255
-            dets.append({"bbox": (int(round(x0)), int(round(y0)), int(round(x1)), int(round(y1))),
-                         "confidence": float(confs[k]), "class": "speech_bubble", "sam_mask": m,
+                return masks[n]
+            bx0, by0, bx1, by1 = clip_rect(prompts[n])
+            m = torch.zeros((h, w), dtype=torch.uint8, device=page.device)
+            m[by0:by1, bx0:bx1] = 255
+            return m
+
+        for n, k in enumerate(simple):
+            bx0, by0, bx1, by1 = clip_rect(boxes[k])
+            dets.append({"bbox": tuple(int(round(float(v))) for v in boxes[k]), "confidence": float(confs[k]),
+                         "class": "speech_bubble", "sam_mask": prompt_mask(n),
                          "mask_bbox": (bx0, by0, max(bx1, bx0 + 1), max(by1, by0 + 1))})
+        for gi, members in enumerate(groups):
+            px0, py0, px1, py1 = clip_rect(prompts[len(simple) + gi])
+            window = (px0, py0, max(px1, px0 + 1), max(py1, py0 + 1))
+            child_masks, plan = split_conjoined_device(prompt_mask(len(simple) + gi), tb[members], window=window)
+            for n, k in enumerate(members):
+                dets.append({"bbox": plan.bboxes[n], "confidence": float(confs[k]), "class": "speech_bubble",
+                             "sam_mask": child_masks[n], "mask_bbox": window,
+                             "conjoined_neighbor_bboxes": [b for m, b in enumerate(plan.bboxes) if m != n]})
         out.append(dets)
     return out

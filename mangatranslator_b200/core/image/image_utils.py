@@ -49,7 +49,7 @@ def tensor_to_image(tensor: torch.Tensor) -> Image.Image:
 def _page_to_device(image: Image.Image, device: torch.device) -> torch.Tensor:
     if image.mode != "RGB":
         image = image.convert("RGB")                  # alpha is dropped like image_to_tensor does (:353-354)
-    return torch.from_numpy(np.ascontiguousarray(np.asarray(image))).to(device)
+    return torch.from_numpy(np.array(image)).to(device)
 
 
 def _device_to_pil(page: torch.Tensor) -> Image.Image:

