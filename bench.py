@@ -165,6 +165,10 @@ def measure_dominant_kernel(pipe, page_dev, peaks):
                 peak_source=peaks["source"] + " bf16_tflops_sustained",
                 upscale_launch_ms_by_kind={k: round(v, 3) for k, v in by_kind.items()},
                 conv1_avg_ms=float(np.mean(durs[0::2])), conv2_avg_ms=float(np.mean(durs[1::2])),
+                issued=dict(tflops=4.0 * ach, frac=4.0 * ach / peaks["bf16_sustained"],
+                            note="bf16 MMA FLOPs the kernel actually issues (4 products per fp32-grade product; 3 is the "
+                                 "minimum for bf16 hi/lo operands, the 4th comes with the 128-row MMA granularity): the tensor "
+                                 "pipe is saturated, `frac` above is bounded at 1/4 by the formulation"),
                 note="algorithmic FLOPs (2*MAC of the fp32-grade conv); the channel-major bf16x3 kernel issues 4x that in "
                      "bf16 MMAs ([W_hi;W_lo] rows against the hi and the lo activation plane)")
 

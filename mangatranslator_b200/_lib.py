@@ -80,3 +80,21 @@ def stream_ptr() -> int:
 
 def launch_count() -> int:
     return int(lib().mtb_launch_count())
+
+
+# ---- one device section at a time --------------------------------------------------------------------------------
+# The reference's batch mode runs several page threads against the same model objects (core/pipeline.py:2470); the
+# B200 models keep static activation buffers and CUDA graphs per input size, so their stage functions serialise on
+# this re-entrant lock (the GPU executes one page at a time anyway; host-side work of other threads still overlaps).
+import functools
+import threading
+
+device_section = threading.RLock()
+
+
+def serialized(fn):
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        with device_section:
+            return fn(*args, **kwargs)
+    return wrapper

@@ -19,6 +19,7 @@ from mangatranslator_b200 import clean_host as H
 from mangatranslator_b200.clean_engine import STATUS_NAMES, clean_batch
 from mangatranslator_b200.utils.exceptions import CleaningError, ImageProcessingError, ValidationError
 from mangatranslator_b200.utils.logging import log_message
+from mangatranslator_b200._lib import serialized
 
 GRAYSCALE_MIDPOINT = 128
 MIN_CONTOUR_AREA = H.MIN_CONTOUR_AREA
@@ -90,6 +91,7 @@ def _result_to_dict(res: H.CleanResult, det: Dict[str, Any], base_mask, mask, is
     }
 
 
+@serialized
 def clean_pages_device(pages: List[torch.Tensor], detections: List[List[Dict[str, Any]]], *,
                        thresholding_value: int = 200, use_otsu_threshold: bool = False, roi_shrink_px: float = 5,
                        processing_scale: float = 1.0, in_place: bool = False):
@@ -99,6 +101,7 @@ def clean_pages_device(pages: List[torch.Tensor], detections: List[List[Dict[str
     return clean_batch(pages, detections, params, in_place=in_place)
 
 
+@serialized
 def clean_speech_bubbles(
     image_input: Union[str, Path, Image.Image],
     model_path=None,
@@ -193,6 +196,7 @@ def clean_speech_bubbles(
         raise CleaningError(f"Error cleaning speech bubbles: {str(e)}")
 
 
+@serialized
 def retry_cleaning_with_otsu(image_bgr: np.ndarray, bubble_info: dict, thresholding_value: int, roi_shrink_px: int,
                              processing_scale: float = 1.0, verbose: bool = False,
                              classify_colored: bool = False) -> Optional[dict]:
@@ -222,6 +226,7 @@ def retry_cleaning_with_otsu(image_bgr: np.ndarray, bubble_info: dict, threshold
         return None
 
 
+@serialized
 def process_single_bubble(base_mask, img_gray, img_height, img_width, thresholding_value, use_otsu_threshold,
                           roi_shrink_px, verbose, detection_bbox=None, is_sam=False, dilation_kernel=None,
                           constraint_erosion_kernel=None, min_contour_area: float = MIN_CONTOUR_AREA,

@@ -28,6 +28,7 @@ from mangatranslator_b200.core.device import get_best_device
 from mangatranslator_b200.core.ml.model_manager import ModelType, get_model_manager
 from mangatranslator_b200.utils.exceptions import ImageProcessingError, ModelError
 from mangatranslator_b200.utils.logging import log_message
+from mangatranslator_b200._lib import serialized
 
 IOA_THRESHOLD = 0.50
 SAM_MASK_THRESHOLD = 0.5
@@ -263,6 +264,7 @@ def _build_segmentation_detections(primary_boxes, grouping_boxes, sources, prima
     return dets
 
 
+@serialized
 def detect_speech_bubbles(image_path: Path, model_path, confidence=0.6, verbose=False, device=None,
                           seg_model: str = "yolo", conjoined_detection: bool = True, conjoined_confidence=0.35,
                           image_override: Optional[Image.Image] = None, osb_enabled: bool = False,
@@ -399,6 +401,7 @@ def detect_speech_bubbles(image_path: Path, model_path, confidence=0.6, verbose=
 
 
 # ---- device-resident fast path used by the batch pipeline / bench -------------------------------------------------------
+@serialized
 def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.6, imgsz: int = 1600,
                         seg_model: str = "sam2", injected_boxes: Optional[List[np.ndarray]] = None,
                         own_masks: bool = False):

@@ -18,6 +18,7 @@ from mangatranslator_b200.core.caching import get_cache
 from mangatranslator_b200.core.ml.model_manager import get_model_manager
 from mangatranslator_b200.utils.exceptions import ImageProcessingError
 from mangatranslator_b200.utils.logging import log_message
+from mangatranslator_b200._lib import serialized
 
 
 def pil_to_cv2(pil_image: Image.Image) -> np.ndarray:
@@ -76,6 +77,7 @@ def resize_device(page: torch.Tensor, width: int, height: int) -> torch.Tensor:
     return resize_lanczos_device(page.contiguous(), height, width)
 
 
+@serialized
 def _upscale_image(model, image: Image.Image, device: torch.device) -> Image.Image:
     """One 2x pass.  B200 models take the uint8 page directly; any other callable gets the reference's tensor contract."""
     if hasattr(model, "upscale_u8"):
@@ -84,6 +86,7 @@ def _upscale_image(model, image: Image.Image, device: torch.device) -> Image.Ima
         return tensor_to_image(model(image_to_tensor(image, device)))
 
 
+@serialized
 def upscale_image_to_dimension(model, image: Image.Image, target: int, device: torch.device, mode: str = "max",
                                model_type: str = "model", verbose: bool = False) -> Image.Image:
     """Repeat 2x passes until max(w,h) (or min for mode='min') reaches `target` (reference :377-500)."""
@@ -110,6 +113,7 @@ def upscale_image_to_dimension(model, image: Image.Image, target: int, device: t
     return out
 
 
+@serialized
 def upscale_image(image: Image.Image, factor: float, model_type: str = "model", verbose: bool = False) -> Image.Image:
     """Reference :503-548: 2x passes until the larger side reaches the target, then an exact-size LANCZOS resample.  With
     the B200 upscaler the page is uploaded once and both steps run on the device."""
@@ -135,6 +139,7 @@ def upscale_image(image: Image.Image, factor: float, model_type: str = "model", 
     return result
 
 
+@serialized
 def _resize_pil(image: Image.Image, new_width: int, new_height: int) -> Image.Image:
     """`image.resize(..., Image.LANCZOS)` through the device kernel.  The hot path only resamples RGB pages and crops
     (alpha is dropped before the upscaler, :353-354); other modes are refused rather than handed to a CPU library."""
@@ -172,6 +177,7 @@ def resize_to_min_side(image: Image.Image, min_side: int, verbose: bool = False)
     return image if g is None else _resize_pil(image, *g)
 
 
+@serialized
 def process_bubble_image_cached(bubble_image_pil: Image.Image, upscale_model, device: torch.device,
                                 target_min_side: int = 200, mode: str = "min", model_type: str = "model",
                                 verbose: bool = False) -> Image.Image:
@@ -206,6 +212,7 @@ def process_bubble_crop_device(crop: torch.Tensor, upscale_model, target_min_sid
     return up.clone() if g is None else resize_device(up, *g)
 
 
+@serialized
 def process_page_bubbles_device(page_rgb: torch.Tensor, bboxes, upscale_model, target_min_side: int = 200,
                                 mode: str = "min") -> list:
     """All bubble crops of one device-resident page (the loop of core/services/translation.py:2097-2258 around

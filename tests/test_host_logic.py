@@ -128,3 +128,28 @@ def test_drop_in_aliases_share_singletons():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_cache_keys_are_bound_to_the_image_object():
+    """Keys compare by image identity and keep the image alive, so a recycled id() can never alias another image's
+    entry (many short-lived bubble crops go through process_bubble_image_cached); the store is a bounded LRU."""
+    import gc
+    from PIL import Image
+    from mangatranslator_b200.core import caching
+    c = caching.UnifiedCache()
+    a = Image.new("RGB", (4, 4), (1, 2, 3))
+    k = c.get_bubble_processing_cache_key(a, 200, "min", "model_lite")
+    c.set_upscaled_image(k, "result-a")
+    assert c.get_upscaled_image(c.get_bubble_processing_cache_key(a, 200, "min", "model_lite")) == "result-a"
+    assert c.get_upscaled_image(c.get_bubble_processing_cache_key(a, 201, "min", "model_lite")) is None
+    ida = id(a)
+    del a, k
+    gc.collect()
+    for _ in range(200):                       # whatever object lands on the old address, it is not the cached image
+        b = Image.new("RGB", (4, 4), (9, 9, 9))
+        assert c.get_upscaled_image(c.get_bubble_processing_cache_key(b, 200, "min", "model_lite")) is None
+        if id(b) == ida:
+            break
+    for i in range(caching.MAX_ENTRIES + 10):
+        c.set_upscaled_image(c.get_upscale_cache_key(Image.new("RGB", (2, 2)), 2.0, "model"), i)
+    assert len(c._store) == caching.MAX_ENTRIES

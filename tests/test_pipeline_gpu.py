@@ -128,3 +128,43 @@ def test_reference_shaped_stage_functions(small_models, tmp_path):
         assert out.size == (2 * w, 2 * h) and (tmp_path / "out.png").exists()
     finally:
         mm.models[ModelType.YOLO_SPEECH_BUBBLE] = real
+
+
+def test_stage_functions_are_safe_under_page_threads(small_models):
+    """The reference's batch mode calls the same model objects from several page threads (core/pipeline.py:2470); the
+    B200 models keep static buffers per input size, so the stage functions serialise on one device section: concurrent
+    callers must get exactly what sequential callers get."""
+    import threading
+    from mangatranslator_b200 import synth
+    from mangatranslator_b200.core.caching import get_cache
+    from mangatranslator_b200.core.image.cleaning import clean_speech_bubbles
+    from mangatranslator_b200.core.image.image_utils import upscale_image
+    pages = [synth.make_page(40 + i, 320 + 32 * (i % 2), 288, n_bubbles=3) for i in range(4)]
+
+    def work(pg):
+        pil = Image.fromarray(pg.image_rgb)
+        cleaned, info = clean_speech_bubbles(pil, "x.pt", pre_computed_detections=synth.detections_from_page(pg),
+                                             processing_scale=1.0)
+        get_cache().clear()
+        up = upscale_image(Image.fromarray(np.ascontiguousarray(cleaned[:, :, ::-1])), 2.0, model_type="model")
+        return cleaned, np.asarray(up), len(info)
+
+    expected = [work(p) for p in pages]
+    got = [None] * len(pages)
+    errors = []
+
+    def runner(i):
+        try:
+            for _ in range(3):
+                got[i] = work(pages[i])
+        except Exception as e:                                   # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=runner, args=(i,)) for i in range(len(pages))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for (c0, u0, n0), (c1, u1, n1) in zip(expected, got):
+        assert n0 == n1 and np.array_equal(c0, c1) and np.array_equal(u0, u1)
