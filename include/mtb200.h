@@ -241,6 +241,19 @@ int mtb_split_conjoined(const uint8_t* parent, int H, int W, int K, const int* r
                         const int* window, int n_pairs, const mtb_split_pair* pairs, uint8_t* out, void* workspace,
                         long long workspace_bytes, void* stream);
 
+/* ---- RT-DETRv2 glue (core/ml/rtdetr_adapter.py:61-113 -> transformers RTDetrV2ForObjectDetection; secondary detector of
+ * core/image/detection.py:1392-1548) --------------------------------------------------------------------------
+ * maxpool2d   : ResNet stem MaxPool2d(k, stride, pad) on NHWC planes (padding never wins)
+ * deform_attn : multi_scale_deformable_attention_v2 (method "default") for one image: value bf16 planes [tokens][ctotal]
+ *               (levels concatenated; level l = H_l x W_l rows from row start_l), offsets fp32 [Q][off_stride] laid out
+ *               (head, level*point, xy), logits fp32 [Q][logit_stride] laid out (head, level*point), ref fp32 [Q][4]
+ *               (cx, cy, w, h in [0,1]); out bf16 planes [Q][ctotal].  Head dim must be 32. */
+int mtb_maxpool2d(const void* x, void* y, int N, int H, int W, int C, int k, int stride, int pad, int planes, void* stream);
+int mtb_deform_attn(const void* value, long long value_plane_stride, int planes, int ctotal, int heads, int hd, int n_levels,
+                    const int* level_h_w_start /* host [n_levels][3] */, int n_points, const float* offsets, int off_stride,
+                    const float* logits, int logit_stride, const float* ref_cxcywh, int Q, float offset_scale, void* out,
+                    long long out_plane_stride, void* stream);
+
 /* ---- input pre-processing, bit-exact with the CPU libraries the reference calls ----------------------------
  * letterbox_u8 : ultralytics LetterBox (cv2.resize INTER_LINEAR on uint8 + 114 border + BGR->RGB), detection.py:1338-1345
  * resize_aa_u8 : Sam2ImageProcessorFast resize (torchvision bilinear, antialias=True, uint8), detection.py:494-495

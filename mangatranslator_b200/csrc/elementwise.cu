@@ -160,7 +160,8 @@ rcan_gate_kernel(const float* __restrict__ sums, int parts, const float* __restr
                  const float* __restrict__ bconv, const float* __restrict__ w1, const float* __restrict__ b1,
                  const float* __restrict__ w2, const float* __restrict__ b2, int R, float* __restrict__ scale) {
   constexpr int C = 64;
-  __shared__ float red[32][C];                      // per-warp partials (border lines) / per-group partials (total)
+  __shared__ float red[32][C];                      // per-warp partials (border lines) / quarter sums (total)
+  __shared__ float wide[64][C];                     // per-row-group partials of the two partial-row reductions
   __shared__ float tot[C], line[4][C], corner[4][C], shifted[9][C], mean[C], hid[64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // second conv's weights for this thread's slice of the mean (16 threads per output channel, 36 terms each): issued
@@ -219,30 +220,75 @@ rcan_gate_kernel(const float* __restrict__ sums, int parts, const float* __restr
     corner[b][c] = cv;
   }
   __syncthreads();
-  {  // total per channel from the conv epilogue's partial rows (fixed order -> deterministic)
-    const int c = tid & 63, g = tid >> 6;
-    float acc = 0.f;
-    for (int p = g; p < parts; p += 16) acc += sums[static_cast<long long>(p) * C + c];
-    red[g][c] = acc;
+  // Totals and border lines from the conv epilogue's partial rows.  Both reductions walk a few hundred L2-resident rows;
+  // a plain `acc += row[p]` loop serialises one L2 round trip per row (the 148-iteration border loop alone cost ~30 us),
+  // so every thread keeps four independent 16-byte loads in flight and the groups are folded through shared memory in a
+  // fixed order (deterministic).
+  {  // total per channel: 16 float4 lanes x 64 row groups
+    const int c4 = tid & 15, g = tid >> 4;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    const float4* src = reinterpret_cast<const float4*>(sums) + c4;
+    int p = g;
+    for (; p + 192 < parts; p += 256) {
+      const float4 v0 = src[static_cast<long long>(p) * 16], v1 = src[static_cast<long long>(p + 64) * 16];
+      const float4 v2 = src[static_cast<long long>(p + 128) * 16], v3 = src[static_cast<long long>(p + 192) * 16];
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+      a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+      a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+      a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+    }
+    for (; p < parts; p += 64) {
+      const float4 v0 = src[static_cast<long long>(p) * 16];
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    }
+    float* dst = &wide[g][c4 * 4];
+    dst[0] = (a0.x + a1.x) + (a2.x + a3.x);
+    dst[1] = (a0.y + a1.y) + (a2.y + a3.y);
+    dst[2] = (a0.z + a1.z) + (a2.z + a3.z);
+    dst[3] = (a0.w + a1.w) + (a2.w + a3.w);
   }
   __syncthreads();
-  if (tid < C) {
+  if (tid < 4 * C) {   // 64 groups -> 4 quarter sums per channel -> total
+    const int c = tid & 63, qd = tid >> 6;
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) t += red[k][tid];
-    tot[tid] = t;
+    for (int k = 0; k < 16; ++k) t += wide[qd * 16 + k][c];
+    red[qd][c] = t;
   }
   __syncthreads();
+  if (tid < C) tot[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+  __syncthreads();
   if (border != nullptr) {
-    // the four border lines arrive as partial rows from the same conv epilogue: 4 lines x 64 channels x 4 row groups
-    const int c = tid & 63, b = (tid >> 6) & 3, g = tid >> 8;
-    float acc = 0.f;
-    for (int p = g; p < parts; p += 4) acc += border[(static_cast<long long>(p) * 4 + b) * C + c];
-    red[g * 4 + b][c] = acc;
+    // the four border lines arrive as partial rows from the same conv epilogue: [parts][4 lines][64 channels];
+    // 16 float4 lanes x 4 lines x 16 row groups
+    const int c4 = tid & 15, b = (tid >> 4) & 3, g = tid >> 6;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    const float4* src = reinterpret_cast<const float4*>(border) + b * 16 + c4;
+    int p = g;
+    for (; p + 48 < parts; p += 64) {
+      const float4 v0 = src[static_cast<long long>(p) * 64], v1 = src[static_cast<long long>(p + 16) * 64];
+      const float4 v2 = src[static_cast<long long>(p + 32) * 64], v3 = src[static_cast<long long>(p + 48) * 64];
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+      a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+      a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+      a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+    }
+    for (; p < parts; p += 16) {
+      const float4 v0 = src[static_cast<long long>(p) * 64];
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    }
+    float* dst = &wide[g * 4 + b][c4 * 4];
+    dst[0] = (a0.x + a1.x) + (a2.x + a3.x);
+    dst[1] = (a0.y + a1.y) + (a2.y + a3.y);
+    dst[2] = (a0.z + a1.z) + (a2.z + a3.z);
+    dst[3] = (a0.w + a1.w) + (a2.w + a3.w);
     __syncthreads();
     if (tid < 4 * C) {
       const int b2 = tid >> 6, c2 = tid & 63;
-      line[b2][c2] = red[b2][c2] + red[4 + b2][c2] + red[8 + b2][c2] + red[12 + b2][c2];
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t += wide[k * 4 + b2][c2];
+      line[b2][c2] = t;
     }
     __syncthreads();
   }
