@@ -10,9 +10,9 @@ B200-native objects everything between the page upload and the final masks stays
 Conjoined bubbles (:345-472, :582-1035, :1075-1260): primaries that overlap each other are grouped into synthetic
 conjoined bubbles on every page (:1596-1619), SAM segments the group's union box, and the parent mask is divided between
 the members by `mtb_split_conjoined` (mangatranslator_b200/conjoined.py holds the box geometry).  The same code serves
-conjoined parents found by a secondary detector when one is present in the ModelManager; the RT-DETRv2 network itself
-is out of scope: `load_rtdetr_conjoined_bubble` raises and the failure is swallowed exactly like the
-reference does at :1541-1548.  Also out of scope: OSB-text verification, SAM3, panel detection.
+conjoined parents found by the secondary RT-DETRv2 detector (mangatranslator_b200/rtdetr.py, loaded by
+`load_rtdetr_conjoined_bubble` when its checkpoint exists; otherwise the load failure is swallowed exactly like the
+reference does at :1541-1548 and the primaries are kept).  Out of scope: OSB-text verification, SAM3, panel detection.
 """
 from __future__ import annotations
 
@@ -143,10 +143,11 @@ def _class_name(model, results, idx) -> str:
 
 
 def _secondary_detections(mm, image_cv, primary_boxes, sources, conjoined_confidence, device, osb_enabled, verbose):
-    """The RT-DETR branch of the reference (:1392-1548) for a secondary detector present in the ModelManager (this build
-    ships none: `load_rtdetr_conjoined_bubble` raises and the caller keeps the primaries, like the reference does when
-    the model cannot be loaded).  Returns (primary_boxes, sources, secondary_boxes, secondary_sources, secondary_results,
-    text_free_boxes)."""
+    """The RT-DETR branch of the reference (:1392-1548): run the secondary detector (mangatranslator_b200.rtdetr.RtDetrB200,
+    or whatever duck-typed detector sits in the ModelManager slot), drop nested secondary boxes, route `text_free` boxes
+    aside, add bubbles the primary detector missed, remove primaries that are really free text.  A load failure propagates
+    to the caller, which keeps the primaries like the reference does.  Returns (primary_boxes, sources, secondary_boxes,
+    secondary_sources, secondary_results, text_free_boxes)."""
     text_free: List[List[float]] = []
     model = mm.load_rtdetr_conjoined_bubble()
     results = model(image_cv, conf=conjoined_confidence, device=device, verbose=False, imgsz=640)[0]
@@ -404,15 +405,18 @@ def detect_speech_bubbles(image_path: Path, model_path, confidence=0.6, verbose=
 @serialized
 def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.6, imgsz: int = 1600,
                         seg_model: str = "sam2", injected_boxes: Optional[List[np.ndarray]] = None,
-                        own_masks: bool = False):
+                        own_masks: bool = False, conjoined_detection: bool = False, conjoined_confidence: float = 0.35):
     """pages_bgr: device uint8 HxWx3 (BGR, like the cleaning stage wants).  Per page: letterbox -> YOLO graph -> decode
-    + NMS + scale_boxes + reference dedup/containment (all on device, one small D2H of the box table) -> SAM 2.1
-    masks on device.  Returns per page a list of detection dicts whose `sam_mask` is a DEVICE uint8 tensor and which
-    carry `mask_bbox` so the cleaning stage needs no further host work.  `injected_boxes` (per page [P,4] float32
-    original-pixel boxes) bypasses the detector output (ground-truth boxes for stage-level parity runs).  The SAM masks
-    live in the segmenter's static output buffer, which the next page overwrites: pass `own_masks=True` to get a copy
-    when detections of several pages must stay alive together."""
-    from mangatranslator_b200.conjoined import detect_overlapping_primaries, split_conjoined_device, union_box
+    + NMS + scale_boxes + reference dedup/containment (all on device, one small D2H of the box table) -> [secondary
+    RT-DETR detections merged like :1392-1548 when `conjoined_detection`] -> grouping (conjoined parents, synthetic
+    groups of overlapping primaries) -> SAM 2.1 masks on device -> parent masks divided on device.  Returns per page a
+    list of detection dicts in the reference's order (simple, conjoined children, synthetic children) whose `sam_mask`
+    is a DEVICE uint8 tensor and which carry `mask_bbox` so the cleaning stage needs no further host work.
+    `injected_boxes` (per page [P,4] float32 original-pixel boxes) bypasses the primary detector's output (ground-truth
+    boxes for stage-level parity runs).  The SAM masks live in the segmenter's static output buffer, which the next
+    page overwrites: pass `own_masks=True` to get a copy when detections of several pages must stay alive together."""
+    from mangatranslator_b200.conjoined import (categorize_detections, detect_overlapping_primaries, split_conjoined_device,
+                                               union_box)
     from mangatranslator_b200.preproc import letterbox_device
     mm = get_model_manager()
     yolo = mm.load_yolo_speech_bubble(None)
@@ -428,18 +432,48 @@ def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.
         n_final = int(cnt[1].item())                                   # the one host sync of the detect stage
         rows = det[final_idx[:n_final].long()].cpu().numpy() if n_final else np.zeros((0, 8), np.float32)
         boxes = rows[:, :4].astype(np.float32)
-        confs = rows[:, 4]
+        confs = rows[:, 4].astype(np.float32)
         if injected_boxes is not None:
             boxes = np.asarray(injected_boxes[pi], np.float32).reshape(-1, 4)
             confs = np.full((boxes.shape[0],), 0.9, np.float32)
-        dets: List[Dict[str, Any]] = []
-        # overlapping primaries form synthetic conjoined groups (:1596-1619): SAM is prompted with the group's union box
-        # and the parent mask is divided between the members on the device
         tb = torch.from_numpy(boxes)
-        simple, groups = list(range(boxes.shape[0])), []
-        if boxes.shape[0] > 1:
+        sources = [("primary", i) for i in range(len(tb))]
+        sec, sec_src, sec_conf, sec_names, sec_cls = torch.zeros((0, 4)), [], None, None, None
+        if conjoined_detection and len(tb):
+            try:
+                tb, sources, sec, sec_src, sec_res, _free = _secondary_detections(mm, page, tb, sources, conjoined_confidence,
+                                                                                 page.device, False, False)
+                tb, sec = tb.detach().float().cpu(), sec.detach().float().cpu()
+                sec_conf, sec_cls = sec_res.boxes.conf.detach().float().cpu(), sec_res.boxes.cls.detach().cpu()
+                sec_names = getattr(sec_res, "names", None)
+            except Exception as e:                                     # like the reference: keep the primaries (:1541-1548)
+                log_message(f"Warning: Could not load/run secondary RT-DETR model: {e}. "
+                            "Proceeding without conjoined/fallback detection.", verbose=False)
+                sec, sec_src = torch.zeros((0, 4)), []
+
+        def meta(src):
+            if src[0] == "primary":
+                return float(confs[src[1]]), "speech_bubble"
+            cid = int(sec_cls[src[1]])
+            return float(sec_conf[src[1]]), (sec_names.get(cid, "speech_bubble") if sec_names is not None else "speech_bubble")
+
+        dets: List[Dict[str, Any]] = []
+        if len(tb) == 0:
+            out.append(dets)
+            continue
+        # grouping: conjoined parents from the secondary boxes, then synthetic groups of overlapping primaries
+        # (:1596-1619, formed with or without a secondary detector); SAM is prompted with each group's union box
+        conjoined, simple = [], list(range(len(tb)))
+        if len(sec) > 0:
+            conjoined, simple = categorize_detections(tb, sec, IOA_THRESHOLD)
+        groups = []
+        if len(simple) > 1:
             groups, simple = detect_overlapping_primaries(tb, simple)
-        prompts = [tb[i] for i in simple] + [union_box(tb[g]) for g in groups]
+        group_boxes = [sec[s_idx] for _, s_idx in conjoined] + [tb[m] for m in groups]
+        group_srcs = [[sec_src[s] for s in s_idx] for _, s_idx in conjoined] + [[sources[m] for m in ms] for ms in groups]
+        parents = [union_box(torch.cat([tb[p].unsqueeze(0), sec[s_idx]], 0)) for p, s_idx in conjoined] + \
+                  [union_box(tb[m]) for m in groups]
+        prompts = [tb[i] for i in simple] + parents
         masks = None
         if sam is not None and prompts:
             rgb = page[:, :, [2, 1, 0]].contiguous()
@@ -463,17 +497,18 @@ def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.
             return m
 
         for n, k in enumerate(simple):
-            bx0, by0, bx1, by1 = clip_rect(boxes[k])
-            dets.append({"bbox": tuple(int(round(float(v))) for v in boxes[k]), "confidence": float(confs[k]),
-                         "class": "speech_bubble", "sam_mask": prompt_mask(n),
-                         "mask_bbox": (bx0, by0, max(bx1, bx0 + 1), max(by1, by0 + 1))})
-        for gi, members in enumerate(groups):
+            bx0, by0, bx1, by1 = clip_rect(tb[k])
+            conf, cls = meta(sources[k])
+            dets.append({"bbox": tuple(int(round(float(v))) for v in tb[k]), "confidence": conf, "class": cls,
+                         "sam_mask": prompt_mask(n), "mask_bbox": (bx0, by0, max(bx1, bx0 + 1), max(by1, by0 + 1))})
+        for gi, (gb, gs) in enumerate(zip(group_boxes, group_srcs)):
             px0, py0, px1, py1 = clip_rect(prompts[len(simple) + gi])
             window = (px0, py0, max(px1, px0 + 1), max(py1, py0 + 1))
-            child_masks, plan = split_conjoined_device(prompt_mask(len(simple) + gi), tb[members], window=window)
-            for n, k in enumerate(members):
-                dets.append({"bbox": plan.bboxes[n], "confidence": float(confs[k]), "class": "speech_bubble",
-                             "sam_mask": child_masks[n], "mask_bbox": window,
+            child_masks, plan = split_conjoined_device(prompt_mask(len(simple) + gi), gb, window=window)
+            for n, src in enumerate(gs):
+                conf, cls = meta(src)
+                dets.append({"bbox": plan.bboxes[n], "confidence": conf, "class": cls, "sam_mask": child_masks[n],
+                             "mask_bbox": window,
                              "conjoined_neighbor_bboxes": [b for m, b in enumerate(plan.bboxes) if m != n]})
         out.append(dets)
     return out

@@ -75,6 +75,7 @@ class ModelManager:
                 ModelType.UPSCALE_LITE: self.models_dir / "upscale" / "2x-AnimeSharpV4_Fast_RCAN_PU.safetensors",
                 ModelType.YOLO_SPEECH_BUBBLE: self.models_dir / "yolo" / "yolov8m_seg-speech-bubble.pt",
                 ModelType.YOLO_SPEECH_BUBBLE_2: self.models_dir / "yolo" / "manga109-segmentation-bubble.pt",
+                ModelType.RTDETR_CONJOINED_BUBBLE: self.models_dir / "rtdetr" / "comic-text-and-bubble-detector",
             }
             self.model_hf_repos: Dict[ModelType, str] = {
                 ModelType.SAM2: "facebook/sam2.1-hiera-large",
@@ -171,9 +172,28 @@ class ModelManager:
         raise ModelError(f"{what} is outside the B200 hot path of this build (SURVEY.md §8f)")
 
     def load_rtdetr_conjoined_bubble(self, verbose: bool = False):
-        if ModelType.RTDETR_CONJOINED_BUBBLE in self.models:
-            return self.models[ModelType.RTDETR_CONJOINED_BUBBLE]
-        self._out_of_scope("RT-DETRv2 conjoined-bubble detector")
+        """RT-DETRv2 conjoined / fallback bubble detector (reference :745-778 returns an RTDetrYOLOAdapter; the B200
+        object has the same call shape and `.names`)."""
+        with self._lock:
+            if ModelType.RTDETR_CONJOINED_BUBBLE in self.models:
+                return self.models[ModelType.RTDETR_CONJOINED_BUBBLE]
+            from mangatranslator_b200.rtdetr import RtDetrB200
+            dev = self._require_cuda()
+            log_message("Loading RT-DETR conjoined bubble detection model...", verbose=verbose)
+            # Unlike the primary detector, the secondary one is optional in the reference's flow (a load failure is
+            # swallowed, core/image/detection.py:1541-1548), and random boxes from seeded weights would be merged into the
+            # primaries as "missed bubbles": without a checkpoint it only loads when explicitly asked for.
+            ckpt = self.model_paths[ModelType.RTDETR_CONJOINED_BUBBLE]
+            if not ckpt.is_dir() and os.environ.get("MTB200_SYNTHETIC_RTDETR", "0") != "1":
+                raise ModelError(f"Failed to load RT-DETR conjoined model: no checkpoint at {ckpt} "
+                                 "(set MTB200_SYNTHETIC_RTDETR=1 for seeded synthetic weights)")
+            try:
+                cfg, sd = W.rtdetr_model_and_state(self.synthetic_seed)
+                model = RtDetrB200(sd, cfg, dev, precision=self.precision)
+            except Exception as e:
+                raise ModelError(f"Failed to load RT-DETR conjoined model: {e}") from e
+            self.models[ModelType.RTDETR_CONJOINED_BUBBLE] = model
+            return model
 
     def load_yolo_osbtext(self, token: str = "", verbose: bool = False):
         if ModelType.YOLO_OSBTEXT in self.models:

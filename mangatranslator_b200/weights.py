@@ -155,3 +155,52 @@ def sam2_model_and_state(seed: int = 0, variant: str = "tiny"):
         for mlp in m.mask_decoder.output_hypernetworks_mlps:   # default init gives |logit| ~ 1e-2: widen for real masks
             mlp.proj_out.weight.mul_(100.0)
     return cfg, m.state_dict()
+
+
+# ---- RT-DETRv2 (secondary conjoined / fallback bubble detector) ------------------------------------------------------
+RTDETR_NAMES = {0: "bubble", 1: "text_bubble", 2: "text_free"}     # classes the stage code looks for (detection.py:1430-1437)
+
+
+def rtdetr_model_and_state(seed: int = 0, **config_overrides):
+    """(config, state_dict) of `RTDetrV2ForObjectDetection`.  Like the SAM weights, initialisation and (when
+    `<models>/rtdetr/comic-text-and-bubble-detector` exists) loading go through the library the reference uses
+    (core/ml/model_manager.py:758-766); no forward pass happens here.  Synthetic weights: seeded default init, non-trivial
+    frozen-batch-norm statistics, and class biases lifted from the focal-loss prior so a few dozen queries pass conf 0.35."""
+    from transformers import RTDetrV2Config, RTDetrV2ForObjectDetection
+    d = models_dir()
+    ckpt = os.path.join(d, "rtdetr", "comic-text-and-bubble-detector") if d else None
+    if ckpt and os.path.isdir(ckpt):
+        m = RTDetrV2ForObjectDetection.from_pretrained(ckpt).eval()
+        return m.config, m.state_dict()
+    cfg = RTDetrV2Config(num_labels=len(RTDETR_NAMES), id2label=dict(RTDETR_NAMES),
+                         label2id={v: k for k, v in RTDETR_NAMES.items()}, **config_overrides)
+    torch.manual_seed(seed)
+    model = RTDetrV2ForObjectDetection(cfg).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for name, buf in model.named_buffers():
+            if name.endswith("running_mean"):
+                buf.copy_(torch.randn(buf.shape, generator=g) * 0.1)
+            elif name.endswith("running_var"):
+                buf.copy_(torch.rand(buf.shape, generator=g) * 0.5 + 0.75)
+        for name, p in model.named_parameters():
+            is_bn = "normalization." in name or ".norm." in name or ("input_proj" in name and ".1." in name)
+            if is_bn and name.endswith("weight"):
+                p.copy_(torch.rand(p.shape, generator=g) * 0.4 + 0.8)
+            elif is_bn and name.endswith("bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+        for head in list(model.class_embed) + [model.model.enc_score_head]:
+            head.bias.copy_(torch.tensor([-0.2, -1.0, -0.8]))
+            head.weight.mul_(3.0)
+        # A randomly initialised decoder gives all queries nearly the same class logits.  Calibrate the last class head on
+        # one seeded noise image (a CPU forward of the library model, synthetic weights only) so that ~20 % of the queries
+        # are "bubble" detections above conf 0.35, ~5 % "text_free", and no "text_bubble".
+        last = model.class_embed[-1]
+        last.weight.mul_(4.0)
+        probe = torch.rand((1, 3, 640, 640), generator=g)
+        logits = model(pixel_values=probe).logits[0]
+        thr = math.log(0.35 / 0.65)
+        for c, q in ((0, 0.80), (1, 1.0), (2, 0.95)):
+            cut = torch.quantile(logits[:, c], q).item() if q < 1.0 else logits[:, c].max().item() + 1.0
+            last.bias[c] -= cut - thr
+    return cfg, model.state_dict()
