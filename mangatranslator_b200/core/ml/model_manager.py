@@ -178,7 +178,6 @@ class ModelManager:
             if ModelType.RTDETR_CONJOINED_BUBBLE in self.models:
                 return self.models[ModelType.RTDETR_CONJOINED_BUBBLE]
             from mangatranslator_b200.rtdetr import RtDetrB200
-            dev = self._require_cuda()
             log_message("Loading RT-DETR conjoined bubble detection model...", verbose=verbose)
             # Unlike the primary detector, the secondary one is optional in the reference's flow (a load failure is
             # swallowed, core/image/detection.py:1541-1548), and random boxes from seeded weights would be merged into the
@@ -187,6 +186,7 @@ class ModelManager:
             if not ckpt.is_dir() and os.environ.get("MTB200_SYNTHETIC_RTDETR", "0") != "1":
                 raise ModelError(f"Failed to load RT-DETR conjoined model: no checkpoint at {ckpt} "
                                  "(set MTB200_SYNTHETIC_RTDETR=1 for seeded synthetic weights)")
+            dev = self._require_cuda()
             try:
                 cfg, sd = W.rtdetr_model_and_state(self.synthetic_seed)
                 model = RtDetrB200(sd, cfg, dev, precision=self.precision)

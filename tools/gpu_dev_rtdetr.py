@@ -29,3 +29,24 @@ for seed, (h, w) in ((3, (640, 640)), (4, (900, 620)), (2, (640, 640))):
     a = torch.tensor([c[0] for c in common]); b = torch.tensor([c[1] for c in common])
     print("  logits err", (logits.cpu()[a] - ref["logits"][b]).abs().max().item(), "boxes err", (boxes.cpu()[a] - ref["pred_boxes"][b]).abs().max().item(),
           "n det", len(ref["conf"]))
+# timing: eager first call vs graph replays
+import time
+x = torch.from_numpy(synth.make_page(7, 640, 640, n_bubbles=5).image_rgb).cuda()
+l0, b0 = [t.clone() for t in net.forward_u8(x)]
+for _ in range(3):
+    l1, b1 = net.forward_u8(x)
+torch.cuda.synchronize()
+print("graph == eager:", torch.equal(l0, l1), torch.equal(b0, b1))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    net.forward_u8(x)
+e1.record(); torch.cuda.synchronize()
+print("ms per image (graph):", e0.elapsed_time(e1) / 10)
+from mangatranslator_b200 import graphs
+graphs.ENABLED = False
+e0.record()
+for _ in range(5):
+    net.forward_u8(x)
+e1.record(); torch.cuda.synchronize()
+print("ms per image (eager):", e0.elapsed_time(e1) / 5)
