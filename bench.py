@@ -173,6 +173,56 @@ def measure_dominant_kernel(pipe, page_dev, peaks):
                      "bf16 MMAs ([W_hi;W_lo] rows against the hi and the lo activation plane)")
 
 
+def _time_ms(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def measure_side_stages(page_dev, dev, peaks):
+    """Stages of the path that are not part of the headline workload, timed on their own after the timed region (ms per
+    call on one 1536x1024 page): the secondary RT-DETRv2 detector, a conjoined-bubble split, the exact-size LANCZOS
+    resample of the upscaled page, and the per-bubble crop upscaling with the lite model."""
+    from mangatranslator_b200 import conjoined as Cj
+    from mangatranslator_b200 import weights as Wt
+    from mangatranslator_b200.core.image.image_utils import process_page_bubbles_device
+    from mangatranslator_b200.preproc import resize_lanczos_device
+    from mangatranslator_b200.rcan import RcanB200
+    from mangatranslator_b200.rtdetr import RtDetrB200
+    out = {}
+    try:
+        cfg, sd = Wt.rtdetr_model_and_state(0)
+        det = RtDetrB200(sd, cfg, dev)
+        out["rtdetr_secondary_detect_ms"] = round(_time_ms(lambda: det(page_dev, conf=0.35, imgsz=640)), 3)
+        del det
+        mask = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+        mask[300:720, 150:820] = 255
+        boxes = torch.tensor([[150.0, 300.0, 520.0, 700.0], [440.0, 320.0, 820.0, 720.0]])
+        out["conjoined_split_2_children_ms"] = round(_time_ms(lambda: Cj.split_conjoined_device(mask, boxes, window=(150, 300, 820, 720))), 3)
+        up = torch.randint(0, 256, (2 * H, 2 * W, 3), dtype=torch.uint8, device=dev)
+        ms = _time_ms(lambda: resize_lanczos_device(up, int(1.5 * H), int(1.5 * W)))
+        traffic = (2 * H * 2 * W * 3 + 2 * (2 * H) * int(1.5 * W) * 3 + int(1.5 * H) * int(1.5 * W) * 3) / 1e9
+        out["lanczos_3072x2048_to_2304x1536_ms"] = round(ms, 3)
+        out["lanczos_gbs"] = round(traffic / (ms * 1e-3), 1)
+        out["lanczos_hbm_frac"] = round(traffic / (ms * 1e-3) / peaks["hbm_gbs"], 4)
+        lite = RcanB200(Wt.rcan_state_dict(0, n_resgroups=4, n_resblocks=6, unshuffle=2), dev)
+        rgb = page_dev[:, :, [2, 1, 0]].contiguous()
+        crops = [(60 + 64 * i, 90 + 105 * i, 60 + 64 * i + 130 + 13 * i, 90 + 105 * i + 110 + 17 * i) for i in range(BUBBLES)]  # ragged
+        process_page_bubbles_device(rgb, crops, lite, 200, "min")        # builds the 12 ragged plans; next call captures graphs
+        out["bubble_crops_lite_12_ms"] = round(_time_ms(lambda: process_page_bubbles_device(rgb, crops, lite, 200, "min"), reps=3), 3)
+        del lite
+    except Exception as e:                       # side measurements must never take the headline line down
+        out["error"] = repr(e)[:200]
+    torch.cuda.empty_cache()
+    return out
+
+
 def stage_rooflines(stage, peaks, sam_variant):
     """Per-stage achieved rate against the measured peaks, from SURVEY.md section 8(d)'s algorithmic work per page:
     YOLOv8m-seg@1600x1088 468 GFLOP, SAM 2.1 encoder 207.3 (tiny) / 1621.9 (large) GFLOP, decoder 3.56 GFLOP x 12 boxes,
@@ -283,6 +333,7 @@ def run_ours(args, coord):
     del gd
     if coord.rank != 0:
         return
+    extras = measure_side_stages(devp[0], dev, peaks)
     roof = measure_dominant_kernel(pipe, devp[0], peaks)
     prof = os.path.join(ROOT, "profiles", "r01_halo_cm_ncu.json")
     if not os.path.exists(prof):
@@ -309,7 +360,7 @@ def run_ours(args, coord):
                          d2h_bytes_per_step=coord.world * args.batch * 4 * H * W * 3, ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches) * coord.world, clocks=clocks, roofline=roof,
                 stage_ms_per_page={k: round(v, 3) for k, v in stage.items()},
-                stage_roofline=stage_rooflines(stage, peaks, sam_variant))
+                stage_roofline=stage_rooflines(stage, peaks, sam_variant), side_stage_ms=extras)
     if base is not None:
         line["cpu_baseline"] = base
     print(json.dumps(line))

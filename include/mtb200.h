@@ -272,8 +272,11 @@ int mtb_resize_aa_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp /*
  * rounded to 22 bits, uint8 intermediate after the horizontal pass.  `tables_dev`: caller-owned scratch of
  * mtb_resize_lanczos_table_ints(...) ints; `tmp`: sh x ow x 3 (may be NULL when only one axis changes). */
 long long mtb_resize_lanczos_table_ints(int sh, int sw, int oh, int ow);
+/* fills `tables_dev` for one geometry (host-side coefficient generation + one staged H2D copy) */
+int mtb_resize_lanczos_tables(int sh, int sw, int oh, int ow, int* tables_dev, long long tables_ints, void* stream);
+/* tables_ready = 1: `tables_dev` already holds this geometry's tables (callers keep one scratch per geometry) */
 int mtb_resize_lanczos_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp, uint8_t* dst /* oh x ow x 3 */,
-                          int oh, int ow, int* tables_dev, long long tables_ints, void* stream);
+                          int oh, int ow, int* tables_dev, long long tables_ints, int tables_ready, void* stream);
 /* host-only: Pillow's 22-bit LANCZOS coefficient table of one axis (what resize_lanczos_u8 uploads); CPU tests */
 int mtb_lanczos_weights_host(int in_size, int out_size, int* start, int* len, int* weights, int ksize_cap, int* ksize);
 

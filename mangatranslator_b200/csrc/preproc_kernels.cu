@@ -79,7 +79,9 @@ short sat_short(int v) { return static_cast<short>(v < -32768 ? -32768 : (v > 32
 
 // separable antialiased resample of one axis: out[o] = clip8((half + sum_k w[o][k] * in[start[o] + k]) >> prec)
 // WT = short (ATen int16 tables) or int (Pillow's 22-bit tables; 255 * sum|w| stays below 2^31 by construction)
-template <typename WT>
+// WT_TRANSPOSED: the table is laid out [k][n_out] so that the threads of a warp (adjacent output samples of the
+// horizontal pass) read adjacent words; the vertical pass shares one table row per warp and keeps [n_out][k].
+template <typename WT, bool WT_TRANSPOSED = false>
 __global__ void resample_axis_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int out_h, int out_w,
                                      int in_w_stride /* pixels per src row */, int c_in, int c_out, int horizontal,
                                      const int* __restrict__ start, const int* __restrict__ len,
@@ -90,12 +92,13 @@ __global__ void resample_axis_kernel(const uint8_t* __restrict__ src, uint8_t* _
     const int oy = static_cast<int>(i / out_w), ox = static_cast<int>(i - static_cast<long long>(oy) * out_w);
     const int o = horizontal ? ox : oy;
     const int s0 = start[o], n = len[o];
-    const WT* w = wts + static_cast<long long>(o) * kmax;
+    const WT* w = WT_TRANSPOSED ? wts + o : wts + static_cast<long long>(o) * kmax;
+    const long long wstep = WT_TRANSPOSED ? (horizontal ? out_w : out_h) : 1;
     int acc[3] = {1 << (prec - 1), 1 << (prec - 1), 1 << (prec - 1)};
     for (int k = 0; k < n; ++k) {
       const uint8_t* px = horizontal ? src + (static_cast<long long>(oy) * in_w_stride + s0 + k) * c_in
                                      : src + (static_cast<long long>(s0 + k) * in_w_stride + ox) * c_in;
-      const int wk = w[k];
+      const int wk = w[k * wstep];
 #pragma unroll
       for (int c = 0; c < 3; ++c) acc[c] += wk * px[c];
     }
@@ -420,16 +423,12 @@ long long mtb_resize_lanczos_table_ints(int sh, int sw, int oh, int ow) {
   return 2LL * ow + 2LL * oh + ow * kx + oh * ky;
 }
 
-// PIL `Image.resize((ow, oh), Image.LANCZOS)` of a uint8 image (first 3 channels): horizontal pass into `tmp`
-// (sh x ow x 3, uint8 like Pillow's intermediate image), then vertical; a pass whose size does not change is skipped
-// as in ImagingResample.  `tables_dev` is caller-owned scratch of mtb_resize_lanczos_table_ints() ints.
-int mtb_resize_lanczos_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp, uint8_t* dst, int oh, int ow,
-                          int* tables_dev, long long tables_ints, void* stream) {
-  MTB_REQUIRE(src && dst && tables_dev && (sc == 3 || sc == 4) && sh > 0 && sw > 0 && oh > 0 && ow > 0,
-              "mtb_resize_lanczos_u8: bad arguments");
-  MTB_REQUIRE(tables_ints >= mtb_resize_lanczos_table_ints(sh, sw, oh, ow), "mtb_resize_lanczos_u8: table scratch too small");
-  MTB_REQUIRE(tmp || ow == sw || oh == sh, "mtb_resize_lanczos_u8: two passes need the intermediate buffer");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// Coefficient tables of one geometry, written into caller-owned device scratch (layout: h start/len, v start/len,
+// h weights TRANSPOSED [k][ow], v weights [oh][k]).  Computing them costs ~35k sin() calls for a page, so callers keep
+// the filled scratch per geometry and pass `tables_ready = 1` on later calls.
+int mtb_resize_lanczos_tables(int sh, int sw, int oh, int ow, int* tables_dev, long long tables_ints, void* stream) {
+  MTB_REQUIRE(tables_dev && sh > 0 && sw > 0 && oh > 0 && ow > 0, "mtb_resize_lanczos_tables: bad arguments");
+  MTB_REQUIRE(tables_ints >= mtb_resize_lanczos_table_ints(sh, sw, oh, ow), "mtb_resize_lanczos_tables: table scratch too small");
   std::vector<int> hs, hl, hw, vs, vl, vw;
   int hk = 0, vk = 0;
   lanczos_weights(sw, ow, hs, hl, hw, hk);
@@ -440,24 +439,46 @@ int mtb_resize_lanczos_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* t
   all.insert(all.end(), hl.begin(), hl.end());
   all.insert(all.end(), vs.begin(), vs.end());
   all.insert(all.end(), vl.begin(), vl.end());
-  all.insert(all.end(), hw.begin(), hw.end());
+  for (int k = 0; k < hk; ++k)
+    for (int o = 0; o < ow; ++o) all.push_back(hw[static_cast<size_t>(o) * hk + k]);
   all.insert(all.end(), vw.begin(), vw.end());
-  MTB_REQUIRE(static_cast<long long>(all.size()) <= tables_ints, "mtb_resize_lanczos_u8: table scratch too small");
+  MTB_REQUIRE(static_cast<long long>(all.size()) <= tables_ints, "mtb_resize_lanczos_tables: table scratch too small");
   // pageable source: the copy is staged before the call returns, so `all` may go out of scope
-  MTB_CUDA_OK(cudaMemcpyAsync(tables_dev, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  MTB_CUDA_OK(cudaMemcpyAsync(tables_dev, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice,
+                              static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// PIL `Image.resize((ow, oh), Image.LANCZOS)` of a uint8 image (first 3 channels): horizontal pass into `tmp`
+// (sh x ow x 3, uint8 like Pillow's intermediate image), then vertical; a pass whose size does not change is skipped
+// as in ImagingResample.  `tables_dev` is caller-owned scratch of mtb_resize_lanczos_table_ints() ints, filled here
+// unless `tables_ready` says a previous call (or mtb_resize_lanczos_tables) already did for this geometry.
+int mtb_resize_lanczos_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp, uint8_t* dst, int oh, int ow,
+                          int* tables_dev, long long tables_ints, int tables_ready, void* stream) {
+  MTB_REQUIRE(src && dst && tables_dev && (sc == 3 || sc == 4) && sh > 0 && sw > 0 && oh > 0 && ow > 0,
+              "mtb_resize_lanczos_u8: bad arguments");
+  MTB_REQUIRE(tables_ints >= mtb_resize_lanczos_table_ints(sh, sw, oh, ow), "mtb_resize_lanczos_u8: table scratch too small");
+  MTB_REQUIRE(tmp || ow == sw || oh == sh, "mtb_resize_lanczos_u8: two passes need the intermediate buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!tables_ready) {
+    const int rc = mtb_resize_lanczos_tables(sh, sw, oh, ow, tables_dev, tables_ints, stream);
+    if (rc != 0) return rc;
+  }
+  const double fx = sw > ow ? static_cast<double>(sw) / ow : 1.0, fy = sh > oh ? static_cast<double>(sh) / oh : 1.0;
+  const int hk = static_cast<int>(ceil(3.0 * fx)) * 2 + 1, vk = static_cast<int>(ceil(3.0 * fy)) * 2 + 1;
   const int* d_hs = tables_dev;
   const int* d_hl = d_hs + ow;
   const int* d_vs = d_hl + ow;
   const int* d_vl = d_vs + oh;
   const int* d_hw = d_vl + oh;
-  const int* d_vw = d_hw + hw.size();
+  const int* d_vw = d_hw + static_cast<size_t>(ow) * hk;
   const int grid = sm_count3() * 8;
   const uint8_t* cur = src;
   int cur_w = sw, cur_c = sc;
   const bool need_h = ow != sw, need_v = oh != sh;
   if (need_h) {
     uint8_t* out = need_v ? tmp : dst;
-    resample_axis_kernel<int><<<grid, 256, 0, st>>>(cur, out, sh, ow, sw, sc, 3, 1, d_hs, d_hl, d_hw, hk, kPilPrecisionBits);
+    resample_axis_kernel<int, true><<<grid, 256, 0, st>>>(cur, out, sh, ow, sw, sc, 3, 1, d_hs, d_hl, d_hw, hk, kPilPrecisionBits);
     MTB_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     cur = out;

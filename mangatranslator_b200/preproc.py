@@ -1,6 +1,7 @@
 """Device pre-/post-processing wrappers (C ABI: mtb_letterbox_u8, mtb_resize_aa_u8, mtb_resize_lanczos_u8)."""
 from __future__ import annotations
 
+import collections
 import ctypes as C
 
 import torch
@@ -18,7 +19,7 @@ def _declare(l) -> None:
     l.mtb_resize_aa_u8.restype = i32
     l.mtb_resize_lanczos_table_ints.argtypes = [i32] * 4
     l.mtb_resize_lanczos_table_ints.restype = C.c_longlong
-    l.mtb_resize_lanczos_u8.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, C.c_longlong, vp]
+    l.mtb_resize_lanczos_u8.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, C.c_longlong, i32, vp]
     l.mtb_resize_lanczos_u8.restype = i32
     l._pre_declared = True
 
@@ -62,9 +63,14 @@ def resize_aa_device(img: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
     return out
 
 
+_LANCZOS_TABLES: "collections.OrderedDict" = collections.OrderedDict()     # (device, sh, sw, oh, ow) -> filled device scratch
+_LANCZOS_TABLES_MAX = 32
+
+
 def resize_lanczos_device(img: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
     """PIL `Image.resize((ow, oh), Image.LANCZOS)` of a device uint8 HxWx(3|4) image -> uint8 oh x ow x 3, bit-exact with
-    Pillow (reference: core/image/image_utils.py:545,551-595)."""
+    Pillow (reference: core/image/image_utils.py:545,551-595).  The coefficient tables of the last few geometries stay on
+    the device (a page geometry repeats for a whole batch; bubble crops are ragged and simply cycle through the LRU)."""
     l = lib()
     _declare(l)
     assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_contiguous()
@@ -73,8 +79,17 @@ def resize_lanczos_device(img: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
         return img                                   # PIL returns a copy of the same pixels
     tmp = torch.empty((h0, ow, 3), dtype=torch.uint8, device=img.device) if (ow != w0 and oh != h0) else None
     out = torch.empty((oh, ow, 3), dtype=torch.uint8, device=img.device)
-    n_ints = int(l.mtb_resize_lanczos_table_ints(h0, w0, oh, ow))
-    tables = torch.empty(n_ints, dtype=torch.int32, device=img.device)
-    check(l.mtb_resize_lanczos_u8(ptr(img), h0, w0, c, ptr(tmp), ptr(out), oh, ow, ptr(tables), n_ints, stream_ptr()),
-          "mtb_resize_lanczos_u8")
+    key = (str(img.device), h0, w0, oh, ow)
+    ready = key in _LANCZOS_TABLES
+    if ready:
+        _LANCZOS_TABLES.move_to_end(key)
+        tables = _LANCZOS_TABLES[key]
+    else:
+        n_ints = int(l.mtb_resize_lanczos_table_ints(h0, w0, oh, ow))
+        tables = torch.empty(n_ints, dtype=torch.int32, device=img.device)
+        _LANCZOS_TABLES[key] = tables
+        while len(_LANCZOS_TABLES) > _LANCZOS_TABLES_MAX:
+            _LANCZOS_TABLES.popitem(last=False)
+    check(l.mtb_resize_lanczos_u8(ptr(img), h0, w0, c, ptr(tmp), ptr(out), oh, ow, ptr(tables), tables.numel(), int(ready),
+                                  stream_ptr()), "mtb_resize_lanczos_u8")
     return out
