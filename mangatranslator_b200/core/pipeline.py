@@ -164,11 +164,15 @@ class HotPathPipeline:
 
     def __init__(self, *, confidence: float = 0.6, imgsz: int = 1600, seg_model: str = "sam2", upscale: bool = True,
                  upscale_model: str = "model", thresholding_value: int = 200, roi_shrink_px: int = 5,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, conjoined_detection: bool = False,
+                 conjoined_confidence: float = 0.35):
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.confidence, self.imgsz, self.seg_model = confidence, imgsz, seg_model
         self.upscale, self.upscale_model = upscale, upscale_model
         self.thr, self.shrink = thresholding_value, roi_shrink_px
+        # secondary RT-DETR detector merged like the reference's default (detection.py:1392-1548); off here by default
+        # because without its checkpoint the loader refuses and every page would log the swallowed failure
+        self.conjoined = dict(conjoined_detection=conjoined_detection, conjoined_confidence=conjoined_confidence)
         mm = get_model_manager()
         self.yolo = mm.load_yolo_speech_bubble(None)
         self.sam = mm.load_sam2() if seg_model == "sam2" else None
@@ -184,7 +188,7 @@ class HotPathPipeline:
         if t: t[0].record()
         h, w = int(page_bgr.shape[0]), int(page_bgr.shape[1])
         dets = detect_pages_device([page_bgr], confidence=self.confidence, imgsz=self.imgsz, seg_model=self.seg_model,
-                                   injected_boxes=None if injected_boxes is None else [injected_boxes])[0]
+                                   injected_boxes=None if injected_boxes is None else [injected_boxes], **self.conjoined)[0]
         if t: t[1].record()
         scale = _processing_scale(w, h)
         batch = clean_pages_device([page_bgr], [dets], thresholding_value=self.thr, roi_shrink_px=self.shrink,
@@ -213,7 +217,7 @@ class HotPathPipeline:
         for i, page in enumerate(pages_bgr):
             inj = None if injected_boxes is None or injected_boxes[i] is None else [injected_boxes[i]]
             dets.append(detect_pages_device([page], confidence=self.confidence, imgsz=self.imgsz, seg_model=self.seg_model,
-                                            injected_boxes=inj, own_masks=n > 1)[0])
+                                            injected_boxes=inj, own_masks=n > 1, **self.conjoined)[0])
         scales = {_processing_scale(int(p.shape[1]), int(p.shape[0])) for p in pages_bgr}
         if len(scales) == 1:
             batch = clean_pages_device(list(pages_bgr), dets, thresholding_value=self.thr, roi_shrink_px=self.shrink,

@@ -142,29 +142,41 @@ __global__ void split_resolve_kernel(const uint8_t* __restrict__ parent, const S
   }
 }
 
-// one thread per (child, window row): distance to the nearest pixel of that child in the row, for every column
+// one WARP per (child, window row): distance to the nearest pixel of that child in the row, for every column.  Each
+// 32-column chunk is one coalesced load and one ballot; the nearest seed at-or-left of a lane is the highest set bit at
+// or below it (or the carry from earlier chunks), the nearest at-or-right the lowest set bit at or above it.
 __global__ void split_rowdist_kernel(const SplitParams* __restrict__ P, const SplitFlags* __restrict__ F,
                                      const uint16_t* __restrict__ bits, uint16_t* __restrict__ rowdist) {
   if (!F->any_remaining) return;
   const int ww = P->ww, wh = P->wh, K = P->K;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= K * wh) return;
   const int k = t / wh, row = t - k * wh;
   if (!F->seed_any[k]) return;
   const uint16_t* b = bits + static_cast<long long>(row) * ww;
   uint16_t* rd = rowdist + (static_cast<long long>(k) * wh + row) * ww;
   int last = -1;
-  for (int x = 0; x < ww; ++x) {
-    if ((b[x] >> k) & 1u) last = x;
-    rd[x] = last < 0 ? kNoSeedInRow : static_cast<uint16_t>(min(x - last, 65534));
+  for (int x0 = 0; x0 < ww; x0 += 32) {
+    const int x = x0 + lane;
+    const bool s = x < ww && ((b[x] >> k) & 1u);
+    const unsigned m = __ballot_sync(0xffffffffu, s);
+    const unsigned below = m & (0xffffffffu >> (31 - lane));
+    const int l = below ? x0 + 31 - __clz(below) : last;
+    if (x < ww) rd[x] = l < 0 ? kNoSeedInRow : static_cast<uint16_t>(min(x - l, 65534));
+    if (m) last = x0 + 31 - __clz(m);
   }
-  last = -1;
-  for (int x = ww - 1; x >= 0; --x) {
-    if ((b[x] >> k) & 1u) last = x;
-    if (last >= 0) {
-      const int d = min(last - x, 65534);
-      if (d < rd[x]) rd[x] = static_cast<uint16_t>(d);
+  int next = -1;
+  for (int x0 = ((ww - 1) / 32) * 32; x0 >= 0; x0 -= 32) {
+    const int x = x0 + lane;
+    const bool s = x < ww && ((b[x] >> k) & 1u);
+    const unsigned m = __ballot_sync(0xffffffffu, s);
+    const unsigned above = m & (0xffffffffu << lane);
+    const int r = above ? x0 + __ffs(above) - 1 : next;
+    if (x < ww && r >= 0) {
+      const int d = min(r - x, 65534);
+      if (d < rd[x]) rd[x] = static_cast<uint16_t>(d);      // same lane wrote rd[x] in the forward sweep
     }
+    if (m) next = x0 + __ffs(m) - 1;
   }
 }
 
@@ -304,7 +316,7 @@ int mtb_split_conjoined(const uint8_t* parent, int H, int W, int K, const int* r
   MTB_CUDA_OK(cudaGetLastError());
   split_resolve_kernel<<<grid(wpx), 256, 0, st>>>(parent, dP, dF, dBits);
   MTB_CUDA_OK(cudaGetLastError());
-  split_rowdist_kernel<<<(K * wh + 127) / 128, 128, 0, st>>>(dP, dF, dBits, dRow);
+  split_rowdist_kernel<<<(K * wh + 7) / 8, 256, 0, st>>>(dP, dF, dBits, dRow);      // one warp per (child, row)
   MTB_CUDA_OK(cudaGetLastError());
   split_expand_kernel<<<grid(static_cast<long long>(H) * W), 256, 0, st>>>(dP, dF, dBits, dRow, out);
   MTB_CUDA_OK(cudaGetLastError());
