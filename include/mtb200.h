@@ -277,6 +277,8 @@ int mtb_resize_lanczos_tables(int sh, int sw, int oh, int ow, int* tables_dev, l
 /* tables_ready = 1: `tables_dev` already holds this geometry's tables (callers keep one scratch per geometry) */
 int mtb_resize_lanczos_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* tmp, uint8_t* dst /* oh x ow x 3 */,
                           int oh, int ow, int* tables_dev, long long tables_ints, int tables_ready, void* stream);
+/* flatten_alpha_u8 : `background.paste(image, mask=alpha)` of convert_image_to_target_mode (image_utils.py:598-675) */
+int mtb_flatten_alpha_u8(const uint8_t* src, int H, int W, const int* bg3 /* host */, uint8_t* dst, void* stream);
 /* host-only: Pillow's 22-bit LANCZOS coefficient table of one axis (what resize_lanczos_u8 uploads); CPU tests */
 int mtb_lanczos_weights_host(int in_size, int out_size, int* start, int* len, int* weights, int ksize_cap, int* ksize);
 

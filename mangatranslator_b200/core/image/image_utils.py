@@ -18,7 +18,7 @@ from mangatranslator_b200.core.caching import get_cache
 from mangatranslator_b200.core.ml.model_manager import get_model_manager
 from mangatranslator_b200.utils.exceptions import ImageProcessingError
 from mangatranslator_b200.utils.logging import log_message
-from mangatranslator_b200._lib import serialized
+from mangatranslator_b200._lib import device_section, serialized
 
 
 def pil_to_cv2(pil_image: Image.Image) -> np.ndarray:
@@ -229,11 +229,16 @@ def process_page_bubbles_device(page_rgb: torch.Tensor, bboxes, upscale_model, t
 
 
 def convert_image_to_target_mode(image: Image.Image, target_mode: str, verbose: bool = False) -> Image.Image:
+    """Reference :598-675.  RGBA / LA / P-with-transparency pages headed for RGB are flattened onto white with Pillow's
+    paste arithmetic — on the device for RGBA pages (mtb_flatten_alpha_u8); mode bookkeeping (LA / P expansion, plain
+    conversions) stays with Pillow."""
     if image.mode == target_mode:
         return image
-    if target_mode == "RGB" and image.mode in ("RGBA", "LA", "P"):
-        rgba = image.convert("RGBA")
-        bg = Image.new("RGB", rgba.size, (255, 255, 255))
-        bg.paste(rgba, mask=rgba.split()[3])
-        return bg
+    if target_mode == "RGB" and (image.mode in ("RGBA", "LA") or (image.mode == "P" and "transparency" in image.info)):
+        log_message(f"Converting {image.mode} to RGB (flattening transparency)", verbose=verbose)
+        rgba = image if image.mode == "RGBA" else image.convert("RGBA")
+        with device_section:
+            dev = get_model_manager()._require_cuda()
+            from mangatranslator_b200.preproc import flatten_alpha_device
+            return _device_to_pil(flatten_alpha_device(torch.from_numpy(np.array(rgba)).to(dev)))
     return image.convert(target_mode)

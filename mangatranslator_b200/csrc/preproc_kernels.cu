@@ -73,6 +73,22 @@ __global__ void copy_pad_kernel(const uint8_t* __restrict__ src, int sh, int sw,
   }
 }
 
+// Pillow `background.paste(image, mask=alpha)` (ImagingPaste with an "L" mask): per channel
+// (bg * (255 - a) + src * a + 128 + ((... + 128) >> 8)) >> 8  -- checked exhaustively against Pillow in tests/test_preproc.py
+__global__ void flatten_alpha_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long npix, int bg0,
+                                     int bg1, int bg2) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < npix;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uchar4 p = reinterpret_cast<const uchar4*>(src)[i];
+    const int a = p.w, bg[3] = {bg0, bg1, bg2}, c[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int t = bg[k] * (255 - a) + c[k] * a + 128;
+      dst[i * 3 + k] = static_cast<uint8_t>((t + (t >> 8)) >> 8);
+    }
+  }
+}
+
 int cv_round_f(float v) { return static_cast<int>(lrintf(v)); }  // round half to even (default FP mode)
 
 short sat_short(int v) { return static_cast<short>(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
@@ -494,6 +510,22 @@ int mtb_resize_lanczos_u8(const uint8_t* src, int sh, int sw, int sc, uint8_t* t
     MTB_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
   }
+  return 0;
+}
+
+// RGBA -> RGB over a constant background, Pillow paste arithmetic (core/image/image_utils.py:598-675
+// convert_image_to_target_mode: transparency is flattened onto white before JPEG-bound processing)
+int mtb_flatten_alpha_u8(const uint8_t* src /* H x W x 4, alpha last */, int H, int W, const int* bg3 /* host */,
+                         uint8_t* dst /* H x W x 3 */, void* stream) {
+  MTB_REQUIRE(src && dst && bg3 && H > 0 && W > 0, "mtb_flatten_alpha_u8: bad arguments");
+  MTB_REQUIRE(reinterpret_cast<uintptr_t>(src) % 4 == 0, "mtb_flatten_alpha_u8: source must be 4-byte aligned");
+  const long long npix = static_cast<long long>(H) * W;
+  long long g = (npix + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count3()) * 16;
+  if (g > cap) g = cap;
+  flatten_alpha_kernel<<<static_cast<int>(g), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, npix, bg3[0], bg3[1], bg3[2]);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
   return 0;
 }
 

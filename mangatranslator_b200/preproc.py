@@ -21,6 +21,8 @@ def _declare(l) -> None:
     l.mtb_resize_lanczos_table_ints.restype = C.c_longlong
     l.mtb_resize_lanczos_u8.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, C.c_longlong, i32, vp]
     l.mtb_resize_lanczos_u8.restype = i32
+    l.mtb_flatten_alpha_u8.argtypes = [vp, i32, i32, C.POINTER(i32), vp, vp]
+    l.mtb_flatten_alpha_u8.restype = i32
     l._pre_declared = True
 
 
@@ -92,4 +94,17 @@ def resize_lanczos_device(img: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
             _LANCZOS_TABLES.popitem(last=False)
     check(l.mtb_resize_lanczos_u8(ptr(img), h0, w0, c, ptr(tmp), ptr(out), oh, ow, ptr(tables), tables.numel(), int(ready),
                                   stream_ptr()), "mtb_resize_lanczos_u8")
+    return out
+
+
+def flatten_alpha_device(img: torch.Tensor, background=(255, 255, 255)) -> torch.Tensor:
+    """Device uint8 HxWx4 (alpha last) -> HxWx3 over a constant background with Pillow's paste arithmetic
+    (reference: convert_image_to_target_mode, core/image/image_utils.py:598-675)."""
+    l = lib()
+    _declare(l)
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 4 and img.is_contiguous()
+    h, w, _ = img.shape
+    out = torch.empty((h, w, 3), dtype=torch.uint8, device=img.device)
+    bg = (C.c_int * 3)(*[int(v) for v in background])
+    check(l.mtb_flatten_alpha_u8(ptr(img), h, w, bg, ptr(out), stream_ptr()), "mtb_flatten_alpha_u8")
     return out

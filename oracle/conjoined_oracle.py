@@ -160,3 +160,45 @@ def split_group(parent_mask, group_boxes, *, ipp: bool = False):
         v = b.tolist() if hasattr(b, "tolist") else b
         bboxes.append((int(round(v[0])), int(round(v[1])), int(round(v[2])), int(round(v[3]))))
     return masks, bboxes
+
+
+# ---- grouping (detection.py:408-472 `_detect_overlapping_primaries`, :1596-1619) -------------------------------------
+def _ioa(inner, outer):
+    area = max(0.0, inner[2] - inner[0]) * max(0.0, inner[3] - inner[1])
+    if area <= 0:
+        return 0.0
+    iw = max(0.0, min(inner[2], outer[2]) - max(inner[0], outer[0]))
+    ih = max(0.0, min(inner[3], outer[3]) - max(inner[1], outer[1]))
+    return iw * ih / area
+
+
+def overlapping_groups(boxes, threshold: float = 0.15):
+    """Connected components (either-direction IoA > threshold) of size >= 2 among the boxes, as sorted index lists in order
+    of their first member; and the indices left over as simple bubbles."""
+    b = [[float(v) for v in (x.tolist() if hasattr(x, "tolist") else x)] for x in boxes]
+    n = len(b)
+    comp = list(range(n))
+
+    def find(i):
+        while comp[i] != i:
+            comp[i] = comp[comp[i]]
+            i = comp[i]
+        return i
+
+    for i in range(n):
+        for j in range(i + 1, n):
+            if _ioa(b[i], b[j]) > threshold or _ioa(b[j], b[i]) > threshold:
+                ri, rj = find(i), find(j)
+                if ri != rj:
+                    comp[rj] = ri
+    members = {}
+    for i in range(n):
+        members.setdefault(find(i), []).append(i)
+    groups = [sorted(m) for m in members.values() if len(m) >= 2]
+    grouped = {i for g in groups for i in g}
+    return groups, [i for i in range(n) if i not in grouped]
+
+
+def union_box(boxes):
+    arr = np.asarray([[float(v) for v in (x.tolist() if hasattr(x, "tolist") else x)] for x in boxes], np.float32)
+    return np.concatenate([arr[:, :2].min(0), arr[:, 2:].max(0)])

@@ -47,9 +47,21 @@ class CpuPipeline:
         if boxes is None:
             boxes = det["xyxy"].numpy()
         t0 = time.perf_counter()
-        seg = sam2_oracle.segment(self.sam, self.proc, Image.fromarray(rgb), boxes) if len(boxes) else dict(masks=[])
+        # the reference groups overlapping primaries into synthetic conjoined bubbles (detection.py:1596-1619): SAM is
+        # prompted with the simple boxes and each group's union box, the parent masks are split between the members
+        import conjoined_oracle
+        groups, simple = conjoined_oracle.overlapping_groups(boxes) if len(boxes) > 1 else ([], list(range(len(boxes))))
+        prompts = [boxes[i] for i in simple] + [conjoined_oracle.union_box([boxes[i] for i in g]) for g in groups]
+        seg = sam2_oracle.segment(self.sam, self.proc, Image.fromarray(rgb), np.asarray(prompts, np.float32)) if len(prompts) \
+            else dict(masks=[])
+        dets = [{"bbox": tuple(int(round(float(v))) for v in boxes[i]), "sam_mask": seg["masks"][n]} for n, i in enumerate(simple)]
+        for gi, g in enumerate(groups):
+            masks, bboxes = conjoined_oracle.split_group(seg["masks"][len(simple) + gi], [boxes[i] for i in g])
+            for n in range(len(g)):
+                dets.append({"bbox": bboxes[n], "sam_mask": masks[n],
+                             "conjoined_neighbor_bboxes": [b for m, b in enumerate(bboxes) if m != n]})
         t["segment"] = time.perf_counter() - t0
-        dets = [{"bbox": tuple(int(round(float(v))) for v in b), "sam_mask": m} for b, m in zip(boxes, seg["masks"])]
+        seg = dict(seg, masks=np.stack([d["sam_mask"] for d in dets]) if dets else np.zeros((0, h, w), np.uint8))
         t0 = time.perf_counter()
         cleaned, bubbles = clean_oracle.clean_page(bgr, dets, processing_scale=(h * w / 1e6) ** 0.5)
         t["clean"] = time.perf_counter() - t0

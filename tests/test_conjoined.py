@@ -75,6 +75,11 @@ def test_grouping_geometry_matches_live_reference():
         n_groups += len(exp[0])
         grp = [b for b in prim[: int(rng.integers(1, len(prim) + 1))]]
         assert Cj.group_arrangement(grp) == ref._detect_group_arrangement(grp)
+        # the oracle's own grouping (used by oracle/pipeline_oracle.py) is pinned to the same reference function
+        allp = list(range(len(prim)))
+        og, osimple = O.overlapping_groups(prim)
+        eg, esimple = ref._detect_overlapping_primaries(prim, allp)
+        assert og == eg and osimple == list(esimple)
     assert n_groups > 50 and n_conj > 20            # the random cases do exercise both kinds of group
 
 

@@ -168,3 +168,30 @@ def test_stage_functions_are_safe_under_page_threads(small_models):
     assert not errors, errors
     for (c0, u0, n0), (c1, u1, n1) in zip(expected, got):
         assert n0 == n1 and np.array_equal(c0, c1) and np.array_equal(u0, u1)
+
+
+def test_hot_path_with_conjoined_group_matches_cpu_pipeline(small_models):
+    """A page whose injected boxes overlap (two of them form a synthetic conjoined group): the device pipeline and the CPU
+    pipeline (transformers SAM on the union box, oracle split, cv2 clean with neighbour boxes, oracle RCAN) agree like the
+    plain pages do — SAM knife-edge pixels aside."""
+    import pipeline_oracle
+    from mangatranslator_b200 import synth
+    from mangatranslator_b200.core.pipeline import HotPathPipeline
+    h, w = 448, 384
+    pg = synth.make_page(22, h, w, n_bubbles=4)
+    boxes = np.asarray(pg.boxes_xyxy, np.float32).copy()
+    boxes[1] = boxes[0] + np.array([0.45, 0.1, 0.45, 0.1], np.float32) * (boxes[0, 2] - boxes[0, 0])   # overlaps box 0
+    boxes[1, [0, 2]] = np.clip(boxes[1, [0, 2]], 0, w)
+    cpu = pipeline_oracle.CpuPipeline(0, yolo_variant="n", rcan_groups=2, rcan_blocks=2)
+    ref = cpu.run_page(pg.image_rgb, boxes, imgsz=640)
+    pipe = HotPathPipeline(seg_model="sam2", upscale=True, imgsz=640)
+    host = torch.from_numpy(np.ascontiguousarray(pg.image_rgb[:, :, ::-1])).pin_memory()
+    out, dets, batch = pipe.run_page(host, injected_boxes=boxes)
+    assert sum(1 for d in dets if d.get("conjoined_neighbor_bboxes")) == 2
+    assert [d["bbox"] for d in dets] == [b["bbox"] for b in ref["bubbles"]] or len(dets) == ref["masks"].shape[0]
+    got_masks = np.stack([d["sam_mask"].cpu().numpy() for d in dets])
+    assert got_masks.shape == ref["masks"].shape
+    assert (got_masks != ref["masks"]).mean() < 2e-3
+    assert (batch.pages_out[0].cpu().numpy() != ref["cleaned"]).mean() < 2e-3
+    d = np.abs(out.numpy().astype(int) - ref["upscaled"].astype(int))
+    assert (d > 1).mean() < 5e-3

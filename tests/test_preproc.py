@@ -179,3 +179,47 @@ def test_lanczos_kernel_matches_pillow(case):
     img4 = np.concatenate([img, np.full((h, w, 1), 7, np.uint8)], axis=2)
     got4 = resize_lanczos_device(torch.from_numpy(img4).cuda(), oh, ow).cpu().numpy()
     assert np.array_equal(got4, ref)
+
+
+# ---- transparency flattening (Pillow paste with the alpha channel as mask) -------------------------------------------
+def _flatten_numpy(rgba, bg=255):
+    src, a = rgba[..., :3].astype(np.int64), rgba[..., 3:4].astype(np.int64)
+    t = bg * (255 - a) + src * a + 128
+    return ((t + (t >> 8)) >> 8).astype(np.uint8)
+
+
+def _all_alpha_pairs():
+    s, m = np.meshgrid(np.arange(256), np.arange(256))
+    a = np.zeros((256, 256, 4), np.uint8)
+    a[..., 0], a[..., 1], a[..., 2], a[..., 3] = s, 255 - s, (s * 7) % 256, m
+    return a
+
+
+def test_flatten_arithmetic_matches_pillow_exhaustively():
+    from PIL import Image
+    a = _all_alpha_pairs()                                       # every (value, alpha) pair
+    im = Image.fromarray(a, "RGBA")
+    bg = Image.new("RGB", im.size, (255, 255, 255))
+    bg.paste(im, mask=im.split()[3])
+    assert np.array_equal(_flatten_numpy(a), np.asarray(bg))
+
+
+@pytest.mark.gpu
+def test_flatten_kernel_and_convert_image_to_target_mode_match_pillow():
+    from PIL import Image
+    from mangatranslator_b200.core.image.image_utils import convert_image_to_target_mode
+    from mangatranslator_b200.preproc import flatten_alpha_device
+    a = _all_alpha_pairs()
+    got = flatten_alpha_device(torch.from_numpy(a).cuda()).cpu().numpy()
+    assert np.array_equal(got, _flatten_numpy(a))
+    rgba = np.random.default_rng(3).integers(0, 256, size=(333, 217, 4), dtype=np.uint8)
+    im = Image.fromarray(rgba, "RGBA")
+    bg = Image.new("RGB", im.size, (255, 255, 255))
+    bg.paste(im, mask=im.split()[3])
+    out = convert_image_to_target_mode(im, "RGB")
+    assert out.mode == "RGB" and np.array_equal(np.asarray(out), np.asarray(bg))
+    la = im.convert("LA")
+    bg2 = Image.new("RGB", la.size, (255, 255, 255))
+    bg2.paste(la.convert("RGBA"), mask=la.split()[1])
+    assert np.array_equal(np.asarray(convert_image_to_target_mode(la, "RGB")), np.asarray(bg2))
+    assert convert_image_to_target_mode(im.convert("RGB"), "RGBA").mode == "RGBA"
