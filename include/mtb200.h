@@ -231,7 +231,7 @@ int mtb_nms(const mtb_nms_params* p /* host */, const float* cand, const int* ca
  * from both children and re-divided by v = (x-cx)*ax + (y-cy)*ay in float64: mode 1 gives i the pixels with v <= 0
  * and j those with v > 0, mode 2 gives i v >= 0 and j v < 0, mode 0 leaves the zone to the nearest-child rule.
  * out: uint8 [K][H][W] {0,255}.  Bit-exact with the reference under OpenCV's own (non-IPP) distanceTransform. */
-#define MTB_SPLIT_MAX_CHILDREN 12
+#define MTB_SPLIT_MAX_CHILDREN 15
 typedef struct mtb_split_pair {
   int i, j, mode, reserved;
   double cx, cy, ax, ay;

@@ -28,7 +28,7 @@ IOA_THRESHOLD = 0.50                        # detection.py:16
 IOA_OVERLAP_THRESHOLD = 0.5                 # :18
 SYNTHETIC_CONJOINED_IOA_THRESHOLD = 0.15    # :31-33
 AXIS_DOMINANCE_RATIO = 3.0                  # :34-36
-MAX_CHILDREN = 12                           # MTB_SPLIT_MAX_CHILDREN
+MAX_CHILDREN = 15                           # MTB_SPLIT_MAX_CHILDREN
 
 
 def _as_list(box) -> List[float]:

@@ -209,6 +209,17 @@ def test_split_kernel_degenerate_groups_match_oracle():
     # an all-zero parent gives all-zero children
     out, _ = Cj.split_conjoined_device(torch.zeros((h, w), dtype=torch.uint8, device=dev), groups[0], include_child_rects=False)
     assert int(out.sum()) == 0
+    # the largest group the kernel takes: a chain of MAX_CHILDREN overlapping boxes (105 candidate pairs)
+    big = np.zeros((200, 900), np.uint8)
+    big[30:170, 10:890] = 255
+    chain = [[20.0 + 55 * i, 40.0 + 3 * (i % 3), 95.0 + 55 * i, 150.0 - 2 * (i % 2)] for i in range(Cj.MAX_CHILDREN)]
+    exp = O.split_group(big, chain)[0]
+    out, plan = Cj.split_conjoined_device(torch.from_numpy(big).to(dev), chain)
+    assert len(plan.pairs) >= Cj.MAX_CHILDREN - 1
+    for a, b in zip(out.cpu().numpy(), exp):
+        assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        Cj.plan_split(chain + [[5.0, 5.0, 50.0, 50.0]], 200, 900)
 
 
 # ---- the whole detection flow with duck-typed models, against the UNMODIFIED reference -----------------------------
