@@ -188,7 +188,7 @@ class ModelManager:
                                  "(set MTB200_SYNTHETIC_RTDETR=1 for seeded synthetic weights)")
             dev = self._require_cuda()
             try:
-                cfg, sd = W.rtdetr_model_and_state(self.synthetic_seed)
+                cfg, sd = W.rtdetr_model_and_state(self.synthetic_seed, checkpoint_dir=str(ckpt) if ckpt.is_dir() else None)
                 model = RtDetrB200(sd, cfg, dev, precision=self.precision)
             except Exception as e:
                 raise ModelError(f"Failed to load RT-DETR conjoined model: {e}") from e

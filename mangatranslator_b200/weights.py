@@ -161,14 +161,15 @@ def sam2_model_and_state(seed: int = 0, variant: str = "tiny"):
 RTDETR_NAMES = {0: "bubble", 1: "text_bubble", 2: "text_free"}     # classes the stage code looks for (detection.py:1430-1437)
 
 
-def rtdetr_model_and_state(seed: int = 0, **config_overrides):
+def rtdetr_model_and_state(seed: int = 0, checkpoint_dir: Optional[str] = None, **config_overrides):
     """(config, state_dict) of `RTDetrV2ForObjectDetection`.  Like the SAM weights, initialisation and (when
-    `<models>/rtdetr/comic-text-and-bubble-detector` exists) loading go through the library the reference uses
+    `checkpoint_dir` or `$MT_MODELS_DIR/rtdetr/comic-text-and-bubble-detector` exists) loading go through the library the
+    reference uses
     (core/ml/model_manager.py:758-766); no forward pass happens here.  Synthetic weights: seeded default init, non-trivial
     frozen-batch-norm statistics, and class biases lifted from the focal-loss prior so a few dozen queries pass conf 0.35."""
     from transformers import RTDetrV2Config, RTDetrV2ForObjectDetection
     d = models_dir()
-    ckpt = os.path.join(d, "rtdetr", "comic-text-and-bubble-detector") if d else None
+    ckpt = checkpoint_dir or (os.path.join(d, "rtdetr", "comic-text-and-bubble-detector") if d else None)
     if ckpt and os.path.isdir(ckpt):
         m = RTDetrV2ForObjectDetection.from_pretrained(ckpt).eval()
         return m.config, m.state_dict()
