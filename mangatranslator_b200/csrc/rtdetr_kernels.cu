@@ -143,7 +143,10 @@ __global__ void deform_attn_kernel(const uint16_t* __restrict__ value, const flo
       const float lx = rx + of[2 * i] * pscale * rw * P.offset_scale;
       const float ly = ry + of[2 * i + 1] * pscale * rh * P.offset_scale;
       const float gx = 2.0f * lx - 1.0f, gy = 2.0f * ly - 1.0f;
-      const float ix = ((gx + 1.0f) * W - 1.0f) * 0.5f, iy = ((gy + 1.0f) * H - 1.0f) * 0.5f;
+      float ix = ((gx + 1.0f) * W - 1.0f) * 0.5f, iy = ((gy + 1.0f) * H - 1.0f) * 0.5f;
+      // far-outside samples contribute zero either way; keep the float -> int conversion defined (NaN maps outside too)
+      ix = (ix > -4.0f && ix < 1.0e6f) ? ix : -4.0f;
+      iy = (iy > -4.0f && iy < 1.0e6f) ? iy : -4.0f;
       const float fx = floorf(ix), fy = floorf(iy);
       const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
       const float ax = ix - fx, ay = iy - fy;
