@@ -25,7 +25,7 @@ from PIL import Image
 
 from mangatranslator_b200.core.caching import get_cache
 from mangatranslator_b200.core.device import get_best_device
-from mangatranslator_b200.core.ml.model_manager import ModelType, get_model_manager
+from mangatranslator_b200.core.ml.model_manager import get_model_manager
 from mangatranslator_b200.utils.exceptions import ImageProcessingError, ModelError
 from mangatranslator_b200.utils.logging import log_message
 from mangatranslator_b200._lib import serialized

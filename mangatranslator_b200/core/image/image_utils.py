@@ -8,7 +8,7 @@ process_bubble_image_cached (:678-746, the per-bubble crops of core/services/tra
 """
 from __future__ import annotations
 
-from typing import Optional
+
 
 import numpy as np
 import torch

@@ -26,7 +26,6 @@ values (top-k, gathers, the 300x4 box refinement).
 from __future__ import annotations
 
 import ctypes as C
-import math
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Tuple
 
