@@ -173,8 +173,9 @@ def measure_dominant_kernel(pipe, page_dev, peaks):
                      "bf16 MMAs ([W_hi;W_lo] rows against the hi and the lo activation plane)")
 
 
-def _time_ms(fn, reps=5):
-    fn()
+def _time_ms(fn, reps=5, warm=3):
+    for _ in range(warm):                    # plans are built on the first call and graph-captured on the second
+        fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
