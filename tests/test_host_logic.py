@@ -153,3 +153,27 @@ def test_cache_keys_are_bound_to_the_image_object():
     for i in range(caching.MAX_ENTRIES + 10):
         c.set_upscaled_image(c.get_upscale_cache_key(Image.new("RGB", (2, 2)), 2.0, "model"), i)
     assert len(c._store) == caching.MAX_ENTRIES
+
+
+def test_yolo_oracle_nms_is_pinned_to_torchvision():
+    """ultralytics' non_max_suppression ends in `torchvision.ops.nms` (present in this image even though ultralytics is
+    not): the oracle's restated greedy NMS must return exactly the library's indices, on random boxes with heavy overlap,
+    class offsets and exact score ties."""
+    import torch
+    import torchvision
+    import yolo_oracle
+    g = torch.Generator().manual_seed(0)
+    for trial in range(40):
+        n = int(torch.randint(1, 400, (1,), generator=g))
+        centers = torch.rand(n, 2, generator=g) * 300
+        wh = torch.rand(n, 2, generator=g) * 120 + 4
+        boxes = torch.cat([centers - wh / 2, centers + wh / 2], 1)
+        if trial % 3 == 0:
+            boxes = boxes + (torch.randint(0, 3, (n, 1), generator=g).float() * 7680)      # class offsets like ultralytics
+        scores = torch.rand(n, generator=g)
+        if trial % 4 == 1:
+            scores = (scores * 8).round() / 8                                              # many exact ties
+        order = scores.argsort(descending=True, stable=True)                               # what non_max_suppression feeds
+        b, s = boxes[order], scores[order]
+        for thr in (0.45, 0.7):
+            assert torch.equal(yolo_oracle.nms(b, s, thr), torchvision.ops.nms(b, s, thr))
