@@ -56,3 +56,58 @@ def test_loader_does_not_invent_a_secondary_detector(monkeypatch, tmp_path):
     monkeypatch.setitem(mm.model_paths, ModelType.RTDETR_CONJOINED_BUBBLE, tmp_path / "absent")
     with pytest.raises(ModelError):
         mm.load_rtdetr_conjoined_bubble()
+
+
+def _deform_attn_numpy(value, shapes, offsets, logits, ref, n_points, offset_scale):
+    """The arithmetic of csrc/rtdetr_kernels.cu::deform_attn_kernel, in NumPy float32 (one image).
+    value [tokens][heads][hd], offsets [Q][heads][L*P][2], logits [Q][heads][L*P], ref [Q][4] -> [Q][heads*hd]."""
+    import numpy as np
+    Q, heads, LP, _ = offsets.shape
+    hd = value.shape[2]
+    out = np.zeros((Q, heads, hd), np.float32)
+    starts = np.cumsum([0] + [h * w for h, w in shapes])
+    e = np.exp(logits - logits.max(-1, keepdims=True))
+    wts = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+    for q in range(Q):
+        rx, ry, rw, rh = ref[q]
+        for h in range(heads):
+            for l, (H, W) in enumerate(shapes):
+                for pnt in range(n_points):
+                    i = l * n_points + pnt
+                    lx = rx + offsets[q, h, i, 0] * (1.0 / n_points) * rw * offset_scale
+                    ly = ry + offsets[q, h, i, 1] * (1.0 / n_points) * rh * offset_scale
+                    ix, iy = ((2 * lx - 1 + 1) * W - 1) * 0.5, ((2 * ly - 1 + 1) * H - 1) * 0.5
+                    ix = ix if -4.0 < ix < 1.0e6 else -4.0
+                    iy = iy if -4.0 < iy < 1.0e6 else -4.0
+                    x0, y0 = int(np.floor(ix)), int(np.floor(iy))
+                    ax, ay = ix - x0, iy - y0
+                    sv = np.zeros(hd, np.float32)
+                    for yy, xx, w8 in ((y0, x0, (1 - ax) * (1 - ay)), (y0, x0 + 1, ax * (1 - ay)),
+                                       (y0 + 1, x0, (1 - ax) * ay), (y0 + 1, x0 + 1, ax * ay)):
+                        if 0 <= yy < H and 0 <= xx < W:
+                            sv += np.float32(w8) * value[starts[l] + yy * W + xx, h]
+                    out[q, h] += sv * wts[q, h, i]
+    return out.reshape(Q, heads * hd)
+
+
+def test_deformable_attention_arithmetic_matches_transformers():
+    """The kernel's restatement of `multi_scale_deformable_attention_v2` (softmax over levels x points, reference-box
+    scaled offsets, bilinear grid_sample with zero padding, weighted sum) against the library function itself on CPU,
+    with sampling points inside, on the border of, and far outside the feature maps."""
+    import numpy as np
+    from transformers.models.rt_detr_v2.modeling_rt_detr_v2 import multi_scale_deformable_attention_v2
+    g = torch.Generator().manual_seed(0)
+    shapes, heads, hd, Q, P_ = [(10, 12), (5, 6), (3, 3)], 2, 32, 7, 4
+    n_tok = sum(h * w for h, w in shapes)
+    value = torch.randn(1, n_tok, heads, hd, generator=g)
+    offsets = torch.randn(1, Q, heads, len(shapes) * P_, 2, generator=g) * 3.0
+    offsets[0, 0] *= 40.0                                               # far outside
+    logits = torch.randn(1, Q, heads, len(shapes) * P_, generator=g)
+    ref = torch.rand(1, Q, 4, generator=g)
+    ref[0, 1] = torch.tensor([0.0, 1.0, 0.3, 0.3])                      # on the border
+    attn = torch.softmax(logits, -1)
+    scale = torch.tensor([1.0 / P_] * (len(shapes) * P_)).unsqueeze(-1)
+    loc = ref[:, :, None, None, :2] + offsets * scale * ref[:, :, None, None, 2:] * 0.5
+    exp = multi_scale_deformable_attention_v2(value, shapes, loc, attn, [P_] * len(shapes), "default")[0].numpy()
+    got = _deform_attn_numpy(value[0].numpy(), shapes, offsets[0].numpy(), logits[0].numpy(), ref[0].numpy(), P_, 0.5)
+    assert np.abs(got - exp).max() < 2e-5
