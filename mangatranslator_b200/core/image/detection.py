@@ -429,6 +429,9 @@ def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.
         lb = letterbox_device(page, imgsz, swap_rb=True)
         g = yolo.forward_letterboxed(lb)
         det, cnt, final_idx = yolo.detect(g, confidence, (h, w), tuple(lb.shape[:2]), apply_reference_dedup=True)
+        # The SAM image encoder does not depend on the boxes: enqueue it before the host waits for the detector, so the
+        # box table's round trip and the host-side grouping below run under ~5 ms of encoder work instead of an idle GPU.
+        enc = sam.encode(page[:, :, [2, 1, 0]].contiguous()) if sam is not None else None
         n_final = int(cnt[1].item())                                   # the one host sync of the detect stage
         rows = det[final_idx[:n_final].long()].cpu().numpy() if n_final else np.zeros((0, 8), np.float32)
         boxes = rows[:, :4].astype(np.float32)
@@ -476,8 +479,6 @@ def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.
         prompts = [tb[i] for i in simple] + parents
         masks = None
         if sam is not None and prompts:
-            rgb = page[:, :, [2, 1, 0]].contiguous()
-            enc = sam.encode(rgb)
             masks = sam.decode(enc, torch.stack(prompts), (h, w))
             if own_masks:
                 masks = masks.clone()
