@@ -334,7 +334,7 @@ def run_ours(args, coord):
     del gd
     if coord.rank != 0:
         return
-    extras = measure_side_stages(devp[0], dev, peaks)
+    extras = measure_side_stages(devp[0], dev, peaks) if coord.world == 1 else {}     # N = 1 only, like cpu_baseline
     roof = measure_dominant_kernel(pipe, devp[0], peaks)
     prof = os.path.join(ROOT, "profiles", "r01_halo_cm_ncu.json")
     if not os.path.exists(prof):
