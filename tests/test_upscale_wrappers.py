@@ -109,3 +109,26 @@ def test_page_bubble_crops_stay_on_device_and_match_single_calls():
         assert o.is_cuda and min(o.shape[0], o.shape[1]) == 200
         single = iu.process_bubble_crop_device(page[y0:y1, x0:x1].contiguous(), net, 200, "min")
         assert torch.equal(single, o)
+
+
+def test_resize_geometry_matches_live_reference():
+    """resize_to_min_side / resize_to_max_side output sizes against the unmodified reference functions (live, when the
+    reference tree is present) on random geometries, including extreme aspect ratios."""
+    import _refimport
+    if not _refimport.available():
+        pytest.skip("reference tree not present (GPU box)")
+    _refimport.import_reference()
+    import core.image.image_utils as ref_iu
+    from mangatranslator_b200.core.image import image_utils as iu
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        w, h = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+        t = int(rng.integers(1, 500))
+        im = Image.new("RGB", (w, h))
+        exp = ref_iu.resize_to_min_side(im, t).size
+        g = iu.resize_side_geometry(w, h, t)
+        assert (g if g is not None else (w, h)) == exp
+        exp_max = ref_iu.resize_to_max_side(im, t).size
+        cur = max(w, h)
+        got_max = (w, h) if cur == t else (max(1, int(round(w * (t / cur)))), max(1, int(round(h * (t / cur)))))
+        assert got_max == exp_max
