@@ -45,3 +45,24 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
         raised = True
     assert raised
     importlib.reload(L)
+
+
+def test_header_is_plain_c_and_ctypes_structs_match_the_compiler(tmp_path):
+    """include/mtb200.h is the drop-in boundary: it must compile as C99 (no C++ / torch types), and every ctypes mirror
+    in the Python layer must have exactly the size the C compiler gives the header's struct."""
+    import json
+    import subprocess
+    from mangatranslator_b200 import _lib, clean_host, conjoined, sam2, yolo
+    hdr = os.path.join(ROOT, "include", "mtb200.h")
+    subprocess.check_call(["gcc", "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", hdr])
+    pairs = {"mtb_conv_desc": _lib.ConvDesc, "mtb_clean_params": clean_host.CleanParams, "mtb_clean_job": clean_host.CleanJob,
+             "mtb_clean_result": clean_host.CleanResult, "mtb_yolo_level": yolo.YoloLevel, "mtb_nms_params": yolo.NmsParams,
+             "mtb_split_pair": conjoined.SplitPair, "mtb_attn_desc": sam2.AttnDesc}
+    src = tmp_path / "sizes.c"
+    body = "".join(f'  printf("%s\\"{n}\\": %zu", first ? "" : ", ", sizeof({n})); first = 0;\n' for n in pairs)
+    src.write_text(f'#include <stdio.h>\n#include "{hdr}"\nint main(void) {{ int first = 1; printf("{{");\n{body}  printf("}}\\n"); return 0; }}\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-o", str(exe), str(src)])
+    sizes = json.loads(subprocess.check_output([str(exe)]).decode())
+    for name, cls in pairs.items():
+        assert C.sizeof(cls) == sizes[name], (name, C.sizeof(cls), sizes[name])
