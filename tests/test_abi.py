@@ -66,3 +66,16 @@ def test_header_is_plain_c_and_ctypes_structs_match_the_compiler(tmp_path):
     sizes = json.loads(subprocess.check_output([str(exe)]).decode())
     for name, cls in pairs.items():
         assert C.sizeof(cls) == sizes[name], (name, C.sizeof(cls), sizes[name])
+    # ... and every field sits at the compiler's offset (the ctypes mirrors use the header's field names)
+    lines = "".join(f'  printf("{n}.{f[0]} %zu\\n", offsetof({n}, {f[0]}));\n' for n, cls in pairs.items() for f in cls._fields_)
+    src2 = tmp_path / "offsets.c"
+    src2.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{hdr}"\nint main(void) {{\n{lines}  return 0; }}\n')
+    exe2 = tmp_path / "offsets"
+    subprocess.check_call(["gcc", "-std=c99", "-o", str(exe2), str(src2)])
+    checked = 0
+    for line in subprocess.check_output([str(exe2)]).decode().splitlines():
+        key, off = line.split()
+        n, f = key.split(".")
+        assert getattr(pairs[n], f).offset == int(off), key
+        checked += 1
+    assert checked > 100
