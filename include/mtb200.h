@@ -282,6 +282,38 @@ int mtb_flatten_alpha_u8(const uint8_t* src, int H, int W, const int* bg3 /* hos
 /* host-only: Pillow's 22-bit LANCZOS coefficient table of one axis (what resize_lanczos_u8 uploads); CPU tests */
 int mtb_lanczos_weights_host(int in_size, int out_size, int* start, int* len, int* weights, int ksize_cap, int* ksize);
 
+/* ---- safe text box of a cleaned bubble mask (bit-exact integer path) ----------------------------------------------
+ * Replaces core/image/image_utils.py:173-348 calculate_centroid_expansion_box(cleaned_mask, padding_pixels), which the
+ * reference's renderer runs per bubble on the masks clean_speech_bubbles returned (core/text/text_renderer.py:162):
+ * exact Euclidean distance transform, safe area, centroid / pole of inaccessibility / nearest safe pixel, ray casts,
+ * box.  One CTA per bubble, all bubbles in one launch; masks are read once by a bounds pass. */
+typedef struct mtb_safebox_job {
+  const uint8_t* mask; /* device, H x W uint8, nonzero = bubble interior (the reference passes 0 / 255) */
+  long long pitch;     /* bytes between rows */
+  int H, W;
+  unsigned int t2;     /* mtb_safebox_threshold_sq(padding_pixels): safe <=> squared distance >= t2 */
+  int cap;             /* capacity of g / safe in pixels; (mask bbox + 2)^2 must fit, (H+2)*(W+2) always does */
+  uint16_t* g;         /* device workspace [cap] */
+  uint8_t* safe;       /* device workspace [cap]; holds the window's safe-area map (0 / 255) afterwards */
+} mtb_safebox_job;
+
+typedef struct mtb_safebox_result {
+  int status;       /* 0 ok; 1 empty mask ("Invalid or empty mask provided", :204-205); 2 no safe area, 3 no width or
+                       height, 4 box leaves the image (all three: "Safe area calculation failed", :348); 5 workspace */
+  int box[4];       /* x, y, width, height (:320) */
+  int moved;        /* bit 0: anchor moved to the pole of inaccessibility (:247-253); bit 1: to the nearest safe pixel (:262-281) */
+  int max_d2;       /* squared distance at the pole of inaccessibility */
+  int anchor[2];    /* pixel the rays were cast from */
+  int mask_bbox[4]; /* x0, y0, x1, y1 (inclusive) of the mask's nonzero pixels */
+  int reserved;
+  double cx, cy;    /* the centroid the reference returns (:255) */
+} mtb_safebox_result;
+
+/* host-only: smallest n with sqrtf((float)n) >= (float)padding_pixels, i.e. `distance_map >= padding_pixels` (:218) */
+unsigned int mtb_safebox_threshold_sq(double padding_pixels);
+/* jobs / results are device arrays; results need no initialisation.  Three stream operations: memset, bounds, boxes. */
+int mtb_safe_boxes(const mtb_safebox_job* jobs_dev, mtb_safebox_result* results_dev, int n_jobs, void* stream);
+
 /* ---- SAM 2.1 glue (transformers Sam2Model behind core/image/detection.py:475-511) -------------------------------- */
 int mtb_layernorm(const void* x, long long rows, int C, int ct_in, int ci, int planes_in, const float* gamma,
                   const float* beta, float eps, void* y, int ct_out, int co, int planes_out, int gelu, void* stream);

@@ -5,6 +5,8 @@ With the B200 upscaler (mangatranslator_b200.rcan.RcanB200) the page stays uint8
 RCAN conv stack, the clamp/*255/truncate back to u8 and the final exact-size LANCZOS resample (:545; bit-exact with
 Pillow, mtb_resize_lanczos_u8) are all kernels.  resize_to_min_side / resize_to_max_side (:551-595) and
 process_bubble_image_cached (:678-746, the per-bubble crops of core/services/translation.py:2097-2258) go the same way.
+calculate_centroid_expansion_box (:173-348, the renderer's per-bubble safe text box on the cleaned masks) is one
+integer kernel launch for all bubbles of a page (csrc/safebox_core.cuh).
 """
 from __future__ import annotations
 
@@ -242,3 +244,46 @@ def convert_image_to_target_mode(image: Image.Image, target_mode: str, verbose: 
             from mangatranslator_b200.preproc import flatten_alpha_device
             return _device_to_pil(flatten_alpha_device(torch.from_numpy(np.array(rgba)).to(dev)))
     return image.convert(target_mode)
+
+
+def safe_boxes_for_masks(masks, padding_pixels: float = 4.0, bboxes=None):
+    """All bubbles of a page in one launch: `masks` are device uint8 HxW tensors (e.g. the cleaned masks of
+    clean_pages_device).  Returns a list with, per mask, ((x, y, w, h), (cx, cy)) or the ImageProcessingError the
+    reference would have raised for it (returned, not raised, so one bad bubble does not hide the others)."""
+    from mangatranslator_b200 import safebox_host as S
+    with device_section:
+        recs = S.safe_boxes_device(masks, padding_pixels, bboxes)
+    out = []
+    for r in recs:
+        try:
+            out.append(S.decode(r))
+        except ValueError as e:
+            out.append(ImageProcessingError(e.args[0]))
+    return out
+
+
+def calculate_centroid_expansion_box(cleaned_mask, padding_pixels: float = 4.0, verbose: bool = False):
+    """Reference signature (:173-175): mask (numpy uint8 HxW, or a device tensor) -> ((x, y, width, height), (cx, cy));
+    raises ImageProcessingError with the reference's messages (:204-205, :348)."""
+    if cleaned_mask is None:
+        raise ImageProcessingError("Invalid or empty mask provided")
+    dev = get_model_manager()._require_cuda()
+    if isinstance(cleaned_mask, torch.Tensor):
+        m = cleaned_mask.to(dev)
+    else:
+        a = np.asarray(cleaned_mask)
+        if a.ndim != 2:
+            raise ImageProcessingError("Safe area calculation failed")
+        if a.dtype != np.uint8:
+            a = a.astype(np.uint8)                      # what assigning into the reference's uint8 frame does (:213)
+        m = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    if m.numel() == 0:
+        raise ImageProcessingError("Invalid or empty mask provided")
+    res = safe_boxes_for_masks([m.contiguous()], padding_pixels)[0]
+    if isinstance(res, Exception):
+        if res.args[0] != "Invalid or empty mask provided":
+            log_message(f"Safe area calculation failed: {res}", verbose=verbose, always_print=True)
+        raise res
+    box, centroid = res
+    log_message(f"Safe area: {box[2]:.0f}x{box[3]:.0f} at ({centroid[0]:.0f}, {centroid[1]:.0f})", verbose=verbose)
+    return box, centroid

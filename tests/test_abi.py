@@ -52,12 +52,13 @@ def test_header_is_plain_c_and_ctypes_structs_match_the_compiler(tmp_path):
     in the Python layer must have exactly the size the C compiler gives the header's struct."""
     import json
     import subprocess
-    from mangatranslator_b200 import _lib, clean_host, conjoined, sam2, yolo
+    from mangatranslator_b200 import _lib, clean_host, conjoined, safebox_host, sam2, yolo
     hdr = os.path.join(ROOT, "include", "mtb200.h")
     subprocess.check_call(["gcc", "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", hdr])
     pairs = {"mtb_conv_desc": _lib.ConvDesc, "mtb_clean_params": clean_host.CleanParams, "mtb_clean_job": clean_host.CleanJob,
              "mtb_clean_result": clean_host.CleanResult, "mtb_yolo_level": yolo.YoloLevel, "mtb_nms_params": yolo.NmsParams,
-             "mtb_split_pair": conjoined.SplitPair, "mtb_attn_desc": sam2.AttnDesc}
+             "mtb_split_pair": conjoined.SplitPair, "mtb_attn_desc": sam2.AttnDesc,
+             "mtb_safebox_job": safebox_host.SafeBoxJob, "mtb_safebox_result": safebox_host.SafeBoxResult}
     src = tmp_path / "sizes.c"
     body = "".join(f'  printf("%s\\"{n}\\": %zu", first ? "" : ", ", sizeof({n})); first = 0;\n' for n in pairs)
     src.write_text(f'#include <stdio.h>\n#include "{hdr}"\nint main(void) {{ int first = 1; printf("{{");\n{body}  printf("}}\\n"); return 0; }}\n')

@@ -1,0 +1,201 @@
+"""CPU: the safe text box (reference core/image/image_utils.py:173-348 `calculate_centroid_expansion_box`).
+
+  * the oracle (oracle/safebox_oracle.py) equals the UNMODIFIED reference function, live (build container) and on the
+    committed golden vectors (tests/golden/safebox_golden.json, written by oracle/gen_golden_safebox.py);
+  * the KERNEL LOGIC (csrc/safebox_core.cuh compiled as a sequential host emulation, tests/host_emul) equals the oracle
+    bit for bit: box, centroid doubles, which anchor rule fired, anchor pixel, maximal squared distance, error class;
+  * the facts the integer formulation rests on are checked against cv2 / NumPy themselves.
+The device run of the same source is tests/test_zz_safebox_gpu.py."""
+import ctypes as C
+import json
+import os
+
+import cv2
+import numpy as np
+import pytest
+
+import _refimport
+import safebox_oracle as O
+from helpers import ROOT, SAFEBOX_KINDS, emul_safe_box, safebox_mask, safebox_page_masks, sha
+from mangatranslator_b200 import safebox_host as S
+
+with open(os.path.join(ROOT, "tests", "golden", "safebox_golden.json")) as f:
+    GOLD = json.load(f)["cases"]
+
+
+def _golden_mask(case):
+    if case["name"].startswith("seed"):
+        m, pad = safebox_mask(int(case["name"][4:]))
+        assert pad == case["padding"]
+    else:
+        m = safebox_page_masks(0)[int(case["name"].split("bubble")[1])]
+    assert list(m.shape) == case["shape"] and sha(m) == case["mask_sha256"], "mask generator drifted from the fixture"
+    return m
+
+
+def _expected(case):
+    if "error" in case:
+        return case["error"]
+    return tuple(case["box"]), tuple(float.fromhex(v) for v in case["centroid"])
+
+
+def _oracle(mask, pad, trace=None):
+    try:
+        return O.safe_box(mask, pad, trace)
+    except O.SafeBoxError as e:
+        return e.args[0]
+
+
+def _emul(mask, pad, **kw):
+    rec = np.frombuffer(bytes(emul_safe_box(mask, pad, **kw)), S.RESULT_DTYPE)[0]
+    try:
+        return S.decode(rec), rec
+    except ValueError as e:
+        return e.args[0], rec
+    except RuntimeError:
+        return None, rec
+
+
+def test_golden_covers_every_branch():
+    assert len(GOLD) >= 130
+    kinds = {SAFEBOX_KINDS[int(c["name"][4:]) % len(SAFEBOX_KINDS)] for c in GOLD if c["name"].startswith("seed")}
+    assert kinds == set(SAFEBOX_KINDS)
+    assert {c.get("error") for c in GOLD} >= {None, O.EMPTY, O.FAILED} - {O.EMPTY} and any("error" in c for c in GOLD)
+    moved = set()
+    for c in GOLD:
+        t = {}
+        _oracle(_golden_mask(c), c["padding"], t)
+        moved.add(t["moved"])
+    assert moved >= {0, 1, 2}, moved          # centroid, pole of inaccessibility, nearest safe pixel
+
+
+@pytest.mark.parametrize("case", GOLD, ids=[c["name"] for c in GOLD])
+def test_oracle_and_kernel_logic_match_reference_golden(case):
+    m = _golden_mask(case)
+    exp = _expected(case)
+    trace = {}
+    assert _oracle(m, case["padding"], trace) == exp
+    got, rec = _emul(m, case["padding"])
+    assert got == exp
+    if not isinstance(exp, str):
+        assert int(rec["moved"]) == trace["moved"] and tuple(rec["anchor"]) == trace["anchor"]
+        assert int(rec["max_d2"]) == trace["max_d2"]
+        ys, xs = np.nonzero(m)
+        assert list(rec["mask_bbox"]) == [xs.min(), ys.min(), xs.max(), ys.max()]
+
+
+@pytest.mark.skipif(not _refimport.available(), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("ipp", [False, True])
+def test_oracle_matches_live_reference_random(ipp):
+    _refimport.import_reference()
+    import core.image.image_utils as RU
+    from utils.exceptions import ImageProcessingError
+    cv2.ipp.setUseIPP(ipp)
+    try:
+        n_fail = 0
+        for seed in range(2000, 2300):
+            m, pad = safebox_mask(seed)
+            try:
+                exp = RU.calculate_centroid_expansion_box(m, pad)
+            except ImageProcessingError as e:
+                exp = str(e)
+                n_fail += 1
+            assert _oracle(m, pad) == exp, (seed, m.shape, pad)
+        assert 10 < n_fail < 150
+    finally:
+        cv2.ipp.setUseIPP(True)
+
+
+def test_kernel_logic_matches_oracle_random():
+    seen = set()
+    for seed in range(3000, 3400):
+        m, pad = safebox_mask(seed)
+        t = {}
+        exp = _oracle(m, pad, t)
+        got, rec = _emul(m, pad)
+        assert got == exp, (seed, m.shape, pad)
+        if not isinstance(exp, str):
+            assert (int(rec["moved"]), tuple(rec["anchor"]), int(rec["max_d2"])) == (t["moved"], t["anchor"], t["max_d2"])
+            seen.add(t["moved"])
+    assert seen >= {0, 1, 2}
+
+
+def test_precise_distance_transform_is_sqrt_of_exact_squared_distance():
+    """OpenCV's own DIST_MASK_PRECISE transform == float32 sqrt of the exact squared distance (what the kernel's integer
+    d2 stands for); the IPP build of the same call may differ by an ulp, never by more."""
+    worst_ipp = 0
+    for seed in range(40):
+        m, _ = safebox_mask(seed)
+        framed = np.zeros((m.shape[0] + 2, m.shape[1] + 2), np.uint8)
+        framed[1:-1, 1:-1] = m
+        exact = np.sqrt(O.squared_edt(m).astype(np.float32))
+        cv2.ipp.setUseIPP(False)
+        try:
+            own = cv2.distanceTransform(framed, cv2.DIST_L2, cv2.DIST_MASK_PRECISE)[1:-1, 1:-1]
+        finally:
+            cv2.ipp.setUseIPP(True)
+        assert np.array_equal(own, exact)
+        ipp = cv2.distanceTransform(framed, cv2.DIST_L2, cv2.DIST_MASK_PRECISE)[1:-1, 1:-1]
+        assert np.all(np.abs(ipp - exact) <= np.spacing(exact) * 1.01)
+        worst_ipp = max(worst_ipp, int((ipp != exact).sum()))
+    print("pixels where the IPP transform differs by one ulp (worst mask):", worst_ipp)
+
+
+def test_threshold_and_scalar_semantics():
+    # NumPy 2 compares a float32 array / scalar with a Python float in float32 (image_utils.py:218,247)
+    assert bool(np.float32(3.0) < 3.0000001) is False
+    assert bool((np.array([3.0], np.float32) >= 3.0000001)[0]) is True
+    for pad in [0.0, -1.0, 0.3, 0.5, 1.0, 1.41421, 2 ** 0.5, 2.5, 4.0, 4.3, 5.0, 7.3, 9.999999, 10.0, 15.0, 63.5, 100.25]:
+        t2 = O.threshold_sq(pad)
+        assert S.threshold_sq(pad) == t2                      # the C helper the product uses
+        n = np.arange(0, max(4, int(pad * pad) + 40), dtype=np.int64)
+        assert np.array_equal(np.sqrt(n.astype(np.float32)) >= pad, n >= t2), pad
+    # first maximum in raster order (cv2.minMaxLoc, :237)
+    z = np.zeros((5, 7), np.float32)
+    z[1, 4] = z[3, 2] = z[1, 6] = 2
+    assert cv2.minMaxLoc(z)[3] == (4, 1)
+
+
+def test_kernel_logic_edge_cases():
+    # empty mask -> the reference's first error (:204-205)
+    got, rec = _emul(np.zeros((40, 50), np.uint8), 4.0)
+    assert got == O.EMPTY and int(rec["status"]) == S.ST_EMPTY_MASK
+    # padding <= 0: every pixel of the frame is "safe" (0 >= 0), the window becomes the whole image
+    m = np.zeros((37, 53), np.uint8)
+    m[10:20, 5:30] = 255
+    for pad in (0.0, -2.0):
+        assert _emul(m, pad)[0] == _oracle(m, pad)
+    # one-pixel mask, one-pixel image, mask filling the frame of a non-square image
+    one = np.zeros((9, 9), np.uint8)
+    one[4, 4] = 255
+    for pad in (0.5, 1.0, 2.0):
+        assert _emul(one, pad)[0] == _oracle(one, pad)
+    assert _emul(np.full((1, 1), 255, np.uint8), 1.0)[0] == _oracle(np.full((1, 1), 255, np.uint8), 1.0)
+    full = np.full((61, 200), 255, np.uint8)
+    for pad in (1.0, 4.0, 30.0, 31.0, 40.0):
+        assert _emul(full, pad)[0] == _oracle(full, pad)
+    # nonzero values other than 255 count as interior (the reference copies the mask into a uint8 frame)
+    odd = (safebox_mask(0)[0] // 255) * 7
+    assert _emul(odd.astype(np.uint8), 4.0)[0] == _oracle(safebox_mask(0)[0], 4.0)
+
+
+def test_workspace_bound_by_bbox_and_overflow_status():
+    m = safebox_page_masks(0, 384, 256, 12)[7]
+    ys, xs = np.nonzero(m)
+    bbox = (int(xs.min()), int(ys.min()), int(xs.max()) + 1, int(ys.max()) + 1)
+    cap = S.window_cap(*m.shape, bbox)
+    assert cap == (bbox[2] - bbox[0] + 2) * (bbox[3] - bbox[1] + 2) < S.window_cap(*m.shape)
+    assert _emul(m, 3.0, cap=cap)[0] == _oracle(m, 3.0)
+    got, rec = _emul(m, 3.0, cap=cap - 1)
+    assert int(rec["status"]) == S.ST_WORKSPACE and list(rec["mask_bbox"]) == [bbox[0], bbox[1], bbox[2] - 1, bbox[3] - 1]
+    with pytest.raises(RuntimeError):
+        S.decode(rec)
+
+
+def test_ctypes_mirrors_have_the_kernel_struct_sizes():
+    from helpers import safebox_emul_lib
+    E = safebox_emul_lib()
+    assert E.emul_safebox_sizeof(0) == C.sizeof(S.SafeBoxJob)
+    assert E.emul_safebox_sizeof(1) == C.sizeof(S.SafeBoxResult) == S.RESULT_DTYPE.itemsize
+    for name, (dt, off) in S.RESULT_DTYPE.fields.items():
+        assert getattr(S.SafeBoxResult, name).offset == off, name
