@@ -189,7 +189,8 @@ def _time_ms(fn, reps=5, warm=3):
 def measure_side_stages(page_dev, dev, peaks):
     """Stages of the path that are not part of the headline workload, timed on their own after the timed region (ms per
     call on one 1536x1024 page): the secondary RT-DETRv2 detector, a conjoined-bubble split, the exact-size LANCZOS
-    resample of the upscaled page, and the per-bubble crop upscaling with the lite model."""
+    resample of the upscaled page, the per-bubble crop upscaling with the lite model, and the safe text boxes of the
+    page's bubbles."""
     from mangatranslator_b200 import conjoined as Cj
     from mangatranslator_b200 import weights as Wt
     from mangatranslator_b200.core.image.image_utils import process_page_bubbles_device
@@ -220,6 +221,20 @@ def measure_side_stages(page_dev, dev, peaks):
         del lite
     except Exception as e:                       # side measurements must never take the headline line down
         out["error"] = repr(e)[:200]
+    try:                                         # safe text boxes of the page's bubbles (image_utils.py:173-348), one launch
+        from mangatranslator_b200 import safebox_host as Sb
+        yy, xx = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+        masks = [((((xx - (i % 3 + 0.5) * W / 3) / 140.0) ** 2 + ((yy - (i // 3 + 0.5) * H / 4) / 110.0) ** 2) <= 1.0)
+                 .to(torch.uint8).mul_(255).contiguous() for i in range(BUBBLES)]
+        recs = Sb.safe_boxes_device(masks, 6.0)
+        if int((recs["status"] != 0).sum()):
+            raise RuntimeError(f"safe box statuses {recs['status'].tolist()}")
+        ms = _time_ms(lambda: Sb.safe_boxes_device(masks, 6.0))
+        out["safe_text_boxes_12_ms"] = round(ms, 3)
+        out["safe_text_boxes_mask_gbs"] = round(BUBBLES * H * W / 1e9 / (ms * 1e-3), 1)
+        del masks
+    except Exception as e:
+        out["safebox_error"] = repr(e)[:200]
     torch.cuda.empty_cache()
     return out
 
