@@ -61,6 +61,30 @@ class CleanBatchResult:
               "mtb_clean_export_mask")
         return out
 
+    def text_boxes(self, padding_pixels: float = 4.0):
+        """Safe text box of every cleaned bubble (what the reference's renderer computes per bubble from the `mask` entry
+        of clean_speech_bubbles' records: core/pipeline.py:1657 -> core/text/text_renderer.py:162 ->
+        core/image/image_utils.py:173-348).  All bubbles of all pages in ONE launch on the exported final masks.
+        Returns, per page and detection: ((x, y, w, h), (cx, cy)), the reference's error message (str) when the safe-area
+        calculation fails for that bubble (the renderer then falls back to the padded bbox), or None for detections
+        whose cleaning failed / was skipped."""
+        from . import safebox_host as S
+        slots, masks = [], []
+        for pi, row in enumerate(self.results):
+            for di, r in enumerate(row):
+                if r is not None and r.status == 0:
+                    slots.append((pi, di))
+                    masks.append(self.export_mask(pi, di))
+        out = [[None] * len(row) for row in self.results]
+        if not masks:
+            return out
+        for (pi, di), rec in zip(slots, S.safe_boxes_device(masks, padding_pixels)):
+            try:
+                out[pi][di] = S.decode(rec)
+            except ValueError as e:
+                out[pi][di] = e.args[0]
+        return out
+
 
 def clean_batch(pages: Sequence[torch.Tensor], detections: Sequence[Sequence[Dict[str, Any]]],
                 params: H.CleanParams, *, in_place: bool = False, max_color_ranks: int = 2) -> CleanBatchResult:

@@ -120,3 +120,25 @@ def test_reference_shaped_function():
         calculate_centroid_expansion_box(np.zeros((20, 20), np.uint8))
     with pytest.raises(ImageProcessingError, match="Safe area calculation failed"):
         calculate_centroid_expansion_box(m, 500.0)
+
+
+def test_text_boxes_of_a_cleaned_page_follow_the_reference_chain():
+    """clean -> final masks -> safe boxes, all on the device (CleanBatchResult.text_boxes), against the CPU chain the
+    reference runs: clean_speech_bubbles' `mask` records -> calculate_centroid_expansion_box per bubble."""
+    import clean_oracle
+    from mangatranslator_b200 import synth
+    from mangatranslator_b200.core.image.cleaning import clean_pages_device
+    dev = torch.device("cuda")
+    pg = synth.make_page(0, 768, 1024, n_bubbles=6)
+    dets = synth.detections_from_page(pg)
+    bgr = np.ascontiguousarray(pg.image_rgb[:, :, ::-1])
+    scale = (768 * 1024 / 1e6) ** 0.5
+    batch = clean_pages_device([torch.from_numpy(bgr).to(dev)], [dets], processing_scale=scale)
+    _, bubbles = clean_oracle.clean_page(bgr, dets, processing_scale=scale)
+    got = [b for b in batch.text_boxes(4.0)[0] if b is not None]
+    assert len(got) == len(bubbles) > 0
+    n_boxes = 0
+    for g, b in zip(got, bubbles):
+        assert g == _oracle(b["mask"], 4.0)
+        n_boxes += not isinstance(g, str)
+    assert n_boxes > 0
