@@ -188,6 +188,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with 8-bit float operands (kind::f8f6f4: K = 32 per instruction, formats in the instruction descriptor).
+__device__ __forceinline__ void umma_f8f6f4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrive when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -236,6 +248,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
+
+// Instruction descriptors of the other operand formats (bit layout: cute/arch/mma_sm100_desc.hpp InstrDescriptor —
+// c_format [4,6) 1 = F32; a_format [7,10), b_format [10,13): kind::f16 0 = F16, 1 = BF16; kind::f8f6f4 0 = E4M3, 1 = E5M2).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc_e5m2(int M, int N) { return make_idesc_bf16(M, N); }  // same bits, other kind
 
 // ---- bf16 hi/lo split arithmetic (fp32-grade values carried as two bf16 planes) ----
 __device__ __forceinline__ float bf16_to_f(uint16_t b) { return __uint_as_float(static_cast<uint32_t>(b) << 16); }

@@ -68,12 +68,91 @@ shifted_desc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, 64);
 }
 
+// Mixed-kind accumulation probe: D[128][64] = A16 * B16^T (fp16, K = 64: four kind::f16 MMAs) +
+// A8 * B8^T (e5m2, K = 128: four kind::f8f6f4 MMAs of M = m8 rows) accumulated in ONE fp32 TMEM tile.  All operands are
+// K-major 128-byte rows written by TMA with the 128B swizzle (a row of 64 halves or 128 bytes).  The host compares D with
+// the float64 product; with m8 = 64 it also shows in which TMEM lanes an M = 64 instruction puts its rows.
+__global__ void __launch_bounds__(128, 1)
+mixed_kind_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmB16,
+                  const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8, float* D, int m8,
+                  int which) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA16 = smem;                       // 128 rows x 128 B
+  uint8_t* sB16 = smem + 16 * 1024;           //  64 rows x 128 B
+  uint8_t* sA8 = smem + 24 * 1024;            // 128 rows x 128 B
+  uint8_t* sB8 = smem + 40 * 1024;            //  64 rows x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 48 * 1024);
+  uint64_t* mma_bar = bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(mma_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (128 + 64 + 128 + 64) * 128);
+    tma_load_2d(sA16, &tmA16, bar, 0, 0);
+    tma_load_2d(sB16, &tmB16, bar, 0, 0);
+    tma_load_2d(sA8, &tmA8, bar, 0, 0);
+    tma_load_2d(sB8, &tmB8, bar, 0, 0);
+  }
+  if (warp == 1) {
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    if (lane == 0) {
+      bool acc = false;
+      if (which & 1) {
+        const uint32_t idesc = make_idesc_f16(128, 64);
+        for (int k = 0; k < 4; ++k) {
+          umma_bf16(tmem_base, make_sdesc_sw128(smem_u32(sA16) + k * 32, 1024, 0),
+                    make_sdesc_sw128(smem_u32(sB16) + k * 32, 1024, 0), idesc, acc);
+          acc = true;
+        }
+      }
+      if (which & 2) {
+        const uint32_t idesc = make_idesc_e5m2(m8, 64);
+        for (int k = 0; k < 4; ++k) {
+          umma_f8f6f4(tmem_base, make_sdesc_sw128(smem_u32(sA8) + k * 32, 1024, 0),
+                      make_sdesc_sw128(smem_u32(sB8) + k * 32, 1024, 0), idesc, acc);
+          acc = true;
+        }
+      }
+      umma_commit(mma_bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(mma_bar, 0);
+  tc_fence_after();
+  const int r = warp * 32 + lane;
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    uint32_t acc[16];
+    tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, acc);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[r * 64 + c0 + j] = __uint_as_float(acc[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
 // MMA rate probe: one elected lane per CTA issues `iters` rounds of 36 tcgen05.mma (nine row-shifted A views x four
 // k16 slices, like one output tile of the halo kernels) on arbitrary shared-memory contents and the CTA reports the
 // clock64 span from first issue to commit arrival.  The shape is a template parameter and the issue loop is branch-free
 // so that the tensor pipe, not the issuing thread, is what is measured.  M2 > 0 appends a second MMA of shape M2 x N2
 // after each one (the mixed shapes of the bf16x3 schemes).
-template <int M1, int N1, int M2, int N2>
+// FP8 = 1: the FIRST MMA is kind::f8f6f4 (e5m2, K = 32); FP8 = 2: the SECOND one is, and it accumulates into the same TMEM
+// columns as the first (the fp16 + e5m2-correction scheme of DESIGN.md §8.0: mixed kinds into one fp32 accumulator).
+template <int M1, int N1, int M2, int N2, int FP8 = 0>
 __global__ void __launch_bounds__(64, 1) mma_rate_kernel(long long* cycles, int iters, int a_sbo, int a_shift) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -108,8 +187,12 @@ __global__ void __launch_bounds__(64, 1) mma_rate_kernel(long long* cycles, int 
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = make_sdesc_sw128(a0 + k * 32, a_sbo, 0);
             const uint64_t db = make_sdesc_sw128(b0 + k * 32, 1024, 0);
-            umma_bf16(0, da, db, id1, (it | tap | k) ? 1u : 0u);
-            if (M2 > 0) umma_bf16(256, da, db, id2, (it | tap | k) ? 1u : 0u);
+            if (FP8 == 1) umma_f8f6f4(0, da, db, id1, (it | tap | k) ? 1u : 0u);
+            else umma_bf16(0, da, db, id1, (it | tap | k) ? 1u : 0u);
+            if (M2 > 0) {
+              if (FP8 == 2) umma_f8f6f4(0, da, db, id2, 1u);
+              else umma_bf16(256, da, db, id2, (it | tap | k) ? 1u : 0u);
+            }
           }
         }
       }
@@ -127,18 +210,20 @@ __global__ void __launch_bounds__(64, 1) mma_rate_kernel(long long* cycles, int 
 }  // namespace
 
 // pattern: 0 M128N64, 1 M128N128, 2 M128N256, 3 M128N128+M128N64, 4 M128N240, 5 M64N240, 6 M64N256, 7 M64N128,
-//          8 M128N240+M64N240, 9 M64N64
+//          8 M128N240+M64N240, 9 M64N64, 10 M128N240 e5m2, 11 M64N240 e5m2, 12 M128N240 f16 + M64N240 e5m2 into one
+//          accumulator, 13 M128N240 f16 + M128N240 e5m2 into one accumulator
 extern "C" int mtb_exp_mma_rate(long long* cycles, int ctas, int pattern, int iters, int a_sbo, int a_shift, int a_off,
                                 void* stream) {
   (void)a_off;
   const size_t smem = 1024 + (48 + 144) * 1024 + 64;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define MTB_RATE(M1, N1, M2, N2)                                                                              \
-  do {                                                                                                        \
-    MTB_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel<M1, N1, M2, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     static_cast<int>(smem)));                                                \
-    mma_rate_kernel<M1, N1, M2, N2><<<ctas, 64, smem, st>>>(cycles, iters, a_sbo, a_shift);                   \
+#define MTB_RATE8(M1, N1, M2, N2, F8)                                                                             \
+  do {                                                                                                            \
+    MTB_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel<M1, N1, M2, N2, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     static_cast<int>(smem)));                                                    \
+    mma_rate_kernel<M1, N1, M2, N2, F8><<<ctas, 64, smem, st>>>(cycles, iters, a_sbo, a_shift);                   \
   } while (0)
+#define MTB_RATE(M1, N1, M2, N2) MTB_RATE8(M1, N1, M2, N2, 0)
   switch (pattern) {
     case 0: MTB_RATE(128, 64, 0, 0); break;
     case 1: MTB_RATE(128, 128, 0, 0); break;
@@ -149,9 +234,14 @@ extern "C" int mtb_exp_mma_rate(long long* cycles, int ctas, int pattern, int it
     case 6: MTB_RATE(64, 256, 0, 0); break;
     case 7: MTB_RATE(64, 128, 0, 0); break;
     case 8: MTB_RATE(128, 240, 64, 240); break;
+    case 10: MTB_RATE8(128, 240, 0, 0, 1); break;
+    case 11: MTB_RATE8(64, 240, 0, 0, 1); break;
+    case 12: MTB_RATE8(128, 240, 64, 240, 2); break;
+    case 13: MTB_RATE8(128, 240, 128, 240, 2); break;
     default: MTB_RATE(64, 64, 0, 0); break;
   }
 #undef MTB_RATE
+#undef MTB_RATE8
   MTB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -181,6 +271,33 @@ extern "C" int mtb_exp_shifted_desc(const void* A /* bf16 [512][64] */, const vo
                                    static_cast<int>(smem)));
   shifted_desc_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, D, shift_rows, sbo_bytes,
                                                                           base_offset);
+  MTB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+
+// which: bit 0 = the four fp16 MMAs, bit 1 = the four e5m2 MMAs (m8 = 64 or 128 rows).  With bit 0 clear and m8 = 64 the
+// accumulator is not initialised in the lanes an M = 64 instruction does not write: zero D first and read where rows land.
+extern "C" int mtb_exp_mixed_kind(const void* A16 /* fp16 [128][64] */, const void* B16 /* fp16 [64][64] */,
+                                  const void* A8 /* e5m2 [128][128] */, const void* B8 /* e5m2 [64][128] */,
+                                  float* D /* [128][64] */, int m8, int which, void* stream) {
+  MTB_REQUIRE(m8 == 64 || m8 == 128, "mtb_exp_mixed_kind: m8 must be 64 or 128");
+  CUtensorMap t[4];
+  const void* ptrs[4] = {A16, B16, A8, B8};
+  const uint64_t rows[4] = {128, 64, 128, 64};
+  for (int i = 0; i < 4; ++i) {
+    const bool half = i < 2;
+    const uint64_t dims[2] = {half ? 64u : 128u, rows[i]};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {half ? 64u : 128u, static_cast<uint32_t>(rows[i])};
+    if (encode_tmap(&t[i], half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ptrs[i], dims,
+                    strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B))
+      return -3;
+  }
+  const size_t smem = 1024 + 48 * 1024 + 64;
+  MTB_CUDA_OK(cudaFuncSetAttribute(mixed_kind_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+  mixed_kind_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(t[0], t[1], t[2], t[3], D, m8, which);
   MTB_CUDA_OK(cudaGetLastError());
   return 0;
 }
