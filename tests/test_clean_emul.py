@@ -139,3 +139,92 @@ def test_emulated_kernel_fuzz_against_oracle():
                 tc = tuple(R.text_color)[:3] if R.text_color[3] == -1 else tuple(R.text_color)[:c]
             assert tc == o.text_color, it
     assert n_ok > 20
+
+
+# ---- wider fuzz: masks the synthetic pages never produce ---------------------------------------------------------------
+def _exotic_case(rng, it):
+    h, w = int(rng.integers(40, 420)), int(rng.integers(40, 420))
+    c = 4 if rng.random() < 0.3 else 3
+    scale = float(rng.choice([0.5, 0.8868, 1.0, 1.2541, 2.0, 3.1]))
+    img = rng.integers(0, 256, size=(h, w, c), dtype=np.uint8)
+    mask = np.zeros((h, w), np.uint8)
+    kind = int(rng.integers(0, 6))
+    if kind == 0:      # several blobs
+        for _ in range(int(rng.integers(1, 5))):
+            cv2.ellipse(mask, (int(rng.integers(0, w)), int(rng.integers(0, h))), (int(rng.integers(3, w // 2 + 4)), int(rng.integers(3, h // 2 + 4))), int(rng.integers(0, 180)), 0, 360, 255, -1)
+    elif kind == 1:    # ragged SAM-like: blob + noise holes + specks
+        cv2.ellipse(mask, (w // 2, h // 2), (max(3, w // 3), max(3, h // 3)), int(rng.integers(0, 180)), 0, 360, 255, -1)
+        mask[rng.random((h, w)) < 0.01] = 0
+        mask[rng.random((h, w)) < 0.003] = 255
+    elif kind == 2:    # polygon
+        pts = rng.integers(0, [w, h], size=(int(rng.integers(3, 9)), 2)).astype(np.int32)
+        cv2.fillPoly(mask, [pts], 255)
+    elif kind == 3:    # rectangle touching borders
+        x0, y0 = int(rng.integers(0, w // 2)), int(rng.integers(0, h // 2))
+        mask[y0:int(rng.integers(y0 + 1, h + 1)), x0:int(rng.integers(x0 + 1, w + 1))] = 255
+        if rng.random() < 0.5: mask[:, :] = np.where(rng.random((h, w)) < 0.0005, 0, mask)
+    elif kind == 4:    # full frame
+        mask[:] = 255
+    else:              # thin strips
+        for _ in range(int(rng.integers(1, 4))):
+            cv2.line(mask, (int(rng.integers(0, w)), int(rng.integers(0, h))), (int(rng.integers(0, w)), int(rng.integers(0, h))), 255, int(rng.integers(1, 40)))
+    if not mask.any(): return None
+    bright = 255 if rng.random() < 0.7 else 5
+    sel = mask > 0
+    r = rng.random()
+    if r < 0.6:
+        img[sel] = np.clip(bright + rng.integers(-25, 26, size=(int(sel.sum()), c)), 0, 255).astype(np.uint8)
+    elif r < 0.8:    # gradient interior
+        gx = np.linspace(0, 255, w)[None, :, None].repeat(h, 0).repeat(c, 2).astype(np.uint8)
+        img[sel] = gx[sel]
+    for _ in range(int(rng.integers(0, 60))):
+        p0 = (int(rng.integers(0, w)), int(rng.integers(0, h)))
+        col = tuple(int(v) for v in (rng.integers(0, 60, size=c) if bright == 255 else rng.integers(200, 256, size=c)))
+        if rng.random() < 0.2:
+            cv2.circle(img, p0, int(rng.integers(1, 25)), col, -1 if rng.random() < 0.5 else int(rng.integers(1, 4)))
+        else:
+            cv2.line(img, p0, (p0[0] + int(rng.integers(-40, 41)), p0[1] + int(rng.integers(-40, 41))), col, int(rng.integers(1, 6)))
+    img = np.ascontiguousarray(img)
+    gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY if c == 3 else cv2.COLOR_BGRA2GRAY)
+    thr = int(rng.choice([200, 180, 128, 220, 250, 60]))
+    otsu = bool(rng.random() < 0.3)
+    shrink = float(rng.choice([5, 0, 2, 8, 12, 20, 1]))
+    ys, xs = np.nonzero(mask)
+    bbox = (int(xs.min()), int(ys.min()), int(xs.max()) + 1, int(ys.max()) + 1)
+    if rng.random() < 0.2:   # detection bbox not equal to the mask bbox
+        bbox = (max(0, bbox[0] - int(rng.integers(0, 9))), max(0, bbox[1] - int(rng.integers(0, 9))), min(w, bbox[2] + int(rng.integers(0, 9))), min(h, bbox[3] + int(rng.integers(0, 9))))
+    nbs = None
+    if rng.random() < 0.35:
+        nbs = [(bbox[2] - int(rng.integers(0, 30)), bbox[1] + int(rng.integers(-20, 20)), bbox[2] + int(rng.integers(20, 100)), bbox[3] + int(rng.integers(-20, 20)))]
+        if rng.random() < 0.4:
+            nbs.append((bbox[0] - int(rng.integers(20, 100)), bbox[1] + int(rng.integers(-20, 20)), bbox[0] + int(rng.integers(0, 30)), bbox[3] + int(rng.integers(-20, 20))))
+    kd, ke, eff, min_area = clean_oracle.scaled_params(shrink, scale)
+    o = clean_oracle.clean_bubble(mask, gray, img, threshold=thr, otsu=otsu, shrink_px=eff, kd=kd, ke=ke, min_area=min_area, bbox=bbox, neighbors=nbs, scale=scale)
+    params = H.build_params(thr, otsu, shrink, scale, retry_otsu=False)
+    R, m = emul_clean_bubble(img, mask, bbox, params, nbs)
+    desc = dict(it=it, kind=kind, shape=(h, w, c), scale=scale, thr=thr, otsu=otsu, shrink=shrink, nbs=nbs, bbox=bbox)
+    if (R.status == 0) != o.ok: return ("status", R.status, o.reason, desc)
+    if o.ok:
+        if not np.array_equal(m, o.mask): return ("mask", int((m != o.mask).sum()), desc)
+        if tuple(R.fill_bgr) != tuple(o.fill_bgr): return ("fill", tuple(R.fill_bgr), o.fill_bgr, desc)
+        if tuple(R.text_bbox) != tuple(o.text_bbox): return ("text_bbox", tuple(R.text_bbox), o.text_bbox, desc)
+        tc = None
+        if R.has_text_color: tc = tuple(R.text_color)[:3] if R.text_color[3] == -1 else tuple(R.text_color)[:c]
+        if tc != o.text_color: return ("text_color", tc, o.text_color, desc)
+        return "ok"
+    return "fail_both"
+
+
+def test_emulated_kernel_fuzz_exotic_masks():
+    """Several blobs, ragged SAM-like masks with pin-holes and specks, polygons, border-touching rectangles, full frames,
+    thin strips; gradient interiors, circles, detection boxes larger than the mask, two conjoined neighbours, scales up to
+    3.1, thresholds 60..250.  (Seven seeds x 400 cases of this generator ran clean when the test was written.)"""
+    rng = np.random.default_rng(2024)
+    seen = {"ok": 0, "fail_both": 0}
+    for it in range(300):
+        r = _exotic_case(rng, it)
+        if r is None:
+            continue
+        assert not isinstance(r, tuple), r
+        seen[r] += 1
+    assert seen["ok"] > 150 and seen["fail_both"] > 20
