@@ -9,6 +9,7 @@ _MODULES = [
     ("utils.logging", "mangatranslator_b200.utils.logging"),
     ("utils.exceptions", "mangatranslator_b200.utils.exceptions"),
     ("core", "mangatranslator_b200.core"),
+    ("core._version", "mangatranslator_b200.core._version"),
     ("core.scaling", "mangatranslator_b200.core.scaling"),
     ("core.device", "mangatranslator_b200.core.device"),
     ("core.caching", "mangatranslator_b200.core.caching"),

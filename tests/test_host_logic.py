@@ -10,6 +10,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
+H_ROOT = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+
 
 def test_scaling_matches_reference_when_present():
     import _refimport
@@ -177,3 +179,29 @@ def test_yolo_oracle_nms_is_pinned_to_torchvision():
         b, s = boxes[order], scores[order]
         for thr in (0.45, 0.7):
             assert torch.equal(yolo_oracle.nms(b, s, thr), torchvision.ops.nms(b, s, thr))
+
+
+def test_core_package_exports_the_reference_names_lazily():
+    """`from core import ...` (core/__init__.py:8-41): hot-path names resolve to this build's objects, names of
+    subsystems outside the build raise AttributeError, and importing the package alone stays cheap."""
+    import importlib
+    import subprocess
+    import sys
+    import mangatranslator_b200.core as core
+    from mangatranslator_b200.core.caching import UnifiedCache, get_cache
+    from mangatranslator_b200.core.image.cleaning import clean_speech_bubbles
+    from mangatranslator_b200.core.pipeline import batch_translate_images
+    assert core.get_cache is get_cache and core.UnifiedCache is UnifiedCache
+    assert core.clean_speech_bubbles is clean_speech_bubbles and core.batch_translate_images is batch_translate_images
+    assert core.__version_info__ == (1, 22, 2) and core.__version__.startswith("1.22.2")
+    for name in ("render_text_skia", "call_translation_api_batch", "FluxKontextInpainter", "OutsideTextDetector"):
+        try:
+            getattr(core, name)
+            raised = False
+        except AttributeError as e:
+            raised = "outside the B200 hot path" in str(e)
+        assert raised, name
+    code = "import sys; import mangatranslator_b200.core; print('torch' in sys.modules)"
+    out = subprocess.check_output([sys.executable, "-c", code], cwd=H_ROOT).decode().strip()
+    assert out == "False"
+    assert importlib.import_module("mangatranslator_b200.core._version").__version__ == core.__version__
