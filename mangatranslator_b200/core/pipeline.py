@@ -35,7 +35,6 @@ from mangatranslator_b200.core.ml.model_manager import get_model_manager
 from mangatranslator_b200.utils.exceptions import CancellationError, ImageProcessingError, ValidationError
 from mangatranslator_b200.utils.logging import log_message
 
-IMAGE_EXTS = {".png", ".jpg", ".jpeg", ".webp", ".bmp"}
 
 
 def _processing_scale(width: int, height: int, auto: bool = True) -> float:
@@ -59,6 +58,42 @@ def _clean_speech_bubbles_for_page(pil_image, config: MangaTranslatorConfig, bub
         return pil_image, []
 
 
+def _target_mode(config: MangaTranslatorConfig, image_path, output_path) -> str:
+    """pipeline.py:702-712: RGB for JPEG output (or `auto` with a .jpg/.jpeg target), RGBA for everything else."""
+    ext = (Path(output_path) if output_path else Path(image_path)).suffix.lower()
+    fmt = config.output.output_format
+    return "RGB" if fmt == "jpeg" or (fmt == "auto" and ext in (".jpg", ".jpeg")) else "RGBA"
+
+
+def save_image(image: Image.Image, output_path, jpeg_quality: int = 95, png_compression: int = 2, verbose: bool = False):
+    """What reaches the file in the reference's save_image_with_compression (image_utils.py:59-170): JPEG on a white
+    background with the clamped quality, lossless PNG / WEBP, unknown extensions become .png.  The reference re-packs the
+    PNG stream with oxipng; that is lossless, so the decoded pixels are identical while the file bytes differ (image
+    encoding is outside this build).  Returns the path written."""
+    path = Path(output_path)
+    ext = path.suffix.lower()
+    try:
+        path.parent.mkdir(parents=True, exist_ok=True)
+        if ext in (".jpg", ".jpeg"):
+            if image.mode in ("RGBA", "LA"):
+                flat = Image.new("RGB", image.size, (255, 255, 255))
+                flat.paste(image, mask=image.split()[-1])
+                image = flat
+            elif image.mode != "RGB":
+                image = image.convert("RGB")
+            image.save(path, format="JPEG", quality=max(1, min(int(jpeg_quality), 100)))
+        elif ext == ".webp":
+            image.save(path, format="WEBP", lossless=True)
+        else:
+            if ext != ".png":
+                log_message(f"Warning: Unknown output extension '{ext}'. Saving as PNG.", verbose=verbose, always_print=True)
+                path = path.with_suffix(".png")
+            image.save(path, format="PNG", compress_level=min(6, max(0, int(png_compression))))
+    except Exception as e:
+        raise ImageProcessingError(f"Failed to save image to {output_path}") from e
+    return path
+
+
 def translate_and_render(image_path, config: MangaTranslatorConfig, output_path=None, cancellation_manager=None,
                          previous_context_images=None, previous_context_texts=None,
                          previous_context_texts_provider=None, ocr_texts_out=None) -> Image.Image:
@@ -69,12 +104,13 @@ def translate_and_render(image_path, config: MangaTranslatorConfig, output_path=
                               "(translation/rendering are outside scope, SURVEY.md §8)")
     if cancellation_manager is not None and cancellation_manager.is_cancelled():
         raise CancellationError("Process cancelled by user.")
+    image_path = Path(image_path)
     try:
         pil = Image.open(image_path)
         pil.load()
     except Exception as e:
         raise ImageProcessingError(f"Error loading image {image_path}: {e}")
-    target_mode = "RGBA" if (config.output.output_format == "png" and pil.mode in ("RGBA", "LA")) else "RGB"
+    target_mode = _target_mode(config, image_path, output_path)
     pil = convert_image_to_target_mode(pil, target_mode, verbose)
     if config.preprocessing.enabled:
         pil = upscale_image(pil, config.preprocessing.factor, model_type="model_lite", verbose=verbose)
@@ -86,7 +122,7 @@ def translate_and_render(image_path, config: MangaTranslatorConfig, output_path=
         get_cache().set_current_image(pil, verbose)
         try:
             bubbles, _ = detect_speech_bubbles(
-                Path(image_path), config.yolo_model_path, config.detection.confidence, verbose=verbose,
+                image_path, config.yolo_model_path, config.detection.confidence, verbose=verbose,
                 device=config.device, seg_model=config.detection.seg_model,
                 conjoined_detection=config.detection.conjoined_detection,
                 conjoined_confidence=config.detection.conjoined_confidence, image_override=pil,
@@ -103,55 +139,208 @@ def translate_and_render(image_path, config: MangaTranslatorConfig, output_path=
     if output_path:
         if out.mode != target_mode:
             out = out.convert(target_mode)
-        Path(output_path).parent.mkdir(parents=True, exist_ok=True)
-        out.save(output_path)
+        try:                        # pipeline.py:2001-2018: a failed save is logged and re-raised
+            save_image(out, output_path, config.output.jpeg_quality, config.output.png_compression, verbose)
+        except ImageProcessingError as e:
+            log_message(f"Failed to save image: {e}", always_print=True)
+            raise
     log_message(f"Processing completed in {time.time() - start:.2f}s", always_print=True)
     return out
 
 
-def _natural_key(p: Path):
-    return [int(t) if t.isdigit() else t.lower() for t in re.split(r"(\d+)", p.name)]
+_DIGITS = re.compile(r"(\d+)")
+BATCH_EXTS = (".jpg", ".jpeg", ".png", ".webp")                    # pipeline.py:2533
+
+
+def natural_path_key(path: Path):
+    """Reading-order sort of page files (pipeline.py:133-142): per path component, digit runs compare as numbers and sort
+    before text, text compares case-insensitively, the raw token breaks ties."""
+    return tuple(tuple((0, int(t), t) if t.isdigit() else (1, t.lower(), t) for t in _DIGITS.split(part) if t)
+                 for part in path.parts)
+
+
+def resolve_output_path(img_path: Path, input_dir: Path, output_dir: Path, config: MangaTranslatorConfig,
+                        preserve_structure: bool):
+    """(output file, display name, error key) of one page (pipeline.py:2027-2064): `<stem>_translated` + the extension
+    output_format asks for ("jpeg" -> .jpg, "png" -> .png, "auto" / anything else -> the source's), under the mirrored
+    sub-directory when the structure is preserved."""
+    if preserve_structure:
+        rel = img_path.relative_to(input_dir)
+        folder = output_dir / rel.parent
+        folder.mkdir(parents=True, exist_ok=True)
+        shown = key = str(rel)
+        stem = rel.stem
+    else:
+        folder, shown, key, stem = output_dir, img_path.name, img_path.name, img_path.stem
+    src_ext = img_path.suffix.lower()
+    fmt = config.output.output_format
+    if fmt not in ("jpeg", "png", "auto"):
+        log_message(f"Warning: Invalid output_format '{fmt}' in config. Using original extension '{src_ext}'.",
+                    always_print=True)
+    ext = {"jpeg": ".jpg", "png": ".png"}.get(fmt, src_ext)
+    return folder / f"{stem}_translated{ext}", shown, key
+
+
+def resolve_source_path(img_path, source_path_map=None) -> str:
+    """utils/path_list.py:12-33: absolute path of a page, mapped back to where the UI / CLI copied it from."""
+    path = Path(img_path)
+    try:
+        resolved = str(path.resolve())
+    except OSError:
+        resolved = str(path)
+    if source_path_map:
+        for k in (resolved, str(path)):
+            if k in source_path_map:
+                return source_path_map[k]
+    return resolved
+
+
+def write_failed_paths(output_dir, paths) -> Optional[Path]:
+    """utils/path_list.py:36-75: unique absolute paths, one per line, to <output_dir>/failed_paths.txt."""
+    unique: List[str] = []
+    for raw in paths:
+        text = "" if raw is None else str(raw).strip()
+        if not text:
+            continue
+        try:
+            text = str(Path(text).resolve())
+        except OSError:
+            pass
+        if text not in unique:
+            unique.append(text)
+    if not unique:
+        return None
+    try:
+        out = Path(output_dir)
+        out.mkdir(parents=True, exist_ok=True)
+        (out / "failed_paths.txt").write_text("\n".join(unique) + "\n", encoding="utf-8")
+        return out / "failed_paths.txt"
+    except OSError as e:
+        log_message(f"Warning: failed to write failed_paths.txt: {e}", always_print=True)
+        return None
+
+
+def _list_batch_images(input_dir: Path, preserve_structure: bool) -> List[Path]:
+    if preserve_structure:
+        files = [Path(root) / f for root, _, names in os.walk(input_dir) for f in names]
+        files = [f for f in files if f.suffix.lower() in BATCH_EXTS]
+        return sorted(files, key=lambda f: natural_path_key(f.relative_to(input_dir)))
+    files = [f for f in input_dir.iterdir() if f.is_file() and f.suffix.lower() in BATCH_EXTS]
+    return sorted(files, key=lambda f: natural_path_key(Path(f.name)))
 
 
 def batch_translate_images(input_dir, config: MangaTranslatorConfig, output_dir=None, progress_callback=None,
                            preserve_structure: bool = False, cancellation_manager=None, source_path_map=None) -> dict:
-    """Reference contract (pipeline.py:2481-2511): processes every image of `input_dir` in natural order and returns
-    {success_count, error_count, errors, failed_image_paths[, failed_paths_file]}.  When launched under torchrun the
-    pages are sharded across the ranks by PageShardCoordinator and rank 0 returns the merged result."""
+    """Reference contract (pipeline.py:2481-2731): the images of `input_dir` (its sub-directories too when
+    `preserve_structure`) in natural order, each written as `<stem>_translated.<ext>`; returns {success_count,
+    error_count, errors{name: message}, failed_image_paths[source paths][, failed_paths_file][, retry_*]}; failed pages
+    are retried once when `config.retry_failed_once`; a cancellation propagates as CancellationError.
+    Under torchrun the sorted page list is sharded over the ranks (`PageShardCoordinator`: page i goes to rank i mod R,
+    no data-path collective); every rank returns its own counts and rank 0 the merged result with the failure file."""
+    empty = {"success_count": 0, "error_count": 0, "errors": {}, "failed_image_paths": []}
     input_dir = Path(input_dir)
-    files = sorted([p for p in input_dir.rglob("*") if p.suffix.lower() in IMAGE_EXTS], key=_natural_key)
-    out_dir = Path(output_dir) if output_dir else input_dir / "output_translated"
+    if not input_dir.is_dir():
+        log_message(f"Input path '{input_dir}' is not a directory", always_print=True)
+        return empty
+    out_dir = Path(output_dir) if output_dir else Path("./output") / time.strftime("%Y%m%d_%H%M%S")
+    out_dir.mkdir(parents=True, exist_ok=True)
+    files = _list_batch_images(input_dir, preserve_structure)
+    if not files:
+        log_message(f"No image files found in '{input_dir}'", always_print=True)
+        return empty
     coord = PageShardCoordinator()
-    mine = coord.shard(list(enumerate(files)))
+    mine = coord.shard(files)
+    total = len(mine)
+    t0 = time.time()
+    if progress_callback:
+        progress_callback(0.0, f"Starting batch processing of {total} images...")
+    log_message(f"Starting batch processing: {len(files)} images" +
+                (f" ({total} on rank {coord.rank} of {coord.world})" if coord.world > 1 else ""), always_print=True)
     res = {"success_count": 0, "error_count": 0, "errors": {}, "failed_image_paths": []}
-    for k, (idx, path) in enumerate(mine):
+    failed_jobs = []
+    for i, path in enumerate(mine):
+        out_path, shown, key = resolve_output_path(path, input_dir, out_dir, config, preserve_structure)
         if cancellation_manager is not None and cancellation_manager.is_cancelled():
-            break
-        rel = path.relative_to(input_dir) if preserve_structure else Path(path.name)
-        try:
-            translate_and_render(path, config, out_dir / rel, cancellation_manager)
-            res["success_count"] += 1
-        except Exception as e:
-            res["error_count"] += 1
-            res["errors"][str(path)] = str(e)
-            res["failed_image_paths"].append(str(path))
+            raise CancellationError("Batch process cancelled by user.")
         if progress_callback:
-            progress_callback((k + 1) / max(len(mine), 1), f"Processed {k + 1}/{len(mine)}")
+            progress_callback(i / total, f"Processing image {i + 1}/{total}: {shown}")
+        log_message(f"Processing {i + 1}/{total}: {shown}", always_print=True)
+        try:
+            translate_and_render(path, config, out_path, cancellation_manager=cancellation_manager)
+            res["success_count"] += 1
+            note = f"Completed {i + 1}/{total} images"
+        except CancellationError:
+            raise
+        except Exception as e:
+            log_message(f"Error processing {shown}: {e}", always_print=True)
+            src = resolve_source_path(path, source_path_map)
+            res["error_count"] += 1
+            res["errors"][key] = str(e)
+            res["failed_image_paths"].append(src)
+            failed_jobs.append((key, path, src))
+            note = f"Completed {i + 1}/{total} images (with errors)"
+        if progress_callback:
+            progress_callback((i + 1) / total, note)
+    cancelled = cancellation_manager is not None and cancellation_manager.is_cancelled()
+    if getattr(config, "retry_failed_once", False) and failed_jobs and not cancelled:
+        _retry_failed(failed_jobs, res, config, input_dir, out_dir, preserve_structure, progress_callback, cancellation_manager)
+    if progress_callback:
+        progress_callback(1.0, "Processing complete")
     parts = coord.gather(res)
-    if coord.rank != 0:
+    if coord.rank != 0 or parts is None:
         return res
     merged = {"success_count": 0, "error_count": 0, "errors": {}, "failed_image_paths": []}
-    for p in parts:
-        merged["success_count"] += p["success_count"]
-        merged["error_count"] += p["error_count"]
-        merged["errors"].update(p["errors"])
-        merged["failed_image_paths"].extend(p["failed_image_paths"])
-    if merged["failed_image_paths"]:
-        out_dir.mkdir(parents=True, exist_ok=True)
-        fp = out_dir / "failed_paths.txt"
-        fp.write_text("\n".join(merged["failed_image_paths"]))
-        merged["failed_paths_file"] = str(fp)
+    for part in parts:
+        for k, v in part.items():
+            if isinstance(v, int):
+                merged[k] = merged.get(k, 0) + v
+            elif isinstance(v, dict):
+                merged.setdefault(k, {}).update(v)
+            else:
+                merged.setdefault(k, []).extend(v)
+    dt = time.time() - t0
+    log_message(f"Batch complete: {merged['success_count']}/{len(files)} images in {dt:.2f}s "
+                f"({dt / len(files):.2f}s/image)", always_print=True)
+    if merged["error_count"] > 0:
+        log_message(f"Failed: {merged['error_count']} images", always_print=True)
+        for name, msg in merged["errors"].items():
+            log_message(f"  - {name}: {msg}", always_print=True)
+    failed_file = write_failed_paths(out_dir, merged["failed_image_paths"])
+    if failed_file:
+        merged["failed_paths_file"] = str(failed_file)
     return merged
+
+
+def _retry_failed(failed_jobs, res, config, input_dir, out_dir, preserve_structure, progress_callback, cancellation_manager):
+    """One more attempt per failed page (pipeline.py:2081-2212); updates the counts, the error table and the failed
+    path list in place and records retry_attempted_count / retry_success_count / retry_failed_count."""
+    attempted = recovered = still = 0
+    n = len(failed_jobs)
+    log_message(f"Retrying {n} failed image(s) once...", always_print=True)
+    for i, (key, path, src) in enumerate(failed_jobs):
+        if cancellation_manager is not None and cancellation_manager.is_cancelled():
+            break
+        out_path, shown, _ = resolve_output_path(path, input_dir, out_dir, config, preserve_structure)
+        if progress_callback:
+            progress_callback(0.95 + 0.05 * (i / max(n, 1)), f"Retrying failed image {i + 1}/{n}: {shown}")
+        attempted += 1
+        try:
+            translate_and_render(path, config, out_path, cancellation_manager=cancellation_manager)
+        except CancellationError:
+            attempted -= 1
+            break
+        except Exception as e:
+            res["errors"][key] = str(e)
+            still += 1
+            log_message(f"Retry failed for {shown}: {e}", always_print=True)
+            continue
+        res["success_count"] += 1
+        res["error_count"] = max(0, res["error_count"] - 1)
+        res["errors"].pop(key, None)
+        res["failed_image_paths"] = [p for p in res["failed_image_paths"] if p != src]
+        recovered += 1
+        log_message(f"Retry succeeded: {shown}", always_print=True)
+    res["retry_attempted_count"], res["retry_success_count"], res["retry_failed_count"] = attempted, recovered, still
 
 
 # ---- device-resident batch engine --------------------------------------------------------------------------------------

@@ -1,0 +1,214 @@
+"""CPU: host side of the page driver (core/pipeline.py) against the reference's own helpers (live, when the checkout is
+present): natural page order, output naming, source-path mapping, failed-path file, target mode, save rules, config
+defaults; and the batch flow itself (counts, error keys, retry pass, cancellation, sharding over two gloo ranks) with
+`translate_and_render` replaced by a stand-in (the real one needs a GPU)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+from PIL import Image
+
+import _refimport
+from helpers import ROOT
+from mangatranslator_b200.core import pipeline as P
+from mangatranslator_b200.core.config import (CleaningConfig, DetectionConfig, MangaTranslatorConfig, OutputConfig,
+                                              PreprocessingConfig)
+
+needs_ref = pytest.mark.skipif(not _refimport.available(), reason="reference checkout not present (GPU box)")
+
+NAMES = ["10.png", "2.png", "page_2.jpg", "page_10.jpg", "Page_3.jpg", "a/1.png", "a/10.png", "B/2.png", "b/2.png",
+         "001.png", "1.png", "x9y10.webp", "x9y2.webp", "ch2/p1.png", "ch10/p1.png", "ch2/p01.png", "é.png", "Z.PNG"]
+
+
+def _ref():
+    _refimport.import_reference()
+    import core.pipeline as RP
+    import utils.path_list as RL
+    return RP, RL
+
+
+def test_natural_order_known_cases():
+    order = sorted(["10.png", "2.png", "1.png", "page_10.jpg", "page_2.jpg", "Page_3.jpg"], key=lambda n: P.natural_path_key(Path(n)))
+    # the raw token breaks case-insensitive ties before the next token is looked at: "Page_" < "page_"
+    assert order == ["1.png", "2.png", "10.png", "Page_3.jpg", "page_2.jpg", "page_10.jpg"]
+
+
+@needs_ref
+def test_natural_order_and_output_naming_match_live_reference(tmp_path):
+    RP, RL = _ref()
+    paths = [Path(n) for n in NAMES]
+    assert sorted(paths, key=P.natural_path_key) == sorted(paths, key=RP._natural_path_sort_key)
+    rng = np.random.default_rng(0)
+    rand = [Path("/".join("".join(rng.choice(list("aAbB019_ ."), size=rng.integers(1, 7))) for _ in range(rng.integers(1, 4))))
+            for _ in range(300)]
+    rand = [p for p in rand if all(part not in ("", ".", "..") for part in p.parts)]
+    assert sorted(rand, key=P.natural_path_key) == sorted(rand, key=RP._natural_path_sort_key)
+    inp, out = tmp_path / "in", tmp_path / "out"
+    for fmt in ("png", "jpeg", "auto", "tiff"):
+        cfg = MangaTranslatorConfig()
+        cfg.output.output_format = fmt
+        for n in NAMES:
+            for keep in (False, True):
+                ours = P.resolve_output_path(inp / n, inp, out, cfg, keep)
+                theirs = RP._resolve_output_path(inp / n, inp, out, cfg, keep)
+                assert ours == theirs, (fmt, n, keep)
+    # source path mapping and the failed-path file
+    f = tmp_path / "in" / "x.png"
+    f.parent.mkdir(parents=True, exist_ok=True)
+    f.write_bytes(b"")
+    for m in (None, {}, {str(f.resolve()): "/orig/x.png"}, {str(f): "/orig/y.png"}, {"other": "z"}):
+        assert P.resolve_source_path(f, m) == RL.resolve_source_path(f, m)
+    lists = [[], [None, "", "  "], [str(f), str(f), " " + str(f) + " ", "rel/a.png", None, "/abs/b.png"]]
+    for i, lst in enumerate(lists):
+        a, b = P.write_failed_paths(tmp_path / f"o{i}", lst), RL.write_failed_paths(tmp_path / f"r{i}", lst)
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a.name == b.name and a.read_text() == b.read_text()
+
+
+@needs_ref
+def test_config_defaults_match_live_reference():
+    _refimport.import_reference()
+    import dataclasses
+    import core.config as RC
+    for ours, theirs in ((DetectionConfig, RC.DetectionConfig), (CleaningConfig, RC.CleaningConfig),
+                         (OutputConfig, RC.OutputConfig), (PreprocessingConfig, RC.PreprocessingConfig)):
+        mine = {f.name: f.default for f in dataclasses.fields(ours)}
+        ref = {f.name: f.default for f in dataclasses.fields(theirs)}
+        assert mine == ref, (ours.__name__, mine, ref)
+    ref_top = {f.name: f.default for f in dataclasses.fields(RC.MangaTranslatorConfig) if f.default is not dataclasses.MISSING}
+    mine_top = {f.name: f.default for f in dataclasses.fields(MangaTranslatorConfig) if f.default is not dataclasses.MISSING}
+    for name, val in mine_top.items():
+        if name in ref_top:
+            assert ref_top[name] == val, name
+    assert {"retry_failed_once", "processing_scale", "parallel_requests", "request_coordinator", "cleaning_only",
+            "upscaling_only"} <= set(mine_top)
+
+
+def test_target_mode_rule():
+    cfg = MangaTranslatorConfig()
+    table = [("png", "a.jpg", None, "RGBA"), ("jpeg", "a.png", None, "RGB"), ("auto", "a.jpg", None, "RGB"),
+             ("auto", "a.png", "o.jpeg", "RGB"), ("auto", "a.jpg", "o.png", "RGBA"), ("auto", "a.webp", None, "RGBA")]
+    for fmt, src, out, mode in table:
+        cfg.output.output_format = fmt
+        assert P._target_mode(cfg, Path(src), out) == mode, (fmt, src, out)
+
+
+def test_save_image_rules(tmp_path):
+    rgba = Image.new("RGBA", (8, 6), (10, 200, 30, 0))
+    rgba.putpixel((1, 1), (10, 200, 30, 255))
+    p = P.save_image(rgba, tmp_path / "a.jpg", jpeg_quality=500)
+    back = Image.open(p)
+    assert back.mode == "RGB" and back.getpixel((6, 4))[0] > 240          # transparent pixels land on white
+    p = P.save_image(rgba, tmp_path / "sub" / "b.png", png_compression=99)
+    assert np.array_equal(np.asarray(Image.open(p)), np.asarray(rgba))     # lossless
+    p = P.save_image(rgba.convert("RGB"), tmp_path / "c.webp")
+    assert np.array_equal(np.asarray(Image.open(p).convert("RGB")), np.asarray(rgba.convert("RGB")))
+    p = P.save_image(rgba, tmp_path / "d.tiff")
+    assert p.suffix == ".png" and p.exists()
+    pal = Image.new("P", (4, 4))
+    assert Image.open(P.save_image(pal, tmp_path / "e.jpeg")).mode == "RGB"
+
+
+class _Cancel:
+    def __init__(self, after):
+        self.n, self.after = 0, after
+
+    def is_cancelled(self):
+        self.n += 1
+        return self.n > self.after
+
+
+def _make_dir(tmp_path):
+    inp = tmp_path / "in"
+    (inp / "ch2").mkdir(parents=True)
+    for n in ["10.png", "2.png", "1.jpg", "bad.png", "notes.txt", "ch2/3.png", "x.bmp"]:
+        (inp / n).write_bytes(b"x")
+    return inp
+
+
+def test_batch_flow_counts_errors_retry_and_cancellation(tmp_path, monkeypatch):
+    inp = _make_dir(tmp_path)
+    seen, fail_once = [], {"bad.png": 1}
+
+    def fake(path, config, output_path=None, cancellation_manager=None, **kw):
+        seen.append((Path(path).name, Path(output_path).name))
+        if Path(path).name == "bad.png" and fail_once["bad.png"] != 0:
+            fail_once["bad.png"] -= 1
+            raise RuntimeError("boom")
+        Path(output_path).write_bytes(b"ok")
+
+    monkeypatch.setattr(P, "translate_and_render", fake)
+    cfg = MangaTranslatorConfig(cleaning_only=True)
+    prog = []
+    res = P.batch_translate_images(inp, cfg, tmp_path / "out", progress_callback=lambda f, m: prog.append(f),
+                                   source_path_map={str((inp / "bad.png").resolve()): "/orig/bad.png"})
+    # root only, natural order, .bmp / .txt ignored, <stem>_translated.png naming (output_format default "png")
+    assert seen == [("1.jpg", "1_translated.png"), ("2.png", "2_translated.png"), ("10.png", "10_translated.png"),
+                    ("bad.png", "bad_translated.png")]
+    assert res["success_count"] == 3 and res["error_count"] == 1 and res["errors"] == {"bad.png": "boom"}
+    assert res["failed_image_paths"] == ["/orig/bad.png"]
+    assert Path(res["failed_paths_file"]).read_text() == "/orig/bad.png\n"
+    assert prog[0] == 0.0 and prog[-1] == 1.0 and all(0 <= f <= 1 for f in prog)
+    # with retry_failed_once the page recovers and the failure bookkeeping is undone
+    seen.clear()
+    fail_once["bad.png"] = 1
+    cfg.retry_failed_once = True
+    res = P.batch_translate_images(inp, cfg, tmp_path / "out2", preserve_structure=True)
+    assert [s[0] for s in seen] == ["1.jpg", "2.png", "10.png", "bad.png", "3.png", "bad.png"]
+    assert (tmp_path / "out2" / "ch2" / "3_translated.png").exists()
+    assert res["success_count"] == 5 and res["error_count"] == 0 and res["errors"] == {} and res["failed_image_paths"] == []
+    assert (res["retry_attempted_count"], res["retry_success_count"], res["retry_failed_count"]) == (1, 1, 0)
+    assert "failed_paths_file" not in res
+    # a permanently failing page stays failed after the retry
+    fail_once["bad.png"] = -1
+    res = P.batch_translate_images(inp, cfg, tmp_path / "out3")
+    assert res["error_count"] == 1 and res["retry_failed_count"] == 1 and res["errors"] == {"bad.png": "boom"}
+    # cancellation propagates (pipeline.py:2601-2602)
+    from mangatranslator_b200.utils.exceptions import CancellationError
+    with pytest.raises(CancellationError):
+        P.batch_translate_images(inp, cfg, tmp_path / "out4", cancellation_manager=_Cancel(after=2))
+    # not a directory / nothing to do
+    empty = {"success_count": 0, "error_count": 0, "errors": {}, "failed_image_paths": []}
+    assert P.batch_translate_images(inp / "nope", cfg, tmp_path / "o5") == empty
+    (tmp_path / "void").mkdir()
+    assert P.batch_translate_images(tmp_path / "void", cfg, tmp_path / "o6") == empty
+
+
+_WORKER = r"""
+import os, sys
+from pathlib import Path
+sys.path.insert(0, {root!r})
+from mangatranslator_b200.core import pipeline as P
+from mangatranslator_b200.core.config import MangaTranslatorConfig
+rank = int(os.environ["RANK"])
+def fake(path, config, output_path=None, cancellation_manager=None, **kw):
+    if Path(path).name == "7.png":
+        raise RuntimeError("bad page")
+    Path(output_path).write_text(str(rank))
+P.translate_and_render = fake
+res = P.batch_translate_images({inp!r}, MangaTranslatorConfig(cleaning_only=True), {out!r})
+print("RANK", rank, res["success_count"], res["error_count"], sorted(res["errors"]), flush=True)
+"""
+
+
+def test_batch_flow_shards_pages_over_two_gloo_ranks(tmp_path):
+    inp, out = tmp_path / "in", tmp_path / "out"
+    inp.mkdir()
+    for i in range(1, 12):
+        (inp / f"{i}.png").write_bytes(b"x")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, inp=str(inp), out=str(out)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", str(script)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # natural order 1..11 -> rank 0 takes pages 1,3,5,7,9,11, rank 1 takes 2,4,6,8,10; rank 0 returns the merged result
+    assert "RANK 0 10 1 ['7.png']" in r.stdout and "RANK 1 5 0 []" in r.stdout, r.stdout
+    owners = {int(p.name.split("_")[0]): p.read_text() for p in out.glob("*_translated.png")}
+    assert owners == {i: str((i - 1) % 2) for i in range(1, 12) if i != 7}
+    assert (out / "failed_paths.txt").read_text().strip().endswith("7.png")
