@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import numpy as np
 

@@ -2,7 +2,7 @@
 
 The names the reference re-exports from `core` (core/__init__.py:8-41) resolve lazily, so importing the package does not
 pull torch / the CUDA library in; names whose subsystem is outside this build (LLM calls, text rendering, OCR, Flux,
-reading-order sorting, image encoding: SURVEY.md §2 "OUT") raise AttributeError with a pointer instead of importing."""
+reading-order sorting: SURVEY.md §2 "OUT") raise AttributeError with a pointer instead of importing."""
 from ._version import __version__, __version_info__
 
 _EXPORTS = {
@@ -10,11 +10,12 @@ _EXPORTS = {
     "clean_speech_bubbles": "image.cleaning",
     "detect_speech_bubbles": "image.detection",
     "cv2_to_pil": "image.image_utils", "pil_to_cv2": "image.image_utils",
+    "save_image_with_compression": "image.image_utils",
     "ModelManager": "ml.model_manager", "get_model_manager": "ml.model_manager",
     "batch_translate_images": "pipeline", "translate_and_render": "pipeline",
 }
 _OUT_OF_SCOPE = {"render_text_skia", "call_translation_api_batch", "sort_bubbles_by_reading_order",
-                 "save_image_with_compression", "OutsideTextDetector", "FluxKontextInpainter", "FluxKleinInpainter"}
+                 "OutsideTextDetector", "FluxKontextInpainter", "FluxKleinInpainter"}
 __all__ = ["__version__", "__version_info__", *sorted(_EXPORTS)]
 
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import collections
 import threading
-from typing import Any, Optional
+from typing import Any, Optional  # noqa: F401  (Any: quoted annotation below)
 
 MAX_ENTRIES = 64
 

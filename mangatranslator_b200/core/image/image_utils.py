@@ -12,6 +12,8 @@ from __future__ import annotations
 
 
 
+from pathlib import Path
+
 import numpy as np
 import torch
 from PIL import Image
@@ -244,6 +246,36 @@ def convert_image_to_target_mode(image: Image.Image, target_mode: str, verbose: 
             from mangatranslator_b200.preproc import flatten_alpha_device
             return _device_to_pil(flatten_alpha_device(torch.from_numpy(np.array(rgba)).to(dev)))
     return image.convert(target_mode)
+
+
+def save_image_with_compression(image: Image.Image, output_path, jpeg_quality: int = 95, png_compression: int = 2,
+                                verbose: bool = False):
+    """What reaches the file in the reference's function of the same name (image_utils.py:59-170): JPEG on a white
+    background with the clamped quality, lossless PNG / WEBP, unknown extensions become .png.  The reference re-packs the
+    PNG stream with oxipng; that is lossless, so the decoded pixels are identical while the file bytes differ (image
+    encoding is outside this build).  Returns the path written."""
+    path = Path(output_path)
+    ext = path.suffix.lower()
+    try:
+        path.parent.mkdir(parents=True, exist_ok=True)
+        if ext in (".jpg", ".jpeg"):
+            if image.mode in ("RGBA", "LA"):
+                flat = Image.new("RGB", image.size, (255, 255, 255))
+                flat.paste(image, mask=image.split()[-1])
+                image = flat
+            elif image.mode != "RGB":
+                image = image.convert("RGB")
+            image.save(path, format="JPEG", quality=max(1, min(int(jpeg_quality), 100)))
+        elif ext == ".webp":
+            image.save(path, format="WEBP", lossless=True)
+        else:
+            if ext != ".png":
+                log_message(f"Warning: Unknown output extension '{ext}'. Saving as PNG.", verbose=verbose, always_print=True)
+                path = path.with_suffix(".png")
+            image.save(path, format="PNG", compress_level=min(6, max(0, int(png_compression))))
+    except Exception as e:
+        raise ImageProcessingError(f"Failed to save image to {output_path}") from e
+    return path
 
 
 def safe_boxes_for_masks(masks, padding_pixels: float = 4.0, bboxes=None):

@@ -19,7 +19,7 @@ import os
 import re
 import time
 from pathlib import Path
-from typing import Any, Callable, Dict, List, Optional, Sequence
+from typing import Callable, Dict, List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -30,7 +30,8 @@ from mangatranslator_b200.core.caching import get_cache
 from mangatranslator_b200.core.config import MangaTranslatorConfig
 from mangatranslator_b200.core.image.cleaning import clean_pages_device, clean_speech_bubbles
 from mangatranslator_b200.core.image.detection import detect_pages_device, detect_speech_bubbles
-from mangatranslator_b200.core.image.image_utils import convert_image_to_target_mode, cv2_to_pil, upscale_image
+from mangatranslator_b200.core.image.image_utils import (convert_image_to_target_mode, cv2_to_pil,
+                                                          save_image_with_compression, upscale_image)
 from mangatranslator_b200.core.ml.model_manager import get_model_manager
 from mangatranslator_b200.utils.exceptions import CancellationError, ImageProcessingError, ValidationError
 from mangatranslator_b200.utils.logging import log_message
@@ -63,35 +64,6 @@ def _target_mode(config: MangaTranslatorConfig, image_path, output_path) -> str:
     ext = (Path(output_path) if output_path else Path(image_path)).suffix.lower()
     fmt = config.output.output_format
     return "RGB" if fmt == "jpeg" or (fmt == "auto" and ext in (".jpg", ".jpeg")) else "RGBA"
-
-
-def save_image(image: Image.Image, output_path, jpeg_quality: int = 95, png_compression: int = 2, verbose: bool = False):
-    """What reaches the file in the reference's save_image_with_compression (image_utils.py:59-170): JPEG on a white
-    background with the clamped quality, lossless PNG / WEBP, unknown extensions become .png.  The reference re-packs the
-    PNG stream with oxipng; that is lossless, so the decoded pixels are identical while the file bytes differ (image
-    encoding is outside this build).  Returns the path written."""
-    path = Path(output_path)
-    ext = path.suffix.lower()
-    try:
-        path.parent.mkdir(parents=True, exist_ok=True)
-        if ext in (".jpg", ".jpeg"):
-            if image.mode in ("RGBA", "LA"):
-                flat = Image.new("RGB", image.size, (255, 255, 255))
-                flat.paste(image, mask=image.split()[-1])
-                image = flat
-            elif image.mode != "RGB":
-                image = image.convert("RGB")
-            image.save(path, format="JPEG", quality=max(1, min(int(jpeg_quality), 100)))
-        elif ext == ".webp":
-            image.save(path, format="WEBP", lossless=True)
-        else:
-            if ext != ".png":
-                log_message(f"Warning: Unknown output extension '{ext}'. Saving as PNG.", verbose=verbose, always_print=True)
-                path = path.with_suffix(".png")
-            image.save(path, format="PNG", compress_level=min(6, max(0, int(png_compression))))
-    except Exception as e:
-        raise ImageProcessingError(f"Failed to save image to {output_path}") from e
-    return path
 
 
 def translate_and_render(image_path, config: MangaTranslatorConfig, output_path=None, cancellation_manager=None,
@@ -140,7 +112,8 @@ def translate_and_render(image_path, config: MangaTranslatorConfig, output_path=
         if out.mode != target_mode:
             out = out.convert(target_mode)
         try:                        # pipeline.py:2001-2018: a failed save is logged and re-raised
-            save_image(out, output_path, config.output.jpeg_quality, config.output.png_compression, verbose)
+            save_image_with_compression(out, output_path, jpeg_quality=config.output.jpeg_quality,
+                                        png_compression=config.output.png_compression, verbose=verbose)
         except ImageProcessingError as e:
             log_message(f"Failed to save image: {e}", always_print=True)
             raise

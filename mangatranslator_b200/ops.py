@@ -5,7 +5,6 @@ import ctypes as C
 
 import torch
 
-from . import _lib
 from ._lib import ConvDesc, check, lib, ptr, stream_ptr
 
 ACT = {None: 0, "none": 0, "relu": 1, "silu": 2, "gelu": 3, "sigmoid": 4}

@@ -7,7 +7,7 @@ Nothing is computed here: `safe_boxes_device` allocates the job table + workspac
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -12,7 +12,6 @@ addressing), the hyper-network mask product and the mask writer are the kernels 
 from __future__ import annotations
 
 import ctypes as C
-import math
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np

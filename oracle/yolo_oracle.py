@@ -13,7 +13,6 @@ checked for internal consistency only and is the yard-stick for the CUDA path on
 from __future__ import annotations
 
 import math
-from typing import List, Tuple
 
 import numpy as np
 import torch

@@ -100,17 +100,17 @@ def test_target_mode_rule():
 def test_save_image_rules(tmp_path):
     rgba = Image.new("RGBA", (8, 6), (10, 200, 30, 0))
     rgba.putpixel((1, 1), (10, 200, 30, 255))
-    p = P.save_image(rgba, tmp_path / "a.jpg", jpeg_quality=500)
+    p = P.save_image_with_compression(rgba, tmp_path / "a.jpg", jpeg_quality=500)
     back = Image.open(p)
     assert back.mode == "RGB" and back.getpixel((6, 4))[0] > 240          # transparent pixels land on white
-    p = P.save_image(rgba, tmp_path / "sub" / "b.png", png_compression=99)
+    p = P.save_image_with_compression(rgba, tmp_path / "sub" / "b.png", png_compression=99)
     assert np.array_equal(np.asarray(Image.open(p)), np.asarray(rgba))     # lossless
-    p = P.save_image(rgba.convert("RGB"), tmp_path / "c.webp")
+    p = P.save_image_with_compression(rgba.convert("RGB"), tmp_path / "c.webp")
     assert np.array_equal(np.asarray(Image.open(p).convert("RGB")), np.asarray(rgba.convert("RGB")))
-    p = P.save_image(rgba, tmp_path / "d.tiff")
+    p = P.save_image_with_compression(rgba, tmp_path / "d.tiff")
     assert p.suffix == ".png" and p.exists()
     pal = Image.new("P", (4, 4))
-    assert Image.open(P.save_image(pal, tmp_path / "e.jpeg")).mode == "RGB"
+    assert Image.open(P.save_image_with_compression(pal, tmp_path / "e.jpeg")).mode == "RGB"
 
 
 class _Cancel:
