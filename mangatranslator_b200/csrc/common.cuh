@@ -243,6 +243,17 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t saddr, uint32_t sb
   d |= static_cast<uint64_t>(2) << 61;                           // layout type: SWIZZLE_128B
   return d;
 }
+// Same for rows of 64 B (e.g. 64 channels of an 8-bit plane): 64-byte swizzle, 8-row atoms of 512 B.
+__device__ __forceinline__ uint64_t make_sdesc_sw64(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_offset & 7) << 49;
+  d |= static_cast<uint64_t>(4) << 61;                           // layout type: SWIZZLE_64B
+  return d;
+}
 // kind::f16, A/B = bf16 K-major, D = fp32, shape M x N (M in {64,128}, N % 16 == 0)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |

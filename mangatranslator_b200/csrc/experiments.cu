@@ -68,6 +68,69 @@ shifted_desc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, 64);
 }
 
+// Shifted-view probe for 8-bit operands with 64-byte rows (the e5m2 activation plane of DESIGN.md §8.0: 64 channels x 1 B
+// per pixel): same question as shifted_desc_kernel, for SWIZZLE_64B and kind::f8f6f4.  A = 512 rows x 64 B written by TMA
+// with the 64B swizzle; the descriptor starts `shift_rows` rows into the tile and walks 8-row groups `sbo_bytes` apart;
+// D[128][64] = A_view * B^T over K = 64 (two K = 32 instructions).
+__global__ void __launch_bounds__(128, 1)
+shifted_desc8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* D,
+                     int shift_rows, int sbo_bytes, int base_offset) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                 // 512 rows x 64 B = 32 KB
+  uint8_t* sB = smem + 512 * 64;      // 64 rows x 64 B = 4 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 64 * 64);
+  uint64_t* mma_bar = bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(mma_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, 512 * 64 + 64 * 64);
+    tma_load_2d(sA, &tmA, bar, 0, 0);
+    tma_load_2d(sA + 256 * 64, &tmA, bar, 0, 256);
+    tma_load_2d(sB, &tmB, bar, 0, 0);
+  }
+  if (warp == 1) {
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_e5m2(128, 64);
+      const uint32_t a0 = smem_u32(sA) + shift_rows * 64;
+      const uint32_t b0 = smem_u32(sB);
+      for (int k = 0; k < 2; ++k) {
+        umma_f8f6f4(tmem_base, make_sdesc_sw64(a0 + k * 32, sbo_bytes, base_offset),
+                    make_sdesc_sw64(b0 + k * 32, 512, 0), idesc, k > 0);
+      }
+      umma_commit(mma_bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(mma_bar, 0);
+  tc_fence_after();
+  const int r = warp * 32 + lane;
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    uint32_t acc[16];
+    tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, acc);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[r * 64 + c0 + j] = __uint_as_float(acc[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
 // Mixed-kind accumulation probe: D[128][64] = A16 * B16^T (fp16, K = 64: four kind::f16 MMAs) +
 // A8 * B8^T (e5m2, K = 128: four kind::f8f6f4 MMAs of M = m8 rows) accumulated in ONE fp32 TMEM tile.  All operands are
 // K-major 128-byte rows written by TMA with the 128B swizzle (a row of 64 halves or 128 bytes).  The host compares D with
@@ -298,6 +361,33 @@ extern "C" int mtb_exp_mixed_kind(const void* A16 /* fp16 [128][64] */, const vo
   MTB_CUDA_OK(cudaFuncSetAttribute(mixed_kind_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
   mixed_kind_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(t[0], t[1], t[2], t[3], D, m8, which);
+  MTB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mtb_exp_shifted_desc8(const void* A /* e5m2 [512][64] */, const void* B /* e5m2 [64][64] */,
+                                     float* D /* [128][64] */, int shift_rows, int sbo_bytes, int base_offset,
+                                     void* stream) {
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {64, 512};
+    const uint64_t strides[1] = {64};
+    const uint32_t box[2] = {64, 256};
+    if (encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, A, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_64B))
+      return -3;
+  }
+  {
+    const uint64_t dims[2] = {64, 64};
+    const uint64_t strides[1] = {64};
+    const uint32_t box[2] = {64, 64};
+    if (encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, B, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_64B))
+      return -3;
+  }
+  const size_t smem = 1024 + 512 * 64 + 64 * 64 + 64;
+  MTB_CUDA_OK(cudaFuncSetAttribute(shifted_desc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+  shifted_desc8_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, D, shift_rows, sbo_bytes,
+                                                                           base_offset);
   MTB_CUDA_OK(cudaGetLastError());
   return 0;
 }

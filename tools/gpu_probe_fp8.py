@@ -68,6 +68,26 @@ if rows:
     out["mixed_m64_on_its_lanes_max_abs_err"] = err      # fp16 M = 128 product + e5m2 M = 64 product, lane by lane
     print("mixed m64 err", err, flush=True)
 
+# tap-shifted views of a 64-byte-swizzled 8-bit tile (the e5m2 activation plane: 64 channels x 1 B per pixel)
+lib.mtb_exp_shifted_desc8.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+lib.mtb_exp_shifted_desc8.restype = C.c_int
+ta = (torch.randn(512, 64, device=dev) * 0.25).to(torch.float8_e5m2)
+tb = (torch.randn(64, 64, device=dev) * 0.25).to(torch.float8_e5m2)
+out["shifted_sw64"] = {}
+for shift, sbo in ((0, 512), (8, 512), (1, 512), (3, 512), (0, 640), (1, 640), (11, 640), (21, 640), (22, 640)):
+    rows = torch.tensor([shift + (r // 8) * (sbo // 64) + (r % 8) for r in range(128)], device=dev)
+    exp = ta.double()[rows] @ tb.double().T
+    best = None
+    for base_offset in (0, (shift % 8)):
+        d = torch.zeros((128, 64), dtype=torch.float32, device=dev)
+        assert lib.mtb_exp_shifted_desc8(ta.view(torch.uint8).data_ptr(), tb.view(torch.uint8).data_ptr(), d.data_ptr(),
+                                         shift, sbo, base_offset, _lib.stream_ptr()) == 0
+        torch.cuda.synchronize()
+        err = float((d.double() - exp).abs().max())
+        out["shifted_sw64"][f"shift{shift}_sbo{sbo}_base{base_offset}"] = err
+        best = err if best is None else min(best, err)
+    print(f"sw64 shift {shift} sbo {sbo}: max abs err {best:.3e} (ref max {float(exp.abs().max()):.2f})", flush=True)
+
 names = {4: "M128N240_f16", 5: "M64N240_f16", 10: "M128N240_e5m2", 11: "M64N240_e5m2",
          12: "M128N240_f16+M64N240_e5m2_one_acc", 13: "M128N240_f16+M128N240_e5m2_one_acc"}
 for pattern, nm in names.items():
