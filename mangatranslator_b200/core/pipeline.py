@@ -66,10 +66,8 @@ def _target_mode(config: MangaTranslatorConfig, image_path, output_path) -> str:
     return "RGB" if fmt == "jpeg" or (fmt == "auto" and ext in (".jpg", ".jpeg")) else "RGBA"
 
 
-def translate_and_render(image_path, config: MangaTranslatorConfig, output_path=None, cancellation_manager=None,
-                         previous_context_images=None, previous_context_texts=None,
-                         previous_context_texts_provider=None, ocr_texts_out=None) -> Image.Image:
-    start = time.time()
+def _render_page(image_path, config: MangaTranslatorConfig, output_path=None, cancellation_manager=None):
+    """Everything of translate_and_render up to (not including) the save: returns (image, target_mode)."""
     verbose = config.verbose
     if not (config.cleaning_only or config.upscaling_only):
         raise ValidationError("this build implements the vision hot path only: set cleaning_only or upscaling_only "
@@ -108,17 +106,63 @@ def translate_and_render(image_path, config: MangaTranslatorConfig, output_path=
         if config.output.upscale_final_image:
             out = upscale_image(out, config.output.image_upscale_factor, model_type=config.output.image_upscale_model,
                                 verbose=verbose)
+    return out, target_mode
+
+
+def _save_page(image: Image.Image, target_mode: str, output_path, config: MangaTranslatorConfig) -> None:
+    """pipeline.py:1996-2018: convert to the target mode, save with the configured compression; a failed save is logged
+    and re-raised."""
+    if image.mode != target_mode:
+        image = image.convert(target_mode)
+    try:
+        save_image_with_compression(image, output_path, jpeg_quality=config.output.jpeg_quality,
+                                    png_compression=config.output.png_compression, verbose=config.verbose)
+    except ImageProcessingError as e:
+        log_message(f"Failed to save image: {e}", always_print=True)
+        raise
+
+
+def translate_and_render(image_path, config: MangaTranslatorConfig, output_path=None, cancellation_manager=None,
+                         previous_context_images=None, previous_context_texts=None,
+                         previous_context_texts_provider=None, ocr_texts_out=None) -> Image.Image:
+    start = time.time()
+    out, target_mode = _render_page(image_path, config, output_path, cancellation_manager)
     if output_path:
-        if out.mode != target_mode:
-            out = out.convert(target_mode)
-        try:                        # pipeline.py:2001-2018: a failed save is logged and re-raised
-            save_image_with_compression(out, output_path, jpeg_quality=config.output.jpeg_quality,
-                                        png_compression=config.output.png_compression, verbose=verbose)
-        except ImageProcessingError as e:
-            log_message(f"Failed to save image: {e}", always_print=True)
-            raise
+        _save_page(out, target_mode, output_path, config)
     log_message(f"Processing completed in {time.time() - start:.2f}s", always_print=True)
     return out
+
+
+def _process_page(path, config, out_path, cancellation_manager, saver):
+    """One page of the batch: with a writer pool the encode + write of this page overlaps the next page's device work
+    (returns the pending save), otherwise exactly translate_and_render."""
+    if saver is None:
+        translate_and_render(path, config, out_path, cancellation_manager=cancellation_manager)
+        return None
+    start = time.time()
+    out, target_mode = _render_page(path, config, out_path, cancellation_manager)
+    log_message(f"Processing completed in {time.time() - start:.2f}s (save queued)", always_print=True)
+    return saver.submit(_save_page, out, target_mode, out_path, config)
+
+
+class _BoundedPool:
+    """ThreadPoolExecutor whose submit() blocks while `depth` tasks are pending, so finished pages cannot pile up in host
+    memory faster than they are written (an upscaled page is ~25 MB)."""
+
+    def __init__(self, workers: int, depth: int):
+        import concurrent.futures
+        import threading
+        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=workers, thread_name_prefix="mtb200-save")
+        self._slots = threading.BoundedSemaphore(depth)
+
+    def submit(self, fn, *args):
+        self._slots.acquire()
+        fut = self._pool.submit(fn, *args)
+        fut.add_done_callback(lambda _f: self._slots.release())
+        return fut
+
+    def close(self):
+        self._pool.shutdown(wait=True)
 
 
 _DIGITS = re.compile(r"(\d+)")
@@ -208,6 +252,8 @@ def batch_translate_images(input_dir, config: MangaTranslatorConfig, output_dir=
     `preserve_structure`) in natural order, each written as `<stem>_translated.<ext>`; returns {success_count,
     error_count, errors{name: message}, failed_image_paths[source paths][, failed_paths_file][, retry_*]}; failed pages
     are retried once when `config.retry_failed_once`; a cancellation propagates as CancellationError.
+    The encode + write of a finished page runs on a small writer pool (`MTB200_SAVE_WORKERS`, default 2, 0 = inline) so it
+    overlaps the next page's device work; a page is counted once its file is on disk.
     Under torchrun the sorted page list is sharded over the ranks (`PageShardCoordinator`: page i goes to rank i mod R,
     no data-path collective); every rank returns its own counts and rank 0 the merged result with the failure file."""
     empty = {"success_count": 0, "error_count": 0, "errors": {}, "failed_image_paths": []}
@@ -231,29 +277,59 @@ def batch_translate_images(input_dir, config: MangaTranslatorConfig, output_dir=
                 (f" ({total} on rank {coord.rank} of {coord.world})" if coord.world > 1 else ""), always_print=True)
     res = {"success_count": 0, "error_count": 0, "errors": {}, "failed_image_paths": []}
     failed_jobs = []
-    for i, path in enumerate(mine):
-        out_path, shown, key = resolve_output_path(path, input_dir, out_dir, config, preserve_structure)
-        if cancellation_manager is not None and cancellation_manager.is_cancelled():
-            raise CancellationError("Batch process cancelled by user.")
-        if progress_callback:
-            progress_callback(i / total, f"Processing image {i + 1}/{total}: {shown}")
-        log_message(f"Processing {i + 1}/{total}: {shown}", always_print=True)
-        try:
-            translate_and_render(path, config, out_path, cancellation_manager=cancellation_manager)
-            res["success_count"] += 1
-            note = f"Completed {i + 1}/{total} images"
-        except CancellationError:
-            raise
-        except Exception as e:
-            log_message(f"Error processing {shown}: {e}", always_print=True)
-            src = resolve_source_path(path, source_path_map)
-            res["error_count"] += 1
-            res["errors"][key] = str(e)
-            res["failed_image_paths"].append(src)
-            failed_jobs.append((key, path, src))
-            note = f"Completed {i + 1}/{total} images (with errors)"
-        if progress_callback:
-            progress_callback((i + 1) / total, note)
+    workers = int(os.environ.get("MTB200_SAVE_WORKERS", "2"))
+    saver = _BoundedPool(workers, depth=2 * workers) if workers > 0 else None
+    pending = []                                   # (future, key, path, shown) of queued saves
+
+    def failed(key, path, shown, e):
+        log_message(f"Error processing {shown}: {e}", always_print=True)
+        src = resolve_source_path(path, source_path_map)
+        res["error_count"] += 1
+        res["errors"][key] = str(e)
+        res["failed_image_paths"].append(src)
+        failed_jobs.append((key, path, src))
+
+    def settle(block: bool):
+        """Book finished saves (all of them when `block`): a page counts as done once its file is written."""
+        keep = []
+        for fut, key, path, shown in pending:
+            if not block and not fut.done():
+                keep.append((fut, key, path, shown))
+                continue
+            try:
+                fut.result()
+                res["success_count"] += 1
+            except Exception as e:
+                failed(key, path, shown, e)
+        pending[:] = keep
+
+    try:
+        for i, path in enumerate(mine):
+            out_path, shown, key = resolve_output_path(path, input_dir, out_dir, config, preserve_structure)
+            if cancellation_manager is not None and cancellation_manager.is_cancelled():
+                raise CancellationError("Batch process cancelled by user.")
+            if progress_callback:
+                progress_callback(i / total, f"Processing image {i + 1}/{total}: {shown}")
+            log_message(f"Processing {i + 1}/{total}: {shown}", always_print=True)
+            try:
+                fut = _process_page(path, config, out_path, cancellation_manager, saver)
+                if fut is None:
+                    res["success_count"] += 1
+                else:
+                    pending.append((fut, key, path, shown))
+                note = f"Completed {i + 1}/{total} images"
+            except CancellationError:
+                raise
+            except Exception as e:
+                failed(key, path, shown, e)
+                note = f"Completed {i + 1}/{total} images (with errors)"
+            settle(block=False)
+            if progress_callback:
+                progress_callback((i + 1) / total, note)
+        settle(block=True)
+    finally:
+        if saver is not None:
+            saver.close()                          # queued files are still written when the batch is cancelled
     cancelled = cancellation_manager is not None and cancellation_manager.is_cancelled()
     if getattr(config, "retry_failed_once", False) and failed_jobs and not cancelled:
         _retry_failed(failed_jobs, res, config, input_dir, out_dir, preserve_structure, progress_callback, cancellation_manager)

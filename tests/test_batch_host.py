@@ -1,7 +1,7 @@
 """CPU: host side of the page driver (core/pipeline.py) against the reference's own helpers (live, when the checkout is
 present): natural page order, output naming, source-path mapping, failed-path file, target mode, save rules, config
 defaults; and the batch flow itself (counts, error keys, retry pass, cancellation, sharding over two gloo ranks) with
-`translate_and_render` replaced by a stand-in (the real one needs a GPU)."""
+the render and save halves of a page replaced by stand-ins (the real render needs a GPU)."""
 import os
 import subprocess
 import sys
@@ -130,18 +130,29 @@ def _make_dir(tmp_path):
     return inp
 
 
-def test_batch_flow_counts_errors_retry_and_cancellation(tmp_path, monkeypatch):
+@pytest.mark.parametrize("workers", ["0", "2"], ids=["inline_save", "writer_pool"])
+def test_batch_flow_counts_errors_retry_and_cancellation(tmp_path, monkeypatch, workers):
+    """The render half (device work) and the save half are replaced by stand-ins; `workers` selects saving inline
+    (translate_and_render as a whole) or on the writer pool."""
+    monkeypatch.setenv("MTB200_SAVE_WORKERS", workers)
     inp = _make_dir(tmp_path)
-    seen, fail_once = [], {"bad.png": 1}
+    seen, fail_once = [], {"bad.png": 1, "stage": "render"}
 
-    def fake(path, config, output_path=None, cancellation_manager=None, **kw):
+    def fake_render(path, config, output_path=None, cancellation_manager=None):
         seen.append((Path(path).name, Path(output_path).name))
-        if Path(path).name == "bad.png" and fail_once["bad.png"] != 0:
+        if Path(path).name == "bad.png" and fail_once["stage"] == "render" and fail_once["bad.png"] != 0:
             fail_once["bad.png"] -= 1
             raise RuntimeError("boom")
+        return Path(path).name, "RGB"
+
+    def fake_save(image, target_mode, output_path, config):
+        if image == "bad.png" and fail_once["stage"] == "save" and fail_once["bad.png"] != 0:
+            fail_once["bad.png"] -= 1
+            raise RuntimeError("disk full")
         Path(output_path).write_bytes(b"ok")
 
-    monkeypatch.setattr(P, "translate_and_render", fake)
+    monkeypatch.setattr(P, "_render_page", fake_render)
+    monkeypatch.setattr(P, "_save_page", fake_save)
     cfg = MangaTranslatorConfig(cleaning_only=True)
     prog = []
     res = P.batch_translate_images(inp, cfg, tmp_path / "out", progress_callback=lambda f, m: prog.append(f),
@@ -153,9 +164,15 @@ def test_batch_flow_counts_errors_retry_and_cancellation(tmp_path, monkeypatch):
     assert res["failed_image_paths"] == ["/orig/bad.png"]
     assert Path(res["failed_paths_file"]).read_text() == "/orig/bad.png\n"
     assert prog[0] == 0.0 and prog[-1] == 1.0 and all(0 <= f <= 1 for f in prog)
+    assert sorted(p.name for p in (tmp_path / "out").glob("*_translated.png")) == ["10_translated.png", "1_translated.png",
+                                                                                  "2_translated.png"]
+    # a failure while SAVING is booked the same way, whichever thread wrote the file
+    fail_once.update({"bad.png": 1, "stage": "save"})
+    res = P.batch_translate_images(inp, cfg, tmp_path / "out_s")
+    assert res["success_count"] == 3 and res["error_count"] == 1 and res["errors"] == {"bad.png": "disk full"}
     # with retry_failed_once the page recovers and the failure bookkeeping is undone
     seen.clear()
-    fail_once["bad.png"] = 1
+    fail_once.update({"bad.png": 1, "stage": "render"})
     cfg.retry_failed_once = True
     res = P.batch_translate_images(inp, cfg, tmp_path / "out2", preserve_structure=True)
     assert [s[0] for s in seen] == ["1.jpg", "2.png", "10.png", "bad.png", "3.png", "bad.png"]
@@ -167,15 +184,38 @@ def test_batch_flow_counts_errors_retry_and_cancellation(tmp_path, monkeypatch):
     fail_once["bad.png"] = -1
     res = P.batch_translate_images(inp, cfg, tmp_path / "out3")
     assert res["error_count"] == 1 and res["retry_failed_count"] == 1 and res["errors"] == {"bad.png": "boom"}
-    # cancellation propagates (pipeline.py:2601-2602)
+    # cancellation propagates (pipeline.py:2601-2602); pages already rendered are still written
     from mangatranslator_b200.utils.exceptions import CancellationError
+    fail_once["bad.png"] = 0
     with pytest.raises(CancellationError):
         P.batch_translate_images(inp, cfg, tmp_path / "out4", cancellation_manager=_Cancel(after=2))
+    assert sorted(p.name for p in (tmp_path / "out4").glob("*")) == ["1_translated.png", "2_translated.png"]
     # not a directory / nothing to do
     empty = {"success_count": 0, "error_count": 0, "errors": {}, "failed_image_paths": []}
     assert P.batch_translate_images(inp / "nope", cfg, tmp_path / "o5") == empty
     (tmp_path / "void").mkdir()
     assert P.batch_translate_images(tmp_path / "void", cfg, tmp_path / "o6") == empty
+
+
+def test_writer_pool_overlaps_saving_with_the_next_pages_device_work(tmp_path, monkeypatch):
+    import time
+    inp = tmp_path / "in"
+    inp.mkdir()
+    for i in range(8):
+        (inp / f"{i}.png").write_bytes(b"x")
+    monkeypatch.setattr(P, "_render_page", lambda path, config, output_path=None, cancellation_manager=None:
+                        (time.sleep(0.05), ("img", "RGB"))[1])
+    monkeypatch.setattr(P, "_save_page", lambda image, mode, out, config: (time.sleep(0.15), Path(out).write_bytes(b"ok"))[1])
+    cfg = MangaTranslatorConfig(cleaning_only=True)
+    took = {}
+    for workers in ("0", "2"):
+        monkeypatch.setenv("MTB200_SAVE_WORKERS", workers)
+        t0 = time.perf_counter()
+        res = P.batch_translate_images(inp, cfg, tmp_path / f"out{workers}")
+        took[workers] = time.perf_counter() - t0
+        assert res["success_count"] == 8 and len(list((tmp_path / f"out{workers}").glob("*.png"))) == 8
+    assert took["0"] > 1.5                       # 8 x (0.05 + 0.15) s back to back
+    assert took["2"] < 0.75 * took["0"], took    # saves ride under the following renders, two at a time
 
 
 _WORKER = r"""
@@ -185,11 +225,12 @@ sys.path.insert(0, {root!r})
 from mangatranslator_b200.core import pipeline as P
 from mangatranslator_b200.core.config import MangaTranslatorConfig
 rank = int(os.environ["RANK"])
-def fake(path, config, output_path=None, cancellation_manager=None, **kw):
+def render(path, config, output_path=None, cancellation_manager=None):
     if Path(path).name == "7.png":
         raise RuntimeError("bad page")
-    Path(output_path).write_text(str(rank))
-P.translate_and_render = fake
+    return "img", "RGB"
+P._render_page = render
+P._save_page = lambda image, mode, out, config: Path(out).write_text(str(rank))
 res = P.batch_translate_images({inp!r}, MangaTranslatorConfig(cleaning_only=True), {out!r})
 print("RANK", rank, res["success_count"], res["error_count"], sorted(res["errors"]), flush=True)
 """
