@@ -7,6 +7,7 @@ so the numbers isolate the format.  Prints max / mean |dy| on the network output
   fp16            X rounded to fp16, W exact (fp16 hi + lo)                                          (one MMA per tap)
   fp16+e5m2       ... plus the correction product e5m2(X - fp16(X)) * e5m2(W)                        (kind::f8f6f4, K = 32)
   fp16+e4m3       same with e4m3 (underflows: X - fp16(X) is ~2^-12 |X|)
+  fp16+mxfp4      same with e2m1 values and one power-of-two scale per 32 input channels (kind::mxf4, K = 64)
   +trunk3         additionally every RCAB / group output (the residual trunk) is STORED as fp16 hi + e5m2 lo (3 bytes)
 
     python tools/cpu_operand_format_accuracy.py [size] [seeds] [init]
@@ -53,10 +54,28 @@ class Conv(torch.nn.Module):
         xh, wh = q(x, torch.float16), q(w, torch.float16)
         wl = q(w - wh, torch.float16)
         y = F.conv2d(xh, wh + wl, b, padding=1)
-        if "+" in m:
+        if m.endswith("+mxfp4"):
+            y = y + F.conv2d(mxfp4(x - xh, 1), mxfp4(w, 1), None, padding=1)
+        elif "+" in m:
             dt = F8[m.split("+")[1]]
             y = y + F.conv2d(q((x - xh).float(), dt), q(w.float(), dt), None, padding=1)
         return y
+
+
+E2M1 = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0], dtype=torch.float64)
+
+
+def mxfp4(t, dim):
+    """e2m1 with a shared power-of-two scale per block of 32 along `dim` (the contraction dimension)."""
+    t = t.movedim(dim, -1)
+    shape = t.shape
+    b = t.reshape(*shape[:-1], shape[-1] // 32, 32)
+    amax = b.abs().amax(-1, keepdim=True).clamp_min(1e-300)
+    scale = torch.exp2(torch.ceil(torch.log2(amax / 6.0)))
+    v = (b / scale).abs().clamp(max=6.0)
+    idx = (v.unsqueeze(-1) - E2M1).abs().argmin(-1)
+    qv = E2M1[idx] * torch.sign(b) * scale
+    return qv.reshape(shape).movedim(-1, dim)
 
 
 def store3(x):
@@ -106,7 +125,7 @@ def main():
             x = F.avg_pool2d(F.pad(x, (2, 2, 2, 2), mode="reflect"), 5, 1)
         with torch.no_grad():
             ref = build(seed, None)(x)
-            for mode in ("bf16x3", "tf32", "fp16", "fp16+e5m2", "fp16+e4m3", "fp16+e5m2+trunk3"):
+            for mode in ("bf16x3", "tf32", "fp16", "fp16+e5m2", "fp16+e4m3", "fp16+mxfp4", "fp16+e5m2+trunk3"):
                 d = (build(seed, mode)(x) - ref).abs()
                 print(f"seed {seed} {mode:18s} max {float(d.max()):.2e} mean {float(d.mean()):.2e}", flush=True)
 
