@@ -6,8 +6,8 @@ Restated on INTEGER squared distances, which is the formulation the CUDA kernel 
   * `cv2.distanceTransform(padded, DIST_L2, DIST_MASK_PRECISE)` (:214-216) of OpenCV's own code is the exact Euclidean
     transform: float32 sqrt of the exact integer squared distance to the nearest zero pixel, the image being framed by a
     one-pixel ring of zeros (:210-213).  Checked in tests/test_safebox.py against cv2 with IPP disabled; the wheel's IPP
-    build of that call is off by one float32 ulp on some pixels (not correctly rounded sqrt), which only matters on exact
-    threshold ties.
+    build of that call is off by one float32 ulp on some pixels (not correctly rounded sqrt, alignment dependent), which
+    only matters on exact ties: 1 of 3000 random masks, where two pixels share the maximal distance.
   * `dist >= padding_pixels` (:218) compares float32 with a Python float: NumPy 2 casts the scalar to float32.
   * `cv2.moments` of the 0/255 safe mask (:228-234): integer sums, m10/m00 = (255*Sx)/(255*S) in double.
   * `cv2.minMaxLoc` (:237): first maximum in raster order.
