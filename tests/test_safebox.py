@@ -87,21 +87,35 @@ def test_oracle_and_kernel_logic_match_reference_golden(case):
 @pytest.mark.skipif(not _refimport.available(), reason="reference checkout not present (GPU box)")
 @pytest.mark.parametrize("ipp", [False, True])
 def test_oracle_matches_live_reference_random(ipp):
+    """With IPP off (OpenCV's own transform, the parity target) every case must agree.  With IPP on a disagreement is
+    tolerated only if it disappears when the same reference call is repeated with IPP off (an exact tie decided by IPP's
+    last-bit noise, see the next test), and at most twice in 300 masks."""
     _refimport.import_reference()
     import core.image.image_utils as RU
     from utils.exceptions import ImageProcessingError
+
+    def reference(m, pad):
+        try:
+            box, c = RU.calculate_centroid_expansion_box(m, pad)
+            return tuple(int(v) for v in box), c
+        except ImageProcessingError as e:
+            return str(e)
+
     cv2.ipp.setUseIPP(ipp)
     try:
-        n_fail = 0
+        n_fail = ipp_flips = 0
         for seed in range(2000, 2300):
             m, pad = safebox_mask(seed)
-            try:
-                exp = RU.calculate_centroid_expansion_box(m, pad)
-            except ImageProcessingError as e:
-                exp = str(e)
-                n_fail += 1
-            assert _oracle(m, pad) == exp, (seed, m.shape, pad)
-        assert 10 < n_fail < 150
+            exp = reference(m, pad)
+            n_fail += isinstance(exp, str)
+            got = _oracle(m, pad)
+            if got != exp and ipp:
+                cv2.ipp.setUseIPP(False)
+                exp = reference(m, pad)
+                cv2.ipp.setUseIPP(True)
+                ipp_flips += 1
+            assert got == exp, (seed, m.shape, pad)
+        assert 10 < n_fail < 150 and ipp_flips <= 2
     finally:
         cv2.ipp.setUseIPP(True)
 
