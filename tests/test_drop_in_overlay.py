@@ -115,3 +115,32 @@ def test_reference_pipeline_runs_through_the_overlay_with_our_signatures():
         print("OK")
     """)
     assert out.strip().endswith("OK")
+
+
+def test_overlaid_functions_have_the_reference_signatures():
+    """Every function / loader the overlay replaces takes the reference's parameters: same names, same order, same
+    defaults (reading signatures only; nothing is rebound here)."""
+    import importlib
+    import inspect
+    _refimport.import_reference()
+    from mangatranslator_b200 import drop_in as D
+    checked = 0
+    for ref_name, (our_name, names) in D._STAGE_FUNCTIONS.items():
+        ref_mod, our_mod = importlib.import_module(ref_name), importlib.import_module(our_name)
+        for n in names:
+            ref_p = list(inspect.signature(getattr(ref_mod, n)).parameters.values())
+            our_p = list(inspect.signature(getattr(our_mod, n)).parameters.values())
+            assert [p.name for p in our_p[:len(ref_p)]] == [p.name for p in ref_p], n
+            for r, o in zip(ref_p, our_p):
+                if r.default is not inspect.Parameter.empty:
+                    assert o.default == r.default, (n, r.name, r.default, o.default)
+            assert all(p.default is not inspect.Parameter.empty for p in our_p[len(ref_p):]), n
+            checked += 1
+    ref_mm = importlib.import_module("core.ml.model_manager").ModelManager
+    our_mm = importlib.import_module("mangatranslator_b200.core.ml.model_manager").ModelManager
+    for m in D._LOADERS:
+        ref_p = list(inspect.signature(getattr(ref_mm, m)).parameters.values())
+        our_p = list(inspect.signature(getattr(our_mm, m)).parameters.values())
+        assert [(p.name, p.default) for p in ref_p] == [(p.name, p.default) for p in our_p], m
+        checked += 1
+    assert checked == 14
