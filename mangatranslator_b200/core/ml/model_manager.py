@@ -98,7 +98,7 @@ class ModelManager:
         self.hf_token = token or ""
 
     def is_loaded(self, model_type: ModelType) -> bool:
-        return model_type in self.models
+        return self.models.get(model_type) is not None        # the reference leaves `models[t] = None` after an unload
 
     def _load_file_state_dict(self, path: Path) -> Optional[dict]:
         if not path.exists():
@@ -122,7 +122,7 @@ class ModelManager:
     def load_yolo_speech_bubble(self, model_path=None, verbose: bool = False):
         mt = self._resolve_yolo_type(model_path)
         with self._lock:
-            if mt in self.models:
+            if self.models.get(mt) is not None:
                 return self.models[mt]
             from mangatranslator_b200.yolo import YoloB200
             dev = self._require_cuda()
@@ -137,7 +137,7 @@ class ModelManager:
 
     def load_sam2(self, verbose: bool = False):
         with self._lock:
-            if ModelType.SAM2 in self.models:
+            if self.models.get(ModelType.SAM2) is not None:
                 return self.models[ModelType.SAM2]
             from mangatranslator_b200.sam2 import Sam2B200
             from mangatranslator_b200.sam2_api import Sam2ModelB200, Sam2ProcessorB200
@@ -149,7 +149,7 @@ class ModelManager:
 
     def _load_rcan(self, mt: ModelType, verbose: bool):
         with self._lock:
-            if mt in self.models:
+            if self.models.get(mt) is not None:
                 return self.models[mt]
             from mangatranslator_b200.rcan import RcanB200
             dev = self._require_cuda()
@@ -175,7 +175,7 @@ class ModelManager:
         """RT-DETRv2 conjoined / fallback bubble detector (reference :745-778 returns an RTDetrYOLOAdapter; the B200
         object has the same call shape and `.names`)."""
         with self._lock:
-            if ModelType.RTDETR_CONJOINED_BUBBLE in self.models:
+            if self.models.get(ModelType.RTDETR_CONJOINED_BUBBLE) is not None:
                 return self.models[ModelType.RTDETR_CONJOINED_BUBBLE]
             from mangatranslator_b200.rtdetr import RtDetrB200
             log_message("Loading RT-DETR conjoined bubble detection model...", verbose=verbose)
@@ -196,12 +196,12 @@ class ModelManager:
             return model
 
     def load_yolo_osbtext(self, token: str = "", verbose: bool = False):
-        if ModelType.YOLO_OSBTEXT in self.models:
+        if self.models.get(ModelType.YOLO_OSBTEXT) is not None:
             return self.models[ModelType.YOLO_OSBTEXT]
         self._out_of_scope("OSB text detector")
 
     def load_yolo_panel(self, verbose: bool = False):
-        if ModelType.YOLO_PANEL in self.models:
+        if self.models.get(ModelType.YOLO_PANEL) is not None:
             return self.models[ModelType.YOLO_PANEL]
         self._out_of_scope("panel detector")
 
@@ -216,7 +216,16 @@ class ModelManager:
             self.clear_cache()
 
     def unload_ocr_models(self, verbose: bool = False) -> None:
-        self.unload_model(ModelType.MANGA_OCR, verbose=verbose)
+        """Same set as the reference (:1397-1432): what it calls "OCR-related" includes the detectors and SAM."""
+        group = (ModelType.YOLO_SPEECH_BUBBLE, ModelType.YOLO_SPEECH_BUBBLE_2, ModelType.RTDETR_CONJOINED_BUBBLE,
+                 ModelType.SAM2, ModelType.SAM3, ModelType.YOLO_OSBTEXT, ModelType.YOLO_PANEL, ModelType.MANGA_OCR,
+                 ModelType.PADDLE_OCR_VL)
+        had = [t for t in group if self.is_loaded(t)]
+        for t in group:
+            self.unload_model(t, force_gc=False, verbose=verbose)
+        self.clear_cache()
+        if had:
+            log_message("OCR models unloaded.", verbose=verbose)
 
     def unload_upscale_models(self, verbose: bool = False) -> None:
         self.unload_model(ModelType.UPSCALE, verbose=verbose)
@@ -233,7 +242,7 @@ class ModelManager:
             torch.cuda.empty_cache()
 
     def get_memory_stats(self) -> dict:
-        stats = {"loaded_models": [m.value for m in self.models]}
+        stats = {"loaded_models": [m.value for m, v in self.models.items() if v is not None]}
         if torch.cuda.is_available():
             stats["cuda_allocated_mb"] = torch.cuda.memory_allocated() / 2 ** 20
             stats["cuda_reserved_mb"] = torch.cuda.memory_reserved() / 2 ** 20

@@ -15,7 +15,9 @@
                        * the hot-path loaders of the reference's ModelManager (load_yolo_speech_bubble, load_sam2,
                          load_upscale, load_upscale_lite, load_rtdetr_conjoined_bubble: core/ml/model_manager.py:617-1010)
                          delegate to this build's manager, so reference code that loads a model itself and passes it on
-                         (core/pipeline.py:235-237,889-891, core/outside_text_processor.py:94-107) gets a B200 object;
+                         (core/pipeline.py:235-237,889-891, core/outside_text_processor.py:94-107) gets a B200 object, which is
+                         also entered in the reference manager's `models` table; `unload_model` / `unload_all` (and
+                         through them unload_ocr_models / unload_upscale_models) are forwarded;
                        * this build's exception classes are rebound to the reference's (utils/exceptions.py), so the
                          reference's `except ImageProcessingError` / `except ModelError` clauses catch what the B200 stage
                          functions raise.
@@ -134,9 +136,17 @@ def install_overlay(reference_root: Optional[str] = None, extra_prefixes: Tuple[
     ref_mm = importlib.import_module("core.ml.model_manager")
     our_mm = importlib.import_module("mangatranslator_b200.core.ml.model_manager")
 
+    def mirror(ref_self, obj):
+        """Make the delegated object visible in the reference manager's own table (is_loaded, memory stats)."""
+        for t, v in list(our_mm.get_model_manager().models.items()):
+            if v is obj and hasattr(ref_mm.ModelType, t.name):
+                ref_self.models[ref_mm.ModelType[t.name]] = obj
+
     def delegate(method: str):
         def loader(self, *args, **kwargs):
-            return getattr(our_mm.get_model_manager(), method)(*args, **kwargs)
+            obj = getattr(our_mm.get_model_manager(), method)(*args, **kwargs)
+            mirror(self, obj)
+            return obj
         loader.__name__ = method
         loader.__doc__ = f"B200 overlay: delegates to mangatranslator_b200 ModelManager.{method}"
         return loader
@@ -145,12 +155,26 @@ def install_overlay(reference_root: Optional[str] = None, extra_prefixes: Tuple[
         if m in ref_mm.ModelManager.__dict__:
             _set(ref_mm.ModelManager, m, delegate(m))
             stats["loaders"] += 1
-    orig_unload = ref_mm.ModelManager.__dict__.get("unload_upscale_models")
-    if orig_unload is not None:
-        def unload_upscale_models(self, *args, **kwargs):
-            our_mm.get_model_manager().unload_upscale_models(*args, **kwargs)
-            return orig_unload(self, *args, **kwargs)
-        _set(ref_mm.ModelManager, "unload_upscale_models", unload_upscale_models)
+
+    # unloads are forwarded so the B200 objects really leave the device when the reference drops its handle
+    def forward(method: str, call):
+        orig = ref_mm.ModelManager.__dict__.get(method)
+        if orig is None:
+            return
+
+        def wrapper(self, *args, **kwargs):
+            call(our_mm.get_model_manager(), *args, **kwargs)
+            return orig(self, *args, **kwargs)
+        wrapper.__name__ = method
+        _set(ref_mm.ModelManager, method, wrapper)
+
+    def unload_one(ours, model_type, force_gc=True, verbose=False):
+        name = getattr(model_type, "name", None)
+        if name in our_mm.ModelType.__members__:
+            ours.unload_model(our_mm.ModelType[name], force_gc=force_gc, verbose=verbose)
+
+    forward("unload_model", unload_one)
+    forward("unload_all", lambda ours, verbose=False: ours.unload_all(verbose=verbose))
     del our_mods
     return stats
 

@@ -60,6 +60,22 @@ def test_overlay_rebinds_stage_functions_exceptions_and_loaders_and_restores_the
                 raise SystemExit(m + " did not raise")
             except RE.ModelError as e:
                 assert "no CPU fallback" in str(e)
+        # a delegated load is entered in the reference manager's own table; its unloads reach the B200 manager
+        import mangatranslator_b200.core.ml.model_manager as OM
+        ours, theirs, dummy = OM.get_model_manager(), RM.get_model_manager(), object()
+
+        def fake_load(verbose=False):
+            ours.models[OM.ModelType.UPSCALE] = dummy
+            return dummy
+        ours.load_upscale = fake_load
+        assert theirs.load_upscale() is dummy and theirs.is_loaded(RM.ModelType.UPSCALE)
+        assert theirs.models[RM.ModelType.UPSCALE] is dummy and ours.is_loaded(OM.ModelType.UPSCALE)
+        theirs.unload_upscale_models()
+        assert not theirs.is_loaded(RM.ModelType.UPSCALE) and not ours.is_loaded(OM.ModelType.UPSCALE)
+        ours.models[OM.ModelType.SAM2] = dummy
+        theirs.unload_all()
+        assert not ours.is_loaded(OM.ModelType.SAM2) and not ours.models
+        del ours.load_upscale
         D.uninstall_overlay()
         assert (RP.detect_speech_bubbles, RD.detect_speech_bubbles, RT.calculate_centroid_expansion_box) == before
         assert OU.ImageProcessingError is not RE.ImageProcessingError

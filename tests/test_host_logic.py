@@ -205,3 +205,27 @@ def test_core_package_exports_the_reference_names_lazily():
     out = subprocess.check_output([sys.executable, "-c", code], cwd=H_ROOT).decode().strip()
     assert out == "False"
     assert importlib.import_module("mangatranslator_b200.core._version").__version__ == core.__version__
+
+
+def test_model_manager_lifecycle_follows_the_reference_conventions():
+    """unload_ocr_models releases what the reference calls OCR-related (detectors, SAM, manga-ocr: model_manager.py
+    :1397-1432) and keeps the upscalers; a slot left as None (the reference's state after an unload, :1384-1385) counts as
+    not loaded."""
+    from mangatranslator_b200.core.ml.model_manager import ModelType, get_model_manager
+    mm = get_model_manager()
+    saved = dict(mm.models)
+    try:
+        mm.models.clear()
+        for t in (ModelType.YOLO_SPEECH_BUBBLE, ModelType.YOLO_SPEECH_BUBBLE_2, ModelType.RTDETR_CONJOINED_BUBBLE,
+                  ModelType.SAM2, ModelType.MANGA_OCR, ModelType.UPSCALE, ModelType.UPSCALE_LITE):
+            mm.models[t] = object()
+        mm.unload_ocr_models()
+        assert sorted(t.name for t in mm.models if mm.is_loaded(t)) == ["UPSCALE", "UPSCALE_LITE"]
+        mm.models[ModelType.UPSCALE] = None
+        assert not mm.is_loaded(ModelType.UPSCALE) and mm.is_loaded(ModelType.UPSCALE_LITE)
+        assert mm.get_memory_stats()["loaded_models"] == ["upscale_lite"]
+        mm.unload_upscale_models()
+        assert not any(mm.is_loaded(t) for t in ModelType)
+    finally:
+        mm.models.clear()
+        mm.models.update(saved)
