@@ -27,3 +27,18 @@ def empty_cache(device: Optional[torch.device] = None) -> None:
 def synchronize(device: Optional[torch.device] = None) -> None:
     if torch.cuda.is_available():
         torch.cuda.synchronize()
+
+
+def get_device_info(device: Optional[torch.device] = None) -> dict:
+    """The reference's report format (core/device.py:116-172): device name + allocated / reserved GB as 2-decimal strings
+    on CUDA, {"device": "cpu", "memory": "N/A"} otherwise."""
+    device = device or get_best_device()
+    if device.type == "cuda" and torch.cuda.is_available():
+        return {"device": torch.cuda.get_device_name(0),
+                "allocated_gb": f"{torch.cuda.memory_allocated() / 1024 ** 3:.2f}",
+                "reserved_gb": f"{torch.cuda.memory_reserved() / 1024 ** 3:.2f}"}
+    return {"device": "cpu", "memory": "N/A"}
+
+
+def is_gpu_available() -> bool:
+    return torch.cuda.is_available()

@@ -242,14 +242,19 @@ class ModelManager:
             torch.cuda.empty_cache()
 
     def get_memory_stats(self) -> dict:
-        stats = {"loaded_models": [m.value for m, v in self.models.items() if v is not None]}
-        if torch.cuda.is_available():
-            stats["cuda_allocated_mb"] = torch.cuda.memory_allocated() / 2 ** 20
-            stats["cuda_reserved_mb"] = torch.cuda.memory_reserved() / 2 ** 20
+        """The reference's device report (:1495-1497 -> core/device.py get_device_info) plus the loaded model names."""
+        from mangatranslator_b200.core.device import get_device_info
+        stats = get_device_info(self.device if isinstance(self.device, torch.device) else None)
+        stats["loaded_models"] = [m.value for m, v in self.models.items() if v is not None]
         return stats
 
     def print_memory_stats(self) -> None:
-        log_message(f"Model memory: {self.get_memory_stats()}", always_print=True)
+        stats = self.get_memory_stats()
+        if stats.get("memory") == "N/A":
+            log_message(f"Device: {stats['device']}", always_print=True)
+        else:
+            log_message(f"GPU Memory - Allocated: {stats['allocated_gb']} GB, Reserved: {stats['reserved_gb']} GB",
+                        always_print=True)
 
 
 def get_model_manager() -> ModelManager:

@@ -223,7 +223,10 @@ def test_model_manager_lifecycle_follows_the_reference_conventions():
         assert sorted(t.name for t in mm.models if mm.is_loaded(t)) == ["UPSCALE", "UPSCALE_LITE"]
         mm.models[ModelType.UPSCALE] = None
         assert not mm.is_loaded(ModelType.UPSCALE) and mm.is_loaded(ModelType.UPSCALE_LITE)
-        assert mm.get_memory_stats()["loaded_models"] == ["upscale_lite"]
+        stats = mm.get_memory_stats()
+        assert stats["loaded_models"] == ["upscale_lite"]
+        assert ("allocated_gb" in stats and "reserved_gb" in stats) or stats.get("memory") == "N/A"   # core/device.py:116-172
+        mm.print_memory_stats()
         mm.unload_upscale_models()
         assert not any(mm.is_loaded(t) for t in ModelType)
     finally:
