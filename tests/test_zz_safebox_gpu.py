@@ -1,7 +1,8 @@
 """GPU: the safe-text-box kernels (mtb_safe_boxes, through the C ABI) against the reference's golden vectors and the CPU
 oracle — bit-exact boxes, centroid doubles, anchor rule, anchor pixel, maximal squared distance, mask bounds, errors.
 Reference: core/image/image_utils.py:173-348 `calculate_centroid_expansion_box`.
-(Sorted last on purpose: first device run of this kernel family happens at the end of round 1.)"""
+(The first four tests ran green on a B200 in round 1, profiles/r01_safebox_timing.json; the clean -> text-box chain test
+was written after the round's GPU budget was spent, which is why the file sorts last.)"""
 import json
 import os
 
