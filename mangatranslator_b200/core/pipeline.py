@@ -66,8 +66,20 @@ def _target_mode(config: MangaTranslatorConfig, image_path, output_path) -> str:
     return "RGB" if fmt == "jpeg" or (fmt == "auto" and ext in (".jpg", ".jpeg")) else "RGBA"
 
 
-def _render_page(image_path, config: MangaTranslatorConfig, output_path=None, cancellation_manager=None):
-    """Everything of translate_and_render up to (not including) the save: returns (image, target_mode)."""
+def _load_page(image_path) -> Image.Image:
+    """Open and fully decode a page file (pipeline.py:689-696)."""
+    try:
+        pil = Image.open(image_path)
+        pil.load()
+        return pil
+    except Exception as e:
+        raise ImageProcessingError(f"Error loading image {image_path}: {e}")
+
+
+def _render_page(image_path, config: MangaTranslatorConfig, output_path=None, cancellation_manager=None, preloaded=None):
+    """Everything of translate_and_render up to (not including) the save: returns (image, target_mode).  `preloaded`:
+    a pending decode of this page (concurrent.futures.Future of _load_page) started while the previous page was on the
+    device."""
     verbose = config.verbose
     if not (config.cleaning_only or config.upscaling_only):
         raise ValidationError("this build implements the vision hot path only: set cleaning_only or upscaling_only "
@@ -75,11 +87,7 @@ def _render_page(image_path, config: MangaTranslatorConfig, output_path=None, ca
     if cancellation_manager is not None and cancellation_manager.is_cancelled():
         raise CancellationError("Process cancelled by user.")
     image_path = Path(image_path)
-    try:
-        pil = Image.open(image_path)
-        pil.load()
-    except Exception as e:
-        raise ImageProcessingError(f"Error loading image {image_path}: {e}")
+    pil = preloaded.result() if preloaded is not None else _load_page(image_path)
     target_mode = _target_mode(config, image_path, output_path)
     pil = convert_image_to_target_mode(pil, target_mode, verbose)
     if config.preprocessing.enabled:
@@ -133,14 +141,14 @@ def translate_and_render(image_path, config: MangaTranslatorConfig, output_path=
     return out
 
 
-def _process_page(path, config, out_path, cancellation_manager, saver):
+def _process_page(path, config, out_path, cancellation_manager, saver, preloaded=None):
     """One page of the batch: with a writer pool the encode + write of this page overlaps the next page's device work
     (returns the pending save), otherwise exactly translate_and_render."""
     if saver is None:
         translate_and_render(path, config, out_path, cancellation_manager=cancellation_manager)
         return None
     start = time.time()
-    out, target_mode = _render_page(path, config, out_path, cancellation_manager)
+    out, target_mode = _render_page(path, config, out_path, cancellation_manager, preloaded)
     log_message(f"Processing completed in {time.time() - start:.2f}s (save queued)", always_print=True)
     return saver.submit(_save_page, out, target_mode, out_path, config)
 
@@ -160,6 +168,11 @@ class _BoundedPool:
         fut = self._pool.submit(fn, *args)
         fut.add_done_callback(lambda _f: self._slots.release())
         return fut
+
+    def submit_unbounded(self, fn, *args):
+        """For the page decode that runs one page ahead: at most one is pending, it must never wait behind the saves'
+        back-pressure."""
+        return self._pool.submit(fn, *args)
 
     def close(self):
         self._pool.shutdown(wait=True)
@@ -252,8 +265,9 @@ def batch_translate_images(input_dir, config: MangaTranslatorConfig, output_dir=
     `preserve_structure`) in natural order, each written as `<stem>_translated.<ext>`; returns {success_count,
     error_count, errors{name: message}, failed_image_paths[source paths][, failed_paths_file][, retry_*]}; failed pages
     are retried once when `config.retry_failed_once`; a cancellation propagates as CancellationError.
-    The encode + write of a finished page runs on a small writer pool (`MTB200_SAVE_WORKERS`, default 2, 0 = inline) so it
-    overlaps the next page's device work; a page is counted once its file is on disk.
+    The encode + write of a finished page runs on a small worker pool (`MTB200_SAVE_WORKERS`, default 2, 0 = inline) so it
+    overlaps the next page's device work, and the next page's file is decoded one page ahead on the same pool; a page is
+    counted once its file is on disk.
     Under torchrun the sorted page list is sharded over the ranks (`PageShardCoordinator`: page i goes to rank i mod R,
     no data-path collective); every rank returns its own counts and rank 0 the merged result with the failure file."""
     empty = {"success_count": 0, "error_count": 0, "errors": {}, "failed_image_paths": []}
@@ -303,8 +317,16 @@ def batch_translate_images(input_dir, config: MangaTranslatorConfig, output_dir=
                 failed(key, path, shown, e)
         pending[:] = keep
 
+    decode = {}                                    # index -> pending decode of that page (one page ahead)
+
+    def prefetch(j):
+        if saver is not None and j < total and j not in decode:
+            decode[j] = saver.submit_unbounded(_load_page, mine[j])
+
     try:
         for i, path in enumerate(mine):
+            prefetch(i)
+            prefetch(i + 1)                        # decoded while page i is on the device
             out_path, shown, key = resolve_output_path(path, input_dir, out_dir, config, preserve_structure)
             if cancellation_manager is not None and cancellation_manager.is_cancelled():
                 raise CancellationError("Batch process cancelled by user.")
@@ -312,7 +334,7 @@ def batch_translate_images(input_dir, config: MangaTranslatorConfig, output_dir=
                 progress_callback(i / total, f"Processing image {i + 1}/{total}: {shown}")
             log_message(f"Processing {i + 1}/{total}: {shown}", always_print=True)
             try:
-                fut = _process_page(path, config, out_path, cancellation_manager, saver)
+                fut = _process_page(path, config, out_path, cancellation_manager, saver, decode.pop(i, None))
                 if fut is None:
                     res["success_count"] += 1
                 else:

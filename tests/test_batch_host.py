@@ -138,7 +138,7 @@ def test_batch_flow_counts_errors_retry_and_cancellation(tmp_path, monkeypatch, 
     inp = _make_dir(tmp_path)
     seen, fail_once = [], {"bad.png": 1, "stage": "render"}
 
-    def fake_render(path, config, output_path=None, cancellation_manager=None):
+    def fake_render(path, config, output_path=None, cancellation_manager=None, preloaded=None):
         seen.append((Path(path).name, Path(output_path).name))
         if Path(path).name == "bad.png" and fail_once["stage"] == "render" and fail_once["bad.png"] != 0:
             fail_once["bad.png"] -= 1
@@ -203,7 +203,7 @@ def test_writer_pool_overlaps_saving_with_the_next_pages_device_work(tmp_path, m
     inp.mkdir()
     for i in range(8):
         (inp / f"{i}.png").write_bytes(b"x")
-    monkeypatch.setattr(P, "_render_page", lambda path, config, output_path=None, cancellation_manager=None:
+    monkeypatch.setattr(P, "_render_page", lambda path, config, output_path=None, cancellation_manager=None, preloaded=None:
                         (time.sleep(0.05), ("img", "RGB"))[1])
     monkeypatch.setattr(P, "_save_page", lambda image, mode, out, config: (time.sleep(0.15), Path(out).write_bytes(b"ok"))[1])
     cfg = MangaTranslatorConfig(cleaning_only=True)
@@ -218,6 +218,33 @@ def test_writer_pool_overlaps_saving_with_the_next_pages_device_work(tmp_path, m
     assert took["2"] < 0.75 * took["0"], took    # saves ride under the following renders, two at a time
 
 
+@pytest.mark.parametrize("workers", ["0", "2"], ids=["inline", "decoded_ahead"])
+def test_unreadable_page_is_booked_with_the_reference_message(tmp_path, monkeypatch, workers):
+    """The real load path (inline or one page ahead on the worker pool): a corrupt file fails with "Error loading image"
+    (pipeline.py:689-696) and the following page is still decoded and handed on."""
+    monkeypatch.setenv("MTB200_SAVE_WORKERS", workers)
+    inp = tmp_path / "in"
+    inp.mkdir()
+    (inp / "1.png").write_bytes(b"not a png")
+    Image.new("RGB", (8, 8), (1, 2, 3)).save(inp / "2.png")
+    got = []
+    real_load = P._load_page
+
+    def stage(pil, config, bubbles, scale, verbose):           # stands for detect + clean (needs a GPU)
+        got.append(pil.size)
+        return pil, []
+
+    monkeypatch.setattr(P, "detect_speech_bubbles", lambda *a, **k: ([], []))
+    monkeypatch.setattr(P, "_clean_speech_bubbles_for_page", stage)
+    monkeypatch.setattr(P, "get_cache", lambda: type("C", (), {"set_current_image": staticmethod(lambda *a, **k: None)})())
+    res = P.batch_translate_images(inp, MangaTranslatorConfig(cleaning_only=True), tmp_path / "out")
+    assert P._load_page is real_load
+    assert res["success_count"] == 1 and res["error_count"] == 1
+    assert list(res["errors"]) == ["1.png"] and res["errors"]["1.png"].startswith("Error loading image")
+    assert got == [(8, 8)] and (tmp_path / "out" / "2_translated.png").exists()
+    assert Image.open(tmp_path / "out" / "2_translated.png").mode == "RGBA"       # PNG target mode (pipeline.py:702-712)
+
+
 _WORKER = r"""
 import os, sys
 from pathlib import Path
@@ -225,7 +252,7 @@ sys.path.insert(0, {root!r})
 from mangatranslator_b200.core import pipeline as P
 from mangatranslator_b200.core.config import MangaTranslatorConfig
 rank = int(os.environ["RANK"])
-def render(path, config, output_path=None, cancellation_manager=None):
+def render(path, config, output_path=None, cancellation_manager=None, preloaded=None):
     if Path(path).name == "7.png":
         raise RuntimeError("bad page")
     return "img", "RGB"
