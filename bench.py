@@ -128,6 +128,74 @@ def cpu_baseline(sample_pages: int = 1, crop: int = 0):
                 stage_seconds={k: round(v, 3) for k, v in stages.items()})
 
 
+def gpu_baseline(dev, reps: int = 3):
+    """Secondary comparator: the SAME torch modules the CPU arm runs (oracle/*), moved to the
+    GPU with torch's defaults — cuDNN TF32 convolutions for the RCAN and YOLO (core/ml/model_manager.py:640-654 puts the
+    fp32 module on the device and calls it), bf16 weights for SAM (model_manager.py:1001).  ms per 1536x1024 page and
+    per stage; not the product path and not a parity reference (TF32 misses the 1e-3 bound)."""
+    import pipeline_oracle
+    import yolo_oracle
+    from PIL import Image
+    from mangatranslator_b200 import synth
+    out = {}
+    pipe = pipeline_oracle.CpuPipeline(0)
+    pg = synth.make_page(9000, H, W, n_bubbles=BUBBLES)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    with torch.no_grad():
+        x = torch.from_numpy(np.ascontiguousarray(pg.image_rgb)).to(dev).permute(2, 0, 1).float().div(255.0).unsqueeze(0)
+        rcan = pipe.rcan.to(dev)
+        rcan.forward = _rcan_forward_on(rcan, dev)
+        out["upscale_tf32_ms"] = round(timed(lambda: rcan(x)), 2)
+        rcl = rcan.to(memory_format=torch.channels_last)
+        xcl = x.contiguous(memory_format=torch.channels_last)
+        torch.backends.cudnn.benchmark = True
+        out["upscale_tf32_channels_last_autotuned_ms"] = round(timed(lambda: rcl(xcl)), 2)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out["upscale_bf16_autocast_ms"] = round(timed(lambda: rcl(xcl)), 2)
+        torch.backends.cudnn.benchmark = False
+        del rcan, rcl
+        yolo = pipe.yolo.to(dev)
+        xin = yolo_oracle.preprocess(np.ascontiguousarray(pg.image_rgb[:, :, ::-1]), 1600).to(dev)
+        out["detect_network_tf32_ms"] = round(timed(lambda: yolo(xin)), 2)
+        del yolo
+        sam = pipe.sam.to(dev).to(torch.bfloat16)
+        boxes = torch.as_tensor(pg.boxes_xyxy, dtype=torch.float32).unsqueeze(0)
+        inputs = pipe.proc(Image.fromarray(pg.image_rgb), input_boxes=boxes, return_tensors="pt")
+        inputs = {k: (v.to(dev).to(torch.bfloat16) if torch.is_tensor(v) and v.is_floating_point() else
+                      v.to(dev) if torch.is_tensor(v) else v) for k, v in inputs.items()}
+        out["segment_network_bf16_ms"] = round(timed(lambda: sam(multimask_output=False, **inputs)), 2)
+        del sam
+    torch.cuda.empty_cache()
+    tot = out["upscale_tf32_ms"] + out["detect_network_tf32_ms"] + out["segment_network_bf16_ms"]
+    out["pages_per_s_networks_only"] = round(1000.0 / tot, 3)
+    out["note"] = ("torch eager on the same B200, same seeded weights: RCAN/YOLO fp32 modules with cuDNN TF32 (torch default), "
+                   "SAM 2.1 in bf16; networks only (no letterbox, NMS, mask post-processing, cleaning or copies)")
+    return out
+
+
+def _rcan_forward_on(rcan, dev):
+    """The oracle builds its mean tensor on the CPU; bind a forward that keeps every operand on `dev`."""
+    import torch.nn.functional as F
+
+    def fwd(x):
+        x = x * rcan.rgb_range
+        h = rcan.head(x)
+        y = rcan.body(h) + h
+        return rcan.tail(y) / rcan.rgb_range
+    return fwd
+
+
 def run_reference(args, coord):
     if coord.rank != 0:
         return
@@ -359,6 +427,12 @@ def run_ours(args, coord):
             roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             pass
+    gbase = None
+    if coord.world == 1 and not args.no_gpu_baseline:
+        try:
+            gbase = gpu_baseline(dev)
+        except Exception as e:                     # a comparator must never take the headline line down
+            gbase = dict(error=repr(e)[:200])
     base = cpu_baseline() if coord.world == 1 and not args.no_cpu_baseline else None
     line = dict(metric=METRIC, value=value, unit="pages/s", n_gpus=coord.world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -379,6 +453,8 @@ def run_ours(args, coord):
                 stage_roofline=stage_rooflines(stage, peaks, sam_variant), side_stage_ms=extras)
     if base is not None:
         line["cpu_baseline"] = base
+    if gbase is not None:
+        line["gpu_baseline"] = gbase
     print(json.dumps(line))
 
 
@@ -393,7 +469,12 @@ def main():
                     help="SAM 2.1 variant (BASELINE.json names tiny; large = the checkpoint the reference loads)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--only-gpu-baseline", action="store_true", help="print the torch-eager-on-GPU comparator and exit")
     args = ap.parse_args()
+    if args.only_gpu_baseline:
+        print(json.dumps(dict(gpu_baseline=gpu_baseline(torch.device("cuda", 0)))))
+        return
     from mangatranslator_b200.core.batch_coordinator import PageShardCoordinator
     if args.impl == "reference":
         os.environ.setdefault("CUDA_VISIBLE_DEVICES", "")

@@ -57,9 +57,24 @@ def _declare(l: C.CDLL) -> None:
     l.mtb_conv_plan_set_border_sums.restype = i32
     l.mtb_conv_plan_destroy.argtypes = [vp]
     l.mtb_conv_plan_destroy.restype = None
-    if hasattr(l, "mtb_exp_shifted_desc"):
-        l.mtb_exp_shifted_desc.argtypes = [vp, vp, vp, i32, i32, i32, vp]
-        l.mtb_exp_shifted_desc.restype = i32
+
+
+_exp = None
+
+
+def exp_lib() -> C.CDLL:
+    """libmtb200_exp.so: hardware-behaviour probes (csrc/experiments.cu).  Tools only; nothing in the product imports it."""
+    global _exp
+    if _exp is None:
+        lib()   # the probes link against the product library (TMA-descriptor and error helpers)
+        path = LIB_PATH.parent / "libmtb200_exp.so"
+        if not path.exists():
+            raise MtbError(f"{path} not found: run `make -C mangatranslator_b200/csrc`")
+        _exp = C.CDLL(str(path))
+        vp, i32 = C.c_void_p, C.c_int
+        _exp.mtb_exp_shifted_desc.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+        _exp.mtb_exp_shifted_desc.restype = i32
+    return _exp
 
 
 def check(rc: int, what: str = "") -> None:

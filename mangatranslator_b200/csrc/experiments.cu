@@ -74,7 +74,7 @@ shifted_desc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // D[128][64] = A_view * B^T over K = 64 (two K = 32 instructions).
 __global__ void __launch_bounds__(128, 1)
 shifted_desc8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* D,
-                     int shift_rows, int sbo_bytes, int base_offset) {
+                     int shift_rows, int sbo_bytes, int base_offset, int kind /* 0: e5m2 K=32, 1: fp16 K=16 */) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                 // 512 rows x 64 B = 32 KB
@@ -106,12 +106,16 @@ shifted_desc8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     mbar_wait(bar, 0);
     tc_fence_after();
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_e5m2(128, 64);
       const uint32_t a0 = smem_u32(sA) + shift_rows * 64;
       const uint32_t b0 = smem_u32(sB);
       for (int k = 0; k < 2; ++k) {
-        umma_f8f6f4(tmem_base, make_sdesc_sw64(a0 + k * 32, sbo_bytes, base_offset),
-                    make_sdesc_sw64(b0 + k * 32, 512, 0), idesc, k > 0);
+        // a 64-byte row is K = 64 e5m2 values or K = 32 halves: either way two instructions, 32 B apart
+        if (kind == 0)
+          umma_f8f6f4(tmem_base, make_sdesc_sw64(a0 + k * 32, sbo_bytes, base_offset),
+                      make_sdesc_sw64(b0 + k * 32, 512, 0), make_idesc_e5m2(128, 64), k > 0);
+        else
+          umma_bf16(tmem_base, make_sdesc_sw64(a0 + k * 32, sbo_bytes, base_offset),
+                    make_sdesc_sw64(b0 + k * 32, 512, 0), make_idesc_f16(128, 64), k > 0);
       }
       umma_commit(mma_bar);
     }
@@ -215,7 +219,9 @@ mixed_kind_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_consta
 // after each one (the mixed shapes of the bf16x3 schemes).
 // FP8 = 1: the FIRST MMA is kind::f8f6f4 (e5m2, K = 32); FP8 = 2: the SECOND one is, and it accumulates into the same TMEM
 // columns as the first (the fp16 + e5m2-correction scheme of DESIGN.md §8.0: mixed kinds into one fp32 accumulator).
-template <int M1, int N1, int M2, int N2, int FP8 = 0>
+// FP8 = 3 (the slot schedule of the fp16 + e5m2 body conv): two kind::f16 M1 x N1 MMAs, then one e5m2 M2 x N2 MMA, all
+// into one accumulator.  SW64: operands described as 64-byte-swizzled 64-byte rows (B groups 512 B apart).
+template <int M1, int N1, int M2, int N2, int FP8 = 0, bool SW64 = false>
 __global__ void __launch_bounds__(64, 1) mma_rate_kernel(long long* cycles, int iters, int a_sbo, int a_shift) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -248,8 +254,16 @@ __global__ void __launch_bounds__(64, 1) mma_rate_kernel(long long* cycles, int 
           const uint32_t a0 = a_base + tap * a_shift, b0 = b_base + (tap & 7) * 16384;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_sdesc_sw128(a0 + k * 32, a_sbo, 0);
-            const uint64_t db = make_sdesc_sw128(b0 + k * 32, 1024, 0);
+            const uint64_t da = SW64 ? make_sdesc_sw64(a0 + (k & 1) * 32 + (k >> 1) * 8192, a_sbo, 0)
+                                     : make_sdesc_sw128(a0 + k * 32, a_sbo, 0);
+            const uint64_t db = SW64 ? make_sdesc_sw64(b0 + (k & 1) * 32 + (k >> 1) * 8192, 512, 0)
+                                     : make_sdesc_sw128(b0 + k * 32, 1024, 0);
+            if (FP8 == 3) {
+              umma_bf16(0, da, db, id1, (it | tap | k) ? 1u : 0u);
+              umma_bf16(0, da, db, id1, 1u);
+              umma_f8f6f4(0, da, db, id2, 1u);
+              continue;
+            }
             if (FP8 == 1) umma_f8f6f4(0, da, db, id1, (it | tap | k) ? 1u : 0u);
             else umma_bf16(0, da, db, id1, (it | tap | k) ? 1u : 0u);
             if (M2 > 0) {
@@ -274,18 +288,21 @@ __global__ void __launch_bounds__(64, 1) mma_rate_kernel(long long* cycles, int 
 
 // pattern: 0 M128N64, 1 M128N128, 2 M128N256, 3 M128N128+M128N64, 4 M128N240, 5 M64N240, 6 M64N256, 7 M64N128,
 //          8 M128N240+M64N240, 9 M64N64, 10 M128N240 e5m2, 11 M64N240 e5m2, 12 M128N240 f16 + M64N240 e5m2 into one
-//          accumulator, 13 M128N240 f16 + M128N240 e5m2 into one accumulator
+//          accumulator, 13 M128N240 f16 + M128N240 e5m2 into one accumulator, 14 = 2 x M128N240 f16 + 1 x M64N240 e5m2
+//          (one accumulator, 128B swizzle), 15 = 14 with 64-byte-swizzled 64-byte rows, 16 = M128N240 f16 alone, 64B swizzle,
+//          17 = M64N240 e5m2 alone, 64B swizzle
 extern "C" int mtb_exp_mma_rate(long long* cycles, int ctas, int pattern, int iters, int a_sbo, int a_shift, int a_off,
                                 void* stream) {
   (void)a_off;
   const size_t smem = 1024 + (48 + 144) * 1024 + 64;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define MTB_RATE8(M1, N1, M2, N2, F8)                                                                             \
+#define MTB_RATE9(M1, N1, M2, N2, F8, S64)                                                                        \
   do {                                                                                                            \
-    MTB_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel<M1, N1, M2, N2, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     static_cast<int>(smem)));                                                    \
-    mma_rate_kernel<M1, N1, M2, N2, F8><<<ctas, 64, smem, st>>>(cycles, iters, a_sbo, a_shift);                   \
+    MTB_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel<M1, N1, M2, N2, F8, S64>,                                    \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));       \
+    mma_rate_kernel<M1, N1, M2, N2, F8, S64><<<ctas, 64, smem, st>>>(cycles, iters, a_sbo, a_shift);              \
   } while (0)
+#define MTB_RATE8(M1, N1, M2, N2, F8) MTB_RATE9(M1, N1, M2, N2, F8, false)
 #define MTB_RATE(M1, N1, M2, N2) MTB_RATE8(M1, N1, M2, N2, 0)
   switch (pattern) {
     case 0: MTB_RATE(128, 64, 0, 0); break;
@@ -301,10 +318,15 @@ extern "C" int mtb_exp_mma_rate(long long* cycles, int ctas, int pattern, int it
     case 11: MTB_RATE8(64, 240, 0, 0, 1); break;
     case 12: MTB_RATE8(128, 240, 64, 240, 2); break;
     case 13: MTB_RATE8(128, 240, 128, 240, 2); break;
+    case 14: MTB_RATE9(128, 240, 64, 240, 3, false); break;
+    case 15: MTB_RATE9(128, 240, 64, 240, 3, true); break;
+    case 16: MTB_RATE9(128, 240, 0, 0, 0, true); break;
+    case 17: MTB_RATE9(64, 240, 0, 0, 1, true); break;
     default: MTB_RATE(64, 64, 0, 0); break;
   }
 #undef MTB_RATE
 #undef MTB_RATE8
+#undef MTB_RATE9
   MTB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -365,9 +387,9 @@ extern "C" int mtb_exp_mixed_kind(const void* A16 /* fp16 [128][64] */, const vo
   return 0;
 }
 
-extern "C" int mtb_exp_shifted_desc8(const void* A /* e5m2 [512][64] */, const void* B /* e5m2 [64][64] */,
-                                     float* D /* [128][64] */, int shift_rows, int sbo_bytes, int base_offset,
-                                     void* stream) {
+extern "C" int mtb_exp_shifted_desc8(const void* A /* e5m2 [512][64] or fp16 [512][32] */,
+                                     const void* B /* e5m2 [64][64] or fp16 [64][32] */, float* D /* [128][64] */,
+                                     int shift_rows, int sbo_bytes, int base_offset, int kind, void* stream) {
   CUtensorMap tmA, tmB;
   {
     const uint64_t dims[2] = {64, 512};
@@ -387,7 +409,7 @@ extern "C" int mtb_exp_shifted_desc8(const void* A /* e5m2 [512][64] */, const v
   MTB_CUDA_OK(cudaFuncSetAttribute(shifted_desc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
   shifted_desc8_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, D, shift_rows, sbo_bytes,
-                                                                           base_offset);
+                                                                           base_offset, kind);
   MTB_CUDA_OK(cudaGetLastError());
   return 0;
 }

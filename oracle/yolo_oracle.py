@@ -156,16 +156,16 @@ class YoloV8Seg(nn.Module):
             box.append(h.cv2[i](f).view(b, 64, -1))
             cls.append(h.cv3[i](f).view(b, h.nc, -1))
             mc.append(h.cv4[i](f).view(b, h.nm, -1))
-            sx = torch.arange(fw, dtype=torch.float32) + 0.5
-            sy = torch.arange(fh, dtype=torch.float32) + 0.5
+            sx = torch.arange(fw, dtype=torch.float32, device=f.device) + 0.5
+            sy = torch.arange(fh, dtype=torch.float32, device=f.device) + 0.5
             yy, xx = torch.meshgrid(sy, sx, indexing="ij")
             anchors.append(torch.stack((xx, yy), -1).view(-1, 2))
-            strides.append(torch.full((fh * fw, 1), float(self.strides[i])))
+            strides.append(torch.full((fh * fw, 1), float(self.strides[i]), device=f.device))
         box, cls, mc = torch.cat(box, 2), torch.cat(cls, 2), torch.cat(mc, 2)
         anchors, strides = torch.cat(anchors).t().unsqueeze(0), torch.cat(strides).t()
         b, _, a = box.shape
         dist = box.view(b, 4, 16, a).transpose(2, 1).softmax(1)            # DFL: softmax over 16 bins
-        dist = (dist * torch.arange(16, dtype=torch.float32).view(1, 16, 1, 1)).sum(1)
+        dist = (dist * torch.arange(16, dtype=torch.float32, device=box.device).view(1, 16, 1, 1)).sum(1)
         lt, rb = dist.chunk(2, 1)
         x1y1, x2y2 = anchors - lt, anchors + rb
         dbox = torch.cat(((x1y1 + x2y2) / 2, x2y2 - x1y1), 1) * strides      # xywh

@@ -57,8 +57,13 @@ class Conv(torch.nn.Module):
         if m.endswith("+mxfp4"):
             y = y + F.conv2d(mxfp4(x - xh, 1), mxfp4(w, 1), None, padding=1)
         elif "+" in m:
-            dt = F8[m.split("+")[1]]
-            y = y + F.conv2d(q((x - xh).float(), dt), q(w.float(), dt), None, padding=1)
+            name = m.split("+")[1]
+            sc = 1.0
+            if "s" in name:                      # "e5m2s4": residual scaled by 2^4 before the cast, weights by 2^-4
+                name, sh = name.split("s")
+                sc = 2.0 ** int(sh)
+            dt = F8[name]
+            y = y + F.conv2d(q(((x - xh) * sc).float(), dt), q((w / sc).float(), dt), None, padding=1)
         return y
 
 
@@ -125,7 +130,10 @@ def main():
             x = F.avg_pool2d(F.pad(x, (2, 2, 2, 2), mode="reflect"), 5, 1)
         with torch.no_grad():
             ref = build(seed, None)(x)
-            for mode in ("bf16x3", "tf32", "fp16", "fp16+e5m2", "fp16+e4m3", "fp16+mxfp4", "fp16+e5m2+trunk3"):
+            modes = ("bf16x3", "tf32", "fp16", "fp16+e5m2", "fp16+e4m3", "fp16+mxfp4", "fp16+e5m2+trunk3")
+            if len(sys.argv) > 4:
+                modes = tuple(sys.argv[4].split(","))
+            for mode in modes:
                 d = (build(seed, mode)(x) - ref).abs()
                 print(f"seed {seed} {mode:18s} max {float(d.max()):.2e} mean {float(d.mean()):.2e}", flush=True)
 

@@ -10,6 +10,7 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda:0")
 L = _lib.lib()
+LX = _lib.exp_lib()
 out = {}
 
 
@@ -28,7 +29,7 @@ def probe():
                 maps = []
                 for A in (A_row, A_row_hi, A_col):
                     Ab = A.to(torch.bfloat16).contiguous()
-                    _lib.check(L.mtb_exp_shifted_desc(Ab.data_ptr(), Bb.data_ptr(), D.data_ptr(), shift, sbo, bo, None))
+                    _lib.check(LX.mtb_exp_shifted_desc(Ab.data_ptr(), Bb.data_ptr(), D.data_ptr(), shift, sbo, bo, None))
                     torch.cuda.synchronize()
                     maps.append(D.clone())
                 src_row = (maps[0] + 256 * maps[1]).long()   # [128][64] source row of each element

@@ -4,7 +4,8 @@ import torch
 sys.path.insert(0, "/root/repo")
 from mangatranslator_b200 import _lib
 
-lib = _lib.lib()
+lib = _lib.exp_lib()
+main = _lib.lib()
 fn = lib.mtb_exp_mma_rate
 fn.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p]
 fn.restype = ctypes.c_int
