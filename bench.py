@@ -228,17 +228,25 @@ def measure_dominant_kernel(pipe, page_dev, peaks):
         by_kind[k] = by_kind.get(k, 0.0) + ms
     flops = 2.0 * H * W * 64 * 64 * 9
     ach = flops / (avg_ms * 1e-3) / 1e12
+    fp16c = getattr(rcan, "precision", "") == "fp16c"
+    # tensor-pipe work actually issued, in units of the algorithmic FLOPs: bf16x3 = 2 M128 MMAs per (tap, k16) where half an
+    # MMA would do = 4x; fp16c = 1 M128 fp16 MMA + half an e5m2 MMA slot (K = 32) = 3x
+    issue = 3.0 if fp16c else 4.0
+    kernel = "conv3x3_c64_fp16c_kernel<fp16 + e5m2 correction>" if fp16c else "conv3x3_c64_cm_kernel<bf16x3>"
+    note = ("algorithmic FLOPs (2*MAC of the fp32-grade conv); the kernel issues one [W16_hi;W16_lo] x X16 kind::f16 MMA per (tap, 16 "
+            "input channels) and one W8 x X8 kind::f8f6f4 MMA per (tap, 32 input channels): 54 MMA slots of 120 clk per 240-pixel "
+            "tile" if fp16c else
+            "algorithmic FLOPs (2*MAC of the fp32-grade conv); the channel-major bf16x3 kernel issues 4x that in bf16 MMAs "
+            "([W_hi;W_lo] rows against the hi and the lo activation plane)")
     return dict(bound="tensor", achieved=ach, peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=ach / peaks["bf16_sustained"],
-                traffic=None, kernel="conv3x3_c64_cm_kernel<bf16x3>", launches_timed=len(durs), avg_ms=avg_ms,
+                traffic=None, kernel=kernel, launches_timed=len(durs), avg_ms=avg_ms,
                 peak_source=peaks["source"] + " bf16_tflops_sustained",
                 upscale_launch_ms_by_kind={k: round(v, 3) for k, v in by_kind.items()},
                 conv1_avg_ms=float(np.mean(durs[0::2])), conv2_avg_ms=float(np.mean(durs[1::2])),
-                issued=dict(tflops=4.0 * ach, frac=4.0 * ach / peaks["bf16_sustained"],
-                            note="bf16 MMA FLOPs the kernel actually issues (4 products per fp32-grade product; 3 is the "
-                                 "minimum for bf16 hi/lo operands, the 4th comes with the 128-row MMA granularity): the tensor "
-                                 "pipe is saturated, `frac` above is bounded at 1/4 by the formulation"),
-                note="algorithmic FLOPs (2*MAC of the fp32-grade conv); the channel-major bf16x3 kernel issues 4x that in "
-                     "bf16 MMAs ([W_hi;W_lo] rows against the hi and the lo activation plane)")
+                issued=dict(tflops=issue * ach, frac=issue * ach / peaks["bf16_sustained"], factor=issue,
+                            note="tensor-pipe slots the kernel occupies, expressed as bf16-rate FLOPs: `frac` above is bounded "
+                                 f"at 1/{issue:g} by the formulation (fp32-grade result from 16/8-bit operands)"),
+                note=note)
 
 
 def _time_ms(fn, reps=5, warm=3):
@@ -325,7 +333,8 @@ def stage_rooflines(stage, peaks, sam_variant):
         t = 48600.0 / ms
         out["upscale"] = dict(bound="tensor", algorithmic_gflop=48600.0, ms=round(ms, 3), achieved_tflops=round(t, 1),
                               frac=round(t / peaks["bf16_sustained"], 4),
-                              note="fp32-grade via bf16 hi/lo planes: 4x the algorithmic FLOPs are issued as bf16 MMAs")
+                              note="fp32-grade result from 16/8-bit operand planes: 3x (fp16 + e5m2 correction) or 4x (bf16x3) the "
+                                   "algorithmic FLOPs occupy the tensor pipe, see roofline.issued")
     ms = stage.get("clean_grouped") or stage.get("clean")
     if ms:
         g = 13.0e-3 / (ms * 1e-3)               # GB/s
@@ -419,12 +428,14 @@ def run_ours(args, coord):
         return
     extras = measure_side_stages(devp[0], dev, peaks) if coord.world == 1 else {}     # N = 1 only, like cpu_baseline
     roof = measure_dominant_kernel(pipe, devp[0], peaks)
-    prof = os.path.join(ROOT, "profiles", "r01_halo_cm_ncu.json")
-    if not os.path.exists(prof):
-        prof = os.path.join(ROOT, "profiles", "r01_halo_conv_ncu.json")
+    # dram__bytes_read + dram__bytes_write per launch come from the committed `ncu --set full` capture of the same kernel
+    # (profiles/): ncu cannot run inside the timed bench, so the figure is labelled with its source
+    fp16c = "fp16c" in roof["kernel"]
+    prof = os.path.join(ROOT, "profiles", "r02_fp16c_ncu.json" if fp16c else "r01_halo_cm_ncu.json")
     if os.path.exists(prof):
         try:
             roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            roof["traffic_source"] = "from_profile:" + os.path.relpath(prof, ROOT)
         except Exception:
             pass
     gbase = None
@@ -436,7 +447,10 @@ def run_ours(args, coord):
     base = cpu_baseline() if coord.world == 1 and not args.no_cpu_baseline else None
     line = dict(metric=METRIC, value=value, unit="pages/s", n_gpus=coord.world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="bf16x3 (fp32-grade: hi/lo bf16 operand planes on tcgen05, fp32 accumulate); integer u8/bit ops for cleaning",
+                dtype=("fp16+e5m2 (fp32-grade: fp16 operand planes + an e5m2 correction product on tcgen05, fp32 accumulate; bf16 hi/lo "
+                       "planes = bf16x3 outside the RCAN body); integer u8/bit ops for cleaning"
+                       if "fp16c" in roof["kernel"] else
+                       "bf16x3 (fp32-grade: hi/lo bf16 operand planes on tcgen05, fp32 accumulate); integer u8/bit ops for cleaning"),
                 data="synthetic",
                 config=dict(workload=(WORKLOAD if args.batch == 64 else WORKLOAD.replace("Batch 64", f"Batch {args.batch}")
                                       ).replace("SAM2.1-tiny", f"SAM2.1-{sam_variant}"),

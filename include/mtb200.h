@@ -61,6 +61,20 @@ typedef struct mtb_conv_plan mtb_conv_plan;
  * tile_sums: fp32 [mtb_conv_plan_num_sum_rows()][Cout] or NULL (partial channel sums of the output). */
 int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, const float* bias, void* out,
                          const void* residual, float* tile_sums, mtb_conv_plan** plan);
+
+/* RCAN body layer (3x3, stride 1, pad 1, 64 -> 64 channels) in the "fp16c" format: one fp16 product plus an e5m2
+ * correction product per tap instead of the four bf16 products of the bf16x3 path (same fp32-grade result within the
+ * 1e-3 bound, 25 % fewer tensor-core cycles, 3 bytes per activation).  Replaces the same spandrel RCAN conv stack
+ * (reference core/image/image_utils.py:369-374, loader core/ml/model_manager.py:640-654).
+ * x / out / residual: byte planes [3][N][H][W][64]: plane 0 = fp16 of channels 0-31, plane 1 = fp16 of channels 32-63,
+ * plane 2 = e5m2 of (v - fp16(v)) * 2^lo_shift for channels 0-63.  w_packed: [2880][64] bytes in the kernel's
+ * shared-memory order (mangatranslator_b200.planes.conv_weight_to_fp16c).  act: 0 none, 1 relu.  The plan is run,
+ * configured (channel scale, border sums, sum rows) and destroyed with the mtb_conv_plan_* functions. */
+int mtb_rcan_conv_plan_create(int N, int H, int W, const void* x, const void* w_packed, const float* bias, void* out,
+                              const void* residual, float* tile_sums, int act, int lo_shift, mtb_conv_plan** plan_out);
+/* bf16 hi/lo planes [2][npix][64] <-> fp16c planes [3][npix][64 B] at the boundary of the RCAN body */
+int mtb_planes_bf16x2_to_fp16c(const void* in, long long npix, void* out, int lo_shift, void* stream);
+int mtb_planes_fp16c_to_bf16x2(const void* in, long long npix, void* out, int lo_shift, void* stream);
 int mtb_conv_plan_run(mtb_conv_plan* plan, void* stream);
 /* optional per-output-channel factor applied to (acc + bias) before activation / residual: out = act((acc+b)*s) + res.
  * `scale` ([Cout] floats, device) is read at run time, so a kernel earlier in the stream may produce it. */
@@ -166,6 +180,17 @@ int mtb_scale_residual(const void* t, const void* x, const float* scale, void* y
 int mtb_rcan_gate(const float* sums, int parts, const float* border_sums /* [parts][4][64] or NULL: read u's lines */,
                   const void* u, int planes, int H, int W, const float* conv_w, const float* conv_b, const float* w1,
                   const float* b1, const float* w2, const float* b2, int R, float* scale_out, void* stream);
+/* same for an RCAB whose body runs in the fp16c format (mtb_rcan_conv_plan_create): u = conv1's byte planes
+ * [3][H][W][64], lo_shift as given to the plans; the border sums always come from conv1's epilogue. */
+int mtb_rcan_gate_fp16c(const float* sums, int parts, const float* border_sums /* [parts][4][64] */,
+                        long long* fixed_sums /* or: [5][64] from mtb_conv_plan_set_fixed_sums, consumed and zeroed */,
+                        const void* u, int lo_shift, int H, int W, const float* conv_w, const float* conv_b,
+                        const float* w1, const float* b1, const float* w2, const float* b2, int R, float* scale_out,
+                        void* stream);
+/* fp16c plans: accumulate the channel sums of the output (whole image, row 0, row Ho-1, column 0, column Wo-1) into
+ * `fixed` ([5][64] int64, units of 2^-20, zero before the launch) with integer atomics instead of writing per-CTA
+ * rows: the order of the additions cannot change the result, and the gate reads 2.5 KB instead of ~750 KB. */
+int mtb_conv_plan_set_fixed_sums(mtb_conv_plan* plan, long long* fixed);
 int mtb_f32_to_u8(const float* in, long long npix, int cpad, const float* add3 /* host */, float mul, uint8_t* out,
                   float* out_f /* optional float copy [npix][3] */, void* stream);
 /* "_PU" RCAN variants (ModelManager.load_upscale_lite, core/ml/model_manager.py:660-700 -> spandrel RCAN with

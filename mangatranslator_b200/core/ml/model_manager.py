@@ -159,7 +159,9 @@ class ModelManager:
                 lite = mt == ModelType.UPSCALE_LITE        # "_PU": pixel-unshuffle x2 in front of a shallower body
                 sd = W.rcan_state_dict(self.synthetic_seed, n_resblocks=6 if lite else 20, n_resgroups=4 if lite else 10,
                                        unshuffle=2 if lite else 1)
-            self.models[mt] = RcanB200(sd, dev, precision=self.precision)
+            # fp32-grade mode: the RCAN body runs in its own format (fp16 + e5m2 correction, MTB200_RCAN_PRECISION=bf16x3
+            # selects the bf16 hi/lo A/B partner); MTB200_PRECISION=bf16 is the plain-bf16 (non-parity) network
+            self.models[mt] = RcanB200(sd, dev, precision=None if self.precision == "bf16x3" else self.precision)
             return self.models[mt]
 
     def load_upscale(self, verbose: bool = False):

@@ -75,6 +75,11 @@ int launch_conv_halo_cm(const CUtensorMap& tmX, const CUtensorMap& tmW, const CU
                         cudaStream_t stream);
 int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int nsplit,
                      cudaStream_t stream);
+void conv_halo_fp16c_tile(int* tw, int* th);
+int launch_conv_halo_fp16c(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmR, const ConvParams& p,
+                           cudaStream_t stream);
+int launch_bf16x2_to_fp16c(const void* in, long long npix, void* out, float lo_scale, cudaStream_t stream);
+int launch_fp16c_to_bf16x2(const void* in, long long npix, void* out, float lo_inv, cudaStream_t stream);
 }  // namespace mtb
 
 struct mtb_conv_plan {
@@ -279,10 +284,103 @@ int mtb_conv_plan_create(const mtb_conv_desc* d, const void* x, const void* w, c
   return 0;
 }
 
+/* RCAN body layer (3x3, stride 1, pad 1, 64 -> 64) in the fp16 + e5m2-correction format (conv_halo_fp16c.cu). */
+int mtb_rcan_conv_plan_create(int N, int H, int W, const void* x, const void* w_packed, const float* bias, void* out,
+                              const void* residual, float* tile_sums, int act, int lo_shift, mtb_conv_plan** plan_out) {
+  MTB_REQUIRE(x && w_packed && out && plan_out, "mtb_rcan_conv_plan_create: null argument");
+  MTB_REQUIRE(N > 0 && H > 0 && W > 0, "mtb_rcan_conv_plan_create: empty tensor");
+  MTB_REQUIRE(lo_shift >= -14 && lo_shift <= 14, "mtb_rcan_conv_plan_create: lo_shift out of range");
+  MTB_REQUIRE(static_cast<long long>(N) * 3 < 65536, "mtb_rcan_conv_plan_create: batch too large for the plane index");
+  mtb_conv_plan* pl = new (std::nothrow) mtb_conv_plan();
+  MTB_REQUIRE(pl != nullptr, "conv: out of host memory");
+  ConvParams& p = pl->p;
+  memset(&p, 0, sizeof(p));
+  p.N = N;
+  p.H = p.Ho = H;
+  p.W = p.Wo = W;
+  p.KH = p.KW = 3;
+  p.pad = 1;
+  p.stride = 1;
+  p.cin_chunks = 1;
+  p.Cout = 64;
+  p.BN = 64;
+  p.n_tiles_n = 1;
+  conv_halo_fp16c_tile(&p.TW, &p.TH);
+  p.tiles_x = (W + p.TW - 1) / p.TW;
+  p.tiles_y = (H + p.TH - 1) / p.TH;
+  p.planes_out = 3;
+  p.act = act;
+  p.out_cstride = p.res_cstride = 64;
+  p.out_plane_stride = p.res_plane_stride = static_cast<long long>(N) * H * W * 64;     /* bytes */
+  p.res_planes = residual ? 3 : 0;
+  p.bias = bias;
+  p.out = static_cast<uint16_t*>(out);
+  p.residual = static_cast<const uint16_t*>(residual);
+  p.tile_sums = tile_sums;
+  p.sums_per_cta = (N == 1) ? 1 : 0;
+  p.lo_scale = ldexpf(1.0f, lo_shift);
+  p.lo_inv_scale = ldexpf(1.0f, -lo_shift);
+  pl->halo = 3;
+  pl->nsplit = 1;
+  {
+    // activations: byte planes [3*N][H][W][64 B] (fp16 channels 0-31 | fp16 channels 32-63 | e5m2 channels 0-63)
+    const uint64_t dims[4] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(N) * 3};
+    const uint64_t strides[3] = {64, static_cast<uint64_t>(W) * 64, static_cast<uint64_t>(H) * W * 64};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(p.TW + 2), static_cast<uint32_t>(p.TH + 2), 1};
+    if (encode_tmap(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, x, dims, strides, box, nullptr,
+                    CU_TENSOR_MAP_SWIZZLE_64B) != 0) {
+      delete pl;
+      return -3;
+    }
+  }
+  {
+    // weights: [2880 rows][64 B], already in shared-memory order (planes.conv_weight_to_fp16c)
+    const uint64_t dims[2] = {64, 2880};
+    const uint64_t strides[1] = {64};
+    const uint32_t box[2] = {64, 64};
+    if (encode_tmap(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, w_packed, dims, strides, box, nullptr,
+                    CU_TENSOR_MAP_SWIZZLE_64B) != 0) {
+      delete pl;
+      return -3;
+    }
+  }
+  memset(&pl->tmO, 0, sizeof(pl->tmO));
+  if (residual) {
+    // the residual tile (no halo), for the producer's L2 prefetch
+    const uint64_t dims[4] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(N) * 3};
+    const uint64_t strides[3] = {64, static_cast<uint64_t>(W) * 64, static_cast<uint64_t>(H) * W * 64};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(p.TH), 1};
+    if (encode_tmap(&pl->tmO, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, residual, dims, strides, box, nullptr,
+                    CU_TENSOR_MAP_SWIZZLE_NONE) != 0) {
+      delete pl;
+      return -3;
+    }
+  } else {
+    pl->tmO = pl->tmA;      /* never dereferenced without a residual; keeps the kernel parameter a valid descriptor */
+  }
+  *plan_out = pl;
+  return 0;
+}
+
+int mtb_planes_bf16x2_to_fp16c(const void* in, long long npix, void* out, int lo_shift, void* stream) {
+  MTB_REQUIRE(in && out && npix >= 0, "mtb_planes_bf16x2_to_fp16c: bad arguments");
+  const int rc = launch_bf16x2_to_fp16c(in, npix, out, ldexpf(1.0f, lo_shift), static_cast<cudaStream_t>(stream));
+  if (rc == 0) mtb::g_launches.fetch_add(1);
+  return rc;
+}
+
+int mtb_planes_fp16c_to_bf16x2(const void* in, long long npix, void* out, int lo_shift, void* stream) {
+  MTB_REQUIRE(in && out && npix >= 0, "mtb_planes_fp16c_to_bf16x2: bad arguments");
+  const int rc = launch_fp16c_to_bf16x2(in, npix, out, ldexpf(1.0f, -lo_shift), static_cast<cudaStream_t>(stream));
+  if (rc == 0) mtb::g_launches.fetch_add(1);
+  return rc;
+}
+
 int mtb_conv_plan_run(mtb_conv_plan* plan, void* stream) {
   MTB_REQUIRE(plan != nullptr, "mtb_conv_plan_run: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = plan->halo == 2   ? launch_conv_halo_cm(plan->tmA, plan->tmB, plan->tmO, plan->p, st)
+  int rc = plan->halo == 3   ? launch_conv_halo_fp16c(plan->tmA, plan->tmB, plan->tmO, plan->p, st)
+           : plan->halo == 2 ? launch_conv_halo_cm(plan->tmA, plan->tmB, plan->tmO, plan->p, st)
            : plan->halo == 1 ? launch_conv_halo(plan->tmA, plan->tmB, plan->p, plan->nsplit, st)
                              : launch_conv_gemm(plan->tmA, plan->tmB, plan->p, plan->nsplit, st);
   if (rc == 0) mtb::g_launches.fetch_add(1);
@@ -298,9 +396,17 @@ int mtb_conv_plan_set_channel_scale(mtb_conv_plan* plan, const float* scale) {
 
 int mtb_conv_plan_set_border_sums(mtb_conv_plan* plan, float* border) {
   MTB_REQUIRE(plan != nullptr, "mtb_conv_plan_set_border_sums: null plan");
-  MTB_REQUIRE(plan->halo == 2 && plan->p.sums_per_cta && plan->p.tile_sums != nullptr,
+  MTB_REQUIRE((plan->halo == 2 || plan->halo == 3) && plan->p.sums_per_cta && plan->p.tile_sums != nullptr,
               "conv: border sums need the channel-major halo kernel with per-CTA tile sums (one image, bf16x3)");
   plan->p.border_sums = border;
+  return 0;
+}
+
+int mtb_conv_plan_set_fixed_sums(mtb_conv_plan* plan, long long* fixed) {
+  MTB_REQUIRE(plan != nullptr, "mtb_conv_plan_set_fixed_sums: null plan");
+  MTB_REQUIRE(plan->halo == 3 && plan->p.sums_per_cta && plan->p.tile_sums != nullptr && plan->p.border_sums != nullptr,
+              "conv: fixed-point sums need an fp16c plan (one image) with tile sums and border sums set");
+  plan->p.sums_fixed = fixed;
   return 0;
 }
 

@@ -57,6 +57,12 @@ struct ConvParams {
   int debug;                   // perf experiments only (halo kernel): 1 skip stores, 2 skip MMA issue, 4 skip TMA loads
   long long* dbg_out;          // perf experiments only: per-CTA counters (halo kernels, debug bit 16)
   int pixel_shuffle;           // 1: Cout = 4 blocks of Cout/4 channels, block (dy*2+dx) is stored at pixel (2y+dy, 2x+dx)
+  long long* sums_fixed;       // fp16c kernel, optional: [5][64] fixed-point (2^-20) accumulators of the output's channel sums
+                               //   over the image, row 0, row Ho-1, column 0, column Wo-1, added with integer atomics
+                               //   (order-independent, so bit-reproducible); replaces tile_sums / border_sums rows
+  int pf_x, pf_res;            // fp16c kernel: L2 prefetch distances (tiles ahead) of the activation / residual tiles
+  float lo_scale, lo_inv_scale;  // fp16c kernel (conv_halo_fp16c.cu): the e5m2 residual plane holds (v - fp16(v)) * lo_scale;
+                               //   there `out` / `residual` are byte tensors [3][N][H][W][64 B] and the plane strides are bytes
 };
 
 int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int nsplit,

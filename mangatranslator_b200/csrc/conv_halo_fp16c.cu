@@ -1,0 +1,863 @@
+// 3x3 / stride 1 / pad 1 / 64 -> 64 channel convolution, fp32-grade, as ONE fp16 product + an e5m2 correction product —
+// the RCAN body layer (reference: spandrel RCAN behind core/image/image_utils.py:369-374; ~400 launches per page).
+//
+// conv_halo_cm.cu (bf16x3) issues two M=128 x N=240 x K=16 kind::f16 MMAs per (tap, 16 input channels): [W_hi;W_lo] x X_hi
+// and [W_hi;W_lo] x X_lo, i.e. four bf16 products where three are needed — the tensor pipe is saturated (92 % active) at a
+// quarter of its rate in useful work.  Here a value v is carried as
+//        X16 = fp16_rn(v)                       2 B   (11 significant bits)
+//        X8  = e5m2_rn((v - X16) * 2^s)         1 B   (the rounding residual, ~2^-12 |v|, two more bits)
+// and a weight as W16_hi = fp16(w), W16_lo = fp16(w - W16_hi), W8 = e5m2(w * 2^-s).  Per (tap, 16 input channels):
+//        D[128 x 240] += [W16_hi ; W16_lo][128 x 16] x X16[240 x 16]          kind::f16     120 clk
+//   and per (tap, 32 input channels):
+//        D[ 64 x 240] += W8[64 x 32] x X8[240 x 32]                          kind::f8f6f4  120 clk  (M = 64 rows land in
+//                                                                             TMEM lanes 32q .. 32q+15, measured)
+// into the same fp32 TMEM accumulator: 36 + 18 = 54 MMA slots per tile instead of 72 (-25 % tensor-pipe cycles) and
+// 3 bytes per activation instead of 4.  Measured first on the device (profiles/r02_fp8_probe.json): kinds mix on one
+// accumulator, an M = 64 instruction writes row i to lane 32*(i/16) + i%16, tap-shifted descriptors work on
+// 64-byte-swizzled tiles for both kinds, and every one of these MMAs costs 120 clk.  Accuracy, float64 emulation of the
+// full 10x20 network with only these operand roundings applied (tools/cpu_operand_format_accuracy.py,
+// profiles/r01_cpu_operand_format_accuracy.json): 1.7e-4 max abs against the 1e-3 parity bound (bf16x3: 1.8e-5).
+//
+// Shared memory (the constraint that shaped the layout): resident weights 9 taps x (2 x 8 KB fp16 [128 rows x 32 ch] +
+// 4 KB e5m2 [64 rows x 64 ch]) = 180 KB; the activation tile arrives as THREE 64-byte-row planes of the 10 x 32 pixel
+// halo — fp16 channels 0-31, fp16 channels 32-63, e5m2 channels 0-63 — 20 KB each, all 64B-swizzled with the same
+// geometry, through a ring of two slots (220 KB + 1 KB alignment of 227 KB).  A slot feeds 18 MMAs (2160 clk).
+// As in conv_halo_cm.cu weights are the M operand (rows interleaved in groups of 16 so a channel's hi and lo partial
+// sums sit in one warp's TMEM lane quarter), pixels the N operand (8 x 30 output tile), tap (ky,kx) = descriptor start +
+// (ky*10+kx)*64 B with SBO = 640 B, persistent grid, 1 TMA warp + 1 MMA warp + 16 epilogue warps.
+// Epilogue: with 25 % less MMA time per tile the 330-instruction chunk loop of conv_halo_cm.cu (twelve shuffles with
+// their selects to fold hi + lo rows and pair channels, per-pixel bounds branches) became the limiter (measured: the MMA
+// warp waited 35-42 % of the time for accumulator stages).  Here each warp reads the 16 hi rows and the 16 lo rows of its
+// lane quarter with two tcgen05.ld.16x256b (the m16n8 fragment: both loads put a channel's partial sums into the same
+// thread, so the fold is an FADD), the weight rows are permuted so that a thread's rows r and r + 8 are adjacent
+// channels (4-byte fp16 pair stores), and tiles that lie inside the image and touch no border line take a path without
+// predicates: ~100 instructions per chunk.
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <stdlib.h>
+
+#include "conv_gemm.cuh"
+#include "epilogue.cuh"
+
+namespace mtb {
+
+namespace {
+
+constexpr int kThreads = kConvThreads;
+constexpr int kTW = 8, kTH = 30;                    // output tile (pixels)
+constexpr int kHW = kTW + 2, kHH = kTH + 2;         // halo tile
+constexpr int kNPix = kTW * kTH;                    // N of the MMA (240)
+constexpr int kSlots = 2;
+constexpr int kSlotBytes = kHW * kHH * 64;          // 20480: one 64-byte-row plane of the halo tile
+constexpr int kW16TapBytes = 2 * 128 * 64;          // per tap: two channel halves x 128 interleaved rows x 64 B
+constexpr int kW16Bytes = 9 * kW16TapBytes;         // 147456
+constexpr int kW8TapBytes = 64 * 64;                // per tap: 64 rows x 64 B
+constexpr int kWBytes = kW16Bytes + 9 * kW8TapBytes;   // 184320
+constexpr int kAccCols = 256;                       // TMEM columns per accumulator stage
+constexpr int kChunks = kNPix / 16;                 // column chunks of 16 pixels (= 2 tile rows)
+
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t w) { return __half22float2(*reinterpret_cast<__half2*>(&w)); }
+__device__ __forceinline__ uint16_t pack_e5m2x2(float a, float b) {
+  return static_cast<uint16_t>(__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2));
+}
+__device__ __forceinline__ float2 unpack_e5m2x2(uint16_t w) {
+  const __half2_raw r = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(w), __NV_E5M2);
+  return __half22float2(*reinterpret_cast<const __half2*>(&r));
+}
+
+
+// 16 TMEM lanes x 16 columns as the m16n8 accumulator fragment (measured, profiles/r02_ldtm_layout.json): thread T,
+// register 4g + 2h + e  <-  lane (base + T/4 + 8h), column (col + 8g + 2(T%4) + e).  Reading the 16 hi rows and the 16 lo
+// rows of a lane quarter with two of these puts both partial sums of a channel into the SAME thread: the hi + lo fold is
+// eight FADDs instead of twelve shuffles with their selects.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+constexpr float kFixedScale = 1048576.0f;   // 2^20: fixed-point unit of ConvParams::sums_fixed
+
+__device__ __forceinline__ void add_fixed(long long* dst, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst), static_cast<unsigned long long>(__float2ll_rn(v * kFixedScale)));
+}
+
+struct EpiLane {            // per-thread constants of the fragment epilogue
+  int q, wj, c0;            // lane quarter, chunk phase, first of the thread's two adjacent channels
+  int jx;                   // first of the thread's two adjacent tile columns (2 * (T % 4))
+  float s0, s1, bs0, bs1;   // channel scale and bias * scale of the two channels
+  long long o16, o8;        // byte offsets of the thread's channel pair inside a pixel's fp16 / e5m2 rows (plane included)
+  long long r16, r8;        // same inside the residual tensor
+};
+
+// One output tile drained by one epilogue warp (its chunks ci = wj, wj + 4, ...).  FAST: the tile lies fully inside the
+// image and contributes to no border line, so every predicate below folds away.
+template <int ACT, bool HAS_RES, bool SUMS, bool FAST, int RA = 1>
+__device__ __forceinline__ void epi_tile_frag(const ConvParams& p, const EpiLane& L, uint32_t taddr_hi, int n, int ty0,
+                                              int tx0, uint64_t* tempty, int lane, float& sum0, float& sum1,
+                                              float (&bsum)[8]) {
+  uint8_t* const out_b = reinterpret_cast<uint8_t*>(p.out);
+  const uint8_t* const res_b = reinterpret_cast<const uint8_t*>(p.residual);
+  const float lo_scale = p.lo_scale, lo_inv = p.lo_inv_scale;
+  const long long rowb = static_cast<long long>(p.Wo) * 64;           // bytes per image row of a plane
+  const long long pix0 = ((static_cast<long long>(n) * p.Ho + ty0) * p.Wo + tx0 + L.jx) * 64;
+  const bool want_border = SUMS && !FAST && p.sums_per_cta && p.border_sums != nullptr;
+  const int ox0 = tx0 + L.jx;
+  // residual words in flight: chunk k in (rh, rl), chunk k + 1 in (rh1, rl1) when RA == 2
+  uint32_t rh[4] = {0u, 0u, 0u, 0u}, rh1[4] = {0u, 0u, 0u, 0u};
+  uint16_t rl[4] = {0, 0, 0, 0}, rl1[4] = {0, 0, 0, 0};
+  auto load_res = [&](int ci, uint32_t (&h)[4], uint16_t (&l)[4]) {
+    const uint8_t* rp = res_b + pix0 + (2ll * ci) * rowb;
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = FAST || (ty0 + 2 * ci + g < p.Ho && ox0 + e < p.Wo);
+        if (ok) {
+          h[2 * g + e] = *reinterpret_cast<const uint32_t*>(rp + g * rowb + e * 64 + L.r16);
+          l[2 * g + e] = *reinterpret_cast<const uint16_t*>(rp + g * rowb + e * 64 + L.r8);
+        }
+      }
+  };
+  if (HAS_RES) {
+    load_res(L.wj, rh, rl);
+    if (RA == 2 && L.wj + 4 < kChunks) load_res(L.wj + 4, rh1, rl1);
+  }
+  float t0 = 0.0f, t1 = 0.0f;
+#pragma unroll 1
+  for (int ci = L.wj; ci < kChunks; ci += 4) {
+    uint32_t ah[8], al[8];
+    tmem_ld_16x256b_x2(taddr_hi + ci * 16, ah);
+    tmem_ld_16x256b_x2(taddr_hi + (16u << 16) + ci * 16, al);
+    uint32_t nh[4] = {0u, 0u, 0u, 0u};
+    uint16_t nl[4] = {0, 0, 0, 0};
+    if (HAS_RES && ci + 4 * RA < kChunks) load_res(ci + 4 * RA, nh, nl);
+    tmem_ld_wait();
+    if (ci + 4 >= kChunks) {
+      // last TMEM read of this warp for the tile: hand the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+    uint8_t* op = out_b + pix0 + (2ll * ci) * rowb;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int oy = ty0 + 2 * ci + g;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        // registers 4g + e (channel c0) and 4g + 2 + e (channel c0 + 1) of the pixel (oy, ox0 + e)
+        float a = epi_act<ACT>(fmaf(__uint_as_float(ah[4 * g + e]) + __uint_as_float(al[4 * g + e]), L.s0, L.bs0), p.act);
+        float b = epi_act<ACT>(fmaf(__uint_as_float(ah[4 * g + 2 + e]) + __uint_as_float(al[4 * g + 2 + e]), L.s1, L.bs1), p.act);
+        if (HAS_RES) {
+          const float2 r0 = unpack_f16x2(rh[2 * g + e]), r1 = unpack_e5m2x2(rl[2 * g + e]);
+          a += r0.x + r1.x * lo_inv;
+          b += r0.y + r1.y * lo_inv;
+        }
+        const bool ok = FAST || (oy < p.Ho && ox0 + e < p.Wo);
+        if (ok) {
+          if (SUMS) {
+            t0 += a;
+            t1 += b;
+            if (want_border) {
+              const int ox = ox0 + e;
+              if (oy == 0) { bsum[0] += a; bsum[1] += b; }
+              if (oy == p.Ho - 1) { bsum[2] += a; bsum[3] += b; }
+              if (ox == 0) { bsum[4] += a; bsum[5] += b; }
+              if (ox == p.Wo - 1) { bsum[6] += a; bsum[7] += b; }
+            }
+          }
+          const uint32_t h16 = pack_f16x2(a, b);
+          const float2 hf = unpack_f16x2(h16);
+          *reinterpret_cast<uint32_t*>(op + g * rowb + e * 64 + L.o16) = h16;
+          *reinterpret_cast<uint16_t*>(op + g * rowb + e * 64 + L.o8) = pack_e5m2x2((a - hf.x) * lo_scale, (b - hf.y) * lo_scale);
+        }
+      }
+    }
+    if (HAS_RES) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        rh[k] = RA == 2 ? rh1[k] : nh[k];
+        rl[k] = RA == 2 ? rl1[k] : nl[k];
+        rh1[k] = nh[k];
+        rl1[k] = nl[k];
+      }
+    }
+  }
+  if (SUMS) {
+    if (p.sums_per_cta) {
+      sum0 += t0;
+      sum1 += t1;
+    } else {
+      // the four lanes of a row group hold the same channel pair (different pixels)
+      t0 += __shfl_xor_sync(0xffffffffu, t0, 1);
+      t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+      t0 += __shfl_xor_sync(0xffffffffu, t0, 2);
+      t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+      if ((lane & 3) == 0) {
+        const int tile = (n * p.tiles_y + ty0 / kTH) * p.tiles_x + tx0 / kTW;
+        float* row = p.tile_sums + (static_cast<long long>(tile) * 4 + L.wj) * 64 + L.c0;
+        row[0] = t0;
+        row[1] = t1;
+      }
+    }
+  }
+}
+
+
+// ---- exchange epilogue (EPI == 2) ---------------------------------------------------------------------------------
+// The pair epilogue above stores 4 bytes (2 channels) per pixel and thread: every store / residual load instruction of a
+// warp touches four 128-byte lines, and ncu showed the LSU data pipe at 80 % of its wavefront rate in the residual layer
+// (50 % without residual) — the epilogue, not the tensor pipe, set the pace.  Here lanes T and T^4 (accumulator row
+// groups r and r^1 = channel pairs 2r.. and 2(r^1)..) swap one pixel column each, so a thread ends with FOUR adjacent
+// channels of ONE pixel: 8-byte fp16 and 4-byte e5m2 accesses, half the instructions and half the wavefronts, for four
+// shuffles per chunk.
+struct EpiLaneX {
+  int q, wj;
+  bool odd;                 // r & 1: keeps tile column 2j + 1 (else 2j)
+  int px;                   // the thread's tile column
+  int c_own, c_recv;        // first channel of the pair it computed itself / of the pair it receives
+  float s[4], bs[4];        // channel scale and bias * scale per slot [own0, own1, recv0, recv1]
+  long long o16, o8;        // byte offsets of the thread's four channels inside a pixel's fp16 / e5m2 rows (plane included)
+  long long r16, r8;
+};
+
+template <int ACT, bool HAS_RES, bool SUMS, bool FAST>
+__device__ __forceinline__ void epi_tile_x4(const ConvParams& p, const EpiLaneX& L, uint32_t taddr_hi, int n, int ty0,
+                                            int tx0, uint64_t* tempty, int lane, float (&sum)[4], float (&bsum)[16]) {
+  uint8_t* const out_b = reinterpret_cast<uint8_t*>(p.out);
+  const uint8_t* const res_b = reinterpret_cast<const uint8_t*>(p.residual);
+  const float lo_scale = p.lo_scale, lo_inv = p.lo_inv_scale;
+  const long long rowb = static_cast<long long>(p.Wo) * 64;           // bytes per image row of a plane
+  const int ox = tx0 + L.px;
+  const long long pix0 = ((static_cast<long long>(n) * p.Ho + ty0) * p.Wo + ox) * 64;
+  const bool want_border = SUMS && !FAST && p.sums_per_cta && p.border_sums != nullptr;
+  const bool col_ok = FAST || ox < p.Wo;
+  const uint32_t sel16 = L.odd ? 0x1032u : 0x3210u;   // byte_perm selector: own pair's 16 bits in the low / high half
+  uint2 rh[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
+  uint32_t rl[2] = {0u, 0u};
+  auto load_res = [&](int ci, uint2 (&h)[2], uint32_t (&l)[2]) {
+    const uint8_t* rp = res_b + pix0 + (2ll * ci) * rowb;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const bool ok = FAST || (col_ok && ty0 + 2 * ci + g < p.Ho);
+      if (ok) {
+        h[g] = *reinterpret_cast<const uint2*>(rp + g * rowb + L.r16);
+        l[g] = *reinterpret_cast<const uint32_t*>(rp + g * rowb + L.r8);
+      }
+    }
+  };
+  if (HAS_RES) load_res(L.wj, rh, rl);
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int ci = L.wj; ci < kChunks; ci += 4) {
+    uint32_t ah[8], al[8];
+    tmem_ld_16x256b_x2(taddr_hi + ci * 16, ah);
+    tmem_ld_16x256b_x2(taddr_hi + (16u << 16) + ci * 16, al);
+    uint2 nh[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
+    uint32_t nl[2] = {0u, 0u};
+    if (HAS_RES && ci + 4 < kChunks) load_res(ci + 4, nh, nl);
+    tmem_ld_wait();
+    if (ci + 4 >= kChunks) {
+      // last TMEM read of this warp for the tile: hand the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+    uint8_t* op = out_b + pix0 + (2ll * ci) * rowb;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      // fold hi + lo rows; registers 4g + 2h + e = channel pair member h, tile column 2j + e
+      float f[2][2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          f[h][e] = __uint_as_float(ah[4 * g + 2 * h + e]) + __uint_as_float(al[4 * g + 2 * h + e]);
+      float v[4];                                   // [own0, own1, recv0, recv1] of the column this thread keeps
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        v[h] = L.odd ? f[h][1] : f[h][0];
+        v[2 + h] = __shfl_xor_sync(0xffffffffu, L.odd ? f[h][0] : f[h][1], 4);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = epi_act<ACT>(fmaf(v[k], L.s[k], L.bs[k]), p.act);
+      if (HAS_RES) {
+        // memory order is channel order: the own pair is the low word for even row groups, the high word for odd ones
+        const float2 ro = unpack_f16x2(L.odd ? rh[g].y : rh[g].x), rr = unpack_f16x2(L.odd ? rh[g].x : rh[g].y);
+        const uint32_t l8 = __byte_perm(rl[g], 0u, sel16);            // own pair in the low half
+        const float2 lo_o = unpack_e5m2x2(static_cast<uint16_t>(l8 & 0xFFFFu)), lo_r = unpack_e5m2x2(static_cast<uint16_t>(l8 >> 16));
+        v[0] += ro.x + lo_o.x * lo_inv;
+        v[1] += ro.y + lo_o.y * lo_inv;
+        v[2] += rr.x + lo_r.x * lo_inv;
+        v[3] += rr.y + lo_r.y * lo_inv;
+      }
+      const int oy = ty0 + 2 * ci + g;
+      const bool ok = FAST || (col_ok && oy < p.Ho);
+      if (ok) {
+        if (SUMS) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) t[k] += v[k];
+          if (want_border) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (oy == 0) bsum[k] += v[k];
+              if (oy == p.Ho - 1) bsum[4 + k] += v[k];
+              if (ox == 0) bsum[8 + k] += v[k];
+              if (ox == p.Wo - 1) bsum[12 + k] += v[k];
+            }
+          }
+        }
+        const uint32_t ho = pack_f16x2(v[0], v[1]), hr = pack_f16x2(v[2], v[3]);
+        const float2 fo = unpack_f16x2(ho), fr = unpack_f16x2(hr);
+        const uint32_t eo = pack_e5m2x2((v[0] - fo.x) * lo_scale, (v[1] - fo.y) * lo_scale);
+        const uint32_t er = pack_e5m2x2((v[2] - fr.x) * lo_scale, (v[3] - fr.y) * lo_scale);
+        *reinterpret_cast<uint2*>(op + g * rowb + L.o16) = L.odd ? make_uint2(hr, ho) : make_uint2(ho, hr);
+        *reinterpret_cast<uint32_t*>(op + g * rowb + L.o8) = __byte_perm(eo | (er << 16), 0u, sel16);
+      }
+    }
+    if (HAS_RES) {
+      rh[0] = nh[0];
+      rh[1] = nh[1];
+      rl[0] = nl[0];
+      rl[1] = nl[1];
+    }
+  }
+  if (SUMS) {
+    if (p.sums_per_cta) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sum[k] += t[k];
+    } else {
+      // lanes that differ only in bits 0-1 (tile column pair) hold the same channels and column parity
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        t[k] += __shfl_xor_sync(0xffffffffu, t[k], 1);
+        t[k] += __shfl_xor_sync(0xffffffffu, t[k], 2);
+      }
+      // own slots of lane T and recv slots of lane T^4 are the same channels: add the two column parities
+      const float a0 = t[0] + __shfl_xor_sync(0xffffffffu, t[2], 4), a1 = t[1] + __shfl_xor_sync(0xffffffffu, t[3], 4);
+      if ((lane & 3) == 0) {
+        const int tile = (n * p.tiles_y + ty0 / kTH) * p.tiles_x + tx0 / kTW;
+        float* row = p.tile_sums + (static_cast<long long>(tile) * 4 + L.wj) * 64 + L.c_own;
+        row[0] = a0;
+        row[1] = a1;
+      }
+    }
+  }
+}
+
+// ACT: activation (-1 = from ConvParams); HAS_RES: a residual in the same three-plane format is added after the
+// activation; DBG: clock64() instrumentation of the barrier waits (perf experiments only, MTB200_HALO_DEBUG)
+// SUMS: channel (and border) sums of the output are wanted; EPI: 2 = exchange epilogue (four channels of one pixel per
+// thread, the default), 1 = pair epilogue (two channels of two pixels; the A/B partner)
+template <int ACT, bool HAS_RES, bool SUMS, bool DBG, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_c64_fp16c_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                         const __grid_constant__ CUtensorMap tmR, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;                         // resident weights (A operand): 9 x W16 tap blocks, then 9 x W8 tap blocks
+  uint8_t* sX = smem + kWBytes;               // ring of halo plane slots (B operand)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sX + kSlots * kSlotBytes);
+  uint64_t* empty_bar = full_bar + kSlots;
+  uint64_t* tfull_bar = empty_bar + kSlots;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint64_t* w_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kEpiWarps);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * kAccCols);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    if (HAS_RES) tma_prefetch_desc(&tmR);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // all 512 TMEM columns are ours: the allocation starts at column 0, and the literal keeps the MMA operands uniform
+  if (*tmem_slot != 0) __trap();
+  constexpr uint32_t tmem_base = 0;
+
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+  const int total_tiles = p.N * tiles_per_img;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: the host packed them in shared-memory order as 45 boxes of 64 rows x 64 B
+      mbar_expect_tx(w_bar, static_cast<uint32_t>(kWBytes));
+      for (int i = 0; i < kWBytes / 4096; ++i) tma_load_2d(sW + i * 4096, &tmW, w_bar, 0, i * 64);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
+        // pull the tile `pf_x` iterations ahead into L2: a slot is free for only one plane's worth of MMAs (~2160 clk), and
+        // (pf_res > 0) the residual tile the epilogue will read `pf_res` iterations from now
+        if (p.pf_x > 0) {
+          const int pt = tile + p.pf_x * gridDim.x;
+          if (pt < total_tiles) {
+            const int pn = pt / tiles_per_img;
+            const int prem = pt - pn * tiles_per_img;
+            const int pty = prem / p.tiles_x, ptx = prem - pty * p.tiles_x;
+            for (int pl = 0; pl < 3; ++pl) tma_prefetch_l2_4d(&tmX, 0, ptx * kTW - 1, pty * kTH - 1, pl * p.N + pn);
+          }
+        }
+        if (HAS_RES && p.pf_res > 0) {
+          const int pt = tile + p.pf_res * gridDim.x;
+          if (pt < total_tiles) {
+            const int pn = pt / tiles_per_img;
+            const int prem = pt - pn * tiles_per_img;
+            const int pty = prem / p.tiles_x, ptx = prem - pty * p.tiles_x;
+            for (int pl = 0; pl < 3; ++pl) tma_prefetch_l2_4d(&tmR, 0, ptx * kTW, pty * kTH, pl * p.N + pn);
+          }
+        }
+        for (int pl = 0; pl < 3; ++pl) {
+          mbar_wait(&empty_bar[slot], phase ^ 1);
+          mbar_expect_tx(&full_bar[slot], kSlotBytes);
+          tma_load_4d(sX + slot * kSlotBytes, &tmX, &full_bar[slot], 0, txi * kTW - 1, tyi * kTH - 1, pl * p.N + n);
+          if (++slot == kSlots) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc16 = make_idesc_f16(128, kNPix);
+    constexpr uint32_t idesc8 = make_idesc_e5m2(64, kNPix);
+    mbar_wait(w_bar, 0);
+    tc_fence_after();
+    // shared-window addresses from 32-bit arithmetic on the (uniform) window offset of the dynamic segment
+    const uint32_t sw = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sx0 = sw + kWBytes;
+    int slot = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    long long dbg_wfull = 0, dbg_wtempty = 0, dbg_tiles = 0;
+    const long long dbg_t0 = DBG ? clock64() : 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const long long ta = DBG ? clock64() : 0;
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      if (DBG) {
+        dbg_wtempty += clock64() - ta;
+        ++dbg_tiles;
+      }
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kAccCols);
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) {
+        const long long tf = DBG ? clock64() : 0;
+        mbar_wait(&full_bar[slot], phase);
+        if (DBG) dbg_wfull += clock64() - tf;
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sx = sx0 + slot * kSlotBytes;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const uint32_t b0 = sx + (ky * kHW + kx) * 64;
+            // planes 0/1: fp16 channels [32 pl, 32 pl + 32) against the [W16_hi;W16_lo] rows of that half (the first
+            // MMA of a tile is one of these: M = 128 overwrites every accumulator lane); plane 2: the e5m2 residuals
+            const uint32_t a0 = pl < 2 ? sw + tap * kW16TapBytes + pl * 8192 : sw + kW16Bytes + tap * kW8TapBytes;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint64_t da = make_sdesc_sw64(a0 + k * 32, 512, 0);
+              const uint64_t db = make_sdesc_sw64(b0 + k * 32, kHW * 64, 0);
+              if (pl < 2) umma_bf16(d_tmem, da, db, idesc16, (pl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              else umma_f8f6f4(d_tmem, da, db, idesc8, 1u);
+            }
+          }
+          umma_commit(&empty_bar[slot]);
+        }
+        __syncwarp();
+        if (++slot == kSlots) {
+          slot = 0;
+          phase ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&tfull_bar[as]);
+      __syncwarp();
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (DBG && p.dbg_out && lane == 0) {
+      p.dbg_out[blockIdx.x * 16 + 4] = dbg_wfull;
+      p.dbg_out[blockIdx.x * 16 + 5] = dbg_wtempty;
+      p.dbg_out[blockIdx.x * 16 + 6] = dbg_tiles;
+      p.dbg_out[blockIdx.x * 16 + 7] = clock64() - dbg_t0;
+    }
+  } else if (EPI == 2) {
+    // 16 epilogue warps, exchange layout (see epi_tile_x4)
+    EpiLaneX L;
+    const int r = lane >> 2;
+    L.q = warp & 3;
+    L.wj = (warp - 2) >> 2;
+    L.odd = (r & 1) != 0;
+    L.px = 2 * (lane & 3) + (r & 1);
+    L.c_own = 16 * L.q + 2 * r;
+    L.c_recv = 16 * L.q + 2 * (r ^ 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = (k < 2 ? L.c_own : L.c_recv) + (k & 1);
+      // the channel scale may be written by the kernel just before this one: plain loads, not the read-only path
+      L.s[k] = p.chan_scale ? p.chan_scale[c] : 1.0f;
+      L.bs[k] = (p.bias ? __ldg(p.bias + c) : 0.0f) * L.s[k];
+    }
+    const int cb = 16 * L.q + 4 * (r >> 1);
+    L.o16 = (L.q >> 1) * p.out_plane_stride + (cb & 31) * 2;
+    L.o8 = 2 * p.out_plane_stride + cb;
+    L.r16 = (L.q >> 1) * p.res_plane_stride + (cb & 31) * 2;
+    L.r8 = 2 * p.res_plane_stride + cb;
+    const bool want_border = SUMS && p.sums_per_cta && p.border_sums != nullptr;
+    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+    float bsum[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) bsum[k] = 0.f;
+    int as = 0;
+    uint32_t aphase = 0;
+    long long dbg_wtfull = 0, dbg_work = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
+      const int ty0 = tyi * kTH, tx0 = txi * kTW;
+      const bool inside = ty0 + kTH <= p.Ho && tx0 + kTW <= p.Wo;
+      const bool touches = ty0 == 0 || tx0 == 0 || ty0 + kTH >= p.Ho || tx0 + kTW >= p.Wo;
+      const bool fast = inside && !(want_border && touches);
+      const long long tw = DBG ? clock64() : 0;
+      mbar_wait(&tfull_bar[as], aphase);
+      const long long tw1 = DBG ? clock64() : 0;
+      if (DBG) dbg_wtfull += tw1 - tw;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(L.q * 32) << 16) + static_cast<uint32_t>(as * kAccCols);
+      if (fast) epi_tile_x4<ACT, HAS_RES, SUMS, true>(p, L, taddr, n, ty0, tx0, &tempty_bar[as], lane, sum, bsum);
+      else epi_tile_x4<ACT, HAS_RES, SUMS, false>(p, L, taddr, n, ty0, tx0, &tempty_bar[as], lane, sum, bsum);
+      if (DBG) dbg_work += clock64() - tw1;
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (DBG && p.dbg_out && lane == 0 && (warp == 2 || warp == 17)) {
+      p.dbg_out[blockIdx.x * 16 + (warp == 2 ? 8 : 10)] = dbg_wtfull;
+      p.dbg_out[blockIdx.x * 16 + (warp == 2 ? 9 : 11)] = dbg_work;
+    }
+    // per-CTA rows: fold the four column pairs (lane bits 0-1), then the two column parities (own slots of lane T and
+    // recv slots of lane T^4 are the same channels)
+    if (want_border) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], 1);
+        bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], 2);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const float a0 = bsum[4 * b] + __shfl_xor_sync(0xffffffffu, bsum[4 * b + 2], 4);
+        const float a1 = bsum[4 * b + 1] + __shfl_xor_sync(0xffffffffu, bsum[4 * b + 3], 4);
+        if ((lane & 3) == 0) {
+          if (p.sums_fixed) {
+            add_fixed(p.sums_fixed + (1 + b) * 64 + L.c_own, a0);
+            add_fixed(p.sums_fixed + (1 + b) * 64 + L.c_own + 1, a1);
+          } else {
+            float* row = p.border_sums + ((static_cast<long long>(blockIdx.x) * 4 + L.wj) * 4 + b) * 64 + L.c_own;
+            row[0] = a0;
+            row[1] = a1;
+          }
+        }
+      }
+    }
+    if (SUMS && p.sums_per_cta && p.tile_sums != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], 1);
+        sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], 2);
+      }
+      const float a0 = sum[0] + __shfl_xor_sync(0xffffffffu, sum[2], 4), a1 = sum[1] + __shfl_xor_sync(0xffffffffu, sum[3], 4);
+      if ((lane & 3) == 0) {
+        if (p.sums_fixed) {
+          add_fixed(p.sums_fixed + L.c_own, a0);
+          add_fixed(p.sums_fixed + L.c_own + 1, a1);
+        } else {
+          float* row = p.tile_sums + (static_cast<long long>(blockIdx.x) * 4 + L.wj) * 64 + L.c_own;
+          row[0] = a0;
+          row[1] = a1;
+        }
+      }
+    }
+  } else {
+    // 16 epilogue warps, fragment layout: q = TMEM lane quarter = channels 16q..16q+15; thread T owns channels
+    // 16q + 2(T/4), +1 and tile columns 2(T%4), +1 of every tile row; wj = which column chunks this warp drains.
+    EpiLane L;
+    L.q = warp & 3;
+    L.wj = (warp - 2) >> 2;
+    L.c0 = 16 * L.q + 2 * (lane >> 2);
+    L.jx = 2 * (lane & 3);
+    // the channel scale may be written by the kernel just before this one: plain loads, not the read-only path
+    L.s0 = p.chan_scale ? p.chan_scale[L.c0] : 1.0f;
+    L.s1 = p.chan_scale ? p.chan_scale[L.c0 + 1] : 1.0f;
+    L.bs0 = (p.bias ? __ldg(p.bias + L.c0) : 0.0f) * L.s0;
+    L.bs1 = (p.bias ? __ldg(p.bias + L.c0 + 1) : 0.0f) * L.s1;
+    L.o16 = (L.q >> 1) * p.out_plane_stride + (L.c0 & 31) * 2;
+    L.o8 = 2 * p.out_plane_stride + L.c0;
+    L.r16 = (L.q >> 1) * p.res_plane_stride + (L.c0 & 31) * 2;
+    L.r8 = 2 * p.res_plane_stride + L.c0;
+    const bool want_border = SUMS && p.sums_per_cta && p.border_sums != nullptr;
+    float sum0 = 0.0f, sum1 = 0.0f;
+    float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // (top, bottom, left, right) x 2 channels
+    int as = 0;
+    uint32_t aphase = 0;
+    long long dbg_wtfull = 0, dbg_work = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
+      const int ty0 = tyi * kTH, tx0 = txi * kTW;
+      const bool inside = ty0 + kTH <= p.Ho && tx0 + kTW <= p.Wo;
+      const bool touches = ty0 == 0 || tx0 == 0 || ty0 + kTH >= p.Ho || tx0 + kTW >= p.Wo;
+      const bool fast = inside && !(want_border && touches);
+      const long long tw = DBG ? clock64() : 0;
+      mbar_wait(&tfull_bar[as], aphase);
+      const long long tw1 = DBG ? clock64() : 0;
+      if (DBG) dbg_wtfull += tw1 - tw;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(L.q * 32) << 16) + static_cast<uint32_t>(as * kAccCols);
+      if (fast) epi_tile_frag<ACT, HAS_RES, SUMS, true>(p, L, taddr, n, ty0, tx0, &tempty_bar[as], lane, sum0, sum1, bsum);
+      else epi_tile_frag<ACT, HAS_RES, SUMS, false>(p, L, taddr, n, ty0, tx0, &tempty_bar[as], lane, sum0, sum1, bsum);
+      if (DBG) dbg_work += clock64() - tw1;
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (DBG && p.dbg_out && lane == 0 && (warp == 2 || warp == 17)) {
+      p.dbg_out[blockIdx.x * 16 + (warp == 2 ? 8 : 10)] = dbg_wtfull;
+      p.dbg_out[blockIdx.x * 16 + (warp == 2 ? 9 : 11)] = dbg_work;
+    }
+    if (want_border) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], 1);
+        bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], 2);
+      }
+      if ((lane & 3) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (p.sums_fixed) {
+            add_fixed(p.sums_fixed + (1 + k) * 64 + L.c0, bsum[2 * k]);
+            add_fixed(p.sums_fixed + (1 + k) * 64 + L.c0 + 1, bsum[2 * k + 1]);
+          } else {
+            float* row = p.border_sums + ((static_cast<long long>(blockIdx.x) * 4 + L.wj) * 4 + k) * 64 + L.c0;
+            row[0] = bsum[2 * k];
+            row[1] = bsum[2 * k + 1];
+          }
+        }
+      }
+    }
+    if (SUMS && p.sums_per_cta && p.tile_sums != nullptr) {
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      if ((lane & 3) == 0) {
+        if (p.sums_fixed) {
+          add_fixed(p.sums_fixed + L.c0, sum0);
+          add_fixed(p.sums_fixed + L.c0 + 1, sum1);
+        } else {
+          float* row = p.tile_sums + (static_cast<long long>(blockIdx.x) * 4 + L.wj) * 64 + L.c0;
+          row[0] = sum0;
+          row[1] = sum1;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * kAccCols);
+}
+
+// ---- format conversions at the body's boundary (head conv output -> body, body output -> upsampler) ----
+// bf16 hi/lo planes [2][npix][64] -> fp16c planes [3][npix][64 B]; one thread per (pixel, 8 channels)
+__global__ void bf16x2_to_fp16c_kernel(const uint16_t* __restrict__ in, long long npix, uint8_t* __restrict__ out,
+                                       float lo_scale) {
+  const long long total = npix * 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i >> 3;
+    const int c0 = static_cast<int>(i & 7) * 8;
+    const uint4 qh = *reinterpret_cast<const uint4*>(in + pix * 64 + c0);
+    const uint4 ql = *reinterpret_cast<const uint4*>(in + npix * 64 + pix * 64 + c0);
+    const uint32_t wh[4] = {qh.x, qh.y, qh.z, qh.w}, wl[4] = {ql.x, ql.y, ql.z, ql.w};
+    uint32_t h16[4];
+    uint16_t l8[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16x2(wh[j]), b = unpack_bf16x2(wl[j]);
+      const float v0 = a.x + b.x, v1 = a.y + b.y;
+      h16[j] = pack_f16x2(v0, v1);
+      const float2 hf = unpack_f16x2(h16[j]);
+      l8[j] = pack_e5m2x2((v0 - hf.x) * lo_scale, (v1 - hf.y) * lo_scale);
+    }
+    uint8_t* p16 = out + (c0 >> 5) * npix * 64 + pix * 64 + (c0 & 31) * 2;
+    *reinterpret_cast<uint4*>(p16) = make_uint4(h16[0], h16[1], h16[2], h16[3]);
+    uint8_t* p8 = out + 2 * npix * 64 + pix * 64 + c0;
+    *reinterpret_cast<uint2*>(p8) = make_uint2(l8[0] | (static_cast<uint32_t>(l8[1]) << 16),
+                                               l8[2] | (static_cast<uint32_t>(l8[3]) << 16));
+  }
+}
+
+__global__ void fp16c_to_bf16x2_kernel(const uint8_t* __restrict__ in, long long npix, uint16_t* __restrict__ out,
+                                       float lo_inv) {
+  const long long total = npix * 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i >> 3;
+    const int c0 = static_cast<int>(i & 7) * 8;
+    const uint4 q16 = *reinterpret_cast<const uint4*>(in + (c0 >> 5) * npix * 64 + pix * 64 + (c0 & 31) * 2);
+    const uint2 q8 = *reinterpret_cast<const uint2*>(in + 2 * npix * 64 + pix * 64 + c0);
+    const uint32_t w16[4] = {q16.x, q16.y, q16.z, q16.w};
+    const uint16_t w8[4] = {static_cast<uint16_t>(q8.x & 0xFFFF), static_cast<uint16_t>(q8.x >> 16),
+                            static_cast<uint16_t>(q8.y & 0xFFFF), static_cast<uint16_t>(q8.y >> 16)};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_f16x2(w16[j]), b = unpack_e5m2x2(w8[j]);
+      const float v0 = a.x + b.x * lo_inv, v1 = a.y + b.y * lo_inv;
+      hi[j] = pack_bf16x2(v0, v1);
+      const float2 hf = unpack_bf16x2(hi[j]);
+      lo[j] = pack_bf16x2(v0 - hf.x, v1 - hf.y);
+    }
+    *reinterpret_cast<uint4*>(out + pix * 64 + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out + npix * 64 + pix * 64 + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+}  // namespace
+
+void conv_halo_fp16c_tile(int* tw, int* th) {
+  *tw = kTW;
+  *th = kTH;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+int launch_conv_halo_fp16c(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmR, const ConvParams& p_in,
+                           cudaStream_t stream) {
+  ConvParams p = p_in;
+  // launch knobs, read per launch so one process can A/B them (tools/sweep_fp16c.py); a captured graph keeps what it saw
+  const int dbg_flags = env_int("MTB200_HALO_DEBUG", 0);
+  const int epi_env = env_int("MTB200_FP16C_EPI", 0);          // 0 = per layer kind (below)
+  const int pf_x = env_int("MTB200_FP16C_PF", 0);
+  const int pf_res = env_int("MTB200_FP16C_RPF", 0);
+  p.debug = dbg_flags;
+  p.pf_x = pf_x;
+  p.pf_res = pf_res;
+  const bool dbg = dbg_flags != 0;
+  if (dbg)
+    if (const char* e = getenv("MTB200_HALO_DEBUG_PTR")) p.dbg_out = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+  MTB_REQUIRE(p.act == ACT_NONE || p.act == ACT_RELU, "fp16c conv: activation %d is not supported (none / relu)", p.act);
+  const size_t smem = 1024 + kWBytes + kSlots * kSlotBytes + 16 * 8 + 16;
+  int dev = 0, sms = 0;
+  MTB_CUDA_OK(cudaGetDevice(&dev));
+  MTB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long total = static_cast<long long>(p.N) * p.tiles_y * p.tiles_x;
+  const int grid = static_cast<int>(total < sms ? total : sms);
+  if (grid <= 0) return 0;
+#define MTB_LAUNCH_F(ACT, RES, SUMS, DBG, EPI)                                                                  \
+  do {                                                                                                          \
+    MTB_CUDA_OK(cudaFuncSetAttribute(conv3x3_c64_fp16c_kernel<ACT, RES, SUMS, DBG, EPI>,                        \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));     \
+    conv3x3_c64_fp16c_kernel<ACT, RES, SUMS, DBG, EPI><<<grid, kThreads, smem, stream>>>(tmX, tmW, tmR, p);     \
+  } while (0)
+#define MTB_PICK_EPI(ACT, RES, SUMS, DBG)                                        \
+  do {                                                                           \
+    if (epi == 1) MTB_LAUNCH_F(ACT, RES, SUMS, DBG, 1);                          \
+    else MTB_LAUNCH_F(ACT, RES, SUMS, DBG, 2);                                   \
+  } while (0)
+#define MTB_PICK_RA(ACT, SUMS, DBG)                                              \
+  do {                                                                           \
+    if (!res) MTB_PICK_EPI(ACT, false, SUMS, DBG);                               \
+    else MTB_PICK_EPI(ACT, true, SUMS, DBG);                                     \
+  } while (0)
+#define MTB_PICK_SUMS(ACT, DBG)                                                  \
+  do {                                                                           \
+    if (sums) MTB_PICK_RA(ACT, true, DBG);                                       \
+    else MTB_PICK_RA(ACT, false, DBG);                                           \
+  } while (0)
+#define MTB_PICK_ACT(DBG)                                                        \
+  do {                                                                           \
+    if (p.act == ACT_RELU) MTB_PICK_SUMS(ACT_RELU, DBG);                         \
+    else MTB_PICK_SUMS(ACT_NONE, DBG);                                           \
+  } while (0)
+  const bool res = p.residual != nullptr;
+  const bool sums = p.tile_sums != nullptr;
+  // exchange epilogue where a residual is read (its loads and stores halve), pair epilogue otherwise (measured A/B)
+  const int epi = epi_env ? epi_env : (res ? 2 : 1);
+  if (dbg) MTB_PICK_ACT(true);
+  else MTB_PICK_ACT(false);
+#undef MTB_PICK_ACT
+#undef MTB_PICK_SUMS
+#undef MTB_PICK_RA
+#undef MTB_PICK_EPI
+#undef MTB_LAUNCH_F
+  MTB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_bf16x2_to_fp16c(const void* in, long long npix, void* out, float lo_scale, cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long blocks = (npix * 8 + 255) / 256;
+  const int grid = static_cast<int>(blocks < sms * 16ll ? blocks : sms * 16ll);
+  if (grid <= 0) return 0;
+  bf16x2_to_fp16c_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(in), npix, static_cast<uint8_t*>(out),
+                                                   lo_scale);
+  MTB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_fp16c_to_bf16x2(const void* in, long long npix, void* out, float lo_inv, cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long blocks = (npix * 8 + 255) / 256;
+  const int grid = static_cast<int>(blocks < sms * 16ll ? blocks : sms * 16ll);
+  if (grid <= 0) return 0;
+  fp16c_to_bf16x2_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(in), npix, static_cast<uint16_t*>(out),
+                                                   lo_inv);
+  MTB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mtb

@@ -3,6 +3,8 @@
 // All are pure streaming kernels: 16-byte vector loads/stores, grid = multiple of the SM count, one pass over HBM.
 #include <atomic>
 
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include "../../include/mtb200.h"
 #include "common.cuh"
 
@@ -158,7 +160,10 @@ rcan_gate_kernel(const float* __restrict__ sums, int parts, const float* __restr
                  const uint16_t* __restrict__ u, long long plane_stride,
                  int planes, int H, int W, const float* __restrict__ wconv /* [64][64][3][3] */,
                  const float* __restrict__ bconv, const float* __restrict__ w1, const float* __restrict__ b1,
-                 const float* __restrict__ w2, const float* __restrict__ b2, int R, float* __restrict__ scale) {
+                 const float* __restrict__ w2, const float* __restrict__ b2, int R, float* __restrict__ scale,
+                 float lo_inv /* planes == 3 (fp16c byte planes): scale of the e5m2 residual plane */,
+                 long long* __restrict__ fixed /* optional [5][64]: totals + border lines in 2^-20 fixed point, accumulated
+                                                  by the conv epilogue with integer atomics; consumed and zeroed here */) {
   constexpr int C = 64;
   __shared__ float red[32][C];                      // per-warp partials (border lines) / quarter sums (total)
   __shared__ float wide[64][C];                     // per-row-group partials of the two partial-row reductions
@@ -216,7 +221,15 @@ rcan_gate_kernel(const float* __restrict__ sums, int parts, const float* __restr
     // corners: 0 = (0,0), 1 = (0,W-1), 2 = (H-1,0), 3 = (H-1,W-1)
     const long long pix = (b & 2 ? static_cast<long long>(H - 1) * W : 0) + (b & 1 ? W - 1 : 0);
     float cv = 0.f;
-    for (int pl = 0; pl < planes; ++pl) cv += bf16_to_f(u[pl * plane_stride + pix * C + c]);
+    if (planes == 3) {
+      // fp16c: fp16 plane (c >> 5) + e5m2 residual plane 2, 64 bytes per pixel each (plane_stride = bytes per plane)
+      const uint8_t* ub = reinterpret_cast<const uint8_t*>(u);
+      const __half h = *reinterpret_cast<const __half*>(ub + (c >> 5) * plane_stride + pix * 64 + (c & 31) * 2);
+      const __half_raw lr = __nv_cvt_fp8_to_halfraw(ub[2 * plane_stride + pix * 64 + c], __NV_E5M2);
+      cv = __half2float(h) + __half2float(*reinterpret_cast<const __half*>(&lr)) * lo_inv;
+    } else {
+      for (int pl = 0; pl < planes; ++pl) cv += bf16_to_f(u[pl * plane_stride + pix * C + c]);
+    }
     corner[b][c] = cv;
   }
   __syncthreads();
@@ -224,7 +237,16 @@ rcan_gate_kernel(const float* __restrict__ sums, int parts, const float* __restr
   // a plain `acc += row[p]` loop serialises one L2 round trip per row (the 148-iteration border loop alone cost ~30 us),
   // so every thread keeps four independent 16-byte loads in flight and the groups are folded through shared memory in a
   // fixed order (deterministic).
-  {  // total per channel: 16 float4 lanes x 64 row groups
+  if (fixed != nullptr) {
+    if (tid < 5 * C) {
+      const float v = static_cast<float>(static_cast<double>(fixed[tid]) * (1.0 / 1048576.0));
+      fixed[tid] = 0;
+      if (tid < C) tot[tid] = v;
+      else line[(tid >> 6) - 1][tid & 63] = v;
+    }
+    __syncthreads();
+  }
+  if (fixed == nullptr) {  // total per channel: 16 float4 lanes x 64 row groups
     const int c4 = tid & 15, g = tid >> 4;
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
     const float4* src = reinterpret_cast<const float4*>(sums) + c4;
@@ -248,7 +270,7 @@ rcan_gate_kernel(const float* __restrict__ sums, int parts, const float* __restr
     dst[3] = (a0.w + a1.w) + (a2.w + a3.w);
   }
   __syncthreads();
-  if (tid < 4 * C) {   // 64 groups -> 4 quarter sums per channel -> total
+  if (fixed == nullptr && tid < 4 * C) {   // 64 groups -> 4 quarter sums per channel -> total
     const int c = tid & 63, qd = tid >> 6;
     float t = 0.f;
 #pragma unroll
@@ -256,9 +278,9 @@ rcan_gate_kernel(const float* __restrict__ sums, int parts, const float* __restr
     red[qd][c] = t;
   }
   __syncthreads();
-  if (tid < C) tot[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+  if (fixed == nullptr && tid < C) tot[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
   __syncthreads();
-  if (border != nullptr) {
+  if (border != nullptr && fixed == nullptr) {
     // the four border lines arrive as partial rows from the same conv epilogue: [parts][4 lines][64 channels];
     // 16 float4 lanes x 4 lines x 16 row groups
     const int c4 = tid & 15, b = (tid >> 4) & 3, g = tid >> 6;
@@ -476,7 +498,21 @@ int mtb_rcan_gate(const float* sums, int parts, const float* border_sums, const 
               "mtb_rcan_gate: bad arguments");
   rcan_gate_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
       sums, parts, border_sums, static_cast<const uint16_t*>(u), static_cast<long long>(H) * W * 64, planes, H, W, conv_w, conv_b, w1,
-      b1, w2, b2, R, scale_out);
+      b1, w2, b2, R, scale_out, 1.0f, nullptr);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_rcan_gate_fp16c(const float* sums, int parts, const float* border_sums, long long* fixed_sums, const void* u,
+                        int lo_shift, int H, int W, const float* conv_w, const float* conv_b, const float* w1,
+                        const float* b1, const float* w2, const float* b2, int R, float* scale_out, void* stream) {
+  MTB_REQUIRE(u && conv_w && w1 && w2 && scale_out, "mtb_rcan_gate_fp16c: null argument");
+  MTB_REQUIRE(fixed_sums || (sums && border_sums && parts > 0), "mtb_rcan_gate_fp16c: needs fixed_sums or sums + border_sums rows");
+  MTB_REQUIRE(H > 0 && W > 0 && R > 0 && R <= 64, "mtb_rcan_gate_fp16c: bad arguments");
+  rcan_gate_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, parts, border_sums, static_cast<const uint16_t*>(u), static_cast<long long>(H) * W * 64, 3, H, W, conv_w, conv_b,
+      w1, b1, w2, b2, R, scale_out, ldexpf(1.0f, -lo_shift), fixed_sums);
   MTB_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -284,7 +284,50 @@ __global__ void __launch_bounds__(64, 1) mma_rate_kernel(long long* cycles, int 
   if (warp == 1) tmem_dealloc(0, 512);
 }
 
+// tcgen05.ld fragment-layout probe: every thread writes its own TMEM lane with tcgen05.st.32x32b (value = lane * 1000 +
+// column), then each warp reads 16 lanes x 16 columns with tcgen05.ld.16x256b.x2 starting at lane 32*warp + lane_off and
+// dumps its 8 registers: out[warp][thread][8].
+__global__ void __launch_bounds__(128, 1) ldtm_layout_kernel(float* out, int lane_off) {
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, 32);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = tmem_slot;
+  uint32_t v[16];
+  for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(static_cast<float>((warp * 32 + lane) * 1000 + j));
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(base + (static_cast<uint32_t>(warp * 32) << 16)), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
+      "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(base + (static_cast<uint32_t>(warp * 32 + lane_off) << 16))
+               : "memory");
+  tmem_ld_wait();
+  for (int j = 0; j < 8; ++j) out[(warp * 32 + lane) * 8 + j] = __uint_as_float(r[j]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(base, 32);
+}
+
 }  // namespace
+
+extern "C" int mtb_exp_ldtm_layout(float* out /* [4][32][8] */, int lane_off, void* stream) {
+  ldtm_layout_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(out, lane_off);
+  MTB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 // pattern: 0 M128N64, 1 M128N128, 2 M128N256, 3 M128N128+M128N64, 4 M128N240, 5 M64N240, 6 M64N256, 7 M64N128,
 //          8 M128N240+M64N240, 9 M64N64, 10 M128N240 e5m2, 11 M64N240 e5m2, 12 M128N240 f16 + M64N240 e5m2 into one

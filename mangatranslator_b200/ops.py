@@ -74,6 +74,16 @@ class ConvPlan:
             self._keep = self._keep + (border,)
         return rc == 0
 
+    def set_fixed_sums(self, fixed) -> None:
+        """fp16c plans: accumulate the channel / border sums into `fixed` (int64 [5][64], 2^-20 units) with integer atomics
+        instead of per-CTA rows (set_border_sums must have been called)."""
+        assert fixed.dtype == torch.int64 and fixed.numel() >= 320
+        l = lib()
+        l.mtb_conv_plan_set_fixed_sums.argtypes = [C.c_void_p, C.c_void_p]
+        l.mtb_conv_plan_set_fixed_sums.restype = C.c_int
+        check(l.mtb_conv_plan_set_fixed_sums(self._h, ptr(fixed)), "mtb_conv_plan_set_fixed_sums")
+        self._keep = self._keep + (fixed,)
+
     def run(self) -> None:
         check(lib().mtb_conv_plan_run(self._h, stream_ptr()), "mtb_conv_plan_run")
 
@@ -84,3 +94,30 @@ class ConvPlan:
                 self._h = None
         except Exception:
             pass
+
+
+class RcanConvPlan(ConvPlan):
+    """RCAN body layer (3x3, 64 -> 64) in the fp16c format (one fp16 product + an e5m2 correction product per tap).
+
+    x / out / residual: uint8 [3][N][H][W][64] (planes.nhwc_to_fp16c); w: uint8 [2880][64] (planes.conv_weight_to_fp16c).
+    Shares run / channel scale / border sums / sum rows with ConvPlan (same plan object underneath)."""
+
+    def __init__(self, x, w, bias, out, *, act=None, residual=None, tile_sums=None, channel_scale=None, lo_shift=0):
+        for t in (x, out) + ((residual,) if residual is not None else ()):
+            assert t.dtype == torch.uint8 and t.dim() == 5 and t.shape[0] == 3 and t.shape[-1] == 64 and t.is_contiguous()
+        assert out.shape == x.shape and (residual is None or residual.shape == x.shape)
+        assert w.dtype == torch.uint8 and tuple(w.shape) == (2880, 64) and w.is_contiguous()
+        _, n, h, wd, _ = x.shape
+        l = lib()
+        l.mtb_rcan_conv_plan_create.argtypes = [C.c_int] * 3 + [C.c_void_p] * 6 + [C.c_int] * 2 + [C.POINTER(C.c_void_p)]
+        l.mtb_rcan_conv_plan_create.restype = C.c_int
+        self._keep = (x, w, bias, out, residual, tile_sums)
+        hd = C.c_void_p()
+        check(l.mtb_rcan_conv_plan_create(n, h, wd, ptr(x), ptr(w), ptr(bias), ptr(out), ptr(residual), ptr(tile_sums),
+                                          ACT[act], lo_shift, C.byref(hd)), "mtb_rcan_conv_plan_create")
+        self._h = hd
+        self.out = out
+        if channel_scale is not None:
+            assert channel_scale.dtype == torch.float32 and channel_scale.numel() >= 64
+            self._keep = self._keep + (channel_scale,)
+            check(l.mtb_conv_plan_set_channel_scale(self._h, ptr(channel_scale)), "mtb_conv_plan_set_channel_scale")

@@ -28,7 +28,7 @@ import torch
 
 from . import planes as P
 from ._lib import check, lib, ptr, stream_ptr
-from .ops import ConvPlan
+from .ops import ConvPlan, RcanConvPlan
 
 
 def _declare(l) -> None:
@@ -42,8 +42,12 @@ def _declare(l) -> None:
     l.mtb_f32_to_u8.argtypes = [vp, C.c_longlong, i32, C.POINTER(f32), f32, vp, vp, vp]
     l.mtb_image_to_planes_unshuffle.argtypes = [vp, i32, i32, i32, i32, f32, C.POINTER(f32), i32, vp, i32, i32, vp]
     l.mtb_f32_to_u8_crop.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(f32), f32, vp, vp, vp]
+    l.mtb_rcan_gate_fp16c.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    l.mtb_planes_bf16x2_to_fp16c.argtypes = [vp, C.c_longlong, vp, i32, vp]
+    l.mtb_planes_fp16c_to_bf16x2.argtypes = [vp, C.c_longlong, vp, i32, vp]
     for n in ("mtb_image_to_planes", "mtb_ca_scale", "mtb_scale_residual", "mtb_f32_to_u8", "mtb_rcan_gate",
-              "mtb_image_to_planes_unshuffle", "mtb_f32_to_u8_crop"):
+              "mtb_image_to_planes_unshuffle", "mtb_f32_to_u8_crop", "mtb_rcan_gate_fp16c", "mtb_planes_bf16x2_to_fp16c",
+              "mtb_planes_fp16c_to_bf16x2"):
         getattr(l, n).restype = i32
     l._ew_declared = True
 
@@ -74,13 +78,22 @@ def infer_config(sd: Dict[str, torch.Tensor]) -> dict:
 class RcanB200:
     DIV2K_MEAN = (0.4488, 0.4371, 0.4040)
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device, *, precision: str = "bf16x3",
-                 rgb_range: float = 1.0, norm: bool = False, conv_mode: int = 0):
-        assert precision in ("bf16x3", "bf16")
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device, *, precision: str | None = None,
+                 rgb_range: float = 1.0, norm: bool = False, conv_mode: int = 0, lo_shift: int = 0):
+        """precision: "fp16c" (default; MTB200_RCAN_PRECISION overrides) runs the 64->64 body convs as one fp16 product +
+        an e5m2 correction product per tap (conv_halo_fp16c.cu; fp32-grade within the 1e-3 parity bound, 25 % fewer
+        tensor-core cycles, 3 B per activation); "bf16x3" keeps them in bf16 hi/lo planes (the A/B partner, ~4e-5);
+        "bf16" is a plain bf16 network (NOT parity grade).  Head, upsampler and tail run in bf16x3 for both."""
+        precision = precision or os.environ.get("MTB200_RCAN_PRECISION", "fp16c")
+        assert precision in ("fp16c", "bf16x3", "bf16")
         self.l = lib()
         _declare(self.l)
         self.device = device
-        self.planes = 2 if precision == "bf16x3" else 1
+        self.planes = 1 if precision == "bf16" else 2
+        self.fp16c = precision == "fp16c"
+        self.lo_shift = int(lo_shift)
+        # channel sums for the RCAB gate as fixed-point integer atomics (default) or as per-CTA float rows (A/B partner)
+        self.fixed_sums = os.environ.get("MTB200_RCAN_FIXED_SUMS", "1") != "0"
         self.precision = precision
         self.cfg = infer_config(state_dict)
         self.rgb_range, self.norm, self.conv_mode = float(rgb_range), bool(norm), conv_mode
@@ -91,7 +104,10 @@ class RcanB200:
         self.F = f
         pl = self.planes
 
-        def conv_w(name):
+        def conv_w(name, body=False):
+            if body and self.fp16c:
+                return (P.conv_weight_to_fp16c(sd[name + ".weight"], self.lo_shift),
+                        P.pad_bias(sd.get(name + ".bias"), sd[name + ".weight"].shape[0]))
             return P.conv_weight_to_planes(sd[name + ".weight"], pl), P.pad_bias(sd.get(name + ".bias"), sd[name + ".weight"].shape[0])
 
         self.w_head = conv_w("head.0")
@@ -101,7 +117,7 @@ class RcanB200:
             grp = []
             for b in range(R):
                 base = f"body.{g}.body.{b}.body"
-                w1, w2 = conv_w(base + ".0"), conv_w(base + ".2")
+                w1, w2 = conv_w(base + ".0", True), conv_w(base + ".2", True)
                 cd1 = sd[base + ".3.conv_du.0.weight"].reshape(-1, f).contiguous()
                 cb1 = sd[base + ".3.conv_du.0.bias"].contiguous()
                 cd2 = sd[base + ".3.conv_du.2.weight"].reshape(f, -1).contiguous()
@@ -109,8 +125,8 @@ class RcanB200:
                 w2f = sd[base + ".2.weight"].contiguous()                 # fp32 [64][64][3][3] for the gate's mean
                 b2f = sd[base + ".2.bias"].contiguous() if (base + ".2.bias") in sd else None
                 grp.append((w1, w2, cd1, cb1, cd2, cb2, w2f, b2f))
-            self.blocks.append((grp, conv_w(f"body.{g}.body.{R}")))
-        self.w_body_tail = conv_w(f"body.{G}")
+            self.blocks.append((grp, conv_w(f"body.{g}.body.{R}", True)))
+        self.w_body_tail = conv_w(f"body.{G}", True)
         # upsampler conv: reorder output channels so the four PixelShuffle phases are contiguous 64-channel blocks
         idx = torch.arange(4 * f, device=device).view(f, 4).t().reshape(-1)   # new[(dy*2+dx)*f + c] = old[c*4 + dy*2+dx]
         self.w_up = []
@@ -136,17 +152,32 @@ class RcanB200:
             nbytes[0] += pl * n * hh * ww * c * 2
             return torch.zeros((pl, n, hh, ww, c), dtype=bf, device=dev)
 
-        b = dict(x_in=act(h, w), head=act(h, w), u=act(h, w), pa=act(h, w), pb=act(h, w),
-                 g0=act(h, w), g1=act(h, w), scale=torch.zeros((n, f), dtype=torch.float32, device=dev))
+        def cact(hh, ww):                      # fp16c byte planes of the body
+            nbytes[0] += 3 * n * hh * ww * 64
+            return torch.zeros((3, n, hh, ww, 64), dtype=torch.uint8, device=dev)
+
+        bact = cact if self.fp16c else act
+        b = dict(x_in=act(h, w), head=act(h, w), u=bact(h, w), pa=bact(h, w), pb=bact(h, w),
+                 g0=bact(h, w), g1=bact(h, w), scale=torch.zeros((n, f), dtype=torch.float32, device=dev))
         steps = []
         mode = self.conv_mode
 
         def conv(x, wgt, out, **kw):
             return ConvPlan(x, wgt[0], wgt[1], out, k=3, pad=1, mode=kw.pop("mode", mode), **kw)
 
+        def bconv(x, wgt, out, **kw):          # a 64 -> 64 body layer
+            if self.fp16c:
+                return RcanConvPlan(x, wgt[0], wgt[1], out, lo_shift=self.lo_shift, **kw)
+            return conv(x, wgt, out, **kw)
+
         # head conv: only 3*d*d of the 64 padded input channels are non-zero (per-tap kernel)
         steps.append(("conv", conv(b["x_in"], self.w_head, b["head"], mode=1)))
-        probe = conv(b["head"], self.blocks[0][0][0][0], b["u"], act="relu")
+        body_in = b["head"]
+        if self.fp16c:
+            b["head_c"] = cact(h, w)
+            steps.append(("to_fp16c", (b["head"], b["head_c"], n * h * w)))
+            body_in = b["head_c"]
+        probe = bconv(body_in, self.blocks[0][0][0][0], b["u"], act="relu")
         parts = probe.num_sum_rows
         sums = torch.zeros((parts, f), dtype=torch.float32, device=dev)
         b["sums"] = sums
@@ -154,25 +185,32 @@ class RcanB200:
         # layer (bf16x3); otherwise the gate kernel reads the four lines of u itself
         border = torch.zeros((parts, 4, f), dtype=torch.float32, device=dev)
         b["border"] = None
-        src = b["head"]
+        b["fixed"] = torch.zeros((5, f), dtype=torch.int64, device=dev)     # fp16c: fixed-point sums (integer atomics)
+        src = body_in
         for gi, (grp, tailw) in enumerate(self.blocks):
             grp_in = src
             x = grp_in
             for (w1, w2, cd1, cb1, cd2, cb2, w2f, b2f) in grp:
                 dst = b["pa"] if x is not b["pa"] else b["pb"]
-                c1 = conv(x, w1, b["u"], act="relu", tile_sums=sums)
+                c1 = bconv(x, w1, b["u"], act="relu", tile_sums=sums)
                 if c1.set_border_sums(border):
                     b["border"] = border
+                if self.fp16c and self.fixed_sums:
+                    c1.set_fixed_sums(b["fixed"])
                 steps.append(("conv_body", c1))
                 steps.append(("gate", (parts, w2f, b2f, cd1, cb1, cd2, cb2)))
-                steps.append(("conv_body", conv(b["u"], w2, dst, residual=x, channel_scale=b["scale"])))
+                steps.append(("conv_body", bconv(b["u"], w2, dst, residual=x, channel_scale=b["scale"])))
                 x = dst
             gout = b["g0"] if grp_in is not b["g0"] else b["g1"]
-            steps.append(("conv", conv(x, tailw, gout, residual=grp_in)))   # group tail conv + group skip
+            steps.append(("conv", bconv(x, tailw, gout, residual=grp_in)))   # group tail conv + group skip
             src = gout
-        steps.append(("conv", conv(src, self.w_body_tail, b["u"], residual=b["head"])))
+        steps.append(("conv", bconv(src, self.w_body_tail, b["u"], residual=body_in)))
         # upsampler: conv F -> 4F with the PixelShuffle(2) folded into the store, once per stage
         cur, hh, ww = b["u"], h, w
+        if self.fp16c:
+            b["body_out"] = act(h, w)
+            steps.append(("from_fp16c", (b["u"], b["body_out"], n * h * w)))
+            cur = b["body_out"]
         for si, wu in enumerate(self.w_up):
             nxt = act(2 * hh, 2 * ww)
             b[f"up{si}"] = nxt
@@ -206,16 +244,33 @@ class RcanB200:
 
     def _run_body(self, b: dict, h: int, w: int) -> None:
         l, st = self.l, stream_ptr()
-        f = self.F
-        inv_hw = 1.0 / float(h * w)
+        if self.fp16c and self.fixed_sums:
+            b["fixed"].zero_()                 # the gate leaves them zeroed; this only matters after an aborted pass
         for kind, arg in b["steps"]:
-            if kind in ("conv", "conv_body"):
-                arg.run()
-            else:
-                self._gate(b, arg, h, w, st)
+            self._run_step(b, kind, arg, h, w, st)
+
+    def _run_step(self, b: dict, kind: str, arg, h: int, w: int, st) -> None:
+        if kind in ("conv", "conv_body"):
+            arg.run()
+        elif kind == "gate":
+            self._gate(b, arg, h, w, st)
+        elif kind == "to_fp16c":
+            check(self.l.mtb_planes_bf16x2_to_fp16c(ptr(arg[0]), arg[2], ptr(arg[1]), self.lo_shift, st), "mtb_planes_bf16x2_to_fp16c")
+        elif kind == "from_fp16c":
+            check(self.l.mtb_planes_fp16c_to_bf16x2(ptr(arg[0]), arg[2], ptr(arg[1]), self.lo_shift, st), "mtb_planes_fp16c_to_bf16x2")
+        else:
+            raise ValueError(kind)
 
     def _gate(self, b: dict, arg, h: int, w: int, st) -> None:
         parts, w2f, b2f, cd1, cb1, cd2, cb2 = arg
+        if self.fp16c:
+            if b["border"] is None:
+                raise RuntimeError("RcanB200: the fp16c body needs the border sums of conv1's epilogue (one image per launch)")
+            check(self.l.mtb_rcan_gate_fp16c(ptr(b["sums"]), parts, ptr(b["border"]), ptr(b["fixed"]) if self.fixed_sums else None,
+                                             ptr(b["u"]), self.lo_shift, h, w, ptr(w2f),
+                                             ptr(b2f), ptr(cd1), ptr(cb1), ptr(cd2), ptr(cb2), cd1.shape[0], ptr(b["scale"]), st),
+                  "mtb_rcan_gate_fp16c")
+            return
         check(self.l.mtb_rcan_gate(ptr(b["sums"]), parts, ptr(b["border"]), ptr(b["u"]), self.planes, h, w, ptr(w2f), ptr(b2f), ptr(cd1),
                                    ptr(cb1), ptr(cd2), ptr(cb2), cd1.shape[0], ptr(b["scale"]), st), "mtb_rcan_gate")
 
@@ -230,10 +285,7 @@ class RcanB200:
         for kind, arg in b["steps"]:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            if kind in ("conv", "conv_body"):
-                arg.run()
-            else:
-                self._gate(b, arg, hb, wb, st)
+            self._run_step(b, kind, arg, hb, wb, st)
             e1.record()
             evs.append((kind, e0, e1))
         torch.cuda.synchronize()

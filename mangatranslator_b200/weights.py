@@ -48,17 +48,19 @@ def rcan_state_dict(seed: int = 0, n_resgroups: int = 10, n_resblocks: int = 20,
         for bi in range(n_resblocks):
             base = f"body.{gi}.body.{bi}.body"
             put(base + ".0", *_conv(g, f, f, 3, gain=1.4))          # conv + ReLU
-            put(base + ".2", *_conv(g, f, f, 3, gain=0.5))          # residual branch kept small, like trained nets
+            put(base + ".2", *_conv(g, f, f, 3, gain=0.25))         # residual branch kept small, like trained nets: the
+                                                                    # trunk stays O(1) over the 200 blocks (with 0.5 it grew
+                                                                    # x46 and the output left [0,1] by an order of magnitude)
             put(base + ".3.conv_du.0", *_conv(g, f // reduction, f, 1, gain=1.0))
             put(base + ".3.conv_du.2", *_conv(g, f, f // reduction, 1, gain=1.0))
-        put(f"body.{gi}.body.{n_resblocks}", *_conv(g, f, f, 3, gain=0.5))
-    put(f"body.{n_resgroups}", *_conv(g, f, f, 3, gain=0.5))
+        put(f"body.{gi}.body.{n_resblocks}", *_conv(g, f, f, 3, gain=0.25))
+    put(f"body.{n_resgroups}", *_conv(g, f, f, 3, gain=0.3))
     put("tail.0.0", *_conv(g, 4 * f, f, 3, gain=1.0))
     up, i = 2 * unshuffle, 2
     while up > 2:
         put(f"tail.0.{i}", *_conv(g, 4 * f, f, 3, gain=1.0))
         up, i = up // 2, i + 2
-    put("tail.1", *_conv(g, 3, f, 3, gain=0.3))
+    put("tail.1", *_conv(g, 3, f, 3, gain=0.2))
     sd["tail.1.bias"] = torch.full((3,), 0.5)                        # mid-grey output so pixels are not clipped
     return sd
 

@@ -1,4 +1,5 @@
-"""GPU: B200 RCAN (tcgen05 bf16x3 convs, halo-tile body layers, fused channel-attention reduce, fused PixelShuffle)
+"""GPU: B200 RCAN (tcgen05 convs: fp16 + e5m2-correction body layers with bf16x3 as the A/B partner, halo tiles, fused
+channel-attention reduce, fused PixelShuffle)
 against the fp32 CPU oracle (oracle/rcan_oracle.py).  Tolerance: 1e-3 abs on the float pixels before quantisation
 (BASELINE.json north_star); uint8 outputs may differ by 1 LSB where the float value sits on a quantisation boundary."""
 import numpy as np
@@ -11,14 +12,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-def _run(cfg, h, w, seed, conv_mode=0):
+def _run(cfg, h, w, seed, conv_mode=0, precision=None):
     from mangatranslator_b200.rcan import RcanB200
     dev = torch.device("cuda:0")
     m = rcan_oracle.make_model(seed, **cfg)
     rng = np.random.default_rng(seed)
     rgb = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
     ref_f, ref_u8 = rcan_oracle.upscale_u8(m, rgb)
-    net = RcanB200(m.state_dict(), dev, conv_mode=conv_mode)
+    net = RcanB200(m.state_dict(), dev, conv_mode=conv_mode, precision=precision)
     out_u8, out_f = net.upscale_u8(torch.from_numpy(rgb).to(dev), want_float=True)
     torch.cuda.synchronize()
     got = out_f.cpu().permute(2, 0, 1).unsqueeze(0)
@@ -27,18 +28,116 @@ def _run(cfg, h, w, seed, conv_mode=0):
     return err, du8, net, m, rgb
 
 
-@pytest.mark.parametrize("conv_mode", [0, 1], ids=["halo", "per_tap"])
-def test_small_rcan_matches_oracle(conv_mode):
-    err, du8, *_ = _run(dict(n_resgroups=2, n_resblocks=3), 96, 80, 1, conv_mode)
+@pytest.mark.parametrize("conv_mode,precision", [(0, "fp16c"), (0, "bf16x3"), (1, "bf16x3")],
+                         ids=["fp16c", "bf16x3_halo", "bf16x3_per_tap"])
+def test_small_rcan_matches_oracle(conv_mode, precision):
+    err, du8, net, *_ = _run(dict(n_resgroups=2, n_resblocks=3), 96, 80, 1, conv_mode, precision)
+    assert net.precision == precision
     assert err < TOL, err
     assert du8.max() <= 1 and (du8 > 0).mean() < 0.01
 
 
-def test_full_depth_rcan_matches_oracle():
-    """10 groups x 20 RCABs (the classic RCAN shape) on a small frame, odd size to exercise tile edges."""
-    err, du8, *_ = _run(dict(n_resgroups=10, n_resblocks=20), 72, 56, 2)
+@pytest.mark.parametrize("precision,bound", [("fp16c", 4e-4), ("bf16x3", 1e-4)])
+def test_full_depth_rcan_matches_oracle(precision, bound):
+    """10 groups x 20 RCABs (the classic RCAN shape) on a small frame, odd size to exercise tile edges.  The parity bound
+    is 1e-3; each format is additionally held to a bound near what it measures (fp16 + e5m2 correction: ~1.8e-4 in the
+    float64 emulation of tools/cpu_operand_format_accuracy.py, bf16x3: ~4e-5) so a regression in either shows."""
+    err, du8, *_ = _run(dict(n_resgroups=10, n_resblocks=20), 72, 56, 2, precision=precision)
+    print(f"full-depth RCAN {precision}: max abs err {err:.3e}")
     assert err < TOL, err
+    assert err < bound, err
     assert du8.max() <= 1
+
+
+@pytest.mark.parametrize("hw,res,lo_shift", [((37, 53), True, 0), ((1, 9), False, 0), ((64, 8), True, 3), ((61, 250), True, 0),
+                                             ((30, 16), False, 0), ((95, 40), True, 0)],
+                         ids=["odd", "one_row", "one_tile_column_shift3", "wide_ragged", "exact_tiles", "interior_tiles"])
+def test_fp16c_conv_layer_matches_float64_of_its_operands(hw, res, lo_shift):
+    """One 64->64 3x3 layer of conv_halo_fp16c.cu against float64 arithmetic on exactly the operands it is given:
+    [fp16(w); fp16(w - fp16 w)] x fp16(x)  +  e5m2(w 2^-s) x e5m2((x - fp16 x) 2^s), then bias, channel scale, ReLU, residual;
+    checks the packed weight order, the three-plane TMA tiles, the M = 64 lane placement, tile edges, the stored planes
+    and the channel / border sums the RCAB gate consumes."""
+    import torch.nn.functional as F
+    from mangatranslator_b200 import planes as P
+    from mangatranslator_b200.ops import RcanConvPlan
+    h, w = hw
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(11 + h)
+    x = torch.randn(1, 64, h, w, generator=g).to(dev)
+    wt = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(dev)
+    bias = torch.randn(64, generator=g).to(dev)
+    scale = (torch.rand(64, generator=g) + 0.5).to(dev)
+    r = torch.randn(1, 64, h, w, generator=g).to(dev)
+    xp, rp = P.nchw_to_fp16c(x, lo_shift), P.nchw_to_fp16c(r, lo_shift)
+    wp = P.conv_weight_to_fp16c(wt, lo_shift)
+    out = torch.zeros_like(xp)
+    probe = RcanConvPlan(xp, wp, bias, out, act="relu", lo_shift=lo_shift)
+    parts = probe.num_sum_rows
+    sums = torch.zeros(parts, 64, device=dev)
+    border = torch.zeros(parts, 4, 64, device=dev)
+    plan = RcanConvPlan(xp, wp, bias, out, act="relu", residual=rp if res else None, tile_sums=sums, channel_scale=scale,
+                        lo_shift=lo_shift)
+    assert plan.set_border_sums(border)
+    plan.run()
+    torch.cuda.synchronize()
+    # the same layer without the sums (the kernel instantiation conv2 / the group tails run) stores the same planes
+    out2 = torch.zeros_like(xp)
+    RcanConvPlan(xp, wp, bias, out2, act="relu", residual=rp if res else None, channel_scale=scale, lo_shift=lo_shift).run()
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
+    # the operands as the kernel sees them
+    x16 = x.half().double()
+    x8 = ((x - x.half().float()) * 2.0 ** lo_shift).to(torch.float8_e5m2).double()
+    w16 = wt.half().double() + (wt - wt.half().float()).half().double()
+    w8 = (wt * 2.0 ** -lo_shift).to(torch.float8_e5m2).double()
+    acc = F.conv2d(x16, w16, None, padding=1) + F.conv2d(x8, w8, None, padding=1)
+    exp = torch.relu((acc + bias.double().view(1, -1, 1, 1)) * scale.double().view(1, -1, 1, 1))
+    if res:
+        exp = exp + P.fp16c_to_nchw(rp, lo_shift).double()
+    got = P.fp16c_to_nchw(out, lo_shift).double()
+    mag = float(exp.abs().max())
+    # stored as fp16 + e5m2 of the rounding residual: 2^-11 * 2^-3 relative, plus fp32 accumulation of 576 terms
+    assert (got - exp).abs().max().item() < mag * 2.0 ** -13 + 2e-5, ((got - exp).abs().max().item(), mag)
+    tot = sums.double().sum(0)
+    assert (tot - exp.sum((0, 2, 3))).abs().max().item() < 1e-3 * max(1.0, float(exp.sum((0, 2, 3)).abs().max()))
+    lines = torch.stack([exp[0, :, 0, :].sum(1), exp[0, :, h - 1, :].sum(1), exp[0, :, :, 0].sum(1), exp[0, :, :, w - 1].sum(1)])
+    assert (border.double().sum(0) - lines).abs().max().item() < 1e-3 * max(1.0, float(lines.abs().max()))
+    # the sums as fixed-point integer atomics (what the network runs): same values, bit-identical from launch to launch
+    fixed = torch.zeros(5, 64, dtype=torch.int64, device=dev)
+    plan.set_fixed_sums(fixed)
+    plan.run()
+    torch.cuda.synchronize()
+    first = fixed.clone()
+    fixed.zero_()
+    plan.run()
+    torch.cuda.synchronize()
+    assert torch.equal(fixed, first)
+    fx = fixed.double() / 2.0 ** 20
+    assert (fx[0] - tot).abs().max().item() < 1e-3 * max(1.0, float(tot.abs().max()))
+    assert (fx[1:] - border.double().sum(0)).abs().max().item() < 1e-3 * max(1.0, float(lines.abs().max()))
+
+
+def test_fp16c_plane_conversions_round_trip():
+    """bf16 hi/lo planes <-> fp16c byte planes (the two passes at the boundary of the RCAN body)."""
+    from mangatranslator_b200 import planes as P
+    from mangatranslator_b200._lib import check, lib, ptr, stream_ptr
+    from mangatranslator_b200.rcan import _declare
+    dev = torch.device("cuda:0")
+    l = lib()
+    _declare(l)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    v = (torch.randn(1, 64, 19, 23, generator=g) * torch.logspace(-3, 1, 64).view(1, 64, 1, 1)).to(dev)
+    bp = P.nchw_to_planes(v, 2)
+    vq = P.planes_to_nchw(bp, 64)
+    for shift in (0, 4):
+        cp = torch.zeros((3, 1, 19, 23, 64), dtype=torch.uint8, device=dev)
+        check(l.mtb_planes_bf16x2_to_fp16c(ptr(bp), 19 * 23, ptr(cp), shift, stream_ptr()), "to_fp16c")
+        torch.cuda.synchronize()
+        assert torch.equal(cp, P.nhwc_to_fp16c(vq.permute(0, 2, 3, 1).contiguous(), shift))
+        back = torch.zeros_like(bp)
+        check(l.mtb_planes_fp16c_to_bf16x2(ptr(cp), 19 * 23, ptr(back), shift, stream_ptr()), "from_fp16c")
+        torch.cuda.synchronize()
+        assert torch.equal(back, P.split_planes(P.fp16c_to_nhwc(cp, shift), 2))
 
 
 @pytest.mark.parametrize("hw", [(96, 80), (37, 53), (9, 131)], ids=["even", "odd_reflect_pad", "thin"])
@@ -130,6 +229,32 @@ def test_gate_from_input_sums_equals_gate_of_conv_output(hw):
     mean = (F.conv2d(uq, wc.double(), bc.double(), padding=1)).mean((0, 2, 3))
     ref = torch.sigmoid(w2.double() @ torch.relu(w1.double() @ mean + b1.double()) + b2.double())
     assert (scale.double() - ref).abs().max().item() < 2e-5
+    # the fp16c body: corners decoded from the byte planes, border lines from the epilogue's partial rows
+    for shift in (0, 3):
+        uc = P.nchw_to_fp16c(u, shift)
+        uq3 = P.fp16c_to_nchw(uc, shift).double()
+        tot3 = uq3.sum((0, 2, 3)).float()
+        rows3 = torch.rand(parts, 64, device=dev)
+        rows3 = (rows3 / rows3.sum(0, keepdim=True) * tot3).contiguous()
+        lines3 = torch.stack([uq3[0, :, 0, :].sum(1), uq3[0, :, h - 1, :].sum(1), uq3[0, :, :, 0].sum(1),
+                              uq3[0, :, :, w - 1].sum(1)]).float()
+        split3 = torch.rand(parts, 4, 64, device=dev)
+        split3 = (split3 / split3.sum(0, keepdim=True) * lines3).contiguous()
+        scale3 = torch.zeros(64, device=dev)
+        check(l.mtb_rcan_gate_fp16c(ptr(rows3), parts, ptr(split3), None, ptr(uc), shift, h, w, ptr(wc), ptr(bc), ptr(w1), ptr(b1),
+                                    ptr(w2), ptr(b2), 4, ptr(scale3), stream_ptr()), "mtb_rcan_gate_fp16c")
+        torch.cuda.synchronize()
+        mean3 = (F.conv2d(uq3, wc.double(), bc.double(), padding=1)).mean((0, 2, 3))
+        ref3 = torch.sigmoid(w2.double() @ torch.relu(w1.double() @ mean3 + b1.double()) + b2.double())
+        assert (scale3.double() - ref3).abs().max().item() < 2e-5
+        # totals and border lines as 2^-20 fixed-point accumulators: same gate, accumulators handed back zeroed
+        fixed = torch.cat([tot3.view(1, 64), lines3]).double().mul(2.0 ** 20).round().to(torch.int64).contiguous()
+        scale4 = torch.zeros(64, device=dev)
+        check(l.mtb_rcan_gate_fp16c(None, 0, None, ptr(fixed), ptr(uc), shift, h, w, ptr(wc), ptr(bc), ptr(w1), ptr(b1),
+                                    ptr(w2), ptr(b2), 4, ptr(scale4), stream_ptr()), "mtb_rcan_gate_fp16c")
+        torch.cuda.synchronize()
+        assert (scale4.double() - ref3).abs().max().item() < 2e-5
+        assert int(fixed.abs().sum()) == 0
 
 
 def test_plain_bf16_mode_is_close():
