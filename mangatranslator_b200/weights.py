@@ -81,17 +81,21 @@ def yolo_state_dict(seed: int = 0, cfg: Optional[dict] = None) -> Dict[str, torc
     c = lambda x: int(math.ceil(min(x, max_ch) * width / 8) * 8)
     sd: Dict[str, torch.Tensor] = {}
 
+    # Gains: 1.6 keeps the second moment through conv -> SiLU chains; the bottlenecks' residual branches (0.8) and the
+    # convs that read a concat (1.4) are damped so that the 8 C2f stages of the "m" layout keep activations at O(1-10)
+    # like a trained, BN-folded detector (with 1.6 everywhere they reached 1e4 and the prototypes 1e4: any absolute
+    # tolerance on head tensors was meaningless).
     def conv(name, cin, cout, k, gain=1.6):
-        w, b = _conv(g, cout, cin, k, gain=gain, bias_std=0.1)
+        w, b = _conv(g, cout, cin, k, gain=gain, bias_std=0.05)
         sd[name + ".weight"], sd[name + ".bias"] = w, b
 
     def c2f(name, c1, c2, n):
         hc = c2 // 2
         conv(f"{name}.cv1.conv", c1, 2 * hc, 1)
-        conv(f"{name}.cv2.conv", (2 + n) * hc, c2, 1)
+        conv(f"{name}.cv2.conv", (2 + n) * hc, c2, 1, gain=1.4)
         for i in range(n):
             conv(f"{name}.m.{i}.cv1.conv", hc, hc, 3)
-            conv(f"{name}.m.{i}.cv2.conv", hc, hc, 3)
+            conv(f"{name}.m.{i}.cv2.conv", hc, hc, 3, gain=0.8)
 
     c64, c128, c256, c512, c1024 = c(64), c(128), c(256), c(512), c(1024)
     conv("l0.conv", 3, c64, 3)
@@ -104,7 +108,7 @@ def yolo_state_dict(seed: int = 0, cfg: Optional[dict] = None) -> Dict[str, torc
     conv("l7.conv", c512, c1024, 3)
     c2f("l8", c1024, c1024, d(3))
     conv("l9.cv1.conv", c1024, c1024 // 2, 1)
-    conv("l9.cv2.conv", c1024 // 2 * 4, c1024, 1)
+    conv("l9.cv2.conv", c1024 // 2 * 4, c1024, 1, gain=1.4)
     c2f("l12", c1024 + c512, c512, d(3))
     c2f("l15", c512 + c256, c256, d(3))
     conv("l16.conv", c256, c256, 3)
