@@ -18,6 +18,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+os.environ.setdefault("MTB200_SYNTHETIC_WEIGHTS", "1")     # `data: synthetic`: seeded weights of the named architectures
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 

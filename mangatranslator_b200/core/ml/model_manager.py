@@ -69,7 +69,7 @@ class ModelManager:
             self.device = get_best_device()
             self.dtype = get_best_dtype(self.device)
             self.models: Dict[ModelType, Any] = {}
-            self.models_dir = Path(models_dir)
+            self.models_dir = Path(os.environ.get("MT_MODELS_DIR") or models_dir)
             self.model_paths: Dict[ModelType, Path] = {
                 ModelType.UPSCALE: self.models_dir / "upscale" / "2x-AnimeSharpV4_RCAN.safetensors",
                 ModelType.UPSCALE_LITE: self.models_dir / "upscale" / "2x-AnimeSharpV4_Fast_RCAN_PU.safetensors",
@@ -106,8 +106,10 @@ class ModelManager:
         if path.suffix == ".safetensors":
             from safetensors.torch import load_file
             return load_file(str(path))
-        obj = torch.load(str(path), map_location="cpu")
-        return obj if isinstance(obj, dict) else None
+        obj = torch.load(str(path), map_location="cpu", weights_only=True)
+        if not isinstance(obj, dict):
+            raise ModelError(f"{path}: not a state dict")
+        return obj
 
     # ---- loaders -----------------------------------------------------------------------------------------------
     def _resolve_yolo_type(self, model_path) -> ModelType:
@@ -119,6 +121,17 @@ class ModelManager:
             pass
         return ModelType.YOLO_SPEECH_BUBBLE
 
+    def _synthetic_or_raise(self, what: str, looked: list):
+        """Weight policy: a missing checkpoint is an error (the reference would download it; there is no network here)
+        unless seeded synthetic weights were asked for explicitly with MTB200_SYNTHETIC_WEIGHTS=1 (tests, bench, smoke)."""
+        where = ", ".join(str(p) for p in looked) or "no path given"
+        if not W.synthetic_allowed():
+            raise ModelError(f"{what}: checkpoint not found ({where}). Put the reference's model file there (or point "
+                             "MT_MODELS_DIR at the models directory); set MTB200_SYNTHETIC_WEIGHTS=1 only to run with seeded "
+                             "synthetic weights (benchmarks / tests: outputs are meaningless on real pages).")
+        log_message(f"{what}: NO CHECKPOINT ({where}) - using seeded SYNTHETIC weights (MTB200_SYNTHETIC_WEIGHTS=1, seed "
+                    f"{self.synthetic_seed}); outputs are meaningless on real pages", always_print=True)
+
     def load_yolo_speech_bubble(self, model_path=None, verbose: bool = False):
         mt = self._resolve_yolo_type(model_path)
         with self._lock:
@@ -126,14 +139,41 @@ class ModelManager:
                 return self.models[mt]
             from mangatranslator_b200.yolo import YoloB200
             dev = self._require_cuda()
-            cfg = W.yolo_cfg("m")
-            sd = self._load_file_state_dict(Path(model_path)) if model_path else None
-            if sd is None:
-                log_message("YOLO: no checkpoint on disk, using seeded synthetic weights (MTB200_WEIGHT_SEED)",
-                            verbose=verbose)
+            # the path the caller configured, then the reference's default locations under the models directory
+            cands = ([Path(model_path)] if model_path else []) + [self.model_paths[mt], self.model_paths[ModelType.YOLO_SPEECH_BUBBLE_2],
+                                                                 self.model_paths[ModelType.YOLO_SPEECH_BUBBLE]]
+            path = next((p for p in cands if p.is_file()), None)
+            names = None
+            if path is not None:
+                try:
+                    raw, names = W.load_ultralytics_state_dict(str(path))
+                    sd, cfg = W.yolo_from_ultralytics(raw, names)
+                except W.UnsupportedCheckpoint as e:
+                    raise ModelError(f"YOLO speech-bubble detector: cannot use {path}: {e}") from e
+                except Exception as e:
+                    raise ModelError(f"YOLO speech-bubble detector: failed to read {path}: {e}") from e
+                log_message(f"YOLO speech-bubble detector: weights from {path} (YOLOv8-seg, {len(sd)} tensors, nc={cfg['nc']})",
+                            always_print=True)
+            else:
+                self._synthetic_or_raise("YOLO speech-bubble detector", cands[:2])
+                cfg = W.yolo_cfg("m")
                 sd = W.yolo_state_dict(self.synthetic_seed, cfg)
-            self.models[mt] = YoloB200(sd, cfg, dev, precision=self.precision)
+            if isinstance(names, (list, tuple)):
+                names = dict(enumerate(names))
+            self.models[mt] = YoloB200(sd, cfg, dev, precision=self.precision, names=names if isinstance(names, dict) else None)
             return self.models[mt]
+
+    def _sam_checkpoint_dir(self) -> Optional[str]:
+        """A `from_pretrained`-loadable directory: $MT_MODELS_DIR/sam (flat), or the snapshot inside the Hugging Face cache
+        the reference fills (`cache_dir="models/sam"`, core/ml/model_manager.py:994-1003)."""
+        roots = [self.models_dir / "sam", Path("models") / "sam"]
+        for root in roots:
+            if (root / "config.json").is_file():
+                return str(root)
+            for snap in sorted(root.glob("models--facebook--sam2*/snapshots/*")):
+                if (snap / "config.json").is_file():
+                    return str(snap)
+        return None
 
     def load_sam2(self, verbose: bool = False):
         with self._lock:
@@ -142,7 +182,18 @@ class ModelManager:
             from mangatranslator_b200.sam2 import Sam2B200
             from mangatranslator_b200.sam2_api import Sam2ModelB200, Sam2ProcessorB200
             dev = self._require_cuda()
-            cfg, sd = W.sam2_model_and_state(self.synthetic_seed, os.environ.get("MTB200_SAM_VARIANT", "tiny"))
+            ckpt = self._sam_checkpoint_dir()
+            if ckpt is not None:
+                try:
+                    from transformers import Sam2Model
+                    m = Sam2Model.from_pretrained(ckpt, local_files_only=True)
+                    cfg, sd = m.config, m.state_dict()
+                except Exception as e:
+                    raise ModelError(f"SAM 2.1: failed to read {ckpt}: {e}") from e
+                log_message(f"SAM 2.1: weights from {ckpt}", always_print=True)
+            else:
+                self._synthetic_or_raise("SAM 2.1", [self.models_dir / "sam"])
+                cfg, sd = W.sam2_model_and_state(self.synthetic_seed, os.environ.get("MTB200_SAM_VARIANT", "tiny"))
             net = Sam2B200(sd, cfg, dev, precision=self.precision)
             self.models[ModelType.SAM2] = (Sam2ProcessorB200(net), Sam2ModelB200(net))
             return self.models[ModelType.SAM2]
@@ -153,9 +204,14 @@ class ModelManager:
                 return self.models[mt]
             from mangatranslator_b200.rcan import RcanB200
             dev = self._require_cuda()
-            sd = self._load_file_state_dict(self.model_paths[mt])
-            if sd is None:
-                log_message("Upscaler: no checkpoint on disk, using seeded synthetic RCAN weights", verbose=verbose)
+            try:
+                sd = self._load_file_state_dict(self.model_paths[mt])
+            except Exception as e:
+                raise ModelError(f"Upscaler: failed to read {self.model_paths[mt]}: {e}") from e
+            if sd is not None:
+                log_message(f"Upscaler ({mt.value}): weights from {self.model_paths[mt]}", always_print=True)
+            else:
+                self._synthetic_or_raise(f"Upscaler ({mt.value})", [self.model_paths[mt]])
                 lite = mt == ModelType.UPSCALE_LITE        # "_PU": pixel-unshuffle x2 in front of a shallower body
                 sd = W.rcan_state_dict(self.synthetic_seed, n_resblocks=6 if lite else 20, n_resgroups=4 if lite else 10,
                                        unshuffle=2 if lite else 1)

@@ -122,10 +122,11 @@ def yolo_state_dict(seed: int = 0, cfg: Optional[dict] = None) -> Dict[str, torc
         for br, hcx, oc in (("cv2", c2h, 64), ("cv3", c3h, nc), ("cv4", c4h, nm)):
             conv(f"head.{br}.{i}.0.conv", x, hcx, 3)
             conv(f"head.{br}.{i}.1.conv", hcx, hcx, 3)
-            conv(f"head.{br}.{i}.2", hcx, oc, 1, gain=0.05)
-        # class head: tiny gain and a negative bias so that (like a trained detector on a clean page) only a handful of
-        # anchors, not thousands, clear conf=0.6; stage-level runs inject the page's ground-truth boxes anyway
-        sd[f"head.cv3.{i}.2.weight"] *= 0.02
+            conv(f"head.{br}.{i}.2", hcx, oc, 1, gain=0.2 if br == "cv2" else 0.05)
+        # class head: logits of about -4 +- 1.5, so that (like a trained detector on a clean page) a handful of anchors,
+        # not thousands, clear conf=0.6 and the scores differ from anchor to anchor by far more than the numerical noise;
+        # stage-level runs inject the page's ground-truth boxes anyway
+        sd[f"head.cv3.{i}.2.weight"] *= 5.0
         sd[f"head.cv3.{i}.2.bias"] = torch.full((nc,), -4.0)
     npr = c(cfg["npr"])
     conv("head.proto.cv1.conv", c256, npr, 3)
@@ -136,15 +137,170 @@ def yolo_state_dict(seed: int = 0, cfg: Optional[dict] = None) -> Dict[str, torc
     return sd
 
 
+# ---- ultralytics checkpoints (the reference's detector files: core/ml/model_manager.py:183-190, 711-743) -----------------
+class UnsupportedCheckpoint(ValueError):
+    pass
+
+
+def synthetic_allowed() -> bool:
+    """Seeded synthetic weights are an explicit opt-in (tests, bench, smoke): a missing checkpoint is an error otherwise."""
+    return os.environ.get("MTB200_SYNTHETIC_WEIGHTS", "0") == "1"
+
+
+def load_ultralytics_state_dict(path: str):
+    """State dict (+ class names) of an ultralytics `.pt` without ultralytics installed.
+
+    `YOLO(path)` unpickles `ckpt["model"]`, an `ultralytics.nn.tasks.SegmentationModel` object.  Here the pickle is read
+    with an Unpickler that resolves torch / numpy / builtin classes normally and replaces every `ultralytics.*` (and any
+    other unknown) class by an inert attribute bag, then the module tree (`_modules` / `_parameters` / `_buffers`) is
+    walked into the flat `model.N....` names a state dict has.  Nothing from the file is executed.  Plain state-dict
+    files (a dict of tensors, or {"model": state_dict}) are accepted as they are."""
+    import pickle
+
+    class _Bag:
+        def __init__(self, *a, **k):
+            pass
+
+        def __setstate__(self, state):
+            if isinstance(state, dict):
+                self.__dict__.update(state)
+            elif isinstance(state, tuple) and len(state) == 2 and isinstance(state[1], dict):
+                self.__dict__.update(state[0] or {})
+                self.__dict__.update(state[1])
+
+        def __call__(self, *a, **k):
+            return self
+
+    _safe_roots = ("torch", "collections", "numpy", "builtins", "_codecs", "copyreg", "pathlib", "__builtin__")
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module.split(".")[0] in _safe_roots and not (module == "builtins" and name in ("eval", "exec", "compile", "open",
+                                                                                          "__import__", "getattr", "setattr")):
+                try:
+                    return super().find_class(module, name)
+                except Exception:
+                    pass
+            return type(name, (_Bag,), {"__module__": module})
+
+    class _PickleModule:
+        Unpickler = _Unpickler
+        load = staticmethod(lambda f, **kw: _Unpickler(f, **kw).load())
+        __name__ = "pickle"
+
+    obj = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_PickleModule)
+    names = None
+    root = obj
+    if isinstance(obj, dict):
+        root = obj.get("ema") or obj.get("model") or obj
+        if isinstance(root, dict) and all(torch.is_tensor(v) for v in root.values()):
+            return {k: v.float() for k, v in root.items()}, obj.get("names")
+        if isinstance(obj, dict) and all(torch.is_tensor(v) for v in obj.values()):
+            return {k: v.float() for k, v in obj.items()}, None
+    names = getattr(root, "names", None)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def walk(mod, prefix):
+        d = getattr(mod, "__dict__", {})
+        for store in ("_parameters", "_buffers"):
+            for k, v in (d.get(store) or {}).items():
+                if v is not None and torch.is_tensor(v):
+                    sd[prefix + k] = v.detach().float()
+        for k, sub in (d.get("_modules") or {}).items():
+            if sub is not None:
+                walk(sub, prefix + k + ".")
+
+    walk(root, "")
+    if not sd:
+        raise UnsupportedCheckpoint(f"{path}: no tensors found in the checkpoint")
+    return sd, (dict(names) if isinstance(names, dict) else names)
+
+
+def yolo_from_ultralytics(sd: Dict[str, torch.Tensor], names=None):
+    """ultralytics YOLOv8-seg state dict (`model.N.conv.weight`, `model.N.bn.*`, `model.22.cv2/cv3/cv4/proto`) ->
+    (state dict in this package's layout with BatchNorm folded into the convs, cfg).  Raises UnsupportedCheckpoint for
+    other families (YOLO11's C3k2 / C2PSA blocks, detection-only heads, ...).  What ultralytics itself does at first
+    predict (`model.fuse()`): w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps), eps = 1e-3."""
+    if any(k.startswith("model.model.") for k in sd):
+        sd = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
+    keys = set(sd)
+    if "model.0.conv.weight" not in keys:
+        raise UnsupportedCheckpoint("not an ultralytics detection checkpoint (no model.0.conv.weight)")
+    if any(".attn." in k or ".m.0.m." in k or k.startswith("model.23.") for k in keys):
+        raise UnsupportedCheckpoint("YOLO11 / YOLO12 layout (C3k2 / C2PSA / A2C2f blocks): only YOLOv8-seg checkpoints are "
+                                    "supported by the speech-bubble detector of this build")
+    if "model.22.proto.cv1.conv.weight" not in keys or "model.22.cv4.0.2.weight" not in keys:
+        raise UnsupportedCheckpoint("not a YOLOv8 *segmentation* checkpoint (no model.22.proto / cv4 mask branch)")
+    eps = 1e-3
+
+    def fold(src: str):
+        w = sd[src + ".conv.weight"].float()
+        if src + ".bn.weight" in keys:
+            g, b = sd[src + ".bn.weight"].float(), sd[src + ".bn.bias"].float()
+            m, v = sd[src + ".bn.running_mean"].float(), sd[src + ".bn.running_var"].float()
+            k = g / torch.sqrt(v + eps)
+            return w * k.view(-1, 1, 1, 1), b - m * k
+        bias = sd.get(src + ".conv.bias")                    # an already fused export
+        return w, (bias.float() if bias is not None else torch.zeros(w.shape[0]))
+
+    out: Dict[str, torch.Tensor] = {}
+
+    def put(dst: str, src: str):
+        out[dst + ".conv.weight"], out[dst + ".conv.bias"] = fold(src)
+
+    def c2f(i: int):
+        put(f"l{i}.cv1", f"model.{i}.cv1")
+        put(f"l{i}.cv2", f"model.{i}.cv2")
+        j = 0
+        while f"model.{i}.m.{j}.cv1.conv.weight" in keys:
+            put(f"l{i}.m.{j}.cv1", f"model.{i}.m.{j}.cv1")
+            put(f"l{i}.m.{j}.cv2", f"model.{i}.m.{j}.cv2")
+            j += 1
+        return j
+
+    for i in (0, 1, 3, 5, 7, 16, 19):
+        put(f"l{i}", f"model.{i}")
+    nb = {i: c2f(i) for i in (2, 4, 6, 8, 12, 15, 18, 21)}
+    put("l9.cv1", "model.9.cv1")
+    put("l9.cv2", "model.9.cv2")
+    for br in ("cv2", "cv3", "cv4"):
+        for lvl in range(3):
+            for k in (0, 1):
+                put(f"head.{br}.{lvl}.{k}", f"model.22.{br}.{lvl}.{k}")
+            out[f"head.{br}.{lvl}.2.weight"] = sd[f"model.22.{br}.{lvl}.2.weight"].float()
+            out[f"head.{br}.{lvl}.2.bias"] = sd[f"model.22.{br}.{lvl}.2.bias"].float()
+    for k in ("cv1", "cv2", "cv3"):
+        put(f"head.proto.{k}", f"model.22.proto.{k}")
+    out["head.proto.upsample.weight"] = sd["model.22.proto.upsample.weight"].float()
+    out["head.proto.upsample.bias"] = sd["model.22.proto.upsample.bias"].float()
+    # scale: width from the stem, depth from the bottleneck counts, as ultralytics' yaml scales define them
+    c0 = out["l0.conv.weight"].shape[0]
+    table = {16: "n", 32: "s", 48: "m", 64: "l", 80: "x"}
+    if c0 not in table:
+        raise UnsupportedCheckpoint(f"unknown YOLOv8 width (stem has {c0} channels)")
+    cfg = yolo_cfg(table[c0], nc=int(out["head.cv3.0.2.weight"].shape[0]))
+    cfg["nm"] = int(out["head.cv4.0.2.weight"].shape[0])
+    # npr is stored un-scaled in the cfg (YoloB200 / the oracle apply the width multiple): invert c(x) = ceil(x*w/8)*8
+    npr_scaled = int(out["head.proto.cv1.conv.weight"].shape[0])
+    cfg["npr"] = next((n for n in (256, 128, 64, 32, 512) if int(math.ceil(min(n, cfg["max_ch"]) * cfg["width"] / 8) * 8) == npr_scaled),
+                      None)
+    if cfg["npr"] is None:
+        raise UnsupportedCheckpoint(f"unexpected prototype width {npr_scaled}")
+    d = lambda n: max(round(n * cfg["depth"]), 1)
+    expect = {2: d(3), 4: d(6), 6: d(6), 8: d(3), 12: d(3), 15: d(3), 18: d(3), 21: d(3)}
+    if nb != expect:
+        raise UnsupportedCheckpoint(f"bottleneck counts {nb} do not match YOLOv8{table[c0]}-seg {expect}")
+    if int(out["head.cv2.0.2.weight"].shape[0]) != 64:
+        raise UnsupportedCheckpoint("DFL with reg_max != 16 is not supported")
+    return out, cfg
+
+
 # ---- SAM 2.1 ----------------------------------------------------------------------------------------------------------
 def sam2_model_and_state(seed: int = 0, variant: str = "tiny"):
-    """(config, state_dict).  Initialisation and (when a checkpoint directory exists) loading go through the same
-    library the reference uses (`transformers`, core/ml/model_manager.py:996-1005); no forward pass happens here."""
+    """(config, state_dict) of seeded SYNTHETIC weights, initialised by the library the reference uses (`transformers`,
+    core/ml/model_manager.py:996-1005); no forward pass happens here.  Real checkpoints are resolved by
+    ModelManager.load_sam2."""
     from transformers import Sam2Config, Sam2Model
-    d = models_dir()
-    if d and os.path.isdir(os.path.join(d, "sam")):
-        m = Sam2Model.from_pretrained(os.path.join(d, "sam"))
-        return m.config, m.state_dict()
     torch.manual_seed(seed)
     if variant == "tiny":
         cfg = Sam2Config()

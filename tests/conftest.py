@@ -9,6 +9,11 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 
+# No checkpoint exists offline: the tests run the loaders with seeded synthetic weights, which is an explicit opt-in
+# (without it ModelManager raises for a missing checkpoint; tests/test_weights_host.py checks that).
+os.environ.setdefault("MTB200_SYNTHETIC_WEIGHTS", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -1,0 +1,205 @@
+"""GPU: stage-by-stage parity AT THE BENCHMARKED CONFIGURATION (BASELINE.json configs[2]: 1536x1024 page, YOLOv8m-seg @1600,
+SAM 2.1-tiny with the page's prompts, bit-exact cleaning, RCAN 10 x 20 whole frame) against CPU-oracle fixtures generated
+once by oracle/gen_golden_fullsize.py (tests/golden/fullsize_golden.npz; the full-depth RCAN alone takes minutes on the
+CPU, which is why the vectors are committed instead of recomputed here).
+
+Every stage is fed the ORACLE's output of the stage before it, so one stage's float noise cannot hide in the next, and
+every comparison reports what it measured: max-abs errors for float tensors (bound 1e-3 abs, BASELINE.json north_star),
+and COUNTS — not fractions — for index / bit results: NMS anchor ids must be identical, mask bits must be identical
+outside the pixels whose oracle logit is within 2e-3 of zero, and the number of flipped bits inside that band is bounded
+by the band itself and printed."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-3
+
+
+def sha(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def G():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "fullsize_golden.npz"))
+    meta = json.loads(bytes(g["meta"]).decode())
+    return g, meta
+
+
+@pytest.fixture(scope="module")
+def setup(G):
+    from mangatranslator_b200 import synth
+    from mangatranslator_b200.core.ml.model_manager import get_model_manager
+    from mangatranslator_b200.core.pipeline import HotPathPipeline
+    g, meta = G
+    mm = get_model_manager()
+    mm.unload_all()
+    pipe = HotPathPipeline(seg_model="sam2", upscale=True, upscale_model="model")     # the bench's models (seed 0)
+    pg = synth.make_page(meta["seed"], meta["H"], meta["W"], n_bubbles=12)
+    bgr = np.ascontiguousarray(pg.image_rgb[:, :, ::-1])
+    assert sha(bgr) == meta["page_sha256"], "synthetic page generator changed: regenerate the fixtures"
+    page = torch.from_numpy(bgr).cuda()
+    yield pipe, pg, page
+    mm.unload_all()
+
+
+def _unpack(bits, w):
+    return np.unpackbits(bits, axis=-1)[..., :w].astype(bool)
+
+
+def test_detector_head_tensors_at_1600(G, setup):
+    from mangatranslator_b200.preproc import letterbox_device
+    g, meta = G
+    pipe, pg, page = setup
+    lb = letterbox_device(page, meta["imgsz"], swap_rb=True)
+    assert list(lb.shape[:2]) == meta["letterbox_hw"]
+    gr = pipe.yolo.forward_letterboxed(lb)
+    torch.cuda.synchronize()
+    step = meta["anchor_step"]
+    worst = {}
+    for i, (box, cls, mc, fh, fw, st) in enumerate(gr["levels"]):
+        a = fh * fw
+        cls_g = cls[0, :, :, :1].reshape(a, 1).t().cpu().numpy()
+        box_g = box[0].reshape(a, 64).t().cpu().numpy()
+        mc_g = mc[0].reshape(a, -1).t().cpu().numpy()
+        worst[f"cls{i}"] = float(np.abs(cls_g - g[f"yolo_cls_{i}"]).max())
+        worst[f"box{i}"] = float(np.abs(box_g[:, ::step] - g[f"yolo_box_{i}"]).max())
+        worst[f"mc{i}"] = float(np.abs(mc_g[:, ::step] - g[f"yolo_mc_{i}"]).max())
+        # float64 checksums of the FULL tensors (every anchor), relative to the sum of magnitudes (bf16x3 products carry a
+        # ~2^-16 relative error that does not average out completely over ~1e6 values: measured 2.4e-5)
+        s_box, a_box, s_mc, a_mc = meta[f"yolo_sum_{i}"]
+        worst[f"sum_box{i}_rel"] = abs(float(box.double().sum()) - s_box) / a_box
+        worst[f"sum_mc{i}_rel"] = abs(float(mc.double().sum()) - s_mc) / a_mc
+    ps = meta["proto_step"]
+    proto = gr["proto"][0].permute(2, 0, 1)
+    worst["proto"] = float((proto[:, ::ps, ::ps].cpu() - torch.from_numpy(g["yolo_proto"])).abs().max())
+    s_p, a_p = meta["yolo_proto_sum"]
+    worst["sum_proto_rel"] = abs(float(proto.double().sum()) - s_p) / a_p
+    print("YOLOv8m@1600 head tensors, max abs error vs CPU oracle:", {k: f"{v:.2e}" for k, v in worst.items()})
+    # prototypes reach |v| ~ 50-100 with the seeded weights: their bound is relative to that magnitude
+    pmag = float(np.abs(g["yolo_proto"]).max())
+    for k, v in worst.items():
+        bound = 1e-4 if k.startswith("sum_") else TOL * max(1.0, pmag / 10.0) if k == "proto" else TOL
+        assert v < bound, (k, v, bound)
+
+
+def test_detector_nms_indices_at_1600(G, setup):
+    from mangatranslator_b200.preproc import letterbox_device
+    g, meta = G
+    pipe, pg, page = setup
+    mg = meta["yolo_margins"]
+    lb = letterbox_device(page, meta["imgsz"], swap_rb=True)
+    gr = pipe.yolo.forward_letterboxed(lb)
+    det, cnt, _ = pipe.yolo.detect(gr, meta["yolo_conf"], (meta["H"], meta["W"]), tuple(lb.shape[:2]), apply_reference_dedup=False)
+    torch.cuda.synchronize()
+    n = int(cnt[0])
+    d = det[:n].cpu()
+    ref_anchors = torch.from_numpy(g["yolo_det_anchors"])
+    print(f"NMS at conf {meta['yolo_conf']:.6f}: {n} kept (oracle {len(ref_anchors)}); oracle margins {mg}")
+    assert n == len(ref_anchors)
+    assert torch.equal(d[:, 6].long(), ref_anchors), "NMS anchor ids differ"            # bit-exact indices, in score order
+    e_box = float((d[:, :4] - torch.from_numpy(g["yolo_det_xyxy"])).abs().max())
+    e_conf = float((d[:, 4] - torch.from_numpy(g["yolo_det_conf"])).abs().max())
+    print(f"boxes max abs {e_box:.2e} px, scores max abs {e_conf:.2e}")
+    assert e_box < 2e-2 and e_conf < 1e-4          # boxes span up to 1536 px: 2e-2 px is 1.3e-5 of the range
+    masks = pipe.yolo.retina_masks(gr, det, None, n, (meta["H"], meta["W"]), tuple(lb.shape[:2]))
+    got_px = masks.reshape(n, -1).sum(1).cpu().numpy().astype(np.int64)
+    diff = np.abs(got_px - g["yolo_det_mask_pixels"])
+    print("retina mask pixel counts, |got - oracle| per detection:", diff.tolist())
+    assert int(diff.sum()) <= max(8, int(1e-4 * g["yolo_det_mask_pixels"].sum()))
+
+
+def test_segmenter_masks_for_the_page_prompts(G, setup):
+    g, meta = G
+    pipe, pg, page = setup
+    H, W = meta["H"], meta["W"]
+    net = pipe.sam[1].net
+    prompts = torch.from_numpy(g["sam_prompts"])
+    enc = net.encode(page[:, :, [2, 1, 0]].contiguous())
+    masks, logits, sel, lo, iou = net.decode(enc, prompts, (H, W), want_logits=True)
+    torch.cuda.synchronize()
+    P = prompts.shape[0]
+    S = int(round((logits.shape[2]) ** 0.5))
+    low = torch.gather(logits, 1, sel.long().view(-1, 1, 1).expand(-1, 1, S * S)).view(P, S, S)
+    ls = meta["lowres_step"]
+    e_low = float((low[:, ::ls, ::ls].cpu() - torch.from_numpy(g["sam_lowres"])).abs().max())
+    ref_iou = torch.from_numpy(g["sam_iou"])
+    got_iou = torch.gather(iou, 1, sel.long().view(-1, 1)).cpu() if iou.shape[1] != ref_iou.shape[1] else iou.cpu()
+    e_iou = float((got_iou - ref_iou).abs().max())
+    ref = _unpack(g["sam_masks_bits"], W)
+    band = _unpack(g["sam_band_bits"], W)
+    got = masks.cpu().numpy() > 0
+    flips = got != ref
+    outside = int((flips & ~band).sum())
+    inside = int((flips & band).sum())
+    print(f"SAM 2.1-tiny, {P} prompts at {H}x{W}: low-res logits max abs {e_low:.2e}, IoU head {e_iou:.2e}; mask bits flipped: "
+          f"{outside} outside the |logit| < 2e-3 band, {inside} of {int(band.sum())} band pixels ({ref.sum()} mask pixels)")
+    assert e_low < TOL and e_iou < TOL
+    assert outside == 0
+    assert inside <= int(band.sum())
+
+
+@pytest.fixture(scope="module")
+def cleaned_from_oracle_masks(G, setup):
+    """The cleaning stage on the ORACLE's masks (so its input is bit-identical to what the CPU path cleaned)."""
+    from mangatranslator_b200.core.image.cleaning import clean_pages_device
+    g, meta = G
+    pipe, pg, page = setup
+    H, W = meta["H"], meta["W"]
+    dm = _unpack(g["det_masks_bits"], W)
+    dets = []
+    for k, bb in enumerate(meta["det_bboxes"]):
+        d = {"bbox": tuple(bb), "sam_mask": torch.from_numpy(dm[k].astype(np.uint8) * 255).cuda()}
+        if meta["det_neighbors"][k]:
+            d["conjoined_neighbor_bboxes"] = [tuple(nb) for nb in meta["det_neighbors"][k]]
+        dets.append(d)
+    batch = clean_pages_device([page], [dets], processing_scale=(H * W / 1e6) ** 0.5)
+    torch.cuda.synchronize()
+    return batch
+
+
+def test_cleaning_is_bit_exact_on_the_oracle_masks(G, setup, cleaned_from_oracle_masks):
+    g, meta = G
+    batch = cleaned_from_oracle_masks
+    cleaned = batch.pages_out[0].cpu().numpy()
+    ok = [(di, r) for di, r in enumerate(batch.results[0]) if r is not None and r.status == 0]
+    print(f"cleaning: {len(ok)} of {len(batch.results[0])} bubbles cleaned (oracle {len(meta['bubbles'])}); page sha "
+          f"{sha(cleaned)[:16]} vs {meta['cleaned_sha256'][:16]}")
+    assert len(ok) == len(meta["bubbles"])
+    for (di, r), b in zip(ok, meta["bubbles"]):
+        assert [int(v) for v in r.fill_bgr][:3] == b["color"][:3]
+        m = batch.export_mask(0, di).cpu().numpy()
+        assert int((m > 0).sum()) == b["mask_pixels"] and sha(m) == b["mask_sha256"]
+    assert sha(cleaned) == meta["cleaned_sha256"]                                      # every byte of the page
+
+
+def test_full_depth_rcan_whole_frame(G, setup, cleaned_from_oracle_masks):
+    g, meta = G
+    pipe, pg, page = setup
+    cleaned = cleaned_from_oracle_masks.pages_out[0]
+    assert sha(cleaned.cpu().numpy()) == meta["cleaned_sha256"]
+    out_u8, out_f = pipe.rcan.upscale_u8(cleaned, swap_rb=True, want_float=True)
+    torch.cuda.synchronize()
+    assert pipe.rcan.cfg["n_resgroups"] == 10 and pipe.rcan.cfg["n_resblocks"] == 20
+    y = out_f.permute(2, 0, 1).cpu()                                                   # [3][2H][2W]
+    us, T = meta["up_step"], meta["tile"]
+    e_grid = float((y[:, ::us, ::us] - torch.from_numpy(g["up_grid"])).abs().max())
+    e_tile, lsb = 0.0, 0
+    u8 = out_u8.cpu().numpy()
+    for k, (a, b) in enumerate(meta["up_tiles"]):
+        e_tile = max(e_tile, float((y[:, a:a + T, b:b + T] - torch.from_numpy(g["up_tiles_f"][k])).abs().max()))
+        d = np.abs(u8[a:a + T, b:b + T].astype(int) - g["up_tiles_u8"][k].astype(int))
+        assert d.max() <= 1
+        lsb += int((d > 0).sum())
+    n_u8 = len(meta["up_tiles"]) * T * T * 3
+    print(f"RCAN 10x20 ({pipe.rcan.precision}) on the 1536x1024 page: float output max abs error {e_grid:.2e} on the "
+          f"{us}-pixel grid, {e_tile:.2e} in the {len(meta['up_tiles'])} full tiles (output range {meta['up_range']}); uint8: "
+          f"{lsb} of {n_u8} tile values differ, each by 1 LSB")
+    assert e_grid < TOL and e_tile < TOL
+    assert lsb <= n_u8 // 200
