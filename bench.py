@@ -82,12 +82,27 @@ def make_pages(n_distinct: int, seed0: int):
     return pages
 
 
+_CPU_PIPE = {}
+RCAN_CROP = 256            # fixed, host-independent: the CPU arm's RCAN sample (see cpu_baseline)
+
+
+def _cpu_pipe():
+    """The CPU pipeline (oracle modules with the bench's seeded weights) is built once per process."""
+    if "pipe" not in _CPU_PIPE:
+        import pipeline_oracle
+        pipe = pipeline_oracle.CpuPipeline(0)
+        _CPU_PIPE["pipe"] = pipe
+        _CPU_PIPE["threads"] = _best_threads(pipe)
+    torch.set_num_threads(_CPU_PIPE["threads"])
+    return _CPU_PIPE["pipe"], _CPU_PIPE["threads"]
+
+
 def _best_threads(pipe) -> int:
-    """The oracle's torch ops scale badly past a few dozen threads on big hosts: pick the fastest of a few settings on
-    one SAM-encoder-sized probe (bounded: a few seconds)."""
+    """torch's CPU convolutions scale badly past a few dozen threads on big hosts: pick the fastest of a few settings on a
+    short RCAN probe (a few seconds, once per process)."""
     cores = os.cpu_count() or 1
     cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
-    x = torch.rand(1, 3, 512, 512)
+    x = torch.rand(1, 3, RCAN_CROP, RCAN_CROP)
     best, best_t = cands[-1], 1e9
     for c in cands:
         torch.set_num_threads(c)
@@ -95,7 +110,7 @@ def _best_threads(pipe) -> int:
             pipe.rcan.head(x)
             t0 = time.perf_counter()
             y = pipe.rcan.head(x)
-            for blk in list(pipe.rcan.body[0].body)[:2]:
+            for blk in list(pipe.rcan.body[0].body)[:4]:
                 y = blk(y)
             dt = time.perf_counter() - t0
         if dt < best_t:
@@ -104,28 +119,32 @@ def _best_threads(pipe) -> int:
     return best
 
 
-def cpu_baseline(sample_pages: int = 1, crop: int = 0):
-    """The reference's CPU pipeline (oracle, same weights) on a bounded sample: `sample_pages` full pages through
-    detect/segment/clean, the RCAN on a centre crop scaled by the pixel ratio."""
-    import pipeline_oracle
+def cpu_baseline(sample_pages: int = 1, page_seed: int = 9000):
+    """The reference's CPU pipeline (oracle port, same seeded weights) on a bounded sample of the workload:
+    `sample_pages` pages through detect / segment / clean IN FULL at 1536x1024, and the RCAN on a fixed 256x256 centre crop
+    of the cleaned page.  The RCAN's cost is proportional to the pixel count (every layer is a 3x3 conv at input
+    resolution; measured here: 215-254 s for the whole frame on 8 cores = 24.6x the crop), so its page time is the crop
+    time x (H*W / 256^2) — stated as `extrapolated` with the factor; everything else is measured."""
     from mangatranslator_b200 import synth
     cores = os.cpu_count() or 1
-    if crop <= 0:
-        crop = 512 if cores >= 32 else 192
-    pipe = pipeline_oracle.CpuPipeline(0)
-    threads = _best_threads(pipe)
-    tot = 0.0
-    stages = {}
+    pipe, threads = _cpu_pipe()
+    tot, wall, stages = 0.0, 0.0, {}
     for i in range(sample_pages):
-        pg = synth.make_page(9000 + i, H, W, n_bubbles=BUBBLES)
-        r = pipe.run_page(pg.image_rgb, pg.boxes_xyxy, upscale_crop=crop)
+        pg = synth.make_page(page_seed + i, H, W, n_bubbles=BUBBLES)
+        t0 = time.perf_counter()
+        r = pipe.run_page(pg.image_rgb, pg.boxes_xyxy, upscale_crop=RCAN_CROP)
+        wall += time.perf_counter() - t0
         tot += r["times"]["total"]
         for k, v in r["times"].items():
             stages[k] = stages.get(k, 0.0) + v / sample_pages
+    factor = H * W / float(RCAN_CROP * RCAN_CROP)
     return dict(value=sample_pages / tot, unit="pages/s", cores=threads, kind="port",
-                sample=f"{sample_pages} page(s) 1536x1024: YOLOv8m-seg@1600 + SAM2.1-tiny (12 boxes) + cv2 clean in full, "
-                       f"RCAN(10x20,64) on a {crop}x{crop} crop scaled by pixel ratio {H * W / crop / crop:.0f}x; "
-                       f"{threads} torch threads (fastest of a probe) on a {cores}-core host",
+                sample=f"{sample_pages} page(s) 1536x1024: YOLOv8m-seg@1600 + SAM2.1-tiny (12 boxes) + cv2 clean measured in full; "
+                       f"RCAN(10x20,64) measured on a {RCAN_CROP}x{RCAN_CROP} crop and scaled by the pixel ratio {factor:.1f}; "
+                       f"{threads} torch threads on a {cores}-core host",
+                extrapolated=True, extrapolation=dict(stage="upscale", factor=round(factor, 2), measured_s=round(stages["upscale"] / factor, 3),
+                                                      why="whole-frame 10x20 RCAN takes minutes per page on the host cores"),
+                sample_wall_s=round(wall / sample_pages, 3),
                 stage_seconds={k: round(v, 3) for k, v in stages.items()})
 
 
@@ -198,20 +217,27 @@ def _rcan_forward_on(rcan, dev):
 
 
 def run_reference(args, coord):
+    """The reference arm: the CPU pipeline on the box's host cores, rank 0 only.  One step = one bounded sample (one page:
+    detect / segment / clean in full, the RCAN on the fixed crop); `ms_per_step` is the WALL time of a step as it ran, and
+    `value` the pages/s that follow from the per-page time with the RCAN scaled to the whole frame (`extrapolated`)."""
     if coord.rank != 0:
         return
-    vals = []
+    vals, walls = [], []
     for s in range(args.warmup + args.steps):
-        b = cpu_baseline(sample_pages=1)
+        t0 = time.perf_counter()
+        b = cpu_baseline(sample_pages=1, page_seed=9000 + s)
         if s >= args.warmup:
             vals.append(b)
+            walls.append(time.perf_counter() - t0)
     v = float(np.mean([b["value"] for b in vals]))
     base = vals[-1]
     base["value"] = v
     line = dict(metric=METRIC, value=v, unit="pages/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1000.0 / v, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",
-                data="synthetic", impl="reference",
-                config=dict(workload=WORKLOAD, sample_per_step=base["sample"]),
+                ms_per_step=1000.0 * float(np.mean(walls)), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",
+                data="synthetic", impl="reference", extrapolated=True,
+                config=dict(workload=WORKLOAD, sample_per_step=base["sample"],
+                            note="value = 1 / (measured detect + segment + clean seconds + crop RCAN seconds x pixel ratio); "
+                                 "ms_per_step = wall time of one sample step, not of a 64-page batch"),
                 cpu_baseline=base, e2e=dict(value=v, unit="pages/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 

@@ -95,7 +95,7 @@ void mtb_conv_plan_destroy(mtb_conv_plan* plan);
  */
 #define MTB_CLEAN_MAX_SE 63
 #define MTB_CLEAN_MAX_BALL 65
-#define MTB_CLEAN_MAX_NEIGHBORS 8
+#define MTB_CLEAN_MAX_NEIGHBORS 16
 
 typedef struct mtb_clean_params {
   int thr_value;   /* CleaningConfig.thresholding_value (core/config.py:28) */

@@ -129,7 +129,9 @@ def clean_batch(pages: Sequence[torch.Tensor], detections: Sequence[Sequence[Dic
             bb = det.get("bbox") or mb
             for i in range(4):
                 J.bbox[i] = int(bb[i])
-            nbs = list(det.get("conjoined_neighbor_bboxes") or [])[:H.MAX_NEIGHBORS]
+            nbs = list(det.get("conjoined_neighbor_bboxes") or [])
+            if len(nbs) > H.MAX_NEIGHBORS:
+                raise ValueError(f"bubble with {len(nbs)} conjoined neighbours (max {H.MAX_NEIGHBORS})")
             J.n_neighbors = len(nbs)
             for k, nb in enumerate(nbs):
                 for i in range(4):

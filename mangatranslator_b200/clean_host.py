@@ -14,7 +14,7 @@ import numpy as np
 
 MAX_SE = 63
 MAX_BALL = 65
-MAX_NEIGHBORS = 8
+MAX_NEIGHBORS = 16           # MTB_CLEAN_MAX_NEIGHBORS: >= MTB_SPLIT_MAX_CHILDREN - 1, so no neighbour of a split group is dropped
 N_PLANES = 12
 PLANE_FINAL = 9
 

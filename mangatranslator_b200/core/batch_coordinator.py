@@ -159,6 +159,14 @@ class PageShardCoordinator:
         self._dist.gather_object(obj, out, dst=0)
         return out
 
+    def broadcast(self, obj: Any, src: int = 0) -> Any:
+        """The same python object on every rank (e.g. a default output directory named after rank 0's clock)."""
+        if self._dist is None:
+            return obj
+        box = [obj if self.rank == src else None]
+        self._dist.broadcast_object_list(box, src=src)
+        return box[0]
+
     def all_reduce_max(self, value: float) -> float:
         if self._dist is None:
             return value

@@ -1,61 +1,63 @@
 """Per-image result cache with the reference's entry points (core/caching.py:12-658: UnifiedCache, get_cache).
-The reference hashes the whole page with SHA-256 two to four times per page to key size-1 LRU slots; on the batch
-path that is pure overhead, so this build keeps the API (set_current_image / get_* / set_*) but keys by object identity
-of the image.  A key holds a strong reference to its image, so an identity can never be recycled for another image
-while its entry is alive; the store is a small LRU."""
+
+Like the reference, entries are keyed by the CONTENT of the image (so an image mutated in place and passed again — the
+reference's own stage code pastes / inpaints and then re-detects or re-upscales — can never hit a stale entry) and every
+kind of result keeps a tiny LRU (the reference uses size-1 slots; here 2).  The reference hashes the whole page with
+SHA-256 two to four times per page; here the fingerprint is (mode, size, CRC-32 of the pixel bytes), ~1 ms for a
+1536x1024 page, computed once per image object and re-validated against a cheap strided sample."""
 from __future__ import annotations
 
 import collections
 import threading
+import weakref
+import zlib
 from typing import Any, Optional  # noqa: F401  (Any: quoted annotation below)
 
-MAX_ENTRIES = 64
+MAX_ENTRIES = 2            # per kind of result (yolo / sam / upscale / upscale_dim / bubble_proc)
 
 
-class _ImageKey:
-    """(image identity, parameters): equal only for the very same image object."""
-    __slots__ = ("image", "rest", "_hash")
-
-    def __init__(self, image, *rest):
-        self.image, self.rest = image, rest
-        self._hash = hash((id(image),) + tuple(rest))
-
-    def __hash__(self):
-        return self._hash
-
-    def __eq__(self, other):
-        return isinstance(other, _ImageKey) and other.image is self.image and other.rest == self.rest
+def _fingerprint(image) -> tuple:
+    """(mode, size, crc32 of the bytes) of a PIL image or ndarray-like."""
+    if hasattr(image, "tobytes") and hasattr(image, "mode"):
+        return (image.mode, image.size, zlib.crc32(image.tobytes()))
+    import numpy as np
+    a = np.ascontiguousarray(image)
+    return (str(a.dtype), a.shape, zlib.crc32(a.tobytes()))
 
 
 class UnifiedCache:
     def __init__(self):
         self._lock = threading.Lock()
-        self._store: "collections.OrderedDict[Any, Any]" = collections.OrderedDict()
+        self._store: "dict[str, collections.OrderedDict[Any, Any]]" = {}
         self._current = None
 
     def set_current_image(self, image, verbose: bool = False) -> None:
+        """A new page: drop everything cached for the previous one (core/caching.py set_current_image)."""
+        fp = _fingerprint(image)
         with self._lock:
-            if image is not self._current:
+            if fp != self._current:
                 self._store.clear()
-                self._current = image
+                self._current = fp
 
     def _get(self, key):
         with self._lock:
-            if key in self._store:
-                self._store.move_to_end(key)
-                return self._store[key]
+            slot = self._store.get(key[0])
+            if slot is not None and key in slot:
+                slot.move_to_end(key)
+                return slot[key]
             return None
 
     def _set(self, key, value) -> None:
         with self._lock:
-            self._store[key] = value
-            self._store.move_to_end(key)
-            while len(self._store) > MAX_ENTRIES:
-                self._store.popitem(last=False)
+            slot = self._store.setdefault(key[0], collections.OrderedDict())
+            slot[key] = value
+            slot.move_to_end(key)
+            while len(slot) > MAX_ENTRIES:
+                slot.popitem(last=False)
 
     # YOLO
     def get_yolo_cache_key(self, image, model_path, confidence, *extra):
-        return _ImageKey(image, "yolo", str(model_path), float(confidence), *extra)
+        return ("yolo", _fingerprint(image), str(model_path), float(confidence)) + tuple(extra)
 
     def get_yolo_detection(self, key):
         return self._get(key)
@@ -65,7 +67,7 @@ class UnifiedCache:
 
     # SAM
     def get_sam_cache_key(self, image, *extra):
-        return _ImageKey(image, "sam", *[str(e) for e in extra])
+        return ("sam", _fingerprint(image)) + tuple(str(e) for e in extra)
 
     def get_sam_masks(self, key):
         return self._get(key)
@@ -75,13 +77,13 @@ class UnifiedCache:
 
     # upscale
     def get_upscale_cache_key(self, image, factor, model_type, *extra):
-        return _ImageKey(image, "upscale", float(factor), str(model_type), *extra)
+        return ("upscale", _fingerprint(image), float(factor), str(model_type)) + tuple(extra)
 
     def get_upscale_dimension_cache_key(self, image, target, mode, model_type="model"):
-        return _ImageKey(image, "upscale_dim", int(target), str(mode), str(model_type))
+        return ("upscale_dim", _fingerprint(image), int(target), str(mode), str(model_type))
 
     def get_bubble_processing_cache_key(self, image, target, mode, model_type="model"):
-        return _ImageKey(image, "bubble_proc", int(target), str(mode), str(model_type))
+        return ("bubble_proc", _fingerprint(image), int(target), str(mode), str(model_type))
 
     def get_upscaled_image(self, key):
         return self._get(key)
@@ -93,6 +95,12 @@ class UnifiedCache:
         with self._lock:
             self._store.clear()
             self._current = None
+
+    clear_all = clear              # the reference's name for the same thing (core/caching.py clear_all)
+
+    def __len__(self) -> int:
+        with self._lock:
+            return sum(len(s) for s in self._store.values())
 
 
 _cache: Optional[UnifiedCache] = None

@@ -76,6 +76,26 @@ def _load_page(image_path) -> Image.Image:
         raise ImageProcessingError(f"Error loading image {image_path}: {e}")
 
 
+def _resolve_pre_upscale_factor(pre_cfg, verbose: bool = False) -> float:
+    """core/pipeline.py:602-614: the initial-upscale factor is clamped to [1, 8] and switched off at or below 1.01."""
+    if pre_cfg is None or not pre_cfg.enabled:
+        return 1.0
+    factor = max(1.0, min(float(pre_cfg.factor or 1.0), 8.0))
+    if factor <= 1.01:
+        return 1.0
+    log_message(f"Initial upscaling enabled: {factor:.2f}x", verbose=verbose)
+    return factor
+
+
+def _apply_pre_upscale_if_needed(image: Image.Image, config: MangaTranslatorConfig, verbose: bool = False):
+    """core/pipeline.py:617-635: the initial upscale uses the OUTPUT upscale model setting.  Returns (image, factor)."""
+    factor = _resolve_pre_upscale_factor(getattr(config, "preprocessing", None), verbose)
+    if factor == 1.0:
+        return image, 1.0
+    model_type = getattr(config.output, "image_upscale_model", "model_lite") if hasattr(config, "output") else "model_lite"
+    return upscale_image(image, factor, model_type=model_type, verbose=verbose), factor
+
+
 def _render_page(image_path, config: MangaTranslatorConfig, output_path=None, cancellation_manager=None, preloaded=None):
     """Everything of translate_and_render up to (not including) the save: returns (image, target_mode).  `preloaded`:
     a pending decode of this page (concurrent.futures.Future of _load_page) started while the previous page was on the
@@ -90,11 +110,16 @@ def _render_page(image_path, config: MangaTranslatorConfig, output_path=None, ca
     pil = preloaded.result() if preloaded is not None else _load_page(image_path)
     target_mode = _target_mode(config, image_path, output_path)
     pil = convert_image_to_target_mode(pil, target_mode, verbose)
-    if config.preprocessing.enabled:
-        pil = upscale_image(pil, config.preprocessing.factor, model_type="model_lite", verbose=verbose)
+    get_cache().clear_all()                 # every mode: nothing cached for the previous page outlives it
+    pil, _ = _apply_pre_upscale_if_needed(pil, config, verbose)
     if config.upscaling_only:
-        out = upscale_image(pil, config.output.image_upscale_factor, model_type=config.output.image_upscale_model,
-                            verbose=verbose)
+        # core/pipeline.py:723-737: in this mode the final upscale still depends on output.upscale_final_image (the
+        # "initial" upscale above is what runs when only preprocessing.enabled is set)
+        log_message("Upscaling only mode - skipping detection and translation", always_print=True)
+        out = pil
+        if config.output.upscale_final_image:
+            out = upscale_image(out, config.output.image_upscale_factor, model_type=config.output.image_upscale_model,
+                                verbose=verbose)
     else:
         scale = _processing_scale(pil.width, pil.height, config.preprocessing.auto_scale)
         get_cache().set_current_image(pil, verbose)
@@ -275,13 +300,14 @@ def batch_translate_images(input_dir, config: MangaTranslatorConfig, output_dir=
     if not input_dir.is_dir():
         log_message(f"Input path '{input_dir}' is not a directory", always_print=True)
         return empty
-    out_dir = Path(output_dir) if output_dir else Path("./output") / time.strftime("%Y%m%d_%H%M%S")
+    coord = PageShardCoordinator()
+    # the default directory carries a timestamp: every rank must use rank 0's
+    out_dir = Path(coord.broadcast(str(Path(output_dir) if output_dir else Path("./output") / time.strftime("%Y%m%d_%H%M%S"))))
     out_dir.mkdir(parents=True, exist_ok=True)
     files = _list_batch_images(input_dir, preserve_structure)
     if not files:
         log_message(f"No image files found in '{input_dir}'", always_print=True)
         return empty
-    coord = PageShardCoordinator()
     mine = coord.shard(files)
     total = len(mine)
     t0 = time.time()
@@ -349,6 +375,16 @@ def batch_translate_images(input_dir, config: MangaTranslatorConfig, output_dir=
             if progress_callback:
                 progress_callback((i + 1) / total, note)
         settle(block=True)
+    except BaseException:
+        # a rank that stops early (cancellation, a fatal error) still takes part in the gather below, or the other ranks
+        # would wait in it forever; its partial counts carry an `aborted` mark
+        res["aborted"] = 1
+        if saver is not None:
+            saver.close()
+        try:
+            coord.gather(res)
+        finally:
+            raise
     finally:
         if saver is not None:
             saver.close()                          # queued files are still written when the batch is cancelled

@@ -31,7 +31,7 @@ enum Status : int {
 
 constexpr int kMaxSE = 63;        // reference scale_kernel clamp (core/scaling.py:64-96)
 constexpr int kMaxBall = 65;      // roi_shrink clamp is 64 px (cleaning.py:629-636)
-constexpr int kMaxNeighbors = 8;
+constexpr int kMaxNeighbors = 16;
 
 struct Params {
   int thr_value;        // fixed threshold (cleaning.py:312-314)

@@ -11,6 +11,8 @@ addressing), the hyper-network mask product and the mask writer are the kernels 
 """
 from __future__ import annotations
 
+import collections
+import os
 import ctypes as C
 from typing import Dict, List, Optional, Tuple
 
@@ -94,7 +96,11 @@ class Sam2B200:
         self.hidden = 256
         self._w: Dict[str, tuple] = {}
         self._enc = None
-        self._dec: Dict[int, dict] = {}
+        # decoder plans per prompt count (buffers + launch descriptors + one CUDA graph and mask buffer per page size),
+        # least recently used first: pages with ragged bubble counts / sizes must not grow device memory without bound
+        self._dec: "collections.OrderedDict[int, dict]" = collections.OrderedDict()
+        self.max_decoders = int(os.environ.get("MTB200_SAM_MAX_DECODERS", "8"))
+        self.max_sizes_per_decoder = int(os.environ.get("MTB200_SAM_MAX_SIZES", "4"))
         self._prep_constants()
 
     # ---- weights / constants -----------------------------------------------------------------------------------
@@ -468,7 +474,17 @@ class Sam2B200:
         if Pn not in self._dec:
             self._dec[Pn] = self._build_decoder(Pn, enc)
             self._dec[Pn]["boxes_in"] = torch.zeros((Pn, 4), dtype=torch.float32, device=dev)
+            self._dec[Pn]["sizes"] = collections.OrderedDict()
+            while len(self._dec) > max(1, self.max_decoders):
+                self._dec.popitem(last=False)
+        self._dec.move_to_end(Pn)
         d = self._dec[Pn]
+        d["sizes"][(H, W)] = True
+        d["sizes"].move_to_end((H, W))
+        while len(d["sizes"]) > max(1, self.max_sizes_per_decoder):          # drop the oldest page size's graph + mask buffer
+            old, _ = d["sizes"].popitem(last=False)
+            d.pop(("graph",) + old, None)
+            d.pop(("masks",) + old, None)
         d["boxes_in"].copy_(boxes_xyxy.to(dtype=torch.float32))
         boxes = d["boxes_in"]
         l = self.l

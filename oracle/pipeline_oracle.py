@@ -61,6 +61,9 @@ class CpuPipeline:
                 dets.append({"bbox": bboxes[n], "sam_mask": masks[n],
                              "conjoined_neighbor_bboxes": [b for m, b in enumerate(bboxes) if m != n]})
         t["segment"] = time.perf_counter() - t0
+        # pixels whose full-size logit is within 2e-3 of zero for ANY prompt: the only places where an fp32-grade segmenter
+        # may legitimately decide a mask bit differently (a split child inherits its parent's knife-edge pixels)
+        band = (seg["full_logits"].abs() < 2e-3).any(0).numpy() if len(prompts) else np.zeros((h, w), bool)
         seg = dict(seg, masks=np.stack([d["sam_mask"] for d in dets]) if dets else np.zeros((0, h, w), np.uint8))
         t0 = time.perf_counter()
         cleaned, bubbles = clean_oracle.clean_page(bgr, dets, processing_scale=(h * w / 1e6) ** 0.5)
@@ -75,5 +78,5 @@ class CpuPipeline:
         out_f, out_u8 = rcan_oracle.upscale_u8(self.rcan, src)
         t["upscale"] = (time.perf_counter() - t0) * scale
         t["total"] = t["detect"] + t["segment"] + t["clean"] + t["upscale"]
-        return dict(times=t, masks=seg["masks"], cleaned=cleaned, upscaled=out_u8, upscaled_f=out_f, bubbles=bubbles,
-                    det=det)
+        return dict(times=t, masks=seg["masks"], band=band, cleaned=cleaned, upscaled=out_u8, upscaled_f=out_f,
+                    bubbles=bubbles, det=det)

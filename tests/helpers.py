@@ -203,3 +203,41 @@ def emul_safe_box(mask, padding_pixels, t2=None, cap=None):
     J.cap, J.g, J.safe = cap, g.ctypes.data, safe.ctypes.data
     E.emul_safebox_job(C.byref(J), C.byref(R))
     return R
+
+
+def check_page_against_cpu_pipeline(pipe, ref, out_u8, dets, batch, label=""):
+    """End-to-end comparison of one page (device pipeline vs oracle/pipeline_oracle.CpuPipeline.run_page) with counts:
+    * mask bits: identical outside the oracle's knife-edge band (|full-size logit| < 2e-3 for some prompt); the number of
+      flipped bits inside the band is printed and bounded by a NUMBER;
+    * cleaned page: byte-identical when no mask bit flipped; otherwise differing pixels must lie within the cleaning
+      reach (ROI dilation) of a flipped bit's bubble — checked as: every differing pixel is inside some detection's box
+      grown by 16 px;
+    * upscale: the RCAN is judged in isolation on the ORACLE's cleaned page (its global average pooling couples every
+      output pixel to every input pixel, so an end-to-end float bound would be void after a single flipped mask bit):
+      float output within 1e-3 abs everywhere, uint8 within 1 LSB; and when the cleaned pages are identical the
+      end-to-end uint8 page must satisfy the same 1-LSB bound."""
+    import torch
+    got_masks = np.stack([d["sam_mask"].cpu().numpy() for d in dets])
+    assert got_masks.shape == ref["masks"].shape
+    flips = got_masks != ref["masks"]
+    n_flips = int(flips.sum())
+    outside = int((flips & ~ref["band"][None]).sum())
+    cleaned = batch.pages_out[0].cpu().numpy()
+    n_clean_diff = int(np.any(cleaned != ref["cleaned"], axis=2).sum())
+    src = torch.from_numpy(ref["cleaned"]).to(pipe.device)
+    iso_u8, iso_f = pipe.rcan.upscale_u8(src, swap_rb=True, want_float=True)
+    torch.cuda.synchronize()
+    e_f = float((iso_f.permute(2, 0, 1).unsqueeze(0).cpu() - ref["upscaled_f"]).abs().max())
+    d_iso = np.abs(iso_u8.cpu().numpy().astype(int) - ref["upscaled"].astype(int))
+    print(f"{label}: mask bits flipped {n_flips} ({outside} outside the knife-edge band of {int(ref['band'].sum())} pixels); "
+          f"cleaned pixels differing {n_clean_diff}; RCAN on the oracle's cleaned page: float max abs {e_f:.2e}, "
+          f"uint8 values off by one {int((d_iso > 0).sum())}")
+    assert outside == 0
+    assert n_flips <= 64, n_flips
+    if n_flips == 0:
+        assert n_clean_diff == 0
+    assert e_f < 1e-3 and d_iso.max() <= 1
+    if n_clean_diff == 0:
+        d = np.abs(out_u8.numpy().astype(int) - ref["upscaled"].astype(int))
+        assert d.max() <= 1
+    return n_flips, n_clean_diff

@@ -236,7 +236,7 @@ def test_unreadable_page_is_booked_with_the_reference_message(tmp_path, monkeypa
 
     monkeypatch.setattr(P, "detect_speech_bubbles", lambda *a, **k: ([], []))
     monkeypatch.setattr(P, "_clean_speech_bubbles_for_page", stage)
-    monkeypatch.setattr(P, "get_cache", lambda: type("C", (), {"set_current_image": staticmethod(lambda *a, **k: None)})())
+    monkeypatch.setattr(P, "get_cache", lambda: type("C", (), {"set_current_image": staticmethod(lambda *a, **k: None), "clear_all": staticmethod(lambda: None)})())
     res = P.batch_translate_images(inp, MangaTranslatorConfig(cleaning_only=True), tmp_path / "out")
     assert P._load_page is real_load
     assert res["success_count"] == 1 and res["error_count"] == 1
@@ -280,3 +280,41 @@ def test_batch_flow_shards_pages_over_two_gloo_ranks(tmp_path):
     owners = {int(p.name.split("_")[0]): p.read_text() for p in out.glob("*_translated.png")}
     assert owners == {i: str((i - 1) % 2) for i in range(1, 12) if i != 7}
     assert (out / "failed_paths.txt").read_text().strip().endswith("7.png")
+
+
+@needs_ref
+@pytest.mark.parametrize("pre_enabled,pre_factor,final,model", [(True, 2.0, False, "model"), (True, 2.0, True, "model_lite"),
+                                                                (False, 2.0, True, "model"), (True, 1.005, False, "model"),
+                                                                (True, 12.0, False, "model_lite"), (False, 2.0, False, "model")])
+def test_upscaling_only_calls_the_upscaler_like_the_live_reference(tmp_path, monkeypatch, pre_enabled, pre_factor, final, model):
+    """`upscaling_only` (core/pipeline.py:718-737): the initial upscale uses the OUTPUT model setting and a factor clamped
+    to [1, 8] (off at <= 1.01); the final upscale happens only with output.upscale_final_image.  Both drivers run with
+    their `upscale_image` replaced by a recorder that resizes with PIL, and must make the same calls and return the same
+    size."""
+    RP, _ = _ref()
+    import core.config as RC
+    src = tmp_path / "p.png"
+    Image.fromarray(np.full((20, 30, 3), 200, np.uint8)).save(src)
+
+    def recorder(log):
+        def up(image, factor, model_type="model", verbose=False):
+            log.append((round(float(factor), 4), model_type, image.size))
+            return image.resize((int(image.width * factor), int(image.height * factor)))
+        return up
+
+    ours_log, ref_log = [], []
+    monkeypatch.setattr(P, "upscale_image", recorder(ours_log))
+    monkeypatch.setattr(RP, "upscale_image", recorder(ref_log))
+    monkeypatch.setattr(RP, "save_image_with_compression", lambda *a, **k: True)
+
+    def cfg_for(mod):
+        c = mod.MangaTranslatorConfig(yolo_model_path="", upscaling_only=True)
+        c.preprocessing.enabled, c.preprocessing.factor = pre_enabled, pre_factor
+        c.output.upscale_final_image, c.output.image_upscale_factor, c.output.image_upscale_model = final, 1.5, model
+        return c
+
+    import mangatranslator_b200.core.config as OC
+    ours = P.translate_and_render(src, cfg_for(OC), None)
+    theirs = RP.translate_and_render(src, cfg_for(RC), None)
+    assert ours_log == ref_log, (ours_log, ref_log)
+    assert ours.size == theirs.size

@@ -62,7 +62,7 @@ def test_detector_head_tensors_at_1600(G, setup):
     gr = pipe.yolo.forward_letterboxed(lb)
     torch.cuda.synchronize()
     step = meta["anchor_step"]
-    worst = {}
+    worst, mags = {}, {}
     for i, (box, cls, mc, fh, fw, st) in enumerate(gr["levels"]):
         a = fh * fw
         cls_g = cls[0, :, :, :1].reshape(a, 1).t().cpu().numpy()
@@ -71,6 +71,7 @@ def test_detector_head_tensors_at_1600(G, setup):
         worst[f"cls{i}"] = float(np.abs(cls_g - g[f"yolo_cls_{i}"]).max())
         worst[f"box{i}"] = float(np.abs(box_g[:, ::step] - g[f"yolo_box_{i}"]).max())
         worst[f"mc{i}"] = float(np.abs(mc_g[:, ::step] - g[f"yolo_mc_{i}"]).max())
+        mags[f"cls{i}"], mags[f"box{i}"], mags[f"mc{i}"] = (float(np.abs(g[f"yolo_{t}_{i}"]).max()) for t in ("cls", "box", "mc"))
         # float64 checksums of the FULL tensors (every anchor), relative to the sum of magnitudes (bf16x3 products carry a
         # ~2^-16 relative error that does not average out completely over ~1e6 values: measured 2.4e-5)
         s_box, a_box, s_mc, a_mc = meta[f"yolo_sum_{i}"]
@@ -81,11 +82,14 @@ def test_detector_head_tensors_at_1600(G, setup):
     worst["proto"] = float((proto[:, ::ps, ::ps].cpu() - torch.from_numpy(g["yolo_proto"])).abs().max())
     s_p, a_p = meta["yolo_proto_sum"]
     worst["sum_proto_rel"] = abs(float(proto.double().sum()) - s_p) / a_p
+    mags["proto"] = float(np.abs(g["yolo_proto"]).max())
     print("YOLOv8m@1600 head tensors, max abs error vs CPU oracle:", {k: f"{v:.2e}" for k, v in worst.items()})
-    # prototypes reach |v| ~ 50-100 with the seeded weights: their bound is relative to that magnitude
-    pmag = float(np.abs(g["yolo_proto"]).max())
+    print("tensor magnitudes (max |oracle value|):", {k: f"{v:.1f}" for k, v in mags.items()})
+    # ~65 bf16x3 layers deep, activations up to |x| ~ 80: the float tensors are held to 1e-3 abs or 2.5e-4 of the tensor's
+    # magnitude, whichever is larger (measured: 1.3e-4 relative); what the stage must get bit-exact — the NMS indices —
+    # is asserted in the next test
     for k, v in worst.items():
-        bound = 1e-4 if k.startswith("sum_") else TOL * max(1.0, pmag / 10.0) if k == "proto" else TOL
+        bound = 1e-4 if k.startswith("sum_") else max(TOL, 2.5e-4 * mags[k])
         assert v < bound, (k, v, bound)
 
 
@@ -142,7 +146,7 @@ def test_segmenter_masks_for_the_page_prompts(G, setup):
           f"{outside} outside the |logit| < 2e-3 band, {inside} of {int(band.sum())} band pixels ({ref.sum()} mask pixels)")
     assert e_low < TOL and e_iou < TOL
     assert outside == 0
-    assert inside <= int(band.sum())
+    assert inside <= 64, inside                     # a number, not a fraction (measured: 6 of 18.9 M mask bits)
 
 
 @pytest.fixture(scope="module")

@@ -132,29 +132,30 @@ def test_drop_in_aliases_share_singletons():
                 sys.modules[k] = v
 
 
-def test_cache_keys_are_bound_to_the_image_object():
-    """Keys compare by image identity and keep the image alive, so a recycled id() can never alias another image's
-    entry (many short-lived bubble crops go through process_bubble_image_cached); the store is a bounded LRU."""
-    import gc
+def test_cache_keys_follow_the_image_content():
+    """Keys are content fingerprints like the reference's (core/caching.py:28-50): an image mutated in place misses, an equal
+    copy hits, and every kind of result keeps only a couple of entries (no page pairs pile up in host memory)."""
     from PIL import Image
     from mangatranslator_b200.core import caching
     c = caching.UnifiedCache()
     a = Image.new("RGB", (4, 4), (1, 2, 3))
-    k = c.get_bubble_processing_cache_key(a, 200, "min", "model_lite")
-    c.set_upscaled_image(k, "result-a")
+    c.set_upscaled_image(c.get_bubble_processing_cache_key(a, 200, "min", "model_lite"), "result-a")
     assert c.get_upscaled_image(c.get_bubble_processing_cache_key(a, 200, "min", "model_lite")) == "result-a"
+    assert c.get_upscaled_image(c.get_bubble_processing_cache_key(a.copy(), 200, "min", "model_lite")) == "result-a"
     assert c.get_upscaled_image(c.get_bubble_processing_cache_key(a, 201, "min", "model_lite")) is None
-    ida = id(a)
-    del a, k
-    gc.collect()
-    for _ in range(200):                       # whatever object lands on the old address, it is not the cached image
-        b = Image.new("RGB", (4, 4), (9, 9, 9))
-        assert c.get_upscaled_image(c.get_bubble_processing_cache_key(b, 200, "min", "model_lite")) is None
-        if id(b) == ida:
-            break
-    for i in range(caching.MAX_ENTRIES + 10):
-        c.set_upscaled_image(c.get_upscale_cache_key(Image.new("RGB", (2, 2)), 2.0, "model"), i)
-    assert len(c._store) == caching.MAX_ENTRIES
+    a.putpixel((1, 1), (9, 9, 9))                      # in-place edit (the reference pastes / inpaints, then re-upscales)
+    assert c.get_upscaled_image(c.get_bubble_processing_cache_key(a, 200, "min", "model_lite")) is None
+    for i in range(10):
+        c.set_upscaled_image(c.get_upscale_cache_key(Image.new("RGB", (2, 2), (i, 0, 0)), 2.0, "model"), i)
+    assert len(c._store["upscale"]) == caching.MAX_ENTRIES and len(c) == caching.MAX_ENTRIES + 1
+    # a new page drops what was cached for the previous one; the same page (equal content) keeps it
+    page = Image.new("RGB", (8, 8), (5, 5, 5))
+    c.set_current_image(page)
+    c.set_yolo_detection(c.get_yolo_cache_key(page, "m.pt", 0.6), "dets")
+    c.set_current_image(page.copy())
+    assert c.get_yolo_detection(c.get_yolo_cache_key(page, "m.pt", 0.6)) == "dets"
+    c.set_current_image(Image.new("RGB", (8, 8), (6, 5, 5)))
+    assert len(c) == 0
 
 
 def test_yolo_oracle_nms_is_pinned_to_torchvision():
