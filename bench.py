@@ -499,6 +499,90 @@ def run_ours(args, coord):
     print(json.dumps(line))
 
 
+def run_corpus(args, coord):
+    """BASELINE.json configs[4]: a corpus of page FILES through `batch_translate_images` (the reference's batch entry,
+    core/pipeline.py:2481-2731), sharded page i -> rank i mod R: decode -> detect -> segment -> clean -> 2x upscale ->
+    encode -> write, strong scaling (the corpus is fixed, ranks split it).  Reports files/s over the wall time of the
+    slowest rank and where the time went (seconds summed over a rank's threads, max over ranks)."""
+    import shutil
+    import tempfile
+    from PIL import Image
+    from mangatranslator_b200.core import pipeline as P
+    from mangatranslator_b200.core.config import MangaTranslatorConfig
+    dev = torch.device("cuda", coord.local_rank)
+    torch.cuda.set_device(dev)
+    root = coord.broadcast(tempfile.mkdtemp(prefix="mtb200_corpus_") if coord.rank == 0 else None)
+    inp, out = os.path.join(root, "in"), os.path.join(root, "out")
+    n, fmt = args.corpus, args.corpus_format
+    if coord.rank == 0:
+        os.makedirs(inp, exist_ok=True)
+        distinct = min(n, 16)
+        pages = make_pages(distinct, 7000)
+        for i in range(distinct):
+            Image.fromarray(pages[i].image_rgb).save(os.path.join(inp, f"page_{i:05d}.png"), compress_level=1)
+        for i in range(distinct, n):                      # hard links: a large corpus without minutes of PNG writing
+            os.link(os.path.join(inp, f"page_{i % distinct:05d}.png"), os.path.join(inp, f"page_{i:05d}.png"))
+    coord.barrier()
+    cores = os.cpu_count() or 1
+    workers = args.save_workers if args.save_workers > 0 else max(1, cores // coord.world - 1)
+    os.environ["MTB200_SAVE_WORKERS"] = str(workers)
+    cfg = MangaTranslatorConfig(cleaning_only=True)
+    cfg.detection.seg_model = "sam2"
+    cfg.detection.conjoined_detection = False             # the secondary RT-DETR detector has no checkpoint offline
+    cfg.output.upscale_final_image, cfg.output.image_upscale_factor, cfg.output.image_upscale_model = True, 2.0, "model"
+    cfg.output.output_format = fmt
+    os.environ["MTB200_PNG_WRITER"] = args.png_writer     # the config classes keep the reference's fields: the knob is an env var
+    # warm-up: models, plans and CUDA graphs (a separate tiny batch that is not timed)
+    warm = os.path.join(root, "warm")
+    if coord.rank == 0:
+        os.makedirs(warm, exist_ok=True)
+        for i in range(2 * coord.world):
+            os.link(os.path.join(inp, f"page_{i % min(n, 16):05d}.png"), os.path.join(warm, f"w_{i:03d}.png"))
+    coord.barrier()
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):          # the page driver logs to stdout; this program prints ONE JSON line
+        P.batch_translate_images(warm, cfg, os.path.join(root, "warm_out"))
+    P.STAGE_CLOCK.reset()
+    sampler = ClockSampler(coord.local_rank)
+    coord.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(sys.stderr):
+        res = P.batch_translate_images(inp, cfg, out)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    stage = P.STAGE_CLOCK.snapshot()
+    wall_max = coord.all_reduce_max(wall)
+    stage_max = {k: coord.all_reduce_max(stage.get(k, 0.0)) for k in ("decode", "decode_wait", "render", "save_wait", "encode")}
+    ok = res["success_count"] if coord.rank == 0 else 0
+    if coord.rank == 0:
+        written = sum(len(f) for _, _, f in os.walk(out))
+        sizes = [os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(out) for f in fs][:64]
+        per_rank = n / coord.world
+        line = dict(metric="manga page files/sec through batch_translate_images (decode->detect->segment->clean->upscale->encode)",
+                    value=n / wall_max, unit="files/s", n_gpus=coord.world, steps=1, warmup=1, ms_per_step=1000.0 * wall_max,
+                    higher_is_better=True, scaling="strong", vs_baseline=None, dtype="fp16+e5m2 / bf16x3 (see the default line)",
+                    data="synthetic", mode="corpus",
+                    config=dict(workload=f"{n}-page corpus of 1536x1024 PNG files, full pipeline through batch_translate_images, "
+                                         f"{fmt} output, sharded i mod {coord.world} (BASELINE.json configs[4])",
+                                files=n, output_format=fmt, png_writer=args.png_writer, save_workers_per_rank=workers,
+                                host_cores=cores, l2="file-backed pages: every page is decoded and uploaded once"),
+                    files_written=written, success_count=ok, error_count=res.get("error_count"),
+                    avg_output_mb=round(float(np.mean(sizes)) / 1e6, 2) if sizes else None,
+                    seconds_per_rank_max=stage_max,
+                    per_page_ms={k: round(1000.0 * v / per_rank, 2) for k, v in stage_max.items()},
+                    limiter=max(("render", "encode", "decode"),
+                                key=lambda k: stage_max[k] / (workers if k == "encode" else 1)),
+                    clocks=clocks,
+                    e2e=dict(value=n / wall_max, unit="files/s", h2d_bytes_per_step=n * H * W * 3, d2h_bytes_per_step=n * 4 * H * W * 3),
+                    gpu_launches=None)
+        print(json.dumps(line))
+        shutil.rmtree(root, ignore_errors=True)
+    coord.barrier()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -512,6 +596,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--only-gpu-baseline", action="store_true", help="print the torch-eager-on-GPU comparator and exit")
+    ap.add_argument("--corpus", type=int, default=0, help="N > 0: corpus mode, N page files through batch_translate_images")
+    ap.add_argument("--corpus-format", default="png", choices=["png", "jpeg"])
+    ap.add_argument("--png-writer", default="auto", choices=["auto", "pil", "device"],
+                    help="PNG encoder of the batch path: PIL on host threads, or the device deflate encoder")
+    ap.add_argument("--save-workers", type=int, default=0, help="writer threads per rank (0 = host cores / ranks - 1)")
     args = ap.parse_args()
     if args.only_gpu_baseline:
         print(json.dumps(dict(gpu_baseline=gpu_baseline(torch.device("cuda", 0)))))
@@ -523,6 +612,8 @@ def main():
     try:
         if args.impl == "reference":
             run_reference(args, coord)
+        elif args.corpus > 0:
+            run_corpus(args, coord)
         else:
             run_ours(args, coord)
     finally:

@@ -380,6 +380,30 @@ int mtb_sam_select_mask(const float* logits, const float* iou, int P, int K, lon
 int mtb_sam_mask_write(const float* logits, const int* sel, int K, int S, const float* boxes, int P, int H, int W,
                        uint8_t* masks, float* logit_out, void* stream);
 
+/* ---- lossless PNG encoding of a finished page on the device --------------------------------------------------------
+ * Replaces the host-side encoder of core/image/image_utils.py:59-170 save_image_with_compression (PIL's PNG writer, called
+ * per page from core/pipeline.py:1996-2018) for the batch path: scanline filtering, one dynamic-Huffman deflate block per
+ * 16 KB of filtered bytes (literals + distance-1 run matches), blocks byte-aligned with an empty stored block so they
+ * concatenate.  The host builds the Huffman table from the histogram and wraps the stream in the PNG container.
+ * Call order: mtb_png_filter -> mtb_png_histogram -> (host: table) -> mtb_png_deflate -> (prefix sum of sizes) ->
+ * mtb_png_compact. */
+#define MTB_PNG_SEGMENT 16384          /* filtered bytes per deflate block */
+#define MTB_PNG_SEGMENT_STRIDE 32768   /* bytes reserved per encoded block in the staging buffer (worst case + header) */
+/* img: uint8 [H][W][in_channels] (3 or 4) -> stream: [H][1 + W*out_channels] filter-type byte + filtered bytes; a fourth
+ * output channel that the input lacks is opaque alpha (255).  Filter per row = libpng's minimum sum of absolute differences. */
+int mtb_png_filter(const uint8_t* img, int H, int W, int in_channels, int out_channels, uint8_t* stream, void* cuda_stream);
+/* hist: uint32 [288] (zero before the call) symbol counts of the literal/length alphabet over all blocks (incl. one
+ * end-of-block per segment); adler_parts: uint64 [segments][2] = (sum of bytes, sum of (n - i) * byte_i) per segment. */
+int mtb_png_histogram(const uint8_t* stream, long long total, unsigned int* hist, unsigned long long* adler_parts,
+                      void* cuda_stream);
+/* code: bit-reversed canonical Huffman codes, code_len: their lengths (0 = unused), header: the dynamic-block header with
+ * BFINAL = 0 as little-endian 32-bit words (header_bits bits); staged: [segments][stride] bytes; sizes: bytes per block. */
+int mtb_png_deflate(const uint8_t* stream, long long total, const unsigned short* code, const unsigned char* code_len,
+                    const unsigned int* header, int header_bits, uint8_t* staged, int stride, unsigned int* sizes,
+                    void* cuda_stream);
+int mtb_png_compact(const uint8_t* staged, int stride, const unsigned int* sizes, const long long* offsets, int segments,
+                    uint8_t* out, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

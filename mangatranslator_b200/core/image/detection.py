@@ -346,6 +346,8 @@ def detect_speech_bubbles(image_path: Path, model_path, confidence=0.6, verbose=
     synthetic_groups: List[dict] = []
     if len(simple) > 1:
         groups, simple = detect_overlapping_primaries(grouping_boxes, simple)
+        from mangatranslator_b200.conjoined import MAX_CHILDREN
+        groups, simple = _ungroup_oversized(groups, simple, MAX_CHILDREN, verbose)
         if groups:
             log_message(f"Detected {len(groups)} synthetic conjoined group(s) from "
                         f"{sum(len(g) for g in groups)} overlapping primary detections", always_print=True)
@@ -403,6 +405,20 @@ def detect_speech_bubbles(image_path: Path, model_path, confidence=0.6, verbose=
 
 # ---- device-resident fast path used by the batch pipeline / bench -------------------------------------------------------
 @serialized
+def _ungroup_oversized(groups, simple, limit: int, verbose: bool = False):
+    """The device splitter divides a parent mask between at most MTB_SPLIT_MAX_CHILDREN members.  A larger synthetic group
+    (dozens of mutually overlapping boxes: a detector gone wrong, not a page layout) is not split: its members are
+    segmented one by one like simple bubbles — the page keeps its other bubbles instead of failing as a whole."""
+    keep = [g for g in groups if len(g) <= limit]
+    big = [g for g in groups if len(g) > limit]
+    if big:
+        log_message(f"Warning: {len(big)} conjoined group(s) with more than {limit} members are not split; their "
+                    f"{sum(len(g) for g in big)} boxes are segmented individually", always_print=True)
+        simple = sorted(list(simple) + [i for g in big for i in g])
+    return keep, simple
+
+
+
 def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.6, imgsz: int = 1600,
                         seg_model: str = "sam2", injected_boxes: Optional[List[np.ndarray]] = None,
                         own_masks: bool = False, conjoined_detection: bool = False, conjoined_confidence: float = 0.35):
@@ -472,6 +488,8 @@ def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.
         groups = []
         if len(simple) > 1:
             groups, simple = detect_overlapping_primaries(tb, simple)
+            from mangatranslator_b200.conjoined import MAX_CHILDREN
+            groups, simple = _ungroup_oversized(groups, simple, MAX_CHILDREN)
         group_boxes = [sec[s_idx] for _, s_idx in conjoined] + [tb[m] for m in groups]
         group_srcs = [[sec_src[s] for s in s_idx] for _, s_idx in conjoined] + [[sources[m] for m in ms] for ms in groups]
         parents = [union_box(torch.cat([tb[p].unsqueeze(0), sec[s_idx]], 0)) for p, s_idx in conjoined] + \

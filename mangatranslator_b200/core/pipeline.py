@@ -38,6 +38,32 @@ from mangatranslator_b200.utils.logging import log_message
 
 
 
+class _StageClock:
+    """Where a batch spends its time (seconds, summed over threads): `decode` (file -> PIL), `render` (everything between
+    the decoded page and the finished PIL image: H2D, the device stages, D2H, host glue), `encode` (PIL -> file),
+    `save_wait` (the page loop blocked on the writer pool's back-pressure).  Read by bench.py --corpus."""
+
+    def __init__(self):
+        import threading
+        self._lock, self.seconds, self.counts = threading.Lock(), {}, {}
+
+    def add(self, name: str, dt: float) -> None:
+        with self._lock:
+            self.seconds[name] = self.seconds.get(name, 0.0) + dt
+            self.counts[name] = self.counts.get(name, 0) + 1
+
+    def reset(self) -> None:
+        with self._lock:
+            self.seconds, self.counts = {}, {}
+
+    def snapshot(self) -> dict:
+        with self._lock:
+            return {k: round(v, 4) for k, v in self.seconds.items()}
+
+
+STAGE_CLOCK = _StageClock()
+
+
 def _processing_scale(width: int, height: int, auto: bool = True) -> float:
     return math.sqrt((width * height) / 1_000_000) if auto else 1.0     # pipeline.py:765-772
 
@@ -68,12 +94,15 @@ def _target_mode(config: MangaTranslatorConfig, image_path, output_path) -> str:
 
 def _load_page(image_path) -> Image.Image:
     """Open and fully decode a page file (pipeline.py:689-696)."""
+    t0 = time.perf_counter()
     try:
         pil = Image.open(image_path)
         pil.load()
         return pil
     except Exception as e:
         raise ImageProcessingError(f"Error loading image {image_path}: {e}")
+    finally:
+        STAGE_CLOCK.add("decode", time.perf_counter() - t0)
 
 
 def _resolve_pre_upscale_factor(pre_cfg, verbose: bool = False) -> float:
@@ -96,7 +125,119 @@ def _apply_pre_upscale_if_needed(image: Image.Image, config: MangaTranslatorConf
     return upscale_image(image, factor, model_type=model_type, verbose=verbose), factor
 
 
-def _render_page(image_path, config: MangaTranslatorConfig, output_path=None, cancellation_manager=None, preloaded=None):
+class EncodedPng:
+    """A finished page that left the device already PNG-encoded (mangatranslator_b200/png_device.py): `_save_page` writes
+    the bytes as they are.  `size` / `mode` describe the picture like a PIL image would."""
+
+    def __init__(self, data: bytes, size, mode: str):
+        self.data, self.size, self.mode = data, size, mode
+
+    @property
+    def width(self):
+        return self.size[0]
+
+    @property
+    def height(self):
+        return self.size[1]
+
+
+_FAST: Dict[tuple, "HotPathPipeline"] = {}
+_PNG = {}
+
+
+def _png_encoder(device):
+    from mangatranslator_b200.png_device import PngEncoderB200
+    if device not in _PNG:
+        _PNG[device] = PngEncoderB200(device)
+    return _PNG[device]
+
+
+def _device_png_wanted(output_path) -> bool:
+    """PNG files of the batch path are encoded on the device unless MTB200_PNG_WRITER=pil (host threads, like the
+    reference's writer)."""
+    return (output_path is not None and Path(output_path).suffix.lower() == ".png"
+            and os.environ.get("MTB200_PNG_WRITER", "auto") in ("auto", "device"))
+
+
+def _fast_path_pipeline(config: MangaTranslatorConfig, pil: Image.Image) -> Optional["HotPathPipeline"]:
+    """The device-resident engine for this configuration, or None when the page must go through the stage functions.
+
+    `cleaning_only` pages whose stages are all on the device path (SAM 2.1 masks, threshold cleaning, optional final
+    upscale) need no PIL / numpy round trips between the stages: the page is uploaded once, every stage runs in CUDA
+    kernels and the finished page comes back once (MTB200_FAST_PATH=0 forces the stage functions).  The results are the
+    stage functions' results (tests/test_pipeline_gpu.py::test_batch_fast_path_equals_stage_functions).  Not eligible:
+    translucent pages (the stage functions clean the RGBA page itself), the proto-mask segmenter, coloured-bubble
+    inpainting, outside-text processing."""
+    if os.environ.get("MTB200_FAST_PATH", "1") == "0" or not config.cleaning_only:
+        return None
+    if (config.detection.seg_model != "sam2" or config.cleaning.inpaint_colored_bubbles
+            or getattr(config.outside_text, "enabled", False) or not config.preprocessing.auto_scale
+            or not torch.cuda.is_available()):
+        return None
+    if pil.mode not in ("RGB", "RGBA", "L"):
+        return None
+    if pil.mode == "RGBA" and pil.getextrema()[3][0] < 255:
+        return None
+    key = (float(config.detection.confidence), int(config.cleaning.thresholding_value), float(config.cleaning.roi_shrink_px),
+           bool(config.cleaning.use_otsu_threshold), bool(config.detection.conjoined_detection),
+           float(config.detection.conjoined_confidence), bool(config.output.upscale_final_image),
+           str(config.output.image_upscale_model), str(config.yolo_model_path or ""))
+    if key not in _FAST:
+        # objects a caller injected into ModelManager.models (duck-typed detectors / segmenters, like the reference's own
+        # integrations do) only promise the reference's call shapes: they go through the stage functions
+        from mangatranslator_b200.rcan import RcanB200
+        from mangatranslator_b200.sam2_api import Sam2ModelB200
+        from mangatranslator_b200.yolo import YoloB200
+        mm = get_model_manager()
+        try:
+            det = mm.load_yolo_speech_bubble(key[8] or None)
+            seg = mm.load_sam2()
+            up = (mm.load_upscale() if key[7] == "model" else mm.load_upscale_lite()) if key[6] else None
+        except Exception:
+            return None                            # the stage functions report / degrade like the reference does
+        if not (isinstance(det, YoloB200) and isinstance(seg, tuple) and isinstance(seg[1], Sam2ModelB200)
+                and (up is None or isinstance(up, RcanB200))):
+            return None
+        _FAST[key] = HotPathPipeline(confidence=key[0], seg_model="sam2", upscale=key[6],
+                                     upscale_model="model" if key[7] == "model" else "model_lite",
+                                     thresholding_value=key[1], roi_shrink_px=key[2], use_otsu_threshold=key[3],
+                                     conjoined_detection=key[4], conjoined_confidence=key[5], yolo_model_path=key[8])
+    return _FAST[key]
+
+
+def _render_fast(pipe: "HotPathPipeline", pil: Image.Image, config: MangaTranslatorConfig, png_mode: Optional[str] = None):
+    """One page through the device engine: RGB page -> cleaned (and, for a 2x final upscale, upscaled) RGB page.  With
+    `png_mode` ("RGB" / "RGBA") the finished page is PNG-encoded on the device and only the compressed bytes come back."""
+    from mangatranslator_b200._lib import device_section
+    rgb = np.asarray(pil.convert("RGB"))
+    host = torch.from_numpy(np.ascontiguousarray(rgb[:, :, ::-1]))
+    with device_section:
+        two_x = pipe.rcan is not None and abs(float(config.output.image_upscale_factor) - float(pipe.rcan.scale)) < 1e-9
+        if two_x and png_mode:
+            out, _, _ = pipe.run_page_device(host.to(pipe.device, non_blocking=True))    # RGB, 2H x 2W, stays on the device
+            data = _png_encoder(pipe.device).encode(out, out_channels=4 if png_mode == "RGBA" else 3)
+            return EncodedPng(data, (int(out.shape[1]), int(out.shape[0])), png_mode)
+        if two_x:
+            out, _, _ = pipe.run_page(host)                         # RGB, 2H x 2W
+            return Image.fromarray(out.numpy())
+        page = host.to(pipe.device)
+        dets = detect_pages_device([page], confidence=pipe.confidence, imgsz=pipe.imgsz, seg_model="sam2", **pipe.conjoined)[0]
+        batch = clean_pages_device([page], [dets], thresholding_value=pipe.thr, roi_shrink_px=pipe.shrink,
+                                   use_otsu_threshold=pipe.otsu, processing_scale=_processing_scale(pil.width, pil.height,
+                                                                                                  config.preprocessing.auto_scale))
+        if png_mode and not config.output.upscale_final_image:
+            out = batch.pages_out[0][:, :, [2, 1, 0]].contiguous()
+            data = _png_encoder(pipe.device).encode(out, out_channels=4 if png_mode == "RGBA" else 3)
+            return EncodedPng(data, (int(out.shape[1]), int(out.shape[0])), png_mode)
+        cleaned = Image.fromarray(np.ascontiguousarray(batch.pages_out[0].cpu().numpy()[:, :, ::-1]))
+    if config.output.upscale_final_image:      # any other factor: the wrapper's pass loop + exact-size resample
+        cleaned = upscale_image(cleaned, config.output.image_upscale_factor, model_type=config.output.image_upscale_model,
+                                verbose=config.verbose)
+    return cleaned
+
+
+def _render_page(image_path, config: MangaTranslatorConfig, output_path=None, cancellation_manager=None, preloaded=None,
+                 device_png: bool = False):
     """Everything of translate_and_render up to (not including) the save: returns (image, target_mode).  `preloaded`:
     a pending decode of this page (concurrent.futures.Future of _load_page) started while the previous page was on the
     device."""
@@ -107,7 +248,19 @@ def _render_page(image_path, config: MangaTranslatorConfig, output_path=None, ca
     if cancellation_manager is not None and cancellation_manager.is_cancelled():
         raise CancellationError("Process cancelled by user.")
     image_path = Path(image_path)
+    t0 = time.perf_counter()
     pil = preloaded.result() if preloaded is not None else _load_page(image_path)
+    if preloaded is not None:                       # the decode has its own clock; what was left of it is waited for here
+        STAGE_CLOCK.add("decode_wait", time.perf_counter() - t0)
+    t_render = time.perf_counter()
+    try:
+        return _render_decoded(pil, image_path, config, output_path, verbose, device_png)
+    finally:
+        STAGE_CLOCK.add("render", time.perf_counter() - t_render)
+
+
+def _render_decoded(pil: Image.Image, image_path: Path, config: MangaTranslatorConfig, output_path, verbose: bool,
+                    device_png: bool = False):
     target_mode = _target_mode(config, image_path, output_path)
     pil = convert_image_to_target_mode(pil, target_mode, verbose)
     get_cache().clear_all()                 # every mode: nothing cached for the previous page outlives it
@@ -120,6 +273,8 @@ def _render_page(image_path, config: MangaTranslatorConfig, output_path=None, ca
         if config.output.upscale_final_image:
             out = upscale_image(out, config.output.image_upscale_factor, model_type=config.output.image_upscale_model,
                                 verbose=verbose)
+    elif (fast := _fast_path_pipeline(config, pil)) is not None:
+        out = _render_fast(fast, pil, config, target_mode if device_png and _device_png_wanted(output_path) else None)
     else:
         scale = _processing_scale(pil.width, pil.height, config.preprocessing.auto_scale)
         get_cache().set_current_image(pil, verbose)
@@ -145,6 +300,18 @@ def _render_page(image_path, config: MangaTranslatorConfig, output_path=None, ca
 def _save_page(image: Image.Image, target_mode: str, output_path, config: MangaTranslatorConfig) -> None:
     """pipeline.py:1996-2018: convert to the target mode, save with the configured compression; a failed save is logged
     and re-raised."""
+    t0 = time.perf_counter()
+    if isinstance(image, EncodedPng):               # encoded on the device: the bytes are the file
+        try:
+            path = Path(output_path)
+            path.parent.mkdir(parents=True, exist_ok=True)
+            path.write_bytes(image.data)
+            return
+        except Exception as e:
+            log_message(f"Failed to save image: Failed to save image to {output_path}", always_print=True)
+            raise ImageProcessingError(f"Failed to save image to {output_path}") from e
+        finally:
+            STAGE_CLOCK.add("encode", time.perf_counter() - t0)
     if image.mode != target_mode:
         image = image.convert(target_mode)
     try:
@@ -153,6 +320,8 @@ def _save_page(image: Image.Image, target_mode: str, output_path, config: MangaT
     except ImageProcessingError as e:
         log_message(f"Failed to save image: {e}", always_print=True)
         raise
+    finally:
+        STAGE_CLOCK.add("encode", time.perf_counter() - t0)
 
 
 def translate_and_render(image_path, config: MangaTranslatorConfig, output_path=None, cancellation_manager=None,
@@ -173,9 +342,12 @@ def _process_page(path, config, out_path, cancellation_manager, saver, preloaded
         translate_and_render(path, config, out_path, cancellation_manager=cancellation_manager)
         return None
     start = time.time()
-    out, target_mode = _render_page(path, config, out_path, cancellation_manager, preloaded)
-    log_message(f"Processing completed in {time.time() - start:.2f}s (save queued)", always_print=True)
-    return saver.submit(_save_page, out, target_mode, out_path, config)
+    out, target_mode = _render_page(path, config, out_path, cancellation_manager, preloaded, device_png=True)
+    log_message(f"Processing completed in {time.time() - start:.2f}s (save queued)", verbose=config.verbose)
+    t0 = time.perf_counter()
+    fut = saver.submit(_save_page, out, target_mode, out_path, config)
+    STAGE_CLOCK.add("save_wait", time.perf_counter() - t0)
+    return fut
 
 
 class _BoundedPool:
@@ -461,16 +633,16 @@ class HotPathPipeline:
     def __init__(self, *, confidence: float = 0.6, imgsz: int = 1600, seg_model: str = "sam2", upscale: bool = True,
                  upscale_model: str = "model", thresholding_value: int = 200, roi_shrink_px: int = 5,
                  device: Optional[torch.device] = None, conjoined_detection: bool = False,
-                 conjoined_confidence: float = 0.35):
+                 conjoined_confidence: float = 0.35, use_otsu_threshold: bool = False, yolo_model_path=None):
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.confidence, self.imgsz, self.seg_model = confidence, imgsz, seg_model
         self.upscale, self.upscale_model = upscale, upscale_model
-        self.thr, self.shrink = thresholding_value, roi_shrink_px
+        self.thr, self.shrink, self.otsu = thresholding_value, roi_shrink_px, bool(use_otsu_threshold)
         # secondary RT-DETR detector merged like the reference's default (detection.py:1392-1548); off here by default
         # because without its checkpoint the loader refuses and every page would log the swallowed failure
         self.conjoined = dict(conjoined_detection=conjoined_detection, conjoined_confidence=conjoined_confidence)
         mm = get_model_manager()
-        self.yolo = mm.load_yolo_speech_bubble(None)
+        self.yolo = mm.load_yolo_speech_bubble(yolo_model_path or None)
         self.sam = mm.load_sam2() if seg_model == "sam2" else None
         self.rcan = (mm.load_upscale() if upscale_model == "model" else mm.load_upscale_lite()) if upscale else None
         self.stage_ms: Dict[str, float] = {}
@@ -488,7 +660,7 @@ class HotPathPipeline:
         if t: t[1].record()
         scale = _processing_scale(w, h)
         batch = clean_pages_device([page_bgr], [dets], thresholding_value=self.thr, roi_shrink_px=self.shrink,
-                                   processing_scale=scale)
+                                   use_otsu_threshold=self.otsu, processing_scale=scale)
         cleaned = batch.pages_out[0]
         if t: t[2].record()
         out = cleaned
@@ -517,13 +689,13 @@ class HotPathPipeline:
         scales = {_processing_scale(int(p.shape[1]), int(p.shape[0])) for p in pages_bgr}
         if len(scales) == 1:
             batch = clean_pages_device(list(pages_bgr), dets, thresholding_value=self.thr, roi_shrink_px=self.shrink,
-                                       processing_scale=scales.pop())
+                                       use_otsu_threshold=self.otsu, processing_scale=scales.pop())
             cleaned = batch.pages_out
         else:                                   # mixed page sizes: the scale-derived parameters differ per page
             batch, cleaned = None, []
             for page, d in zip(pages_bgr, dets):
                 b1 = clean_pages_device([page], [d], thresholding_value=self.thr, roi_shrink_px=self.shrink,
-                                        processing_scale=_processing_scale(int(page.shape[1]), int(page.shape[0])))
+                                        use_otsu_threshold=self.otsu, processing_scale=_processing_scale(int(page.shape[1]), int(page.shape[0])))
                 cleaned.append(b1.pages_out[0])
         outs = []
         for i in range(n):

@@ -138,7 +138,7 @@ def test_batch_flow_counts_errors_retry_and_cancellation(tmp_path, monkeypatch, 
     inp = _make_dir(tmp_path)
     seen, fail_once = [], {"bad.png": 1, "stage": "render"}
 
-    def fake_render(path, config, output_path=None, cancellation_manager=None, preloaded=None):
+    def fake_render(path, config, output_path=None, cancellation_manager=None, preloaded=None, device_png=False):
         seen.append((Path(path).name, Path(output_path).name))
         if Path(path).name == "bad.png" and fail_once["stage"] == "render" and fail_once["bad.png"] != 0:
             fail_once["bad.png"] -= 1
@@ -203,7 +203,7 @@ def test_writer_pool_overlaps_saving_with_the_next_pages_device_work(tmp_path, m
     inp.mkdir()
     for i in range(8):
         (inp / f"{i}.png").write_bytes(b"x")
-    monkeypatch.setattr(P, "_render_page", lambda path, config, output_path=None, cancellation_manager=None, preloaded=None:
+    monkeypatch.setattr(P, "_render_page", lambda path, config, output_path=None, cancellation_manager=None, preloaded=None, device_png=False:
                         (time.sleep(0.05), ("img", "RGB"))[1])
     monkeypatch.setattr(P, "_save_page", lambda image, mode, out, config: (time.sleep(0.15), Path(out).write_bytes(b"ok"))[1])
     cfg = MangaTranslatorConfig(cleaning_only=True)
@@ -252,7 +252,7 @@ sys.path.insert(0, {root!r})
 from mangatranslator_b200.core import pipeline as P
 from mangatranslator_b200.core.config import MangaTranslatorConfig
 rank = int(os.environ["RANK"])
-def render(path, config, output_path=None, cancellation_manager=None, preloaded=None):
+def render(path, config, output_path=None, cancellation_manager=None, preloaded=None, device_png=False):
     if Path(path).name == "7.png":
         raise RuntimeError("bad page")
     return "img", "RGB"

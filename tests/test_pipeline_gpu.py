@@ -184,3 +184,28 @@ def test_hot_path_with_conjoined_group_matches_cpu_pipeline(small_models):
     assert [d["bbox"] for d in dets] == [b["bbox"] for b in ref["bubbles"]] or len(dets) == ref["masks"].shape[0]
     from helpers import check_page_against_cpu_pipeline
     check_page_against_cpu_pipeline(pipe, ref, out, dets, batch, "448x384 page with a conjoined group")
+
+
+@pytest.mark.parametrize("final,factor", [(True, 2.0), (False, 2.0), (True, 1.5)], ids=["upscale_2x", "clean_only", "upscale_1p5x"])
+def test_batch_fast_path_equals_stage_functions(small_models, tmp_path, monkeypatch, final, factor):
+    """`translate_and_render` sends eligible cleaning_only pages through the device-resident engine (one upload, one
+    download); the result must be byte-identical to the reference-shaped stage functions (detect_speech_bubbles ->
+    clean_speech_bubbles -> upscale_image) it replaces, for opaque RGB and RGBA sources."""
+    from mangatranslator_b200 import synth
+    from mangatranslator_b200.core.config import MangaTranslatorConfig
+    from mangatranslator_b200.core import pipeline as P
+    pg = synth.make_page(51, 416, 352, n_bubbles=4)
+    cfg = MangaTranslatorConfig(cleaning_only=True)
+    cfg.detection.seg_model, cfg.detection.conjoined_detection, cfg.detection.confidence = "sam2", False, 0.25
+    cfg.output.upscale_final_image, cfg.output.image_upscale_factor, cfg.output.image_upscale_model = final, factor, "model"
+    for mode in ("RGB", "RGBA"):
+        src = tmp_path / f"page_{mode}.png"
+        Image.fromarray(pg.image_rgb).convert(mode).save(src)
+        monkeypatch.setenv("MTB200_FAST_PATH", "0")
+        slow = P.translate_and_render(src, cfg, None)
+        monkeypatch.setenv("MTB200_FAST_PATH", "1")
+        P._FAST.clear()
+        fast = P.translate_and_render(src, cfg, None)
+        assert P._FAST, "the fast path was not taken"
+        assert fast.size == slow.size
+        assert np.array_equal(np.asarray(fast.convert("RGB")), np.asarray(slow.convert("RGB"))), (mode, final, factor)
