@@ -129,8 +129,17 @@ class EncodedPng:
     """A finished page that left the device already PNG-encoded (mangatranslator_b200/png_device.py): `_save_page` writes
     the bytes as they are.  `size` / `mode` describe the picture like a PIL image would."""
 
-    def __init__(self, data: bytes, size, mode: str):
-        self.data, self.size, self.mode = data, size, mode
+    def __init__(self, data, size, mode: str):
+        self._data, self.size, self.mode = data, size, mode
+
+    @property
+    def data(self) -> bytes:
+        """The file's bytes.  The encoder hands over the deflate stream and its checksums' ingredients; the container
+        (zlib trailer, chunk CRCs) is put around it here, i.e. on the writer thread that saves the page."""
+        if not isinstance(self._data, (bytes, bytearray)):
+            from mangatranslator_b200.png_device import finalize_png
+            self._data = finalize_png(self._data)
+        return self._data
 
     @property
     def width(self):
@@ -209,17 +218,43 @@ def _render_fast(pipe: "HotPathPipeline", pil: Image.Image, config: MangaTransla
     """One page through the device engine: RGB page -> cleaned (and, for a 2x final upscale, upscaled) RGB page.  With
     `png_mode` ("RGB" / "RGBA") the finished page is PNG-encoded on the device and only the compressed bytes come back."""
     from mangatranslator_b200._lib import device_section
-    rgb = np.asarray(pil.convert("RGB"))
-    host = torch.from_numpy(np.ascontiguousarray(rgb[:, :, ::-1]))
+    t_prep = time.perf_counter()
+    rgb = np.asarray(pil if pil.mode == "RGB" else pil.convert("RGB"))
+    h, w = rgb.shape[:2]
+    STAGE_CLOCK.add("render_host_prep", time.perf_counter() - t_prep)
     with device_section:
+        # pinned staging buffers are kept per page size (cudaHostAlloc per page costs more than the copy it speeds up)
+        stage = pipe.__dict__.setdefault("_staging", {})
+        key = (h, w)
+        if key not in stage:
+            if len(stage) >= 4:
+                stage.pop(next(iter(stage)))
+            stage[key] = dict(inp=torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True))
+        sb = stage[key]
+        np.copyto(sb["inp"].numpy(), rgb[:, :, ::-1])                    # BGR, like the cleaning stage wants
+        host = sb["inp"]
         two_x = pipe.rcan is not None and abs(float(config.output.image_upscale_factor) - float(pipe.rcan.scale)) < 1e-9
         if two_x and png_mode:
-            out, _, _ = pipe.run_page_device(host.to(pipe.device, non_blocking=True))    # RGB, 2H x 2W, stays on the device
-            data = _png_encoder(pipe.device).encode(out, out_channels=4 if png_mode == "RGBA" else 3)
+            t0 = time.perf_counter()
+            out, dets, _ = pipe.run_page_device(host.to(pipe.device, non_blocking=True))    # RGB, 2H x 2W, stays on the device
+            torch.cuda.current_stream().synchronize()
+            STAGE_CLOCK.add("render_device", time.perf_counter() - t0)
+            STAGE_CLOCK.add("bubbles", float(len(dets)))
+            t0 = time.perf_counter()
+            data = _png_encoder(pipe.device).encode(out, out_channels=4 if png_mode == "RGBA" else 3, finalize=False)
+            STAGE_CLOCK.add("render_device_png", time.perf_counter() - t0)
             return EncodedPng(data, (int(out.shape[1]), int(out.shape[0])), png_mode)
         if two_x:
-            out, _, _ = pipe.run_page(host)                         # RGB, 2H x 2W
-            return Image.fromarray(out.numpy())
+            if "out" not in sb:
+                sb["out"] = torch.empty((pipe.rcan.scale * h, pipe.rcan.scale * w, 3), dtype=torch.uint8, pin_memory=True)
+            t0 = time.perf_counter()
+            out, dets, _ = pipe.run_page(host, out_host=sb["out"])      # RGB, 2H x 2W
+            STAGE_CLOCK.add("render_device", time.perf_counter() - t0)
+            STAGE_CLOCK.add("bubbles", float(len(dets)))
+            t0 = time.perf_counter()
+            img = Image.fromarray(out.numpy().copy())
+            STAGE_CLOCK.add("render_to_pil", time.perf_counter() - t0)
+            return img
         page = host.to(pipe.device)
         dets = detect_pages_device([page], confidence=pipe.confidence, imgsz=pipe.imgsz, seg_model="sam2", **pipe.conjoined)[0]
         batch = clean_pages_device([page], [dets], thresholding_value=pipe.thr, roi_shrink_px=pipe.shrink,
@@ -227,7 +262,7 @@ def _render_fast(pipe: "HotPathPipeline", pil: Image.Image, config: MangaTransla
                                                                                                   config.preprocessing.auto_scale))
         if png_mode and not config.output.upscale_final_image:
             out = batch.pages_out[0][:, :, [2, 1, 0]].contiguous()
-            data = _png_encoder(pipe.device).encode(out, out_channels=4 if png_mode == "RGBA" else 3)
+            data = _png_encoder(pipe.device).encode(out, out_channels=4 if png_mode == "RGBA" else 3, finalize=False)
             return EncodedPng(data, (int(out.shape[1]), int(out.shape[0])), png_mode)
         cleaned = Image.fromarray(np.ascontiguousarray(batch.pages_out[0].cpu().numpy()[:, :, ::-1]))
     if config.output.upscale_final_image:      # any other factor: the wrapper's pass loop + exact-size resample
@@ -262,8 +297,14 @@ def _render_page(image_path, config: MangaTranslatorConfig, output_path=None, ca
 def _render_decoded(pil: Image.Image, image_path: Path, config: MangaTranslatorConfig, output_path, verbose: bool,
                     device_png: bool = False):
     target_mode = _target_mode(config, image_path, output_path)
-    pil = convert_image_to_target_mode(pil, target_mode, verbose)
     get_cache().clear_all()                 # every mode: nothing cached for the previous page outlives it
+    pre = _resolve_pre_upscale_factor(getattr(config, "preprocessing", None))
+    if not config.upscaling_only and pre == 1.0 and (fast := _fast_path_pipeline(config, pil)) is not None:
+        # the device engine works on the opaque RGB page: converting to the target mode first (an alpha plane of 255 for
+        # PNG output) and back would only cost two host passes over the page
+        return (_render_fast(fast, pil, config, target_mode if device_png and _device_png_wanted(output_path) else None),
+                target_mode)
+    pil = convert_image_to_target_mode(pil, target_mode, verbose)
     pil, _ = _apply_pre_upscale_if_needed(pil, config, verbose)
     if config.upscaling_only:
         # core/pipeline.py:723-737: in this mode the final upscale still depends on output.upscale_final_image (the

@@ -210,9 +210,11 @@ class PngEncoderB200:
                 host=torch.empty(segs * STRIDE, dtype=torch.uint8, pin_memory=True))
         return self._bufs[key]
 
-    def encode(self, img: torch.Tensor, out_channels: int = 0) -> bytes:
+    def encode(self, img: torch.Tensor, out_channels: int = 0, finalize: bool = True):
         """img: device uint8 [H][W][3|4], RGB(A) order.  out_channels 4 with a 3-channel image writes an opaque RGBA file
-        (the reference's target mode for PNG output, core/pipeline.py:702-712)."""
+        (the reference's target mode for PNG output, core/pipeline.py:702-712).  Returns the file's bytes, or with
+        finalize=False the ingredients for `finalize_png` (so the checksums and the container can be made on another
+        thread while the device moves on to the next page)."""
         assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_contiguous() and img.shape[2] in (3, 4)
         h, w, ic = int(img.shape[0]), int(img.shape[1]), int(img.shape[2])
         oc = out_channels or ic
@@ -234,7 +236,13 @@ class PngEncoderB200:
         b["host"][:nbytes].copy_(b["out"][:nbytes], non_blocking=True)
         parts = b["adler"].cpu().numpy()
         torch.cuda.current_stream().synchronize()
-        adler = adler32_from_parts(parts, total)
-        body = b"\x78\x01" + b["host"][:nbytes].numpy().tobytes() + struct.pack(">I", adler)
-        ihdr = struct.pack(">IIBBBBB", w, h, 8, 6 if oc == 4 else 2, 0, 0, 0)
-        return b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", ihdr) + _chunk(b"IDAT", body) + _chunk(b"IEND", b"")
+        raw = dict(deflate=b["host"][:nbytes].numpy().tobytes(), adler_parts=parts, total=total, w=w, h=h, oc=oc)
+        return finalize_png(raw) if finalize else raw
+
+
+def finalize_png(raw: dict) -> bytes:
+    """Deflate stream + Adler-32 partial sums -> the bytes of the PNG file (zlib header / trailer, IHDR, IDAT, IEND)."""
+    adler = adler32_from_parts(raw["adler_parts"], raw["total"])
+    body = b"\x78\x01" + raw["deflate"] + struct.pack(">I", adler)
+    ihdr = struct.pack(">IIBBBBB", raw["w"], raw["h"], 8, 6 if raw["oc"] == 4 else 2, 0, 0, 0)
+    return b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", ihdr) + _chunk(b"IDAT", body) + _chunk(b"IEND", b"")

@@ -466,10 +466,18 @@ class Sam2B200:
         """boxes_xyxy: float32 [P][4] in ORIGINAL page pixels (device or host).  Returns uint8 masks [P][H][W] {0,255}
         (and, optionally, the low-res logits [P][4][256*256], selection [P] and interpolated logits [P][H][W])."""
         H, W = orig_hw
-        Pn = int(boxes_xyxy.shape[0])
+        n_real = int(boxes_xyxy.shape[0])
         dev = self.device
-        if Pn == 0:
+        if n_real == 0:
             return torch.zeros((0, H, W), dtype=torch.uint8, device=dev)
+        # Prompt counts are bucketed (multiples of 4): every distinct count owns buffers, launch descriptors and a CUDA graph
+        # per page size, and a detector's count changes from page to page.  The padding prompts repeat the first box (the
+        # decoder treats prompts independently); their masks are dropped.
+        bucket = int(os.environ.get("MTB200_SAM_PROMPT_BUCKET", "4"))
+        Pn = -(-n_real // bucket) * bucket if bucket > 1 and not want_logits else n_real
+        if Pn != n_real:
+            boxes_xyxy = torch.cat([boxes_xyxy.to(dtype=torch.float32),
+                                    boxes_xyxy[:1].to(dtype=torch.float32).expand(Pn - n_real, -1)], 0)
         from . import graphs
         if Pn not in self._dec:
             self._dec[Pn] = self._build_decoder(Pn, enc)
@@ -534,7 +542,7 @@ class Sam2B200:
                                        stream_ptr()), "mtb_sam_mask_write")
         if want_logits:
             return masks, d["logits"], d["sel"], lo, iou
-        return masks
+        return masks[:n_real]
 
     def decode_lowres(self, enc: dict, boxes_xyxy: torch.Tensor, orig_hw: Tuple[int, int]) -> torch.Tensor:
         """Low-res logits [P][256][256] of the selected mask (what Sam2Model returns as pred_masks)."""
