@@ -162,10 +162,18 @@ def _png_encoder(device):
 
 
 def _device_png_wanted(output_path) -> bool:
-    """PNG files of the batch path are encoded on the device unless MTB200_PNG_WRITER=pil (host threads, like the
-    reference's writer)."""
-    return (output_path is not None and Path(output_path).suffix.lower() == ".png"
-            and os.environ.get("MTB200_PNG_WRITER", "auto") in ("auto", "device"))
+    """Who encodes the PNG files of the batch path: MTB200_PNG_WRITER = "device" (csrc/png_kernels.cu), "pil" (host
+    threads, like the reference's writer) or "auto".  A 3072x2048 page costs ~0.63 s of one host core with PIL (measured),
+    so PIL keeps up only with ~6 or more writer cores per GPU; measured on 2 GPUs: with 11 writer threads per rank PIL
+    13.5 files/s vs device 11.6 (the device encoder adds ~20 ms to a page's critical path), with 3 threads per rank — the
+    share of a 32-core 8-GPU box — PIL 8.9 vs device 11.6.  "auto" = device when the rank has fewer than 8 host cores."""
+    if output_path is None or Path(output_path).suffix.lower() != ".png":
+        return False
+    mode = os.environ.get("MTB200_PNG_WRITER", "auto")
+    if mode == "auto":
+        world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+        return (os.cpu_count() or 1) // world < 8
+    return mode == "device"
 
 
 def _fast_path_pipeline(config: MangaTranslatorConfig, pil: Image.Image) -> Optional["HotPathPipeline"]:
