@@ -191,6 +191,15 @@ int mtb_rcan_gate_fp16c(const float* sums, int parts, const float* border_sums /
  * `fixed` ([5][64] int64, units of 2^-20, zero before the launch) with integer atomics instead of writing per-CTA
  * rows: the order of the additions cannot change the result, and the gate reads 2.5 KB instead of ~750 KB. */
 int mtb_conv_plan_set_fixed_sums(mtb_conv_plan* plan, long long* fixed);
+/* fp16c plans, an RCAB's second conv: compute the block's CALayer gate in this launch's prologue instead of a launch of
+ * its own (mtb_rcan_gate_fp16c).  Every CTA derives the 64 gates from `fixed_in` (what the first conv accumulated through
+ * mtb_conv_plan_set_fixed_sums) and the four corner pixels of `u` (this layer's input planes) while its weights stream
+ * in, and applies them as the channel scale; CTA 0 zeroes `fixed_zero` (the accumulators the NEXT block's first conv
+ * uses: alternate two buffers) — `fixed_in` itself is left as it is.  conv_w/conv_b: this layer's fp32 weights
+ * [64][64][3][3] / bias; w1,b1,w2,b2,R: conv_du as in mtb_rcan_gate. */
+int mtb_conv_plan_set_fused_gate(mtb_conv_plan* plan, const long long* fixed_in, long long* fixed_zero, const void* u,
+                                 const float* conv_w, const float* conv_b, const float* w1, const float* b1,
+                                 const float* w2, const float* b2, int R);
 int mtb_f32_to_u8(const float* in, long long npix, int cpad, const float* add3 /* host */, float mul, uint8_t* out,
                   float* out_f /* optional float copy [npix][3] */, void* stream);
 /* "_PU" RCAN variants (ModelManager.load_upscale_lite, core/ml/model_manager.py:660-700 -> spandrel RCAN with

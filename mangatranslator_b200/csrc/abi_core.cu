@@ -410,6 +410,29 @@ int mtb_conv_plan_set_fixed_sums(mtb_conv_plan* plan, long long* fixed) {
   return 0;
 }
 
+int mtb_conv_plan_set_fused_gate(mtb_conv_plan* plan, const long long* fixed_in, long long* fixed_zero, const void* u,
+                                 const float* conv_w, const float* conv_b, const float* w1, const float* b1,
+                                 const float* w2, const float* b2, int R) {
+  MTB_REQUIRE(plan != nullptr, "mtb_conv_plan_set_fused_gate: null plan");
+  MTB_REQUIRE(plan->halo == 3 && plan->p.N == 1 && plan->p.residual != nullptr && plan->p.tile_sums == nullptr,
+              "conv: a fused gate needs an fp16c plan (one image) with a residual and without sums (an RCAB's second conv)");
+  MTB_REQUIRE(fixed_in && u && conv_w && w1 && w2 && R > 0 && R <= 16,
+              "mtb_conv_plan_set_fused_gate: bad arguments (the fused gate handles up to 16 hidden units; use mtb_rcan_gate_fp16c)");
+  ConvParams& p = plan->p;
+  p.gate_fixed = fixed_in;
+  p.gate_zero = fixed_zero;
+  p.gate_u = static_cast<const uint8_t*>(u);
+  p.gate_w = conv_w;
+  p.gate_b = conv_b;
+  p.gate_w1 = w1;
+  p.gate_b1 = b1;
+  p.gate_w2 = w2;
+  p.gate_b2 = b2;
+  p.gate_R = R;
+  p.chan_scale = nullptr;
+  return 0;
+}
+
 int mtb_conv_plan_num_mtiles(const mtb_conv_plan* plan) {
   return plan ? plan->p.N * plan->p.tiles_y * plan->p.tiles_x : 0;
 }

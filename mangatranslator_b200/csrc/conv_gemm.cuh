@@ -60,6 +60,15 @@ struct ConvParams {
   long long* sums_fixed;       // fp16c kernel, optional: [5][64] fixed-point (2^-20) accumulators of the output's channel sums
                                //   over the image, row 0, row Ho-1, column 0, column Wo-1, added with integer atomics
                                //   (order-independent, so bit-reproducible); replaces tile_sums / border_sums rows
+  // fp16c kernel, optional: the RCAB gate computed in THIS launch's prologue (the layer is the block's second conv).  Every
+  // CTA derives the 64 gates redundantly from `gate_fixed` (the [5][64] fixed-point sums of its input that the first conv
+  // accumulated) while its weights stream in, and uses them as the channel scale; CTA 0 zeroes `gate_zero` (the other
+  // block parity's accumulators) for the next block's first conv.
+  const long long* gate_fixed;
+  long long* gate_zero;
+  const uint8_t* gate_u;       // this layer's input planes (fp16c), for the four corner pixels
+  const float *gate_w, *gate_b, *gate_w1, *gate_b1, *gate_w2, *gate_b2;   // conv weights fp32 [64][64][3][3] / bias, conv_du
+  int gate_R;
   int pf_x, pf_res;            // fp16c kernel: L2 prefetch distances (tiles ahead) of the activation / residual tiles
   float lo_scale, lo_inv_scale;  // fp16c kernel (conv_halo_fp16c.cu): the e5m2 residual plane holds (v - fp16(v)) * lo_scale;
                                //   there `out` / `residual` are byte tensors [3][N][H][W][64 B] and the plane strides are bytes

@@ -47,12 +47,18 @@ constexpr int kThreads = kConvThreads;
 constexpr int kTW = 8, kTH = 30;                    // output tile (pixels)
 constexpr int kHW = kTW + 2, kHH = kTH + 2;         // halo tile
 constexpr int kNPix = kTW * kTH;                    // N of the MMA (240)
-constexpr int kSlots = 2;
+constexpr int kSlots = 2;                           // resident-weights variant
+constexpr int kSlotsS = 3;                          // streaming variant (STREAM): taps 0-4 of the e5m2 weights travel through
+                                                    // the ring once per tile instead of being resident, which frees exactly
+                                                    // one 20 KB slot: TMA loads run two planes ahead instead of one
+constexpr int kMaxSlots = 3;
 constexpr int kSlotBytes = kHW * kHH * 64;          // 20480: one 64-byte-row plane of the halo tile
 constexpr int kW16TapBytes = 2 * 128 * 64;          // per tap: two channel halves x 128 interleaved rows x 64 B
 constexpr int kW16Bytes = 9 * kW16TapBytes;         // 147456
 constexpr int kW8TapBytes = 64 * 64;                // per tap: 64 rows x 64 B
 constexpr int kWBytes = kW16Bytes + 9 * kW8TapBytes;   // 184320
+constexpr int kWBytesS = kW16Bytes + 4 * kW8TapBytes;  // 163840: STREAM keeps the e5m2 weights of taps 5-8 resident
+constexpr int kW8StreamTaps = 5;                       // 5 x 4 KB = one slot
 constexpr int kAccCols = 256;                       // TMEM columns per accumulator stage
 constexpr int kChunks = kNPix / 16;                 // column chunks of 16 pixels (= 2 tile rows)
 
@@ -350,30 +356,147 @@ __device__ __forceinline__ void epi_tile_x4(const ConvParams& p, const EpiLaneX&
   }
 }
 
+
+constexpr int kGateFloats = 21 * 64;     // tot, line[4], corner[4], shifted[9], mean, hid, scale
+
+// The CALayer gate of an RCAB from sums of the second conv's INPUT u (linearity of the zero-padded conv, see
+// elementwise.cu::rcan_gate_kernel for the derivation): run by the 512 epilogue threads of every CTA before their first
+// tile.  g = shared scratch of kGateFloats floats; the 64 gates end up in g[20*64 ..).
+__device__ __forceinline__ void gate_prologue(const ConvParams& p, float* g, int t /* 0..511 */, const uint8_t* sW,
+                                              uint64_t* w_bar) {
+  float* tot = g;
+  float* line = g + 64;          // [4][64]: row 0, row H-1, column 0, column W-1
+  float* corner = g + 5 * 64;    // [4][64]
+  float* shifted = g + 9 * 64;   // [9][64]
+  float* mean = g + 18 * 64;
+  float* hid = g + 19 * 64;
+  float* scale = g + 20 * 64;
+  const int H = p.Ho, W = p.Wo;
+  if (t < 320) {
+    const float v = static_cast<float>(static_cast<double>(p.gate_fixed[t]) * (1.0 / 1048576.0));
+    if (t < 64) tot[t] = v;
+    else line[t - 64] = v;
+    if (blockIdx.x == 0 && p.gate_zero) p.gate_zero[t] = 0;
+  }
+  if (t >= 256) {
+    // corners: 0 = (0,0), 1 = (0,W-1), 2 = (H-1,0), 3 = (H-1,W-1)
+    const int b = (t - 256) >> 6, c = t & 63;
+    const long long pix = (b & 2 ? static_cast<long long>(H - 1) * W : 0) + (b & 1 ? W - 1 : 0);
+    const long long ps = p.out_plane_stride;       // the input has the output's geometry
+    const __half h = *reinterpret_cast<const __half*>(p.gate_u + (c >> 5) * ps + pix * 64 + (c & 31) * 2);
+    const __half_raw lr = __nv_cvt_fp8_to_halfraw(p.gate_u[2 * ps + pix * 64 + c], __NV_E5M2);
+    corner[b * 64 + c] = __half2float(h) + __half2float(*reinterpret_cast<const __half*>(&lr)) * p.lo_inv_scale;
+  }
+  // operands of the small MLP, requested now so their L2 round trip overlaps the phases below
+  float w1a = 0.f, w1b = 0.f, b1v = 0.f, b2v = 0.f;
+  const int mr = t >> 5, ml = t & 31;
+  if (mr < p.gate_R) {
+    w1a = __ldg(p.gate_w1 + mr * 64 + ml);
+    w1b = __ldg(p.gate_w1 + mr * 64 + ml + 32);
+    b1v = p.gate_b1 ? __ldg(p.gate_b1 + mr) : 0.f;
+  }
+  float w2v[4] = {0.f, 0.f, 0.f, 0.f};
+  const float bconv = (t < 64 && p.gate_b) ? __ldg(p.gate_b + t) : 0.f;
+  if (t < 64) {
+    b2v = p.gate_b2 ? __ldg(p.gate_b2 + t) : 0.f;
+    if (p.gate_R <= 4)
+      for (int k = 0; k < p.gate_R; ++k) w2v[k] = __ldg(p.gate_w2 + t * p.gate_R + k);
+  }
+  named_bar_sync(2, 512);
+  for (int i = t; i < 576; i += 512) {
+    const int tap = i >> 6, c = i & 63;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    float sft = tot[c];
+    if (dy == 1) sft -= line[0 * 64 + c];
+    if (dy == -1) sft -= line[1 * 64 + c];
+    if (dx == 1) sft -= line[2 * 64 + c];
+    if (dx == -1) sft -= line[3 * 64 + c];
+    if (dy != 0 && dx != 0) sft += corner[((dy == -1 ? 2 : 0) + (dx == -1 ? 1 : 0)) * 64 + c];
+    shifted[tap * 64 + c] = sft;
+  }
+  named_bar_sync(2, 512);
+  {
+    // mean of this conv's output per channel: W . shifted / (H W) + bias, with the weights read from the RESIDENT shared-
+    // memory copy the MMAs use (fp16 hi + lo = the fp32 weight to 2^-22; no second pass over the weights through L2):
+    // thread (co, part) takes input channels 8 part .. 8 part + 7 of every tap as one 16-byte chunk of the hi row and one
+    // of the lo row.  Row of channel c inside its group of 16: 2r -> r, 2r + 1 -> r + 8 (planes.fp16c_row_channels).
+    mbar_wait(w_bar, 0);
+    const int co = t >> 3, part = t & 7;
+    const int c16 = co & 15;
+    const int row_hi = 32 * (co >> 4) + ((c16 & 1) ? 8 + (c16 >> 1) : (c16 >> 1));
+    const int half = part >> 2, chunk = part & 3;
+    float acc = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const uint8_t* base = sW + tap * kW16TapBytes + half * 8192;
+      const float* sh = shifted + tap * 64 + 8 * part;
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        const int row = row_hi + 16 * pl;
+        const uint4 v = *reinterpret_cast<const uint4*>(base + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_f16x2(w4[k]);
+          acc = fmaf(f.x, sh[2 * k], acc);
+          acc = fmaf(f.y, sh[2 * k + 1], acc);
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (part == 0) mean[co] = acc / (static_cast<float>(H) * static_cast<float>(W));       // + bias below
+  }
+  named_bar_sync(2, 512);
+  if (t < 64) mean[t] += bconv;
+  named_bar_sync(2, 512);
+  if (mr < p.gate_R) {
+    float h = w1a * mean[ml] + w1b * mean[ml + 32];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if (ml == 0) hid[mr] = fmaxf(h + b1v, 0.f);
+  }
+  named_bar_sync(2, 512);
+  if (t < 64) {
+    float o = b2v;
+    if (p.gate_R <= 4) {
+      for (int k = 0; k < p.gate_R; ++k) o += w2v[k] * hid[k];
+    } else {
+      for (int k = 0; k < p.gate_R; ++k) o += __ldg(p.gate_w2 + t * p.gate_R + k) * hid[k];
+    }
+    scale[t] = 1.0f / (1.0f + expf(-o));
+  }
+  named_bar_sync(2, 512);
+}
+
 // ACT: activation (-1 = from ConvParams); HAS_RES: a residual in the same three-plane format is added after the
 // activation; DBG: clock64() instrumentation of the barrier waits (perf experiments only, MTB200_HALO_DEBUG)
 // SUMS: channel (and border) sums of the output are wanted; EPI: 2 = exchange epilogue (four channels of one pixel per
 // thread, the default), 1 = pair epilogue (two channels of two pixels; the A/B partner)
-template <int ACT, bool HAS_RES, bool SUMS, bool DBG, int EPI>
+template <int ACT, bool HAS_RES, bool SUMS, bool DBG, int EPI, bool STREAM>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_c64_fp16c_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                          const __grid_constant__ CUtensorMap tmR, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;                         // resident weights (A operand): 9 x W16 tap blocks, then 9 x W8 tap blocks
-  uint8_t* sX = smem + kWBytes;               // ring of halo plane slots (B operand)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sX + kSlots * kSlotBytes);
-  uint64_t* empty_bar = full_bar + kSlots;
-  uint64_t* tfull_bar = empty_bar + kSlots;   // [2]
+  constexpr int kRes = STREAM ? kWBytesS : kWBytes;     // resident weight bytes
+  constexpr int kNS = STREAM ? kSlotsS : kSlots;        // ring slots (kRes + kNS * kSlotBytes is the same for both)
+  uint8_t* sX = smem + kRes;                  // ring of 20 KB slots: halo planes (B operand) and, STREAM, e5m2 weight taps
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sX + kNS * kSlotBytes);
+  uint64_t* empty_bar = full_bar + kMaxSlots;
+  uint64_t* tfull_bar = empty_bar + kMaxSlots;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint64_t* w_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* gate_s = reinterpret_cast<float*>(tmem_slot + 4);        // kGateFloats floats (only used with a fused gate)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kSlots; ++s) {
+    for (int s = 0; s < kNS; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -405,9 +528,13 @@ conv3x3_c64_fp16c_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      // resident weights: the host packed them in shared-memory order as 45 boxes of 64 rows x 64 B
-      mbar_expect_tx(w_bar, static_cast<uint32_t>(kWBytes));
-      for (int i = 0; i < kWBytes / 4096; ++i) tma_load_2d(sW + i * 4096, &tmW, w_bar, 0, i * 64);
+      // resident weights: the host packed them in shared-memory order as 45 boxes of 64 rows x 64 B (36 fp16 boxes, then
+      // one e5m2 box per tap); STREAM keeps only the e5m2 boxes of taps 5-8
+      mbar_expect_tx(w_bar, static_cast<uint32_t>(kRes));
+      for (int i = 0; i < kW16Bytes / 4096; ++i) tma_load_2d(sW + i * 4096, &tmW, w_bar, 0, i * 64);
+      for (int tap = STREAM ? kW8StreamTaps : 0; tap < 9; ++tap)
+        tma_load_2d(sW + kW16Bytes + (tap - (STREAM ? kW8StreamTaps : 0)) * kW8TapBytes, &tmW, w_bar, 0,
+                    (kW16Bytes / 4096 + tap) * 64);
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -434,11 +561,19 @@ conv3x3_c64_fp16c_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
             for (int pl = 0; pl < 3; ++pl) tma_prefetch_l2_4d(&tmR, 0, ptx * kTW, pty * kTH, pl * p.N + pn);
           }
         }
-        for (int pl = 0; pl < 3; ++pl) {
+        // ring order = the order in which the MMA warp releases the slots: fp16 plane 0, fp16 plane 1, [STREAM: e5m2 weights
+        // of taps 0-4,] e5m2 plane
+        for (int q = 0; q < (STREAM ? 4 : 3); ++q) {
           mbar_wait(&empty_bar[slot], phase ^ 1);
           mbar_expect_tx(&full_bar[slot], kSlotBytes);
-          tma_load_4d(sX + slot * kSlotBytes, &tmX, &full_bar[slot], 0, txi * kTW - 1, tyi * kTH - 1, pl * p.N + n);
-          if (++slot == kSlots) {
+          if (STREAM && q == 2) {
+            for (int tap = 0; tap < kW8StreamTaps; ++tap)
+              tma_load_2d(sX + slot * kSlotBytes + tap * kW8TapBytes, &tmW, &full_bar[slot], 0, (kW16Bytes / 4096 + tap) * 64);
+          } else {
+            const int pl = (STREAM && q == 3) ? 2 : q;
+            tma_load_4d(sX + slot * kSlotBytes, &tmX, &full_bar[slot], 0, txi * kTW - 1, tyi * kTH - 1, pl * p.N + n);
+          }
+          if (++slot == kNS) {
             slot = 0;
             phase ^= 1;
           }
@@ -452,13 +587,25 @@ conv3x3_c64_fp16c_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     tc_fence_after();
     // shared-window addresses from 32-bit arithmetic on the (uniform) window offset of the dynamic segment
     const uint32_t sw = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sx0 = sw + kWBytes;
+    const uint32_t sx0 = sw + kRes;
     int slot = 0;
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
     long long dbg_wfull = 0, dbg_wtempty = 0, dbg_tiles = 0;
     const long long dbg_t0 = DBG ? clock64() : 0;
+    auto next_slot = [&]() {
+      if (++slot == kNS) {
+        slot = 0;
+        phase ^= 1;
+      }
+    };
+    auto wait_full = [&]() {
+      const long long tf = DBG ? clock64() : 0;
+      mbar_wait(&full_bar[slot], phase);
+      if (DBG) dbg_wfull += clock64() - tf;
+      tc_fence_after();
+    };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const long long ta = DBG ? clock64() : 0;
       mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -468,37 +615,55 @@ conv3x3_c64_fp16c_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kAccCols);
+      // fp16 planes 0 / 1: channels [32 pl, 32 pl + 32) against the [W16_hi;W16_lo] rows of that half (the first MMA of a tile
+      // is one of these: M = 128 overwrites every accumulator lane)
 #pragma unroll
-      for (int pl = 0; pl < 3; ++pl) {
-        const long long tf = DBG ? clock64() : 0;
-        mbar_wait(&full_bar[slot], phase);
-        if (DBG) dbg_wfull += clock64() - tf;
-        tc_fence_after();
+      for (int pl = 0; pl < 2; ++pl) {
+        wait_full();
         if (elect_one()) {
           const uint32_t sx = sx0 + slot * kSlotBytes;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const int ky = tap / 3, kx = tap - ky * 3;
             const uint32_t b0 = sx + (ky * kHW + kx) * 64;
-            // planes 0/1: fp16 channels [32 pl, 32 pl + 32) against the [W16_hi;W16_lo] rows of that half (the first
-            // MMA of a tile is one of these: M = 128 overwrites every accumulator lane); plane 2: the e5m2 residuals
-            const uint32_t a0 = pl < 2 ? sw + tap * kW16TapBytes + pl * 8192 : sw + kW16Bytes + tap * kW8TapBytes;
+            const uint32_t a0 = sw + tap * kW16TapBytes + pl * 8192;
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const uint64_t da = make_sdesc_sw64(a0 + k * 32, 512, 0);
-              const uint64_t db = make_sdesc_sw64(b0 + k * 32, kHW * 64, 0);
-              if (pl < 2) umma_bf16(d_tmem, da, db, idesc16, (pl > 0 || tap > 0 || k > 0) ? 1u : 0u);
-              else umma_f8f6f4(d_tmem, da, db, idesc8, 1u);
-            }
+            for (int k = 0; k < 2; ++k)
+              umma_bf16(d_tmem, make_sdesc_sw64(a0 + k * 32, 512, 0), make_sdesc_sw64(b0 + k * 32, kHW * 64, 0), idesc16,
+                        (pl > 0 || tap > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[slot]);
         }
         __syncwarp();
-        if (++slot == kSlots) {
-          slot = 0;
-          phase ^= 1;
-        }
+        next_slot();
       }
+      // e5m2 plane (the rounding residuals) against the e5m2 weights; STREAM: the weights of taps 0-4 sit in the ring slot
+      // before the plane's, taps 5-8 are resident
+      int wslot = 0;
+      if (STREAM) {
+        wait_full();
+        wslot = slot;
+        next_slot();
+      }
+      wait_full();
+      if (elect_one()) {
+        const uint32_t sx = sx0 + slot * kSlotBytes;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - ky * 3;
+          const uint32_t b0 = sx + (ky * kHW + kx) * 64;
+          const uint32_t a0 = !STREAM ? sw + kW16Bytes + tap * kW8TapBytes
+                              : tap < kW8StreamTaps ? sx0 + wslot * kSlotBytes + tap * kW8TapBytes
+                                                    : sw + kW16Bytes + (tap - kW8StreamTaps) * kW8TapBytes;
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_f8f6f4(d_tmem, make_sdesc_sw64(a0 + k * 32, 512, 0), make_sdesc_sw64(b0 + k * 32, kHW * 64, 0), idesc8, 1u);
+          if (STREAM && tap == kW8StreamTaps - 1) umma_commit(&empty_bar[wslot]);
+        }
+        umma_commit(&empty_bar[slot]);
+      }
+      __syncwarp();
+      next_slot();
       if (elect_one()) umma_commit(&tfull_bar[as]);
       __syncwarp();
       if (++as == 2) {
@@ -522,11 +687,13 @@ conv3x3_c64_fp16c_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     L.px = 2 * (lane & 3) + (r & 1);
     L.c_own = 16 * L.q + 2 * r;
     L.c_recv = 16 * L.q + 2 * (r ^ 1);
+    const bool fused_gate = HAS_RES && p.gate_fixed != nullptr;
+    if (fused_gate) gate_prologue(p, gate_s, static_cast<int>(threadIdx.x) - 64, sW, w_bar);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int c = (k < 2 ? L.c_own : L.c_recv) + (k & 1);
       // the channel scale may be written by the kernel just before this one: plain loads, not the read-only path
-      L.s[k] = p.chan_scale ? p.chan_scale[c] : 1.0f;
+      L.s[k] = fused_gate ? gate_s[20 * 64 + c] : p.chan_scale ? p.chan_scale[c] : 1.0f;
       L.bs[k] = (p.bias ? __ldg(p.bias + c) : 0.0f) * L.s[k];
     }
     const int cb = 16 * L.q + 4 * (r >> 1);
@@ -779,6 +946,7 @@ int launch_conv_halo_fp16c(const CUtensorMap& tmX, const CUtensorMap& tmW, const
   const int epi_env = env_int("MTB200_FP16C_EPI", 0);          // 0 = per layer kind (below)
   const int pf_x = env_int("MTB200_FP16C_PF", 0);
   const int pf_res = env_int("MTB200_FP16C_RPF", 0);
+  const bool stream_w8 = env_int("MTB200_FP16C_STREAM", 1) != 0;     // e5m2 weights of taps 0-4 through the ring: a third slot
   p.debug = dbg_flags;
   p.pf_x = pf_x;
   p.pf_res = pf_res;
@@ -786,18 +954,24 @@ int launch_conv_halo_fp16c(const CUtensorMap& tmX, const CUtensorMap& tmW, const
   if (dbg)
     if (const char* e = getenv("MTB200_HALO_DEBUG_PTR")) p.dbg_out = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   MTB_REQUIRE(p.act == ACT_NONE || p.act == ACT_RELU, "fp16c conv: activation %d is not supported (none / relu)", p.act);
-  const size_t smem = 1024 + kWBytes + kSlots * kSlotBytes + 16 * 8 + 16;
+  static_assert(kWBytes + kSlots * kSlotBytes == kWBytesS + kSlotsS * kSlotBytes, "both variants use the same shared memory");
+  const size_t smem = 1024 + kWBytes + kSlots * kSlotBytes + 16 * 8 + 16 + kGateFloats * sizeof(float);
   int dev = 0, sms = 0;
   MTB_CUDA_OK(cudaGetDevice(&dev));
   MTB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long total = static_cast<long long>(p.N) * p.tiles_y * p.tiles_x;
   const int grid = static_cast<int>(total < sms ? total : sms);
   if (grid <= 0) return 0;
-#define MTB_LAUNCH_F(ACT, RES, SUMS, DBG, EPI)                                                                  \
+#define MTB_LAUNCH_S(ACT, RES, SUMS, DBG, EPI, STR)                                                             \
   do {                                                                                                          \
-    MTB_CUDA_OK(cudaFuncSetAttribute(conv3x3_c64_fp16c_kernel<ACT, RES, SUMS, DBG, EPI>,                        \
+    MTB_CUDA_OK(cudaFuncSetAttribute(conv3x3_c64_fp16c_kernel<ACT, RES, SUMS, DBG, EPI, STR>,                   \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));     \
-    conv3x3_c64_fp16c_kernel<ACT, RES, SUMS, DBG, EPI><<<grid, kThreads, smem, stream>>>(tmX, tmW, tmR, p);     \
+    conv3x3_c64_fp16c_kernel<ACT, RES, SUMS, DBG, EPI, STR><<<grid, kThreads, smem, stream>>>(tmX, tmW, tmR, p); \
+  } while (0)
+#define MTB_LAUNCH_F(ACT, RES, SUMS, DBG, EPI)                                   \
+  do {                                                                           \
+    if (stream_w8) MTB_LAUNCH_S(ACT, RES, SUMS, DBG, EPI, true);                 \
+    else MTB_LAUNCH_S(ACT, RES, SUMS, DBG, EPI, false);                          \
   } while (0)
 #define MTB_PICK_EPI(ACT, RES, SUMS, DBG)                                        \
   do {                                                                           \
@@ -822,7 +996,7 @@ int launch_conv_halo_fp16c(const CUtensorMap& tmX, const CUtensorMap& tmW, const
   const bool res = p.residual != nullptr;
   const bool sums = p.tile_sums != nullptr;
   // exchange epilogue where a residual is read (its loads and stores halve), pair epilogue otherwise (measured A/B)
-  const int epi = epi_env ? epi_env : (res ? 2 : 1);
+  const int epi = (p.gate_fixed != nullptr) ? 2 : epi_env ? epi_env : (res ? 2 : 1);
   if (dbg) MTB_PICK_ACT(true);
   else MTB_PICK_ACT(false);
 #undef MTB_PICK_ACT
@@ -830,6 +1004,7 @@ int launch_conv_halo_fp16c(const CUtensorMap& tmX, const CUtensorMap& tmW, const
 #undef MTB_PICK_RA
 #undef MTB_PICK_EPI
 #undef MTB_LAUNCH_F
+#undef MTB_LAUNCH_S
   MTB_CUDA_OK(cudaGetLastError());
   return 0;
 }

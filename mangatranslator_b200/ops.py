@@ -84,6 +84,16 @@ class ConvPlan:
         check(l.mtb_conv_plan_set_fixed_sums(self._h, ptr(fixed)), "mtb_conv_plan_set_fixed_sums")
         self._keep = self._keep + (fixed,)
 
+    def set_fused_gate(self, fixed_in, fixed_zero, u, conv_w, conv_b, w1, b1, w2, b2) -> None:
+        """fp16c plans, an RCAB's second conv: compute the CALayer gate in this launch's prologue from the fixed-point sums
+        the first conv accumulated (`fixed_in`), zero `fixed_zero` for the next block (include/mtb200.h)."""
+        l = lib()
+        l.mtb_conv_plan_set_fused_gate.argtypes = [C.c_void_p] * 10 + [C.c_int]
+        l.mtb_conv_plan_set_fused_gate.restype = C.c_int
+        check(l.mtb_conv_plan_set_fused_gate(self._h, ptr(fixed_in), ptr(fixed_zero), ptr(u), ptr(conv_w), ptr(conv_b), ptr(w1),
+                                             ptr(b1), ptr(w2), ptr(b2), int(w1.shape[0])), "mtb_conv_plan_set_fused_gate")
+        self._keep = self._keep + (fixed_in, fixed_zero, u, conv_w, conv_b, w1, b1, w2, b2)
+
     def run(self) -> None:
         check(lib().mtb_conv_plan_run(self._h, stream_ptr()), "mtb_conv_plan_run")
 

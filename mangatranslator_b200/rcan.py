@@ -94,6 +94,8 @@ class RcanB200:
         self.lo_shift = int(lo_shift)
         # channel sums for the RCAB gate as fixed-point integer atomics (default) or as per-CTA float rows (A/B partner)
         self.fixed_sums = os.environ.get("MTB200_RCAN_FIXED_SUMS", "1") != "0"
+        # the gate computed in the prologue of the block's second conv (no launch of its own) or by mtb_rcan_gate_fp16c
+        self.fused_gate = self.fixed_sums and os.environ.get("MTB200_RCAN_FUSED_GATE", "1") != "0"
         self.precision = precision
         self.cfg = infer_config(state_dict)
         self.rgb_range, self.norm, self.conv_mode = float(rgb_range), bool(norm), conv_mode
@@ -185,8 +187,11 @@ class RcanB200:
         # layer (bf16x3); otherwise the gate kernel reads the four lines of u itself
         border = torch.zeros((parts, 4, f), dtype=torch.float32, device=dev)
         b["border"] = None
-        b["fixed"] = torch.zeros((5, f), dtype=torch.int64, device=dev)     # fp16c: fixed-point sums (integer atomics)
+        # fp16c: fixed-point sums (integer atomics); two buffers alternate between consecutive blocks when the gate is fused
+        b["fixed2"] = torch.zeros((2, 5, f), dtype=torch.int64, device=dev)
+        b["fixed"] = b["fixed2"][0]
         src = body_in
+        nblk = 0
         for gi, (grp, tailw) in enumerate(self.blocks):
             grp_in = src
             x = grp_in
@@ -195,11 +200,19 @@ class RcanB200:
                 c1 = bconv(x, w1, b["u"], act="relu", tile_sums=sums)
                 if c1.set_border_sums(border):
                     b["border"] = border
+                fuse = self.fp16c and self.fused_gate and cd1.shape[0] <= 16
+                fx = b["fixed2"][nblk % 2] if fuse else b["fixed"]
                 if self.fp16c and self.fixed_sums:
-                    c1.set_fixed_sums(b["fixed"])
+                    c1.set_fixed_sums(fx)
                 steps.append(("conv_body", c1))
-                steps.append(("gate", (parts, w2f, b2f, cd1, cb1, cd2, cb2)))
-                steps.append(("conv_body", bconv(b["u"], w2, dst, residual=x, channel_scale=b["scale"])))
+                if fuse:
+                    c2 = bconv(b["u"], w2, dst, residual=x)
+                    c2.set_fused_gate(fx, b["fixed2"][(nblk + 1) % 2], b["u"], w2f, b2f, cd1, cb1, cd2, cb2)
+                    steps.append(("conv_body", c2))
+                else:
+                    steps.append(("gate", (parts, w2f, b2f, cd1, cb1, cd2, cb2)))
+                    steps.append(("conv_body", bconv(b["u"], w2, dst, residual=x, channel_scale=b["scale"])))
+                nblk += 1
                 x = dst
             gout = b["g0"] if grp_in is not b["g0"] else b["g1"]
             steps.append(("conv", bconv(x, tailw, gout, residual=grp_in)))   # group tail conv + group skip
@@ -245,7 +258,7 @@ class RcanB200:
     def _run_body(self, b: dict, h: int, w: int) -> None:
         l, st = self.l, stream_ptr()
         if self.fp16c and self.fixed_sums:
-            b["fixed"].zero_()                 # the gate leaves them zeroed; this only matters after an aborted pass
+            b["fixed2"].zero_()                # the gate leaves them zeroed; this only matters after an aborted pass
         for kind, arg in b["steps"]:
             self._run_step(b, kind, arg, h, w, st)
 
@@ -282,6 +295,8 @@ class RcanB200:
         hb, wb = self.body_hw(h, w)
         evs = []
         st = stream_ptr()
+        if self.fp16c and self.fixed_sums:
+            b["fixed2"].zero_()
         for kind, arg in b["steps"]:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

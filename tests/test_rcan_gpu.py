@@ -271,3 +271,31 @@ def test_plain_bf16_mode_is_close():
     torch.cuda.synchronize()
     err = (out_f.cpu().permute(2, 0, 1).unsqueeze(0) - ref_f).abs().max().item()
     assert err < 5e-2, err
+
+
+def test_fused_gate_equals_the_gate_kernel(monkeypatch):
+    """The RCAB gate computed in the prologue of the block's second conv (default) against the stand-alone gate kernel fed
+    by the same fixed-point sums, and against per-CTA float rows: the same network output to float noise, on an odd number
+    of blocks (the two accumulator buffers alternate) and a frame with partial tiles."""
+    from mangatranslator_b200.rcan import RcanB200
+    dev = torch.device("cuda:0")
+    m = rcan_oracle.make_model(9, n_resgroups=1, n_resblocks=3)
+    rgb = torch.from_numpy(np.random.default_rng(9).integers(0, 256, size=(70, 90, 3), dtype=np.uint8)).to(dev)
+    outs = {}
+    for name, env in (("fused", {}), ("gate_kernel", {"MTB200_RCAN_FUSED_GATE": "0"}), ("float_rows", {"MTB200_RCAN_FIXED_SUMS": "0"})):
+        for k in ("MTB200_RCAN_FUSED_GATE", "MTB200_RCAN_FIXED_SUMS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        net = RcanB200(m.state_dict(), dev, precision="fp16c")
+        assert net.fused_gate == (name == "fused")
+        a = net.upscale_u8(rgb, want_float=True)[1].clone()
+        b = net.upscale_u8(rgb, want_float=True)[1].clone()       # second call replays the captured graph
+        assert torch.equal(a, b)
+        outs[name] = a
+    # the three differ in the summation order of the gate's inputs (~1e-7 on a gate); a gate that moves by one float ulp can
+    # flip the fp16 / e5m2 rounding of an activation, hence the format-level bound
+    d1 = (outs["fused"] - outs["gate_kernel"]).abs().max().item()
+    d2 = (outs["fused"] - outs["float_rows"]).abs().max().item()
+    print(f"fused gate vs gate kernel {d1:.2e}, vs float rows {d2:.2e}")
+    assert d1 < 5e-5 and d2 < 5e-5

@@ -18,7 +18,7 @@ dev = torch.device("cuda:0")
 net = RcanB200(W.rcan_state_dict(0, n_resgroups=int(os.environ.get("SWEEP_GROUPS", "3"))), dev, precision="fp16c")
 img = torch.randint(0, 256, (1536, 1024, 3), dtype=torch.uint8, device=dev)
 net.time_steps(img)
-configs = [dict(MTB200_FP16C_EPI=e, MTB200_FP16C_PF=pf) for e in (0, 1, 2) for pf in (0, 2)]
+configs = [dict(MTB200_FP16C_STREAM=st, MTB200_FP16C_PF=pf) for st in (1, 0) for pf in (0, 2)]
 acc = {i: [] for i in range(len(configs))}
 for rep in range(int(os.environ.get("SWEEP_REPS", "6"))):
     for i, cfg in enumerate(configs):
