@@ -31,6 +31,15 @@ WORKLOAD = ("Batch 64 synthetic 1536x1024 pages, full detect->segment->clean->2x
 H, W, BUBBLES = 1536, 1024, 12
 
 
+_REAL_STDOUT = sys.stdout
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of this program goes to the real stdout; everything else the libraries and the page driver print
+    (weight-source notices, progress) is routed to stderr (see main)."""
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -239,7 +248,7 @@ def run_reference(args, coord):
                             note="value = 1 / (measured detect + segment + clean seconds + crop RCAN seconds x pixel ratio); "
                                  "ms_per_step = wall time of one sample step, not of a 64-page batch"),
                 cpu_baseline=base, e2e=dict(value=v, unit="pages/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
 
 
 def measure_dominant_kernel(pipe, page_dev, peaks):
@@ -496,7 +505,7 @@ def run_ours(args, coord):
         line["cpu_baseline"] = base
     if gbase is not None:
         line["gpu_baseline"] = gbase
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_corpus(args, coord):
@@ -580,7 +589,7 @@ def run_corpus(args, coord):
                     clocks=clocks,
                     e2e=dict(value=n / wall_max, unit="files/s", h2d_bytes_per_step=n * H * W * 3, d2h_bytes_per_step=n * 4 * H * W * 3),
                     gpu_launches=None)
-        print(json.dumps(line))
+        emit(line)
         shutil.rmtree(root, ignore_errors=True)
     coord.barrier()
 
@@ -604,8 +613,9 @@ def main():
                     help="PNG encoder of the batch path: PIL on host threads, or the device deflate encoder")
     ap.add_argument("--save-workers", type=int, default=0, help="writer threads per rank (0 = host cores / ranks - 1)")
     args = ap.parse_args()
+    sys.stdout = sys.stderr                       # stdout carries the JSON line only
     if args.only_gpu_baseline:
-        print(json.dumps(dict(gpu_baseline=gpu_baseline(torch.device("cuda", 0)))))
+        emit(dict(gpu_baseline=gpu_baseline(torch.device("cuda", 0))))
         return
     from mangatranslator_b200.core.batch_coordinator import PageShardCoordinator
     if args.impl == "reference":
