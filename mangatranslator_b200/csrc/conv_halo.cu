@@ -19,6 +19,13 @@
 #include "conv_gemm.cuh"
 #include "epilogue.cuh"
 
+// The clock64() / skip-stage instrumentation of this kernel (ConvParams::debug, MTB200_HALO_DEBUG) is compiled OUT of the
+// product library: build with `make EXTRA=-DMTB_HALO_DEBUG=1` to get it back for a perf experiment.
+#ifndef MTB_HALO_DEBUG
+#define MTB_HALO_DEBUG 0
+#endif
+#define HALO_DBG(p) (MTB_HALO_DEBUG ? (p).debug : 0)
+
 namespace mtb {
 
 namespace {
@@ -107,7 +114,7 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
         for (int pl = 0; pl < PLANES; ++pl) {
           mbar_wait(&empty_bar[slot], phase ^ 1);
-          if (p.debug & 4) {
+          if (HALO_DBG(p) & 4) {
             mbar_arrive(&full_bar[slot]);
           } else {
             mbar_expect_tx(&full_bar[slot], kHaloBytes);
@@ -133,24 +140,24 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     long long dbg_wfull = 0, dbg_wtempty = 0, dbg_tiles = 0;
     const long long dbg_t0 = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const long long ta = (p.debug & 32) ? clock64() : 0;
+      const long long ta = (HALO_DBG(p) & 32) ? clock64() : 0;
       mbar_wait(&tempty_bar[as], aphase ^ 1);
-      if (p.debug & 32) {
+      if (HALO_DBG(p) & 32) {
         dbg_wtempty += clock64() - ta;
         ++dbg_tiles;
       }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * ACC_COLS);
       for (int pl = 0; pl < PLANES; ++pl) {
-        const long long tf = (p.debug & 32) ? clock64() : 0;
+        const long long tf = (HALO_DBG(p) & 32) ? clock64() : 0;
         mbar_wait(&full_bar[slot], phase);
-        if (p.debug & 32) dbg_wfull += clock64() - tf;
+        if (HALO_DBG(p) & 32) dbg_wfull += clock64() - tf;
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(sA + slot * kSlotBytes);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            if ((p.debug & 2) && tap > 0) continue;
+            if ((HALO_DBG(p) & 2) && tap > 0) continue;
             const int ky = tap / 3, kx = tap - ky * 3;
             const uint32_t a0 = sa + (ky * kHW + kx) * 128;
             const uint32_t b0 = sw + tap * kTapBytes;
@@ -177,7 +184,7 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         aphase ^= 1;
       }
     }
-    if ((p.debug & 32) && p.dbg_out && lane == 0) {
+    if ((HALO_DBG(p) & 32) && p.dbg_out && lane == 0) {
       p.dbg_out[blockIdx.x * 16 + 4] = dbg_wfull;
       p.dbg_out[blockIdx.x * 16 + 5] = dbg_wtempty;
       p.dbg_out[blockIdx.x * 16 + 6] = dbg_tiles;
@@ -221,7 +228,7 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      epilogue_chunk16<ACT>(p, v, valid && !(p.debug & 1), pix, c0, n, oy, ox, lane, q, tile, cta_sum);
+      epilogue_chunk16<ACT>(p, v, valid && !(HALO_DBG(p) & 1), pix, c0, n, oy, ox, lane, q, tile, cta_sum);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;

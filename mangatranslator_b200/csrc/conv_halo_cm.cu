@@ -30,6 +30,13 @@
 #include "conv_gemm.cuh"
 #include "epilogue.cuh"
 
+// The clock64() / skip-stage instrumentation of this kernel (ConvParams::debug, MTB200_HALO_DEBUG) is compiled OUT of the
+// product library: build with `make EXTRA=-DMTB_HALO_DEBUG=1` to get it back for a perf experiment.
+#ifndef MTB_HALO_DEBUG
+#define MTB_HALO_DEBUG 0
+#endif
+#define HALO_DBG(p) (MTB_HALO_DEBUG ? (p).debug : 0)
+
 namespace mtb {
 
 namespace {
@@ -123,7 +130,7 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
         // pull the tile two iterations ahead into L2: with only two plane slots a TMA load has one plane's worth of
         // MMAs (~2.6 us) to land, which HBM latency under store traffic does not always meet
-        if (!(p.debug & 8)) {
+        if (!(HALO_DBG(p) & 8)) {
           const int pt = tile + 2 * gridDim.x;
           if (pt < total_tiles) {
             const int pn = pt / tiles_per_img;
@@ -133,16 +140,16 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           }
         }
         for (int pl = 0; pl < 2; ++pl) {
-          const long long te = (p.debug & 16) ? clock64() : 0;
+          const long long te = (HALO_DBG(p) & 16) ? clock64() : 0;
           mbar_wait(&empty_bar[slot], phase ^ 1);
-          const long long ti = (p.debug & 16) ? clock64() : 0;
-          if (p.debug & 4) {
+          const long long ti = (HALO_DBG(p) & 16) ? clock64() : 0;
+          if (HALO_DBG(p) & 4) {
             mbar_arrive(&full_bar[slot]);
           } else {
             mbar_expect_tx(&full_bar[slot], kSlotBytes);
             tma_load_4d(sX + slot * kSlotBytes, &tmX, &full_bar[slot], 0, txi * kTW - 1, tyi * kTH - 1, pl * p.N + n);
           }
-          if (p.debug & 16) {   // experiment: time from TMA issue to landing, and the wait for a free slot
+          if (HALO_DBG(p) & 16) {   // experiment: time from TMA issue to landing, and the wait for a free slot
             mbar_wait(&full_bar[slot], phase);
             dbg_tma += clock64() - ti;
             dbg_empty += ti - te;
@@ -154,7 +161,7 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           }
         }
       }
-      if ((p.debug & 16) && p.dbg_out) {
+      if ((HALO_DBG(p) & 16) && p.dbg_out) {
         p.dbg_out[blockIdx.x * 16 + 0] = dbg_tma;
         p.dbg_out[blockIdx.x * 16 + 1] = dbg_empty;
         p.dbg_out[blockIdx.x * 16 + 2] = dbg_n;
@@ -174,24 +181,24 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     long long dbg_wfull = 0, dbg_wtempty = 0, dbg_tiles = 0;
     const long long dbg_t0 = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const long long ta = (p.debug & 32) ? clock64() : 0;
+      const long long ta = (HALO_DBG(p) & 32) ? clock64() : 0;
       mbar_wait(&tempty_bar[as], aphase ^ 1);
-      if (p.debug & 32) {
+      if (HALO_DBG(p) & 32) {
         dbg_wtempty += clock64() - ta;
         ++dbg_tiles;
       }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kAccCols);
       for (int pl = 0; pl < 2; ++pl) {
-        const long long tf = (p.debug & 32) ? clock64() : 0;
+        const long long tf = (HALO_DBG(p) & 32) ? clock64() : 0;
         mbar_wait(&full_bar[slot], phase);
-        if (p.debug & 32) dbg_wfull += clock64() - tf;
+        if (HALO_DBG(p) & 32) dbg_wfull += clock64() - tf;
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sx = sx0 + slot * kSlotBytes;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            if ((p.debug & 2) && tap > 0) continue;
+            if ((HALO_DBG(p) & 2) && tap > 0) continue;
             const int ky = tap / 3, kx = tap - ky * 3;
             const uint32_t a0 = sw + tap * kTapBytes;
             const uint32_t b0 = sx + (ky * kHW + kx) * 128;
@@ -217,7 +224,7 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         aphase ^= 1;
       }
     }
-    if ((p.debug & 32) && p.dbg_out && lane == 0) {
+    if ((HALO_DBG(p) & 32) && p.dbg_out && lane == 0) {
       p.dbg_out[blockIdx.x * 16 + 4] = dbg_wfull;
       p.dbg_out[blockIdx.x * 16 + 5] = dbg_wtempty;
       p.dbg_out[blockIdx.x * 16 + 6] = dbg_tiles;
@@ -251,7 +258,7 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       // this lane's pixels of chunk ci: tile row 2*ci + upper, columns ox0 .. ox0+3, channels cpair, cpair+1
       const int oy0 = tyi * kTH + (upper ? 1 : 0);
       const int ox0 = txi * kTW + (odd ? 4 : 0);
-      const int nvalid = (p.debug & 1) ? 0 : min(4, p.Wo - ox0);            // valid columns (<= 0: none)
+      const int nvalid = (HALO_DBG(p) & 1) ? 0 : min(4, p.Wo - ox0);            // valid columns (<= 0: none)
       const long long off0 = ((static_cast<long long>(n) * p.Ho + oy0) * p.Wo + ox0) * 64 + cpair;
       // residual words of the first chunk are requested before the accumulator is waited for
       uint32_t rh[4] = {0u, 0u, 0u, 0u}, rl[4] = {0u, 0u, 0u, 0u};
@@ -267,9 +274,9 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             }
         }
       }
-      const long long tw = (p.debug & 32) ? clock64() : 0;
+      const long long tw = (HALO_DBG(p) & 32) ? clock64() : 0;
       mbar_wait(&tfull_bar[as], aphase);
-      const long long tw1 = (p.debug & 32) ? clock64() : 0;
+      const long long tw1 = (HALO_DBG(p) & 32) ? clock64() : 0;
       dbg_wtfull += tw1 - tw;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * kAccCols);
@@ -378,7 +385,7 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           }
           fence_proxy_async();
           named_bar_sync(1 + wj, 128);
-          if (q == 0 && lane == 0 && !(p.debug & 1)) {
+          if (q == 0 && lane == 0 && !(HALO_DBG(p) & 1)) {
             tma_store_4d(&tmO, stg, 0, txi * kTW, tyi * kTH + 2 * ci, n);
             tma_store_4d(&tmO, stg + 2048, 0, txi * kTW, tyi * kTH + 2 * ci, p.N + n);
             bulk_commit_group();
@@ -421,14 +428,14 @@ conv3x3_c64_cm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           }
         }
       }
-      if (p.debug & 32) dbg_work += clock64() - tw1;
+      if (HALO_DBG(p) & 32) dbg_work += clock64() - tw1;
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
       }
     }
     if (kStaged && q == 0 && lane == 0) bulk_wait_all0();      // all staged stores have landed
-    if ((p.debug & 32) && p.dbg_out && lane == 0 && (warp == 2 || warp == 17)) {
+    if ((HALO_DBG(p) & 32) && p.dbg_out && lane == 0 && (warp == 2 || warp == 17)) {
       p.dbg_out[blockIdx.x * 16 + (warp == 2 ? 8 : 10)] = dbg_wtfull;
       p.dbg_out[blockIdx.x * 16 + (warp == 2 ? 9 : 11)] = dbg_work;
     }
