@@ -31,13 +31,29 @@ WORKLOAD = ("Batch 64 synthetic 1536x1024 pages, full detect->segment->clean->2x
 H, W, BUBBLES = 1536, 1024, 12
 
 
-_REAL_STDOUT = sys.stdout
+_REAL_STDOUT_FD = None
+
+
+def _stdout_carries_only_the_json_line() -> None:
+    """File descriptor 1 is pointed at stderr for the rest of the process and the real stdout kept aside: whatever Python
+    code (weight-source notices, the page driver's progress) or native libraries (NCCL prints its version banner to fd 1)
+    write goes to stderr, and `emit` alone writes to stdout."""
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
 
 
 def emit(line: dict) -> None:
-    """The ONE JSON line of this program goes to the real stdout; everything else the libraries and the page driver print
-    (weight-source notices, progress) is routed to stderr (see main)."""
-    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
+    """The ONE JSON line of this program, on the real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT_FD, data)
 
 
 def load_peaks():
@@ -613,7 +629,7 @@ def main():
                     help="PNG encoder of the batch path: PIL on host threads, or the device deflate encoder")
     ap.add_argument("--save-workers", type=int, default=0, help="writer threads per rank (0 = host cores / ranks - 1)")
     args = ap.parse_args()
-    sys.stdout = sys.stderr                       # stdout carries the JSON line only
+    _stdout_carries_only_the_json_line()
     if args.only_gpu_baseline:
         emit(dict(gpu_baseline=gpu_baseline(torch.device("cuda", 0))))
         return
