@@ -581,7 +581,7 @@ def run_corpus(args, coord):
     stage = P.STAGE_CLOCK.snapshot()
     wall_max = coord.all_reduce_max(wall)
     stage_max = {k: coord.all_reduce_max(stage.get(k, 0.0)) for k in ("decode", "decode_wait", "render", "render_host_prep",
-                                                                     "render_device", "render_device_png", "render_to_pil",
+                                                                     "render_device", "render_device_png", "render_to_pil", "prep_ahead",
                                                                      "save_wait", "encode", "bubbles")}
     ok = res["success_count"] if coord.rank == 0 else 0
     if coord.rank == 0:

@@ -154,6 +154,54 @@ _FAST: Dict[tuple, "HotPathPipeline"] = {}
 _PNG = {}
 
 
+class _PinnedPages:
+    """Pinned BGR staging buffers for decoded pages, a few per page size: the thread that decodes page i + 1 also converts it
+    and fills one while page i is on the device, so neither the RGB conversion nor the copy into pinned memory sits on the
+    page loop's critical path (cudaHostAlloc per page would cost more than it saves, hence the pool)."""
+
+    def __init__(self, per_size: int = 3):
+        import threading
+        self._lock, self._free, self._made, self._per = threading.Lock(), {}, {}, per_size
+
+    def acquire(self, h: int, w: int):
+        with self._lock:
+            free = self._free.setdefault((h, w), [])
+            if free:
+                return free.pop()
+            if self._made.get((h, w), 0) >= self._per:
+                return None                              # all in flight: the caller falls back to the unpinned path
+            if len(self._made) >= 4 and (h, w) not in self._made:
+                return None
+            self._made[(h, w)] = self._made.get((h, w), 0) + 1
+        return torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
+
+    def release(self, buf) -> None:
+        with self._lock:
+            self._free.setdefault((int(buf.shape[0]), int(buf.shape[1])), []).append(buf)
+
+
+_PINNED = _PinnedPages()
+
+
+def _load_page_prepared(image_path, config: MangaTranslatorConfig) -> Image.Image:
+    """`_load_page` for the decode-ahead thread: additionally, for pages the device engine can take (opaque RGB / RGBA / L,
+    `cleaning_only`), the BGR copy the engine uploads is made here, into a pinned buffer attached to the image."""
+    pil = _load_page(image_path)
+    try:
+        if (config.cleaning_only and os.environ.get("MTB200_FAST_PATH", "1") != "0" and torch.cuda.is_available()
+                and pil.mode in ("RGB", "RGBA", "L") and not (pil.mode == "RGBA" and pil.getextrema()[3][0] < 255)):
+            t0 = time.perf_counter()
+            rgb = np.asarray(pil if pil.mode == "RGB" else pil.convert("RGB"))
+            buf = _PINNED.acquire(rgb.shape[0], rgb.shape[1])
+            if buf is not None:
+                np.copyto(buf.numpy(), rgb[:, :, ::-1])
+                pil._mtb_bgr_pinned = buf
+            STAGE_CLOCK.add("prep_ahead", time.perf_counter() - t0)
+    except Exception:
+        pass                                             # preparation is an optimisation: the page itself is fine
+    return pil
+
+
 def _png_encoder(device):
     from mangatranslator_b200.png_device import PngEncoderB200
     if device not in _PNG:
@@ -227,9 +275,12 @@ def _render_fast(pipe: "HotPathPipeline", pil: Image.Image, config: MangaTransla
     `png_mode` ("RGB" / "RGBA") the finished page is PNG-encoded on the device and only the compressed bytes come back."""
     from mangatranslator_b200._lib import device_section
     t_prep = time.perf_counter()
-    rgb = np.asarray(pil if pil.mode == "RGB" else pil.convert("RGB"))
-    h, w = rgb.shape[:2]
-    STAGE_CLOCK.add("render_host_prep", time.perf_counter() - t_prep)
+    ahead = getattr(pil, "_mtb_bgr_pinned", None)        # filled by the decode-ahead thread (_load_page_prepared)
+    if ahead is not None:
+        h, w, rgb = int(ahead.shape[0]), int(ahead.shape[1]), None
+    else:
+        rgb = np.asarray(pil if pil.mode == "RGB" else pil.convert("RGB"))
+        h, w = rgb.shape[:2]
     with device_section:
         # pinned staging buffers are kept per page size (cudaHostAlloc per page costs more than the copy it speeds up)
         stage = pipe.__dict__.setdefault("_staging", {})
@@ -239,40 +290,54 @@ def _render_fast(pipe: "HotPathPipeline", pil: Image.Image, config: MangaTransla
                 stage.pop(next(iter(stage)))
             stage[key] = dict(inp=torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True))
         sb = stage[key]
-        np.copyto(sb["inp"].numpy(), rgb[:, :, ::-1])                    # BGR, like the cleaning stage wants
-        host = sb["inp"]
-        two_x = pipe.rcan is not None and abs(float(config.output.image_upscale_factor) - float(pipe.rcan.scale)) < 1e-9
-        if two_x and png_mode:
-            t0 = time.perf_counter()
-            out, dets, _ = pipe.run_page_device(host.to(pipe.device, non_blocking=True))    # RGB, 2H x 2W, stays on the device
-            torch.cuda.current_stream().synchronize()
-            STAGE_CLOCK.add("render_device", time.perf_counter() - t0)
-            STAGE_CLOCK.add("bubbles", float(len(dets)))
-            t0 = time.perf_counter()
-            data = _png_encoder(pipe.device).encode(out, out_channels=4 if png_mode == "RGBA" else 3, finalize=False)
-            STAGE_CLOCK.add("render_device_png", time.perf_counter() - t0)
-            return EncodedPng(data, (int(out.shape[1]), int(out.shape[0])), png_mode)
-        if two_x:
-            if "out" not in sb:
-                sb["out"] = torch.empty((pipe.rcan.scale * h, pipe.rcan.scale * w, 3), dtype=torch.uint8, pin_memory=True)
-            t0 = time.perf_counter()
-            out, dets, _ = pipe.run_page(host, out_host=sb["out"])      # RGB, 2H x 2W
-            STAGE_CLOCK.add("render_device", time.perf_counter() - t0)
-            STAGE_CLOCK.add("bubbles", float(len(dets)))
-            t0 = time.perf_counter()
-            img = Image.fromarray(out.numpy().copy())
-            STAGE_CLOCK.add("render_to_pil", time.perf_counter() - t0)
-            return img
-        page = host.to(pipe.device)
-        dets = detect_pages_device([page], confidence=pipe.confidence, imgsz=pipe.imgsz, seg_model="sam2", **pipe.conjoined)[0]
-        batch = clean_pages_device([page], [dets], thresholding_value=pipe.thr, roi_shrink_px=pipe.shrink,
-                                   use_otsu_threshold=pipe.otsu, processing_scale=_processing_scale(pil.width, pil.height,
-                                                                                                  config.preprocessing.auto_scale))
-        if png_mode and not config.output.upscale_final_image:
-            out = batch.pages_out[0][:, :, [2, 1, 0]].contiguous()
-            data = _png_encoder(pipe.device).encode(out, out_channels=4 if png_mode == "RGBA" else 3, finalize=False)
-            return EncodedPng(data, (int(out.shape[1]), int(out.shape[0])), png_mode)
-        cleaned = Image.fromarray(np.ascontiguousarray(batch.pages_out[0].cpu().numpy()[:, :, ::-1]))
+        if ahead is not None:
+            host = ahead
+        else:
+            np.copyto(sb["inp"].numpy(), rgb[:, :, ::-1])                    # BGR, like the cleaning stage wants
+            host = sb["inp"]
+        STAGE_CLOCK.add("render_host_prep", time.perf_counter() - t_prep)
+        try:
+            return _render_fast_device(pipe, pil, config, png_mode, host, sb, h, w)
+        finally:
+            if ahead is not None:                        # every path below has synchronised: the upload is done
+                pil._mtb_bgr_pinned = None
+                _PINNED.release(ahead)
+
+
+def _render_fast_device(pipe: "HotPathPipeline", pil: Image.Image, config: MangaTranslatorConfig, png_mode, host, sb, h: int, w: int):
+    """The device half of `_render_fast` (called inside the device section with the page in a pinned BGR buffer)."""
+    two_x = pipe.rcan is not None and abs(float(config.output.image_upscale_factor) - float(pipe.rcan.scale)) < 1e-9
+    if two_x and png_mode:
+        t0 = time.perf_counter()
+        out, dets, _ = pipe.run_page_device(host.to(pipe.device, non_blocking=True))    # RGB, 2H x 2W, stays on the device
+        torch.cuda.current_stream().synchronize()
+        STAGE_CLOCK.add("render_device", time.perf_counter() - t0)
+        STAGE_CLOCK.add("bubbles", float(len(dets)))
+        t0 = time.perf_counter()
+        data = _png_encoder(pipe.device).encode(out, out_channels=4 if png_mode == "RGBA" else 3, finalize=False)
+        STAGE_CLOCK.add("render_device_png", time.perf_counter() - t0)
+        return EncodedPng(data, (int(out.shape[1]), int(out.shape[0])), png_mode)
+    if two_x:
+        if "out" not in sb:
+            sb["out"] = torch.empty((pipe.rcan.scale * h, pipe.rcan.scale * w, 3), dtype=torch.uint8, pin_memory=True)
+        t0 = time.perf_counter()
+        out, dets, _ = pipe.run_page(host, out_host=sb["out"])      # RGB, 2H x 2W
+        STAGE_CLOCK.add("render_device", time.perf_counter() - t0)
+        STAGE_CLOCK.add("bubbles", float(len(dets)))
+        t0 = time.perf_counter()
+        img = Image.fromarray(out.numpy().copy())
+        STAGE_CLOCK.add("render_to_pil", time.perf_counter() - t0)
+        return img
+    page = host.to(pipe.device)
+    dets = detect_pages_device([page], confidence=pipe.confidence, imgsz=pipe.imgsz, seg_model="sam2", **pipe.conjoined)[0]
+    batch = clean_pages_device([page], [dets], thresholding_value=pipe.thr, roi_shrink_px=pipe.shrink,
+                               use_otsu_threshold=pipe.otsu, processing_scale=_processing_scale(pil.width, pil.height,
+                                                                                              config.preprocessing.auto_scale))
+    if png_mode and not config.output.upscale_final_image:
+        out = batch.pages_out[0][:, :, [2, 1, 0]].contiguous()
+        data = _png_encoder(pipe.device).encode(out, out_channels=4 if png_mode == "RGBA" else 3, finalize=False)
+        return EncodedPng(data, (int(out.shape[1]), int(out.shape[0])), png_mode)
+    cleaned = Image.fromarray(np.ascontiguousarray(batch.pages_out[0].cpu().numpy()[:, :, ::-1]))
     if config.output.upscale_final_image:      # any other factor: the wrapper's pass loop + exact-size resample
         cleaned = upscale_image(cleaned, config.output.image_upscale_factor, model_type=config.output.image_upscale_model,
                                 verbose=config.verbose)
@@ -568,7 +633,7 @@ def batch_translate_images(input_dir, config: MangaTranslatorConfig, output_dir=
 
     def prefetch(j):
         if saver is not None and j < total and j not in decode:
-            decode[j] = saver.submit_unbounded(_load_page, mine[j])
+            decode[j] = saver.submit_unbounded(_load_page_prepared, mine[j], config)
 
     try:
         for i, path in enumerate(mine):

@@ -10,6 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import heapq
 import struct
+import threading
 import zlib
 from typing import Dict, Tuple
 
@@ -207,8 +208,27 @@ class PngEncoderB200:
                 hist=torch.zeros(288, dtype=torch.int32, device=dev), adler=torch.zeros((segs, 2), dtype=torch.int64, device=dev),
                 staged=torch.empty(segs * STRIDE, dtype=torch.uint8, device=dev), sizes=torch.zeros(segs, dtype=torch.int32, device=dev),
                 out=torch.empty(segs * STRIDE, dtype=torch.uint8, device=dev),
-                host=torch.empty(segs * STRIDE, dtype=torch.uint8, pin_memory=True))
+                # pinned landing buffers rotate: the writer thread that wraps page i's stream in the PNG container still reads
+                # one while the device encodes page i + 1 (finalize=False); sized for a typical stream, grown on demand
+                host=[torch.empty(max(total // 2, 1 << 16), dtype=torch.uint8, pin_memory=True) for _ in range(3)],
+                free=[0, 1, 2], cv=threading.Condition())
         return self._bufs[key]
+
+    @staticmethod
+    def _acquire(b: dict, nbytes: int):
+        with b["cv"]:
+            while not b["free"]:
+                b["cv"].wait()
+            k = b["free"].pop()
+        if b["host"][k].numel() < nbytes:
+            b["host"][k] = torch.empty(int(nbytes * 1.25), dtype=torch.uint8, pin_memory=True)
+        return k
+
+    @staticmethod
+    def _release(b: dict, k: int) -> None:
+        with b["cv"]:
+            b["free"].append(k)
+            b["cv"].notify()
 
     def encode(self, img: torch.Tensor, out_channels: int = 0, finalize: bool = True):
         """img: device uint8 [H][W][3|4], RGB(A) order.  out_channels 4 with a 3-channel image writes an opaque RGBA file
@@ -233,16 +253,22 @@ class PngEncoderB200:
         offsets = torch.cumsum(sizes64, 0) - sizes64
         check(l.mtb_png_compact(ptr(b["staged"]), STRIDE, ptr(b["sizes"]), ptr(offsets), segs, ptr(b["out"]), st), "mtb_png_compact")
         nbytes = int(sizes64.sum().item())
-        b["host"][:nbytes].copy_(b["out"][:nbytes], non_blocking=True)
+        k = self._acquire(b, nbytes)
+        b["host"][k][:nbytes].copy_(b["out"][:nbytes], non_blocking=True)
         parts = b["adler"].cpu().numpy()
         torch.cuda.current_stream().synchronize()
-        raw = dict(deflate=b["host"][:nbytes].numpy().tobytes(), adler_parts=parts, total=total, w=w, h=h, oc=oc)
+        raw = dict(deflate=b["host"][k][:nbytes].numpy(), release=lambda: self._release(b, k), adler_parts=parts, total=total,
+                   w=w, h=h, oc=oc)
         return finalize_png(raw) if finalize else raw
 
 
 def finalize_png(raw: dict) -> bytes:
     """Deflate stream + Adler-32 partial sums -> the bytes of the PNG file (zlib header / trailer, IHDR, IDAT, IEND)."""
     adler = adler32_from_parts(raw["adler_parts"], raw["total"])
-    body = b"\x78\x01" + raw["deflate"] + struct.pack(">I", adler)
+    try:
+        body = b"\x78\x01" + raw["deflate"].tobytes() + struct.pack(">I", adler)
+    finally:
+        if raw.get("release"):
+            raw["release"]()                 # the pinned landing buffer goes back to the encoder
     ihdr = struct.pack(">IIBBBBB", raw["w"], raw["h"], 8, 6 if raw["oc"] == 4 else 2, 0, 0, 0)
     return b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", ihdr) + _chunk(b"IDAT", body) + _chunk(b"IEND", b"")
