@@ -440,16 +440,34 @@ def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.
     if seg_model == "sam2":
         sam = mm.load_sam2()[1].net
     out = []
+    # Phase 1 (several pages): the detector of EVERY page is enqueued first — letterbox, YOLO graph, decode, NMS, the
+    # reference's dedup, final rows gathered into a per-page slot (the graph's own output buffers are overwritten by the next
+    # page) — and the host reads all box tables with ONE synchronisation; phase 2 then runs segmentation page by page with no
+    # further host wait, so the grouping of page i + 1 on the host overlaps the device work of page i.  A single page keeps
+    # the older order: its SAM encoder is enqueued before the host waits for the box table.
+    npages = len(pages_bgr)
+    tables = torch.zeros((npages, 300, 8), dtype=torch.float32, device=pages_bgr[0].device) if npages else None
+    counts = torch.zeros((npages,), dtype=torch.int32, device=pages_bgr[0].device) if npages else None
+    enc0 = None
     for pi, page in enumerate(pages_bgr):
         h, w = int(page.shape[0]), int(page.shape[1])
         lb = letterbox_device(page, imgsz, swap_rb=True)
         g = yolo.forward_letterboxed(lb)
         det, cnt, final_idx = yolo.detect(g, confidence, (h, w), tuple(lb.shape[:2]), apply_reference_dedup=True)
-        # The SAM image encoder does not depend on the boxes: enqueue it before the host waits for the detector, so the
-        # box table's round trip and the host-side grouping below run under ~5 ms of encoder work instead of an idle GPU.
-        enc = sam.encode(page[:, :, [2, 1, 0]].contiguous()) if sam is not None else None
-        n_final = int(cnt[1].item())                                   # the one host sync of the detect stage
-        rows = det[final_idx[:n_final].long()].cpu().numpy() if n_final else np.zeros((0, 8), np.float32)
+        tables[pi].copy_(det[final_idx.long().clamp_(0, det.shape[0] - 1)])       # rows beyond the count are ignored below
+        counts[pi].copy_(cnt[1])
+        if npages == 1 and sam is not None:
+            # The SAM image encoder does not depend on the boxes: enqueue it before the host waits for the detector, so
+            # the box table's round trip and the host-side grouping run under ~5 ms of encoder work instead of an idle GPU.
+            enc0 = sam.encode(page[:, :, [2, 1, 0]].contiguous())
+    if npages:
+        counts_h = counts.cpu().numpy()                                            # the one host sync of the detect stage
+        tables_h = tables.cpu().numpy()
+    for pi, page in enumerate(pages_bgr):
+        h, w = int(page.shape[0]), int(page.shape[1])
+        enc = enc0 if npages == 1 else (sam.encode(page[:, :, [2, 1, 0]].contiguous()) if sam is not None else None)
+        n_final = int(counts_h[pi])
+        rows = tables_h[pi, :n_final] if n_final else np.zeros((0, 8), np.float32)
         boxes = rows[:, :4].astype(np.float32)
         confs = rows[:, 4].astype(np.float32)
         if injected_boxes is not None:

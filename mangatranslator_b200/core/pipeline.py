@@ -795,11 +795,17 @@ class HotPathPipeline:
         page by page.  `consume(i, out)` is called as each page's result becomes available (the upscaler's output is a
         static buffer that the next page overwrites).  Returns (outputs or None when consumed, detections, clean batch)."""
         n = len(pages_bgr)
-        dets = []
-        for i, page in enumerate(pages_bgr):
-            inj = None if injected_boxes is None or injected_boxes[i] is None else [injected_boxes[i]]
-            dets.append(detect_pages_device([page], confidence=self.confidence, imgsz=self.imgsz, seg_model=self.seg_model,
-                                            injected_boxes=inj, own_masks=n > 1, **self.conjoined)[0])
+        if injected_boxes is not None and any(b is None for b in injected_boxes):
+            dets = []
+            for i, page in enumerate(pages_bgr):
+                inj = None if injected_boxes[i] is None else [injected_boxes[i]]
+                dets.append(detect_pages_device([page], confidence=self.confidence, imgsz=self.imgsz, seg_model=self.seg_model,
+                                                injected_boxes=inj, own_masks=n > 1, **self.conjoined)[0])
+        else:
+            # the whole group in one call: every page's detector is enqueued before the host reads the box tables once
+            dets = detect_pages_device(list(pages_bgr), confidence=self.confidence, imgsz=self.imgsz, seg_model=self.seg_model,
+                                       injected_boxes=None if injected_boxes is None else list(injected_boxes),
+                                       own_masks=n > 1, **self.conjoined)
         scales = {_processing_scale(int(p.shape[1]), int(p.shape[0])) for p in pages_bgr}
         if len(scales) == 1:
             batch = clean_pages_device(list(pages_bgr), dets, thresholding_value=self.thr, roi_shrink_px=self.shrink,
