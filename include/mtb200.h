@@ -222,6 +222,11 @@ int mtb_maxpool(const void* x, void* y, int N, int H, int W, int ct_in, int ci, 
                 int planes, void* stream);
 int mtb_upsample2x(const void* x, void* y, int N, int H, int W, int ct_in, int ci, int ct_out, int co, int c, int planes,
                    void* stream);
+/* Depthwise k x k convolution (groups = channels; stride 1, pad k/2) + bias (+ SiLU when act != 0) on a channel slice of an
+ * NHWC plane tensor: ultralytics DWConv (YOLO11 class branch, detection.py:1817 panel model) and the positional convolution
+ * of the C2PSA / A2C2f attention blocks (YOLO12x OSB-text model, detection.py:120-201).  w: device fp32 [k*k][c]. */
+int mtb_dwconv(const void* x, void* y, int N, int H, int W, int ct_in, int ci, int ct_out, int co, int c, int k,
+               const float* w, const float* bias, int act, int planes, void* stream);
 
 typedef struct mtb_yolo_level {
   const float* box; /* device fp32 [N][H][W][64] DFL logits */

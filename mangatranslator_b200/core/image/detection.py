@@ -12,7 +12,12 @@ conjoined bubbles on every page (:1596-1619), SAM segments the group's union box
 the members by `mtb_split_conjoined` (mangatranslator_b200/conjoined.py holds the box geometry).  The same code serves
 conjoined parents found by the secondary RT-DETRv2 detector (mangatranslator_b200/rtdetr.py, loaded by
 `load_rtdetr_conjoined_bubble` when its checkpoint exists; otherwise the load failure is swallowed exactly like the
-reference does at :1541-1548 and the primaries are kept).  Out of scope: OSB-text verification, SAM3, panel detection.
+reference does at :1541-1548 and the primaries are kept).
+
+Secondary ultralytics detectors, executed from their checkpoints' module trees (mangatranslator_b200/yolo_tree.py):
+`detect_panels` (:1817-1921, YOLO11-L at imgsz 640, class "frame") and OSB-text verification
+`_expand_boxes_with_osb_text` (:120-201, YOLO12x at imgsz 640: a bubble box grows to hold the text box that belongs to
+it).  Not restated: the text-aware variant of the conjoined split (text boxes nudging the cut line, :975-1020) and SAM3.
 """
 from __future__ import annotations
 
@@ -34,6 +39,7 @@ IOA_THRESHOLD = 0.50
 SAM_MASK_THRESHOLD = 0.5
 IOA_OVERLAP_THRESHOLD = 0.5
 IOU_DUPLICATE_THRESHOLD = 0.7
+OSB_TEXT_MATCH_IOA_THRESHOLD = 0.2      # :20-22
 
 
 # ---- box geometry (host floats, like the reference's Python helpers :44-60,204-216) ------------------------------
@@ -43,6 +49,64 @@ def _box_intersection_area(a, b) -> float:
 
 def _box_area(b) -> float:
     return max(0.0, b[2] - b[0]) * max(0.0, b[3] - b[1])
+
+
+def _box_contains(inner, outer) -> bool:
+    return inner[0] >= outer[0] and inner[1] >= outer[1] and inner[2] <= outer[2] and inner[3] <= outer[3]
+
+
+def _point_in_box(px: float, py: float, box) -> bool:
+    return box[0] <= px <= box[2] and box[1] <= py <= box[3]
+
+
+def _text_box_meaningfully_matches_box(t_box, b_box) -> bool:
+    """:91-106 — a text box belongs to a bubble when a fifth of it lies inside, or its centre does."""
+    inter = _box_intersection_area(t_box, b_box)
+    area = _box_area(t_box)
+    if inter <= 0.0 or area <= 0.0:
+        return False
+    return inter / area >= OSB_TEXT_MATCH_IOA_THRESHOLD or _point_in_box((t_box[0] + t_box[2]) / 2.0,
+                                                                          (t_box[1] + t_box[3]) / 2.0, b_box)
+
+
+def _expand_boxes_with_osb_text(image_cv, image_pil, primary_boxes: torch.Tensor, cache, model_manager, device,
+                                confidence: float, hf_token: str, verbose: bool):
+    """:120-201 — every text box found by the OSB-text detector (imgsz 640) is assigned to the bubble it intersects most;
+    if it meaningfully belongs there and sticks out, the bubble box grows to the union.  Boxes are updated one text box
+    after the other (a later text box sees the grown boxes); any failure leaves the primaries as they were."""
+    if primary_boxes is None or len(primary_boxes) == 0:
+        return primary_boxes
+    try:
+        from mangatranslator_b200.core.ml.model_manager import ModelType
+        key = cache.get_yolo_cache_key(image_pil, str(model_manager.model_paths[ModelType.YOLO_OSBTEXT]), confidence)
+        hit = cache.get_yolo_detection(key)
+        if hit is not None:
+            _, osb_boxes, _ = hit
+        else:
+            res = model_manager.load_yolo_osbtext(token=hf_token)(image_cv, conf=confidence, device=device, verbose=False,
+                                                                  imgsz=640)[0]
+            osb_boxes = res.boxes.xyxy if res.boxes is not None else torch.tensor([])
+            osb_confs = res.boxes.conf if res.boxes is not None else torch.tensor([])
+            cache.set_yolo_detection(key, (res, osb_boxes, osb_confs))
+        if osb_boxes is None or len(osb_boxes) == 0:
+            return primary_boxes
+        pb = primary_boxes.detach().cpu().numpy()
+        for t in osb_boxes.detach().cpu().numpy():
+            best, best_inter = None, 0.0
+            for i, b in enumerate(pb):
+                inter = _box_intersection_area(t, b)
+                if inter > best_inter:
+                    best, best_inter = i, inter
+            if best is None or best_inter <= 0.0:
+                continue
+            if not _text_box_meaningfully_matches_box(t, pb[best]) or _box_contains(t, pb[best]):
+                continue
+            b = pb[best]
+            pb[best] = [min(b[0], t[0]), min(b[1], t[1]), max(b[2], t[2]), max(b[3], t[3])]
+        return torch.tensor(pb, device=primary_boxes.device, dtype=primary_boxes.dtype)
+    except Exception as e:
+        log_message(f"OSB text verification skipped: {e}", verbose=verbose)
+        return primary_boxes
 
 
 def _calculate_ioa(box_inner, box_outer) -> float:
@@ -330,10 +394,11 @@ def detect_speech_bubbles(image_path: Path, model_path, confidence=0.6, verbose=
             secondary_boxes, secondary_sources, secondary_results = torch.tensor([]), [], None
     if len(primary_boxes) == 0:
         return detections, text_free_boxes
-    if osb_text_verification:
-        log_message("OSB text verification is outside this build; boxes are not expanded", verbose=verbose)
     primary_boxes = primary_boxes.detach().float().cpu()
     grouping_boxes = primary_boxes.clone()
+    if osb_text_verification and len(primary_boxes) > 0:       # :1555-1567 (grouping keeps the un-expanded boxes)
+        primary_boxes = _expand_boxes_with_osb_text(image_cv, image_pil, primary_boxes, cache, mm, _device, confidence,
+                                                    osb_text_hf_token, verbose)
 
     conjoined_indices: list = []
     simple = list(range(len(primary_boxes)))
@@ -403,8 +468,42 @@ def detect_speech_bubbles(image_path: Path, model_path, confidence=0.6, verbose=
         return assemble(None), text_free_boxes
 
 
-# ---- device-resident fast path used by the batch pipeline / bench -------------------------------------------------------
 @serialized
+def detect_panels(image_path: Path, confidence: float = 0.25, device=None, verbose=False,
+                  image_override: Optional[Image.Image] = None) -> List[Tuple[int, int, int, int]]:
+    """:1817-1921 — manga panels: the panel detector at imgsz 640, detections of class "frame" (all classes when the
+    model has no such class) as rounded xyxy tuples.  Image loading errors raise ImageProcessingError and a model that
+    cannot be loaded ModelError; a failure while detecting is logged and gives [] like the reference."""
+    _device = device if device is not None else get_best_device()
+    try:
+        if image_override is not None:
+            image_pil = image_override if image_override.mode == "RGB" else image_override.convert("RGB")
+        else:
+            image_pil = Image.open(str(image_path)).convert("RGB")
+        image_cv = np.ascontiguousarray(np.asarray(image_pil)[:, :, ::-1])
+    except Exception as e:
+        raise ImageProcessingError(f"Error loading image: {e}")
+    try:
+        panel_model = get_model_manager().load_yolo_panel(verbose=verbose)
+    except Exception as e:
+        raise ModelError(f"Error loading panel model: {e}")
+    try:
+        res = panel_model(image_cv, conf=confidence, device=_device, verbose=False, imgsz=640)[0]
+        boxes = res.boxes.xyxy if res.boxes is not None else torch.tensor([])
+        classes = res.boxes.cls if res.boxes is not None else torch.tensor([])
+        if len(boxes) == 0:
+            log_message("No panels detected", verbose=verbose)
+            return []
+        frame_id = next((cid for cid, name in getattr(panel_model, "names", {}).items() if str(name).lower() == "frame"), None)
+        boxes_l, classes_l = boxes.detach().cpu().tolist(), classes.detach().cpu().tolist()
+        panels = [tuple(int(round(v)) for v in b) for b, c in zip(boxes_l, classes_l) if frame_id is None or int(c) == frame_id]
+        log_message(f"Detected {len(panels)} panels", verbose=verbose)
+        return panels
+    except Exception as e:
+        log_message(f"Panel detection failed: {e}. Proceeding without panel information.", always_print=True)
+        return []
+
+
 def _ungroup_oversized(groups, simple, limit: int, verbose: bool = False):
     """The device splitter divides a parent mask between at most MTB_SPLIT_MAX_CHILDREN members.  A larger synthetic group
     (dozens of mutually overlapping boxes: a detector gone wrong, not a page layout) is not split: its members are
@@ -419,6 +518,8 @@ def _ungroup_oversized(groups, simple, limit: int, verbose: bool = False):
 
 
 
+# ---- device-resident fast path used by the batch pipeline / bench -------------------------------------------------------
+@serialized
 def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.6, imgsz: int = 1600,
                         seg_model: str = "sam2", injected_boxes: Optional[List[np.ndarray]] = None,
                         own_masks: bool = False, conjoined_detection: bool = False, conjoined_confidence: float = 0.35):

@@ -7,7 +7,7 @@ exactly what the stage functions touch on the third-party objects the reference 
   SAM 2.1  -> (Sam2ProcessorB200, Sam2ModelB200)     (processor(...), model(...).pred_masks, post_process_masks)
   upscaler -> mangatranslator_b200.rcan.RcanB200     (callable float32 (1,3,h,w) -> (1,3,2h,2w))
 Objects injected into ``ModelManager.models[ModelType.X]`` by a caller are returned as they are (the reference's tests /
-integrations do that).  Models outside the hot path (RT-DETR, OSB text, panels, Flux, SAM3) raise ModelError.
+integrations do that).  Models outside the hot path (Flux, SAM3, OCR) raise ModelError.
 """
 from __future__ import annotations
 
@@ -76,11 +76,15 @@ class ModelManager:
                 ModelType.YOLO_SPEECH_BUBBLE: self.models_dir / "yolo" / "yolov8m_seg-speech-bubble.pt",
                 ModelType.YOLO_SPEECH_BUBBLE_2: self.models_dir / "yolo" / "manga109-segmentation-bubble.pt",
                 ModelType.RTDETR_CONJOINED_BUBBLE: self.models_dir / "rtdetr" / "comic-text-and-bubble-detector",
+                ModelType.YOLO_OSBTEXT: self.models_dir / "yolo" / "animetext_yolov12x.pt",
+                ModelType.YOLO_PANEL: self.models_dir / "yolo" / "manga109_v2023.12.07_l_yolov11.pt",
             }
             self.model_hf_repos: Dict[ModelType, str] = {
                 ModelType.SAM2: "facebook/sam2.1-hiera-large",
                 ModelType.YOLO_SPEECH_BUBBLE: "kitsumed/yolov8m_seg-speech-bubble",
                 ModelType.YOLO_SPEECH_BUBBLE_2: "huyvux3005/manga109-segmentation-bubble",
+                ModelType.YOLO_OSBTEXT: "deepghs/AnimeText_yolo",
+                ModelType.YOLO_PANEL: "deepghs/manga109_yolo",
             }
             self.hf_token: str = ""
             self.flux_inference_lock = threading.Lock()
@@ -253,15 +257,47 @@ class ModelManager:
             self.models[ModelType.RTDETR_CONJOINED_BUBBLE] = model
             return model
 
+    def _load_tree_detector(self, mt: ModelType, what: str, family: str, scale: str, names: dict, env: str):
+        """Panel (YOLO11-L, reference :809-833) and OSB-text (YOLO12x, :780-807) detectors: executed from the module tree
+        the ultralytics `.pt` pickles (mangatranslator_b200/yolo_tree.py), no architecture assumed.  Like the RT-DETR
+        model they are optional in the reference's flow, so without a checkpoint they only load when explicitly asked
+        for (seeded synthetic tree of the published layout and scale)."""
+        with self._lock:
+            if self.models.get(mt) is not None:
+                return self.models[mt]
+            from mangatranslator_b200.yolo_tree import YoloTreeB200, synthetic_tree
+            path = self.model_paths[mt]
+            if path.is_file():
+                try:
+                    tree = W.load_ultralytics_tree(str(path))
+                except W.UnsupportedCheckpoint as e:
+                    raise ModelError(f"{what}: cannot use {path}: {e}") from e
+                except Exception as e:
+                    raise ModelError(f"{what}: failed to read {path}: {e}") from e
+                log_message(f"{what}: module tree and weights from {path} ({len(tree['layers'])} layers)", always_print=True)
+            elif os.environ.get(env, "0") == "1":
+                log_message(f"{what}: NO CHECKPOINT ({path}) - seeded SYNTHETIC YOLO{family}{scale} tree ({env}=1); outputs are "
+                            "meaningless on real pages", always_print=True)
+                tree = synthetic_tree(family, scale, nc=len(names), seed=self.synthetic_seed, names=names)
+            else:
+                raise ModelError(f"{what}: no checkpoint at {path} (set {env}=1 for a seeded synthetic model)")
+            dev = self._require_cuda()
+            try:
+                self.models[mt] = YoloTreeB200(tree, dev, precision=self.precision)
+            except W.UnsupportedCheckpoint as e:
+                raise ModelError(f"{what}: cannot use {path}: {e}") from e
+            return self.models[mt]
+
     def load_yolo_osbtext(self, token: str = "", verbose: bool = False):
-        if self.models.get(ModelType.YOLO_OSBTEXT) is not None:
-            return self.models[ModelType.YOLO_OSBTEXT]
-        self._out_of_scope("OSB text detector")
+        log_message("Loading YOLO OSB Text detection model...", verbose=verbose)
+        return self._load_tree_detector(ModelType.YOLO_OSBTEXT, "OSB text detector", "12", "x", {0: "text"},
+                                        "MTB200_SYNTHETIC_OSBTEXT")
 
     def load_yolo_panel(self, verbose: bool = False):
-        if self.models.get(ModelType.YOLO_PANEL) is not None:
-            return self.models[ModelType.YOLO_PANEL]
-        self._out_of_scope("panel detector")
+        log_message("Loading YOLO panel detection model...", verbose=verbose)
+        # deepghs/manga109_yolo classes; `detect_panels` keeps the "frame" class (core/image/detection.py:1878-1895)
+        return self._load_tree_detector(ModelType.YOLO_PANEL, "Panel detector", "11", "l",
+                                        {0: "body", 1: "face", 2: "frame", 3: "text"}, "MTB200_SYNTHETIC_PANEL")
 
     def load_sam3(self, token: str = "", verbose: bool = False):
         self._out_of_scope("SAM3")

@@ -91,6 +91,72 @@ __global__ void maxpool_kernel(const uint16_t* __restrict__ x, uint16_t* __restr
   }
 }
 
+// Depthwise k x k convolution (groups = channels), stride 1, pad k/2, + bias (+ SiLU) on channels [ci, ci+c) -> [co, co+c):
+// the DWConv of the YOLO11 class branch and the 3x3 / 7x7 positional convolution of the PSA / area-attention blocks
+// (ultralytics nn/modules/conv.py DWConv, block.py Attention.pe / AAttn.pe).  No contraction over channels, so no tensor
+// cores: 8 channels per thread (16-byte loads of both planes), fp32 accumulation in tap order (ky, kx) like a direct conv.
+// w: fp32 [k*k][c] (tap-major, so a thread's 8 weights are contiguous), bias fp32 [c].
+__global__ void dwconv_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W, int ct_in, int ci,
+                              int ct_out, int co, int c, int k, const float* __restrict__ w, const float* __restrict__ bias,
+                              int act, int planes, long long ps_in, long long ps_out) {
+  const int vec = c / 8;
+  const long long total = static_cast<long long>(N) * H * W * vec;
+  const int r = k / 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vec);
+    long long p = i / vec;
+    const int px = static_cast<int>(p % W);
+    p /= W;
+    const int py = static_cast<int>(p % H);
+    const int n = static_cast<int>(p / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int dy = -r; dy <= r; ++dy) {
+      const int yy = py + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = -r; dx <= r; ++dx) {
+        const int xx = px + dx;
+        if (xx < 0 || xx >= W) continue;
+        const long long off = ((static_cast<long long>(n) * H + yy) * W + xx) * ct_in + ci + v * 8;
+        const uint4 h4 = *reinterpret_cast<const uint4*>(x + off);
+        uint4 l4 = make_uint4(0, 0, 0, 0);
+        if (planes == 2) l4 = *reinterpret_cast<const uint4*>(x + ps_in + off);
+        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+        const float* wt = w + static_cast<long long>((dy + r) * k + (dx + r)) * c + v * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(wt), w1 = *reinterpret_cast<const float4*>(wt + 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint16_t hh = (j & 1) ? (hw[j >> 1] >> 16) : (hw[j >> 1] & 0xFFFF);
+          const uint16_t ll = (j & 1) ? (lw[j >> 1] >> 16) : (lw[j >> 1] & 0xFFFF);
+          acc[j] = fmaf(bf16_to_f(hh) + bf16_to_f(ll), wv[j], acc[j]);
+        }
+      }
+    }
+    uint16_t oh[8], ol[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float o = acc[j] + bias[v * 8 + j];
+      if (act) o = o / (1.0f + expf(-o));
+      split_bf16(o, oh[j], ol[j]);
+    }
+    const long long oo = ((static_cast<long long>(n) * H + py) * W + px) * ct_out + co + v * 8;
+    uint4 qh, ql;
+    qh.x = oh[0] | (static_cast<uint32_t>(oh[1]) << 16);
+    qh.y = oh[2] | (static_cast<uint32_t>(oh[3]) << 16);
+    qh.z = oh[4] | (static_cast<uint32_t>(oh[5]) << 16);
+    qh.w = oh[6] | (static_cast<uint32_t>(oh[7]) << 16);
+    ql.x = ol[0] | (static_cast<uint32_t>(ol[1]) << 16);
+    ql.y = ol[2] | (static_cast<uint32_t>(ol[3]) << 16);
+    ql.z = ol[4] | (static_cast<uint32_t>(ol[5]) << 16);
+    ql.w = ol[6] | (static_cast<uint32_t>(ol[7]) << 16);
+    *reinterpret_cast<uint4*>(y + oo) = qh;
+    if (planes == 2) *reinterpret_cast<uint4*>(y + ps_out + oo) = ql;
+  }
+}
+
 // nearest 2x upsample of a channel slice: out[n, 2y+a, 2x+b, co+..] = in[n, y, x, ci+..]
 __global__ void upsample2x_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W, int ct_in,
                                   int ci, int ct_out, int co, int c, int planes, long long ps_in, long long ps_out) {
@@ -445,6 +511,22 @@ int mtb_maxpool(const void* x, void* y, int N, int H, int W, int ct_in, int ci, 
   const long long total = static_cast<long long>(N) * H * W * (c / 8);
   maxpool_kernel<<<grid_for2(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), N, H, W, ct_in, ci, ct_out, co, c, k, planes,
+      static_cast<long long>(N) * H * W * ct_in, static_cast<long long>(N) * H * W * ct_out);
+  MTB_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int mtb_dwconv(const void* x, void* y, int N, int H, int W, int ct_in, int ci, int ct_out, int co, int c, int k,
+               const float* w, const float* bias, int act, int planes, void* stream) {
+  MTB_REQUIRE(x && y && w && bias && x != y, "mtb_dwconv: null or aliased argument");
+  MTB_REQUIRE(c > 0 && c % 8 == 0 && ci % 8 == 0 && co % 8 == 0 && ct_in % 8 == 0 && ct_out % 8 == 0 && (k & 1) && k <= 15,
+              "mtb_dwconv: channels must come in multiples of 8 and the kernel size must be odd (c %d ci %d co %d k %d)", c,
+              ci, co, k);
+  MTB_REQUIRE(planes == 1 || planes == 2, "mtb_dwconv: planes must be 1 or 2");
+  const long long total = static_cast<long long>(N) * H * W * (c / 8);
+  dwconv_kernel<<<grid_for2(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), N, H, W, ct_in, ci, ct_out, co, c, k, w, bias, act, planes,
       static_cast<long long>(N) * H * W * ct_in, static_cast<long long>(N) * H * W * ct_out);
   MTB_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1);

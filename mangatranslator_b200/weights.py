@@ -149,14 +149,9 @@ def synthetic_allowed() -> bool:
     return os.environ.get("MTB200_SYNTHETIC_WEIGHTS", "0") == "1"
 
 
-def load_ultralytics_state_dict(path: str):
-    """State dict (+ class names) of an ultralytics `.pt` without ultralytics installed.
-
-    `YOLO(path)` unpickles `ckpt["model"]`, an `ultralytics.nn.tasks.SegmentationModel` object.  Here the pickle is read
-    with an Unpickler that resolves torch / numpy / builtin classes normally and replaces every `ultralytics.*` (and any
-    other unknown) class by an inert attribute bag, then the module tree (`_modules` / `_parameters` / `_buffers`) is
-    walked into the flat `model.N....` names a state dict has.  Nothing from the file is executed.  Plain state-dict
-    files (a dict of tensors, or {"model": state_dict}) are accepted as they are."""
+def _load_pickle_inert(path: str):
+    """torch.load of a file that pickles objects of packages that are not installed (ultralytics): torch / numpy / builtin
+    classes resolve normally, every other class becomes an inert attribute bag.  Nothing from the file is executed."""
     import pickle
 
     class _Bag:
@@ -190,7 +185,18 @@ def load_ultralytics_state_dict(path: str):
         load = staticmethod(lambda f, **kw: _Unpickler(f, **kw).load())
         __name__ = "pickle"
 
-    obj = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_PickleModule)
+    return torch.load(path, map_location="cpu", weights_only=False, pickle_module=_PickleModule)
+
+
+def load_ultralytics_state_dict(path: str):
+    """State dict (+ class names) of an ultralytics `.pt` without ultralytics installed.
+
+    `YOLO(path)` unpickles `ckpt["model"]`, an `ultralytics.nn.tasks.SegmentationModel` object.  Here the pickle is read
+    with an Unpickler that resolves torch / numpy / builtin classes normally and replaces every `ultralytics.*` (and any
+    other unknown) class by an inert attribute bag, then the module tree (`_modules` / `_parameters` / `_buffers`) is
+    walked into the flat `model.N....` names a state dict has.  Nothing from the file is executed.  Plain state-dict
+    files (a dict of tensors, or {"model": state_dict}) are accepted as they are."""
+    obj = _load_pickle_inert(path)
     names = None
     root = obj
     if isinstance(obj, dict):
@@ -295,6 +301,172 @@ def yolo_from_ultralytics(sd: Dict[str, torch.Tensor], names=None):
     if int(out["head.cv2.0.2.weight"].shape[0]) != 64:
         raise UnsupportedCheckpoint("DFL with reg_max != 16 is not supported")
     return out, cfg
+
+
+# ---- ultralytics model OBJECT -> node tree (panel YOLO11 / OSB-text YOLO12 detectors; mangatranslator_b200/yolo_tree.py) -----
+def _mods(obj) -> dict:
+    return getattr(obj, "__dict__", {}).get("_modules") or {}
+
+
+def _cls(obj) -> str:
+    return type(obj).__name__
+
+
+def _attr(obj, name, default=None):
+    d = getattr(obj, "__dict__", {})
+    if name in d:
+        return d[name]
+    for store in ("_parameters", "_buffers", "_modules"):
+        if name in (d.get(store) or {}):
+            return d[store][name]
+    return default
+
+
+def _child(obj, name, where="module"):
+    m = _mods(obj).get(name)
+    if m is None:
+        raise UnsupportedCheckpoint(f"{_cls(obj)} has no `{name}` {where}")
+    return m
+
+
+def _first(v) -> int:
+    return int(v[0] if isinstance(v, (tuple, list)) else v)
+
+
+def _tree_conv(obj) -> dict:
+    """ultralytics Conv / DWConv (conv + bn + act) or a bare torch Conv2d -> Conv node with BatchNorm folded."""
+    name = _cls(obj)
+    if name == "Conv2d":
+        conv, bn, act = obj, None, False
+    elif name in ("Conv", "DWConv"):
+        conv, bn = _child(obj, "conv"), _mods(obj).get("bn")
+        a = _mods(obj).get("act")
+        a = a if a is not None else _attr(obj, "act")
+        an = _cls(a) if a is not None else "Identity"
+        if an not in ("SiLU", "Identity"):
+            raise UnsupportedCheckpoint(f"activation {an} (SiLU or none supported)")
+        act = an == "SiLU"
+    else:
+        raise UnsupportedCheckpoint(f"expected a convolution, found {name}")
+    w = _attr(conv, "weight")
+    if w is None or w.dim() != 4:
+        raise UnsupportedCheckpoint("convolution without a 4-d weight")
+    w = w.detach().float()
+    k, s, p, g = _attr(conv, "kernel_size"), _attr(conv, "stride"), _attr(conv, "padding"), int(_attr(conv, "groups", 1))
+    if int(w.shape[2]) != int(w.shape[3]) or _first(_attr(conv, "dilation", 1)) != 1 or isinstance(p, str):
+        raise UnsupportedCheckpoint("non-square, dilated or string-padded convolution")
+    cb = _attr(conv, "bias")
+    b = cb.detach().float() if cb is not None else torch.zeros(w.shape[0])
+    if bn is not None and _cls(bn) != "Identity":
+        gam, bet = _attr(bn, "weight").detach().float(), _attr(bn, "bias").detach().float()
+        mean, var = _attr(bn, "running_mean").detach().float(), _attr(bn, "running_var").detach().float()
+        kk = gam / torch.sqrt(var + float(_attr(bn, "eps", 1e-3)))
+        w, b = w * kk.view(-1, 1, 1, 1), bet + (b - mean) * kk
+    return {"t": "Conv", "w": w.contiguous(), "b": b.contiguous(), "k": int(w.shape[2]), "s": _first(s), "p": _first(p),
+            "g": g, "act": bool(act)}
+
+
+def _flat_convs(obj) -> list:
+    if _cls(obj) in ("Sequential", "ModuleList"):
+        return [c for m in _mods(obj).values() for c in _flat_convs(m)]
+    return [_tree_conv(obj)]
+
+
+def _tree_block(obj) -> dict:
+    name = _cls(obj)
+    kids = lambda n: list(_mods(_child(obj, n)).values())
+    if name in ("Conv", "DWConv"):
+        return _tree_conv(obj)
+    if name == "Bottleneck":
+        return {"t": "Bottleneck", "cv1": _tree_conv(_child(obj, "cv1")), "cv2": _tree_conv(_child(obj, "cv2")),
+                "add": bool(_attr(obj, "add", False))}
+    if name in ("C2f", "C3k2"):
+        return {"t": "C2f", "cv1": _tree_conv(_child(obj, "cv1")), "cv2": _tree_conv(_child(obj, "cv2")),
+                "m": [_tree_block(m) for m in kids("m")]}
+    if name in ("C3", "C3k"):
+        return {"t": "C3", "cv1": _tree_conv(_child(obj, "cv1")), "cv2": _tree_conv(_child(obj, "cv2")),
+                "cv3": _tree_conv(_child(obj, "cv3")), "m": [_tree_block(m) for m in kids("m")]}
+    if name == "SPPF":
+        return {"t": "SPPF", "cv1": _tree_conv(_child(obj, "cv1")), "cv2": _tree_conv(_child(obj, "cv2")),
+                "k": _first(_attr(_child(obj, "m"), "kernel_size", 5))}
+    if name == "Attention":
+        return {"t": "Attention", "num_heads": int(_attr(obj, "num_heads")), "head_dim": int(_attr(obj, "head_dim")),
+                "key_dim": int(_attr(obj, "key_dim")), "scale": float(_attr(obj, "scale")),
+                "qkv": _tree_conv(_child(obj, "qkv")), "proj": _tree_conv(_child(obj, "proj")), "pe": _tree_conv(_child(obj, "pe"))}
+    if name == "PSABlock":
+        return {"t": "PSABlock", "attn": _tree_block(_child(obj, "attn")), "ffn": _flat_convs(_child(obj, "ffn")),
+                "add": bool(_attr(obj, "add", True))}
+    if name == "C2PSA":
+        return {"t": "C2PSA", "c": int(_attr(obj, "c")), "cv1": _tree_conv(_child(obj, "cv1")),
+                "cv2": _tree_conv(_child(obj, "cv2")), "m": [_tree_block(m) for m in kids("m")]}
+    if name == "AAttn":
+        if "qkv" not in _mods(obj):
+            raise UnsupportedCheckpoint("area attention with separate qk / v projections (the yolov12 fork's layout)")
+        return {"t": "AAttn", "area": int(_attr(obj, "area", 1)), "num_heads": int(_attr(obj, "num_heads")),
+                "head_dim": int(_attr(obj, "head_dim")), "qkv": _tree_conv(_child(obj, "qkv")),
+                "proj": _tree_conv(_child(obj, "proj")), "pe": _tree_conv(_child(obj, "pe"))}
+    if name == "ABlock":
+        return {"t": "ABlock", "attn": _tree_block(_child(obj, "attn")), "mlp": _flat_convs(_child(obj, "mlp"))}
+    if name == "A2C2f":
+        m = []
+        for sub in kids("m"):
+            m.append([_tree_block(a) for a in _mods(sub).values()] if _cls(sub) == "Sequential" else _tree_block(sub))
+        gamma = _attr(obj, "gamma")
+        return {"t": "A2C2f", "cv1": _tree_conv(_child(obj, "cv1")), "cv2": _tree_conv(_child(obj, "cv2")),
+                "gamma": gamma.detach().float() if torch.is_tensor(gamma) else None, "m": m}
+    raise UnsupportedCheckpoint(f"module {name} is not supported by this build")
+
+
+def tree_from_ultralytics_model(root) -> dict:
+    """Unpickled `DetectionModel` (inert bags, see `_load_pickle_inert`) -> the node tree YoloTreeB200 executes."""
+    seq = _mods(root).get("model")
+    if seq is None:
+        raise UnsupportedCheckpoint("no `model` Sequential in the checkpoint object")
+    layers = []
+    for idx, (key, m) in enumerate(_mods(seq).items()):
+        name = _cls(m)
+        f = _attr(m, "f", -1)
+        f = [int(v) for v in f] if isinstance(f, (list, tuple)) else int(f)
+        if name == "Concat":
+            node = {"t": "Concat", "d": int(_attr(m, "d", 1))}
+        elif name == "Upsample":
+            sf, mode = _attr(m, "scale_factor", 2), _attr(m, "mode", "nearest")
+            if mode != "nearest" or float(_first(sf)) != 2.0:
+                raise UnsupportedCheckpoint(f"Upsample(scale_factor={sf}, mode={mode})")
+            node = {"t": "Upsample", "scale": 2}
+        elif name == "Detect":
+            if bool(_attr(m, "end2end", False)):
+                raise UnsupportedCheckpoint("end-to-end (NMS-free) Detect head")
+            stride = _attr(m, "stride")
+            node = {"t": "Detect", "nc": int(_attr(m, "nc")), "reg_max": int(_attr(m, "reg_max", 16)),
+                    "stride": [int(round(float(v))) for v in (stride.tolist() if torch.is_tensor(stride) else stride)],
+                    "cv2": [_flat_convs(b) for b in _mods(_child(m, "cv2")).values()],
+                    "cv3": [_flat_convs(b) for b in _mods(_child(m, "cv3")).values()]}
+        elif name in ("Segment", "Pose", "OBB", "Classify", "RTDETRDecoder", "v10Detect", "YOLOEDetect", "WorldDetect"):
+            raise UnsupportedCheckpoint(f"{name} head: this loader handles detection (`Detect`) models")
+        else:
+            node = _tree_block(m)
+        node["f"] = f
+        layers.append(node)
+    if not layers or layers[-1]["t"] != "Detect":
+        raise UnsupportedCheckpoint("the model does not end in a Detect head")
+    names = _attr(root, "names")
+    return {"layers": layers, "names": dict(names) if isinstance(names, dict) else None}
+
+
+def load_ultralytics_tree(path: str) -> dict:
+    """Node tree of the detection model OBJECT an ultralytics `.pt` holds (`ckpt["ema"] or ckpt["model"]`, what
+    `YOLO(path)` runs: core/ml/model_manager.py:804,830).  Plain state-dict files carry no architecture and are refused."""
+    obj = _load_pickle_inert(path)
+    root = obj
+    if isinstance(obj, dict):
+        root = obj.get("ema") or obj.get("model")
+        if root is None or isinstance(root, dict):
+            raise UnsupportedCheckpoint(f"{path}: a plain state dict carries no module tree; the pickled model object is needed")
+    tree = tree_from_ultralytics_model(root)
+    if tree["names"] is None and isinstance(obj, dict) and isinstance(obj.get("names"), dict):
+        tree["names"] = dict(obj["names"])
+    return tree
 
 
 # ---- SAM 2.1 ----------------------------------------------------------------------------------------------------------

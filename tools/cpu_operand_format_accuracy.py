@@ -53,6 +53,9 @@ class Conv(torch.nn.Module):
             return F.conv2d(tf32(x), tf32(w), b, padding=1)
         xh, wh = q(x, torch.float16), q(w, torch.float16)
         wl = q(w - wh, torch.float16)
+        if m.startswith("fp16w1"):               # weights as ONE fp16 term (18 or 27 slots instead of 36 / 54)
+            wl = wl * 0
+            m = m.replace("fp16w1", "fp16")
         y = F.conv2d(xh, wh + wl, b, padding=1)
         if m.endswith("+mxfp4"):
             y = y + F.conv2d(mxfp4(x - xh, 1), mxfp4(w, 1), None, padding=1)
