@@ -506,7 +506,8 @@ class YoloTreeB200:
             raise UnsupportedCheckpoint("no Detect head")
         total_anchors = sum(fh * fw for (_, _, _, fh, fw, _) in levels)
         max_cand = min(total_anchors, 30000)
-        return dict(steps=steps, keep=keep, x_in=x_in, levels=levels, ncp=P.pad_to(self.nc, 16), max_cand=max_cand,
+        return dict(steps=steps, keep=keep, x_in=x_in, levels=levels, layer_outputs=outs, ncp=P.pad_to(self.nc, 16),
+                    max_cand=max_cand,
                     total_anchors=total_anchors,
                     cand=torch.zeros((n, max_cand, 6), dtype=torch.float32, device=dev),
                     cand_anchor=torch.zeros((n, max_cand), dtype=torch.int32, device=dev),
