@@ -288,7 +288,7 @@ class ModelManager:
                 raise ModelError(f"{what}: cannot use {path}: {e}") from e
             return self.models[mt]
 
-    def load_yolo_osbtext(self, token: str = "", verbose: bool = False):
+    def load_yolo_osbtext(self, token: Optional[str] = None, verbose: bool = False):
         log_message("Loading YOLO OSB Text detection model...", verbose=verbose)
         return self._load_tree_detector(ModelType.YOLO_OSBTEXT, "OSB text detector", "12", "x", {0: "text"},
                                         "MTB200_SYNTHETIC_OSBTEXT")

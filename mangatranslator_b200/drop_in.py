@@ -60,13 +60,14 @@ def install(force: bool = False) -> None:
 # ---- overlay on the unmodified reference ---------------------------------------------------------------------------------
 # reference module -> (our module, names replaced there)
 _STAGE_FUNCTIONS = {
-    "core.image.detection": ("mangatranslator_b200.core.image.detection", ["detect_speech_bubbles"]),
+    "core.image.detection": ("mangatranslator_b200.core.image.detection", ["detect_speech_bubbles", "detect_panels"]),
     "core.image.cleaning": ("mangatranslator_b200.core.image.cleaning", ["clean_speech_bubbles", "retry_cleaning_with_otsu"]),
     "core.image.image_utils": ("mangatranslator_b200.core.image.image_utils",
                                ["upscale_image", "upscale_image_to_dimension", "process_bubble_image_cached",
                                 "resize_to_max_side", "resize_to_min_side", "calculate_centroid_expansion_box"]),
 }
-_LOADERS = ["load_yolo_speech_bubble", "load_sam2", "load_upscale", "load_upscale_lite", "load_rtdetr_conjoined_bubble"]
+_LOADERS = ["load_yolo_speech_bubble", "load_sam2", "load_upscale", "load_upscale_lite", "load_rtdetr_conjoined_bubble",
+            "load_yolo_panel", "load_yolo_osbtext"]
 _undo: List[Tuple[Any, str, Any]] = []          # (namespace dict or class, name, original value)
 
 
