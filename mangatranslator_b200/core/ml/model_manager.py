@@ -153,7 +153,20 @@ class ModelManager:
                     raw, names = W.load_ultralytics_state_dict(str(path))
                     sd, cfg = W.yolo_from_ultralytics(raw, names)
                 except W.UnsupportedCheckpoint as e:
-                    raise ModelError(f"YOLO speech-bubble detector: cannot use {path}: {e}") from e
+                    # not the hard-wired YOLOv8-seg graph (the default `yolo_2` file may be a YOLO11-seg): run the model
+                    # from the module tree the file pickles (mangatranslator_b200/yolo_tree.py)
+                    try:
+                        from mangatranslator_b200.yolo_tree import YoloTreeB200
+                        tree = W.load_ultralytics_tree(str(path))
+                        self.models[mt] = YoloTreeB200(tree, dev, precision=self.precision)
+                    except W.UnsupportedCheckpoint as e2:
+                        raise ModelError(f"YOLO speech-bubble detector: cannot use {path}: {e}; as a module tree: {e2}") from e2
+                    except Exception as e2:
+                        raise ModelError(f"YOLO speech-bubble detector: failed to read {path}: {e2}") from e2
+                    log_message(f"YOLO speech-bubble detector: module tree and weights from {path} "
+                                f"({len(tree['layers'])} layers, {tree['layers'][-1]['t']} head, nc={self.models[mt].nc})",
+                                always_print=True)
+                    return self.models[mt]
                 except Exception as e:
                     raise ModelError(f"YOLO speech-bubble detector: failed to read {path}: {e}") from e
                 log_message(f"YOLO speech-bubble detector: weights from {path} (YOLOv8-seg, {len(sd)} tensors, nc={cfg['nc']})",

@@ -434,22 +434,33 @@ def tree_from_ultralytics_model(root) -> dict:
             if mode != "nearest" or float(_first(sf)) != 2.0:
                 raise UnsupportedCheckpoint(f"Upsample(scale_factor={sf}, mode={mode})")
             node = {"t": "Upsample", "scale": 2}
-        elif name == "Detect":
+        elif name in ("Detect", "Segment"):
             if bool(_attr(m, "end2end", False)):
                 raise UnsupportedCheckpoint("end-to-end (NMS-free) Detect head")
             stride = _attr(m, "stride")
-            node = {"t": "Detect", "nc": int(_attr(m, "nc")), "reg_max": int(_attr(m, "reg_max", 16)),
+            node = {"t": name, "nc": int(_attr(m, "nc")), "reg_max": int(_attr(m, "reg_max", 16)),
                     "stride": [int(round(float(v))) for v in (stride.tolist() if torch.is_tensor(stride) else stride)],
                     "cv2": [_flat_convs(b) for b in _mods(_child(m, "cv2")).values()],
                     "cv3": [_flat_convs(b) for b in _mods(_child(m, "cv3")).values()]}
-        elif name in ("Segment", "Pose", "OBB", "Classify", "RTDETRDecoder", "v10Detect", "YOLOEDetect", "WorldDetect"):
-            raise UnsupportedCheckpoint(f"{name} head: this loader handles detection (`Detect`) models")
+            if name == "Segment":
+                pr = _child(m, "proto")
+                up = _child(pr, "upsample")
+                uw, ub = _attr(up, "weight"), _attr(up, "bias")
+                if _cls(up) != "ConvTranspose2d" or uw is None or tuple(uw.shape[2:]) != (2, 2) or _first(_attr(up, "stride")) != 2:
+                    raise UnsupportedCheckpoint("prototype upsample is not ConvTranspose2d(k=2, s=2)")
+                node.update(nm=int(_attr(m, "nm")), cv4=[_flat_convs(b) for b in _mods(_child(m, "cv4")).values()],
+                            proto={"cv1": _tree_conv(_child(pr, "cv1")),
+                                   "upsample": {"w": uw.detach().float().contiguous(),
+                                                "b": (ub.detach().float() if ub is not None else torch.zeros(uw.shape[1]))},
+                                   "cv2": _tree_conv(_child(pr, "cv2")), "cv3": _tree_conv(_child(pr, "cv3"))})
+        elif name in ("Pose", "OBB", "Classify", "RTDETRDecoder", "v10Detect", "YOLOEDetect", "WorldDetect"):
+            raise UnsupportedCheckpoint(f"{name} head: this loader handles `Detect` and `Segment` models")
         else:
             node = _tree_block(m)
         node["f"] = f
         layers.append(node)
-    if not layers or layers[-1]["t"] != "Detect":
-        raise UnsupportedCheckpoint("the model does not end in a Detect head")
+    if not layers or layers[-1]["t"] not in ("Detect", "Segment"):
+        raise UnsupportedCheckpoint("the model does not end in a Detect / Segment head")
     names = _attr(root, "names")
     return {"layers": layers, "names": dict(names) if isinstance(names, dict) else None}
 

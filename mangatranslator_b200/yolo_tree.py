@@ -12,6 +12,7 @@ nothing from the file is executed) into a plain tree of nodes
     C2PSA{c,cv1,cv2,m[PSABlock{attn,ffn[],add}]}  Attention{num_heads,key_dim,head_dim,scale,qkv,proj,pe}
     A2C2f{cv1,cv2,gamma,m[ [ABlock{attn,mlp[]},..] | C3 ]}  AAttn{area,num_heads,head_dim,qkv,proj,pe}
     Concat{d}  Upsample{scale}  Detect{nc,reg_max,stride[],cv2[][],cv3[][]}            (+ "f": where a layer reads from)
+    Segment = Detect + {nm, cv4[][], proto{cv1, upsample{w,b}, cv2, cv3}}
 
 with BatchNorm folded (eps from the file), and `YoloTreeB200` turns that tree into a static plan of tcgen05 conv plans
 (mtb_conv_plan_*), depthwise convs (mtb_dwconv), attention (mtb_attention, exact fp32 softmax), max-pool / upsample, and
@@ -32,7 +33,7 @@ from . import planes as P
 from ._lib import check, lib, ptr, stream_ptr
 from .ops import ConvPlan
 from .weights import UnsupportedCheckpoint
-from .yolo import Boxes, NmsParams, Results, YoloLevel, _Slice, _declare as _declare_yolo
+from .yolo import Boxes, Masks, Results, YoloB200, _Slice, _declare as _declare_yolo
 
 
 # ---- node helpers -----------------------------------------------------------------------------------------------------
@@ -132,7 +133,7 @@ class _Synth:
         gamma = (0.01 + 0.05 * torch.rand((c2,), generator=self.g)) if (a2 and residual) else None
         return {"t": "A2C2f", "cv1": self.conv(c1, c_), "cv2": self.conv((1 + n) * c_, c2), "gamma": gamma, "m": m}
 
-    def detect(self, chs: List[int], legacy: bool = False):
+    def detect(self, chs: List[int], legacy: bool = False, segment: bool = False, nm: int = 32, npr: int = 256):
         nc, reg_max = self.nc, 16
         c2, c3 = max(16, chs[0] // 4, reg_max * 4), max(chs[0], min(nc, 100))
         cv2, cv3 = [], []
@@ -147,11 +148,20 @@ class _Synth:
             # by margins far above the numerical noise, the rest stay below
             last["b"] = torch.full((nc,), -3.0)
             cv3.append(br + [last])
-        return {"t": "Detect", "nc": nc, "reg_max": reg_max, "stride": [8, 16, 32], "cv2": cv2, "cv3": cv3}
+        head = {"t": "Detect", "nc": nc, "reg_max": reg_max, "stride": [8, 16, 32], "cv2": cv2, "cv3": cv3}
+        if segment:                                   # Segment(nc, nm, npr): mask-coefficient branch + prototype net
+            c4, npr = max(chs[0] // 4, nm), self.ch(npr)
+            head.update(t="Segment", nm=nm,
+                        cv4=[[self.conv(x, c4, 3), self.conv(c4, c4, 3), self.conv(c4, nm, 1, act=False, gain=1.0)] for x in chs],
+                        proto={"cv1": self.conv(chs[0], npr, 3),
+                               "upsample": {"w": torch.randn((npr, npr, 2, 2), generator=self.g) * (1.6 / math.sqrt(npr)),
+                                            "b": torch.randn((npr,), generator=self.g) * 0.1},
+                               "cv2": self.conv(npr, npr, 3), "cv3": self.conv(npr, nm, 1)})
+        return head
 
 
 def synthetic_tree(family: str, scale: str = "s", nc: int = 1, seed: int = 0, names: Optional[dict] = None,
-                   a2_residual: Optional[bool] = None, mlp_ratio: Optional[float] = None) -> dict:
+                   a2_residual: Optional[bool] = None, mlp_ratio: Optional[float] = None, segment: bool = False) -> dict:
     """YOLO11 (`family` "11": C3k2 + C2PSA, DWConv class branch) or YOLO12 ("12": A2C2f area attention) detection model
     of the given yaml scale with seeded weights.  Layouts as published in ultralytics cfg/models/11/yolo11.yaml and
     cfg/models/12/yolo12.yaml (from memory; real checkpoints bring their own tree)."""
@@ -207,7 +217,7 @@ def synthetic_tree(family: str, scale: str = "s", nc: int = 1, seed: int = 0, na
     add(s.conv(ch(512), ch(512), 3, 2))
     add({"t": "Concat", "d": 1}, f=[-1, p5], c=ch(512) + width[p5])
     m5 = add(neck(width[-1], ch(1024), True))
-    add(s.detect([width[n3], width[m4], width[m5]]), f=[n3, m4, m5], c=0)
+    add(s.detect([width[n3], width[m4], width[m5]], segment=segment), f=[n3, m4, m5], c=0)
     return {"layers": layers, "names": names or {i: f"class{i}" for i in range(nc)}, "family": family, "scale": scale}
 
 
@@ -229,9 +239,11 @@ def _declare(l) -> None:
     l._tree_declared = True
 
 
-class YoloTreeB200:
-    """Callable with the reference's call shape (`model(image_bgr, conf=, device=, verbose=, imgsz=)` -> [Results]) and
-    `.names`, like the object `ultralytics.YOLO(path)` gives the reference."""
+class YoloTreeB200(YoloB200):
+    """Callable with the reference's call shape (`model(image_bgr, conf=, device=, verbose=, imgsz=[, retina_masks=])` ->
+    [Results]) and `.names`, like the object `ultralytics.YOLO(path)` gives the reference.  Shares the public methods of the
+    hard-wired YOLOv8-seg detector (`forward_letterboxed`, `detect`, `retina_masks`): the plan it builds has the same
+    head tensors, so a tree with a `Segment` head can also serve as the speech-bubble detector of the page path."""
 
     def __init__(self, tree: dict, device: torch.device, *, precision: str = "bf16x3"):
         self.l = lib()
@@ -241,9 +253,11 @@ class YoloTreeB200:
         self.tree = tree
         self.names = dict(tree.get("names") or {})
         head = tree["layers"][-1]
-        if head["t"] != "Detect":
-            raise UnsupportedCheckpoint(f"last layer is {head['t']}, expected a Detect head")
+        if head["t"] not in ("Detect", "Segment"):
+            raise UnsupportedCheckpoint(f"last layer is {head['t']}, expected a Detect or Segment head")
+        self.has_masks = head["t"] == "Segment"
         self.nc = int(head["nc"])
+        self.cfg = {"nc": self.nc, "nm": int(head.get("nm", 0))}
         if int(head["reg_max"]) != 16:
             raise UnsupportedCheckpoint("DFL with reg_max != 16 is not supported")
         if len(head["cv2"]) != 3:
@@ -281,6 +295,16 @@ class YoloTreeB200:
             w = node["w"].to(self.device)                                  # [C][1][k][k]
             c, k = w.shape[0], w.shape[-1]
             self._w[key] = (w.reshape(c, k * k).t().contiguous(), node["b"].to(self.device).contiguous())   # [k*k][C]
+        return self._w[key]
+
+    def _deconv_tree_w(self, node: dict):
+        """ConvTranspose2d(k=2, s=2) of the prototype branch as a 1x1 conv to 4 * Cout channels + pixel-shuffle store."""
+        key = id(node)
+        if key not in self._w:
+            w = node["w"].to(self.device)                                  # [Cin][Cout][2][2]
+            cin, cout = int(w.shape[0]), int(w.shape[1])
+            w1 = w.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1).contiguous()
+            self._w[key] = (P.conv_weight_to_planes(w1, self.planes), P.pad_bias(node["b"].to(self.device).repeat(4), 4 * cout))
         return self._w[key]
 
     # ---- plan ------------------------------------------------------------------------------------------------
@@ -448,6 +472,7 @@ class YoloTreeB200:
 
         x_in = torch.zeros((pl, n, h, w, 8), dtype=torch.bfloat16, device=dev)    # RGB + 5 zero channels (16-byte pixels)
         keep.append(x_in)
+        proto = None
         outs: List[Tuple[_Slice, int, int]] = []
         cur: Tuple[_Slice, int, int] = (_Slice(x_in, 0, 3), h, w)
         levels = None
@@ -474,12 +499,18 @@ class YoloTreeB200:
                 d = new(2 * hh, 2 * ww, s.c)
                 steps.append(("up", (s, d, hh, ww)))
                 res = (d, 2 * hh, 2 * ww)
-            elif t == "Detect":
+            elif t in ("Detect", "Segment"):
                 levels = []
                 ncp = P.pad_to(self.nc, 16)
+                nm = int(node.get("nm", 0))
                 for i, (s, hh, ww) in enumerate(srcs):
                     outs_l = []
-                    for br, oc, ocp in ((node["cv2"][i], 64, 64), (node["cv3"][i], self.nc, ncp)):
+                    branches = [(node["cv2"][i], 64, 64), (node["cv3"][i], self.nc, ncp)]
+                    if t == "Segment":
+                        if nm % 16:
+                            raise UnsupportedCheckpoint(f"{nm} mask coefficients (a multiple of 16 expected)")
+                        branches.append((node["cv4"][i], nm, nm))
+                    for br, oc, ocp in branches:
                         a, _, _ = seq(br[:-1], s, hh, ww)
                         o = torch.zeros((n, hh, ww, ocp), dtype=torch.float32, device=dev)
                         keep.append(o)
@@ -492,7 +523,24 @@ class YoloTreeB200:
                         steps.append(("conv", ConvPlan(a.buf, wgt[0], wgt[1], o, k=1, act="silu" if last["act"] else None,
                                                        x_coff=a.off)))
                         outs_l.append(o)
-                    levels.append((outs_l[0], outs_l[1], None, hh, ww, int(node["stride"][i])))
+                    levels.append((outs_l[0], outs_l[1], outs_l[2] if t == "Segment" else None, hh, ww, int(node["stride"][i])))
+                if t == "Segment":                              # Proto: cv1 3x3 -> ConvTranspose 2x -> cv2 3x3 -> cv3 1x1 (SiLU)
+                    pr = node["proto"]
+                    s0, hh, ww = srcs[0]
+                    pa, _, _ = conv(pr["cv1"], s0, hh, ww)
+                    npr = int(pr["upsample"]["w"].shape[1])
+                    if (4 * npr) % 64 or int(pr["upsample"]["w"].shape[0]) != pa.c:
+                        raise UnsupportedCheckpoint(f"prototype branch with {npr} channels")
+                    pb = new(2 * hh, 2 * ww, npr)
+                    wgt = self._deconv_tree_w(pr["upsample"])
+                    steps.append(("conv", ConvPlan(pa.buf, wgt[0], wgt[1], pb.buf, k=1, act=None, pixel_shuffle=True)))
+                    pc, _, _ = conv(pr["cv2"], pb, 2 * hh, 2 * ww)
+                    proto = torch.zeros((n, 2 * hh, 2 * ww, nm), dtype=torch.float32, device=dev)
+                    keep.append(proto)
+                    last = pr["cv3"]
+                    wgt = self._detect_w(last, pc.c, nm)
+                    steps.append(("conv", ConvPlan(pc.buf, wgt[0], wgt[1], proto, k=1, act="silu" if last["act"] else None,
+                                                   x_coff=pc.off)))
                 res = (None, 0, 0)
             else:
                 s, hh, ww = srcs[0]
@@ -503,10 +551,10 @@ class YoloTreeB200:
             outs.append(res)
             cur = res
         if levels is None:
-            raise UnsupportedCheckpoint("no Detect head")
+            raise UnsupportedCheckpoint("no Detect / Segment head")
         total_anchors = sum(fh * fw for (_, _, _, fh, fw, _) in levels)
         max_cand = min(total_anchors, 30000)
-        return dict(steps=steps, keep=keep, x_in=x_in, levels=levels, layer_outputs=outs, ncp=P.pad_to(self.nc, 16),
+        return dict(steps=steps, keep=keep, x_in=x_in, levels=levels, proto=proto, layer_outputs=outs, ncp=P.pad_to(self.nc, 16),
                     max_cand=max_cand,
                     total_anchors=total_anchors,
                     cand=torch.zeros((n, max_cand, 6), dtype=torch.float32, device=dev),
@@ -578,63 +626,20 @@ class YoloTreeB200:
             else:
                 raise RuntimeError(kind)
 
-    # ---- public ----------------------------------------------------------------------------------------------
-    def forward_letterboxed(self, lb_rgb_u8: torch.Tensor) -> dict:
-        """lb_rgb_u8: device uint8 [H][W][3] RGB letterboxed input.  Runs the plan; returns it (head tensors in
-        g["levels"]: per level (box logits fp32 [1][h][w][64], class logits fp32 [1][h][w][ncp], None, h, w, stride))."""
-        from . import graphs
-        h, w, _ = lb_rgb_u8.shape
-        if h % 32 or w % 32:
-            raise ValueError(f"letterboxed input must be a multiple of 32 pixels, got {h}x{w}")
-        g = self._get(1, h, w)
-        if "lb_in" not in g:
-            g["lb_in"] = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
-
-        def body():
-            zero = (C.c_float * 3)(0.0, 0.0, 0.0)
-            check(self.l.mtb_image_to_planes(ptr(g["lb_in"]), h, w, 3, 0, 1.0 / 255.0, zero, ptr(g["x_in"]), 8, self.planes,
-                                             stream_ptr()), "mtb_image_to_planes")
-            self._run_graph(g)
-
-        g["lb_in"].copy_(lb_rgb_u8[:, :, :3])
-        if graphs.ENABLED:
-            if "cuda_graph" not in g:
-                g["cuda_graph"] = graphs.CapturedGraph(body)
-            g["cuda_graph"].replay()
-        else:
-            body()
-        return g
-
-    def detect(self, g: dict, conf: float, orig_hw: Tuple[int, int], lb_hw: Tuple[int, int], *, iou: float = 0.7):
-        """Decode + class-offset NMS + scale_boxes, the predictor's post-processing.  -> (det [300][8], counts [2])"""
-        l, st = self.l, stream_ptr()
-        lv = (YoloLevel * 3)()
-        for i, (box, cls, _, fh, fw, s) in enumerate(g["levels"]):
-            lv[i].box, lv[i].cls, lv[i].H, lv[i].W, lv[i].stride = box.data_ptr(), cls.data_ptr(), fh, fw, s
-        check(l.mtb_yolo_decode(lv, 3, 1, self.nc, g["ncp"], float(conf), g["max_cand"], ptr(g["cand"]),
-                                ptr(g["cand_anchor"]), ptr(g["count"]), st), "mtb_yolo_decode")
-        h0, w0 = orig_hw
-        gain = min(lb_hw[0] / h0, lb_hw[1] / w0)
-        p = NmsParams()
-        p.N, p.max_cand, p.max_det = 1, g["max_cand"], 300
-        p.iou_thr, p.max_wh, p.gain = float(iou), 7680.0, float(gain)
-        p.pad_x = int(round((lb_hw[1] - w0 * gain) / 2 - 0.1))
-        p.pad_y = int(round((lb_hw[0] - h0 * gain) / 2 - 0.1))
-        p.img_w, p.img_h = w0, h0
-        p.dedup_iou, p.contain_ioa, p.apply_dedup = 0.7, 0.9, 0
-        check(l.mtb_nms(C.byref(p), ptr(g["cand"]), ptr(g["cand_anchor"]), ptr(g["count"]), ptr(g["order"]),
-                        ptr(g["dead"]), ptr(g["det"]), ptr(g["det_count"]), ptr(g["final_idx"]), st), "mtb_nms")
-        return g["det"][0], g["det_count"][0]
-
-    def __call__(self, image_bgr: np.ndarray, conf: float = 0.25, device=None, verbose: bool = False, imgsz: int = 640, **_):
-        """Reference call shape (core/image/detection.py:1864-1870 panels, :140-146 OSB text)."""
+    # ---- public (forward_letterboxed, detect and retina_masks are the primary detector's) ---------------------
+    def __call__(self, image_bgr: np.ndarray, conf: float = 0.25, device=None, verbose: bool = False, imgsz: int = 640,
+                 retina_masks: bool = True, **_):
+        """Reference call shape (core/image/detection.py:1864-1870 panels, :140-146 OSB text, :1338-1345 bubbles)."""
         from .preproc import letterbox_device
         h0, w0 = image_bgr.shape[:2]
         img = torch.from_numpy(np.ascontiguousarray(image_bgr)).to(self.device)
         lb = letterbox_device(img, imgsz, swap_rb=True)
         g = self.forward_letterboxed(lb)
-        det, cnt = self.detect(g, conf, (h0, w0), tuple(lb.shape[:2]))
+        det, cnt, _ = self.detect(g, conf, (h0, w0), tuple(lb.shape[:2]), apply_reference_dedup=False)
         n = int(cnt[0].item())
         d = det[:n].clone()
         boxes = Boxes(d[:, :4].contiguous(), d[:, 4].contiguous(), d[:, 5].contiguous()) if n else None
-        return [Results(boxes, None, (h0, w0), self.names)]
+        masks = None
+        if n and self.has_masks and retina_masks:
+            masks = Masks(self.retina_masks(g, det, None, n, (h0, w0), tuple(lb.shape[:2])).float())
+        return [Results(boxes, masks, (h0, w0), self.names)]

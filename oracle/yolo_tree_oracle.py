@@ -15,6 +15,7 @@ from memory of ultralytics nn/modules/{conv,block,head}.py:
   ABlock      x = x + attn(x); x = x + mlp(x);   AAttn: per-head [q k v] of hd each, tokens split into `area` contiguous
               row bands, softmax(q^T k * hd^-0.5), + pe(v) (7x7 depthwise), proj
   Detect      per level: cat(cv2(x), cv3(x)); DFL (softmax over 16 bins, expectation) -> ltrb -> xywh * stride; sigmoid cls
+  Segment     Detect + cv4(x) mask coefficients per anchor + Proto(x[0]): cv3(cv2(ConvTranspose2d(2,2)(cv1(x)))), SiLU 1x1
 
 Pre / post-processing (LetterBox, non_max_suppression, scale_boxes) are the functions of oracle/yolo_oracle.py."""
 from __future__ import annotations
@@ -57,6 +58,9 @@ def calibrate(tree: dict, img_bgr: np.ndarray, imgsz: int = 640, cls_mean: float
     finally:
         _CALIBRATING = False
     det = tree["layers"][-1]
+    if det["t"] == "Segment":       # prototypes / coefficients of O(1): mask logits of a few units, like a trained model
+        pr = det["proto"]
+        pr["upsample"]["w"], pr["upsample"]["b"] = pr["upsample"]["w"] * 0.5, pr["upsample"]["b"] * 0.5
     for br in det["cv2"]:
         br[-1]["w"], br[-1]["b"] = br[-1]["w"] * box_std, br[-1]["b"] * box_std
     for br in det["cv3"]:
@@ -177,6 +181,7 @@ def forward(tree: dict, x: torch.Tensor):
     """x [1][3][H][W] in [0,1] -> (pred [1][4+nc][A] (xywh letterbox px, class probabilities), heads [(box, cls)] raw)"""
     outs: List[torch.Tensor] = []
     cur = x
+    seg = None
     for node in tree["layers"]:
         f = node.get("f", -1)
         srcs = [cur if j == -1 else outs[j] for j in (f if isinstance(f, (list, tuple)) else [f])]
@@ -185,8 +190,13 @@ def forward(tree: dict, x: torch.Tensor):
             cur = torch.cat(srcs, 1)
         elif t == "Upsample":
             cur = F.interpolate(srcs[0], scale_factor=2, mode="nearest")
-        elif t == "Detect":
+        elif t in ("Detect", "Segment"):
             heads = [(seq(node["cv2"][i], s), seq(node["cv3"][i], s)) for i, s in enumerate(srcs)]
+            if t == "Segment":
+                mcs = [seq(node["cv4"][i], s) for i, s in enumerate(srcs)]
+                pr = node["proto"]
+                p = F.conv_transpose2d(conv(pr["cv1"], srcs[0]), pr["upsample"]["w"], pr["upsample"]["b"], stride=2)
+                seg = (mcs, conv(pr["cv3"], conv(pr["cv2"], p)))
             cur = heads
         else:
             cur = block(node, srcs[0])
@@ -212,7 +222,11 @@ def forward(tree: dict, x: torch.Tensor):
     lt, rb = dist.chunk(2, 1)
     x1y1, x2y2 = anchors - lt, anchors + rb
     dbox = torch.cat(((x1y1 + x2y2) / 2, x2y2 - x1y1), 1) * strides
-    return torch.cat((dbox, cls.sigmoid()), 1), heads
+    pred = torch.cat((dbox, cls.sigmoid()), 1)
+    if seg is not None:          # Segment: mask coefficients ride behind the class scores, the prototypes come along
+        pred = torch.cat((pred, torch.cat([m.view(bs, m.shape[1], -1) for m in seg[0]], 2)), 1)
+        return pred, heads, seg
+    return pred, heads
 
 
 @torch.no_grad()
@@ -220,10 +234,15 @@ def predict(tree: dict, img_bgr: np.ndarray, conf: float, imgsz: int = 640):
     """-> dict(xyxy [n,4] original px, conf [n], cls [n], anchors [n], heads)"""
     h0, w0 = img_bgr.shape[:2]
     x = yolo_oracle.preprocess(img_bgr, imgsz)
-    pred, heads = forward(tree, x)
+    out = forward(tree, x)
+    pred, heads, seg = out if len(out) == 3 else (out[0], out[1], None)
     nc = int(tree["layers"][-1]["nc"])
     det, anchors = yolo_oracle.non_max_suppression(pred[0], nc, conf)
     if det.shape[0] == 0:
-        return dict(xyxy=torch.zeros((0, 4)), conf=torch.zeros(0), cls=torch.zeros(0), anchors=anchors, heads=heads, raw=pred)
+        return dict(xyxy=torch.zeros((0, 4)), conf=torch.zeros(0), cls=torch.zeros(0), anchors=anchors, heads=heads, raw=pred,
+                    masks=torch.zeros((0, h0, w0), dtype=torch.bool), seg=seg)
     boxes = yolo_oracle.scale_boxes(x.shape[2:], det[:, :4], (h0, w0))
-    return dict(xyxy=boxes, conf=det[:, 4], cls=det[:, 5], anchors=anchors, heads=heads, raw=pred)
+    masks = None
+    if seg is not None:
+        masks = yolo_oracle.process_mask_native(seg[1][0], det[:, 6:], boxes, x.shape[2:], (h0, w0))
+    return dict(xyxy=boxes, conf=det[:, 4], cls=det[:, 5], anchors=anchors, heads=heads, raw=pred, masks=masks, seg=seg)

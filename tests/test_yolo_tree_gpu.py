@@ -90,7 +90,7 @@ def test_heads_and_detections_match_oracle(family, kw):
             assert err < max(1e-3, 4e-3 * float(ref.abs().max())), (family, st, err)      # measured: 1.0e-3 / 3e-4 relative
     print(f"yolo{family}: head tensors max abs err {worst:.2e}")
     ref = O.predict(tree, img, conf, imgsz)
-    det, cnt = net.detect(g, conf, hw, tuple(lb.shape[:2]))
+    det, cnt, _ = net.detect(g, conf, hw, tuple(lb.shape[:2]), apply_reference_dedup=False)
     torch.cuda.synchronize()
     n = int(cnt[0])
     assert n == ref["xyxy"].shape[0] and n > 3, (n, ref["xyxy"].shape[0])
@@ -109,6 +109,62 @@ def test_heads_and_detections_match_oracle(family, kw):
     net(other, conf=conf, imgsz=imgsz)
     again = net(img, conf=conf, imgsz=imgsz)[0]
     assert torch.equal(again.boxes.xyxy, out.boxes.xyxy) and torch.equal(again.boxes.conf, out.boxes.conf)
+
+
+def test_segment_head_serves_as_the_speech_bubble_detector(tmp_path):
+    """A YOLO11-seg checkpoint (what the default `yolo_2` file may be) loads through `load_yolo_speech_bubble`: refused by
+    the hard-wired YOLOv8-seg reader, executed from its module tree, with mask coefficients, prototypes and retina masks
+    (`process_mask_native`) against the oracle, and accepted by the device-resident page path."""
+    import sys
+    from mangatranslator_b200 import yolo_tree as T
+    from mangatranslator_b200.core.ml.model_manager import ModelType, get_model_manager
+    from mangatranslator_b200.preproc import letterbox_device
+    from mangatranslator_b200.yolo import YoloB200
+    from test_yolo_tree_host import _save_with_fake_package
+    hw, imgsz = (300, 420), 448
+    for seed in range(3, 40):
+        img = _image(seed, *hw)
+        tree = T.synthetic_tree("11", "s", nc=1, seed=seed, names={0: "bubble"}, segment=True)
+        O.calibrate(tree, img, imgsz, cls_mean=-6.0, cls_std=1.2)
+        pred, heads, seg = O.forward(tree, Y.preprocess(img, imgsz))
+        conf, cut_gap, min_gap, iou_margin, _ = _well_posed_conf(pred[:, :5])
+        if cut_gap > 0.2 and min_gap > 0.05 and iou_margin > 0.03:
+            break
+    else:
+        pytest.fail("no well-posed synthetic case found")
+    path, stash = _save_with_fake_package(tmp_path, tree)
+    sys.modules.update(stash)
+    mm = get_model_manager()
+    mm.unload_model(ModelType.YOLO_SPEECH_BUBBLE)
+    try:
+        net = mm.load_yolo_speech_bubble(str(path))
+        assert isinstance(net, T.YoloTreeB200) and isinstance(net, YoloB200) and net.has_masks and net.names == {0: "bubble"}
+        dev = net.device
+        lb = letterbox_device(torch.from_numpy(img).to(dev), imgsz, swap_rb=True)
+        g = net.forward_letterboxed(lb)
+        torch.cuda.synchronize()
+        for (gb, gc, gm, fh, fw, st), mc in zip(g["levels"], seg[0]):
+            err = (gm.cpu()[0].permute(2, 0, 1) - mc[0]).abs().max().item()
+            assert err < max(1e-3, 4e-3 * float(mc.abs().max())), ("mask coefficients", st, err)
+        perr = (g["proto"].cpu()[0].permute(2, 0, 1) - seg[1][0]).abs().max().item()
+        assert perr < max(1e-3, 4e-3 * float(seg[1].abs().max())), ("prototypes", perr)
+        ref = O.predict(tree, img, conf, imgsz)
+        out = net(img, conf=conf, imgsz=imgsz, retina_masks=True)[0]
+        n = len(out.boxes)
+        assert n == len(ref["conf"]) and n > 2
+        assert (out.boxes.xyxy.cpu() - ref["xyxy"]).abs().max().item() < 0.5
+        got, want = out.masks.data.cpu() > 0, ref["masks"]
+        assert tuple(got.shape) == tuple(want.shape) == (n, hw[0], hw[1])
+        flips = (got != want).flatten(1).sum(1)
+        area = want.flatten(1).sum(1).clamp_min(1)
+        print(f"yolo11-seg: {n} detections, prototypes max err {perr:.2e}, flipped mask pixels per detection "
+              f"{flips.tolist()} of {area.tolist()}")
+        assert int(want.sum()) > 0 and torch.all(flips <= torch.clamp(0.01 * area, min=30)), (flips, area)
+        # the device-resident page path takes the tree model like the hard-wired one
+        det, cnt, final_idx = net.detect(g, conf, hw, tuple(lb.shape[:2]), apply_reference_dedup=True)
+        assert int(cnt[0]) == n and 0 < int(cnt[1]) <= n
+    finally:
+        mm.unload_model(ModelType.YOLO_SPEECH_BUBBLE)
 
 
 @pytest.mark.parametrize("k,act,planes", [(3, 1, 2), (7, 0, 2), (3, 0, 1)])

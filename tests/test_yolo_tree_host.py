@@ -134,19 +134,36 @@ FAKE = textwrap.dedent('''
                                                    plain(b[4])) for b in n["cv3"])
             self.dfl = DFL()
 
+    class Proto(nn.Module):
+        def __init__(self, n):
+            super().__init__()
+            self.cv1, self.cv2, self.cv3 = conv(n["cv1"]), conv(n["cv2"]), conv(n["cv3"])
+            ci, co = n["upsample"]["w"].shape[:2]
+            self.upsample = nn.ConvTranspose2d(ci, co, 2, 2, 0, bias=True)
+            with torch.no_grad():
+                self.upsample.weight.copy_(n["upsample"]["w"]); self.upsample.bias.copy_(n["upsample"]["b"])
+
     class Segment(Detect):
+        def __init__(self, n):
+            super().__init__(n)
+            self.nm = n["nm"]
+            self.proto = Proto(n["proto"])
+            self.cv4 = nn.ModuleList(nn.Sequential(conv(b[0]), conv(b[1]), plain(b[2])) for b in n["cv4"])
+
+    class Pose(Detect):
         pass
 
     def make(n):
         return {"Conv": conv, "Bottleneck": Bottleneck, "C3": C3k, "C2f": C3k2, "SPPF": SPPF, "C2PSA": C2PSA, "A2C2f": A2C2f,
-                "Concat": Concat, "Detect": Detect, "Upsample": lambda n: nn.Upsample(None, 2, "nearest")}[n["t"]](n)
+                "Concat": Concat, "Detect": Detect, "Segment": Segment,
+                "Upsample": lambda n: nn.Upsample(None, 2, "nearest")}[n["t"]](n)
 
     class DetectionModel(nn.Module):
         def __init__(self, tree, head=None):
             super().__init__()
             mods = []
             for i, n in enumerate(tree["layers"]):
-                m = (head or Detect)(n) if n["t"] == "Detect" else make(n)
+                m = head(n) if (head and n["t"] == "Detect") else make(n)
                 m.f, m.i, m.type = n["f"], i, n["t"]
                 mods.append(m)
             self.model = nn.Sequential(*mods)
@@ -194,7 +211,8 @@ def _save_with_fake_package(tmp_path, tree, head=None, as_state_dict=False):
     return path, stash
 
 
-@pytest.mark.parametrize("family,kw", [("11", {}), ("12", dict(a2_residual=True, mlp_ratio=1.2))])
+@pytest.mark.parametrize("family,kw", [("11", {}), ("12", dict(a2_residual=True, mlp_ratio=1.2)), ("11", dict(segment=True))],
+                         ids=["yolo11", "yolo12", "yolo11-seg"])
 def test_checkpoint_object_is_read_back_into_the_tree_it_was_made_from(tmp_path, family, kw):
     tree = T.synthetic_tree(family, "s", nc=2, seed=3, names={0: "frame", 1: "text"}, **kw)
     path, stash = _save_with_fake_package(tmp_path, tree)
@@ -214,9 +232,9 @@ def test_checkpoint_object_is_read_back_into_the_tree_it_was_made_from(tmp_path,
 
 def test_other_heads_and_plain_state_dicts_are_refused(tmp_path):
     tree = T.synthetic_tree("11", "s", nc=1, seed=0)
-    path, stash = _save_with_fake_package(tmp_path, tree, head="Segment")
+    path, stash = _save_with_fake_package(tmp_path, tree, head="Pose")
     try:
-        with pytest.raises(W.UnsupportedCheckpoint, match="Segment"):
+        with pytest.raises(W.UnsupportedCheckpoint, match="Pose"):
             W.load_ultralytics_tree(str(path))
     finally:
         sys.modules.update(stash)
