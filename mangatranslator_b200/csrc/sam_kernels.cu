@@ -4,7 +4,9 @@
 //   mask product, the stability-based mask selection and the fused "bilinear 256^2 -> HxW, > 0, clip to the box,
 //   write uint8 0/255" mask writer (core/image/detection.py:504-511,1732-1750).
 // All softmax / normalisation math is fp32; activations travel as bf16 hi/lo planes like everywhere else.
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -327,6 +329,225 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnParams P) {
   }
 }
 
+// 8 consecutive channels of one token back into the bf16 planes (16-byte stores)
+__device__ __forceinline__ void store_tok8(const AttnParams& P, long long idx, const float (&v)[8]) {
+  uint16_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split_bf16(v[j], hi[j], lo[j]);
+  uint4 h4, l4;
+  h4.x = hi[0] | (static_cast<uint32_t>(hi[1]) << 16);
+  h4.y = hi[2] | (static_cast<uint32_t>(hi[3]) << 16);
+  h4.z = hi[4] | (static_cast<uint32_t>(hi[5]) << 16);
+  h4.w = hi[6] | (static_cast<uint32_t>(hi[7]) << 16);
+  *reinterpret_cast<uint4*>(P.out + idx) = h4;
+  if (P.planes == 2) {
+    l4.x = lo[0] | (static_cast<uint32_t>(lo[1]) << 16);
+    l4.y = lo[2] | (static_cast<uint32_t>(lo[3]) << 16);
+    l4.z = lo[4] | (static_cast<uint32_t>(lo[5]) << 16);
+    l4.w = lo[6] | (static_cast<uint32_t>(lo[7]) << 16);
+    *reinterpret_cast<uint4*>(P.out + P.o_ps + idx) = l4;
+  }
+}
+
+// Window / small-sequence attention with ONE THREAD PER QUERY (round 2).  attention_kernel above spreads a query's keys
+// over the lanes of a warp: every K element is a separate shared-memory wavefront, probabilities travel by shuffle, and
+// the block needs 74 KB of shared memory whatever the window size (three blocks per SM) — the Hiera window blocks ran at
+// 0.13-0.24 ms per launch, one of them for 4 queries x 16 keys per block.  Here a thread keeps its query and its HD
+// output accumulators in registers and walks the K / V tile with 16-byte BROADCAST loads (all lanes read the same key
+// row: one wavefront feeds 4 x 32 FMAs), the online softmax needs no cross-lane traffic (rescaling once per 8 keys),
+// and shared memory is sized by min(nk, 64) keys, so small windows run many blocks per SM.  Exact fp32 softmax.
+// raw 16-byte loads of 8 channels (hi and lo plane) through the read-only path; a padded token (row < 0) reads row 0 and
+// is patched by the caller, so that no branch sits between the loads and many stay in flight per thread
+__device__ __forceinline__ void ldg_tok8(const AttnParams& P, const uint16_t* base, int ct, int off, long long ps, long long row,
+                                         int ch, uint4& hi, uint4& lo) {
+  const long long idx = (row < 0 ? 0 : row) * ct + off + ch;
+  hi = __ldg(reinterpret_cast<const uint4*>(base + idx));
+  lo = P.planes == 2 ? __ldg(reinterpret_cast<const uint4*>(base + ps + idx)) : make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void cvt_tok8(const uint4& hi, const uint4& lo, const float* pad, bool padded, int ch, float (&v)[8]) {
+  const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+    v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+  }
+  if (padded) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = pad ? pad[ch + j] : 0.f;
+  }
+}
+
+constexpr int kLpqThreads = 64;   // queries per block
+constexpr int kLpqKeys = 64;      // keys per shared-memory tile
+template <int HD>
+__global__ void __launch_bounds__(kLpqThreads) attention_lpq_kernel(AttnParams P, int kt) {
+  extern __shared__ __align__(16) float sm[];
+  float* sK = sm;                 // [kt][HD]
+  float* sV = sm + kt * HD;       // [kt][HD]
+  const int bh = blockIdx.x;
+  const int b = bh / P.heads, h = bh - b * P.heads;
+  const int q0 = blockIdx.y * kLpqThreads;
+  const int tid = threadIdx.x;
+  const int t = q0 + tid;
+  const bool active = t < P.nq;
+  const int wso = P.pool ? P.ws / 2 : P.ws;
+  constexpr int hv = HD / 8;
+  float q[HD], acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) {
+    q[d] = 0.f;
+    acc[d] = 0.f;
+  }
+  if (active) {
+    if (P.mode == 1 && P.pool) {            // Hiera query pooling: 2x2 max inside the window
+      const int qy = t / wso, qx = t - qy * wso;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) q[d] = -INFINITY;
+      for (int a = 0; a < 2; ++a)
+        for (int c = 0; c < 2; ++c) {
+          const long long row = tok_row(P, b, (2 * qy + a) * P.ws + 2 * qx + c, P.nk);
+          uint4 rh[hv], rl[hv];
+#pragma unroll
+          for (int dv = 0; dv < hv; ++dv) ldg_tok8(P, P.q, P.q_ct, P.q_off, P.q_ps, row, h * HD + dv * 8, rh[dv], rl[dv]);
+#pragma unroll
+          for (int dv = 0; dv < hv; ++dv) {
+            float u[8];
+            cvt_tok8(rh[dv], rl[dv], P.pad_q, row < 0, h * HD + dv * 8, u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[dv * 8 + j] = fmaxf(q[dv * 8 + j], u[j]);
+          }
+        }
+    } else {
+      const long long row = tok_row(P, b, t, P.nq);
+      uint4 rh[hv], rl[hv];
+#pragma unroll
+      for (int dv = 0; dv < hv; ++dv) ldg_tok8(P, P.q, P.q_ct, P.q_off, P.q_ps, row, h * HD + dv * 8, rh[dv], rl[dv]);
+#pragma unroll
+      for (int dv = 0; dv < hv; ++dv) {
+        float u[8];
+        cvt_tok8(rh[dv], rl[dv], P.pad_q, row < 0, h * HD + dv * 8, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[dv * 8 + j] = u[j];
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) q[d] *= P.scale;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < P.nk; k0 += kt) {
+    const int nk_tile = min(kt, P.nk - k0);
+    __syncthreads();
+    constexpr int U = HD > 72 ? 2 : 4;        // 8-16 x 16-byte loads in flight per thread (registers: q and acc stay live)
+    const int items = nk_tile * hv;
+    for (int i0 = tid; i0 < items; i0 += U * kLpqThreads) {
+      uint4 kh[U], kl[U], vh[U], vl[U];
+      long long rows[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = min(i0 + u * kLpqThreads, items - 1);
+        const int ki = i / hv, dv = i - ki * hv;
+        rows[u] = tok_row(P, b, k0 + ki, P.nk);
+        ldg_tok8(P, P.k, P.k_ct, P.k_off, P.k_ps, rows[u], h * HD + dv * 8, kh[u], kl[u]);
+        ldg_tok8(P, P.v, P.v_ct, P.v_off, P.v_ps, rows[u], h * HD + dv * 8, vh[u], vl[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * kLpqThreads;
+        if (i >= items) break;
+        const int ki = i / hv, dv = i - ki * hv;
+        float kv[8], vv[8];
+        cvt_tok8(kh[u], kl[u], P.pad_k, rows[u] < 0, h * HD + dv * 8, kv);
+        cvt_tok8(vh[u], vl[u], P.pad_v, rows[u] < 0, h * HD + dv * 8, vv);
+        float4* dk = reinterpret_cast<float4*>(sK + ki * HD + dv * 8);
+        float4* dvp = reinterpret_cast<float4*>(sV + ki * HD + dv * 8);
+        dk[0] = make_float4(kv[0], kv[1], kv[2], kv[3]);
+        dk[1] = make_float4(kv[4], kv[5], kv[6], kv[7]);
+        dvp[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        dvp[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+      }
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int c0 = 0; c0 < nk_tile; c0 += 8) {
+      float sc8[8];
+      float cm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if (c0 + j < nk_tile) {
+          const float4* kr = reinterpret_cast<const float4*>(sK + (c0 + j) * HD);
+#pragma unroll
+          for (int d4 = 0; d4 < HD / 4; ++d4) {
+            const float4 kk = kr[d4];
+            s0 = fmaf(q[4 * d4], kk.x, s0);
+            s1 = fmaf(q[4 * d4 + 1], kk.y, s1);
+            s2 = fmaf(q[4 * d4 + 2], kk.z, s2);
+            s3 = fmaf(q[4 * d4 + 3], kk.w, s3);
+          }
+          sc8[j] = (s0 + s1) + (s2 + s3);
+        } else {
+          sc8[j] = -INFINITY;
+        }
+        cm = fmaxf(cm, sc8[j]);
+      }
+      const float nm = fmaxf(m, cm);          // finite: key c0 is always valid
+      const float corr = expf(m - nm);        // 0 on the first chunk (m = -inf)
+      l *= corr;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] *= corr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c0 + j < nk_tile) {
+          const float pw = expf(sc8[j] - nm);
+          l += pw;
+          const float4* vr = reinterpret_cast<const float4*>(sV + (c0 + j) * HD);
+#pragma unroll
+          for (int d4 = 0; d4 < HD / 4; ++d4) {
+            const float4 vv = vr[d4];
+            acc[4 * d4] = fmaf(pw, vv.x, acc[4 * d4]);
+            acc[4 * d4 + 1] = fmaf(pw, vv.y, acc[4 * d4 + 1]);
+            acc[4 * d4 + 2] = fmaf(pw, vv.z, acc[4 * d4 + 2]);
+            acc[4 * d4 + 3] = fmaf(pw, vv.w, acc[4 * d4 + 3]);
+          }
+        }
+      }
+      m = nm;
+    }
+  }
+  if (!active) return;
+  long long row;
+  if (P.mode == 0) {
+    row = static_cast<long long>(b) * P.nq + t;
+  } else {                                    // un-partition: the window's token goes back to its grid position
+    const int by = b / P.nwx, bx = b - by * P.nwx;
+    const int ty = t / wso, tx = t - ty * wso;
+    const int y = by * wso + ty, x = bx * wso + tx;
+    const int gh = P.pool ? P.grid_h / 2 : P.grid_h, gw = P.pool ? P.grid_w / 2 : P.grid_w;
+    if (y >= gh || x >= gw) return;           // padding of the window partition is dropped
+    row = static_cast<long long>(y) * gw + x;
+  }
+  const float inv = 1.0f / l;
+#pragma unroll
+  for (int dv = 0; dv < hv; ++dv) {
+    float o8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o8[j] = acc[dv * 8 + j] * inv;
+    store_tok8(P, row * P.o_ct + P.o_off + h * HD + dv * 8, o8);
+  }
+}
+
+template <int HD>
+int launch_lpq(const AttnParams& P, cudaStream_t st) {
+  const int kt = P.nk < kLpqKeys ? ((P.nk + 7) / 8) * 8 : kLpqKeys;
+  const size_t smem = sizeof(float) * 2 * static_cast<size_t>(kt) * HD;
+  if (cudaFuncSetAttribute(attention_lpq_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
+      cudaSuccess)
+    return -1;
+  dim3 grid(static_cast<unsigned>(P.B * P.heads), static_cast<unsigned>((P.nq + kLpqThreads - 1) / kLpqThreads));
+  attention_lpq_kernel<HD><<<grid, kLpqThreads, smem, st>>>(P, kt);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 // Few queries against many keys (the mask decoder's token -> image cross attention: 9 queries x 4096 keys per box and
 // head).  The general kernel above parallelises over queries and would leave one warp walking all keys; here one block
 // owns a (batch, head), keeps the whole score matrix [nq][nk] in shared memory and parallelises over KEYS.
@@ -427,6 +648,227 @@ __global__ void __launch_bounds__(kFewQThreads) attention_fewq_kernel(AttnParams
   }
 }
 
+
+// Many queries against a handful of keys (the mask decoder's image -> token cross attention: 4096 queries x 9 keys per
+// box and head).  The general kernel pads the 9 keys to a 64-key tile and keeps 23 of 32 lanes idle; here the K / V rows
+// of a batch entry (all heads) sit in shared memory as fp32 and ONE THREAD owns a (query, head): consecutive threads
+// read consecutive 2 * HD-byte pieces of a query row (coalesced), the scores never leave registers (the dot products
+// are evaluated twice: once for the maximum, once for the weights), output written with 16-byte stores.
+constexpr int kFewKThreads = 256;
+template <int HD>
+__global__ void __launch_bounds__(kFewKThreads) attention_fewk_kernel(AttnParams P) {
+  extern __shared__ float sm[];
+  const int H = P.heads, Wd = H * HD, nk = P.nk;
+  float* sK = sm;                // [nk][H*HD]
+  float* sV = sm + nk * Wd;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < nk * (Wd / 8); i += kFewKThreads) {
+    const int key = i / (Wd / 8), c8 = i - key * (Wd / 8);
+    float t8[8];
+    load_tok8(P, P.k, P.k_ct, P.k_off, P.k_ps, nullptr, static_cast<long long>(b) * nk + key, c8 * 8, t8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sK[key * Wd + c8 * 8 + j] = t8[j];
+    load_tok8(P, P.v, P.v_ct, P.v_off, P.v_ps, nullptr, static_cast<long long>(b) * nk + key, c8 * 8, t8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sV[key * Wd + c8 * 8 + j] = t8[j];
+  }
+  __syncthreads();
+  const int qpb = kFewKThreads / H;
+  const int q = blockIdx.x * qpb + tid / H, h = tid % H;
+  if (tid >= qpb * H || q >= P.nq) return;
+  const long long row = static_cast<long long>(b) * P.nq + q;
+  float qv[HD];
+#pragma unroll
+  for (int c = 0; c < HD; c += 8) {
+    float t8[8];
+    load_tok8(P, P.q, P.q_ct, P.q_off + h * HD, P.q_ps, nullptr, row, c, t8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qv[c + j] = t8[j] * P.scale;
+  }
+  float m = -INFINITY;
+  for (int key = 0; key < nk; ++key) {
+    const float* kr = sK + key * Wd + h * HD;
+    float sdot = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) sdot += qv[d] * kr[d];
+    m = fmaxf(m, sdot);
+  }
+  float l = 0.f, acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+  for (int key = 0; key < nk; ++key) {
+    const float* kr = sK + key * Wd + h * HD;
+    const float* vr = sV + key * Wd + h * HD;
+    float sdot = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) sdot += qv[d] * kr[d];
+    const float pw = expf(sdot - m);
+    l += pw;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] += pw * vr[d];
+  }
+  const float inv = 1.0f / l;
+#pragma unroll
+  for (int c = 0; c < HD; c += 8) {
+    float o8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o8[j] = acc[c + j] * inv;
+    store_tok8(P, row * P.o_ct + P.o_off + h * HD + c, o8);
+  }
+}
+
+// Few queries against many keys, keys split over a THREAD-BLOCK CLUSTER.  attention_fewq_kernel above gives a whole
+// (batch, head) to one CTA: 96 CTAs for 12 boxes x 8 heads, each walking 4096 keys through four block-wide phases —
+// 0.19 ms per launch at 0.3 TB/s.  Here the CTAs of a cluster take nk / S keys each, keep their partial softmax state
+// (local maximum, local sum, unnormalised weighted V sums) in shared memory, and rank 0 folds the S partials through
+// distributed shared memory (exact: every partial is rescaled by exp(m_r - M)).
+namespace cg = cooperative_groups;
+constexpr int kFewQCThreads = 256;
+constexpr int kFewQCSplit = 8;
+template <int HD>
+__global__ void __launch_bounds__(kFewQCThreads) attention_fewq_cluster_kernel(AttnParams P) {
+  extern __shared__ float sm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int S = static_cast<int>(cluster.num_blocks());
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int bh = blockIdx.x / S;
+  const int b = bh / P.heads, h = bh - b * P.heads;
+  const int nq = P.nq, nk = P.nk;
+  constexpr int hd = HD;
+  const int k0 = static_cast<int>(static_cast<long long>(nk) * rank / S);
+  const int k1 = static_cast<int>(static_cast<long long>(nk) * (rank + 1) / S);
+  const int nkl = k1 - k0, nkmax = (nk + S - 1) / S + 1;
+  float* part = sm;                                  // [nq][hd] unnormalised sums, then  [nq] max, [nq] sum
+  float* pm = part + nq * hd;
+  float* pl = pm + nq;
+  float* qs = pl + nq;                               // [nq][hd]
+  float* sc = qs + nq * hd;                          // [nq][nkmax]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < nq * hd; i += kFewQCThreads) {
+    const int qi = i / hd, d = i - qi * hd;
+    const long long idx = (static_cast<long long>(b) * nq + qi) * P.q_ct + P.q_off + h * hd + d;
+    float v = bf16_to_f(P.q[idx]);
+    if (P.planes == 2) v += bf16_to_f(P.q[P.q_ps + idx]);
+    qs[i] = v * P.scale;
+    part[i] = 0.f;
+  }
+  __syncthreads();
+  for (int kl = tid; kl < nkl; kl += kFewQCThreads) {
+    float kv[HD];
+    const long long row = static_cast<long long>(b) * nk + k0 + kl;
+#pragma unroll
+    for (int c = 0; c < hd; c += 8) {
+      float t8[8];
+      load_tok8(P, P.k, P.k_ct, P.k_off + h * hd, P.k_ps, nullptr, row, c, t8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kv[c + j] = t8[j];
+    }
+    for (int qi = 0; qi < nq; ++qi) {
+      float sdot = 0.f;
+#pragma unroll
+      for (int d = 0; d < hd; ++d) sdot += qs[qi * hd + d] * kv[d];
+      sc[qi * nkmax + kl] = sdot;
+    }
+  }
+  __syncthreads();
+  for (int qi = warp; qi < nq; qi += kFewQCThreads / 32) {
+    float* row = sc + qi * nkmax;
+    float m = -INFINITY;
+    for (int k2 = lane; k2 < nkl; k2 += 32) m = fmaxf(m, row[k2]);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float l = 0.f;
+    for (int k2 = lane; k2 < nkl; k2 += 32) {
+      const float pv = expf(row[k2] - m);
+      row[k2] = pv;
+      l += pv;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (lane == 0) {
+      pm[qi] = m;
+      pl[qi] = l;
+    }
+  }
+  __syncthreads();
+  // weighted V sums: thread = (key split, query, 8-channel group)
+  constexpr int DG = HD / 8;
+  const int per = nq * DG;
+  const int nsplit = kFewQCThreads / per;            // >= 1 (checked by the launcher)
+  const int ks = tid / per, r = tid - ks * per;
+  if (ks < nsplit) {
+    const int qi = r / DG, dg = r - qi * DG;
+    const int a0 = static_cast<int>(static_cast<long long>(nkl) * ks / nsplit);
+    const int a1 = static_cast<int>(static_cast<long long>(nkl) * (ks + 1) / nsplit);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* row = sc + qi * nkmax;
+#pragma unroll 2
+    for (int kl = a0; kl < a1; ++kl) {
+      float v8[8];
+      load_tok8(P, P.v, P.v_ct, P.v_off + h * hd, P.v_ps, nullptr, static_cast<long long>(b) * nk + k0 + kl, dg * 8, v8);
+      const float pw = row[kl];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += pw * v8[j];
+    }
+    // one slot per (split, query, channel) behind the scores; folded in split order below (deterministic)
+    float* slot = sc + nq * nkmax + (ks * nq + qi) * hd + dg * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) slot[j] = acc[j];
+  }
+  __syncthreads();
+  for (int i = tid; i < nq * hd; i += kFewQCThreads) {
+    float o = 0.f;
+    for (int s2 = 0; s2 < nsplit; ++s2) o += sc[nq * nkmax + s2 * nq * hd + i];
+    part[i] = o;
+  }
+  cluster.sync();
+  if (rank == 0) {
+    for (int i = tid; i < nq * hd; i += kFewQCThreads) {
+      const int qi = i / hd, d = i - qi * hd;
+      float M = -INFINITY;
+      for (int r2 = 0; r2 < S; ++r2) M = fmaxf(M, cluster.map_shared_rank(pm, r2)[qi]);
+      float num = 0.f, den = 0.f;
+      for (int r2 = 0; r2 < S; ++r2) {
+        const float w = expf(cluster.map_shared_rank(pm, r2)[qi] - M);
+        num += w * cluster.map_shared_rank(part, r2)[i];
+        den += w * cluster.map_shared_rank(pl, r2)[qi];
+      }
+      const float o = num / den;
+      const long long idx = (static_cast<long long>(b) * nq + qi) * P.o_ct + P.o_off + h * hd + d;
+      uint16_t hi, lo;
+      split_bf16(o, hi, lo);
+      P.out[idx] = hi;
+      if (P.planes == 2) P.out[P.o_ps + idx] = lo;
+    }
+  }
+  cluster.sync();                                    // the other ranks' shared memory stays alive until rank 0 has read it
+}
+
+template <int HD>
+int launch_fewq_cluster(const AttnParams& P, cudaStream_t st) {
+  const int nkmax = (P.nk + kFewQCSplit - 1) / kFewQCSplit + 1;
+  const int nsplit = kFewQCThreads / (P.nq * (HD / 8));
+  const size_t smem = sizeof(float) * (static_cast<size_t>(P.nq) * HD * 2 + 2 * P.nq + static_cast<size_t>(P.nq) * nkmax +
+                                       static_cast<size_t>(nsplit) * P.nq * HD);
+  if (smem > 96 * 1024) return 1;
+  cudaError_t e = cudaFuncSetAttribute(attention_fewq_cluster_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(P.B * P.heads * kFewQCSplit));
+  cfg.blockDim = dim3(kFewQCThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kFewQCSplit;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, attention_fewq_cluster_kernel<HD>, P);
+  return e == cudaSuccess ? 0 : -1;
+}
 
 // ---- patch embedding: (u8 - mean')/std' -> conv k x k / stride / pad (3 -> C) + bias + positional embedding -------
 // one thread per (output pixel, 8 output channels); weights in shared memory
@@ -667,6 +1109,32 @@ int mtb_attention(const mtb_attn_desc* d, void* stream) {
   P.grid_h = d->grid_h; P.grid_w = d->grid_w; P.ws = d->ws; P.pool = d->pool;
   P.nwx = d->ws > 0 ? (d->grid_w + d->ws - 1) / d->ws : 1;
   P.pad_q = d->pad_q; P.pad_k = d->pad_k; P.pad_v = d->pad_v;
+  const bool aligned8 = ((d->q_ct | d->k_ct | d->v_ct | d->o_ct | d->q_off | d->k_off | d->v_off | d->o_off) % 8) == 0 &&
+                        ((d->q_ps | d->k_ps | d->v_ps | d->o_ps) % 8) == 0;
+  static const bool use_fewk = !getenv("MTB200_ATTN_FEWK") || atoi(getenv("MTB200_ATTN_FEWK")) != 0;
+  static const bool use_cluster = !getenv("MTB200_ATTN_CLUSTER") || atoi(getenv("MTB200_ATTN_CLUSTER")) != 0;
+  if (use_fewk && d->mode == 0 && d->nk <= 32 && d->nq >= 256 && (d->hd == 16 || d->hd == 32) && aligned8 &&
+      d->heads >= 1 && d->heads <= kFewKThreads &&
+      static_cast<size_t>(d->nk) * d->heads * d->hd * 2 * sizeof(float) <= 48 * 1024) {
+    const size_t ksmem = static_cast<size_t>(d->nk) * d->heads * d->hd * 2 * sizeof(float);
+    const int qpb = kFewKThreads / d->heads;
+    dim3 grid(static_cast<unsigned>((d->nq + qpb - 1) / qpb), static_cast<unsigned>(d->B));
+    if (d->hd == 16) attention_fewk_kernel<16><<<grid, kFewKThreads, ksmem, static_cast<cudaStream_t>(stream)>>>(P);
+    else attention_fewk_kernel<32><<<grid, kFewKThreads, ksmem, static_cast<cudaStream_t>(stream)>>>(P);
+    MTB_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+  }
+  if (use_cluster && d->mode == 0 && d->nq <= 16 && d->nk >= 512 && (d->hd == 16 || d->hd == 32) && aligned8 &&
+      d->nq * (d->hd / 8) <= kFewQCThreads) {
+    const int rc = d->hd == 16 ? launch_fewq_cluster<16>(P, static_cast<cudaStream_t>(stream))
+                               : launch_fewq_cluster<32>(P, static_cast<cudaStream_t>(stream));
+    MTB_REQUIRE(rc >= 0, "mtb_attention: cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == 0) {
+      g_launches.fetch_add(1);
+      return 0;
+    }
+  }
   if (d->mode == 0 && d->nq <= 16 && d->nk >= 512 && (d->hd == 16 || d->hd == 32) && d->nq * d->hd <= kFewQThreads) {
     const size_t fsmem = sizeof(float) * (static_cast<size_t>(d->nq) * d->nk + d->nq * d->hd + 16);
     if (fsmem <= 200 * 1024) {
@@ -683,6 +1151,16 @@ int mtb_attention(const mtb_attn_desc* d, void* stream) {
       g_launches.fetch_add(1);
       return 0;
     }
+  }
+  static const bool use_lpq = !getenv("MTB200_ATTN_LPQ") || atoi(getenv("MTB200_ATTN_LPQ")) != 0;
+  if (use_lpq && aligned8 && !(d->mode == 1 && d->pool && (d->ws & 1)) &&
+      (d->hd == 32 || d->hd == 64 || d->hd == 72 || d->hd == 96)) {
+    const cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    const int rc = d->hd == 32 ? launch_lpq<32>(P, cs) : d->hd == 64 ? launch_lpq<64>(P, cs)
+                 : d->hd == 72 ? launch_lpq<72>(P, cs) : launch_lpq<96>(P, cs);
+    MTB_REQUIRE(rc == 0, "mtb_attention: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(1);
+    return 0;
   }
   const size_t smem = sizeof(float) * (static_cast<size_t>(kKT) * (d->hd + 1) + static_cast<size_t>(kKT) * d->hd +
                                        static_cast<size_t>(kQT) * d->hd);

@@ -82,12 +82,16 @@ def test_sam2_single_box_and_many_boxes_shapes():
 
 
 @pytest.mark.parametrize("shape", [(3, 8, 16, 9, 1024), (2, 2, 32, 100, 77), (1, 4, 96, 512, 512), (12, 8, 16, 9, 4096),
-                                   (1, 4, 96, 4096, 4096), (2, 2, 64, 200, 300), (1, 2, 128, 256, 320)],
+                                   (1, 4, 96, 4096, 4096), (2, 2, 64, 200, 300), (1, 2, 128, 256, 320),
+                                   (12, 8, 16, 4096, 9), (2, 4, 32, 300, 17), (1, 8, 16, 9, 1003), (2, 2, 32, 16, 600),
+                                   (3, 2, 96, 70, 131), (2, 4, 72, 49, 49), (5, 2, 64, 4, 16), (2, 1, 128, 40, 90)],
                          ids=["few_queries", "general", "tc_hd96", "decoder_t2i", "tc_sam_global", "tc_ragged_hd64",
-                              "tc_hd128"])
+                              "tc_hd128", "decoder_i2t_few_keys", "few_keys_hd32", "cluster_ragged_keys", "cluster_hd32",
+                              "lpq_hd96_two_key_tiles", "lpq_hd72", "lpq_tiny_window", "general_hd128"])
 def test_attention_kernels_match_torch(shape):
     """mtb_attention (mode 0) against torch softmax attention on the plane-rounded inputs: every dispatch target
-    (general register-blocked kernel, few-queries/many-keys kernel) must agree to fp32 accuracy."""
+    (general register-blocked kernel, few-queries/many-keys kernel with its keys split over a thread-block cluster,
+    many-queries/few-keys kernel, tensor-core kernel) must agree to fp32 accuracy."""
     import ctypes as C
     from mangatranslator_b200 import planes as P
     from mangatranslator_b200._lib import check, lib, stream_ptr
