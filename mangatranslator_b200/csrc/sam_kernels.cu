@@ -377,24 +377,30 @@ __device__ __forceinline__ void cvt_tok8(const uint4& hi, const uint4& lo, const
   }
 }
 
-constexpr int kLpqThreads = 64;   // queries per block
+constexpr int kLpqQueries = 64;   // queries per block
 constexpr int kLpqKeys = 64;      // keys per shared-memory tile
-template <int HD>
-__global__ void __launch_bounds__(kLpqThreads) attention_lpq_kernel(AttnParams P, int kt) {
+// SP = threads per query: with SP = 2 the two lanes of a pair own one half of the head's channels each (half of q and of
+// the output accumulators: ~130 registers instead of 250, twice the warps per SM); the pair's partial dot products are
+// added with one shuffle per key.
+template <int HD, int SP>
+__global__ void __launch_bounds__(kLpqQueries * SP, SP == 2 ? 3 : 1) attention_lpq_kernel(AttnParams P, int kt) {
+  constexpr int kThreadsB = kLpqQueries * SP;
+  constexpr int HH = HD / SP;                 // channels owned by a thread
+  constexpr int hv = HD / 8, hvh = HH / 8;
   extern __shared__ __align__(16) float sm[];
   float* sK = sm;                 // [kt][HD]
   float* sV = sm + kt * HD;       // [kt][HD]
   const int bh = blockIdx.x;
   const int b = bh / P.heads, h = bh - b * P.heads;
-  const int q0 = blockIdx.y * kLpqThreads;
+  const int q0 = blockIdx.y * kLpqQueries;
   const int tid = threadIdx.x;
-  const int t = q0 + tid;
+  const int t = q0 + tid / SP;
+  const int c_base = (tid % SP) * HH;         // first channel of this thread inside the head
   const bool active = t < P.nq;
   const int wso = P.pool ? P.ws / 2 : P.ws;
-  constexpr int hv = HD / 8;
-  float q[HD], acc[HD];
+  float q[HH], acc[HH];
 #pragma unroll
-  for (int d = 0; d < HD; ++d) {
+  for (int d = 0; d < HH; ++d) {
     q[d] = 0.f;
     acc[d] = 0.f;
   }
@@ -402,49 +408,51 @@ __global__ void __launch_bounds__(kLpqThreads) attention_lpq_kernel(AttnParams P
     if (P.mode == 1 && P.pool) {            // Hiera query pooling: 2x2 max inside the window
       const int qy = t / wso, qx = t - qy * wso;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) q[d] = -INFINITY;
+      for (int d = 0; d < HH; ++d) q[d] = -INFINITY;
       for (int a = 0; a < 2; ++a)
         for (int c = 0; c < 2; ++c) {
           const long long row = tok_row(P, b, (2 * qy + a) * P.ws + 2 * qx + c, P.nk);
-          uint4 rh[hv], rl[hv];
+          uint4 rh[hvh], rl[hvh];
 #pragma unroll
-          for (int dv = 0; dv < hv; ++dv) ldg_tok8(P, P.q, P.q_ct, P.q_off, P.q_ps, row, h * HD + dv * 8, rh[dv], rl[dv]);
+          for (int dv = 0; dv < hvh; ++dv)
+            ldg_tok8(P, P.q, P.q_ct, P.q_off, P.q_ps, row, h * HD + c_base + dv * 8, rh[dv], rl[dv]);
 #pragma unroll
-          for (int dv = 0; dv < hv; ++dv) {
+          for (int dv = 0; dv < hvh; ++dv) {
             float u[8];
-            cvt_tok8(rh[dv], rl[dv], P.pad_q, row < 0, h * HD + dv * 8, u);
+            cvt_tok8(rh[dv], rl[dv], P.pad_q, row < 0, h * HD + c_base + dv * 8, u);
 #pragma unroll
             for (int j = 0; j < 8; ++j) q[dv * 8 + j] = fmaxf(q[dv * 8 + j], u[j]);
           }
         }
     } else {
       const long long row = tok_row(P, b, t, P.nq);
-      uint4 rh[hv], rl[hv];
+      uint4 rh[hvh], rl[hvh];
 #pragma unroll
-      for (int dv = 0; dv < hv; ++dv) ldg_tok8(P, P.q, P.q_ct, P.q_off, P.q_ps, row, h * HD + dv * 8, rh[dv], rl[dv]);
+      for (int dv = 0; dv < hvh; ++dv)
+        ldg_tok8(P, P.q, P.q_ct, P.q_off, P.q_ps, row, h * HD + c_base + dv * 8, rh[dv], rl[dv]);
 #pragma unroll
-      for (int dv = 0; dv < hv; ++dv) {
+      for (int dv = 0; dv < hvh; ++dv) {
         float u[8];
-        cvt_tok8(rh[dv], rl[dv], P.pad_q, row < 0, h * HD + dv * 8, u);
+        cvt_tok8(rh[dv], rl[dv], P.pad_q, row < 0, h * HD + c_base + dv * 8, u);
 #pragma unroll
         for (int j = 0; j < 8; ++j) q[dv * 8 + j] = u[j];
       }
     }
 #pragma unroll
-    for (int d = 0; d < HD; ++d) q[d] *= P.scale;
+    for (int d = 0; d < HH; ++d) q[d] *= P.scale;
   }
   float m = -INFINITY, l = 0.f;
   for (int k0 = 0; k0 < P.nk; k0 += kt) {
     const int nk_tile = min(kt, P.nk - k0);
     __syncthreads();
-    constexpr int U = HD > 72 ? 2 : 4;        // 8-16 x 16-byte loads in flight per thread (registers: q and acc stay live)
+    constexpr int U = (HH > 72 || SP == 2) ? 2 : 4;   // 8-16 x 16-byte loads in flight per thread (q and acc stay live)
     const int items = nk_tile * hv;
-    for (int i0 = tid; i0 < items; i0 += U * kLpqThreads) {
+    for (int i0 = tid; i0 < items; i0 += U * kThreadsB) {
       uint4 kh[U], kl[U], vh[U], vl[U];
       long long rows[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int i = min(i0 + u * kLpqThreads, items - 1);
+        const int i = min(i0 + u * kThreadsB, items - 1);
         const int ki = i / hv, dv = i - ki * hv;
         rows[u] = tok_row(P, b, k0 + ki, P.nk);
         ldg_tok8(P, P.k, P.k_ct, P.k_off, P.k_ps, rows[u], h * HD + dv * 8, kh[u], kl[u]);
@@ -452,7 +460,7 @@ __global__ void __launch_bounds__(kLpqThreads) attention_lpq_kernel(AttnParams P
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * kLpqThreads;
+        const int i = i0 + u * kThreadsB;
         if (i >= items) break;
         const int ki = i / hv, dv = i - ki * hv;
         float kv[8], vv[8];
@@ -467,42 +475,41 @@ __global__ void __launch_bounds__(kLpqThreads) attention_lpq_kernel(AttnParams P
       }
     }
     __syncthreads();
-    if (!active) continue;
+    // (inactive threads walk the tile too: with SP = 2 the pair's shuffle needs both lanes; their q is 0)
     for (int c0 = 0; c0 < nk_tile; c0 += 8) {
       float sc8[8];
       float cm = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        if (c0 + j < nk_tile) {
-          const float4* kr = reinterpret_cast<const float4*>(sK + (c0 + j) * HD);
+        const int key = min(c0 + j, nk_tile - 1);
+        const float4* kr = reinterpret_cast<const float4*>(sK + key * HD + c_base);
 #pragma unroll
-          for (int d4 = 0; d4 < HD / 4; ++d4) {
-            const float4 kk = kr[d4];
-            s0 = fmaf(q[4 * d4], kk.x, s0);
-            s1 = fmaf(q[4 * d4 + 1], kk.y, s1);
-            s2 = fmaf(q[4 * d4 + 2], kk.z, s2);
-            s3 = fmaf(q[4 * d4 + 3], kk.w, s3);
-          }
-          sc8[j] = (s0 + s1) + (s2 + s3);
-        } else {
-          sc8[j] = -INFINITY;
+        for (int d4 = 0; d4 < HH / 4; ++d4) {
+          const float4 kk = kr[d4];
+          s0 = fmaf(q[4 * d4], kk.x, s0);
+          s1 = fmaf(q[4 * d4 + 1], kk.y, s1);
+          s2 = fmaf(q[4 * d4 + 2], kk.z, s2);
+          s3 = fmaf(q[4 * d4 + 3], kk.w, s3);
         }
+        float sd = (s0 + s1) + (s2 + s3);
+        if (SP == 2) sd += __shfl_xor_sync(0xffffffffu, sd, 1);
+        sc8[j] = (c0 + j < nk_tile) ? sd : -INFINITY;
         cm = fmaxf(cm, sc8[j]);
       }
       const float nm = fmaxf(m, cm);          // finite: key c0 is always valid
       const float corr = expf(m - nm);        // 0 on the first chunk (m = -inf)
       l *= corr;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] *= corr;
+      for (int d = 0; d < HH; ++d) acc[d] *= corr;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (c0 + j < nk_tile) {
           const float pw = expf(sc8[j] - nm);
           l += pw;
-          const float4* vr = reinterpret_cast<const float4*>(sV + (c0 + j) * HD);
+          const float4* vr = reinterpret_cast<const float4*>(sV + (c0 + j) * HD + c_base);
 #pragma unroll
-          for (int d4 = 0; d4 < HD / 4; ++d4) {
+          for (int d4 = 0; d4 < HH / 4; ++d4) {
             const float4 vv = vr[d4];
             acc[4 * d4] = fmaf(pw, vv.x, acc[4 * d4]);
             acc[4 * d4 + 1] = fmaf(pw, vv.y, acc[4 * d4 + 1]);
@@ -528,23 +535,23 @@ __global__ void __launch_bounds__(kLpqThreads) attention_lpq_kernel(AttnParams P
   }
   const float inv = 1.0f / l;
 #pragma unroll
-  for (int dv = 0; dv < hv; ++dv) {
+  for (int dv = 0; dv < hvh; ++dv) {
     float o8[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o8[j] = acc[dv * 8 + j] * inv;
-    store_tok8(P, row * P.o_ct + P.o_off + h * HD + dv * 8, o8);
+    store_tok8(P, row * P.o_ct + P.o_off + h * HD + c_base + dv * 8, o8);
   }
 }
 
-template <int HD>
+template <int HD, int SP>
 int launch_lpq(const AttnParams& P, cudaStream_t st) {
   const int kt = P.nk < kLpqKeys ? ((P.nk + 7) / 8) * 8 : kLpqKeys;
   const size_t smem = sizeof(float) * 2 * static_cast<size_t>(kt) * HD;
-  if (cudaFuncSetAttribute(attention_lpq_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
-      cudaSuccess)
+  if (cudaFuncSetAttribute(attention_lpq_kernel<HD, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(smem)) != cudaSuccess)
     return -1;
-  dim3 grid(static_cast<unsigned>(P.B * P.heads), static_cast<unsigned>((P.nq + kLpqThreads - 1) / kLpqThreads));
-  attention_lpq_kernel<HD><<<grid, kLpqThreads, smem, st>>>(P, kt);
+  dim3 grid(static_cast<unsigned>(P.B * P.heads), static_cast<unsigned>((P.nq + kLpqQueries - 1) / kLpqQueries));
+  attention_lpq_kernel<HD, SP><<<grid, kLpqQueries * SP, smem, st>>>(P, kt);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1156,8 +1163,11 @@ int mtb_attention(const mtb_attn_desc* d, void* stream) {
   if (use_lpq && aligned8 && !(d->mode == 1 && d->pool && (d->ws & 1)) &&
       (d->hd == 32 || d->hd == 64 || d->hd == 72 || d->hd == 96)) {
     const cudaStream_t cs = static_cast<cudaStream_t>(stream);
-    const int rc = d->hd == 32 ? launch_lpq<32>(P, cs) : d->hd == 64 ? launch_lpq<64>(P, cs)
-                 : d->hd == 72 ? launch_lpq<72>(P, cs) : launch_lpq<96>(P, cs);
+    static const int split = getenv("MTB200_ATTN_LPQ_SPLIT") ? atoi(getenv("MTB200_ATTN_LPQ_SPLIT")) : 2;
+    const int rc = d->hd == 32 ? launch_lpq<32, 1>(P, cs)
+                 : d->hd == 64 ? (split == 2 ? launch_lpq<64, 2>(P, cs) : launch_lpq<64, 1>(P, cs))
+                 : d->hd == 72 ? launch_lpq<72, 1>(P, cs)
+                               : (split == 2 ? launch_lpq<96, 2>(P, cs) : launch_lpq<96, 1>(P, cs));
     MTB_REQUIRE(rc == 0, "mtb_attention: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches.fetch_add(1);
     return 0;
