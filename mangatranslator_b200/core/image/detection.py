@@ -550,7 +550,20 @@ def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.
     tables = torch.zeros((npages, 300, 8), dtype=torch.float32, device=pages_bgr[0].device) if npages else None
     counts = torch.zeros((npages,), dtype=torch.int32, device=pages_bgr[0].device) if npages else None
     enc0 = None
-    for pi, page in enumerate(pages_bgr):
+    import os as _os
+    batched = (npages > 1 and _os.environ.get("MTB200_YOLO_BATCH", "1") != "0" and hasattr(yolo, "forward_letterboxed_batch")
+               and len({tuple(p.shape) for p in pages_bgr}) == 1)
+    if batched:
+        # pages of one size share ONE detector plan with a batch dimension (the deep layers of a single page leave most
+        # SMs idle); decode / NMS / dedup run for the whole batch in their own batched launches
+        h, w = int(pages_bgr[0].shape[0]), int(pages_bgr[0].shape[1])
+        lbs = [letterbox_device(page, imgsz, swap_rb=True) for page in pages_bgr]
+        g = yolo.forward_letterboxed_batch(lbs)
+        det, cnt, final_idx = yolo.detect_batch(g, confidence, (h, w), tuple(lbs[0].shape[:2]), apply_reference_dedup=True)
+        idx = final_idx.long().clamp_(0, det.shape[1] - 1)
+        tables.copy_(torch.gather(det, 1, idx.unsqueeze(-1).expand(-1, -1, det.shape[2])))
+        counts.copy_(cnt[:, 1])
+    for pi, page in enumerate(pages_bgr if not batched else []):
         h, w = int(page.shape[0]), int(page.shape[1])
         lb = letterbox_device(page, imgsz, swap_rb=True)
         g = yolo.forward_letterboxed(lb)

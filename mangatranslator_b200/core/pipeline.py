@@ -789,12 +789,16 @@ class HotPathPipeline:
 
     def run_pages_device(self, pages_bgr: Sequence[torch.Tensor],
                          injected_boxes: Optional[Sequence[Optional[np.ndarray]]] = None,
-                         consume: Optional[Callable[[int, torch.Tensor], None]] = None):
+                         consume: Optional[Callable[[int, torch.Tensor], None]] = None,
+                         timings: Optional[dict] = None):
         """A group of device pages: detect+segment page by page, ONE cleaning launch for every bubble of the group (the
         cleaning kernel runs one CTA per bubble, so a single page's ~12 bubbles leave most SMs idle), then the upscale
         page by page.  `consume(i, out)` is called as each page's result becomes available (the upscaler's output is a
         static buffer that the next page overwrites).  Returns (outputs or None when consumed, detections, clean batch)."""
         n = len(pages_bgr)
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        t = [ev() for _ in range(4)] if timings is not None else None
+        if t: t[0].record()
         if injected_boxes is not None and any(b is None for b in injected_boxes):
             dets = []
             for i, page in enumerate(pages_bgr):
@@ -806,6 +810,7 @@ class HotPathPipeline:
             dets = detect_pages_device(list(pages_bgr), confidence=self.confidence, imgsz=self.imgsz, seg_model=self.seg_model,
                                        injected_boxes=None if injected_boxes is None else list(injected_boxes),
                                        own_masks=n > 1, **self.conjoined)
+        if t: t[1].record()
         scales = {_processing_scale(int(p.shape[1]), int(p.shape[0])) for p in pages_bgr}
         if len(scales) == 1:
             batch = clean_pages_device(list(pages_bgr), dets, thresholding_value=self.thr, roi_shrink_px=self.shrink,
@@ -817,6 +822,7 @@ class HotPathPipeline:
                 b1 = clean_pages_device([page], [d], thresholding_value=self.thr, roi_shrink_px=self.shrink,
                                         use_otsu_threshold=self.otsu, processing_scale=_processing_scale(int(page.shape[1]), int(page.shape[0])))
                 cleaned.append(b1.pages_out[0])
+        if t: t[2].record()
         outs = []
         for i in range(n):
             out = cleaned[i]
@@ -826,6 +832,11 @@ class HotPathPipeline:
                 consume(i, out)
             else:
                 outs.append(out.clone() if self.rcan is not None else out)
+        if t:                                        # per-page stage times of the group, as the batch path runs them
+            t[3].record()
+            torch.cuda.synchronize()
+            for name, a, b in (("detect_segment", 0, 1), ("clean_grouped", 1, 2), ("upscale", 2, 3)):
+                timings[name] = timings.get(name, 0.0) + t[a].elapsed_time(t[b]) / max(n, 1)
         return (None if consume is not None else outs), dets, batch
 
     def run_pages(self, pages_bgr_host: Sequence[torch.Tensor], outs_host: Optional[Sequence[torch.Tensor]] = None,

@@ -879,25 +879,37 @@ int launch_fewq_cluster(const AttnParams& P, cudaStream_t st) {
 
 // ---- patch embedding: (u8 - mean')/std' -> conv k x k / stride / pad (3 -> C) + bias + positional embedding -------
 // one thread per (output pixel, 8 output channels); weights in shared memory
+// G output channels per thread; a warp = 32 consecutive output pixels of ONE channel group, so the weights (stored
+// tap-major in shared memory: [3*k*k][C]) are read with 16-byte broadcast loads and every normalised input value
+// ((u8 - mean) / std: a division) feeds G FMAs instead of 8.  Per channel the taps are accumulated in the same order
+// (c, ky, kx) as before: results are bit-identical to the round-1 kernel (G = 8, lane = channel group).
+template <int G>
 __global__ void patch_embed_kernel(const uint8_t* __restrict__ img, int H, int W, const float* __restrict__ mean,
                                    const float* __restrict__ stdv, const float* __restrict__ w, const float* __restrict__ b,
                                    const float* __restrict__ pos, int C, int k, int stride, int pad, int Ho, int Wo,
                                    uint16_t* __restrict__ out, long long ps, int planes) {
-  extern __shared__ float sw[];  // [C][3*k*k]
+  extern __shared__ __align__(16) float sw[];  // [3*k*k][C]
   const int kk = 3 * k * k;
-  for (int i = threadIdx.x; i < C * kk; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < C * kk; i += blockDim.x) {
+    const int ch = i / kk, wi = i - ch * kk;
+    sw[wi * C + ch] = w[i];
+  }
   __syncthreads();
-  const int groups = C / 8;
-  const long long total = static_cast<long long>(Ho) * Wo * groups;
+  const int groups = C / G;
+  const long long npix = static_cast<long long>(Ho) * Wo;
+  const long long chunks = (npix + 31) / 32 * groups;        // warp-sized work items
   const float m0 = mean[0], m1 = mean[1], m2 = mean[2], s0 = stdv[0], s1 = stdv[1], s2 = stdv[2];
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % groups);
-    const long long pix = i / groups;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long wk = warp0; wk < chunks; wk += nwarps) {
+    const int g = static_cast<int>(wk % groups);
+    const long long pix = (wk / groups) * 32 + lane;
+    if (pix >= npix) continue;
     const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>(pix / Wo);
-    float acc[8];
+    float acc[G];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int j = 0; j < G; ++j) acc[j] = 0.f;
     for (int c = 0; c < 3; ++c) {
       const float mm = c == 0 ? m0 : (c == 1 ? m1 : m2), ss = c == 0 ? s0 : (c == 1 ? s1 : s2);
       for (int ky = 0; ky < k; ++ky) {
@@ -907,15 +919,21 @@ __global__ void patch_embed_kernel(const uint8_t* __restrict__ img, int H, int W
           const int ix = ox * stride + kx - pad;
           if (ix < 0 || ix >= W) continue;
           const float v = (static_cast<float>(img[(static_cast<long long>(iy) * W + ix) * 3 + c]) - mm) / ss;
-          const int wi = (c * k + ky) * k + kx;
+          const float4* wr = reinterpret_cast<const float4*>(sw + ((c * k + ky) * k + kx) * C + g * G);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += v * sw[(g * 8 + j) * kk + wi];
+          for (int j4 = 0; j4 < G / 4; ++j4) {
+            const float4 ww = wr[j4];
+            acc[4 * j4] += v * ww.x;
+            acc[4 * j4 + 1] += v * ww.y;
+            acc[4 * j4 + 2] += v * ww.z;
+            acc[4 * j4 + 3] += v * ww.w;
+          }
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = g * 8 + j;
+    for (int j = 0; j < G; ++j) {
+      const int ch = g * G + j;
       st_planes(out, pix * C + ch, ps, planes, acc[j] + b[ch] + pos[pix * C + ch]);
     }
   }
@@ -1189,11 +1207,22 @@ int mtb_sam_patch_embed(const uint8_t* img, int H, int W, const float* mean3, co
   MTB_REQUIRE(img && mean3 && std3 && w && b && pos && out && C % 8 == 0, "mtb_sam_patch_embed: bad arguments");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const size_t smem = sizeof(float) * static_cast<size_t>(C) * 3 * k * k;
-  MTB_CUDA_OK(cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const long long total = static_cast<long long>(Ho) * Wo * (C / 8);
-  patch_embed_kernel<<<grid_for4(total, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      img, H, W, mean3, std3, w, b, pos, C, k, stride, pad, Ho, Wo, static_cast<uint16_t*>(out),
-      static_cast<long long>(Ho) * Wo * C, planes);
+  const long long npix = static_cast<long long>(Ho) * Wo;
+  const cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  uint16_t* o = static_cast<uint16_t*>(out);
+  if (C % 32 == 0) {
+    MTB_CUDA_OK(cudaFuncSetAttribute(patch_embed_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    patch_embed_kernel<32><<<grid_for4(npix * (C / 32), 128), 128, smem, cs>>>(img, H, W, mean3, std3, w, b, pos, C, k, stride,
+                                                                              pad, Ho, Wo, o, npix * C, planes);
+  } else if (C % 16 == 0) {
+    MTB_CUDA_OK(cudaFuncSetAttribute(patch_embed_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    patch_embed_kernel<16><<<grid_for4(npix * (C / 16), 128), 128, smem, cs>>>(img, H, W, mean3, std3, w, b, pos, C, k, stride,
+                                                                              pad, Ho, Wo, o, npix * C, planes);
+  } else {
+    MTB_CUDA_OK(cudaFuncSetAttribute(patch_embed_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    patch_embed_kernel<8><<<grid_for4(npix * (C / 8), 128), 128, smem, cs>>>(img, H, W, mean3, std3, w, b, pos, C, k, stride,
+                                                                            pad, Ho, Wo, o, npix * C, planes);
+  }
   MTB_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -286,6 +286,59 @@ class YoloB200:
             body()
         return g
 
+    def forward_letterboxed_batch(self, lbs: List[torch.Tensor]):
+        """Several letterboxed inputs of ONE size through one plan with a batch dimension: the deep layers of a single
+        1600-pixel page fill only a fraction of the 148 SMs (stride 32: 50 x 34 pixels = 14 tiles of 128), a group of 8
+        pages fills them.  Same kernels, same per-output arithmetic: results are bit-identical to page-by-page runs."""
+        from . import graphs
+        n = len(lbs)
+        h, w, _ = lbs[0].shape
+        assert all(tuple(lb.shape) == (h, w, 3) for lb in lbs)
+        g = self._get(n, h, w)
+        if "lb_in" not in g:
+            g["lb_in"] = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device)
+
+        def body():
+            zero = (C.c_float * 3)(0.0, 0.0, 0.0)
+            # [n][h][w][3] is one image of n*h rows: the planes come out as [planes][n][h][w][8]
+            check(self.l.mtb_image_to_planes(ptr(g["lb_in"]), n * h, w, 3, 0, 1.0 / 255.0, zero, ptr(g["x_in"]), 8, self.planes,
+                                             stream_ptr()), "mtb_image_to_planes")
+            self._run_graph(g)
+
+        for i, lb in enumerate(lbs):
+            g["lb_in"][i].copy_(lb[:, :, :3])
+        if graphs.ENABLED:
+            if "cuda_graph" not in g:
+                g["cuda_graph"] = graphs.CapturedGraph(body)
+            g["cuda_graph"].replay()
+        else:
+            body()
+        return g
+
+    def detect_batch(self, g: dict, conf: float, orig_hw: Tuple[int, int], lb_hw: Tuple[int, int], *, iou: float = 0.7,
+                     apply_reference_dedup: bool = True):
+        """`detect` for a batched plan (all pages of one original size).  Returns (det [n][300][8], counts [n][2],
+        final_idx [n][300])."""
+        l, st = self.l, stream_ptr()
+        n = int(g["det"].shape[0])
+        lv = (YoloLevel * 3)()
+        for i, (box, cls, _, fh, fw, s) in enumerate(g["levels"]):
+            lv[i].box, lv[i].cls, lv[i].H, lv[i].W, lv[i].stride = box.data_ptr(), cls.data_ptr(), fh, fw, s
+        check(l.mtb_yolo_decode(lv, 3, n, self.nc, g["ncp"], float(conf), g["max_cand"], ptr(g["cand"]),
+                                ptr(g["cand_anchor"]), ptr(g["count"]), st), "mtb_yolo_decode")
+        h0, w0 = orig_hw
+        gain = min(lb_hw[0] / h0, lb_hw[1] / w0)
+        p = NmsParams()
+        p.N, p.max_cand, p.max_det = n, g["max_cand"], 300
+        p.iou_thr, p.max_wh, p.gain = float(iou), 7680.0, float(gain)
+        p.pad_x = int(round((lb_hw[1] - w0 * gain) / 2 - 0.1))
+        p.pad_y = int(round((lb_hw[0] - h0 * gain) / 2 - 0.1))
+        p.img_w, p.img_h = w0, h0
+        p.dedup_iou, p.contain_ioa, p.apply_dedup = 0.7, 0.9, int(apply_reference_dedup)
+        check(l.mtb_nms(C.byref(p), ptr(g["cand"]), ptr(g["cand_anchor"]), ptr(g["count"]), ptr(g["order"]),
+                        ptr(g["dead"]), ptr(g["det"]), ptr(g["det_count"]), ptr(g["final_idx"]), st), "mtb_nms")
+        return g["det"], g["det_count"], g["final_idx"]
+
     def detect(self, g: dict, conf: float, orig_hw: Tuple[int, int], lb_hw: Tuple[int, int], *, iou: float = 0.7,
                apply_reference_dedup: bool = True):
         """Decode + NMS + scale_boxes (+ the reference's dedup/containment).  Returns device tensors

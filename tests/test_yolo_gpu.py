@@ -186,3 +186,32 @@ def test_call_shape_and_retina_masks_match_oracle():
     assert got.shape == exp.shape
     assert (got != exp).mean() < 1e-3          # knife-edge pixels of the `> 0` decision only
     assert exp.any()
+
+
+def test_batched_plan_equals_page_by_page():
+    """Pages of one size through ONE plan with a batch dimension (`forward_letterboxed_batch` / `detect_batch`, what
+    `detect_pages_device` does for a group): head tensors, detection tables, counts and the reference-dedup index lists
+    are bit-identical to running the pages one by one."""
+    from mangatranslator_b200.preproc import letterbox_device
+    from mangatranslator_b200.yolo import YoloB200
+    cfg, hw, imgsz = NANO, (200, 320), 320
+    m = Y.make_model(4, bias_objects=-3.0, **cfg)
+    dev = torch.device("cuda:0")
+    net = YoloB200(m.state_dict(), m.cfg, dev)
+    imgs = [_image(20 + i, *hw) for i in range(3)]
+    lbs = [letterbox_device(torch.from_numpy(im).to(dev), imgsz, swap_rb=True) for im in imgs]
+    single = []
+    for lb in lbs:
+        g = net.forward_letterboxed(lb)
+        det, cnt, fin = net.detect(g, 0.3, hw, tuple(lb.shape[:2]), apply_reference_dedup=True)
+        single.append((det.clone(), cnt.clone(), fin.clone(), [lv[0].clone() for lv in g["levels"]]))
+    gb = net.forward_letterboxed_batch(lbs)
+    det, cnt, fin = net.detect_batch(gb, 0.3, hw, tuple(lbs[0].shape[:2]), apply_reference_dedup=True)
+    torch.cuda.synchronize()
+    assert int(cnt[:, 0].min()) > 0
+    for i, (d1, c1, f1, heads) in enumerate(single):
+        for lv, h1 in zip(gb["levels"], heads):
+            assert torch.equal(lv[0][i], h1[0])
+        n, nf = int(c1[0]), int(c1[1])
+        assert torch.equal(cnt[i], c1)
+        assert torch.equal(det[i, :n], d1[:n]) and torch.equal(fin[i, :nf], f1[:nf])
