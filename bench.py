@@ -461,16 +461,11 @@ def run_ours(args, coord):
     coord.barrier()
     ms_e2e = coord.all_reduce_max(e0.elapsed_time(e1))
     e2e_v = coord.world * args.batch * args.steps / (ms_e2e / 1e3)
-    # per-page stage times as the timed loop runs them: a GROUP of G pages (one batched detector plan, one cleaning launch),
-    # plus a single page on its own for the un-grouped numbers; both warm (the single-page plans are built by the first call)
+    # per-page stage times: ONE page on its own, warm (the timed loop runs groups of G pages, whose detector is one batched
+    # plan and whose cleaning is one launch — `clean_grouped` below; the single-page plans are built by the first call here)
     pipe.run_page_device(devp[0], injected_boxes=boxes[0])
-    single = {}
-    pipe.run_page_device(devp[0], injected_boxes=boxes[0], timings=single)
     stage = {}
-    pipe.run_pages_device([devp[i] for i in range(G)], injected_boxes=[boxes[i] for i in range(G)],
-                          consume=lambda i, out: None, timings=stage)
-    stage["clean"] = single["clean"]
-    stage["detect_segment_single_page"] = single["detect_segment"]
+    pipe.run_page_device(devp[0], injected_boxes=boxes[0], timings=stage)
     # cleaning as the bench runs it: the bubbles of G pages in one launch
     from mangatranslator_b200.core.image.cleaning import clean_pages_device
     from mangatranslator_b200.core.image.detection import detect_pages_device
