@@ -274,6 +274,7 @@ int mtb_nms(const mtb_nms_params* p /* host */, const float* cand, const int* ca
 typedef struct mtb_split_pair {
   int i, j, mode, reserved;
   double cx, cy, ax, ay;
+  double off; /* v = (x - cx) * ax + (y - cy) * ay - off: the text-safe offset of the cut (detection.py:700-761), 0 otherwise */
 } mtb_split_pair;
 long long mtb_split_conjoined_workspace_bytes(int win_h, int win_w, int K);
 int mtb_split_conjoined(const uint8_t* parent, int H, int W, int K, const int* rects, const double* centers,

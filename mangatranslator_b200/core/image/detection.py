@@ -17,7 +17,8 @@ reference does at :1541-1548 and the primaries are kept).
 Secondary ultralytics detectors, executed from their checkpoints' module trees (mangatranslator_b200/yolo_tree.py):
 `detect_panels` (:1817-1921, YOLO11-L at imgsz 640, class "frame") and OSB-text verification
 `_expand_boxes_with_osb_text` (:120-201, YOLO12x at imgsz 640: a bubble box grows to hold the text box that belongs to
-it).  Not restated: the text-aware variant of the conjoined split (text boxes nudging the cut line, :975-1020) and SAM3.
+it; the same text boxes steer the cut of a conjoined split away from the text, :700-783, mangatranslator_b200/conjoined.py).
+Not restated: SAM3.
 """
 from __future__ import annotations
 
@@ -273,19 +274,37 @@ def _round_bbox(box) -> Tuple[int, int, int, int]:
     return (int(round(x0)), int(round(y0)), int(round(x1)), int(round(y1)))
 
 
-def _split_group_on_device(parent_mask: np.ndarray, group_boxes, device) -> List[np.ndarray]:
-    """`_split_conjoined_mask` of the parent (with the child rectangles ORed in, :1161-1164) through the CUDA kernel."""
+def _split_group_on_device(parent_mask: np.ndarray, group_boxes, device, text_boxes=None) -> List[np.ndarray]:
+    """`_split_conjoined_mask` of the parent (with the child rectangles ORed in, :1161-1164) through the CUDA kernel;
+    `text_boxes` = the group's OSB text boxes (`_get_group_osb_text_boxes`), which move the cut off the text."""
     from mangatranslator_b200.conjoined import split_conjoined_device
     dev = get_model_manager()._require_cuda()
-    out, _ = split_conjoined_device(torch.from_numpy(np.ascontiguousarray(parent_mask)).to(dev), group_boxes)
+    kw = {} if text_boxes is None else {"text_boxes": text_boxes}
+    out, _ = split_conjoined_device(torch.from_numpy(np.ascontiguousarray(parent_mask)).to(dev), group_boxes, **kw)
     return [m for m in out.cpu().numpy()]
+
+
+def _get_cached_osb_text_boxes(cache, model_manager, image_pil, confidence):
+    """:298-314 — the OSB text boxes `_expand_boxes_with_osb_text` left in the detection cache, as an array, or None."""
+    try:
+        from mangatranslator_b200.core.ml.model_manager import ModelType
+        key = cache.get_yolo_cache_key(image_pil, str(model_manager.model_paths[ModelType.YOLO_OSBTEXT]), confidence)
+        hit = cache.get_yolo_detection(key)
+        if hit is not None:
+            _, osb_boxes, _ = hit
+            if osb_boxes is not None and len(osb_boxes) > 0:
+                return osb_boxes.detach().cpu().numpy() if hasattr(osb_boxes, "detach") else np.asarray(osb_boxes)
+    except Exception:
+        pass
+    return None
 
 
 def _build_segmentation_detections(primary_boxes, grouping_boxes, sources, primary_results, primary_model, secondary_boxes,
                                    secondary_sources, secondary_results, simple_indices, conjoined_indices, img_h, img_w,
-                                   conjoined_confidence, sam_masks=None, synthetic_groups=None, device=None) -> List[dict]:
+                                   conjoined_confidence, sam_masks=None, synthetic_groups=None, device=None,
+                                   osb_text_boxes_np=None) -> List[dict]:
     """(:1075-1260) simple boxes first, then the children of every conjoined parent, then the synthetic groups."""
-    from mangatranslator_b200.conjoined import union_box
+    from mangatranslator_b200.conjoined import group_osb_text_boxes, union_box
     dets: List[dict] = []
 
     def meta(src):
@@ -305,8 +324,12 @@ def _build_segmentation_detections(primary_boxes, grouping_boxes, sources, prima
             mask = _build_rect_mask_from_box(primary_boxes[idx], img_h, img_w)
         dets.append({"bbox": _round_bbox(primary_boxes[idx]), "confidence": conf, "class": cls, "sam_mask": mask})
 
-    def emit_group(parent_mask, group_boxes, group_sources):
-        masks = _split_group_on_device(parent_mask, group_boxes, device)
+    def emit_group(parent_mask, group_boxes, group_sources, parent_box):
+        group_osb = group_osb_text_boxes(osb_text_boxes_np, parent_box)          # :1164, :1218
+        if group_osb is None:
+            masks = _split_group_on_device(parent_mask, group_boxes, device)
+        else:
+            masks = _split_group_on_device(parent_mask, group_boxes, device, group_osb)
         bboxes = [_round_bbox(b) for b in group_boxes]
         for k, src in enumerate(group_sources):
             conf, cls = meta(src)
@@ -319,13 +342,13 @@ def _build_segmentation_detections(primary_boxes, grouping_boxes, sources, prima
         parent_mask = own_or_yolo_mask(p_idx)
         if parent_mask is None:
             parent_mask = _build_rect_mask_from_box(parent_box, img_h, img_w)
-        emit_group(parent_mask, [secondary_boxes[s] for s in s_indices], [secondary_sources[s] for s in s_indices])
+        emit_group(parent_mask, [secondary_boxes[s] for s in s_indices], [secondary_sources[s] for s in s_indices], parent_box)
     for sg in synthetic_groups or []:
         parent_mask = sg.get("parent_mask")
         if parent_mask is None:
             parent_mask = _build_rect_mask_from_box(sg["parent_box"], img_h, img_w)
         members = sg["member_indices"]
-        emit_group(parent_mask, [grouping_boxes[m] for m in members], [sources[m] for m in members])
+        emit_group(parent_mask, [grouping_boxes[m] for m in members], [sources[m] for m in members], sg["parent_box"])
     return dets
 
 
@@ -396,9 +419,11 @@ def detect_speech_bubbles(image_path: Path, model_path, confidence=0.6, verbose=
         return detections, text_free_boxes
     primary_boxes = primary_boxes.detach().float().cpu()
     grouping_boxes = primary_boxes.clone()
-    if osb_text_verification and len(primary_boxes) > 0:       # :1555-1567 (grouping keeps the un-expanded boxes)
+    osb_text_boxes_np = None
+    if osb_text_verification and len(primary_boxes) > 0:       # :1555-1571 (grouping keeps the un-expanded boxes)
         primary_boxes = _expand_boxes_with_osb_text(image_cv, image_pil, primary_boxes, cache, mm, _device, confidence,
                                                     osb_text_hf_token, verbose)
+        osb_text_boxes_np = _get_cached_osb_text_boxes(cache, mm, image_pil, confidence)   # they also steer the split cuts
 
     conjoined_indices: list = []
     simple = list(range(len(primary_boxes)))
@@ -424,7 +449,8 @@ def detect_speech_bubbles(image_path: Path, model_path, confidence=0.6, verbose=
         return _build_segmentation_detections(primary_boxes, grouping_boxes, sources, primary_results, primary_model,
                                               secondary_boxes, secondary_sources, secondary_results, simple,
                                               conjoined_indices, img_h, img_w, conjoined_confidence, sam_masks=sam_masks,
-                                              synthetic_groups=synthetic_groups, device=_device)
+                                              synthetic_groups=synthetic_groups, device=_device,
+                                              osb_text_boxes_np=osb_text_boxes_np)
 
     if seg_model not in ("sam2", "sam3"):
         return assemble(None), text_free_boxes

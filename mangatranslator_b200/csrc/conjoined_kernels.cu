@@ -125,8 +125,11 @@ __global__ void split_resolve_kernel(const uint8_t* __restrict__ parent, const S
         if ((inr & bi) && (inr & bj)) {                 // pixel of the overlap zone parent ∧ rect_i ∧ rect_j
           owned &= ~(bi | bj);
           if (pr.mode != 0) {
-            const double v = __dadd_rn(__dmul_rn(__dsub_rn(static_cast<double>(x), pr.cx), pr.ax),
-                                       __dmul_rn(__dsub_rn(static_cast<double>(y), pr.cy), pr.ay));
+            // signed distance to the dividing line minus the text-safe offset of the pair (0 without OSB text boxes),
+            // operation for operation like the reference's `pixel_dist - split_offset` (detection.py:684-687, :761)
+            const double v = __dsub_rn(__dadd_rn(__dmul_rn(__dsub_rn(static_cast<double>(x), pr.cx), pr.ax),
+                                                 __dmul_rn(__dsub_rn(static_cast<double>(y), pr.cy), pr.ay)),
+                                       pr.off);
             const bool to_i = pr.mode == 1 ? (v <= 0.0) : (v >= 0.0);
             const bool to_j = pr.mode == 1 ? (v > 0.0) : (v < 0.0);
             if (to_i) owned |= bi;

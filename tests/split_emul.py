@@ -43,12 +43,12 @@ def apply_plan(parent_u8, plan, include_child_rects=True):
             d = np.where(base, d, np.inf)
             n = int(np.argmin(d))                        # first minimum in row-major order
             owned[kk].flat[n] = True
-    for (i, j, mode, cx, cy, ax, ay) in plan.pairs:
+    for (i, j, mode, cx, cy, ax, ay, off) in plan.pairs:
         zone = base & rects[i] & rects[j]
         owned[i] &= ~zone
         owned[j] &= ~zone
         if mode:
-            v = (xx - cx) * ax + (yy - cy) * ay
+            v = ((xx - cx) * ax + (yy - cy) * ay) - off
             owned[i] |= zone & ((v <= 0) if mode == 1 else (v >= 0))
             owned[j] |= zone & ((v > 0) if mode == 1 else (v < 0))
     taken = np.zeros_like(base)

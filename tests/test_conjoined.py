@@ -135,6 +135,123 @@ def test_oracle_matches_live_reference_on_random_groups():
     assert flipped <= 0.002 * total_rest, (flipped, total_rest)
 
 
+def _text_case(rng, t):
+    """Two to four overlapping child boxes of a bubble-like parent and OSB text boxes: usually one inside each child away
+    from the overlap (a text-safe cut exists), sometimes spanning it, sometimes ambiguous or nested — every branch of
+    the text-aware split."""
+    h, w = int(rng.integers(120, 360)), int(rng.integers(160, 420))
+    k = int(rng.integers(2, 5))
+    horizontal = rng.random() < 0.5
+    boxes = []
+    for i in range(k):
+        if horizontal:
+            x0 = 10 + i * (w - 40) / k * rng.uniform(0.8, 1.0)
+            boxes.append([x0, rng.uniform(5, 30), x0 + (w - 40) / k * rng.uniform(1.15, 1.6), h - rng.uniform(5, 30)])
+        else:
+            y0 = 10 + i * (h - 40) / k * rng.uniform(0.8, 1.0)
+            boxes.append([rng.uniform(5, 30), y0, w - rng.uniform(5, 30), y0 + (h - 40) / k * rng.uniform(1.15, 1.6)])
+    if t % 5 == 4:                                                  # a diagonal pair
+        boxes = [[10.0, 10.0, w * 0.6, h * 0.6], [w * 0.4, h * 0.4, w - 10.0, h - 10.0]]
+    texts = []
+    for b in boxes:
+        bw, bh = b[2] - b[0], b[3] - b[1]
+        r = rng.random()
+        if r < 0.7:                                                 # inside, small, near the middle of the child
+            cx, cy = b[0] + bw * rng.uniform(0.35, 0.65), b[1] + bh * rng.uniform(0.35, 0.65)
+            tw, th = bw * rng.uniform(0.1, 0.35), bh * rng.uniform(0.1, 0.35)
+            texts.append([cx - tw / 2, cy - th / 2, cx + tw / 2, cy + th / 2])
+        elif r < 0.85:                                              # wide: reaches into the neighbour
+            texts.append([b[0] - bw * 0.2, b[1] + bh * 0.3, b[2] + bw * 0.2, b[1] + bh * 0.6])
+    if texts and t % 4 == 1:                                        # a big box that nearly contains a small one
+        s0 = texts[0]
+        texts.append([s0[0] - 3, s0[1] - 3, s0[2] + 30, s0[3] + 20])
+    if t % 6 == 2:
+        texts.append([float(w + 50), float(h + 50), float(w + 90), float(h + 80)])      # outside everything
+    yy, xx = np.mgrid[0:h, 0:w]
+    parent = np.zeros((h, w), bool)
+    for b in boxes:                                                 # an ellipse per child: a conjoined bubble outline
+        parent |= ((xx - (b[0] + b[2]) / 2) / ((b[2] - b[0]) / 2 + 1e-6)) ** 2 + ((yy - (b[1] + b[3]) / 2) / ((b[3] - b[1]) / 2 + 1e-6)) ** 2 <= 1.0
+    return h, w, torch.tensor(boxes, dtype=torch.float32), np.asarray(texts, np.float32).reshape(-1, 4), parent
+
+
+@needs_ref
+def test_text_aware_split_oracle_matches_live_reference():
+    """OSB text boxes that belong to both children move the cut so that no text box is cut (:700-783, :893-905): the
+    oracle's restatement equals the unmodified `_split_conjoined_mask`, `_match_text_boxes_to_bubbles` and
+    `_get_group_osb_text_boxes` on seeded groups; the text boxes change the result in a good share of them."""
+    import cv2
+    _refimport.import_reference()
+    import core.image.detection as ref
+    rng = np.random.default_rng(17)
+    moved = 0
+    for t in range(60):
+        h, w, boxes, texts, parent = _text_case(rng, t)
+        blist = [b for b in boxes]
+        union = torch.cat([boxes[:, :2].min(0).values, boxes[:, 2:].max(0).values])
+        want_group = ref._get_group_osb_text_boxes(texts if len(texts) else None, union)
+        got_group = O.group_text_boxes(texts if len(texts) else None, union)
+        assert (want_group is None) == (got_group is None)
+        if want_group is not None:
+            assert np.array_equal(np.asarray(want_group), np.asarray(got_group))
+            wm = ref._match_text_boxes_to_bubbles(want_group, blist)
+            gm = O.match_text_boxes(got_group, [b.tolist() for b in blist])
+            assert {i: [tuple(x) for x in v] for i, v in wm.items()} == {i: [tuple(x) for x in v] for i, v in gm.items()}
+        full = parent.copy()
+        for b in boxes.tolist():
+            full |= O.rect_mask(b, h, w)
+        cv2.ipp.setUseIPP(False)
+        try:
+            exp = ref._split_conjoined_mask(full, blist, osb_text_boxes=want_group)
+            plain = ref._split_conjoined_mask(full, blist)
+        finally:
+            cv2.ipp.setUseIPP(True)
+        got = O.split_conjoined_mask(full, blist, osb_text_boxes=got_group)
+        assert len(got) == len(exp)
+        for a, b in zip(got, exp):
+            assert np.array_equal(a, b), t
+        moved += int(any(not np.array_equal(a, b) for a, b in zip(exp, plain)))
+    assert moved >= 15, moved
+
+
+def _plan_with_text(parent, boxes, texts, h, w):
+    from mangatranslator_b200 import conjoined as Cj
+    full = parent.copy()
+    for b in boxes.tolist():
+        full |= O.rect_mask(b, h, w)
+
+    def zone_pixels(i, j, rect):
+        x0, y0, x1, y1 = rect
+        ys, xs = np.nonzero(full[y0:y1, x0:x1])
+        return xs + x0, ys + y0
+
+    return Cj.plan_split(boxes, h, w, text_boxes=texts, zone_pixels=zone_pixels)
+
+
+def test_text_aware_split_plan_walked_in_numpy_matches_oracle():
+    """The product's host decisions for the text-aware split (which candidate line, which offset: conjoined.plan_split)
+    walked through the NumPy statement of the kernel give the oracle's masks bit for bit; the offsets are non-zero in a
+    good share of the cases; and the text-box helpers equal the oracle's."""
+    from mangatranslator_b200 import conjoined as Cj
+    rng = np.random.default_rng(17)
+    with_offset = 0
+    for t in range(60):
+        h, w, boxes, texts, parent = _text_case(rng, t)
+        union = torch.cat([boxes[:, :2].min(0).values, boxes[:, 2:].max(0).values])
+        group = Cj.group_osb_text_boxes(texts if len(texts) else None, union)
+        want_group = O.group_text_boxes(texts if len(texts) else None, union)
+        assert (group is None) == (want_group is None)
+        if group is not None:
+            assert np.array_equal(np.asarray(group), np.asarray(want_group))
+        plan = _plan_with_text(parent, boxes, group, h, w)
+        with_offset += int(any(p[7] != 0.0 for p in plan.pairs))
+        got = apply_plan(parent.astype(np.uint8) * 255, plan, include_child_rects=True)
+        exp, _ = O.split_group(parent.astype(np.uint8) * 255, [b for b in boxes], osb_text_boxes=want_group)
+        assert len(got) == len(exp)
+        for a, b in zip(got, exp):
+            assert np.array_equal(a, b), t
+    assert with_offset >= 15, with_offset
+
+
 # ---- the kernel's algorithm (plan + closed-form chamfer) walked in NumPy ----------------------------------------
 @pytest.mark.parametrize("case", CASES[:6], ids=[c[0] for c in CASES[:6]])
 def test_split_plan_walked_in_numpy_matches_golden(case):
@@ -292,6 +409,15 @@ FLOW_CASES = {
                               [625, 95, 815, 295]],
                        confs=[0.8, 0.7, 0.6, 0.9, 0.5], classes=[0, 0, 0, 2, 0],
                        names={0: "bubble", 1: "text_bubble", 2: "text_free"})),
+    # OSB text verification on (the reference's default): text boxes inside both lobes of the overlapping pairs move the
+    # cut into the gap between the texts; one text box sticks out of a lone bubble (its box grows); one is ambiguous
+    # between two lobes; one nearly contains another
+    "synthetic_groups_with_osb_text": dict(
+        primary=[[60, 80, 300, 330], [250, 120, 520, 360], [620, 90, 820, 300], [640, 260, 850, 470], [100, 600, 330, 820],
+                 [290, 640, 520, 850], [480, 610, 700, 840], [760, 700, 900, 860], [50, 950, 250, 1150]],
+        secondary=None,
+        osb=[[90, 150, 262, 260], [310, 180, 480, 300], [640, 120, 800, 235], [660, 330, 830, 440], [120, 650, 250, 780],
+             [340, 690, 470, 800], [545, 650, 680, 800], [850, 740, 930, 800], [255, 200, 300, 240], [86, 146, 290, 290]]),
 }
 
 
@@ -311,16 +437,19 @@ def _run_reference_flow(case, seg_model):
         mm.models[ModelType.RTDETR_CONJOINED_BUBBLE] = _FakeDetector(sec["boxes"], sec["confs"], sec["classes"], sec["names"], 640)
     else:
         mm.models.pop(ModelType.RTDETR_CONJOINED_BUBBLE, None)
+    osb = case.get("osb")
+    if osb is not None:
+        mm.models[ModelType.YOLO_OSBTEXT] = _FakeDetector(osb, [0.9] * len(osb), [0] * len(osb), {0: "text"}, 640)
     get_cache().clear_all()
     from PIL import Image
     pil = Image.fromarray(np.full((1536, 1024, 3), 200, np.uint8))
     cv2.ipp.setUseIPP(False)
     try:
         return ref.detect_speech_bubbles(__import__("pathlib").Path("x.png"), "x.pt", 0.6, seg_model=seg_model, conjoined_detection=sec is not None,
-                                         image_override=pil, device=torch.device("cpu"))
+                                         image_override=pil, device=torch.device("cpu"), osb_text_verification=osb is not None)
     finally:
         cv2.ipp.setUseIPP(True)
-        for k in (ModelType.YOLO_SPEECH_BUBBLE, ModelType.SAM2, ModelType.RTDETR_CONJOINED_BUBBLE):
+        for k in (ModelType.YOLO_SPEECH_BUBBLE, ModelType.SAM2, ModelType.RTDETR_CONJOINED_BUBBLE, ModelType.YOLO_OSBTEXT):
             mm.models.pop(k, None)
 
 
@@ -340,18 +469,30 @@ def _run_our_flow(case, seg_model, monkeypatch=None):
         mm.models[ModelType.RTDETR_CONJOINED_BUBBLE] = _FakeDetector(sec["boxes"], sec["confs"], sec["classes"], sec["names"], 640)
     else:
         mm.models.pop(ModelType.RTDETR_CONJOINED_BUBBLE, None)
+    osb = case.get("osb")
+    if osb is not None:
+        mm.models[ModelType.YOLO_OSBTEXT] = _FakeDetector(osb, [0.9] * len(osb), [0] * len(osb), {0: "text"}, 640)
     get_cache().clear()
     if monkeypatch is not None:          # CPU run: the kernel's algorithm walked in NumPy stands in for the kernel
         from mangatranslator_b200 import conjoined as Cj
 
-        def emul(parent_mask, group_boxes, device):
+        def emul(parent_mask, group_boxes, device, text_boxes=None):
             h, w = parent_mask.shape
-            return apply_plan(parent_mask, Cj.plan_split(group_boxes, h, w), include_child_rects=True)
+            full = np.asarray(parent_mask) > 0
+            for b in group_boxes:
+                x0, y0, x1, y1 = Cj.box_rect(b, h, w)
+                full[y0:y1, x0:x1] = True
+
+            def zone_pixels(i, j, rect):
+                ys, xs = np.nonzero(full[rect[1]:rect[3], rect[0]:rect[2]])
+                return xs + rect[0], ys + rect[1]
+            plan = Cj.plan_split(group_boxes, h, w, text_boxes=text_boxes, zone_pixels=zone_pixels)
+            return apply_plan(parent_mask, plan, include_child_rects=True)
         monkeypatch.setattr(D, "_split_group_on_device", emul)
     try:
         pil = Image.fromarray(np.full((1536, 1024, 3), 200, np.uint8))
         return D.detect_speech_bubbles(__import__("pathlib").Path("x.png"), "x.pt", 0.6, seg_model=seg_model, conjoined_detection=sec is not None,
-                                       image_override=pil, device=torch.device("cpu"))
+                                       image_override=pil, device=torch.device("cpu"), osb_text_verification=osb is not None)
     finally:
         mm.models.clear()
         mm.models.update(saved)
