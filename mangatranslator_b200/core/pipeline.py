@@ -232,7 +232,7 @@ def _fast_path_pipeline(config: MangaTranslatorConfig, pil: Image.Image) -> Opti
     kernels and the finished page comes back once (MTB200_FAST_PATH=0 forces the stage functions).  The results are the
     stage functions' results (tests/test_pipeline_gpu.py::test_batch_fast_path_equals_stage_functions).  Not eligible:
     translucent pages (the stage functions clean the RGBA page itself), the proto-mask segmenter, coloured-bubble
-    inpainting, outside-text processing."""
+    inpainting, outside-text processing, OSB-text verification when its detector is available."""
     if os.environ.get("MTB200_FAST_PATH", "1") == "0" or not config.cleaning_only:
         return None
     if (config.detection.seg_model != "sam2" or config.cleaning.inpaint_colored_bubbles
@@ -243,6 +243,15 @@ def _fast_path_pipeline(config: MangaTranslatorConfig, pil: Image.Image) -> Opti
         return None
     if pil.mode == "RGBA" and pil.getextrema()[3][0] < 255:
         return None
+    if getattr(config.detection, "use_osb_text_verification", False):
+        # OSB-text verification (box expansion, text-safe conjoined cuts) lives in the stage function.  Without its model
+        # the reference skips it (detection.py:198-201), and so does the device path; with a model available the page goes
+        # through `detect_speech_bubbles`
+        from mangatranslator_b200.core.ml.model_manager import ModelType
+        mm0 = get_model_manager()
+        if (mm0.is_loaded(ModelType.YOLO_OSBTEXT) or mm0.model_paths[ModelType.YOLO_OSBTEXT].is_file()
+                or os.environ.get("MTB200_SYNTHETIC_OSBTEXT", "0") == "1"):
+            return None
     key = (float(config.detection.confidence), int(config.cleaning.thresholding_value), float(config.cleaning.roi_shrink_px),
            bool(config.cleaning.use_otsu_threshold), bool(config.detection.conjoined_detection),
            float(config.detection.conjoined_confidence), bool(config.output.upscale_final_image),
