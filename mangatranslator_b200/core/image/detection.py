@@ -577,7 +577,8 @@ def detect_pages_device(pages_bgr: List[torch.Tensor], *, confidence: float = 0.
     counts = torch.zeros((npages,), dtype=torch.int32, device=pages_bgr[0].device) if npages else None
     enc0 = None
     import os as _os
-    batched = (npages > 1 and _os.environ.get("MTB200_YOLO_BATCH", "1") != "0" and hasattr(yolo, "forward_letterboxed_batch")
+    # (the hard-wired YOLOv8-seg plan only: the module-tree executor has been verified page by page)
+    batched = (npages > 1 and _os.environ.get("MTB200_YOLO_BATCH", "1") != "0" and type(yolo).__name__ == "YoloB200"
                and len({tuple(p.shape) for p in pages_bgr}) == 1)
     if batched:
         # pages of one size share ONE detector plan with a batch dimension (the deep layers of a single page leave most
