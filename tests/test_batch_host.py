@@ -318,3 +318,51 @@ def test_upscaling_only_calls_the_upscaler_like_the_live_reference(tmp_path, mon
     theirs = RP.translate_and_render(src, cfg_for(RC), None)
     assert ours_log == ref_log, (ours_log, ref_log)
     assert ours.size == theirs.size
+
+
+def test_fast_path_yields_to_the_stage_function_when_osb_text_verification_can_run(monkeypatch, tmp_path):
+    """`use_osb_text_verification` (default on, core/config.py:21) lives in `detect_speech_bubbles` (box expansion,
+    text-safe conjoined cuts: detection.py:1555-1571).  The device-resident fast path keeps the page only while that step
+    would be skipped anyway (no OSB-text detector available, like the reference after a failed load, :198-201)."""
+    import torch
+    from PIL import Image
+    from mangatranslator_b200.core import pipeline as P
+    from mangatranslator_b200.core.config import MangaTranslatorConfig
+    from mangatranslator_b200.core.ml.model_manager import ModelType, get_model_manager
+    cfg = MangaTranslatorConfig()
+    cfg.cleaning_only = True
+    cfg.detection.seg_model = "sam2"
+    pil = Image.new("RGB", (64, 96), (200, 200, 200))
+    sentinel = object()
+    key_seen = []
+
+    class _Fake(dict):                          # stands in for the cache of built engines: any key "is there"
+        def __contains__(self, k):
+            key_seen.append(k)
+            return True
+
+        def __getitem__(self, k):
+            return sentinel
+    mm = get_model_manager()                    # built before CUDA is "made available" (it asks for the best device)
+    monkeypatch.setattr(P, "_FAST", _Fake())
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.delenv("MTB200_SYNTHETIC_OSBTEXT", raising=False)
+    monkeypatch.delenv("MTB200_FAST_PATH", raising=False)
+    mm.models.pop(ModelType.YOLO_OSBTEXT, None)
+    monkeypatch.setitem(mm.model_paths, ModelType.YOLO_OSBTEXT, tmp_path / "absent.pt")
+    assert cfg.detection.use_osb_text_verification is True
+    assert P._fast_path_pipeline(cfg, pil) is sentinel                      # no detector anywhere: the step is a no-op
+    monkeypatch.setenv("MTB200_SYNTHETIC_OSBTEXT", "1")
+    assert P._fast_path_pipeline(cfg, pil) is None                          # it could load: stage functions
+    monkeypatch.delenv("MTB200_SYNTHETIC_OSBTEXT")
+    (tmp_path / "present.pt").write_bytes(b"x")
+    monkeypatch.setitem(mm.model_paths, ModelType.YOLO_OSBTEXT, tmp_path / "present.pt")
+    assert P._fast_path_pipeline(cfg, pil) is None                          # a checkpoint is there
+    monkeypatch.setitem(mm.model_paths, ModelType.YOLO_OSBTEXT, tmp_path / "absent.pt")
+    mm.models[ModelType.YOLO_OSBTEXT] = object()
+    try:
+        assert P._fast_path_pipeline(cfg, pil) is None                      # an injected detector
+    finally:
+        mm.models.pop(ModelType.YOLO_OSBTEXT, None)
+    cfg.detection.use_osb_text_verification = False
+    assert P._fast_path_pipeline(cfg, pil) is sentinel
