@@ -87,6 +87,11 @@ FAKE = textwrap.dedent('''
             self.ffn = nn.Sequential(*[conv(c) for c in n["ffn"]])
             self.add = n["add"]
 
+    class C2f(C3k2):                 # the YOLOv8 name of the same block
+        pass
+
+    V8_NAMES = False
+
     class C2PSA(nn.Module):
         def __init__(self, n):
             super().__init__()
@@ -130,8 +135,9 @@ FAKE = textwrap.dedent('''
             self.nc, self.reg_max, self.nl = n["nc"], n["reg_max"], len(n["cv2"])
             self.stride = torch.tensor([float(v) for v in n["stride"]])
             self.cv2 = nn.ModuleList(nn.Sequential(conv(b[0]), conv(b[1]), plain(b[2])) for b in n["cv2"])
-            self.cv3 = nn.ModuleList(nn.Sequential(nn.Sequential(conv(b[0]), conv(b[1])), nn.Sequential(conv(b[2]), conv(b[3])),
-                                                   plain(b[4])) for b in n["cv3"])
+            self.cv3 = nn.ModuleList((nn.Sequential(conv(b[0]), conv(b[1]), plain(b[2])) if len(b) == 3 else       # YOLOv8 (legacy)
+                                      nn.Sequential(nn.Sequential(conv(b[0]), conv(b[1])), nn.Sequential(conv(b[2]), conv(b[3])),
+                                                    plain(b[4]))) for b in n["cv3"])
             self.dfl = DFL()
 
     class Proto(nn.Module):
@@ -154,7 +160,7 @@ FAKE = textwrap.dedent('''
         pass
 
     def make(n):
-        return {"Conv": conv, "Bottleneck": Bottleneck, "C3": C3k, "C2f": C3k2, "SPPF": SPPF, "C2PSA": C2PSA, "A2C2f": A2C2f,
+        return {"Conv": conv, "Bottleneck": Bottleneck, "C3": C3k, "C2f": C2f if V8_NAMES else C3k2, "SPPF": SPPF, "C2PSA": C2PSA, "A2C2f": A2C2f,
                 "Concat": Concat, "Detect": Detect, "Segment": Segment,
                 "Upsample": lambda n: nn.Upsample(None, 2, "nearest")}[n["t"]](n)
 
@@ -191,7 +197,7 @@ def _same(a, b, path=""):
         assert a == b, (path, a, b)
 
 
-def _save_with_fake_package(tmp_path, tree, head=None, as_state_dict=False):
+def _save_with_fake_package(tmp_path, tree, head=None, as_state_dict=False, v8_names=False):
     pkg = tmp_path / "fakepkg" / "ultralytics" / "nn"
     pkg.mkdir(parents=True, exist_ok=True)
     (tmp_path / "fakepkg" / "ultralytics" / "__init__.py").write_text("")
@@ -202,6 +208,7 @@ def _save_with_fake_package(tmp_path, tree, head=None, as_state_dict=False):
     path = tmp_path / "model.pt"
     try:
         import ultralytics.nn.tasks as tasks
+        tasks.V8_NAMES = v8_names
         model = tasks.DetectionModel(tree, getattr(tasks, head) if head else None)
         torch.save({"model": model.state_dict() if as_state_dict else model, "epoch": 1}, str(path))
     finally:
@@ -392,3 +399,33 @@ def test_osb_text_expansion_and_panels_match_the_live_reference():
             mm.models.pop(t, None)
         for t in (RefType.YOLO_OSBTEXT, RefType.YOLO_PANEL):
             rmm.models.pop(t, None)
+
+
+def test_yolov8_named_detection_checkpoint_reads_into_the_same_tree(tmp_path):
+    """A YOLOv8 detection model (class names `C2f`, the legacy class branch of plain 3x3 convs) is the same tree: whatever
+    the hard-wired YOLOv8-seg reader refuses (a detection-only `yolo_1`-family file) still runs from its module tree."""
+    s = T._Synth(5, "s", 2)
+    ch = s.ch
+    layers = []
+
+    def add(node, f=-1):
+        node = dict(node)
+        node["f"] = f
+        layers.append(node)
+        return len(layers) - 1
+    add(s.conv(3, ch(64), 3, 2))
+    add(s.conv(ch(64), ch(128), 3, 2))
+    p3 = add(s.c3k2(ch(128), ch(256), 1, False, 0.5))                # C2f(c, c, n=1, shortcut=True)
+    add(s.conv(ch(256), ch(512), 3, 2))
+    p4 = add(s.c3k2(ch(512), ch(512), 2, False, 0.5))
+    add(s.conv(ch(512), ch(1024), 3, 2))
+    p5 = add(s.sppf(ch(1024), ch(1024)))
+    add(s.detect([ch(256), ch(512), ch(1024)], legacy=True), f=[p3, p4, p5])
+    tree = {"layers": layers, "names": {0: "a", 1: "b"}}
+    path, stash = _save_with_fake_package(tmp_path, tree, v8_names=True)
+    try:
+        got = W.load_ultralytics_tree(str(path))
+    finally:
+        sys.modules.update(stash)
+    _same(tree["layers"], got["layers"])
+    assert [len(b) for b in got["layers"][-1]["cv3"]] == [3, 3, 3]
