@@ -2,7 +2,7 @@
 checkpoint (neither exists in the build container, which is why oracle/yolo_oracle.py and oracle/yolo_tree_oracle.py say
 "parity unpinned").
 
-    python tools/pin_ultralytics.py path/to/model.pt [image.jpg] [--imgsz 640] [--conf 0.25] [--cpu-only]
+    python tests/tools/pin_ultralytics.py path/to/model.pt [image.jpg] [--imgsz 640] [--conf 0.25] [--cpu-only]
 
 What it does: runs `ultralytics.YOLO(path)` (the reference's call, core/ml/model_manager.py:740,804,830) and (a) the CPU
 oracle on the module tree read from the same file by `weights.load_ultralytics_tree` (no GPU needed), (b) unless
@@ -14,7 +14,7 @@ import argparse
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 

@@ -1,6 +1,6 @@
 """GPU debug: per-layer error of the module-tree detector against its CPU oracle (where does the head error come from?)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 os.environ.setdefault("MTB200_SYNTHETIC_WEIGHTS", "1")
 import numpy as np, torch, torch.nn.functional as F
